@@ -1,0 +1,237 @@
+"""ctypes front-end of the CPU oracle (oracle/libexo_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import robot_model
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
+ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
+MAP_KINDS = {"EffFrame": 0, "EffPosition": 1, "JointLimit": 2, "SphereCollision": 3}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libexo_oracle.so")
+    src = os.path.join(_HERE, "exo_oracle.c")
+    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libexo_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        L.exo_oracle_create.restype = ctypes.c_void_p
+        L.exo_oracle_create.argtypes = [ctypes.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip, _ip, _dp, _dp, _ip, ctypes.c_int]
+        L.exo_oracle_destroy.argtypes = [ctypes.c_void_p]
+        L.exo_oracle_set_tree_state.argtypes = [ctypes.c_void_p, _dp]
+        L.exo_oracle_set_limits.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.exo_oracle_set_generated.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp]
+        L.exo_oracle_request_frames.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _dp, _ip, _dp]
+        L.exo_oracle_update.argtypes = [ctypes.c_void_p, _dp]
+        L.exo_oracle_get_phi.argtypes = [ctypes.c_void_p, _dp]
+        L.exo_oracle_get_jacobian.argtypes = [ctypes.c_void_p, _dp]
+        L.exo_oracle_get_element_frame.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp]
+        L.exo_oracle_set_rotation.argtypes = [_dp, ctypes.c_int, _dp]
+        L.exo_oracle_get_frame.argtypes = [_dp, ctypes.c_int, _dp]
+        L.exo_oracle_problem_clear.argtypes = [ctypes.c_void_p]
+        L.exo_oracle_problem_add_map.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_double, _ip, _dp, ctypes.c_int]
+        L.exo_oracle_problem_length_phi.argtypes = [ctypes.c_void_p]
+        L.exo_oracle_problem_length_jacobian.argtypes = [ctypes.c_void_p]
+        L.exo_oracle_problem_update.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
+        L.exo_oracle_problem_update_batch.argtypes = [ctypes.c_void_p, _dp, ctypes.c_long, ctypes.c_int, _dp, ctypes.c_int,
+                                                      _dp, _dp, ctypes.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def get_frame(v):
+    """exotica::GetFrame(vector) -> 12 doubles (row-major R, p)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros(12)
+    if lib().exo_oracle_get_frame(_d(v), int(v.size), _d(out)) != 0:
+        raise ValueError("invalid frame vector of length %d" % v.size)
+    return out
+
+
+def set_rotation(rot9, rot_type):
+    rot9 = np.ascontiguousarray(rot9, dtype=np.float64)
+    out = np.zeros(9)
+    n = lib().exo_oracle_set_rotation(_d(rot9), ROTATION_TYPES[rot_type] if isinstance(rot_type, str) else rot_type, _d(out))
+    return out[:n]
+
+
+IDENTITY_FRAME = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+
+
+class Oracle(object):
+    """KinematicTree + task maps + problem Update of the reference, one configuration at a time."""
+
+    def __init__(self, tree):
+        self.tree = tree
+        f = tree.flat()
+        self._keep = f
+        self.n = tree.n_controlled
+        self.h = lib().exo_oracle_create(len(tree.elements), _i(f["id"]), _i(f["parent"]), _i(f["joint_type"]),
+                                         _d(f["origin"]), _d(f["axis"]), _d(f["f_tip"]), _i(f["control_id"]),
+                                         _i(f["mimic_elem"]), _d(f["mimic_mult"]), _d(f["mimic_off"]), _i(f["generated"]),
+                                         self.n)
+        self.set_limits(tree.lower, tree.upper)
+        lib().exo_oracle_set_tree_state(self.h, _d(np.ascontiguousarray(tree.tree_state, dtype=np.float64)))
+        self.n_frames = 0
+        self.maps = []
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().exo_oracle_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_limits(self, lower, upper):
+        self.lower = np.ascontiguousarray(lower, dtype=np.float64).copy()
+        self.upper = np.ascontiguousarray(upper, dtype=np.float64).copy()
+        lib().exo_oracle_set_limits(self.h, _d(self.lower), _d(self.upper))
+
+    def set_generated(self, slot, frame12):
+        lib().exo_oracle_set_generated(self.h, slot, _d(np.ascontiguousarray(frame12, dtype=np.float64)))
+
+    def resolve_frames(self, frames):
+        """frames: list of dicts with the reference's Frame initializer fields
+        (exotica_core/init/frame.in: Link, LinkOffset, Base, BaseOffset)."""
+        ea, eb, oa, ob = [], [], [], []
+        for fr in frames:
+            link, base = fr.get("Link", ""), fr.get("Base", "")
+            for name, what in ((link, "frame_A"), (base, "frame_B")):
+                if name and name not in self.tree.link_index:
+                    raise KeyError("No %s link exists named '%s'" % (what, name))
+            ea.append(self.tree.link_index[link] if link else 0)
+            eb.append(self.tree.link_index[base] if base else 0)
+            oa.append(get_frame(fr["LinkOffset"]) if "LinkOffset" in fr and fr["LinkOffset"] is not None else IDENTITY_FRAME)
+            ob.append(get_frame(fr["BaseOffset"]) if "BaseOffset" in fr and fr["BaseOffset"] is not None else IDENTITY_FRAME)
+        return (np.array(ea, dtype=np.int32), np.array(oa, dtype=np.float64).reshape(-1, 12),
+                np.array(eb, dtype=np.int32), np.array(ob, dtype=np.float64).reshape(-1, 12))
+
+    def request_frames(self, frames):
+        ea, oa, eb, ob = self.resolve_frames(frames)
+        self.n_frames = len(frames)
+        self.frame_request = (ea, oa, eb, ob)
+        if lib().exo_oracle_request_frames(self.h, self.n_frames, _i(ea), _d(oa), _i(eb), _d(ob)) != 0:
+            raise ValueError("bad frame request")
+
+    def update(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != self.n:
+            raise ValueError("Wrong state vector size! Got %d expected %d" % (x.size, self.n))
+        lib().exo_oracle_update(self.h, _d(x))
+
+    def phi(self):
+        out = np.zeros((self.n_frames, 12))
+        lib().exo_oracle_get_phi(self.h, _d(out))
+        return out
+
+    def jacobian(self):
+        """[F][6][N] (the per-frame KDL::Jacobian, rows vx vy vz wx wy wz)."""
+        out = np.zeros((self.n_frames, self.n, 6))
+        lib().exo_oracle_get_jacobian(self.h, _d(out))
+        return np.ascontiguousarray(out.transpose(0, 2, 1))
+
+    def element_frame(self, elem):
+        out = np.zeros(12)
+        lib().exo_oracle_get_element_frame(self.h, elem, _d(out))
+        return out
+
+    # ---- problem level ----------------------------------------------------------------------
+    def set_problem(self, maps):
+        """maps: list of dicts {"type": "EffFrame"|"EffPosition"|"JointLimit"|"SphereCollision",
+        "EndEffector": [frame dicts (+ Radius, Group for spheres)], "Type": rotation type,
+        "SafePercentage": .., "Precision": .., "used": bool}.  Mirrors PlanningProblem::InstantiateBase
+        (planning_problem.cpp:206-238): frames of all maps are concatenated in map order."""
+        frames = []
+        specs = []
+        for m in maps:
+            fr = list(m.get("EndEffector", []))
+            specs.append((m, len(frames), len(fr)))
+            frames.extend(fr)
+        self.request_frames(frames)
+        lib().exo_oracle_problem_clear(self.h)
+        self.maps = []
+        for m, start, n in specs:
+            kind = MAP_KINDS[m["type"]]
+            rot = ROTATION_TYPES[m.get("Type", "RPY")]
+            param = 0.0
+            grp = rad = None
+            if kind == 2:
+                param = float(m.get("SafePercentage", 0.0))
+            if kind == 3:
+                param = float(m["Precision"])
+                names = sorted(set(f.get("Group", "default") for f in m["EndEffector"]))  # std::map order
+                grp = np.array([names.index(f.get("Group", "default")) for f in m["EndEffector"]], dtype=np.int32)
+                rad = np.array([float(f["Radius"]) for f in m["EndEffector"]], dtype=np.float64)
+            r = lib().exo_oracle_problem_add_map(self.h, kind, start, n, rot, param,
+                                                 _i(grp) if grp is not None else None, _d(rad) if rad is not None else None,
+                                                 1 if m.get("used", True) else 0)
+            if r < 0:
+                raise ValueError("bad task map %r" % (m,))
+            self.maps.append(m)
+        self.length_phi = lib().exo_oracle_problem_length_phi(self.h)
+        self.length_jacobian = lib().exo_oracle_problem_length_jacobian(self.h)
+
+    def problem_update(self, x):
+        """Returns (Phi[length_Phi], J[length_jacobian][N])."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        phi = np.zeros(self.length_phi)
+        jac = np.zeros((self.n, self.length_jacobian))
+        lib().exo_oracle_problem_update(self.h, _d(x), _d(phi), _d(jac))
+        return phi, np.ascontiguousarray(jac.T)
+
+    def problem_update_batch(self, X, T=1, generated=None, n_threads=1, discard=False):
+        """X[E][N] -> Phi[E][length_Phi], J[E][length_jacobian][N] (row-major per evaluation)."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.n)
+        E = X.shape[0]
+        n_gen = 0
+        gp = None
+        if generated is not None:
+            generated = np.ascontiguousarray(generated, dtype=np.float64).reshape(T, -1, 12)
+            n_gen = generated.shape[1]
+            gp = _d(generated)
+        if discard:
+            lib().exo_oracle_problem_update_batch(self.h, _d(X), E, T, gp, n_gen, None, None, n_threads)
+            return None, None
+        phi = np.zeros((E, self.length_phi))
+        jac = np.zeros((E, self.n, self.length_jacobian))
+        lib().exo_oracle_problem_update_batch(self.h, _d(X), E, T, gp, n_gen, _d(phi), _d(jac), n_threads)
+        return phi, np.ascontiguousarray(jac.transpose(0, 2, 1))
+
+
+def load_robot(urdf_path, srdf_path, joint_group="", add_collision_elements=False):
+    with open(urdf_path) as f:
+        urdf = f.read()
+    with open(srdf_path) as f:
+        srdf = f.read()
+    return robot_model.RobotTree(urdf, srdf, joint_group, add_collision_elements)
