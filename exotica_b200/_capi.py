@@ -1,0 +1,330 @@
+"""ctypes binding of the C-ABI (include/exotica_b200.h).  Pure forwarding: no torch, no CPU fallback.
+
+Loading fails loudly if exotica_b200/lib/libexotica_b200.so is missing (build it with
+`make -C exotica_b200/csrc` or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libexotica_b200.so")
+
+EXO_OK = 0
+LAYOUT_SOA, LAYOUT_AOS_ROWMAJOR, LAYOUT_AOS_COLMAJOR = 0, 1, 2
+MAP_EFF_FRAME, MAP_EFF_POSITION, MAP_JOINT_LIMIT, MAP_SPHERE_COLLISION, MAP_FRAMES = 0, 1, 2, 3, 4
+ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
+ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_vp = ctypes.c_void_p
+
+
+class TreeDesc(ctypes.Structure):
+    _fields_ = [("n_elements", ctypes.c_int32), ("id", _ip), ("parent", _ip), ("joint_type", _ip), ("joint_origin", _dp),
+                ("joint_axis", _dp), ("f_tip", _dp), ("control_id", _ip), ("mimic_element", _ip), ("mimic_multiplier", _dp),
+                ("mimic_offset", _dp), ("generated_slot", _ip), ("n_controlled", ctypes.c_int32), ("lower", _dp), ("upper", _dp)]
+
+
+class TaskMapDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("n_frames", ctypes.c_int32), ("elem_a", _ip), ("off_a", _dp), ("elem_b", _ip),
+                ("off_b", _dp), ("rotation_type", ctypes.c_int32), ("safe_percentage", ctypes.c_double),
+                ("precision", ctypes.c_double), ("radius", _dp), ("group", _ip), ("is_used", ctypes.c_int32)]
+
+
+class ExoticaError(RuntimeError):
+    """Mirrors exotica::Exception (exotica_core/include/exotica_core/tools/exception.h:36-47)."""
+
+
+# every symbol include/exotica_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("exo_last_error", ctypes.c_char_p, []),
+    ("exo_device_count", ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    ("exo_set_device", ctypes.c_int, [ctypes.c_int]),
+    ("exo_version", ctypes.c_char_p, []),
+    ("exo_device_alloc", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
+    ("exo_device_free", ctypes.c_int, [_vp]),
+    ("exo_host_alloc_pinned", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
+    ("exo_host_free_pinned", ctypes.c_int, [_vp]),
+    ("exo_memcpy_h2d", ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    ("exo_memcpy_d2h", ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    ("exo_memset_device", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_size_t, _vp]),
+    ("exo_stream_create", ctypes.c_int, [ctypes.POINTER(_vp)]),
+    ("exo_stream_destroy", ctypes.c_int, [_vp]),
+    ("exo_stream_synchronize", ctypes.c_int, [_vp]),
+    ("exo_device_synchronize", ctypes.c_int, []),
+    ("exo_tree_create", ctypes.c_int, [ctypes.POINTER(TreeDesc), ctypes.POINTER(_vp)]),
+    ("exo_tree_destroy", ctypes.c_int, [_vp]),
+    ("exo_tree_set_model_state", ctypes.c_int, [_vp, _dp]),
+    ("exo_tree_set_joint_limits", ctypes.c_int, [_vp, _dp, _dp]),
+    ("exo_tree_num_controlled", ctypes.c_int, [_vp]),
+    ("exo_problem_create", ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    ("exo_problem_destroy", ctypes.c_int, [_vp]),
+    ("exo_problem_add_task_map", ctypes.c_int, [_vp, ctypes.POINTER(TaskMapDesc)]),
+    ("exo_problem_finalize", ctypes.c_int, [_vp]),
+    ("exo_problem_length_phi", ctypes.c_int, [_vp]),
+    ("exo_problem_length_jacobian", ctypes.c_int, [_vp]),
+    ("exo_problem_num_maps", ctypes.c_int, [_vp]),
+    ("exo_problem_map_indexing", ctypes.c_int, [_vp, ctypes.c_int, _ip]),
+    ("exo_problem_set_generated", ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_int32, _dp]),
+    ("exo_problem_update_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
+    ("exo_problem_update_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
+    ("exo_problem_launch_count", ctypes.c_int64, [_vp]),
+    ("exo_problem_last_kernel_ms", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    ("exo_problem_program_info", ctypes.c_int, [_vp, _ip]),
+]
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ExoticaError("CUDA extension missing: %s (run `make -C exotica_b200/csrc`); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != EXO_OK:
+        raise ExoticaError(lib().exo_last_error().decode("utf-8", "replace"))
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    rc = lib().exo_device_count(ctypes.byref(n))
+    return n.value if rc == EXO_OK else 0
+
+
+class DeviceBuffer(object):
+    """Raw device allocation of doubles."""
+
+    def __init__(self, n_doubles):
+        self.n = int(n_doubles)
+        p = _vp()
+        check(lib().exo_device_alloc(ctypes.byref(p), self.n * 8))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.size <= self.n
+        check(lib().exo_memcpy_h2d(self.ptr, arr.ctypes.data, arr.size * 8, None))
+        check(lib().exo_stream_synchronize(None))
+
+    def download(self, shape):
+        out = np.empty(shape, dtype=np.float64)
+        assert out.size <= self.n
+        check(lib().exo_memcpy_d2h(out.ctypes.data, self.ptr, out.size * 8, None))
+        check(lib().exo_stream_synchronize(None))
+        return out
+
+    def fill_bytes(self, value):
+        check(lib().exo_memset_device(self.ptr, value, self.n * 8, None))
+
+    def free(self):
+        if self.ptr:
+            lib().exo_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray(object):
+    """numpy view over page-locked host memory (for overlapped copies in update_batch_host)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        n = int(np.prod(self.shape))
+        p = _vp()
+        check(lib().exo_host_alloc_pinned(ctypes.byref(p), max(n, 1) * 8))
+        self.ptr = p.value
+        buf = (ctypes.c_double * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().exo_host_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Tree(object):
+    """exo_tree handle built from flat arrays (see exo_tree_desc)."""
+
+    def __init__(self, flat, n_controlled, lower, upper, tree_state=None):
+        self._keep = {k: np.ascontiguousarray(v) for k, v in flat.items()}
+        f = self._keep
+        self.lower = np.ascontiguousarray(lower, dtype=np.float64)
+        self.upper = np.ascontiguousarray(upper, dtype=np.float64)
+        d = TreeDesc()
+        d.n_elements = len(f["id"])
+        d.id = _i(f["id"])
+        d.parent = _i(f["parent"])
+        d.joint_type = _i(f["joint_type"])
+        d.joint_origin = _d(f["origin"])
+        d.joint_axis = _d(f["axis"])
+        d.f_tip = _d(f["f_tip"])
+        d.control_id = _i(f["control_id"])
+        d.mimic_element = _i(f["mimic_elem"])
+        d.mimic_multiplier = _d(f["mimic_mult"])
+        d.mimic_offset = _d(f["mimic_off"])
+        d.generated_slot = _i(f["generated"])
+        d.n_controlled = int(n_controlled)
+        d.lower = _d(self.lower)
+        d.upper = _d(self.upper)
+        h = _vp()
+        check(lib().exo_tree_create(ctypes.byref(d), ctypes.byref(h)))
+        self.h = h.value
+        self.n = int(n_controlled)
+        self.n_elements = d.n_elements
+        if tree_state is not None:
+            self.set_model_state(tree_state)
+
+    def set_model_state(self, tree_state):
+        s = np.ascontiguousarray(tree_state, dtype=np.float64)
+        if s.size != self.n_elements:
+            raise ExoticaError("tree state has %d entries, expected %d" % (s.size, self.n_elements))
+        check(lib().exo_tree_set_model_state(self.h, _d(s)))
+
+    def set_joint_limits(self, lower, upper):
+        self.lower = np.ascontiguousarray(lower, dtype=np.float64)
+        self.upper = np.ascontiguousarray(upper, dtype=np.float64)
+        check(lib().exo_tree_set_joint_limits(self.h, _d(self.lower), _d(self.upper)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().exo_tree_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Problem(object):
+    """exo_problem handle: ordered task maps over one tree."""
+
+    def __init__(self, tree):
+        self.tree = tree
+        h = _vp()
+        check(lib().exo_problem_create(tree.h, ctypes.byref(h)))
+        self.h = h.value
+        self.finalized = False
+
+    def add_task_map(self, kind, elem_a=None, off_a=None, elem_b=None, off_b=None, rotation_type=1, safe_percentage=0.0,
+                     precision=1.0, radius=None, group=None, is_used=True):
+        d = TaskMapDesc()
+        d.kind = kind
+        n = 0 if elem_a is None else len(elem_a)
+        d.n_frames = n
+        keep = []
+        if n:
+            ea = np.ascontiguousarray(elem_a, dtype=np.int32)
+            eb = np.ascontiguousarray(elem_b if elem_b is not None else np.zeros(n), dtype=np.int32)
+            ident = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64), (n, 1))
+            oa = np.ascontiguousarray(off_a if off_a is not None else ident, dtype=np.float64).reshape(n, 12)
+            ob = np.ascontiguousarray(off_b if off_b is not None else ident, dtype=np.float64).reshape(n, 12)
+            keep += [ea, eb, oa, ob]
+            d.elem_a, d.elem_b, d.off_a, d.off_b = _i(ea), _i(eb), _d(oa), _d(ob)
+        d.rotation_type = int(rotation_type)
+        d.safe_percentage = float(safe_percentage)
+        d.precision = float(precision)
+        if radius is not None:
+            r = np.ascontiguousarray(radius, dtype=np.float64)
+            g = np.ascontiguousarray(group, dtype=np.int32)
+            keep += [r, g]
+            d.radius, d.group = _d(r), _i(g)
+        d.is_used = 1 if is_used else 0
+        check(lib().exo_problem_add_task_map(self.h, ctypes.byref(d)))
+
+    def finalize(self):
+        check(lib().exo_problem_finalize(self.h))
+        self.finalized = True
+        self.length_phi = lib().exo_problem_length_phi(self.h)
+        self.length_jacobian = lib().exo_problem_length_jacobian(self.h)
+        self.n = self.tree.n
+
+    def map_indexing(self, i):
+        out = np.zeros(4, dtype=np.int32)
+        check(lib().exo_problem_map_indexing(self.h, i, _i(out)))
+        return tuple(int(v) for v in out)
+
+    def program_info(self):
+        out = np.zeros(8, dtype=np.int32)
+        check(lib().exo_problem_program_info(self.h, _i(out)))
+        keys = ["joint_ops", "emit_ops", "frame_slots", "joint_slots", "scratch_bytes_per_thread", "image_bytes", "accumulators", "ops"]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def set_generated(self, frames):
+        frames = np.ascontiguousarray(frames, dtype=np.float64)
+        T, n_gen = frames.shape[0], frames.shape[1]
+        check(lib().exo_problem_set_generated(self.h, T, n_gen, _d(frames)))
+
+    def update_batch_device(self, d_x, n_evals, d_phi, d_jac, T=1, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_update_batch(self.h, d_x, int(n_evals), int(T), int(layout), d_phi, d_jac, stream))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float(0)
+        check(lib().exo_problem_last_kernel_ms(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(lib().exo_problem_launch_count(self.h))
+
+    def update_batch_host(self, X, T=1, layout=LAYOUT_AOS_ROWMAJOR, want_jacobian=True, out_phi=None, out_jac=None):
+        """Host arrays in, host arrays out (chunked copy/compute pipeline inside the library).
+        AoS layouts: X[E][N] -> Phi[E][LP], J[E][LJ][N] (row-major) or J[E][N][LJ] (col-major).
+        SoA: X[N][E] -> Phi[LP][E], J[LJ][N][E]."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        N, LP, LJ = self.n, self.length_phi, self.length_jacobian
+        if layout == LAYOUT_SOA:
+            if X.ndim != 2 or X.shape[0] != N:
+                raise ExoticaError("Wrong state vector size! Got %s expected (%d, E)" % (X.shape, N))
+            E = X.shape[1]
+            pshape, jshape = (LP, E), (LJ, N, E)
+        else:
+            if X.ndim != 2 or X.shape[1] != N:
+                raise ExoticaError("Wrong state vector size! Got %s expected (E, %d)" % (X.shape, N))
+            E = X.shape[0]
+            pshape = (E, LP)
+            jshape = (E, LJ, N) if layout == LAYOUT_AOS_ROWMAJOR else (E, N, LJ)
+        phi = out_phi if out_phi is not None else np.empty(pshape, dtype=np.float64)
+        jac = None
+        if want_jacobian:
+            jac = out_jac if out_jac is not None else np.empty(jshape, dtype=np.float64)
+        check(lib().exo_problem_update_batch_host(self.h, X.ctypes.data, E, int(T), int(layout), phi.ctypes.data,
+                                                  jac.ctypes.data if jac is not None else None))
+        return phi, jac
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().exo_problem_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

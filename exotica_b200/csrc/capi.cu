@@ -1,0 +1,609 @@
+// capi.cu -- implementation of the C-ABI declared in include/exotica_b200.h.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/exotica_b200.h"
+#include "compiler.h"
+#include "kernels.cuh"
+
+using namespace exo;
+
+namespace
+{
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return EXO_ERR_CUDA;
+}
+
+#define CUDA_TRY(expr)                                        \
+    do                                                        \
+    {                                                         \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);   \
+    } while (0)
+}  // namespace
+
+struct exo_tree
+{
+    TreeModel model;
+    int64_t version = 0;  // bumped when model state / limits change, so problems recompile
+};
+
+struct exo_problem
+{
+    exo_tree* tree = nullptr;
+    std::vector<MapSpec> maps;
+    bool finalized = false;
+    int64_t compiled_version = -1;
+    Program prog;
+    unsigned char* d_image = nullptr;
+    size_t d_image_bytes = 0;
+    // per-timestep generated frames
+    int T = 1, n_generated = 0;
+    std::vector<double> h_generated;
+    double* d_generated = nullptr;
+    // timing / accounting
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // host pipeline
+    static const int NBUF = 3;
+    cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
+    double* d_x[NBUF] = {nullptr, nullptr, nullptr};
+    double* d_phi[NBUF] = {nullptr, nullptr, nullptr};
+    double* d_jac[NBUF] = {nullptr, nullptr, nullptr};
+    int64_t pipe_chunk = 0;
+    bool pipe_has_jac = false;
+};
+
+extern "C" {
+
+const char* exo_last_error(void)
+{
+    return g_error.c_str();
+}
+
+const char* exo_version(void)
+{
+    return "exotica_b200 0.1 (sm_100a)";
+}
+
+int exo_device_count(int* count)
+{
+    if (!count) return fail(EXO_ERR_INVALID, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess)
+    {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    return EXO_OK;
+}
+
+int exo_set_device(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    return EXO_OK;
+}
+
+int exo_device_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(EXO_ERR_INVALID, "ptr is NULL");
+    CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 8));
+    return EXO_OK;
+}
+
+int exo_device_free(void* ptr)
+{
+    CUDA_TRY(cudaFree(ptr));
+    return EXO_OK;
+}
+
+int exo_host_alloc_pinned(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(EXO_ERR_INVALID, "ptr is NULL");
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 8));
+    return EXO_OK;
+}
+
+int exo_host_free_pinned(void* ptr)
+{
+    CUDA_TRY(cudaFreeHost(ptr));
+    return EXO_OK;
+}
+
+int exo_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return EXO_OK;
+}
+
+int exo_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return EXO_OK;
+}
+
+int exo_memset_device(void* dst, int value, size_t bytes, void* stream)
+{
+    CUDA_TRY(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return EXO_OK;
+}
+
+int exo_stream_create(void** stream)
+{
+    if (!stream) return fail(EXO_ERR_INVALID, "stream is NULL");
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return EXO_OK;
+}
+
+int exo_stream_destroy(void* stream)
+{
+    CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return EXO_OK;
+}
+
+int exo_stream_synchronize(void* stream)
+{
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return EXO_OK;
+}
+
+int exo_device_synchronize(void)
+{
+    CUDA_TRY(cudaDeviceSynchronize());
+    return EXO_OK;
+}
+
+// ---- tree ---------------------------------------------------------------------------------------------
+int exo_tree_create(const exo_tree_desc* d, exo_tree** out)
+{
+    if (!d || !out) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (d->n_elements < 1 || !d->id || !d->parent || !d->joint_type || !d->joint_origin || !d->joint_axis || !d->f_tip || !d->control_id)
+        return fail(EXO_ERR_INVALID, "incomplete tree description");
+    if (d->n_controlled < 1) return fail(EXO_ERR_INVALID, "No update joints specified!");
+    exo_tree* t = new exo_tree();
+    TreeModel& m = t->model;
+    const int n = d->n_elements;
+    m.n = n;
+    m.n_ctrl = d->n_controlled;
+    m.id.assign(d->id, d->id + n);
+    m.parent.assign(d->parent, d->parent + n);
+    m.joint_type.assign(d->joint_type, d->joint_type + n);
+    m.control_id.assign(d->control_id, d->control_id + n);
+    m.origin.assign(d->joint_origin, d->joint_origin + 3 * (size_t)n);
+    m.axis.assign(d->joint_axis, d->joint_axis + 3 * (size_t)n);
+    m.tip.assign(d->f_tip, d->f_tip + 12 * (size_t)n);
+    m.mimic_elem.assign(n, -1);
+    m.mimic_mult.assign(n, 1.0);
+    m.mimic_off.assign(n, 0.0);
+    m.generated.assign(n, -1);
+    if (d->mimic_element) m.mimic_elem.assign(d->mimic_element, d->mimic_element + n);
+    if (d->mimic_multiplier) m.mimic_mult.assign(d->mimic_multiplier, d->mimic_multiplier + n);
+    if (d->mimic_offset) m.mimic_off.assign(d->mimic_offset, d->mimic_offset + n);
+    if (d->generated_slot) m.generated.assign(d->generated_slot, d->generated_slot + n);
+    m.n_generated = 0;
+    for (int e = 0; e < n; ++e) m.n_generated = std::max(m.n_generated, m.generated[e] + 1);
+    m.tree_state.assign(n, 0.0);
+    m.lower.assign(m.n_ctrl, -1e20);
+    m.upper.assign(m.n_ctrl, 1e20);
+    if (d->lower) m.lower.assign(d->lower, d->lower + m.n_ctrl);
+    if (d->upper) m.upper.assign(d->upper, d->upper + m.n_ctrl);
+    std::vector<char> seen(m.n_ctrl, 0);
+    for (int e = 0; e < n; ++e)
+    {
+        if (m.joint_type[e] < 0 || m.joint_type[e] > EXO_JOINT_NONE)
+        {
+            delete t;
+            return fail(EXO_ERR_INVALID, "unknown joint type");
+        }
+        if (m.parent[e] >= e || (e > 0 && m.parent[e] < 0) || (e == 0 && m.parent[e] != -1))
+        {
+            delete t;
+            return fail(EXO_ERR_INVALID, "tree elements must be ordered parents-first with the root at index 0");
+        }
+        if (m.control_id[e] >= m.n_ctrl)
+        {
+            delete t;
+            return fail(EXO_ERR_INVALID, "control_id out of range");
+        }
+        if (m.control_id[e] >= 0) seen[m.control_id[e]] = 1;
+    }
+    for (int c = 0; c < m.n_ctrl; ++c)
+        if (!seen[c])
+        {
+            delete t;
+            return fail(EXO_ERR_INVALID, "controlled joint " + std::to_string(c) + " has no element");
+        }
+    *out = t;
+    return EXO_OK;
+}
+
+int exo_tree_destroy(exo_tree* tree)
+{
+    delete tree;
+    return EXO_OK;
+}
+
+int exo_tree_set_model_state(exo_tree* tree, const double* s)
+{
+    if (!tree || !s) return fail(EXO_ERR_INVALID, "NULL argument");
+    tree->model.tree_state.assign(s, s + tree->model.n);
+    tree->version++;
+    return EXO_OK;
+}
+
+int exo_tree_set_joint_limits(exo_tree* tree, const double* lower, const double* upper)
+{
+    if (!tree || !lower || !upper) return fail(EXO_ERR_INVALID, "NULL argument");
+    tree->model.lower.assign(lower, lower + tree->model.n_ctrl);
+    tree->model.upper.assign(upper, upper + tree->model.n_ctrl);
+    tree->version++;
+    return EXO_OK;
+}
+
+int exo_tree_num_controlled(const exo_tree* tree)
+{
+    return tree ? tree->model.n_ctrl : -1;
+}
+
+// ---- problem ------------------------------------------------------------------------------------------------
+int exo_problem_create(exo_tree* tree, exo_problem** out)
+{
+    if (!tree || !out) return fail(EXO_ERR_INVALID, "NULL argument");
+    exo_problem* p = new exo_problem();
+    p->tree = tree;
+    *out = p;
+    return EXO_OK;
+}
+
+static void free_pipeline(exo_problem* p)
+{
+    for (int i = 0; i < exo_problem::NBUF; ++i)
+    {
+        if (p->d_x[i]) cudaFree(p->d_x[i]);
+        if (p->d_phi[i]) cudaFree(p->d_phi[i]);
+        if (p->d_jac[i]) cudaFree(p->d_jac[i]);
+        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = nullptr;
+    }
+    p->pipe_chunk = 0;
+}
+
+int exo_problem_destroy(exo_problem* p)
+{
+    if (!p) return EXO_OK;
+    free_pipeline(p);
+    for (int i = 0; i < exo_problem::NBUF; ++i)
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+    if (p->d_image) cudaFree(p->d_image);
+    if (p->d_generated) cudaFree(p->d_generated);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+    return EXO_OK;
+}
+
+int exo_problem_add_task_map(exo_problem* p, const exo_task_map_desc* d)
+{
+    if (!p || !d) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (p->finalized) return fail(EXO_ERR_STATE, "problem already finalized");
+    if (d->kind < EXO_MAP_EFF_FRAME || d->kind > EXO_MAP_FRAMES) return fail(EXO_ERR_INVALID, "unknown task map kind");
+    if (d->n_frames < 0) return fail(EXO_ERR_INVALID, "negative frame count");
+    MapSpec m;
+    m.kind = d->kind;
+    m.n_frames = d->n_frames;
+    m.rot_type = d->rotation_type;
+    m.safe_percentage = d->safe_percentage;
+    m.precision = d->precision;
+    m.is_used = d->is_used != 0;
+    const int n = p->tree->model.n;
+    if (d->n_frames > 0)
+    {
+        if (!d->elem_a) return fail(EXO_ERR_INVALID, "elem_a is NULL");
+        m.elem_a.assign(d->elem_a, d->elem_a + d->n_frames);
+        m.elem_b.assign(d->n_frames, 0);
+        if (d->elem_b) m.elem_b.assign(d->elem_b, d->elem_b + d->n_frames);
+        static const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+        m.off_a.resize(12 * (size_t)d->n_frames);
+        m.off_b.resize(12 * (size_t)d->n_frames);
+        for (int f = 0; f < d->n_frames; ++f)
+        {
+            memcpy(&m.off_a[12 * f], d->off_a ? d->off_a + 12 * f : ident, sizeof(ident));
+            memcpy(&m.off_b[12 * f], d->off_b ? d->off_b + 12 * f : ident, sizeof(ident));
+            if (m.elem_a[f] < 0 || m.elem_a[f] >= n) return fail(EXO_ERR_INVALID, "No frame_A link exists with index " + std::to_string(m.elem_a[f]));
+            if (m.elem_b[f] < 0 || m.elem_b[f] >= n) return fail(EXO_ERR_INVALID, "No frame_B link exists with index " + std::to_string(m.elem_b[f]));
+        }
+    }
+    if (m.kind == EXO_MAP_EFF_FRAME && rotation_length(m.rot_type) < 0) return fail(EXO_ERR_INVALID, "Unknown rotation representation type!");
+    if (m.kind == EXO_MAP_SPHERE_COLLISION)
+    {
+        if (!d->radius || !d->group) return fail(EXO_ERR_INVALID, "SphereCollision needs radius[] and group[]");
+        if (!(d->precision != 0.0)) return fail(EXO_ERR_INVALID, "SphereCollision Precision must be non-zero");
+        m.radius.assign(d->radius, d->radius + d->n_frames);
+        m.group.assign(d->group, d->group + d->n_frames);
+        for (int g : m.group)
+            if (g < 0) return fail(EXO_ERR_INVALID, "negative sphere group");
+    }
+    p->maps.push_back(m);
+    return EXO_OK;
+}
+
+static int compile_and_upload(exo_problem* p)
+{
+    std::string err;
+    Program prog;
+    if (!compile_program(p->tree->model, p->maps, prog, err)) return fail(EXO_ERR_INVALID, err);
+    p->prog = prog;
+    if (p->d_image_bytes < p->prog.image.size())
+    {
+        if (p->d_image) cudaFree(p->d_image);
+        p->d_image = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&p->d_image, p->prog.image.size()));
+        p->d_image_bytes = p->prog.image.size();
+    }
+    CUDA_TRY(cudaMemcpy(p->d_image, p->prog.image.data(), p->prog.image.size(), cudaMemcpyHostToDevice));
+    p->compiled_version = p->tree->version;
+    return EXO_OK;
+}
+
+int exo_problem_finalize(exo_problem* p)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (p->finalized) return fail(EXO_ERR_STATE, "problem already finalized");
+    // host-only part first so that size queries work without a device
+    std::string err;
+    int lp = 0, lj = 0;
+    if (!assign_indexing(p->tree->model, p->maps, lp, lj, err)) return fail(EXO_ERR_INVALID, err);
+    Program prog;
+    if (!compile_program(p->tree->model, p->maps, prog, err)) return fail(EXO_ERR_INVALID, err);
+    p->prog = prog;
+    p->finalized = true;
+    p->compiled_version = -1;  // device upload happens lazily at the first update (needs a GPU)
+    return EXO_OK;
+}
+
+int exo_problem_length_phi(const exo_problem* p)
+{
+    return (p && p->finalized) ? p->prog.hdr.length_phi : -1;
+}
+
+int exo_problem_length_jacobian(const exo_problem* p)
+{
+    return (p && p->finalized) ? p->prog.hdr.length_jac : -1;
+}
+
+int exo_problem_num_maps(const exo_problem* p)
+{
+    return p ? (int)p->maps.size() : -1;
+}
+
+int exo_problem_map_indexing(const exo_problem* p, int map, int32_t out[4])
+{
+    if (!p || !out) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (map < 0 || map >= (int)p->maps.size()) return fail(EXO_ERR_INVALID, "map index out of range");
+    out[0] = p->maps[map].start;
+    out[1] = p->maps[map].length;
+    out[2] = p->maps[map].start_jacobian;
+    out[3] = p->maps[map].length_jacobian;
+    return EXO_OK;
+}
+
+int exo_problem_program_info(const exo_problem* p, int32_t out[8])
+{
+    if (!p || !out) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    out[0] = p->prog.n_joint_ops;
+    out[1] = p->prog.n_emit_ops;
+    out[2] = p->prog.hdr.n_frame_slots;
+    out[3] = p->prog.hdr.n_joint_slots;
+    out[4] = (int32_t)((p->prog.hdr.scratch_doubles + p->prog.hdr.n_ctrl) * sizeof(double));
+    out[5] = (int32_t)p->prog.image.size();
+    out[6] = p->prog.hdr.n_acc;
+    out[7] = p->prog.hdr.n_ops;
+    return EXO_OK;
+}
+
+int exo_problem_set_generated(exo_problem* p, int32_t T, int32_t n_generated, const double* frames)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (T < 1) return fail(EXO_ERR_INVALID, "T must be >= 1");
+    if (n_generated != p->tree->model.n_generated) return fail(EXO_ERR_INVALID, "n_generated does not match the tree's trajectory-driven elements");
+    if (n_generated > 0 && !frames) return fail(EXO_ERR_INVALID, "frames is NULL");
+    p->T = T;
+    p->n_generated = n_generated;
+    p->h_generated.assign(frames, frames + (size_t)T * n_generated * 12);
+    if (p->d_generated)
+    {
+        cudaFree(p->d_generated);
+        p->d_generated = nullptr;
+    }
+    if (n_generated > 0)
+    {
+        CUDA_TRY(cudaMalloc((void**)&p->d_generated, p->h_generated.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(p->d_generated, p->h_generated.data(), p->h_generated.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return EXO_OK;
+}
+
+static int fill_strides(const exo_problem* p, int layout, int64_t E, KernelParams& k)
+{
+    const int64_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
+    switch (layout)
+    {
+        case EXO_LAYOUT_SOA:
+            k.x_se = 1; k.x_sk = E;
+            k.phi_se = 1; k.phi_sk = E;
+            k.j_se = 1; k.j_sr = N * E; k.j_sc = E;
+            break;
+        case EXO_LAYOUT_AOS_ROWMAJOR:
+            k.x_se = N; k.x_sk = 1;
+            k.phi_se = LP; k.phi_sk = 1;
+            k.j_se = LJ * N; k.j_sr = N; k.j_sc = 1;
+            break;
+        case EXO_LAYOUT_AOS_COLMAJOR:
+            k.x_se = N; k.x_sk = 1;
+            k.phi_se = LP; k.phi_sk = 1;
+            k.j_se = LJ * N; k.j_sr = 1; k.j_sc = LJ;
+            break;
+        default:
+            return fail(EXO_ERR_INVALID, "unknown layout");
+    }
+    return EXO_OK;
+}
+
+static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E, int32_t T, int32_t layout, double* d_phi, double* d_jac,
+                  cudaStream_t stream, bool timed)
+{
+    if (p->compiled_version != p->tree->version)
+    {
+        int rc = compile_and_upload(p);
+        if (rc != EXO_OK) return rc;
+    }
+    if (p->prog.hdr.n_generated > 0)
+    {
+        if (!p->d_generated) return fail(EXO_ERR_STATE, "trajectory-driven elements need exo_problem_set_generated first");
+        if (T != p->T) return fail(EXO_ERR_INVALID, "T does not match exo_problem_set_generated");
+    }
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    k.program = p->d_image;
+    k.program_bytes = (int32_t)p->prog.image.size();
+    k.dbl_offset = p->prog.dbl_offset;
+    k.T = T < 1 ? 1 : T;
+    k.x = d_x;
+    k.phi = d_phi;
+    k.jac = d_jac;
+    k.generated = p->d_generated;
+    k.n_evals = E;
+    int rc = fill_strides(p, layout, stride_E, k);
+    if (rc != EXO_OK) return rc;
+    LaunchConfig cfg;
+    cudaError_t e = plan_launch(p->prog.hdr, k.program_bytes, E, cfg, k);
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(EXO_ERR_UNSUPPORTED, "compiled program needs more shared memory per thread than one CTA can hold");
+    if (e != cudaSuccess) return cuda_fail(e, "plan_launch");
+    if (timed)
+    {
+        if (!p->ev0)
+        {
+            CUDA_TRY(cudaEventCreate(&p->ev0));
+            CUDA_TRY(cudaEventCreate(&p->ev1));
+        }
+        CUDA_TRY(cudaEventRecord(p->ev0, stream));
+    }
+    e = launch_eval(cfg, k, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    if (timed)
+    {
+        CUDA_TRY(cudaEventRecord(p->ev1, stream));
+        p->timed = true;
+    }
+    p->launches++;
+    return EXO_OK;
+}
+
+int exo_problem_update_batch(exo_problem* p, const double* d_x, int64_t E, int32_t T, int32_t layout, double* d_phi, double* d_jac, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (E < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (E == 0) return EXO_OK;
+    if (!d_x || !d_phi) return fail(EXO_ERR_INVALID, "NULL buffer");
+    return launch(p, d_x, E, E, T, layout, d_phi, d_jac, (cudaStream_t)stream, true);
+}
+
+int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
+{
+    if (!p || !ms) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->timed) return fail(EXO_ERR_STATE, "no timed launch yet");
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return EXO_OK;
+}
+
+int64_t exo_problem_launch_count(const exo_problem* p)
+{
+    return p ? p->launches : -1;
+}
+
+static int ensure_pipeline(exo_problem* p, int64_t chunk, bool with_jac)
+{
+    if (p->pipe_chunk >= chunk && (p->pipe_has_jac || !with_jac)) return EXO_OK;
+    free_pipeline(p);
+    const size_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
+    for (int i = 0; i < exo_problem::NBUF; ++i)
+    {
+        if (!p->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc((void**)&p->d_x[i], std::max<size_t>(8, chunk * N * sizeof(double))));
+        CUDA_TRY(cudaMalloc((void**)&p->d_phi[i], std::max<size_t>(8, chunk * LP * sizeof(double))));
+        if (with_jac) CUDA_TRY(cudaMalloc((void**)&p->d_jac[i], std::max<size_t>(8, chunk * LJ * N * sizeof(double))));
+    }
+    p->pipe_chunk = chunk;
+    p->pipe_has_jac = with_jac;
+    return EXO_OK;
+}
+
+int exo_problem_update_batch_host(exo_problem* p, const double* h_x, int64_t E, int32_t T, int32_t layout, double* h_phi, double* h_jac)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (E < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (E == 0) return EXO_OK;
+    if (!h_x || !h_phi) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (layout < EXO_LAYOUT_SOA || layout > EXO_LAYOUT_AOS_COLMAJOR) return fail(EXO_ERR_INVALID, "unknown layout");
+    const int64_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
+    // chunk: ~32 MiB of output per buffer, multiple of T so that e % T stays aligned per chunk
+    const int64_t bytes_per_eval = (N + LP + (h_jac ? LJ * N : 0)) * (int64_t)sizeof(double);
+    int64_t chunk = std::max<int64_t>(1024, (32ll << 20) / std::max<int64_t>(bytes_per_eval, 1));
+    const int64_t Tm = T < 1 ? 1 : T;
+    chunk = ((chunk + Tm - 1) / Tm) * Tm;
+    if (chunk > E) chunk = E;
+    int rc = ensure_pipeline(p, chunk, h_jac != nullptr);
+    if (rc != EXO_OK) return rc;
+    int b = 0;
+    for (int64_t e0 = 0; e0 < E; e0 += chunk, b = (b + 1) % exo_problem::NBUF)
+    {
+        const int64_t n = std::min(chunk, E - e0);
+        cudaStream_t s = p->streams[b];
+        if (layout == EXO_LAYOUT_SOA)
+        {
+            // host arrays are [K][E]: copy the column block [K][e0:e0+n] into a dense [K][n] device array
+            CUDA_TRY(cudaMemcpy2DAsync(p->d_x[b], n * sizeof(double), h_x + e0, E * sizeof(double), n * sizeof(double), N, cudaMemcpyHostToDevice, s));
+        }
+        else
+            CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + e0 * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
+        rc = launch(p, p->d_x[b], n, n, T, layout, p->d_phi[b], h_jac ? p->d_jac[b] : nullptr, s, false);
+        if (rc != EXO_OK) return rc;
+        if (layout == EXO_LAYOUT_SOA)
+        {
+            CUDA_TRY(cudaMemcpy2DAsync(h_phi + e0, E * sizeof(double), p->d_phi[b], n * sizeof(double), n * sizeof(double), LP, cudaMemcpyDeviceToHost, s));
+            if (h_jac)
+                CUDA_TRY(cudaMemcpy2DAsync(h_jac + e0, E * sizeof(double), p->d_jac[b], n * sizeof(double), n * sizeof(double), LJ * N, cudaMemcpyDeviceToHost, s));
+        }
+        else
+        {
+            CUDA_TRY(cudaMemcpyAsync(h_phi + e0 * LP, p->d_phi[b], n * LP * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (h_jac) CUDA_TRY(cudaMemcpyAsync(h_jac + e0 * LJ * N, p->d_jac[b], n * LJ * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+    return EXO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+/*
+ * exotica_b200.h -- C-ABI of the B200-native batched-kinematics backend for EXOTica.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, caller-owned buffers,
+ * int status codes + a thread-local message (exo_last_error).  No torch / Eigen / KDL types.
+ * Handles are NOT thread-safe (same contract as the reference's stateful KinematicTree / Scene /
+ * PlanningProblem); use one handle per host thread and one per device.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to ipab-slmc/exotica
+ * v6.2.0).  INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - All arithmetic is IEEE FP64, indices are 32-bit, batch sizes 64-bit.
+ *   - A frame is 12 doubles: KDL::Rotation::data[9] (row-major) then KDL::Vector p[3].
+ *   - N  = number of controlled joints, E = number of evaluations in a batch.  For time-indexed
+ *     problems E = B*T with the timestep innermost: evaluation e is timestep t = e % T of
+ *     trajectory b = e / T.
+ *   - Layouts (exo_layout): how the E evaluations are laid out in X / Phi / J.
+ *       EXO_LAYOUT_SOA           X[N][E], Phi[length_Phi][E], J[length_jacobian][N][E]  (batch innermost;
+ *                                the kernels' native, fully coalesced layout)
+ *       EXO_LAYOUT_AOS_ROWMAJOR  X[E][N], Phi[E][length_Phi], J[E][length_jacobian][N]  (numpy-natural)
+ *       EXO_LAYOUT_AOS_COLMAJOR  X[E][N], Phi[E][length_Phi], J[E][N][length_jacobian]  (one Eigen::MatrixXd
+ *                                per evaluation, as problem->jacobian holds it)
+ */
+#ifndef EXOTICA_B200_H_
+#define EXOTICA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXO_OK 0
+#define EXO_ERR_INVALID 1   /* bad argument / size mismatch (the reference throws exotica::Exception) */
+#define EXO_ERR_CUDA 2      /* CUDA runtime failure, message in exo_last_error() */
+#define EXO_ERR_STATE 3     /* call order violated (e.g. update before finalize) */
+#define EXO_ERR_UNSUPPORTED 4
+
+/* KDL::Joint::JointType (external, orocos_kdl joint.hpp) */
+typedef enum
+{
+    EXO_JOINT_ROT_AXIS = 0,
+    EXO_JOINT_ROT_X = 1,
+    EXO_JOINT_ROT_Y = 2,
+    EXO_JOINT_ROT_Z = 3,
+    EXO_JOINT_TRANS_AXIS = 4,
+    EXO_JOINT_TRANS_X = 5,
+    EXO_JOINT_TRANS_Y = 6,
+    EXO_JOINT_TRANS_Z = 7,
+    EXO_JOINT_NONE = 8
+} exo_joint_type;
+
+/* exotica::RotationType, exotica_core/include/exotica_core/tools/conversions.h:80-88 */
+typedef enum
+{
+    EXO_ROT_QUATERNION = 0,
+    EXO_ROT_RPY = 1,
+    EXO_ROT_ZYX = 2,
+    EXO_ROT_ZYZ = 3,
+    EXO_ROT_ANGLE_AXIS = 4,
+    EXO_ROT_MATRIX = 5
+} exo_rotation_type;
+
+typedef enum
+{
+    EXO_LAYOUT_SOA = 0,
+    EXO_LAYOUT_AOS_ROWMAJOR = 1,
+    EXO_LAYOUT_AOS_COLMAJOR = 2
+} exo_layout;
+
+/* Task maps registered by the reference as "exotica/<Type>" (REGISTER_TASKMAP_TYPE,
+ * exotations/exotica_core_task_maps/src/{eff_frame,eff_position,joint_limit,sphere_collision}.cpp)
+ * plus EXO_MAP_FRAMES, the raw KinematicResponse (Phi frames + 6xN Jacobians) that
+ * KinematicTree::Update fills (exotica_core/src/kinematic_tree.cpp:678-693). */
+typedef enum
+{
+    EXO_MAP_EFF_FRAME = 0,
+    EXO_MAP_EFF_POSITION = 1,
+    EXO_MAP_JOINT_LIMIT = 2,
+    EXO_MAP_SPHERE_COLLISION = 3,
+    EXO_MAP_FRAMES = 4
+} exo_map_kind;
+
+typedef struct exo_tree exo_tree;       /* backend of exotica::KinematicTree (scene.h:195 kinematica_) */
+typedef struct exo_problem exo_problem; /* backend of a PlanningProblem's Update path */
+
+/* Flattened KinematicTree::tree_ (kinematic_element.h:54-143), index 0 = root element.
+ * Replaces the KDL::Segment each element holds: joint type/origin/axis and the tip frame f_tip
+ * (Segment::pose(q) = Joint::pose(q) * f_tip). */
+typedef struct
+{
+    int32_t n_elements;
+    const int32_t* id;             /* KinematicElement::id (root -1) */
+    const int32_t* parent;         /* parent element INDEX, -1 for the root */
+    const int32_t* joint_type;     /* exo_joint_type */
+    const double* joint_origin;    /* [n][3]  KDL::Joint origin */
+    const double* joint_axis;      /* [n][3]  unit axis, parent-link coordinates */
+    const double* f_tip;           /* [n][12] */
+    const int32_t* control_id;     /* KinematicElement::control_id, -1 if not controlled */
+    const int32_t* mimic_element;  /* element INDEX of the mimicked joint or -1 (may be NULL) */
+    const double* mimic_multiplier;/* may be NULL */
+    const double* mimic_offset;    /* may be NULL */
+    const int32_t* generated_slot; /* >=0: trajectory-driven element (is_trajectory_generated), index into the
+                                      per-timestep frame table; -1 otherwise (may be NULL) */
+    int32_t n_controlled;          /* KinematicTree::GetNumControlledJoints() */
+    const double* lower;           /* [N] KinematicTree::GetJointLimits() column 0 */
+    const double* upper;           /* [N] column 1 */
+} exo_tree_desc;
+
+/* One task map.  Frames follow exotica_core/init/frame.in after name resolution
+ * (KinematicTree::RequestFrames, kinematic_tree.cpp:628-676) and GetFrame() of the offsets. */
+typedef struct
+{
+    int32_t kind;            /* exo_map_kind */
+    int32_t n_frames;
+    const int32_t* elem_a;   /* [n_frames] element index of frame A (Link) */
+    const double* off_a;     /* [n_frames][12] LinkOffset */
+    const int32_t* elem_b;   /* [n_frames] element index of frame B (Base; 0 = root) */
+    const double* off_b;     /* [n_frames][12] BaseOffset */
+    int32_t rotation_type;   /* EffFrame Type (init/eff_frame.in) */
+    double safe_percentage;  /* JointLimit SafePercentage (init/joint_limit.in) */
+    double precision;        /* SphereCollision Precision (init/sphere_collision.in) */
+    const double* radius;    /* [n_frames] Sphere Radius (init/sphere.in) */
+    const int32_t* group;    /* [n_frames] rank of the sphere's Group name in lexicographic order (std::map order) */
+    int32_t is_used;         /* TaskMap::is_used (rho != 0 somewhere, tasks.cpp:246-259); unused maps only get the
+                                SetZero fill (task_space_vector.cpp:54-62) */
+} exo_task_map_desc;
+
+/* ---- errors / device ------------------------------------------------------------------------- */
+const char* exo_last_error(void);
+int exo_device_count(int* count);
+int exo_set_device(int device);
+const char* exo_version(void);
+
+/* ---- memory and streams (plumbing for callers that do not bring their own CUDA allocator) ------ */
+int exo_device_alloc(void** ptr, size_t bytes);
+int exo_device_free(void* ptr);
+int exo_host_alloc_pinned(void** ptr, size_t bytes);
+int exo_host_free_pinned(void* ptr);
+int exo_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int exo_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int exo_memset_device(void* dst, int value, size_t bytes, void* stream);
+int exo_stream_create(void** stream);
+int exo_stream_destroy(void* stream);
+int exo_stream_synchronize(void* stream); /* NULL = default stream */
+int exo_device_synchronize(void);
+
+/* ---- KinematicTree backend ----------------------------------------------------------------------
+ * exo_tree_create        <- end of KinematicTree::BuildTree / UpdateModel (kinematic_tree.cpp:164-421,423-432)
+ * exo_tree_set_model_state <- KinematicTree::SetModelState (tree_state_ of uncontrolled joints, :1035-1060)
+ * exo_tree_set_joint_limits <- KinematicTree::SetJointLimitsLower/Upper, ResetJointLimits (:1035-1297)
+ */
+int exo_tree_create(const exo_tree_desc* desc, exo_tree** out);
+int exo_tree_destroy(exo_tree* tree);
+int exo_tree_set_model_state(exo_tree* tree, const double* tree_state /* [n_elements] by element index */);
+int exo_tree_set_joint_limits(exo_tree* tree, const double* lower, const double* upper);
+int exo_tree_num_controlled(const exo_tree* tree);
+
+/* ---- Problem backend ------------------------------------------------------------------------------
+ * exo_problem_create / add_task_map / finalize <- PlanningProblem::InstantiateBase (planning_problem.cpp:148-244):
+ *     maps are appended in order; frames of all maps are concatenated into one KinematicsRequest; start /
+ *     length / start_jacobian / length_jacobian are assigned in map order.
+ * exo_problem_set_generated  <- Scene::UpdateTrajectoryGenerators (scene.cpp:329-335): generated_offset of every
+ *     trajectory-driven element for each of the T timesteps.
+ * exo_problem_update_batch   <- for each evaluation: AbstractTimeIndexedProblem::Update(x,t)
+ *     (abstract_time_indexed_problem.cpp:220-292) / UnconstrainedEndPoseProblem::Update (:123-167) up to and
+ *     including the task-map loop: Scene::Update, Phi.SetZero, jacobian.setZero, TaskMap::Update per used map.
+ */
+int exo_problem_create(exo_tree* tree, exo_problem** out);
+int exo_problem_destroy(exo_problem* problem);
+int exo_problem_add_task_map(exo_problem* problem, const exo_task_map_desc* map);
+int exo_problem_finalize(exo_problem* problem);
+int exo_problem_length_phi(const exo_problem* problem);
+int exo_problem_length_jacobian(const exo_problem* problem);
+int exo_problem_num_maps(const exo_problem* problem);
+/* start, length, start_jacobian, length_jacobian of map i (TaskMap::start..., task_map.h:79-84) */
+int exo_problem_map_indexing(const exo_problem* problem, int map, int32_t out[4]);
+/* T timesteps, n_generated frames per timestep: frames[T][n_generated][12] (host pointer, copied). */
+int exo_problem_set_generated(exo_problem* problem, int32_t T, int32_t n_generated, const double* frames);
+
+/* Device buffers (already resident in HBM).  d_jac may be NULL (KIN_FK only).  Asynchronous on `stream`. */
+int exo_problem_update_batch(exo_problem* problem, const double* d_x, int64_t n_evals, int32_t T, int32_t layout,
+                             double* d_phi, double* d_jac, void* stream);
+/* Host buffers: chunked H2D -> kernel -> D2H pipeline on internal streams; returns when the outputs are
+ * complete in host memory.  Fastest with pinned buffers (exo_host_alloc_pinned). */
+int exo_problem_update_batch_host(exo_problem* problem, const double* h_x, int64_t n_evals, int32_t T, int32_t layout,
+                                  double* h_phi, double* h_jac);
+/* Number of kernel launches issued so far by this handle (evidence for bench.py's gpu_launches). */
+int64_t exo_problem_launch_count(const exo_problem* problem);
+/* Device time of the most recent exo_problem_update_batch launch in milliseconds (CUDA events on the
+ * launching stream; blocks until that launch finished). */
+int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
+
+/* Introspection of the compiled program (tests / DESIGN.md): number of joint ops, emit ops, frame slots,
+ * joint slots, shared-memory bytes per thread. */
+int exo_problem_program_info(const exo_problem* problem, int32_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXOTICA_B200_H_ */

@@ -1,0 +1,300 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): |Phi_gpu - Phi_oracle| and |J_gpu - J_oracle| <= 1e-10 absolute, FP64.
+Euler-angle encodings are compared modulo 2 pi (the LWR base yaw sits on the atan2
+cut); the rotation-matrix encoding, which has no cuts, is checked without wrapping.
+"""
+import numpy as np
+import pytest
+
+from conftest import robot_paths
+from exotica_b200 import _capi
+from helpers import angle_entries, gpu_problem_from_maps, max_abs_err, random_states, run_gpu
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _oracle(oracle_lib, robot, group, **kw):
+    return oracle_lib.Oracle(oracle_lib.load_robot(*robot_paths(robot), joint_group=group, **kw))
+
+
+def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    if generated is not None:
+        prob.set_generated(generated)
+    assert prob.length_phi == orc.length_phi and prob.length_jacobian == orc.length_jacobian
+    phi_ref, jac_ref = orc.problem_update_batch(X, T=T, generated=generated)
+    phi, jac = run_gpu(prob, X, layout=layout, T=T)
+    wrap = angle_entries(maps, orc)
+    e_phi = max_abs_err(phi, phi_ref, wrap)
+    e_jac = max_abs_err(jac, jac_ref)
+    assert e_phi <= tol, "Phi error %g" % e_phi
+    assert e_jac <= tol, "J error %g" % e_jac
+    return prob, phi, jac
+
+
+@pytest.mark.parametrize("rot", ["RPY", "Quaternion", "ZYX", "ZYZ", "AngleAxis", "Matrix"])
+def test_lwr_eff_frame_all_rotation_types(oracle_lib, rot):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    X = random_states(orc, 4096, seed=1234)
+    _check(orc, [{"type": "EffFrame", "Type": rot, "EndEffector": [{"Link": "lwr_arm_7_link"}]}], X)
+
+
+@pytest.mark.parametrize("layout", [_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR, _capi.LAYOUT_AOS_COLMAJOR])
+def test_lwr_layouts(oracle_lib, layout):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    X = random_states(orc, 3001, seed=7)  # ragged: not a multiple of the CTA size
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "JointLimit", "SafePercentage": 0.1}]
+    _check(orc, maps, X, layout=layout)
+
+
+def test_lwr_example_ik_config(oracle_lib):
+    # cfg 1: example_ik.xml -- EffFrame(RPY) on lwr_arm_6_link with a quaternion LinkOffset
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_6_link",
+             "LinkOffset": [0, 0, 0, 0.7071067811865476, -4.3297802811774664e-17, 0.7071067811865475, 4.3297802811774664e-17]}]}]
+    X = np.vstack([np.zeros((1, 7)), random_states(orc, 1023, seed=3)])
+    prob, phi, jac = _check(orc, maps, X)
+    assert np.all(jac[:, :, 6] == 0.0)  # joint 6 moves link 7 only
+
+
+def test_lwr_eff_position_and_single_eval(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}, {"Link": "lwr_arm_3_link", "LinkOffset": [0.1, 0.2, 0.3]}]}]
+    _check(orc, maps, random_states(orc, 1, seed=11))
+    _check(orc, maps, random_states(orc, 2048, seed=12))
+
+
+def test_relative_frames_and_base_offsets(oracle_lib):
+    # frame B != root, with offsets on both sides: exercises the subtracting B-chain walk (kinematic_tree.cpp:934-944)
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [
+        {"Link": "lwr_arm_7_link", "LinkOffset": [0.05, 0, 0.1, 0.1, 0.2, 0.3], "Base": "lwr_arm_2_link", "BaseOffset": [0, 0.1, 0, 0.3, -0.2, 0.1]},
+        {"Link": "lwr_arm_1_link", "Base": "lwr_arm_5_link"},
+        {"Link": "lwr_arm_4_link", "Base": "", "BaseOffset": [0.3, 0.2, 0.1, 0, 0, 0.5]},
+        {"Link": "base", "Base": "lwr_arm_3_link"}]}]
+    _check(orc, maps, random_states(orc, 2048, seed=21))
+
+
+def test_raw_frames_map(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    frames = [{"Link": "lwr_arm_%d_link" % i} for i in (7, 5, 2)]
+    orc.request_frames(frames)
+    X = random_states(orc, 257, seed=5)
+    tree, prob = gpu_problem_from_maps(orc, [{"type": "Frames", "EndEffector": frames}])
+    phi, jac = run_gpu(prob, X)
+    for e in range(X.shape[0]):
+        orc.update(X[e])
+        assert max_abs_err(phi[e].reshape(3, 12), orc.phi()) <= TOL
+        assert max_abs_err(jac[e].reshape(3, 6, 7), orc.jacobian()) <= TOL
+
+
+def test_joint_limit_branches(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    X = random_states(orc, 4096, seed=31, spread=0.2)
+    X[0] = orc.lower  # exactly on the limit: phi 0, J 0 (App. C #3)
+    X[1] = orc.upper
+    for safe in (0.0, 0.2):
+        prob, phi, jac = _check(orc, [{"type": "JointLimit", "SafePercentage": safe}], X)
+    assert (np.abs(phi) > 0).any() and (phi == 0).any()
+
+
+def test_time_indexed_style_problem_with_unused_map(oracle_lib):
+    # cfg 3 shape: EffFrame + JointLimit per (b,t); plus an unused quaternion EffFrame that only gets the SetZero fill
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "EffFrame", "Type": "Quaternion", "used": False, "EndEffector": [{"Link": "lwr_arm_5_link"}]},
+            {"type": "JointLimit"}]
+    B, T = 16, 100
+    rng = np.random.default_rng(99)
+    q0 = random_states(orc, B, seed=98)
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+    prob, phi, jac = _check(orc, maps, X.reshape(B * T, 7), T=T)
+    assert np.all(phi[:, 6:13] == np.array([0, 0, 0, 0, 0, 0, 1.0]))  # unused map: identity quaternion (App. C #2)
+
+
+def test_three_dof_goldens_on_gpu(oracle_lib):
+    # the reference's own EffPosition golden inputs (test_maps.cpp:340-347), GPU vs oracle at 1e-10
+    orc = _oracle(oracle_lib, "test_robot", "arm")
+    X = np.array([0.680375, -0.211234, 0.566198, 0.59688, 0.823295, -0.604897, -0.329554, 0.536459, -0.444451, 0.10794,
+                  -0.0452059, 0.257742, -0.270431, 0.0268018, 0.904459]).reshape(5, 3)
+    prob, phi, jac = _check(orc, [{"type": "EffPosition", "EndEffector": [{"Link": "endeff"}]}], X)
+    assert abs(phi[0, 2] - 1.21417) < 1e-5
+
+
+def test_valkyrie_multi_end_effector(oracle_lib):
+    # cfg 4 shape: 38-DoF floating base, 4 end-effectors, branched tree
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [
+        {"Link": "leftFoot"}, {"Link": "rightFoot"}, {"Link": "leftPalm"}, {"Link": "rightPalm", "LinkOffset": [0, 0.05, 0.02]}]}]
+    X = random_states(orc, 1024, seed=41)
+    X[:, 3:6] = np.random.default_rng(42).uniform(-np.pi, np.pi, size=(1024, 3))
+    prob, phi, jac = _check(orc, maps, X)
+    info = prob.program_info()
+    assert info["joint_ops"] == 6 + 6 + 6 + 3 + 7 + 7  # neck is not needed by any frame
+    # relative frame across branches (hand w.r.t. the other hand), RPY away from gimbal lock
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "leftPalm", "Base": "rightPalm"}]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "head"}]}]
+    _check(orc, maps, X[:256])
+
+
+def test_gimbal_lock_set(oracle_lib):
+    # pitch within 1e-13 of +-pi/2 on the floating base: the |pitch| > pi/2 - 1e-12 branch of GetRPY must agree
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    X = np.zeros((64, 38))
+    rng = np.random.default_rng(5)
+    X[:, 3] = rng.uniform(-1, 1, 64)
+    X[:, 5] = rng.uniform(-1, 1, 64)
+    X[:32, 4] = np.pi / 2
+    X[32:, 4] = -np.pi / 2
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "pelvis"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    phi, jac = run_gpu(prob, X)
+    assert max_abs_err(jac, jac_ref) <= TOL
+    assert max_abs_err(phi[:, :3], phi_ref[:, :3]) <= TOL
+    # at the singularity roll/yaw are only defined as a sum; both sides take the same branch (roll == 0)
+    same_branch = (phi[:, 3] == 0) == (phi_ref[:, 3] == 0)
+    assert same_branch.all()
+    assert max_abs_err(phi[:, 3:6], phi_ref[:, 3:6], np.arange(3)) <= 1e-9
+
+
+def test_sphere_collision_goldens_and_fixture(oracle_lib):
+    orc = _oracle(oracle_lib, "test_robot", "arm")
+    X = np.array([-0.590167, 1.2309, 1.67611, -1.72098, 1.79731, 0.103981, -1.65578, -1.23114, 0.652908, 1.56093,
+                  -0.604428, -1.74331, -1.91991, -0.169193, -1.74762]).reshape(5, 3)
+    maps = [{"type": "SphereCollision", "Precision": 1e-2,
+             "EndEffector": [{"Link": "base", "Radius": 0.3, "Group": "base"}, {"Link": "endeff", "Radius": 0.3, "Group": "eff"}]}]
+    prob, phi, jac = _check(orc, maps, X)
+    assert abs(jac[0, 0, 1] - 0.431392) < 1e-5  # reference golden (test_maps.cpp:667)
+
+
+def _lwr_sphere_maps():
+    robot = [("lwr_arm_7_link", None), ("lwr_arm_6_link", None)]
+    for k in (5, 4, 3, 2, 1):
+        robot += [("lwr_arm_%d_link" % k, [0, 0, 0.1]), ("lwr_arm_%d_link" % k, None)]
+    frames = []
+    for link, off in robot:
+        f = {"Link": link, "Radius": 0.1, "Group": "Robot"}
+        if off:
+            f["LinkOffset"] = off
+        frames.append(f)
+    for y in (-0.3, -0.2, -0.1, 0.0, 0.1, 0.2, 0.3):
+        frames.append({"Link": "Obstacle", "Radius": 0.15, "Group": "Obstacle", "LinkOffset": [0, y, 0]})
+    return [{"type": "SphereCollision", "Precision": 0.1, "EndEffector": frames}]
+
+
+def test_sphere_collision_lwr_moving_obstacle(oracle_lib):
+    # cfg 5 fixture shape (example_sphere_collision.xml: 12 robot + 7 obstacle spheres, obstacle link trajectory-driven)
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    tree.add_environment_element("Obstacle", generated_slot=0)
+    orc = oracle_lib.Oracle(tree)
+    B, T = 8, 25
+    gen = np.zeros((T, 1, 12))
+    for t in range(T):
+        gen[t, 0] = oracle_lib.get_frame([0.5 - 0.02 * t, 0.1, 0.6 + 0.01 * t, 0, 0, 0.1 * t])
+    X = random_states(orc, B * T, seed=77)
+    maps = _lwr_sphere_maps() + [{"type": "EffPosition", "EndEffector": [{"Link": "Obstacle", "LinkOffset": [0, 0.3, 0]}]}]
+    prob, phi, jac = _check(orc, maps, X, T=T, generated=gen)
+    assert np.all(jac[:, 1:, :] == 0)  # the obstacle has no controlled ancestors
+
+
+def test_sphere_collision_three_groups_robot_vs_robot(oracle_lib):
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    frames = []
+    for link, grp in (("leftPalm", "a"), ("leftForearmLink", "a"), ("rightPalm", "b"), ("rightForearmLink", "b"),
+                      ("torso", "c"), ("pelvis", "c"), ("leftFoot", "b")):
+        frames.append({"Link": link, "Radius": 0.08, "Group": grp, "LinkOffset": [0.01, 0.02, 0.03]})
+    maps = [{"type": "SphereCollision", "Precision": 0.05, "EndEffector": frames}]
+    X = random_states(orc, 512, seed=78)
+    prob, phi, jac = _check(orc, maps, X)
+    assert phi.shape[1] == 3
+
+
+def test_mimic_and_uncontrolled_joints(oracle_lib):
+    # a second planning group leaves joints uncontrolled at a non-zero model state; add a mimic joint by hand
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    # make joint 5 mimic joint 1 (App. C #5: moves in FK, no Jacobian column of its own)
+    e5 = tree.link_index["lwr_arm_6_link"]
+    e1 = tree.link_index["lwr_arm_2_link"]
+    tree.elements[e5].mimic_elem = e1
+    tree.elements[e5].mimic_mult = -0.5
+    tree.elements[e5].mimic_off = 0.3
+    # and joint 3 uncontrolled, frozen at 0.7
+    e3 = tree.link_index["lwr_arm_4_link"]
+    for e in tree.elements:
+        if e.control_id > 3:
+            e.control_id -= 1
+    tree.elements[e3].control_id = -1
+    tree.controlled_joint_names.pop(3)
+    tree.n_controlled = 6
+    tree.lower = np.delete(tree.lower, 3)
+    tree.upper = np.delete(tree.upper, 3)
+    tree.tree_state[e3] = 0.7
+    orc = oracle_lib.Oracle(tree)
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    prob, phi, jac = _check(orc, maps, random_states(orc, 512, seed=55))
+    assert prob.program_info()["joint_ops"] == 6
+
+
+def test_host_pipeline_matches_device_path(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    E = 200_003
+    X = random_states(orc, E, seed=61)
+    phi_d, jac_d = run_gpu(prob, X, layout=_capi.LAYOUT_AOS_ROWMAJOR)
+    phi_h, jac_h = prob.update_batch_host(X, layout=_capi.LAYOUT_AOS_ROWMAJOR)
+    assert np.array_equal(phi_d, phi_h) and np.array_equal(jac_d, jac_h)
+    phi_s, jac_s = prob.update_batch_host(np.ascontiguousarray(X.T), layout=_capi.LAYOUT_SOA)
+    assert np.array_equal(phi_s.T, phi_h) and np.array_equal(jac_s.transpose(2, 0, 1), jac_h)
+    phi_c, jac_c = prob.update_batch_host(X, layout=_capi.LAYOUT_AOS_COLMAJOR)
+    assert np.array_equal(jac_c.transpose(0, 2, 1), jac_h)
+    # spot-check against the oracle
+    sel = np.random.default_rng(0).integers(0, E, 512)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi_h[sel], phi_ref, angle_entries(maps, orc)) <= TOL
+    assert max_abs_err(jac_h[sel], jac_ref) <= TOL
+
+
+def test_full_size_properties_1m(oracle_lib):
+    """BASELINE cfg 2a at full size (2^20 configurations): size-independent properties + sampled oracle parity."""
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    E = 1 << 20
+    X = random_states(orc, E, seed=1234 + 2)
+    phi, jac = run_gpu(prob, X)
+    R = phi[:, 3:12].reshape(E, 3, 3)
+    # rotation blocks stay orthonormal with det +1
+    assert np.abs(np.einsum("eij,ekj->eik", R, R) - np.eye(3)).max() < 1e-12
+    assert np.abs(np.linalg.det(R) - 1).max() < 1e-12
+    # reach bound of the arm: |p - shoulder| <= sum of link lengths
+    assert np.linalg.norm(phi[:, :3] - np.array([0, 0, 0.3305]), axis=1).max() <= 0.2 * 3 + 0.19 + 0.078 + 1e-12
+    # last joint axis is the tool z axis: angular Jacobian column 6 == R[:, :, 2]
+    assert np.abs(jac[:, 3:6, 6] - R[:, :, 2]).max() < 1e-12
+    # permutation equivariance: evaluating a shuffled batch shuffles the outputs, bit for bit
+    perm = np.random.default_rng(1).permutation(E)[: 1 << 16]
+    phi_p, jac_p = run_gpu(prob, X[perm])
+    assert np.array_equal(phi_p, phi[perm]) and np.array_equal(jac_p, jac[perm])
+    sel = np.random.default_rng(2).integers(0, E, 4096)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi[sel], phi_ref) <= TOL and max_abs_err(jac[sel], jac_ref) <= TOL
+
+
+def test_errors_are_loud(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    tree, prob = gpu_problem_from_maps(orc, [{"type": "JointLimit"}])
+    with pytest.raises(_capi.ExoticaError):
+        prob.update_batch_host(np.zeros((4, 6)))  # wrong state size
+    p2 = _capi.Problem(tree)
+    with pytest.raises(_capi.ExoticaError):
+        p2.add_task_map(_capi.MAP_EFF_POSITION, elem_a=[999])  # unknown link
+    with pytest.raises(_capi.ExoticaError):
+        p2.update_batch_device(None, 1, None, None)  # not finalized
