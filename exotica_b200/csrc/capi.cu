@@ -71,6 +71,12 @@ struct exo_problem
 
 extern "C" {
 
+// used by host/host_capi.cpp to report exotica::Exception messages through the same channel
+void exo_internal_set_error(const char* msg)
+{
+    g_error = msg ? msg : "";
+}
+
 const char* exo_last_error(void)
 {
     return g_error.c_str();

@@ -1,0 +1,710 @@
+// scene_problems.cpp -- host mirror of Scene, the four task maps, the factories and the problem Update paths.
+// Reference: exotica_core/src/{scene.cpp:320-348, task_map.cpp:42-60, planning_problem.cpp:148-266, setup.cpp},
+// exotica_core/src/problems/{abstract_time_indexed_problem.cpp:209-292, unconstrained_end_pose_problem.cpp:123-167},
+// exotations/exotica_core_task_maps/src/{eff_frame,eff_position,joint_limit,sphere_collision}.cpp.
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <set>
+#include <sstream>
+
+#include "exotica_host.h"
+
+namespace exotica
+{
+static void CheckRc(int rc)
+{
+    if (rc != EXO_OK) throw Exception(exo_last_error());
+}
+
+// ---- Initializer ------------------------------------------------------------------------------------------
+std::string Initializer::Require(const std::string& key) const
+{
+    auto it = properties.find(key);
+    if (it == properties.end()) ThrowPretty("Initializer " + name + " requires property " + key + " to be set!");
+    return it->second;
+}
+
+const std::vector<Initializer>& Initializer::List(const std::string& key) const
+{
+    static const std::vector<Initializer> empty;
+    auto it = children.find(key);
+    return it == children.end() ? empty : it->second;
+}
+
+Initializer InitializerFromXml(const xml::Element& e, const std::string& prefix)
+{
+    Initializer init;
+    init.name = prefix + e.name;
+    for (const auto& a : e.attributes) init.properties[a.first] = a.second;
+    for (const auto& c : e.children)
+    {
+        if (c->children.empty())
+        {
+            // leaf element: <T>100</T>  or an attribute-only initializer inside a list (handled by the parent below)
+            if (!c->attributes.empty() && xml::Trim(c->text).empty())
+                init.children[c->name].push_back(InitializerFromXml(*c, prefix));
+            else
+                init.properties[c->name] = xml::Trim(c->text);
+        }
+        else
+        {
+            // container element: its children are initializers (<Maps><EffFrame .../></Maps>, <EndEffector><Frame/></EndEffector>)
+            std::vector<Initializer>& list = init.children[c->name];
+            for (const auto& g : c->children) list.push_back(InitializerFromXml(*g, prefix));
+        }
+    }
+    return init;
+}
+
+// ---- Scene ----------------------------------------------------------------------------------------------------
+Scene::Scene() {}
+
+void Scene::InstantiateFromStrings(const std::string& urdf_xml, const std::string& srdf_xml, const std::string& joint_group)
+{
+    RobotModelPtr model(new RobotModel(urdf_xml, srdf_xml));
+    kinematica_.Instantiate(joint_group, model, name_);
+    num_positions_ = kinematica_.GetNumControlledJoints();
+}
+
+void Scene::Instantiate(const Initializer& init)
+{
+    name_ = init.Get("Name", "");
+    std::string urdf = init.Get("URDF", "");
+    std::string srdf = init.Get("SRDF", "");
+    if (urdf.empty()) ThrowPretty("Scene requires a URDF (file path or XML text); there is no ROS parameter server here");
+    auto load = [](const std::string& v) {
+        const std::string t = xml::Trim(v);
+        if (!t.empty() && t[0] == '<') return t;
+        return Setup::LoadFile(Setup::ParsePath(t));
+    };
+    InstantiateFromStrings(load(urdf), srdf.empty() ? std::string() : load(srdf), init.Get("JointGroup", ""));
+    // scene.cpp:292-303
+    if (init.Has("JointPositionLimitsLower")) kinematica_.SetJointLimitsLower(ParseVector(init.Get("JointPositionLimitsLower", "")));
+    if (init.Has("JointPositionLimitsUpper")) kinematica_.SetJointLimitsUpper(ParseVector(init.Get("JointPositionLimitsUpper", "")));
+}
+
+void Scene::Update(const std::vector<double>& x, double t)
+{
+    (void)t;  // per-timestep frames are tables indexed by the problem's timestep, see TimeIndexedProblem
+    kinematica_.Update(x);
+}
+
+void Scene::AddObject(const std::string& name, const Frame& transform, const std::string& parent)
+{
+    kinematica_.AddEnvironmentElement(name, transform, parent, false);
+}
+
+void Scene::AddTrajectoryFrames(const std::string& link, const std::vector<Frame>& frames_per_timestep)
+{
+    if (frames_per_timestep.empty()) ThrowPretty("Trajectory for '" + link + "' is empty");
+    int idx = kinematica_.GetElementIndex(link);
+    if (idx < 0) idx = kinematica_.AddEnvironmentElement(link, IdentityFrame(), "", true);
+    const KinematicElement& e = kinematica_.GetTree()[idx];
+    if (!e.is_trajectory_generated) ThrowPretty("Link '" + link + "' exists and is not trajectory driven; add it with AddTrajectoryFrames only");
+    trajectories_[e.generated_slot] = frames_per_timestep;
+}
+
+const std::vector<double>& Scene::GetGeneratedTable(int& T, int& n_generated) const
+{
+    n_generated = kinematica_.GetNumGenerated();
+    T = 0;
+    generated_table_.clear();
+    if (n_generated == 0) return generated_table_;
+    for (const auto& kv : trajectories_) T = std::max(T, (int)kv.second.size());
+    if ((int)trajectories_.size() != n_generated) ThrowPretty("Every trajectory-driven link needs AddTrajectoryFrames");
+    generated_table_.assign((size_t)T * n_generated * 12, 0.0);
+    for (const auto& kv : trajectories_)
+        for (int t = 0; t < T; ++t)
+        {
+            const Frame& f = kv.second[std::min<size_t>(t, kv.second.size() - 1)];
+            memcpy(&generated_table_[((size_t)t * n_generated + kv.first) * 12], f.data(), 12 * sizeof(double));
+        }
+    return generated_table_;
+}
+
+// ---- TaskMap base ------------------------------------------------------------------------------------------------
+void TaskMap::InstantiateBase(const Initializer& init)
+{
+    object_name_ = init.Get("Name", "");
+    is_used = true;
+    frames_.clear();
+    for (const Initializer& eff : init.List("EndEffector"))
+    {
+        // init/frame.in: Link (required), LinkOffset, Base, BaseOffset
+        const std::string link = eff.Require("Link");
+        Frame oa = IdentityFrame(), ob = IdentityFrame();
+        if (eff.Has("LinkOffset")) oa = GetFrame(ParseVector(eff.Get("LinkOffset", "")));
+        if (eff.Has("BaseOffset")) ob = GetFrame(ParseVector(eff.Get("BaseOffset", "")));
+        frames_.push_back(KinematicFrameRequest(link, oa, eff.Get("Base", ""), ob));
+    }
+}
+
+void TaskMap::ResolveFrames()
+{
+    if (!scene_) ThrowPretty("Scene is not initialised!");
+    const int F = (int)frames_.size();
+    elem_a_.resize(F);
+    elem_b_.resize(F);
+    off_a_.resize(12 * (size_t)F);
+    off_b_.resize(12 * (size_t)F);
+    for (int i = 0; i < F; ++i)
+    {
+        elem_a_[i] = scene_->GetKinematicTree().ResolveFrame(frames_[i].frame_A_link_name, "frame_A");
+        elem_b_[i] = scene_->GetKinematicTree().ResolveFrame(frames_[i].frame_B_link_name, "frame_B");
+        memcpy(&off_a_[12 * i], frames_[i].frame_A_offset.data(), 12 * sizeof(double));
+        memcpy(&off_b_[12 * i], frames_[i].frame_B_offset.data(), 12 * sizeof(double));
+    }
+}
+
+static void AddMapToBackend(exo_problem* p, TaskMap& m, const std::vector<int32_t>& ea, const std::vector<double>& oa, const std::vector<int32_t>& eb,
+                            const std::vector<double>& ob)
+{
+    exo_task_map_desc d;
+    memset(&d, 0, sizeof(d));
+    d.kind = m.Kind();
+    d.n_frames = (int)ea.size();
+    d.elem_a = ea.data();
+    d.off_a = oa.data();
+    d.elem_b = eb.data();
+    d.off_b = ob.data();
+    d.rotation_type = EXO_ROT_RPY;
+    d.precision = 1.0;
+    d.is_used = m.is_used ? 1 : 0;
+    m.FillDescriptor(d);
+    CheckRc(exo_problem_add_task_map(p, &d));
+}
+
+void TaskMap::ReleaseOwnProblem()
+{
+    if (own_problem_) exo_problem_destroy(own_problem_);
+    own_problem_ = nullptr;
+}
+
+void TaskMap::EnsureOwnProblem()
+{
+    if (own_problem_) return;
+    ResolveFrames();
+    CheckRc(exo_problem_create(scene_->GetKinematicTree().GetBackend(), &own_problem_));
+    const bool used = is_used;
+    is_used = true;
+    try
+    {
+        AddMapToBackend(own_problem_, *this, elem_a_, off_a_, elem_b_, off_b_);
+    }
+    catch (...)
+    {
+        is_used = used;
+        ReleaseOwnProblem();
+        throw;
+    }
+    is_used = used;
+    CheckRc(exo_problem_finalize(own_problem_));
+}
+
+void TaskMap::UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian)
+{
+    EnsureOwnProblem();
+    CheckRc(exo_problem_update_batch_host(own_problem_, x, n_evals, 1, layout, phi, jacobian));
+}
+
+void TaskMap::Update(const std::vector<double>& x, std::vector<double>& phi)
+{
+    const int N = scene_ ? scene_->GetKinematicTree().GetNumControlledJoints() : 0;
+    if ((int)x.size() != N) ThrowPretty("Wrong state vector size! Got " + std::to_string(x.size()) + " expected " + std::to_string(N));
+    if ((int)phi.size() != TaskSpaceDim()) ThrowPretty("Wrong size of Phi!");
+    UpdateBatch(x.data(), 1, EXO_LAYOUT_AOS_COLMAJOR, phi.data(), nullptr);
+}
+
+void TaskMap::Update(const std::vector<double>& x, std::vector<double>& phi, std::vector<double>& jacobian)
+{
+    const int N = scene_ ? scene_->GetKinematicTree().GetNumControlledJoints() : 0;
+    if ((int)x.size() != N) ThrowPretty("Wrong state vector size! Got " + std::to_string(x.size()) + " expected " + std::to_string(N));
+    if ((int)phi.size() != TaskSpaceDim()) ThrowPretty("Wrong size of Phi!");
+    if ((int)jacobian.size() != TaskSpaceJacobianDim() * N) ThrowPretty("Wrong size of jacobian! " + std::to_string(N));
+    UpdateBatch(x.data(), 1, EXO_LAYOUT_AOS_COLMAJOR, phi.data(), jacobian.data());
+}
+
+// ---- the four maps ----------------------------------------------------------------------------------------------------
+void EffFrame::Instantiate(const Initializer& init)
+{
+    rotation_type_ = GetRotationTypeFromString(init.Get("Type", "RPY"));  // init/eff_frame.in
+    small_stride_ = GetRotationTypeLength(rotation_type_);
+    big_stride_ = small_stride_ + 3;
+}
+
+void JointLimit::Instantiate(const Initializer& init)
+{
+    const std::vector<double> v = ParseVector(init.Get("SafePercentage", "0.0"));  // init/joint_limit.in
+    if (v.size() != 1) ThrowPretty("SafePercentage must be a single number");
+    safe_percentage_ = v[0];
+}
+
+void JointLimit::AssignScene(ScenePtr scene)
+{
+    scene_ = scene;
+    N_ = scene_->GetKinematicTree().GetNumControlledJoints();  // joint_limit.cpp:42-56 (kinematic case)
+}
+
+void SphereCollision::InstantiateBase(const Initializer& init)
+{
+    TaskMap::InstantiateBase(init);
+    radiuses_.clear();
+    group_names_.clear();
+    for (const Initializer& eff : init.List("EndEffector"))
+    {
+        // init/sphere.in: Radius (required), Group = "default"
+        const std::vector<double> r = ParseVector(eff.Require("Radius"));
+        if (r.size() != 1) ThrowPretty("Sphere Radius must be a single number");
+        radiuses_.push_back(r[0]);
+        group_names_.push_back(eff.Get("Group", "default"));
+    }
+}
+
+void SphereCollision::Instantiate(const Initializer& init)
+{
+    const std::vector<double> p = ParseVector(init.Require("Precision"));  // init/sphere_collision.in
+    if (p.size() != 1) ThrowPretty("Precision must be a single number");
+    precision_ = p[0];
+    // groups_ is a std::map<string, vector<int>>: lexicographic group order (sphere_collision.cpp:42-47)
+    std::set<std::string> names(group_names_.begin(), group_names_.end());
+    std::vector<std::string> sorted(names.begin(), names.end());
+    group_rank_.clear();
+    for (const std::string& g : group_names_) group_rank_.push_back((int32_t)(std::find(sorted.begin(), sorted.end(), g) - sorted.begin()));
+    dim_ = (int)(sorted.size() * (sorted.size() - 1) / 2);
+}
+
+void SphereCollision::FillDescriptor(exo_task_map_desc& desc)
+{
+    desc.precision = precision_;
+    desc.radius = radiuses_.data();
+    desc.group = group_rank_.data();
+}
+
+// ---- factories ----------------------------------------------------------------------------------------------------------------
+template <class T>
+static TaskMapPtr MakeMap()
+{
+    return TaskMapPtr(new T());
+}
+template <class T>
+static PlanningProblemPtr MakeProblem()
+{
+    return PlanningProblemPtr(new T());
+}
+
+Setup& Setup::Instance()
+{
+    static Setup* s = nullptr;
+    if (!s)
+    {
+        s = new Setup();
+        s->RegisterMap("exotica/EffFrame", &MakeMap<EffFrame>);
+        s->RegisterMap("exotica/EffPosition", &MakeMap<EffPosition>);
+        s->RegisterMap("exotica/JointLimit", &MakeMap<JointLimit>);
+        s->RegisterMap("exotica/SphereCollision", &MakeMap<SphereCollision>);
+        s->RegisterProblem("exotica/UnconstrainedEndPoseProblem", &MakeProblem<UnconstrainedEndPoseProblem>);
+        s->RegisterProblem("exotica/TimeIndexedProblem", &MakeProblem<TimeIndexedProblem>);
+        s->RegisterProblem("exotica/UnconstrainedTimeIndexedProblem", &MakeProblem<TimeIndexedProblem>);
+    }
+    return *s;
+}
+
+void Setup::RegisterMap(const std::string& type, MapCreator creator)
+{
+    if (maps_.count(type)) ThrowPretty("Trying to register already existing type '" + type + "'!");  // factory.h:76-83
+    maps_[type] = creator;
+}
+
+void Setup::RegisterProblem(const std::string& type, ProblemCreator creator)
+{
+    if (problems_.count(type)) ThrowPretty("Trying to register already existing type '" + type + "'!");
+    problems_[type] = creator;
+}
+
+std::vector<std::string> Setup::GetMaps()
+{
+    std::vector<std::string> out;
+    for (const auto& kv : Instance().maps_) out.push_back(kv.first);
+    return out;
+}
+
+std::vector<std::string> Setup::GetProblems()
+{
+    std::vector<std::string> out;
+    for (const auto& kv : Instance().problems_) out.push_back(kv.first);
+    return out;
+}
+
+TaskMapPtr Setup::CreateMap(const Initializer& init)
+{
+    auto it = Instance().maps_.find(init.name);
+    if (it == Instance().maps_.end()) ThrowPretty("Unable to load task map of type '" + init.name + "' (registered on the GPU path: EffFrame, EffPosition, JointLimit, SphereCollision)");
+    TaskMapPtr m = it->second();
+    m->InstantiateBase(init);  // InstantiateInternal = InstantiateBase + Instantiate (property.h:113-119)
+    m->Instantiate(init);
+    return m;
+}
+
+PlanningProblemPtr Setup::CreateProblem(const std::string& type)
+{
+    auto it = Instance().problems_.find(type);
+    if (it == Instance().problems_.end())
+    {
+        std::string all;
+        for (const auto& kv : Instance().problems_) all += " '" + kv.first + "'";
+        ThrowPretty("This factory does not recognize type '" + type + "' (registered:" + all + ")");  // factory.h:100-106
+    }
+    return it->second();
+}
+
+PlanningProblemPtr Setup::CreateProblem(const Initializer& init)
+{
+    PlanningProblemPtr p = CreateProblem(init.name);
+    p->InstantiateBase(init);
+    p->Instantiate(init);
+    return p;
+}
+
+Initializer Setup::LoadProblemInitializer(const std::string& xml_text)
+{
+    std::shared_ptr<xml::Element> doc;
+    try
+    {
+        doc = xml::Parse(xml_text);
+    }
+    catch (const std::exception& e)
+    {
+        ThrowPretty(std::string("Can't load XML: ") + e.what());
+    }
+    auto is_problem = [](const std::string& n) { return Instance().problems_.count("exotica/" + n) > 0; };
+    if (is_problem(doc->name)) return InitializerFromXml(*doc);
+    for (const auto& c : doc->children)
+        if (is_problem(c->name)) return InitializerFromXml(*c);
+    ThrowPretty("No problem definition found in the XML (root <" + doc->name + ">)");
+}
+
+PlanningProblemPtr Setup::LoadProblem(const std::string& xml_text)
+{
+    return CreateProblem(LoadProblemInitializer(xml_text));
+}
+
+void Setup::SetPackagePath(const std::string& package, const std::string& directory)
+{
+    Instance().packages_[package] = directory;
+}
+
+std::string Setup::ParsePath(const std::string& path)
+{
+    // tools.cpp:150-190: "{package}/rest" and "package://package/rest"
+    std::string ret = path;
+    const size_t open = ret.find('{');
+    const size_t close = ret.find('}');
+    if (open != std::string::npos && close != std::string::npos && close > open)
+    {
+        const std::string pkg = ret.substr(open + 1, close - open - 1);
+        auto it = Instance().packages_.find(pkg);
+        if (it == Instance().packages_.end()) ThrowPretty("Unknown package '" + pkg + "' (use Setup::SetPackagePath)");
+        ret = ret.substr(0, open) + it->second + ret.substr(close + 1);
+    }
+    else if (ret.compare(0, 10, "package://") == 0)
+    {
+        const size_t slash = ret.find('/', 10);
+        const std::string pkg = ret.substr(10, slash == std::string::npos ? std::string::npos : slash - 10);
+        auto it = Instance().packages_.find(pkg);
+        if (it == Instance().packages_.end()) ThrowPretty("Unknown package '" + pkg + "' (use Setup::SetPackagePath)");
+        ret = it->second + (slash == std::string::npos ? std::string() : ret.substr(slash));
+    }
+    return ret;
+}
+
+std::string Setup::LoadFile(const std::string& path)
+{
+    std::ifstream f(path.c_str(), std::ios::in | std::ios::binary);
+    if (!f) ThrowPretty("File does not exist: '" + path + "'");  // tools.cpp:98-112
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// ---- PlanningProblem --------------------------------------------------------------------------------------------------------------
+PlanningProblem::~PlanningProblem()
+{
+    InvalidateBackend();
+}
+
+void PlanningProblem::InvalidateBackend()
+{
+    if (backend_) exo_problem_destroy(backend_);
+    backend_ = nullptr;
+}
+
+void PlanningProblem::InstantiateBase(const Initializer& init)
+{
+    object_name_ = init.Get("Name", "");
+    task_maps_.clear();
+    tasks_.clear();
+    InvalidateBackend();
+
+    // Create the scene
+    const std::vector<Initializer>& ps = init.List("PlanningScene");
+    if (ps.empty()) ThrowPretty("Initializer " + init.name + " requires property PlanningScene to be set!");
+    scene_.reset(new Scene());
+    scene_->Instantiate(ps[0]);
+    N = scene_->GetKinematicTree().GetNumControlledJoints();
+
+    start_state_.assign(N, 0.0);
+    if (init.Has("StartState")) SetStartState(ParseVector(init.Get("StartState", "")));
+    const std::vector<double> st = ParseVector(init.Get("StartTime", "0"));
+    if (st.size() != 1 || st[0] < 0) ThrowPretty("Invalid start time " + init.Get("StartTime", "0"));
+    t_start = st[0];
+
+    const int order = init.Has("DerivativeOrder") ? (int)ParseVector(init.Get("DerivativeOrder", "-1")).at(0) : -1;
+    switch (order)
+    {
+        case -1:
+            break;
+        case 0:
+            flags_ = KIN_FK;
+            break;
+        case 1:
+            flags_ = KIN_FK | KIN_J;
+            break;
+        case 2:
+            ThrowPretty("DerivativeOrder 2 (kinematic Hessian) is outside the GPU hot path");
+        default:
+            ThrowPretty("Unsupported DerivativeOrder: " + std::to_string(order));
+    }
+
+    // Create the maps (planning_problem.cpp:204-223)
+    for (const Initializer& map_init : init.List("Maps"))
+    {
+        TaskMapPtr new_map = Setup::CreateMap(map_init);
+        new_map->AssignScene(scene_);
+        new_map->ns_ = object_name_ + "/" + new_map->GetObjectName();
+        if (task_maps_.find(new_map->GetObjectName()) != task_maps_.end()) ThrowPretty("Map '" + new_map->GetObjectName() + "' already exists!");
+        task_maps_[new_map->GetObjectName()] = new_map;
+        tasks_.push_back(new_map);
+    }
+    // planning_problem.cpp:227-238
+    int id = 0, idJ = 0;
+    for (int i = 0; i < (int)tasks_.size(); ++i)
+    {
+        tasks_[i]->ResolveFrames();  // RequestKinematics: unknown links throw here (kinematic_tree.cpp:647,658)
+        tasks_[i]->id = i;
+        tasks_[i]->start = id;
+        tasks_[i]->length = tasks_[i]->TaskSpaceDim();
+        tasks_[i]->start_jacobian = idJ;
+        tasks_[i]->length_jacobian = tasks_[i]->TaskSpaceJacobianDim();
+        id += tasks_[i]->length;
+        idJ += tasks_[i]->length_jacobian;
+    }
+    length_Phi = id;
+    length_jacobian = idJ;
+}
+
+void PlanningProblem::SetStartState(const std::vector<double>& x)
+{
+    // planning_problem.cpp:93-136: N values (controlled) or the full model state
+    if ((int)x.size() == N)
+        start_state_ = x;
+    else if ((int)x.size() == scene_->GetKinematicTree().GetNumModelJoints())
+    {
+        scene_->SetModelState(x);
+        start_state_ = scene_->GetControlledState();
+    }
+    else
+        ThrowPretty("Wrong start state vector size, expected " + std::to_string(N) + ", got " + std::to_string(x.size()));
+}
+
+void PlanningProblem::ParseCost(const Initializer& init, int T)
+{
+    // Task::Initialize (tasks.cpp:36-66) + Rho handling (tasks.cpp:68-118,166-244): a map is used iff some rho != 0
+    cost_tasks_.clear();
+    cost_rho_.clear();
+    const char* blocks[3] = {"Cost", "Inequality", "Equality"};
+    for (const char* block : blocks)
+        for (const Initializer& task : init.List(block))
+        {
+            const std::string name = task.Require("Task");
+            if (task_maps_.find(name) == task_maps_.end()) ThrowPretty("Task map '" + name + "' has not been defined!");
+            std::vector<double> rho = {1.0};
+            if (task.Has("Rho"))
+            {
+                rho = ParseVector(task.Get("Rho", ""));
+                if (rho.size() != 1 && (int)rho.size() != T) ThrowPretty("Invalid task rho size! Expecting 1 or " + std::to_string(T) + " got " + std::to_string(rho.size()));
+            }
+            cost_tasks_.push_back(name);
+            cost_rho_.push_back(rho);
+        }
+    for (TaskMapPtr& m : tasks_) m->is_used = false;
+    for (size_t i = 0; i < cost_tasks_.size(); ++i)
+    {
+        bool nonzero = false;
+        for (double r : cost_rho_[i]) nonzero = nonzero || (r != 0.0);
+        if (nonzero) task_maps_[cost_tasks_[i]]->is_used = true;
+    }
+}
+
+exo_problem* PlanningProblem::GetBackend()
+{
+    if (backend_) return backend_;
+    CheckRc(exo_problem_create(scene_->GetKinematicTree().GetBackend(), &backend_));
+    try
+    {
+        for (TaskMapPtr& m : tasks_)
+        {
+            m->ResolveFrames();
+            AddMapToBackend(backend_, *m, m->elem_a_, m->off_a_, m->elem_b_, m->off_b_);
+        }
+        CheckRc(exo_problem_finalize(backend_));
+        if (exo_problem_length_phi(backend_) != length_Phi || exo_problem_length_jacobian(backend_) != length_jacobian)
+            ThrowPretty("backend indexing disagrees with the host task maps");
+    }
+    catch (...)
+    {
+        InvalidateBackend();
+        throw;
+    }
+    return backend_;
+}
+
+void PlanningProblem::UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian)
+{
+    exo_problem* p = GetBackend();
+    const int T = GetT();
+    if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
+    CheckRc(exo_problem_update_batch_host(p, x, n_evals, T, layout, phi, (flags_ & KIN_J) ? jacobian : nullptr));
+    number_of_problem_updates_ += (unsigned int)n_evals;
+}
+
+void PlanningProblem::UpdateBatchDevice(const double* d_x, int64_t n_evals, int layout, double* d_phi, double* d_jacobian, void* stream)
+{
+    exo_problem* p = GetBackend();
+    const int T = GetT();
+    if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
+    CheckRc(exo_problem_update_batch(p, d_x, n_evals, T, layout, d_phi, (flags_ & KIN_J) ? d_jacobian : nullptr, stream));
+    number_of_problem_updates_ += (unsigned int)n_evals;
+}
+
+float PlanningProblem::LastKernelMs()
+{
+    float ms = 0;
+    CheckRc(exo_problem_last_kernel_ms(GetBackend(), &ms));
+    return ms;
+}
+
+int64_t PlanningProblem::LaunchCount()
+{
+    return backend_ ? exo_problem_launch_count(backend_) : 0;
+}
+
+// ---- UnconstrainedEndPoseProblem ------------------------------------------------------------------------------------------------------
+void UnconstrainedEndPoseProblem::Instantiate(const Initializer& init)
+{
+    ParseCost(init, 1);
+    if (init.Has("W"))
+    {
+        const std::vector<double> w = ParseVector(init.Get("W", ""));
+        if ((int)w.size() != N && w.size() != 1) ThrowPretty("W dimension mismatch! Expected " + std::to_string(N) + ", got " + std::to_string(w.size()));
+    }
+    Phi.assign(length_Phi, 0.0);
+    jacobian.assign((size_t)length_jacobian * N, 0.0);
+}
+
+void UnconstrainedEndPoseProblem::Update(const std::vector<double>& x)
+{
+    if ((int)x.size() != N) ThrowPretty("Wrong state vector size! Got " + std::to_string(x.size()) + " expected " + std::to_string(N));
+    UpdateBatch(x.data(), 1, EXO_LAYOUT_AOS_COLMAJOR, Phi.data(), jacobian.data());
+}
+
+// ---- TimeIndexedProblem ------------------------------------------------------------------------------------------------------------------
+void TimeIndexedProblem::Instantiate(const Initializer& init)
+{
+    const std::vector<double> t = ParseVector(init.Require("T"));
+    if (t.size() != 1) ThrowPretty("T must be a single number");
+    T_ = (int)t[0];
+    if (T_ <= 2) ThrowPretty("Invalid number of timesteps: " + std::to_string(T_));  // abstract_time_indexed_problem.cpp:118-125
+    const std::vector<double> tau = ParseVector(init.Require("tau"));
+    if (tau.size() != 1 || tau[0] <= 0.) ThrowPretty("tau_ is expected to be greater than 0. (tau_=" + init.Get("tau", "") + ")");
+    tau_ = tau[0];
+    ParseCost(init, T_);
+    // time_indexed_problem.cpp:57-72
+    if (init.Has("LowerBound"))
+    {
+        const std::vector<double> lb = ParseVector(init.Get("LowerBound", ""));
+        if ((int)lb.size() == N) scene_->GetKinematicTree().SetJointLimitsLower(lb);
+        else if (!lb.empty()) ThrowPretty("Lower bound size incorrect! Expected " + std::to_string(N) + " got " + std::to_string(lb.size()));
+    }
+    if (init.Has("UpperBound"))
+    {
+        const std::vector<double> ub = ParseVector(init.Get("UpperBound", ""));
+        if ((int)ub.size() == N) scene_->GetKinematicTree().SetJointLimitsUpper(ub);
+        else if (!ub.empty()) ThrowPretty("Upper bound size incorrect! Expected " + std::to_string(N) + " got " + std::to_string(ub.size()));
+    }
+    x.assign(T_, std::vector<double>(N, 0.0));
+    Phi.assign(T_, std::vector<double>(length_Phi, 0.0));
+    jacobian.assign(T_, std::vector<double>((size_t)length_jacobian * N, 0.0));
+}
+
+void TimeIndexedProblem::PushGenerated()
+{
+    int T = 0, n_gen = 0;
+    const std::vector<double>& table = scene_->GetGeneratedTable(T, n_gen);
+    if (n_gen == 0) return;
+    if (T != T_) ThrowPretty("Trajectory tables have " + std::to_string(T) + " timesteps, the problem has T=" + std::to_string(T_));
+    CheckRc(exo_problem_set_generated(GetBackend(), T_, n_gen, table.data()));
+}
+
+void TimeIndexedProblem::Update(const std::vector<double>& x_in, int t)
+{
+    if (t >= T_ || t < -1) ThrowPretty("Requested t=" + std::to_string(t) + " out of range, needs to be 0 =< t < " + std::to_string(T_));
+    if (t == -1) t = T_ - 1;
+    if ((int)x_in.size() != N) ThrowPretty("Wrong state vector size! Got " + std::to_string(x_in.size()) + " expected " + std::to_string(N));
+    x[t] = x_in;
+    exo_problem* p = GetBackend();
+    PushGenerated();
+    // one evaluation at timestep t: a length-T batch would waste work, so shift the table lookup by evaluating a
+    // padded mini-batch only when trajectory-driven links exist
+    if (scene_->GetKinematicTree().GetNumGenerated() == 0)
+    {
+        CheckRc(exo_problem_update_batch_host(p, x_in.data(), 1, T_, EXO_LAYOUT_AOS_COLMAJOR, Phi[t].data(), (flags_ & KIN_J) ? jacobian[t].data() : nullptr));
+    }
+    else
+    {
+        std::vector<double> X((size_t)(t + 1) * N, 0.0), P((size_t)(t + 1) * length_Phi), J((size_t)(t + 1) * length_jacobian * N);
+        for (int k = 0; k <= t; ++k) memcpy(&X[(size_t)k * N], x_in.data(), N * sizeof(double));
+        CheckRc(exo_problem_update_batch_host(p, X.data(), t + 1, T_, EXO_LAYOUT_AOS_COLMAJOR, P.data(), (flags_ & KIN_J) ? J.data() : nullptr));
+        memcpy(Phi[t].data(), &P[(size_t)t * length_Phi], length_Phi * sizeof(double));
+        if (flags_ & KIN_J) memcpy(jacobian[t].data(), &J[(size_t)t * length_jacobian * N], (size_t)length_jacobian * N * sizeof(double));
+    }
+    ++number_of_problem_updates_;
+}
+
+void TimeIndexedProblem::Update(const std::vector<double>& x_trajectory_in)
+{
+    if ((int)x_trajectory_in.size() != (T_ - 1) * N)
+        ThrowPretty("To update using the trajectory Update method, please use a trajectory of size N x (T-1) (" + std::to_string(N * (T_ - 1)) + "), given: " + std::to_string(x_trajectory_in.size()));
+    // t = 0 holds the start state (App. C #9); evaluate all T timesteps of this one trajectory in one launch
+    std::vector<double> X((size_t)T_ * N);
+    memcpy(X.data(), x[0].data(), N * sizeof(double));
+    memcpy(X.data() + N, x_trajectory_in.data(), (size_t)(T_ - 1) * N * sizeof(double));
+    std::vector<double> P((size_t)T_ * length_Phi), J((size_t)T_ * length_jacobian * N);
+    UpdateTrajectories(X.data(), 1, EXO_LAYOUT_AOS_COLMAJOR, P.data(), J.data());
+    for (int t = 1; t < T_; ++t)
+    {
+        x[t].assign(X.begin() + (size_t)t * N, X.begin() + (size_t)(t + 1) * N);
+        memcpy(Phi[t].data(), &P[(size_t)t * length_Phi], length_Phi * sizeof(double));
+        if (flags_ & KIN_J) memcpy(jacobian[t].data(), &J[(size_t)t * length_jacobian * N], (size_t)length_jacobian * N * sizeof(double));
+    }
+}
+
+void TimeIndexedProblem::UpdateTrajectories(const double* xin, int64_t n_trajectories, int layout, double* phi, double* jac)
+{
+    GetBackend();
+    PushGenerated();
+    UpdateBatch(xin, n_trajectories * T_, layout, phi, jac);
+}
+
+}  // namespace exotica

@@ -21,7 +21,6 @@ namespace exo
 {
 namespace
 {
-constexpr int TPB = 128;
 
 struct Fr
 {
@@ -39,6 +38,7 @@ __device__ __forceinline__ Fr fr_identity()
     return f;
 }
 
+template <int TPB>
 __device__ __forceinline__ Fr fr_load_scratch(const double* s)
 {
     Fr f;
@@ -49,6 +49,7 @@ __device__ __forceinline__ Fr fr_load_scratch(const double* s)
     return f;
 }
 
+template <int TPB>
 __device__ __forceinline__ void fr_store_scratch(double* s, const Fr& f)
 {
     s[0 * TPB] = f.m0; s[1 * TPB] = f.m1; s[2 * TPB] = f.m2;
@@ -252,6 +253,7 @@ __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y z w */
     }
 }
 
+template <int TPB>
 __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                 if (op.src == SRC_ROOT)
                     cur = fr_identity();
                 else if (op.src >= 0)
-                    cur = fr_load_scratch(scr + 12 * op.src * TPB);
+                    cur = fr_load_scratch<TPB>(scr + 12 * op.src * TPB);
                 const int pre = op.flags & F_PRE_MASK;
                 if (pre == F_PRE_TRANS)
                     fr_translate(cur, c[9], c[10], c[11]);
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                         js[3 * TPB] = cur.x; js[4 * TPB] = cur.y; js[5 * TPB] = cur.z;
                     }
                 }
-                if (op.dst >= 0) fr_store_scratch(scr + 12 * op.dst * TPB, cur);
+                if (op.dst >= 0) fr_store_scratch<TPB>(scr + 12 * op.dst * TPB, cur);
             }
             else if (op.kind == OP_EMIT_FRAME)
             {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                 Fr A;
                 if (op.src == SRC_CUR) A = cur;
                 else if (op.src == SRC_ROOT) A = fr_identity();
-                else A = fr_load_scratch(scr + 12 * op.src * TPB);
+                else A = fr_load_scratch<TPB>(scr + 12 * op.src * TPB);
                 const int offa = op.flags & F_OFFA_MASK;
                 if (offa == F_OFFA_TRANS) fr_translate(A, c[CE_OFFA_P], c[CE_OFFA_P + 1], c[CE_OFFA_P + 2]);
                 else if (offa == F_OFFA_FULL) A = fr_mul(A, fr_load_const(c + CE_OFFA_M));
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                     {
                         Fr B;
                         if (op.src_b == SRC_CUR) B = cur;
-                        else B = fr_load_scratch(scr + 12 * op.src_b * TPB);
+                        else B = fr_load_scratch<TPB>(scr + 12 * op.src_b * TPB);
                         B = fr_mul(B, fr_load_const(c + CE_B_M));
                         Binv = fr_inverse(B);
                     }
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                             const double ri = sc[4 * i + 3];
                             if (src_i != SRC_ROOT)
                             {
-                                const Fr f = (src_i == SRC_CUR) ? cur : fr_load_scratch(scr + 12 * src_i * TPB);
+                                const Fr f = (src_i == SRC_CUR) ? cur : fr_load_scratch<TPB>(scr + 12 * src_i * TPB);
                                 const double tx = f.m0 * pix + f.m1 * piy + f.m2 * piz + f.x;
                                 const double ty = f.m3 * pix + f.m4 * piy + f.m5 * piz + f.y;
                                 const double tz = f.m6 * pix + f.m7 * piy + f.m8 * piz + f.z;
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                                 double pjx = sc[4 * j], pjy = sc[4 * j + 1], pjz = sc[4 * j + 2];
                                 if (src_j != SRC_ROOT)
                                 {
-                                    const Fr f = (src_j == SRC_CUR) ? cur : fr_load_scratch(scr + 12 * src_j * TPB);
+                                    const Fr f = (src_j == SRC_CUR) ? cur : fr_load_scratch<TPB>(scr + 12 * src_j * TPB);
                                     const double tx = f.m0 * pjx + f.m1 * pjy + f.m2 * pjz + f.x;
                                     const double ty = f.m3 * pjx + f.m4 * pjy + f.m5 * pjz + f.y;
                                     const double tz = f.m6 * pjx + f.m7 * pjy + f.m8 * pjz + f.z;
@@ -698,6 +700,17 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
 }
 }  // namespace
 
+template <int TPB>
+cudaError_t try_config(size_t prog, size_t per_thread, int max_smem, int& ctas_per_sm, size_t& smem_bytes)
+{
+    smem_bytes = prog + per_thread * TPB;
+    ctas_per_sm = 0;
+    if (smem_bytes > (size_t)max_smem) return cudaSuccess;
+    cudaError_t err = cudaFuncSetAttribute(exo_eval_kernel<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exo_eval_kernel<TPB>, TPB, smem_bytes);
+}
+
 cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params)
 {
     int dev = 0, sms = 0, max_smem = 0;
@@ -708,31 +721,42 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (err != cudaSuccess) return err;
     const size_t prog = ((size_t)program_bytes + 15) & ~(size_t)15;
-    const size_t scratch = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * TPB * sizeof(double);
-    cfg.threads = TPB;
-    cfg.smem_bytes = prog + scratch;
+    const size_t per_thread = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * sizeof(double);
     params.scratch_offset = (int32_t)prog;
-    if (cfg.smem_bytes > (size_t)max_smem) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (cfg.smem_bytes > configured)
+    // pick the CTA size that keeps the most threads resident per SM (per-thread scratch lives in shared memory)
+    int best_threads = 0, best_tpb = 0, best_ctas = 0;
+    size_t best_smem = 0;
+    const int sizes[3] = {128, 64, 32};
+    for (int k = 0; k < 3; ++k)
     {
-        err = cudaFuncSetAttribute(exo_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        int ctas = 0;
+        size_t smem_bytes = 0;
+        if (sizes[k] == 128) err = try_config<128>(prog, per_thread, max_smem, ctas, smem_bytes);
+        else if (sizes[k] == 64) err = try_config<64>(prog, per_thread, max_smem, ctas, smem_bytes);
+        else err = try_config<32>(prog, per_thread, max_smem, ctas, smem_bytes);
         if (err != cudaSuccess) return err;
-        configured = (size_t)max_smem;
+        if (ctas * sizes[k] > best_threads)
+        {
+            best_threads = ctas * sizes[k];
+            best_tpb = sizes[k];
+            best_ctas = ctas;
+            best_smem = smem_bytes;
+        }
     }
-    int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exo_eval_kernel, TPB, cfg.smem_bytes);
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) per_sm = 1;
-    const int64_t want = (n_evals + TPB - 1) / TPB;
-    const int64_t resident = (int64_t)sms * per_sm;
+    if (best_threads == 0) return cudaErrorInvalidConfiguration;
+    cfg.threads = best_tpb;
+    cfg.smem_bytes = best_smem;
+    const int64_t want = (n_evals + best_tpb - 1) / best_tpb;
+    const int64_t resident = (int64_t)sms * best_ctas;
     cfg.blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
     return cudaSuccess;
 }
 
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream)
 {
-    exo_eval_kernel<<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(params);
+    if (cfg.threads == 128) exo_eval_kernel<128><<<cfg.blocks, 128, cfg.smem_bytes, stream>>>(params);
+    else if (cfg.threads == 64) exo_eval_kernel<64><<<cfg.blocks, 64, cfg.smem_bytes, stream>>>(params);
+    else exo_eval_kernel<32><<<cfg.blocks, 32, cfg.smem_bytes, stream>>>(params);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,86 @@
+/*
+ * exotica_b200_host.h -- C-ABI over the C++ host mirror (exotica_b200/csrc/host/exotica_host.h) for language
+ * bindings.  The reference binds its C++ classes with pybind11 (exotica_python/src/pyexotica.cpp); here the same
+ * subset is exposed as plain C so that the Python package only forwards (ctypes), with no logic of its own.
+ *
+ * Every function returns EXO_OK or an error code with the message in exo_last_error() (the host classes throw
+ * exotica::Exception; the wrappers translate).  String results are '\n'-joined lists owned by the handle and valid
+ * until the next call on it.
+ */
+#ifndef EXOTICA_B200_HOST_H_
+#define EXOTICA_B200_HOST_H_
+
+#include "exotica_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct exo_host_scene exo_host_scene;     /* exotica::Scene (+ its KinematicTree) */
+typedef struct exo_host_problem exo_host_problem; /* exotica::PlanningProblem */
+
+/* Setup: {package} resolution without ROS (tools.cpp:150-190) and the registered plugin names
+ * (pyexotica.cpp:683-706 Setup.get_maps / get_problems). */
+int exo_host_set_package_path(const char* package, const char* directory);
+const char* exo_host_registered_maps(void);
+const char* exo_host_registered_problems(void);
+/* exotica::GetFrame (tools/conversions.cpp:52-69): n in {3,6,7}. */
+int exo_host_get_frame(const double* v, int n, double out12[12]);
+
+/* ---- Scene / KinematicTree (pyexotica.cpp:1221-1300,1376-1455) ---- */
+int exo_host_scene_create(const char* urdf_xml, const char* srdf_xml, const char* joint_group, exo_host_scene** out);
+int exo_host_scene_destroy(exo_host_scene* scene);
+/* which: 0 controlled joint names, 1 controlled link names, 2 model joint names, 3 model link names (all tree
+ * elements, scene objects included), 4 root frame name, 5 root joint name */
+const char* exo_host_scene_names(exo_host_scene* scene, int which);
+int exo_host_scene_num_controlled(exo_host_scene* scene);
+int exo_host_scene_num_elements(exo_host_scene* scene);
+int exo_host_scene_base_types(exo_host_scene* scene, int32_t out[2]); /* model, controlled: 0 fixed, 10 floating, 20 planar */
+/* flattened tree for cross-checks: id, parent, joint_type, control_id [n]; origin, axis [n][3]; f_tip [n][12] */
+int exo_host_scene_tree(exo_host_scene* scene, int32_t* id, int32_t* parent, int32_t* joint_type, int32_t* control_id,
+                        double* origin, double* axis, double* f_tip);
+int exo_host_scene_element_index(exo_host_scene* scene, const char* link_name); /* -1 if unknown */
+int exo_host_scene_joint_limits(exo_host_scene* scene, double* lower, double* upper);
+int exo_host_scene_set_joint_limits(exo_host_scene* scene, const double* lower, const double* upper);
+int exo_host_scene_set_seed(exo_host_scene* scene, unsigned int seed);
+int exo_host_scene_random_state(exo_host_scene* scene, double* x);
+int exo_host_scene_get_model_state(exo_host_scene* scene, double* state /* [num model joints] */);
+int exo_host_scene_set_model_state(exo_host_scene* scene, const double* state, int n);
+int exo_host_scene_num_model_joints(exo_host_scene* scene);
+int exo_host_scene_add_object(exo_host_scene* scene, const char* name, const double frame12[12], const char* parent);
+int exo_host_scene_add_trajectory(exo_host_scene* scene, const char* link, int T, const double* frames /*[T][12]*/);
+/* KinematicTree::RequestFrames / Update / UpdateBatch: link names '\n'-joined, offsets [F][12] (NULL = identity) */
+int exo_host_scene_request_frames(exo_host_scene* scene, int n_frames, const char* links_a, const double* off_a,
+                                  const char* links_b, const double* off_b, int with_jacobian);
+int exo_host_scene_update(exo_host_scene* scene, const double* x, int n, double* phi /*[F][12]*/, double* jac /*[F][6*N] col-major*/);
+int exo_host_scene_update_batch(exo_host_scene* scene, const double* x, int64_t n_evals, int layout, double* phi, double* jac);
+/* Scene.fk / Scene.jacobian at the current model state */
+int exo_host_scene_fk(exo_host_scene* scene, const char* link_a, const double* off_a, const char* link_b, const double* off_b, double out12[12]);
+int exo_host_scene_jacobian(exo_host_scene* scene, const char* link_a, const double* off_a, const char* link_b, const double* off_b, double* out /*6xN col-major*/);
+
+/* ---- Problems (pyexotica.cpp:935-1060) ---- */
+int exo_host_load_problem_xml(const char* xml_text, exo_host_problem** out); /* Setup::LoadProblem on XML text */
+int exo_host_problem_destroy(exo_host_problem* problem);
+int exo_host_problem_dims(exo_host_problem* problem, int32_t out[4]); /* N, length_Phi, length_jacobian, T (1 for end-pose) */
+const char* exo_host_problem_type(exo_host_problem* problem);
+int exo_host_problem_num_tasks(exo_host_problem* problem);
+const char* exo_host_problem_task_name(exo_host_problem* problem, int task);
+int exo_host_problem_task_indexing(exo_host_problem* problem, int task, int32_t out[6]); /* id,start,length,start_jacobian,length_jacobian,is_used */
+exo_host_scene* exo_host_problem_scene(exo_host_problem* problem); /* borrowed, owned by the problem */
+int exo_host_problem_start_state(exo_host_problem* problem, double* x);
+/* One evaluation: t < 0 -> UnconstrainedEndPoseProblem::Update(x); t >= 0 -> TimeIndexedProblem::Update(x, t).
+ * phi[length_Phi], jac[length_jacobian x N] column-major (the Eigen::MatrixXd the reference exposes). */
+int exo_host_problem_update(exo_host_problem* problem, const double* x, int n, int t, double* phi, double* jac);
+/* NEW batched PlanningProblem::Update: E evaluations (E = B*T for time-indexed problems), host buffers. */
+int exo_host_problem_update_batch(exo_host_problem* problem, const double* x, int64_t n_evals, int layout, double* phi, double* jac);
+int exo_host_problem_update_batch_device(exo_host_problem* problem, const double* d_x, int64_t n_evals, int layout, double* d_phi,
+                                         double* d_jac, void* stream);
+int exo_host_problem_last_kernel_ms(exo_host_problem* problem, float* ms);
+int64_t exo_host_problem_launch_count(exo_host_problem* problem);
+int64_t exo_host_problem_update_count(exo_host_problem* problem); /* number_of_problem_updates_ */
+exo_problem* exo_host_problem_backend(exo_host_problem* problem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
