@@ -74,6 +74,8 @@ SYMBOLS = [
     ("exo_problem_launch_count", ctypes.c_int64, [_vp]),
     ("exo_problem_last_kernel_ms", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     ("exo_problem_program_info", ctypes.c_int, [_vp, _ip]),
+    ("exo_problem_set_kernel", ctypes.c_int, [_vp, ctypes.c_int]),
+    ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
 ]
 
 _LIB = None
@@ -295,6 +297,12 @@ class Problem(object):
 
     def launch_count(self):
         return int(lib().exo_problem_launch_count(self.h))
+
+    def set_kernel(self, choice):
+        check(lib().exo_problem_set_kernel(self.h, int(choice)))
+
+    def last_kernel(self):
+        return lib().exo_problem_last_kernel(self.h).decode()
 
     def update_batch_host(self, X, T=1, layout=LAYOUT_AOS_ROWMAJOR, want_jacobian=True, out_phi=None, out_jac=None):
         """Host arrays in, host arrays out (chunked copy/compute pipeline inside the library).

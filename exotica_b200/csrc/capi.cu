@@ -57,6 +57,8 @@ struct exo_problem
     double* d_generated = nullptr;
     // timing / accounting
     int64_t launches = 0;
+    int kernel_choice = 0;        // 0 auto (chain kernel when the program qualifies), 1 interpreter only
+    const char* last_kernel = "none";
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     // host pipeline
@@ -500,7 +502,8 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
     LaunchConfig cfg;
-    cudaError_t e = plan_launch(p->prog.hdr, k.program_bytes, E, cfg, k);
+    const bool chain = p->kernel_choice == 0 && chain_supported(p->prog.hdr);
+    cudaError_t e = chain ? plan_chain_launch(p->prog.hdr, k.program_bytes, E, cfg, k) : plan_launch(p->prog.hdr, k.program_bytes, E, cfg, k);
     if (e == cudaErrorInvalidConfiguration)
         return fail(EXO_ERR_UNSUPPORTED, "compiled program needs more shared memory per thread than one CTA can hold");
     if (e != cudaSuccess) return cuda_fail(e, "plan_launch");
@@ -513,8 +516,9 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         }
         CUDA_TRY(cudaEventRecord(p->ev0, stream));
     }
-    e = launch_eval(cfg, k, stream);
+    e = chain ? launch_chain(p->prog.hdr.chain_joints, cfg, k, stream) : launch_eval(cfg, k, stream);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    p->last_kernel = chain ? "exo_chain_kernel" : "exo_eval_kernel";
     if (timed)
     {
         CUDA_TRY(cudaEventRecord(p->ev1, stream));
@@ -541,6 +545,19 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
     CUDA_TRY(cudaEventSynchronize(p->ev1));
     CUDA_TRY(cudaEventElapsedTime(ms, p->ev0, p->ev1));
     return EXO_OK;
+}
+
+int exo_problem_set_kernel(exo_problem* p, int choice)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (choice < 0 || choice > 1) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto) or 1 (interpreter)");
+    p->kernel_choice = choice;
+    return EXO_OK;
+}
+
+const char* exo_problem_last_kernel(const exo_problem* p)
+{
+    return p ? p->last_kernel : "none";
 }
 
 int64_t exo_problem_launch_count(const exo_problem* p)

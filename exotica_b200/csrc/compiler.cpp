@@ -681,6 +681,14 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             }
             op.flags = flags;
             for (int c = 0; c < N; ++c) out.ints.push_back(patch_contrib(pl.contrib[c]));
+            // the same contributors keyed by joint-op ordinal (used by the chain kernel, whose joint data sits in
+            // registers indexed by ordinal): (column << 2) | flags
+            {
+                std::vector<int32_t> by_ord(n_ops, -1);
+                for (int c = 0; c < N; ++c)
+                    if (pl.contrib[c] >= 0) by_ord[pl.contrib[c] >> 2] = (c << 2) | (pl.contrib[c] & 3);
+                for (int k = 0; k < n_ops; ++k) out.ints.push_back(by_ord[k]);
+            }
         }
         else if (em.kind == OP_EMIT_JLIMIT)
         {
@@ -793,6 +801,35 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
     h.n_generated = t.n_generated;
     h.n_acc = n_acc_max;
     h.scratch_doubles = 12 * n_frame_slots + 6 * n_joint_slots + 6 * n_acc_max;
+    // chain eligibility: [JointLimit / fill emits]* [joint fed by its predecessor]+ [frame emits reading the final frame]*,
+    // nothing deferred to frame slots, frame B constant
+    {
+        bool chain = n_ops > 0 && n_frame_slots == 0;
+        int ordinal = 0;
+        for (const Op& op : out.ops)
+        {
+            if (op.kind == OP_JOINT)
+            {
+                if (op.src != (ordinal == 0 ? SRC_ROOT : SRC_CUR)) chain = false;
+                ++ordinal;
+            }
+            else if (op.kind == OP_TABLE || op.kind == OP_EMIT_SPHERES)
+                chain = false;
+            else if (op.kind == OP_EMIT_FRAME)
+            {
+                if (op.src != SRC_CUR || op.src_b != SRC_ROOT || ordinal != n_ops) chain = false;
+            }
+            else if (op.kind == OP_EMIT_JLIMIT || op.kind == OP_EMIT_FILL)
+            {
+                if (ordinal != 0) chain = false;
+            }
+        }
+        h.chain_joints = chain ? n_ops : 0;
+        h.chain_tab = (int)out.ints.size();
+        for (int i = 0; i < (int)out.ops.size(); ++i)
+            if (out.ops[i].kind == OP_JOINT || out.ops[i].kind == OP_TABLE) out.ints.push_back(i);
+        h.n_int = (int)out.ints.size();
+    }
 
     // image
     size_t off = sizeof(ProgramHeader) + out.ops.size() * sizeof(Op) + out.ints.size() * sizeof(int32_t);

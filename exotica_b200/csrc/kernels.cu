@@ -13,245 +13,14 @@
 // exactly once (zeros included), so no memset pass is needed.  HBM-bound FP64 streaming work: no tensor cores.
 #include "kernels.cuh"
 
-#include <math_constants.h>
-
-#include "../../include/exotica_b200.h"
+#include "device_math.cuh"
 
 namespace exo
 {
 namespace
 {
 
-struct Fr
-{
-    double m0, m1, m2, m3, m4, m5, m6, m7, m8;  // row-major rotation
-    double x, y, z;
-};
-
-__device__ __forceinline__ Fr fr_identity()
-{
-    Fr f;
-    f.m0 = 1.0; f.m1 = 0.0; f.m2 = 0.0;
-    f.m3 = 0.0; f.m4 = 1.0; f.m5 = 0.0;
-    f.m6 = 0.0; f.m7 = 0.0; f.m8 = 1.0;
-    f.x = f.y = f.z = 0.0;
-    return f;
-}
-
-template <int TPB>
-__device__ __forceinline__ Fr fr_load_scratch(const double* s)
-{
-    Fr f;
-    f.m0 = s[0 * TPB]; f.m1 = s[1 * TPB]; f.m2 = s[2 * TPB];
-    f.m3 = s[3 * TPB]; f.m4 = s[4 * TPB]; f.m5 = s[5 * TPB];
-    f.m6 = s[6 * TPB]; f.m7 = s[7 * TPB]; f.m8 = s[8 * TPB];
-    f.x = s[9 * TPB]; f.y = s[10 * TPB]; f.z = s[11 * TPB];
-    return f;
-}
-
-template <int TPB>
-__device__ __forceinline__ void fr_store_scratch(double* s, const Fr& f)
-{
-    s[0 * TPB] = f.m0; s[1 * TPB] = f.m1; s[2 * TPB] = f.m2;
-    s[3 * TPB] = f.m3; s[4 * TPB] = f.m4; s[5 * TPB] = f.m5;
-    s[6 * TPB] = f.m6; s[7 * TPB] = f.m7; s[8 * TPB] = f.m8;
-    s[9 * TPB] = f.x; s[10 * TPB] = f.y; s[11 * TPB] = f.z;
-}
-
-__device__ __forceinline__ Fr fr_load_const(const double* c)
-{
-    Fr f;
-    f.m0 = c[0]; f.m1 = c[1]; f.m2 = c[2];
-    f.m3 = c[3]; f.m4 = c[4]; f.m5 = c[5];
-    f.m6 = c[6]; f.m7 = c[7]; f.m8 = c[8];
-    f.x = c[9]; f.y = c[10]; f.z = c[11];
-    return f;
-}
-
-// a * b  (Frame * Frame = (Ma Mb, Ma pb + pa))
-__device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b)
-{
-    Fr r;
-    r.m0 = a.m0 * b.m0 + a.m1 * b.m3 + a.m2 * b.m6;
-    r.m1 = a.m0 * b.m1 + a.m1 * b.m4 + a.m2 * b.m7;
-    r.m2 = a.m0 * b.m2 + a.m1 * b.m5 + a.m2 * b.m8;
-    r.m3 = a.m3 * b.m0 + a.m4 * b.m3 + a.m5 * b.m6;
-    r.m4 = a.m3 * b.m1 + a.m4 * b.m4 + a.m5 * b.m7;
-    r.m5 = a.m3 * b.m2 + a.m4 * b.m5 + a.m5 * b.m8;
-    r.m6 = a.m6 * b.m0 + a.m7 * b.m3 + a.m8 * b.m6;
-    r.m7 = a.m6 * b.m1 + a.m7 * b.m4 + a.m8 * b.m7;
-    r.m8 = a.m6 * b.m2 + a.m7 * b.m5 + a.m8 * b.m8;
-    r.x = a.m0 * b.x + a.m1 * b.y + a.m2 * b.z + a.x;
-    r.y = a.m3 * b.x + a.m4 * b.y + a.m5 * b.z + a.y;
-    r.z = a.m6 * b.x + a.m7 * b.y + a.m8 * b.z + a.z;
-    return r;
-}
-
-// a * (I, t)
-__device__ __forceinline__ void fr_translate(Fr& a, double tx, double ty, double tz)
-{
-    a.x += a.m0 * tx + a.m1 * ty + a.m2 * tz;
-    a.y += a.m3 * tx + a.m4 * ty + a.m5 * tz;
-    a.z += a.m6 * tx + a.m7 * ty + a.m8 * tz;
-}
-
-__device__ __forceinline__ Fr fr_inverse(const Fr& a)
-{
-    Fr r;
-    r.m0 = a.m0; r.m1 = a.m3; r.m2 = a.m6;
-    r.m3 = a.m1; r.m4 = a.m4; r.m5 = a.m7;
-    r.m6 = a.m2; r.m7 = a.m5; r.m8 = a.m8;
-    r.x = -(a.m0 * a.x + a.m3 * a.y + a.m6 * a.z);
-    r.y = -(a.m1 * a.x + a.m4 * a.y + a.m7 * a.z);
-    r.z = -(a.m2 * a.x + a.m5 * a.y + a.m8 * a.z);
-    return r;
-}
-
-// ---- rotation encodings: exotica::SetRotation (exotica_core/src/tools/conversions.cpp:150-179) over KDL / Eigen ----
-__device__ __forceinline__ void get_rpy(const Fr& f, double& roll, double& pitch, double& yaw)
-{
-    // KDL::Rotation::GetRPY, including the gimbal-lock branch at |pitch| > pi/2 - 1e-12
-    pitch = atan2(-f.m6, sqrt(f.m0 * f.m0 + f.m3 * f.m3));
-    if (fabs(pitch) > (CUDART_PIO2 - 1e-12))
-    {
-        yaw = atan2(-f.m1, f.m4);
-        roll = 0.0;
-    }
-    else
-    {
-        roll = atan2(f.m7, f.m8);
-        yaw = atan2(f.m3, f.m0);
-    }
-}
-
-__device__ __forceinline__ void get_zyz(const Fr& f, double& alpha, double& beta, double& gamma)
-{
-    if (fabs(f.m8) > 1 - 1e-12)
-    {
-        gamma = 0.0;
-        if (f.m8 > 0)
-        {
-            beta = 0.0;
-            alpha = atan2(f.m3, f.m0);
-        }
-        else
-        {
-            beta = CUDART_PI;
-            alpha = atan2(-f.m3, -f.m0);
-        }
-    }
-    else
-    {
-        alpha = atan2(f.m5, f.m2);
-        beta = atan2(sqrt(f.m6 * f.m6 + f.m7 * f.m7), f.m8);
-        gamma = atan2(f.m7, -f.m6);
-    }
-}
-
-__device__ __forceinline__ double norm3_scaled(double a, double b, double c)
-{
-    // KDL::Vector::Norm (scaled form)
-    double t1 = fabs(a), t2 = fabs(b);
-    if (t1 >= t2)
-    {
-        t2 = fabs(c);
-        if (t1 >= t2)
-        {
-            if (t1 == 0) return 0;
-            return t1 * sqrt(1 + (b / a) * (b / a) + (c / a) * (c / a));
-        }
-        return t2 * sqrt(1 + (a / c) * (a / c) + (b / c) * (b / c));
-    }
-    t1 = fabs(c);
-    if (t2 > t1) return t2 * sqrt(1 + (a / b) * (a / b) + (c / b) * (c / b));
-    return t1 * sqrt(1 + (a / c) * (a / c) + (b / c) * (b / c));
-}
-
-__device__ __noinline__ void get_angle_axis(const Fr& f, double& ox, double& oy, double& oz)
-{
-    // KDL::Rotation::GetRot = axis * angle with GetRotAngle's symmetric-matrix handling
-    const double eps = 1e-6, eps2 = 1e-5;
-    double x, y, z, angle;
-    if ((fabs(f.m1 - f.m3) < eps) && (fabs(f.m2 - f.m6) < eps) && (fabs(f.m5 - f.m7) < eps))
-    {
-        if ((fabs(f.m1 + f.m3) < eps2) && (fabs(f.m2 + f.m6) < eps2) && (fabs(f.m5 + f.m7) < eps2) && (fabs(f.m0 + f.m4 + f.m8 - 3) < eps2))
-        {
-            ox = oy = oz = 0.0;
-            return;
-        }
-        angle = CUDART_PI;
-        const double xx = (f.m0 + 1) / 2, yy = (f.m4 + 1) / 2, zz = (f.m8 + 1) / 2;
-        const double xy = (f.m1 + f.m3) / 4, xz = (f.m2 + f.m6) / 4, yz = (f.m5 + f.m7) / 4;
-        if ((xx > yy) && (xx > zz))
-        {
-            x = sqrt(xx);
-            y = xy / x;
-            z = xz / x;
-        }
-        else if (yy > zz)
-        {
-            y = sqrt(yy);
-            x = xy / y;
-            z = yz / y;
-        }
-        else
-        {
-            z = sqrt(zz);
-            x = xz / z;
-            y = yz / z;
-        }
-    }
-    else
-    {
-        double c = (f.m0 + f.m4 + f.m8 - 1) / 2;
-        c = fmin(1.0, fmax(-1.0, c));
-        angle = acos(c);
-        x = f.m7 - f.m5;
-        y = f.m2 - f.m6;
-        z = f.m3 - f.m1;
-        const double nrm = norm3_scaled(x, y, z);
-        x /= nrm;
-        y /= nrm;
-        z /= nrm;
-    }
-    ox = x * angle;
-    oy = y * angle;
-    oz = z * angle;
-}
-
-__device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y z w */)
-{
-    // Eigen::Quaterniond(Matrix3d).coeffs()
-    const double m[9] = {f.m0, f.m1, f.m2, f.m3, f.m4, f.m5, f.m6, f.m7, f.m8};
-    double t = m[0] + m[4] + m[8];
-    if (t > 0.0)
-    {
-        t = sqrt(t + 1.0);
-        q[3] = 0.5 * t;
-        t = 0.5 / t;
-        q[0] = (m[7] - m[5]) * t;
-        q[1] = (m[2] - m[6]) * t;
-        q[2] = (m[3] - m[1]) * t;
-    }
-    else
-    {
-        int i = 0;
-        if (m[4] > m[0]) i = 1;
-        if (m[8] > m[4 * i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
-        double qi = 0.5 * t;
-        t = 0.5 / t;
-        const double qw = (m[3 * k + j] - m[3 * j + k]) * t;
-        const double qj = (m[3 * j + i] + m[3 * i + j]) * t;
-        const double qk = (m[3 * k + i] + m[3 * i + k]) * t;
-        // scatter without dynamic register indexing
-        q[0] = (i == 0) ? qi : ((j == 0) ? qj : qk);
-        q[1] = (i == 1) ? qi : ((j == 1) ? qj : qk);
-        q[2] = (i == 2) ? qi : ((j == 2) ? qj : qk);
-        q[3] = qw;
-    }
-}
+using namespace dev;
 
 template <int TPB>
 __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
@@ -436,64 +205,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                     }
                     Phi = fr_mul(Binv, A);
                 }
-                double* ph = phi_e + (int64_t)op.phi_off * P.phi_sk;
-                const int64_t sk = P.phi_sk;
-                if (op.map_kind == EXO_MAP_FRAMES)
-                {
-                    ph[0] = Phi.m0; ph[sk] = Phi.m1; ph[2 * sk] = Phi.m2; ph[3 * sk] = Phi.m3; ph[4 * sk] = Phi.m4;
-                    ph[5 * sk] = Phi.m5; ph[6 * sk] = Phi.m6; ph[7 * sk] = Phi.m7; ph[8 * sk] = Phi.m8;
-                    ph[9 * sk] = Phi.x; ph[10 * sk] = Phi.y; ph[11 * sk] = Phi.z;
-                }
-                else
-                {
-                    ph[0] = Phi.x; ph[sk] = Phi.y; ph[2 * sk] = Phi.z;
-                    if (op.map_kind == EXO_MAP_EFF_FRAME)
-                    {
-                        ph += 3 * sk;
-                        switch (op.rot_type)
-                        {
-                            case EXO_ROT_RPY:
-                            {
-                                double r, p, y;
-                                get_rpy(Phi, r, p, y);
-                                ph[0] = r; ph[sk] = p; ph[2 * sk] = y;
-                                break;
-                            }
-                            case EXO_ROT_ZYX:
-                            {
-                                double r, p, y;
-                                get_rpy(Phi, r, p, y);  // GetEulerZYX(a,b,c) == GetRPY(c,b,a)
-                                ph[0] = y; ph[sk] = p; ph[2 * sk] = r;
-                                break;
-                            }
-                            case EXO_ROT_ZYZ:
-                            {
-                                double a, b, g;
-                                get_zyz(Phi, a, b, g);
-                                ph[0] = a; ph[sk] = b; ph[2 * sk] = g;
-                                break;
-                            }
-                            case EXO_ROT_ANGLE_AXIS:
-                            {
-                                double a, b, g;
-                                get_angle_axis(Phi, a, b, g);
-                                ph[0] = a; ph[sk] = b; ph[2 * sk] = g;
-                                break;
-                            }
-                            case EXO_ROT_QUATERNION:
-                            {
-                                double q[4];
-                                get_quaternion(Phi, q);
-                                ph[0] = q[0]; ph[sk] = q[1]; ph[2 * sk] = q[2]; ph[3 * sk] = q[3];
-                                break;
-                            }
-                            default:  // EXO_ROT_MATRIX
-                                ph[0] = Phi.m0; ph[sk] = Phi.m1; ph[2 * sk] = Phi.m2; ph[3 * sk] = Phi.m3; ph[4 * sk] = Phi.m4;
-                                ph[5 * sk] = Phi.m5; ph[6 * sk] = Phi.m6; ph[7 * sk] = Phi.m7; ph[8 * sk] = Phi.m8;
-                                break;
-                        }
-                    }
-                }
+                write_phi(op.map_kind, op.rot_type, Phi, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk);
                 if (want_j)
                 {
                     // ComputeJ (kinematic_tree.cpp:919-945): column c = temp_B.M^-1 * [ w x (temp_A.p - p_joint) ; w ]
@@ -550,38 +262,11 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
             }
             else if (op.kind == OP_EMIT_JLIMIT)
             {
-                // JointLimit::Update (joint_limit.cpp:63-99); phi starts from the SetZero value 0
-                const double safe = c[0];
-                const double* lo = c + 1;
-                const double* hi = c + 1 + N;
-                double* ph = phi_e + (int64_t)op.phi_off * P.phi_sk;
-                double* jr = want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr;
-                for (int i = 0; i < N; ++i)
-                {
-                    const double q = qs[i * TPB];
-                    const double tau = (0.5 * safe) * (hi[i] - lo[i]);
-                    double v = 0.0;
-                    if (q < lo[i] + tau) v = q - lo[i] - tau;
-                    if (q > hi[i] - tau) v = q - hi[i] + tau;
-                    ph[i * P.phi_sk] = v;
-                    if (want_j)
-                    {
-                        const double d = (q >= lo[i] + tau && q <= hi[i] - tau) ? 0.0 : 1.0;
-                        double* row = jr + (int64_t)i * P.j_sr;
-                        for (int col = 0; col < N; ++col) row[(int64_t)col * P.j_sc] = (col == i) ? d : 0.0;
-                    }
-                }
+                emit_joint_limit(c, N, qs, TPB, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
             }
             else if (op.kind == OP_EMIT_FILL)
             {
-                double* ph = phi_e + (int64_t)op.phi_off * P.phi_sk;
-                for (int i = 0; i < op.n_items; ++i) ph[i * P.phi_sk] = c[i];
-                if (want_j)
-                {
-                    double* jr = jac_e + (int64_t)op.jrow_off * P.j_sr;
-                    for (int r = 0; r < op.n_rows; ++r)
-                        for (int col = 0; col < N; ++col) jr[(int64_t)r * P.j_sr + (int64_t)col * P.j_sc] = 0.0;
-                }
+                emit_fill(c, op.n_items, op.n_rows, N, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
             }
             else if (op.kind == OP_EMIT_SPHERES)
             {

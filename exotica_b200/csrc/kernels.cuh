@@ -36,4 +36,9 @@ struct LaunchConfig
 cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params);
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
 
+// Register-resident kernel for serial-chain programs (chain_kernel.cu)
+bool chain_supported(const ProgramHeader& hdr);
+cudaError_t plan_chain_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params);
+cudaError_t launch_chain(int chain_joints, const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
+
 }  // namespace exo

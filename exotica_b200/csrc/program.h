@@ -109,7 +109,9 @@ enum
     CE_B_P = 21,
     CE_SIZE = 24
 };
-// contributor table entry (one per Jacobian column): -1 none, else (jslot << 2) | (prismatic << 1) | negative
+// EMIT_FRAME int table: [N] contributor entries by Jacobian column, then [n_joint_ops] entries by joint-op ordinal.
+// column entry: -1 none, else (jslot << 2) | (prismatic << 1) | negative
+// ordinal entry: -1 none, else (column << 2) | (prismatic << 1) | negative
 static inline int32_t contrib_pack(int jslot, bool prismatic, bool negative) { return (jslot << 2) | (prismatic ? 2 : 0) | (negative ? 1 : 0); }
 
 // OP_EMIT_SPHERES int table layout (per sphere, 4 ints): anchor frame source, anchor accumulator index (-1 if
@@ -133,7 +135,10 @@ struct ProgramHeader
     int32_t n_generated;
     int32_t n_acc;        // sphere wrench accumulators (per-thread scratch, 6 doubles each)
     int32_t scratch_doubles;  // per-thread scratch size in doubles (excluding the q staging)
-    int32_t pad;
+    int32_t chain_joints;     // > 0: the program is a serial chain of that many joint ops and qualifies for the
+                              // register-resident chain kernel (chain_kernel.cu); 0 otherwise
+    int32_t chain_tab;        // offset into the int pool of the op index of every joint ordinal (chain programs)
+    int32_t pad[3];
 };
 
 }  // namespace exo

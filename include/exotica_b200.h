@@ -193,6 +193,12 @@ int64_t exo_problem_launch_count(const exo_problem* problem);
  * launching stream; blocks until that launch finished). */
 int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
 
+/* Kernel selection: 0 = auto (the register-resident chain kernel when the compiled program is a serial chain of at
+ * most 8 joints, else the general interpreter), 1 = always the interpreter (tests compare both). */
+int exo_problem_set_kernel(exo_problem* problem, int choice);
+/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "none"). */
+const char* exo_problem_last_kernel(const exo_problem* problem);
+
 /* Introspection of the compiled program (tests / DESIGN.md): number of joint ops, emit ops, frame slots,
  * joint slots, shared-memory bytes per thread. */
 int exo_problem_program_info(const exo_problem* problem, int32_t out[8]);

@@ -26,12 +26,17 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
         prob.set_generated(generated)
     assert prob.length_phi == orc.length_phi and prob.length_jacobian == orc.length_jacobian
     phi_ref, jac_ref = orc.problem_update_batch(X, T=T, generated=generated)
-    phi, jac = run_gpu(prob, X, layout=layout, T=T)
     wrap = angle_entries(maps, orc)
-    e_phi = max_abs_err(phi, phi_ref, wrap)
-    e_jac = max_abs_err(jac, jac_ref)
-    assert e_phi <= tol, "Phi error %g" % e_phi
-    assert e_jac <= tol, "J error %g" % e_jac
+    kernels = set()
+    for choice in (1, 0):  # 1: general interpreter, 0: auto (register-resident chain kernel when the program qualifies)
+        prob.set_kernel(choice)
+        phi, jac = run_gpu(prob, X, layout=layout, T=T)
+        kernels.add(prob.last_kernel())
+        e_phi = max_abs_err(phi, phi_ref, wrap)
+        e_jac = max_abs_err(jac, jac_ref)
+        assert e_phi <= tol, "Phi error %g (%s)" % (e_phi, prob.last_kernel())
+        assert e_jac <= tol, "J error %g (%s)" % (e_jac, prob.last_kernel())
+    prob.kernels_used = kernels
     return prob, phi, jac
 
 
@@ -58,6 +63,7 @@ def test_lwr_example_ik_config(oracle_lib):
              "LinkOffset": [0, 0, 0, 0.7071067811865476, -4.3297802811774664e-17, 0.7071067811865475, 4.3297802811774664e-17]}]}]
     X = np.vstack([np.zeros((1, 7)), random_states(orc, 1023, seed=3)])
     prob, phi, jac = _check(orc, maps, X)
+    assert prob.kernels_used == {"exo_eval_kernel", "exo_chain_kernel"}
     assert np.all(jac[:, :, 6] == 0.0)  # joint 6 moves link 7 only
 
 
