@@ -74,6 +74,7 @@ SYMBOLS = [
     ("exo_problem_launch_count", ctypes.c_int64, [_vp]),
     ("exo_problem_last_kernel_ms", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     ("exo_problem_program_info", ctypes.c_int, [_vp, _ip]),
+    ("exo_problem_chain_info", ctypes.c_int, [_vp, _ip]),
     ("exo_problem_set_kernel", ctypes.c_int, [_vp, ctypes.c_int]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
 ]
@@ -297,6 +298,11 @@ class Problem(object):
 
     def launch_count(self):
         return int(lib().exo_problem_launch_count(self.h))
+
+    def chain_info(self):
+        out = (ctypes.c_int32 * 4)()
+        check(lib().exo_problem_chain_info(self.h, out))
+        return {"lowered": bool(out[0]), "joints": out[1], "all_revolute": bool(out[2]), "frames": out[3]}
 
     def set_kernel(self, choice):
         check(lib().exo_problem_set_kernel(self.h, int(choice)))

@@ -57,7 +57,12 @@ struct exo_problem
     double* d_generated = nullptr;
     // timing / accounting
     int64_t launches = 0;
-    int kernel_choice = 0;        // 0 auto (chain kernel when the program qualifies), 1 interpreter only
+    int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..4 chain kernel variants (CHAIN_REGS, CHAIN_STASH, CHAIN_TWO_PASS)
+    bool chain_ok = false;        // the compiled program lowered to ChainParams
+    ChainParams chain;            // problem constants of the chain kernel (buffers / strides filled per launch)
+    bool plan_valid = false;      // interpreter launch plan (depends on the program only)
+    LaunchConfig plan_cfg;
+    int32_t plan_scratch_offset = 0;
     const char* last_kernel = "none";
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -365,6 +370,8 @@ static int compile_and_upload(exo_problem* p)
         p->d_image_bytes = p->prog.image.size();
     }
     CUDA_TRY(cudaMemcpy(p->d_image, p->prog.image.data(), p->prog.image.size(), cudaMemcpyHostToDevice));
+    p->chain_ok = chain_lower(p->prog, p->chain);
+    p->plan_valid = false;
     p->compiled_version = p->tree->version;
     return EXO_OK;
 }
@@ -380,6 +387,7 @@ int exo_problem_finalize(exo_problem* p)
     Program prog;
     if (!compile_program(p->tree->model, p->maps, prog, err)) return fail(EXO_ERR_INVALID, err);
     p->prog = prog;
+    p->chain_ok = chain_lower(p->prog, p->chain);
     p->finalized = true;
     p->compiled_version = -1;  // device upload happens lazily at the first update (needs a GPU)
     return EXO_OK;
@@ -424,6 +432,17 @@ int exo_problem_program_info(const exo_problem* p, int32_t out[8])
     out[5] = (int32_t)p->prog.image.size();
     out[6] = p->prog.hdr.n_acc;
     out[7] = p->prog.hdr.n_ops;
+    return EXO_OK;
+}
+
+int exo_problem_chain_info(const exo_problem* p, int32_t out[4])
+{
+    if (!p || !out) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    out[0] = p->chain_ok ? 1 : 0;
+    out[1] = p->chain_ok ? p->chain.n_joints : 0;
+    out[2] = p->chain_ok ? p->chain.all_revolute : 0;
+    out[3] = p->chain_ok ? p->chain.n_frames : 0;
     return EXO_OK;
 }
 
@@ -501,12 +520,25 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     k.n_evals = E;
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
+    const bool chain = p->chain_ok && p->kernel_choice != 1;
+    if (!chain && p->kernel_choice >= 2) return fail(EXO_ERR_UNSUPPORTED, "the compiled program is not a serial chain: the chain kernel cannot run it");
     LaunchConfig cfg;
-    const bool chain = p->kernel_choice == 0 && chain_supported(p->prog.hdr);
-    cudaError_t e = chain ? plan_chain_launch(p->prog.hdr, k.program_bytes, E, cfg, k) : plan_launch(p->prog.hdr, k.program_bytes, E, cfg, k);
-    if (e == cudaErrorInvalidConfiguration)
-        return fail(EXO_ERR_UNSUPPORTED, "compiled program needs more shared memory per thread than one CTA can hold");
-    if (e != cudaSuccess) return cuda_fail(e, "plan_launch");
+    if (!chain)
+    {
+        if (!p->plan_valid)
+        {
+            cudaError_t e = plan_launch(p->prog.hdr, k.program_bytes, (int64_t)1 << 40, p->plan_cfg, k);
+            if (e == cudaErrorInvalidConfiguration)
+                return fail(EXO_ERR_UNSUPPORTED, "compiled program needs more shared memory per thread than one CTA can hold");
+            if (e != cudaSuccess) return cuda_fail(e, "plan_launch");
+            p->plan_scratch_offset = k.scratch_offset;
+            p->plan_valid = true;
+        }
+        cfg = p->plan_cfg;
+        k.scratch_offset = p->plan_scratch_offset;
+        const int64_t want = (E + cfg.threads - 1) / cfg.threads;
+        if (want < cfg.blocks) cfg.blocks = (int)want;
+    }
     if (timed)
     {
         if (!p->ev0)
@@ -516,7 +548,14 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         }
         CUDA_TRY(cudaEventRecord(p->ev0, stream));
     }
-    e = chain ? launch_chain(p->prog.hdr.chain_joints, cfg, k, stream) : launch_eval(cfg, k, stream);
+    cudaError_t e;
+    if (chain)
+    {
+        chain_bind(p->chain, k.x, k.phi, k.jac, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
+        e = chain_launch(p->chain, p->kernel_choice >= 2 ? p->kernel_choice - 2 : CHAIN_DEFAULT, stream);
+    }
+    else
+        e = launch_eval(cfg, k, stream);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     p->last_kernel = chain ? "exo_chain_kernel" : "exo_eval_kernel";
     if (timed)
@@ -550,7 +589,7 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 1) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto) or 1 (interpreter)");
+    if (choice < 0 || choice > 4) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter) or 2..4 (chain kernel variants)");
     p->kernel_choice = choice;
     return EXO_OK;
 }

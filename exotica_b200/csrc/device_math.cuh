@@ -97,6 +97,64 @@ __device__ __forceinline__ Fr fr_inverse(const Fr& a)
     return r;
 }
 
+// ---- sin/cos ---------------------------------------------------------------------------------------------------------
+// Cody-Waite reduction by pi/2 (three FMAs, exact products) + fdlibm's __kernel_sin/__kernel_cos minimax polynomials on
+// [-pi/4, pi/4] (< 1 ulp).  Coefficients sit in __constant__ memory so that they reach the FP64 pipe through uniform
+// registers (one 128-bit constant load per pair) instead of two 32-bit immediates per double.
+__constant__ double kTrig[16] = {
+    6.36619772367581382433e-01,   // 0: 2/pi
+    1.57079632679489655800e+00,   // 1: pi/2 rounded to double
+    6.123233995736757e-17,        // 2: 0x3c91a62633145c00, leading bits of pi/2 - [1]
+    8.478427660368898e-32,        // 3: 0x397b839a252049c0, pi/2 - [1] - [2]
+    -1.66666666666666324348e-01,  // 4: S1
+    8.33333333332248946124e-03,   // 5: S2
+    -1.98412698298579493134e-04,  // 6: S3
+    2.75573137070700676789e-06,   // 7: S4
+    -2.50507602534068634195e-08,  // 8: S5
+    1.58969099521155010221e-10,   // 9: S6
+    4.16666666666666019037e-02,   // 10: C1
+    -1.38888888888741095749e-03,  // 11: C2
+    2.48015872894767294178e-05,   // 12: C3
+    -2.75573143513906633035e-07,  // 13: C4
+    2.08757232129817482790e-09,   // 14: C5
+    -1.13596475577881948265e-11   // 15: C6
+};
+
+// Valid for |x| <= 1e5 (the reduction is exact there); callers route larger arguments to CUDA's sincos.
+__device__ __forceinline__ void fast_sincos(double x, double& s, double& c)
+{
+
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double t = fma(x, kTrig[0], magic);
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(-kd, kTrig[1], x);
+    r = fma(-kd, kTrig[2], r);
+    r = fma(-kd, kTrig[3], r);
+    const double z = r * r;
+    double ps = fma(z, kTrig[9], kTrig[8]);
+    double pc = fma(z, kTrig[15], kTrig[14]);
+    ps = fma(z, ps, kTrig[7]);
+    pc = fma(z, pc, kTrig[13]);
+    ps = fma(z, ps, kTrig[6]);
+    pc = fma(z, pc, kTrig[12]);
+    ps = fma(z, ps, kTrig[5]);
+    pc = fma(z, pc, kTrig[11]);
+    ps = fma(z, ps, kTrig[4]);
+    pc = fma(z, pc, kTrig[10]);
+    const double sr = fma(z * r, ps, r);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant k mod 4: (sin, cos) = (sr, cr), (cr, -sr), (-sr, -cr), (-cr, sr)
+    const bool swap = (k & 1) != 0;
+    double ss = swap ? cr : sr;
+    double cc = swap ? sr : cr;
+    // flip signs through the high word: sin negative for k mod 4 in {2,3}, cos negative for {1,2}
+    const int sflip = (k & 2) << 30;
+    const int cflip = ((k + 1) & 2) << 30;
+    s = __hiloint2double(__double2hiint(ss) ^ sflip, __double2loint(ss));
+    c = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
+}
+
 // ---- rotation encodings: exotica::SetRotation (exotica_core/src/tools/conversions.cpp:150-179) over KDL / Eigen ----
 __device__ __forceinline__ void get_rpy(const Fr& f, double& roll, double& pitch, double& yaw)
 {

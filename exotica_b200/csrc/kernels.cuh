@@ -36,9 +36,75 @@ struct LaunchConfig
 cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params);
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
 
-// Register-resident kernel for serial-chain programs (chain_kernel.cu)
-bool chain_supported(const ProgramHeader& hdr);
-cudaError_t plan_chain_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params);
-cudaError_t launch_chain(int chain_joints, const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
+// ---- constant-bank kernel for serial-chain programs (chain_kernel.cu) ------------------------------------------------
+constexpr int CH_MAXJ = 8;       // joints in the chain
+constexpr int CH_MAXF = 4;       // requested frames hanging off the chain tip
+constexpr int CH_MAXN = 16;      // controlled joints of the problem
+constexpr int CH_MAXFILLS = 2;   // unused maps
+constexpr int CH_MAXFILL = 16;   // Phi entries per unused map
+
+struct ChainJointP
+{
+    double ca, sa, a;  // Rx(alpha) * Tx(a) in front of the joint (unused for joint 0: the base frame holds it)
+    double th0;        // revolute: theta = th0 + qmult * x[qidx];  prismatic: constant rotation about z
+    double c0, s0;     // cos / sin of th0 (used by prismatic joints)
+    double d;          // translation along z after the joint (prismatic: d + qmult * x[qidx])
+    double qmult;      // 0 when the joint value does not depend on the state
+    int32_t qidx;      // state index feeding the joint (-1: none)
+    int32_t col;       // Jacobian column or -1
+    int32_t prismatic;
+    int32_t pad;
+    int64_t x_elem_off;     // qidx * x_sk            (filled per launch by chain_bind)
+    int64_t jcol_elem_off;  // col * j_sc
+};
+struct ChainFrameP
+{
+    double k[12];     // requested frame = D_{n-1} * k
+    double binv[12];  // inverse of the constant temp_B
+    int32_t k_kind;   // F_OFFA_NONE / F_OFFA_TRANS / F_OFFA_FULL
+    int32_t b_const;  // 0: temp_B is the identity
+    int32_t map_kind, rot_type, phi_off, jrow_off, n_rows, pad;
+    int64_t phi_elem_off;   // phi_off * phi_sk       (filled per launch by chain_bind)
+    int64_t jrow_elem_off;  // jrow_off * j_sr
+};
+struct ChainFillP
+{
+    double value[CH_MAXFILL];
+    int32_t phi_off, jrow_off, n_items, n_rows;
+};
+// Passed by value as the kernel parameter (constant bank 0): < 4 KB.
+struct ChainParams
+{
+    const double* x;
+    double* phi;
+    double* jac;  // may be NULL
+    int64_t n_evals;
+    int64_t x_se, x_sk, phi_se, phi_sk, j_se, j_sr, j_sc;
+    int32_t n_joints, n_ctrl, n_frames, n_fill;
+    int32_t has_prefix, jl_enabled, jl_phi_off, jl_jrow_off;
+    uint32_t zero_cols;
+    int32_t all_revolute;
+    double base[12];  // frame in front of joint 0, z axis = joint 0's axis
+    ChainJointP joint[CH_MAXJ];
+    ChainFrameP frame[CH_MAXF];
+    double jl_lo[CH_MAXN], jl_hi[CH_MAXN], jl_tau[CH_MAXN], jl_lo_tau[CH_MAXN], jl_hi_tau[CH_MAXN];
+    ChainFillP fill[CH_MAXFILLS];
+};
+static_assert(sizeof(ChainParams) <= 4000, "ChainParams must fit the classic 4 KB kernel parameter space");
+
+enum
+{
+    CHAIN_REGS = 0,      // one pass, every joint's axis and origin stay in registers until the Jacobian is emitted
+    CHAIN_STASH = 1,     // one pass, joint axes and origins parked in shared memory (fewer registers, more resident warps)
+    CHAIN_TWO_PASS = 2,  // the chain is recomposed for the Jacobian pass (nothing parked at all)
+    CHAIN_DEFAULT = CHAIN_REGS
+};
+struct Program;
+// Fills the problem constants of ChainParams from a chain-eligible program; false if the program does not qualify.
+bool chain_lower(const Program& prog, ChainParams& P);
+// Binds the buffers and strides of one launch (and the element offsets derived from them).
+void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64_t n_evals, int64_t x_se, int64_t x_sk, int64_t phi_se,
+                int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
+cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream);
 
 }  // namespace exo

@@ -193,8 +193,10 @@ int64_t exo_problem_launch_count(const exo_problem* problem);
  * launching stream; blocks until that launch finished). */
 int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
 
-/* Kernel selection: 0 = auto (the register-resident chain kernel when the compiled program is a serial chain of at
- * most 8 joints, else the general interpreter), 1 = always the interpreter (tests compare both). */
+/* Kernel selection: 0 = auto (the Denavit-Hartenberg chain kernel when the compiled program is a serial chain of at
+ * most 8 joints whose frames hang off the last link, else the general interpreter), 1 = always the interpreter,
+ * 2 / 3 / 4 = the chain kernel's variants (joint data in registers / parked in shared memory / chain composed twice;
+ * EXO_ERR_UNSUPPORTED at launch if the program is not a chain).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
 /* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);
@@ -202,6 +204,9 @@ const char* exo_problem_last_kernel(const exo_problem* problem);
 /* Introspection of the compiled program (tests / DESIGN.md): number of joint ops, emit ops, frame slots,
  * joint slots, shared-memory bytes per thread. */
 int exo_problem_program_info(const exo_problem* problem, int32_t out[8]);
+/* Whether the program was lowered to the Denavit-Hartenberg chain kernel: out = {lowered (0/1), joints in the chain,
+ * all joints revolute (0/1), requested frames}.  Host-only (valid after exo_problem_finalize, no device needed). */
+int exo_problem_chain_info(const exo_problem* problem, int32_t out[4]);
 
 #ifdef __cplusplus
 }

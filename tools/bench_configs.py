@@ -76,7 +76,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
-    ap.add_argument("--interpreter", action="store_true", help="force the general interpreter kernel")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 interpreter, 2 chain regs, 3 chain stash, 4 chain two-pass")
     args = ap.parse_args()
     peak = 6549.4
     try:
@@ -97,18 +97,25 @@ def main():
         dx, dphi, djac = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(E * LP), _capi.DeviceBuffer(E * LJ * N)
         dx.upload(X.T)
         backend = _host.lib().exo_host_problem_backend(prob._h)
-        if args.interpreter:
-            _capi.check(_capi.lib().exo_problem_set_kernel(backend, 1))
+        if args.kernel:
+            _capi.check(_capi.lib().exo_problem_set_kernel(backend, args.kernel))
         times = []
         for r in range(args.reps + 3):
-            prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=exo.LAYOUT_SOA)
+            try:
+                prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=exo.LAYOUT_SOA)
+            except Exception as ex:  # e.g. chain kernel forced on a tree program
+                print(json.dumps({"config": name, "kernel_choice": args.kernel, "skipped": str(ex)}), flush=True)
+                times = None
+                break
             ms = prob.last_kernel_ms()
             if r >= 3:
                 times.append(ms)
+        if times is None:
+            continue
         kernel = _capi.lib().exo_problem_last_kernel(backend).decode()
         med = float(np.median(times))
         gbs = bytes_per_eval * E / (med * 1e-3) / 1e9
-        print(json.dumps({"config": name, "evals": E, "N": N, "length_Phi": LP, "length_jacobian": LJ, "kernel": kernel, "ms_median": med,
+        print(json.dumps({"config": name, "evals": E, "N": N, "length_Phi": LP, "length_jacobian": LJ, "kernel": kernel, "kernel_choice": args.kernel, "ms_median": med,
                           "ms_best": float(np.min(times)), "evals_per_s": E / (med * 1e-3), "algorithmic_GBps": gbs,
                           "frac_of_measured_hbm": gbs / peak}), flush=True)
         dx.free()
