@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libexotica_b200.so")
+LIB_PATH = os.environ.get("EXO_B200_LIB") or os.path.join(_HERE, "lib", "libexotica_b200.so")  # env override: kernel tuning builds
 
 EXO_OK = 0
 LAYOUT_SOA, LAYOUT_AOS_ROWMAJOR, LAYOUT_AOS_COLMAJOR = 0, 1, 2

@@ -57,7 +57,7 @@ struct exo_problem
     double* d_generated = nullptr;
     // timing / accounting
     int64_t launches = 0;
-    int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..4 chain kernel variants (CHAIN_REGS, CHAIN_STASH, CHAIN_TWO_PASS)
+    int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..3 chain kernel variants (CHAIN_REGS, CHAIN_TWO_PASS)
     bool chain_ok = false;        // the compiled program lowered to ChainParams
     ChainParams chain;            // problem constants of the chain kernel (buffers / strides filled per launch)
     bool plan_valid = false;      // interpreter launch plan (depends on the program only)
@@ -589,7 +589,7 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 4) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter) or 2..4 (chain kernel variants)");
+    if (choice < 0 || choice > 3) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter) or 2..3 (chain kernel variants)");
     p->kernel_choice = choice;
     return EXO_OK;
 }

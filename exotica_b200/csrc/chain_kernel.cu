@@ -20,12 +20,13 @@
 //
 // Variants (exo_problem_set_kernel; measured in DESIGN.md):
 //   CHAIN_REGS      every joint's world axis and origin stay in registers until the end-effector point is known
-//   CHAIN_STASH     they are parked in shared memory, [slot][thread] as double2 (conflict-free): fewer registers
-//   CHAIN_TWO_PASS  the chain is composed twice; the second pass emits each joint's column on the fly
+//   CHAIN_TWO_PASS  the chain is composed twice; the second pass emits each joint's column on the fly (one requested
+//                   frame; fewer registers, 30 more FP64 instructions per joint)
 //
 // Reference path replaced: KinematicTree::Update/UpdateTree/FK/ComputeJ (exotica_core/src/kinematic_tree.cpp:678-737,
 // 829-867,919-945) + EffFrame/EffPosition/JointLimit::Update (exotations/exotica_core_task_maps/src/*.cpp) +
 // Phi.SetZero/jacobian.setZero (exotica_core/src/problems/abstract_time_indexed_problem.cpp:243-244).
+#include <stdlib.h>
 #include <string.h>
 
 #include "compiler.h"
@@ -38,7 +39,10 @@ namespace
 {
 using namespace dev;
 
-constexpr int CTPB = 128;
+#ifndef EXO_CHAIN_CTPB
+#define EXO_CHAIN_CTPB 64
+#endif
+constexpr int CTPB = EXO_CHAIN_CTPB;
 
 struct Sink
 {
@@ -46,6 +50,19 @@ struct Sink
     double* jac;  // &J[e][0][0] or nullptr
     int64_t phi_sk, j_sr, j_sc;
 };
+
+__device__ __forceinline__ Fr load_frame(const double* c)
+{
+    Fr f;
+    f.m0 = c[0]; f.m1 = c[1]; f.m2 = c[2]; f.m3 = c[3]; f.m4 = c[4]; f.m5 = c[5];
+    f.m6 = c[6]; f.m7 = c[7]; f.m8 = c[8]; f.x = c[9]; f.y = c[10]; f.z = c[11];
+    return f;
+}
+
+__device__ __forceinline__ void st(char* p, double v)
+{
+    *reinterpret_cast<double*>(p) = v;
+}
 
 // Rx(alpha_J) * Tx(a_J) applied on the right of cur (joint 0: already part of the base frame)
 template <int J>
@@ -83,87 +100,72 @@ __device__ __forceinline__ void dh_joint(const ChainParams& P, Fr& cur, double s
     cur.z = fma(d, cur.m8, cur.z);
 }
 
-// Jacobian column of joint J for every requested frame (KinematicTree::ComputeJ, kinematic_tree.cpp:919-945):
+// Jacobian column of joint J for requested frame F (KinematicTree::ComputeJ, kinematic_tree.cpp:919-945):
 //   column = temp_B.M^-1 * [ w x (temp_A.p - p_joint) ; w ]   (revolute)   |   temp_B.M^-1 * [ w ; 0 ]   (prismatic)
-template <int J, bool ALLREV, int NF>
-__device__ __forceinline__ void chain_column(const ChainParams& P, const Sink& o, double wx, double wy, double wz, double px, double py,
-                                             double pz, const double (&pa)[NF][3])
+// WITHB / SIX are per-frame facts hoisted out of the joint loop by the caller.
+template <int J, bool ALLREV, bool WITHB, bool SIX>
+__device__ __forceinline__ void chain_column(const ChainParams& P, int f, char* jac_e, int64_t sr_b, double wx, double wy, double wz, double px,
+                                             double py, double pz, double ax, double ay, double az)
 {
     const ChainJointP& jp = P.joint[J];
     if (jp.col < 0) return;
-    const bool prismatic = !ALLREV && jp.prismatic;
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
+    const ChainFrameP& fp = P.frame[f];
+    double v0, v1, v2, w0, w1, w2;
+    if (!ALLREV && jp.prismatic)
     {
-        if (NF > 1 && f >= P.n_frames) break;
-        const ChainFrameP& fp = P.frame[f];
-        double v0, v1, v2, w0, w1, w2;
-        if (prismatic)
+        v0 = wx; v1 = wy; v2 = wz;
+        w0 = w1 = w2 = 0.0;
+    }
+    else
+    {
+        const double dx = ax - px, dy = ay - py, dz = az - pz;
+        v0 = wy * dz - wz * dy;
+        v1 = wz * dx - wx * dz;
+        v2 = wx * dy - wy * dx;
+        w0 = wx; w1 = wy; w2 = wz;
+    }
+    if (WITHB)
+    {
+        const double t0 = fp.binv[0] * v0 + fp.binv[1] * v1 + fp.binv[2] * v2;
+        const double t1 = fp.binv[3] * v0 + fp.binv[4] * v1 + fp.binv[5] * v2;
+        const double t2 = fp.binv[6] * v0 + fp.binv[7] * v1 + fp.binv[8] * v2;
+        v0 = t0; v1 = t1; v2 = t2;
+        if (SIX)
         {
-            v0 = wx; v1 = wy; v2 = wz;
-            w0 = w1 = w2 = 0.0;
-        }
-        else
-        {
-            const double dx = pa[f][0] - px, dy = pa[f][1] - py, dz = pa[f][2] - pz;
-            v0 = wy * dz - wz * dy;
-            v1 = wz * dx - wx * dz;
-            v2 = wx * dy - wy * dx;
-            w0 = wx; w1 = wy; w2 = wz;
-        }
-        if (fp.b_const)
-        {
-            const double t0 = fp.binv[0] * v0 + fp.binv[1] * v1 + fp.binv[2] * v2;
-            const double t1 = fp.binv[3] * v0 + fp.binv[4] * v1 + fp.binv[5] * v2;
-            const double t2 = fp.binv[6] * v0 + fp.binv[7] * v1 + fp.binv[8] * v2;
-            v0 = t0; v1 = t1; v2 = t2;
             const double u0 = fp.binv[0] * w0 + fp.binv[1] * w1 + fp.binv[2] * w2;
             const double u1 = fp.binv[3] * w0 + fp.binv[4] * w1 + fp.binv[5] * w2;
             const double u2 = fp.binv[6] * w0 + fp.binv[7] * w1 + fp.binv[8] * w2;
             w0 = u0; w1 = u1; w2 = u2;
         }
-        double* jc = o.jac + (fp.jrow_elem_off + jp.jcol_elem_off);
-        jc[0] = v0;
-        jc += o.j_sr; jc[0] = v1;
-        jc += o.j_sr; jc[0] = v2;
-        if (fp.n_rows == 6)
-        {
-            jc += o.j_sr; jc[0] = w0;
-            jc += o.j_sr; jc[0] = w1;
-            jc += o.j_sr; jc[0] = w2;
-        }
+    }
+    char* jc = jac_e + P.jf_byte_off[f][J];
+    st(jc, v0); jc += sr_b;
+    st(jc, v1); jc += sr_b;
+    st(jc, v2);
+    if (SIX)
+    {
+        jc += sr_b; st(jc, w0);
+        jc += sr_b; st(jc, w1);
+        jc += sr_b; st(jc, w2);
     }
 }
 
-// temp_A = D_{n-1} * K_f ; Phi = temp_B^-1 * temp_A ; write Phi ; remember temp_A.p for the Jacobian columns
-template <int NF>
-__device__ __forceinline__ void chain_frames(const ChainParams& P, const Sink& o, const Fr& tip, double (&pa)[NF][3])
+// temp_A = D_{n-1} * K_f
+__device__ __forceinline__ Fr chain_frame_a(const ChainFrameP& fp, const Fr& tip)
 {
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
-    {
-        if (NF > 1 && f >= P.n_frames) break;
-        const ChainFrameP& fp = P.frame[f];
-        Fr A = tip;
-        if (fp.k_kind == F_OFFA_TRANS)
-            fr_translate(A, fp.k[9], fp.k[10], fp.k[11]);
-        else if (fp.k_kind == F_OFFA_FULL)
-        {
-            Fr c;
-            c.m0 = fp.k[0]; c.m1 = fp.k[1]; c.m2 = fp.k[2]; c.m3 = fp.k[3]; c.m4 = fp.k[4]; c.m5 = fp.k[5];
-            c.m6 = fp.k[6]; c.m7 = fp.k[7]; c.m8 = fp.k[8]; c.x = fp.k[9]; c.y = fp.k[10]; c.z = fp.k[11];
-            A = fr_mul(A, c);
-        }
-        pa[f][0] = A.x; pa[f][1] = A.y; pa[f][2] = A.z;
-        if (fp.b_const)
-        {
-            Fr b;
-            b.m0 = fp.binv[0]; b.m1 = fp.binv[1]; b.m2 = fp.binv[2]; b.m3 = fp.binv[3]; b.m4 = fp.binv[4]; b.m5 = fp.binv[5];
-            b.m6 = fp.binv[6]; b.m7 = fp.binv[7]; b.m8 = fp.binv[8]; b.x = fp.binv[9]; b.y = fp.binv[10]; b.z = fp.binv[11];
-            A = fr_mul(b, A);
-        }
-        write_phi(fp.map_kind, fp.rot_type, A, o.phi + fp.phi_elem_off, o.phi_sk);
-    }
+    Fr A = tip;
+    if (fp.k_kind == F_OFFA_TRANS)
+        fr_translate(A, fp.k[9], fp.k[10], fp.k[11]);
+    else if (fp.k_kind == F_OFFA_FULL)
+        A = fr_mul(A, load_frame(fp.k));
+    return A;
+}
+
+// Phi = temp_B^-1 * temp_A, encoded as the task map wants it
+__device__ __forceinline__ void chain_frame_phi(const ChainFrameP& fp, Fr A, char* phi_e, int64_t phi_sk)
+{
+    if (fp.b_const) A = fr_mul(load_frame(fp.binv), A);
+    write_phi(fp.map_kind, fp.rot_type, A, reinterpret_cast<double*>(phi_e + fp.phi_byte_off), phi_sk);
 }
 
 // JointLimit::Update (joint_limit.cpp:63-99), unused-map fills (task_space_vector.cpp:54-62) and the Jacobian entries no
@@ -238,16 +240,14 @@ __device__ __noinline__ void chain_prefix(const ChainParams& P, const Sink& o, c
 // Whole evaluation with CUDA's sincos (Payne-Hanek reduction) and runtime loops: taken only when some joint angle exceeds
 // the range of the Cody-Waite reduction (|theta| > 1e5 rad).  Cold code, kept out of line so that it does not constrain
 // the register allocation of the hot loop.
-__device__ __noinline__ void chain_slow_eval(const ChainParams& P, const Sink& o, const double* xe)
+__device__ __noinline__ void chain_slow_eval(const ChainParams& P, const char* xe, char* phi_e, char* jac_e)
 {
-    Fr cur;
-    cur.m0 = P.base[0]; cur.m1 = P.base[1]; cur.m2 = P.base[2]; cur.m3 = P.base[3]; cur.m4 = P.base[4]; cur.m5 = P.base[5];
-    cur.m6 = P.base[6]; cur.m7 = P.base[7]; cur.m8 = P.base[8]; cur.x = P.base[9]; cur.y = P.base[10]; cur.z = P.base[11];
+    Fr cur = load_frame(P.base);
     double W[CH_MAXJ][3], PJ[CH_MAXJ][3];
     for (int j = 0; j < P.n_joints; ++j)
     {
         const ChainJointP& jp = P.joint[j];
-        const double xq = xe[jp.x_elem_off];
+        const double xq = *reinterpret_cast<const double*>(xe + jp.x_byte_off);
         if (j > 0)
         {
             Fr l = fr_identity();
@@ -267,16 +267,16 @@ __device__ __noinline__ void chain_slow_eval(const ChainParams& P, const Sink& o
         r.z = d;
         cur = fr_mul(cur, r);
     }
-    double pa[CH_MAXF][3];
-    chain_frames<CH_MAXF>(P, o, cur, pa);
-    if (!o.jac) return;
-    for (int j = 0; j < P.n_joints; ++j)
+    for (int f = 0; f < P.n_frames; ++f)
     {
-        const ChainJointP& jp = P.joint[j];
-        if (jp.col < 0) continue;
-        for (int f = 0; f < P.n_frames; ++f)
+        const ChainFrameP& fp = P.frame[f];
+        const Fr A = chain_frame_a(fp, cur);
+        chain_frame_phi(fp, A, phi_e, P.phi_sk);
+        if (!jac_e) continue;
+        for (int j = 0; j < P.n_joints; ++j)
         {
-            const ChainFrameP& fp = P.frame[f];
+            const ChainJointP& jp = P.joint[j];
+            if (jp.col < 0) continue;
             double v[3], w[3] = {0.0, 0.0, 0.0};
             if (jp.prismatic)
             {
@@ -284,26 +284,26 @@ __device__ __noinline__ void chain_slow_eval(const ChainParams& P, const Sink& o
             }
             else
             {
-                const double dx = pa[f][0] - PJ[j][0], dy = pa[f][1] - PJ[j][1], dz = pa[f][2] - PJ[j][2];
+                const double dx = A.x - PJ[j][0], dy = A.y - PJ[j][1], dz = A.z - PJ[j][2];
                 v[0] = W[j][1] * dz - W[j][2] * dy;
                 v[1] = W[j][2] * dx - W[j][0] * dz;
                 v[2] = W[j][0] * dy - W[j][1] * dx;
                 w[0] = W[j][0]; w[1] = W[j][1]; w[2] = W[j][2];
             }
-            double* jc = o.jac + (fp.jrow_elem_off + jp.jcol_elem_off);
+            char* jc = jac_e + P.jf_byte_off[f][j];
             for (int r = 0; r < fp.n_rows; ++r)
             {
                 const double* src = r < 3 ? v : w;
                 double val = src[r % 3];
                 if (fp.b_const) val = fp.binv[3 * (r % 3)] * src[0] + fp.binv[3 * (r % 3) + 1] * src[1] + fp.binv[3 * (r % 3) + 2] * src[2];
-                jc[0] = val;
-                jc += o.j_sr;
+                st(jc, val);
+                jc += P.j_sr_b;
             }
         }
     }
 }
 
-template <int NJ, bool ALLREV, int VARIANT, int NF, int J>
+template <int NJ, bool ALLREV, int J>
 struct ChainUnroll
 {
     // compose only (first pass of CHAIN_TWO_PASS)
@@ -312,70 +312,59 @@ struct ChainUnroll
     {
         dh_link<J>(P, cur);
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
-        ChainUnroll<NJ, ALLREV, VARIANT, NF, J + 1>::compose(P, cur, q, sn, cs);
+        ChainUnroll<NJ, ALLREV, J + 1>::compose(P, cur, q, sn, cs);
     }
-    // compose and emit the column of each joint (second pass of CHAIN_TWO_PASS)
-    static __device__ __forceinline__ void emit(const ChainParams& P, const Sink& o, Fr& cur, const double (&q)[NJ], const double (&sn)[NJ],
-                                                const double (&cs)[NJ], const double (&pa)[NF][3])
+    // compose and emit the column of each joint for frame 0 (second pass of CHAIN_TWO_PASS, one requested frame)
+    template <bool WITHB, bool SIX>
+    static __device__ __forceinline__ void emit(const ChainParams& P, char* jac_e, int64_t sr_b, Fr& cur, const double (&q)[NJ],
+                                                const double (&sn)[NJ], const double (&cs)[NJ], double ax, double ay, double az)
     {
         dh_link<J>(P, cur);
-        chain_column<J, ALLREV, NF>(P, o, cur.m2, cur.m5, cur.m8, cur.x, cur.y, cur.z, pa);
+        chain_column<J, ALLREV, WITHB, SIX>(P, 0, jac_e, sr_b, cur.m2, cur.m5, cur.m8, cur.x, cur.y, cur.z, ax, ay, az);
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
-        ChainUnroll<NJ, ALLREV, VARIANT, NF, J + 1>::emit(P, o, cur, q, sn, cs, pa);
+        ChainUnroll<NJ, ALLREV, J + 1>::template emit<WITHB, SIX>(P, jac_e, sr_b, cur, q, sn, cs, ax, ay, az);
     }
-    // one pass, joint data to registers (W, PJ) or to shared memory (stash)
-    static __device__ __forceinline__ void record(const ChainParams& P, Fr& cur, const double (&q)[NJ], const double (&th)[NJ], double (&W)[NJ][3],
-                                                  double (&PJ)[NJ][3], double2* stash)
+    // one pass: compose and keep every joint's axis and origin
+    static __device__ __forceinline__ void record(const ChainParams& P, Fr& cur, const double (&q)[NJ], const double (&sn)[NJ],
+                                                  const double (&cs)[NJ], double (&W)[NJ][3], double (&PJ)[NJ][3])
     {
-        double sn = 0.0, cs = 1.0;
-        if (ALLREV || !P.joint[J].prismatic) fast_sincos(th[J], sn, cs);
         dh_link<J>(P, cur);
-        if (VARIANT == CHAIN_STASH)
-        {
-            stash[(3 * J + 0) * CTPB] = make_double2(cur.m2, cur.m5);
-            stash[(3 * J + 1) * CTPB] = make_double2(cur.m8, cur.x);
-            stash[(3 * J + 2) * CTPB] = make_double2(cur.y, cur.z);
-        }
-        else
-        {
-            W[J][0] = cur.m2; W[J][1] = cur.m5; W[J][2] = cur.m8;
-            PJ[J][0] = cur.x; PJ[J][1] = cur.y; PJ[J][2] = cur.z;
-        }
-        dh_joint<J, ALLREV>(P, cur, sn, cs, q[J]);
-        ChainUnroll<NJ, ALLREV, VARIANT, NF, J + 1>::record(P, cur, q, th, W, PJ, stash);
+        W[J][0] = cur.m2; W[J][1] = cur.m5; W[J][2] = cur.m8;
+        PJ[J][0] = cur.x; PJ[J][1] = cur.y; PJ[J][2] = cur.z;
+        dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
+        ChainUnroll<NJ, ALLREV, J + 1>::record(P, cur, q, sn, cs, W, PJ);
     }
-    static __device__ __forceinline__ void columns(const ChainParams& P, const Sink& o, const double (&W)[NJ][3], const double (&PJ)[NJ][3],
-                                                   const double2* stash, const double (&pa)[NF][3])
+    template <bool WITHB, bool SIX>
+    static __device__ __forceinline__ void columns(const ChainParams& P, int f, char* jac_e, int64_t sr_b, const double (&W)[NJ][3],
+                                                   const double (&PJ)[NJ][3], double ax, double ay, double az)
     {
-        if (VARIANT == CHAIN_STASH)
-        {
-            const double2 a = stash[(3 * J + 0) * CTPB], b = stash[(3 * J + 1) * CTPB], c = stash[(3 * J + 2) * CTPB];
-            chain_column<J, ALLREV, NF>(P, o, a.x, a.y, b.x, b.y, c.x, c.y, pa);
-        }
-        else
-            chain_column<J, ALLREV, NF>(P, o, W[J][0], W[J][1], W[J][2], PJ[J][0], PJ[J][1], PJ[J][2], pa);
-        ChainUnroll<NJ, ALLREV, VARIANT, NF, J + 1>::columns(P, o, W, PJ, stash, pa);
+        chain_column<J, ALLREV, WITHB, SIX>(P, f, jac_e, sr_b, W[J][0], W[J][1], W[J][2], PJ[J][0], PJ[J][1], PJ[J][2], ax, ay, az);
+        ChainUnroll<NJ, ALLREV, J + 1>::template columns<WITHB, SIX>(P, f, jac_e, sr_b, W, PJ, ax, ay, az);
     }
 };
-template <int NJ, bool ALLREV, int VARIANT, int NF>
-struct ChainUnroll<NJ, ALLREV, VARIANT, NF, NJ>
+template <int NJ, bool ALLREV>
+struct ChainUnroll<NJ, ALLREV, NJ>
 {
     static __device__ __forceinline__ void compose(const ChainParams&, Fr&, const double (&)[NJ], const double (&)[NJ], const double (&)[NJ]) {}
-    static __device__ __forceinline__ void emit(const ChainParams&, const Sink&, Fr&, const double (&)[NJ], const double (&)[NJ],
-                                                const double (&)[NJ], const double (&)[NF][3]) {}
-    static __device__ __forceinline__ void record(const ChainParams&, Fr&, const double (&)[NJ], const double (&)[NJ], double (&)[NJ][3],
-                                                  double (&)[NJ][3], double2*) {}
-    static __device__ __forceinline__ void columns(const ChainParams&, const Sink&, const double (&)[NJ][3], const double (&)[NJ][3], const double2*,
-                                                   const double (&)[NF][3]) {}
+    template <bool WITHB, bool SIX>
+    static __device__ __forceinline__ void emit(const ChainParams&, char*, int64_t, Fr&, const double (&)[NJ], const double (&)[NJ],
+                                                const double (&)[NJ], double, double, double) {}
+    static __device__ __forceinline__ void record(const ChainParams&, Fr&, const double (&)[NJ], const double (&)[NJ], const double (&)[NJ],
+                                                  double (&)[NJ][3], double (&)[NJ][3]) {}
+    template <bool WITHB, bool SIX>
+    static __device__ __forceinline__ void columns(const ChainParams&, int, char*, int64_t, const double (&)[NJ][3], const double (&)[NJ][3], double,
+                                                   double, double) {}
 };
 
+// Register budget per variant (B200: 64 K registers per SM, CTAs of 64 threads): 144 registers -> 7 CTAs = 14 warps per
+// SM for CHAIN_REGS (no spills), 128 -> 8 CTAs = 16 warps for CHAIN_TWO_PASS.  Measured alternatives are in DESIGN.md.
 template <int VARIANT>
 struct ChainOcc
 {
-#ifdef EXO_CHAIN_MINB
-    static constexpr int min_blocks = EXO_CHAIN_MINB;
+#ifdef EXO_CHAIN_MAXNREG
+    static constexpr int maxnreg = EXO_CHAIN_MAXNREG;
 #else
-    static constexpr int min_blocks = VARIANT == CHAIN_REGS ? 3 : (VARIANT == CHAIN_STASH ? 5 : 4);
+    static constexpr int maxnreg = VARIANT == CHAIN_REGS ? 144 : 128;
 #endif
 };
 
@@ -384,115 +373,158 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int NJ, bool ALLREV, int VARIANT, int NF>
-__global__ void __launch_bounds__(CTPB, ChainOcc<VARIANT>::min_blocks) exo_chain_kernel(const __grid_constant__ ChainParams P)
+template <int NJ, bool ALLREV, int VARIANT>
+__global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const __grid_constant__ ChainParams P)
 {
-    extern __shared__ double2 stash_all[];
-    double2* stash = stash_all + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * CTPB;
-    const int64_t x_step = stride * P.x_se;
     int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x;
-    const double* xe = P.x + e * P.x_se;
-    for (; e < P.n_evals; e += stride, xe += x_step)
+    // running byte pointers of this lane's evaluation
+    const char* xe = reinterpret_cast<const char*>(P.x) + e * P.x_se_b;
+    char* phi_e = reinterpret_cast<char*>(P.phi) + e * P.phi_se_b;
+    char* jac_e = P.jac ? reinterpret_cast<char*>(P.jac) + e * P.j_se_b : nullptr;
+    const int64_t x_step = stride * P.x_se_b, phi_step = stride * P.phi_se_b, jac_step = P.jac ? stride * P.j_se_b : 0;
+    const int64_t sr_b = P.j_sr_b;
+    for (; e < P.n_evals; e += stride, xe += x_step, phi_e += phi_step, jac_e += jac_step)
     {
-        double q[NJ], th[NJ];
+        double q[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) q[j] = xe[P.joint[j].x_elem_off];
+        for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
         // pull the next evaluation's joint values into L2 while this one is computed (no registers held)
         if (e + stride < P.n_evals)
         {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) prefetch_l2(xe + x_step + P.joint[j].x_elem_off);
+            for (int j = 0; j < NJ; ++j) prefetch_l2(xe + x_step + P.joint[j].x_byte_off);
         }
-        Sink o;
-        o.phi = P.phi + e * P.phi_se;
-        o.jac = P.jac ? P.jac + e * P.j_se : nullptr;
-        o.phi_sk = P.phi_sk;
-        o.j_sr = P.j_sr;
-        o.j_sc = P.j_sc;
-        if (P.has_prefix) chain_prefix(P, o, xe, P.x_sk);
-
+        if (P.has_prefix)
+        {
+            Sink o;
+            o.phi = reinterpret_cast<double*>(phi_e);
+            o.jac = reinterpret_cast<double*>(jac_e);
+            o.phi_sk = P.phi_sk;
+            o.j_sr = P.j_sr;
+            o.j_sc = P.j_sc;
+            chain_prefix(P, o, reinterpret_cast<const double*>(xe), P.x_sk);
+        }
+        // all joint angles first: NJ independent sin/cos evaluations keep the FP64 pipe busy
+        double sn[NJ], cs[NJ];
         bool big = false;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
         {
-            th[j] = fma(P.joint[j].qmult, q[j], P.joint[j].th0);
-            big = big || !(fabs(th[j]) <= 1.0e5);
+            const double th = fma(P.joint[j].qmult, q[j], P.joint[j].th0);
+            big = big || !(fabs(th) <= 1.0e5);
+            sn[j] = 0.0;
+            cs[j] = 1.0;
+            if (ALLREV || !P.joint[j].prismatic) fast_sincos(th, sn[j], cs[j]);
         }
         if (big)
         {
-            chain_slow_eval(P, o, xe);
+            chain_slow_eval(P, xe, phi_e, jac_e);
             continue;
         }
-
-        Fr cur;
-        cur.m0 = P.base[0]; cur.m1 = P.base[1]; cur.m2 = P.base[2]; cur.m3 = P.base[3]; cur.m4 = P.base[4]; cur.m5 = P.base[5];
-        cur.m6 = P.base[6]; cur.m7 = P.base[7]; cur.m8 = P.base[8]; cur.x = P.base[9]; cur.y = P.base[10]; cur.z = P.base[11];
-        double pa[NF][3];
-        if (VARIANT == CHAIN_TWO_PASS)
+        Fr cur = load_frame(P.base);
+        if (VARIANT == CHAIN_TWO_PASS && P.n_frames == 1)
         {
-            double sn[NJ], cs[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
+            ChainUnroll<NJ, ALLREV, 0>::compose(P, cur, q, sn, cs);
+            const ChainFrameP& fp = P.frame[0];
+            const Fr A = chain_frame_a(fp, cur);
+            if (jac_e)
             {
-                sn[j] = 0.0;
-                cs[j] = 1.0;
-                if (ALLREV || !P.joint[j].prismatic) fast_sincos(th[j], sn[j], cs[j]);
+                cur = load_frame(P.base);
+                const bool six = fp.n_rows == 6;
+                if (fp.b_const)
+                {
+                    if (six) ChainUnroll<NJ, ALLREV, 0>::template emit<true, true>(P, jac_e, sr_b, cur, q, sn, cs, A.x, A.y, A.z);
+                    else ChainUnroll<NJ, ALLREV, 0>::template emit<true, false>(P, jac_e, sr_b, cur, q, sn, cs, A.x, A.y, A.z);
+                }
+                else
+                {
+                    if (six) ChainUnroll<NJ, ALLREV, 0>::template emit<false, true>(P, jac_e, sr_b, cur, q, sn, cs, A.x, A.y, A.z);
+                    else ChainUnroll<NJ, ALLREV, 0>::template emit<false, false>(P, jac_e, sr_b, cur, q, sn, cs, A.x, A.y, A.z);
+                }
             }
-            ChainUnroll<NJ, ALLREV, VARIANT, NF, 0>::compose(P, cur, q, sn, cs);
-            chain_frames<NF>(P, o, cur, pa);
-            if (o.jac)
-            {
-                cur.m0 = P.base[0]; cur.m1 = P.base[1]; cur.m2 = P.base[2]; cur.m3 = P.base[3]; cur.m4 = P.base[4]; cur.m5 = P.base[5];
-                cur.m6 = P.base[6]; cur.m7 = P.base[7]; cur.m8 = P.base[8]; cur.x = P.base[9]; cur.y = P.base[10]; cur.z = P.base[11];
-                ChainUnroll<NJ, ALLREV, VARIANT, NF, 0>::emit(P, o, cur, q, sn, cs, pa);
-            }
+            chain_frame_phi(fp, A, phi_e, P.phi_sk);
         }
         else
         {
             double W[NJ][3], PJ[NJ][3];
-            ChainUnroll<NJ, ALLREV, VARIANT, NF, 0>::record(P, cur, q, th, W, PJ, stash);
-            chain_frames<NF>(P, o, cur, pa);
-            if (o.jac) ChainUnroll<NJ, ALLREV, VARIANT, NF, 0>::columns(P, o, W, PJ, stash, pa);
+            ChainUnroll<NJ, ALLREV, 0>::record(P, cur, q, sn, cs, W, PJ);
+            // Jacobian columns first (they release the joint data), the rotation encodings of Phi after them
+            for (int f = 0; f < P.n_frames; ++f)
+            {
+                const ChainFrameP& fp = P.frame[f];
+                const Fr A = chain_frame_a(fp, cur);
+                if (jac_e)
+                {
+                    const bool six = fp.n_rows == 6;
+                    if (fp.b_const)
+                    {
+                        if (six) ChainUnroll<NJ, ALLREV, 0>::template columns<true, true>(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z);
+                        else ChainUnroll<NJ, ALLREV, 0>::template columns<true, false>(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z);
+                    }
+                    else
+                    {
+                        if (six) ChainUnroll<NJ, ALLREV, 0>::template columns<false, true>(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z);
+                        else ChainUnroll<NJ, ALLREV, 0>::template columns<false, false>(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z);
+                    }
+                }
+            }
+            for (int f = 0; f < P.n_frames; ++f)
+            {
+                const ChainFrameP& fp = P.frame[f];
+                chain_frame_phi(fp, chain_frame_a(fp, cur), phi_e, P.phi_sk);
+            }
         }
     }
 }
 
-template <int NJ, bool ALLREV, int VARIANT, int NF>
+// Grid size in units of "resident CTAs per GPU" (tuning knob, EXO_CHAIN_WAVES; 1 = exactly one persistent wave).
+// Measured on B200 (cfg2a, 2^20 evaluations): 1 wave 98.6 us, 4 waves 90.1 us, 8 waves 88.2 us, one CTA per 64
+// evaluations 94 us -- a few CTA generations per SM de-synchronise the load and store phases of the resident CTAs.
+static int chain_grid_waves()
+{
+    static int waves = 0;
+    if (waves == 0)
+    {
+        const char* env = getenv("EXO_CHAIN_WAVES");
+        waves = env ? atoi(env) : 8;
+        if (waves < 1) waves = 1;
+    }
+    return waves;
+}
+
+template <int NJ, bool ALLREV, int VARIANT>
 cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
 {
     static int ctas_per_sm = 0;  // occupancy is a property of the instantiation: query once
-    const size_t smem = VARIANT == CHAIN_STASH ? (size_t)3 * NJ * CTPB * sizeof(double2) : 0;
     if (ctas_per_sm == 0)
     {
-        cudaError_t err = cudaFuncSetAttribute(exo_chain_kernel<NJ, ALLREV, VARIANT, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
         int ctas = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_chain_kernel<NJ, ALLREV, VARIANT, NF>, CTPB, smem);
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_chain_kernel<NJ, ALLREV, VARIANT>, CTPB, 0);
         if (err != cudaSuccess) return err;
         if (ctas < 1) return cudaErrorInvalidConfiguration;
         ctas_per_sm = ctas;
     }
     const int64_t want = (P.n_evals + CTPB - 1) / CTPB;
-    const int64_t resident = (int64_t)sms * ctas_per_sm;
+    const int64_t resident = (int64_t)sms * ctas_per_sm * chain_grid_waves();
     const int blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
-    exo_chain_kernel<NJ, ALLREV, VARIANT, NF><<<blocks, CTPB, smem, stream>>>(P);
+    exo_chain_kernel<NJ, ALLREV, VARIANT><<<blocks, CTPB, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
-template <bool ALLREV, int VARIANT, int NF>
+template <bool ALLREV, int VARIANT>
 cudaError_t chain_launch_nj(const ChainParams& P, int sms, cudaStream_t stream)
 {
     switch (P.n_joints)
     {
-        case 1: return chain_launch_t<1, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 2: return chain_launch_t<2, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 3: return chain_launch_t<3, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 4: return chain_launch_t<4, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 5: return chain_launch_t<5, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 6: return chain_launch_t<6, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 7: return chain_launch_t<7, ALLREV, VARIANT, NF>(P, sms, stream);
-        case 8: return chain_launch_t<8, ALLREV, VARIANT, NF>(P, sms, stream);
+        case 1: return chain_launch_t<1, ALLREV, VARIANT>(P, sms, stream);
+        case 2: return chain_launch_t<2, ALLREV, VARIANT>(P, sms, stream);
+        case 3: return chain_launch_t<3, ALLREV, VARIANT>(P, sms, stream);
+        case 4: return chain_launch_t<4, ALLREV, VARIANT>(P, sms, stream);
+        case 5: return chain_launch_t<5, ALLREV, VARIANT>(P, sms, stream);
+        case 6: return chain_launch_t<6, ALLREV, VARIANT>(P, sms, stream);
+        case 7: return chain_launch_t<7, ALLREV, VARIANT>(P, sms, stream);
+        case 8: return chain_launch_t<8, ALLREV, VARIANT>(P, sms, stream);
         default: return cudaErrorInvalidConfiguration;
     }
 }
@@ -500,10 +532,7 @@ cudaError_t chain_launch_nj(const ChainParams& P, int sms, cudaStream_t stream)
 template <int VARIANT>
 cudaError_t chain_launch_v(const ChainParams& P, int sms, cudaStream_t stream)
 {
-    // the common shapes (all joints revolute; one requested frame) get their own instantiations
-    if (P.all_revolute)
-        return P.n_frames <= 1 ? chain_launch_nj<true, VARIANT, 1>(P, sms, stream) : chain_launch_nj<true, VARIANT, CH_MAXF>(P, sms, stream);
-    return chain_launch_nj<false, VARIANT, CH_MAXF>(P, sms, stream);
+    return P.all_revolute ? chain_launch_nj<true, VARIANT>(P, sms, stream) : chain_launch_nj<false, VARIANT>(P, sms, stream);
 }
 }  // namespace
 
@@ -511,16 +540,14 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
                 int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc)
 {
     P.x = x; P.phi = phi; P.jac = jac; P.n_evals = n_evals;
-    P.x_se = x_se; P.x_sk = x_sk; P.phi_se = phi_se; P.phi_sk = phi_sk; P.j_se = j_se; P.j_sr = j_sr; P.j_sc = j_sc;
-    for (int j = 0; j < P.n_joints; ++j)
-    {
-        P.joint[j].x_elem_off = (P.joint[j].qidx >= 0 ? P.joint[j].qidx : 0) * x_sk;
-        P.joint[j].jcol_elem_off = (P.joint[j].col >= 0 ? P.joint[j].col : 0) * j_sc;
-    }
+    P.x_sk = x_sk; P.phi_sk = phi_sk; P.j_sr = j_sr; P.j_sc = j_sc;
+    P.x_se_b = x_se * 8; P.phi_se_b = phi_se * 8; P.j_se_b = j_se * 8; P.j_sr_b = j_sr * 8;
+    for (int j = 0; j < P.n_joints; ++j) P.joint[j].x_byte_off = (P.joint[j].qidx >= 0 ? P.joint[j].qidx : 0) * x_sk * 8;
     for (int f = 0; f < P.n_frames; ++f)
     {
-        P.frame[f].phi_elem_off = P.frame[f].phi_off * phi_sk;
-        P.frame[f].jrow_elem_off = P.frame[f].jrow_off * j_sr;
+        P.frame[f].phi_byte_off = P.frame[f].phi_off * phi_sk * 8;
+        for (int j = 0; j < P.n_joints; ++j)
+            P.jf_byte_off[f][j] = (P.frame[f].jrow_off * j_sr + (P.joint[j].col >= 0 ? P.joint[j].col : 0) * j_sc) * 8;
     }
 }
 
@@ -538,7 +565,6 @@ cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream)
     switch (variant)
     {
         case CHAIN_REGS: return chain_launch_v<CHAIN_REGS>(P, sms, stream);
-        case CHAIN_STASH: return chain_launch_v<CHAIN_STASH>(P, sms, stream);
         case CHAIN_TWO_PASS: return chain_launch_v<CHAIN_TWO_PASS>(P, sms, stream);
         default: return cudaErrorInvalidValue;
     }

@@ -155,15 +155,66 @@ __device__ __forceinline__ void fast_sincos(double x, double& s, double& c)
     c = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
 }
 
+// ---- atan2 ---------------------------------------------------------------------------------------------------------------
+// atan2 for the Euler-angle encodings (KDL::Rotation::GetRPY / GetEulerZYZ call std::atan2).  One division, octant
+// reduction to |u| <= tan(pi/8) via atan(t) = pi/4 + atan((t-1)/(t+1)), fdlibm's atan minimax kernel (valid to 7/16,
+// < 1 ulp), coefficients in __constant__ memory.  Signed zeros are honoured (atan2(+0,-0) = pi) because products of
+// rotation-matrix entries do produce -0.0.  Absolute error ~1e-16; inputs are rotation-matrix entries (no
+// overflow/denormal handling beyond the 0/0 case).
+__constant__ double kAtan[12] = {
+    3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,  -1.11111104054623557880e-01,
+    9.09088713343650656196e-02,  -7.69187620504482999495e-02, 6.66107313738753120669e-02,  -5.83357013379057348645e-02,
+    4.97687799461593236017e-02,  -3.65315727442169155270e-02, 1.62858201153657823623e-02,  0.0};
+
+__device__ __forceinline__ double fast_div(double num, double den)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    const double q = num * r;
+    const double rem = fma(-den, q, num);
+    return fma(rem, r, q);
+}
+
+__device__ __forceinline__ double fast_atan2(double y, double x)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool upper = mn > 0.41421356237309503 * mx;  // octant beyond tan(pi/8)
+    const double num = upper ? mn - mx : mn;
+    double den = upper ? mn + mx : mx;
+    den = (den == 0.0) ? 1.0 : den;  // atan2(0, 0): u = 0
+    const double u = fast_div(num, den);
+    const double z = u * u, w = z * z;
+    double s1 = fma(w, kAtan[10], kAtan[8]);
+    double s2 = fma(w, kAtan[9], kAtan[7]);
+    s1 = fma(w, s1, kAtan[6]);
+    s2 = fma(w, s2, kAtan[5]);
+    s1 = fma(w, s1, kAtan[4]);
+    s2 = fma(w, s2, kAtan[3]);
+    s1 = fma(w, s1, kAtan[2]);
+    s2 = fma(w, s2, kAtan[1]);
+    s1 = fma(w, s1, kAtan[0]);
+    const double poly = fma(z, s1, w * s2);
+    double a = fma(-u, poly, u);                       // atan(u)
+    a = upper ? a + 7.85398163397448279e-01 : a;       // + pi/4
+    a = (ay > ax) ? 1.57079632679489656e+00 - a : a;   // reflect about the diagonal
+    a = (__double2hiint(x) < 0) ? 3.14159265358979312e+00 - a : a;
+    return __hiloint2double((__double2hiint(a) & 0x7fffffff) | (__double2hiint(y) & 0x80000000), __double2loint(a));
+}
+
 // ---- rotation encodings: exotica::SetRotation (exotica_core/src/tools/conversions.cpp:150-179) over KDL / Eigen ----
 __device__ __forceinline__ void get_rpy(const Fr& f, double& roll, double& pitch, double& yaw)
 {
     // KDL::Rotation::GetRPY, including the gimbal-lock branch at |pitch| > pi/2 - 1e-12.
     // Written with three atan2 call sites (arguments selected first) to keep the code small.
-    pitch = atan2(-f.m6, sqrt(f.m0 * f.m0 + f.m3 * f.m3));
+    pitch = fast_atan2(-f.m6, sqrt(f.m0 * f.m0 + f.m3 * f.m3));
     const bool lock = fabs(pitch) > (CUDART_PIO2 - 1e-12);
-    const double r = atan2(f.m7, f.m8);
-    yaw = atan2(lock ? -f.m1 : f.m3, lock ? f.m4 : f.m0);
+    const double r = fast_atan2(f.m7, f.m8);
+    yaw = fast_atan2(lock ? -f.m1 : f.m3, lock ? f.m4 : f.m0);
     roll = lock ? 0.0 : r;
 }
 
@@ -174,9 +225,9 @@ __device__ __forceinline__ void get_zyz(const Fr& f, double& alpha, double& beta
     const bool pos = f.m8 > 0;
     const double ay = sing ? (pos ? f.m3 : -f.m3) : f.m5;
     const double ax = sing ? (pos ? f.m0 : -f.m0) : f.m2;
-    alpha = atan2(ay, ax);
-    const double b = atan2(sqrt(f.m6 * f.m6 + f.m7 * f.m7), f.m8);
-    const double g = atan2(f.m7, -f.m6);
+    alpha = fast_atan2(ay, ax);
+    const double b = fast_atan2(sqrt(f.m6 * f.m6 + f.m7 * f.m7), f.m8);
+    const double g = fast_atan2(f.m7, -f.m6);
     beta = sing ? (pos ? 0.0 : CUDART_PI) : b;
     gamma = sing ? 0.0 : g;
 }

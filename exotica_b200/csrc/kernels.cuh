@@ -54,8 +54,7 @@ struct ChainJointP
     int32_t col;       // Jacobian column or -1
     int32_t prismatic;
     int32_t pad;
-    int64_t x_elem_off;     // qidx * x_sk            (filled per launch by chain_bind)
-    int64_t jcol_elem_off;  // col * j_sc
+    int64_t x_byte_off;  // 8 * qidx * x_sk            (filled per launch by chain_bind)
 };
 struct ChainFrameP
 {
@@ -64,8 +63,7 @@ struct ChainFrameP
     int32_t k_kind;   // F_OFFA_NONE / F_OFFA_TRANS / F_OFFA_FULL
     int32_t b_const;  // 0: temp_B is the identity
     int32_t map_kind, rot_type, phi_off, jrow_off, n_rows, pad;
-    int64_t phi_elem_off;   // phi_off * phi_sk       (filled per launch by chain_bind)
-    int64_t jrow_elem_off;  // jrow_off * j_sr
+    int64_t phi_byte_off;  // 8 * phi_off * phi_sk     (filled per launch by chain_bind)
 };
 struct ChainFillP
 {
@@ -79,7 +77,9 @@ struct ChainParams
     double* phi;
     double* jac;  // may be NULL
     int64_t n_evals;
-    int64_t x_se, x_sk, phi_se, phi_sk, j_se, j_sr, j_sc;
+    int64_t x_sk, phi_sk, j_sr, j_sc;              // element strides (doubles) of the entry / row / column index
+    int64_t x_se_b, phi_se_b, j_se_b, j_sr_b;      // byte strides of the evaluation index and of a Jacobian row
+    int64_t jf_byte_off[CH_MAXF][CH_MAXJ];         // byte offset of J(first row of frame f, column of joint j)
     int32_t n_joints, n_ctrl, n_frames, n_fill;
     int32_t has_prefix, jl_enabled, jl_phi_off, jl_jrow_off;
     uint32_t zero_cols;
@@ -95,8 +95,7 @@ static_assert(sizeof(ChainParams) <= 4000, "ChainParams must fit the classic 4 K
 enum
 {
     CHAIN_REGS = 0,      // one pass, every joint's axis and origin stay in registers until the Jacobian is emitted
-    CHAIN_STASH = 1,     // one pass, joint axes and origins parked in shared memory (fewer registers, more resident warps)
-    CHAIN_TWO_PASS = 2,  // the chain is recomposed for the Jacobian pass (nothing parked at all)
+    CHAIN_TWO_PASS = 1,  // the chain is recomposed for the Jacobian pass (nothing parked at all)
     CHAIN_DEFAULT = CHAIN_REGS
 };
 struct Program;

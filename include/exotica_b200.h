@@ -195,8 +195,8 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
 
 /* Kernel selection: 0 = auto (the Denavit-Hartenberg chain kernel when the compiled program is a serial chain of at
  * most 8 joints whose frames hang off the last link, else the general interpreter), 1 = always the interpreter,
- * 2 / 3 / 4 = the chain kernel's variants (joint data in registers / parked in shared memory / chain composed twice;
- * EXO_ERR_UNSUPPORTED at launch if the program is not a chain).  Tests compare all of them. */
+ * 2 / 3 = the chain kernel's variants (joint data kept in registers / chain composed twice; EXO_ERR_UNSUPPORTED at
+ * launch if the program is not a chain).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
 /* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);
