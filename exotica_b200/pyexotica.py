@@ -410,6 +410,11 @@ class PlanningProblem(object):
     def launch_count(self):
         return int(_host.lib().exo_host_problem_launch_count(self._h))
 
+    def last_kernel(self):
+        """Name of the CUDA kernel the most recent batched update launched (bench.py's roofline names it)."""
+        from . import _capi
+        return _capi.lib().exo_problem_last_kernel(_host.lib().exo_host_problem_backend(self._h)).decode()
+
 
 class Setup(object):
     """pyexotica.Setup (pyexotica.cpp:683-706)."""
