@@ -536,7 +536,8 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         }
         cfg = p->plan_cfg;
         k.scratch_offset = p->plan_scratch_offset;
-        const int64_t want = (E + cfg.threads - 1) / cfg.threads;
+        const int64_t per_cta = (int64_t)(cfg.threads / 32) * cfg.tile;
+        const int64_t want = (E + per_cta - 1) / per_cta;
         if (want < cfg.blocks) cfg.blocks = (int)want;
     }
     if (timed)

@@ -424,11 +424,12 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             if (!seq[s].first) cur = seq[s].second;
         }
     }
-    auto use_frame = [&](int elem_anchor, int s) -> int {
+    auto use_frame = [&](int elem_anchor, int s, bool force_slot = false) -> int {
         // returns the source code for reading G[elem_anchor] at sequence position s, registering slot needs
+        // (force_slot: the reader is another lane of the warp, which cannot see this lane's registers)
         if (elem_anchor < 0) return SRC_ROOT;
         const int k = op_of[elem_anchor];
-        if (cur_at[s] == k) return SRC_CUR;
+        if (cur_at[s] == k && !force_slot) return SRC_CUR;
         prod[k].needs_frame_slot = true;
         prod[k].frame_last_use = std::max(prod[k].frame_last_use, s);
         return k;  // provisional: op index, patched to the slot number after allocation
@@ -509,7 +510,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             {
                 const int a = anchor[m.elem_a[i]];
                 pl.sphere_anchor_elem.push_back(a);
-                pl.sphere_src.push_back(use_frame(a, s));
+                pl.sphere_src.push_back(use_frame(a, s, true));
                 if (a >= 0 && std::find(pl.acc_elems.begin(), pl.acc_elems.end(), a) == pl.acc_elems.end()) pl.acc_elems.push_back(a);
             }
             // Jacobian columns: every controlled ancestor of any anchored sphere
@@ -800,7 +801,9 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
     h.length_jac = length_jac;
     h.n_generated = t.n_generated;
     h.n_acc = n_acc_max;
-    h.scratch_doubles = 12 * n_frame_slots + 6 * n_joint_slots + 6 * n_acc_max;
+    h.scratch_doubles = 12 * n_frame_slots + 6 * n_joint_slots;
+    for (const Op& op : out.ops)
+        if (op.kind == OP_EMIT_SPHERES) h.max_spheres = std::max(h.max_spheres, op.n_items);
     // chain eligibility: [JointLimit / fill emits]* [joint fed by its predecessor]+ [frame emits reading the final frame]*,
     // nothing deferred to frame slots, frame B constant
     {

@@ -22,9 +22,226 @@ namespace
 
 using namespace dev;
 
-template <int TPB>
-__global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
+// ---- SphereCollision::Update (sphere_collision.cpp:123-162), one evaluation at a time by a whole warp ----------------------
+// phi[g] = sum over sphere pairs (i in group A, j in group B) of 1 / (1 + exp(5 eps (|p_i - p_j| - r_i - r_j)));
+// J.row(g) = - sum over pairs of (J_i - J_j)^T u_ij,  u_ij = (p_i - p_j) / |p_i - p_j|   (no sigmoid factor: App. C #4).
+// Regrouped per sphere:  J.row(g)[c] = - sum_i (w_c x (p_i - p_c)) . g_i + sum_j (w_c x (p_j - p_c)) . h_j  with
+// g_i = sum_j u_ij, h_j = sum_i u_ij, over the spheres that hang below joint c.  Each lane owns one sphere of the
+// "owner" group and a strided share of the other group; sums over lanes are warp-shuffle reductions.
+__constant__ double kExp[14] = {
+    1.4426950408889634074,      // 0: log2(e)
+    6.93147180369123816490e-01, // 1: ln2 high part (fdlibm)
+    1.90821492927058770002e-10, // 2: ln2 low part
+    1.0 / 39916800.0,           // 3: 1/11!
+    1.0 / 3628800.0,            // 4: 1/10!
+    1.0 / 362880.0,             // 5
+    1.0 / 40320.0,              // 6
+    1.0 / 5040.0,               // 7
+    1.0 / 720.0,                // 8
+    1.0 / 120.0,                // 9
+    1.0 / 24.0,                 // 10
+    1.0 / 6.0,                  // 11
+    0.5,                        // 12
+    0.0};
+
+__device__ __forceinline__ double warp_sum(double v)
 {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// exp(t) for the sigmoid: |relative error| < 1e-14 (degree-11 Taylor on |r| <= ln2/2), t clamped to +-700
+__device__ __forceinline__ double sph_exp(double t)
+{
+    t = fmin(fmax(t, -700.0), 700.0);
+    const double magic = 6755399441055744.0;
+    const double kf = fma(t, kExp[0], magic);
+    const int k = __double2loint(kf);
+    const double kd = kf - magic;
+    double r = fma(-kd, kExp[1], t);
+    r = fma(-kd, kExp[2], r);
+    double p = fma(r, kExp[3], kExp[4]);
+    p = fma(r, p, kExp[5]);
+    p = fma(r, p, kExp[6]);
+    p = fma(r, p, kExp[7]);
+    p = fma(r, p, kExp[8]);
+    p = fma(r, p, kExp[9]);
+    p = fma(r, p, kExp[10]);
+    p = fma(r, p, kExp[11]);
+    p = fma(r, p, kExp[12]);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// one sphere pair: accumulates weight * sigmoid into phi (if WITH_PHI) and weight * unit vector into (gx, gy, gz)
+template <bool WITH_PHI>
+__device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double rsum, double k5, double weight, double& phi, double& gx, double& gy,
+                                         double& gz)
+{
+    const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(n2));
+    const double h = 0.5 * n2;
+    double t = fma(-(h * y), y, 0.5);
+    y = fma(y, t, y);
+    t = fma(-(h * y), y, 0.5);
+    y = fma(y, t, y);  // 1 / |d|  (inf -> NaN for coincident centres, like the reference's division by zero)
+    const double yw = y * weight;  // weight 0 masks the padding pairs of the unrolled loop
+    gx = fma(dx, yw, gx);
+    gy = fma(dy, yw, gy);
+    gz = fma(dz, yw, gz);
+    if (WITH_PHI)
+    {
+        const double n = (n2 == 0.0) ? 0.0 : n2 * y;
+        const double den = 1.0 + sph_exp(k5 * (n - rsum));
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+        double e = fma(-den, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-den, r, 1.0);
+        r = fma(r, e, r);
+        phi = fma(r, weight, phi);
+    }
+}
+
+template <int CS>
+__device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c, const int32_t* tab, int N, int joint_base, double* scr0,
+                                               double* warp_smem, int lane, int warp_col0, int n_valid, int64_t e0, const KernelParams& P,
+                                               bool want_j)
+{
+    const int S = op.n_items;
+    const int G = tab[0];
+    const int32_t* gs = tab + 2;
+    const int32_t* sph = gs + G + 1;
+    const int32_t* cols = sph + SPH_INTS * S;
+    const double k5 = c[0];
+    const double* sc = c + 1;  // per sphere: ox oy oz radius
+    double* centre = warp_smem;       // [S][4]: x y z radius of the evaluation being processed
+    double* rowacc = warp_smem + 4 * S;  // [N]
+    for (int ev = 0; ev < n_valid; ++ev)
+    {
+        const double* scr = scr0 + warp_col0 + ev;  // scratch column of the evaluation being processed
+        // ---- sphere centres of this evaluation ---------------------------------------------------------------
+        for (int s = lane; s < S; s += 32)
+        {
+            const int src = sph[SPH_INTS * s];
+            double px = sc[4 * s], py = sc[4 * s + 1], pz = sc[4 * s + 2];
+            if (src != SRC_ROOT)
+            {
+                const Fr f = fr_load_scratch<CS>(scr + 12 * src * CS);
+                const double tx = f.m0 * px + f.m1 * py + f.m2 * pz + f.x;
+                const double ty = f.m3 * px + f.m4 * py + f.m5 * pz + f.y;
+                const double tz = f.m6 * px + f.m7 * py + f.m8 * pz + f.z;
+                px = tx; py = ty; pz = tz;
+            }
+            centre[4 * s] = px; centre[4 * s + 1] = py; centre[4 * s + 2] = pz; centre[4 * s + 3] = sc[4 * s + 3];
+        }
+        __syncwarp();
+        const int64_t e = e0 + ev;
+        int out_idx = 0;
+        for (int ga = 0; ga < G; ++ga)
+        {
+            for (int gb = ga + 1; gb < G; ++gb, ++out_idx)
+            {
+                if (want_j)
+                    for (int col = lane; col < N; col += 32) rowacc[col] = 0.0;
+                __syncwarp();
+                double phi_part = 0.0;
+                // pass 0: lanes own spheres of group A (phi and -J_i^T g_i); pass 1: lanes own spheres of group B (+J_j^T h_j)
+                for (int pass = 0; pass < (want_j ? 2 : 1); ++pass)
+                {
+                    const int o0 = pass == 0 ? gs[ga] : gs[gb], o1 = pass == 0 ? gs[ga + 1] : gs[gb + 1];
+                    const int t0 = pass == 0 ? gs[gb] : gs[ga], t1 = pass == 0 ? gs[gb + 1] : gs[ga + 1];
+                    if (pass == 1)
+                    {
+                        // skip when no sphere of group B hangs below a controlled joint (fixed or trajectory-driven obstacles)
+                        bool any = false;
+                        for (int j = o0; j < o1; ++j) any = any || sph[SPH_INTS * j + 1] >= 0;
+                        if (!any) break;
+                    }
+                    const int n_own = o1 - o0;
+                    // lanes = (owner sphere, share of the other group): parts = how many lanes share one owner sphere
+                    int own_p2 = 1;
+                    while (own_p2 < n_own && own_p2 < 32) own_p2 <<= 1;
+                    const int parts = 32 / own_p2;
+                    for (int i0 = o0; i0 < o1; i0 += own_p2)
+                    {
+                        const int i = i0 + (lane & (own_p2 - 1));
+                        const int part = lane / own_p2;
+                        const bool live = i < o1;
+                        const int ii = live ? i : o1 - 1;
+                        const double pix = centre[4 * ii], piy = centre[4 * ii + 1], piz = centre[4 * ii + 2], ri = centre[4 * ii + 3];
+                        double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
+                        if (live)
+                        {
+                            // four pairs per iteration: straight-line code whose independent Horner / Newton chains the
+                            // scheduler interleaves (the FP64 pipe needs ~5 independent instructions in flight per warp)
+                            for (int j0 = t0 + part; j0 < t1; j0 += 4 * parts)
+                            {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                {
+                                    const int j = j0 + u * parts;
+                                    const bool ok = j < t1;
+                                    const int jj = ok ? j : t0;
+                                    const double w = ok ? 1.0 : 0.0;
+                                    if (pass == 0)
+                                        sph_pair<true>(pix - centre[4 * jj], piy - centre[4 * jj + 1], piz - centre[4 * jj + 2], ri + centre[4 * jj + 3],
+                                                       k5, w, ph, gx, gy, gz);
+                                    else
+                                        sph_pair<false>(centre[4 * jj] - pix, centre[4 * jj + 1] - piy, centre[4 * jj + 2] - piz, 0.0, k5, w, ph, gx, gy,
+                                                        gz);
+                                }
+                            }
+                        }
+                        phi_part += ph;
+                        if (!want_j) continue;
+                        // Jacobian: every column whose joint carries this lane's sphere gets w_c . ((p_i - p_c) x g)
+                        const int acc_i = live ? sph[SPH_INTS * ii + 1] : -1;
+                        for (int col = 0; col < N; ++col)
+                        {
+                            const int ent = cols[3 * col];
+                            if (ent < 0) continue;
+                            const uint32_t mlo = (uint32_t)cols[3 * col + 1], mhi = (uint32_t)cols[3 * col + 2];
+                            const bool in = acc_i >= 0 && (acc_i < 32 ? ((mlo >> acc_i) & 1u) : ((mhi >> (acc_i - 32)) & 1u));
+                            const double* js = scr + (joint_base + 6 * (ent >> 2)) * CS;
+                            const double ax = js[0], ay = js[CS], az = js[2 * CS];
+                            double v;
+                            if (ent & 2)
+                                v = ax * gx + ay * gy + az * gz;
+                            else
+                            {
+                                const double rx = pix - js[3 * CS], ry = piy - js[4 * CS], rz = piz - js[5 * CS];
+                                v = ax * (ry * gz - rz * gy) + ay * (rz * gx - rx * gz) + az * (rx * gy - ry * gx);
+                            }
+                            v = warp_sum(in ? v : 0.0);
+                            if (lane == 0) rowacc[col] += (pass == 0 ? -v : v);
+                        }
+                    }
+                }
+                phi_part = warp_sum(phi_part);
+                if (lane == 0) P.phi[e * P.phi_se + (int64_t)(op.phi_off + out_idx) * P.phi_sk] = phi_part;
+                if (want_j)
+                {
+                    __syncwarp();
+                    double* row = P.jac + e * P.j_se + (int64_t)(op.jrow_off + out_idx) * P.j_sr;
+                    for (int col = lane; col < N; col += 32) row[(int64_t)col * P.j_sc] = rowacc[col];
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();  // the centre table is rewritten for the next evaluation
+    }
+}
+
+// TPB threads per CTA; W evaluations per warp tile (W < 32: lanes l and l + W work on the same evaluation -- redundant
+// forward kinematics in exchange for a W/32 scratch footprint, used when SphereCollision needs many resident warps).
+template <int TPB, int W>
+__global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
+{
+    constexpr int CS = TPB / 32 * W;  // scratch columns per CTA
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     // ---- stage the program (topology, axes, offsets, tables) once per CTA ---------------------------------
@@ -32,26 +249,35 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
         const int n_words = P.program_bytes >> 2;
         const int32_t* src = reinterpret_cast<const int32_t*>(P.program);
         int32_t* dst = reinterpret_cast<int32_t*>(smem);
-        for (int i = tid; i < n_words; i += TPB) dst[i] = src[i];
+        for (int i = tid; i < n_words; i += TPB) dst[i] = src[i];  // CTA-wide copy
     }
     __syncthreads();
     const ProgramHeader* H = reinterpret_cast<const ProgramHeader*>(smem);
     const Op* ops = reinterpret_cast<const Op*>(smem + sizeof(ProgramHeader));
     const int32_t* ints = reinterpret_cast<const int32_t*>(ops + H->n_ops);
     const double* dbls = reinterpret_cast<const double*>(smem + P.dbl_offset);
-    double* scr = reinterpret_cast<double*>(smem + P.scratch_offset) + tid;  // word k at scr[k * TPB]
+    const int lane = tid & 31;
+    const int col = (tid >> 5) * W + (lane & (W - 1));                        // this lane's scratch column
+    double* scr = reinterpret_cast<double*>(smem + P.scratch_offset) + col;  // word k at scr[k * CS]
     const int N = H->n_ctrl;
     const int joint_base = 12 * H->n_frame_slots;
-    const int acc_base = joint_base + 6 * H->n_joint_slots;
-    double* qs = scr + (size_t)H->scratch_doubles * TPB;
+    double* qs = scr + (size_t)H->scratch_doubles * CS;
+    // per-warp area behind the per-thread scratch: sphere centre table (4 doubles per sphere) + Jacobian row accumulators
+    double* warp_smem = reinterpret_cast<double*>(smem + P.scratch_offset) + (size_t)(H->scratch_doubles + N) * CS +
+                        (size_t)(tid >> 5) * (4 * H->max_spheres + N);
     const bool want_j = P.jac != nullptr;
 
-    for (int64_t e = (int64_t)blockIdx.x * TPB + tid; e < P.n_evals; e += (int64_t)gridDim.x * TPB)
+    // The loop is warp-uniform (SphereCollision is evaluated by the whole warp for one lane's evaluation at a time):
+    // lanes past the end of the batch redo the last evaluation and write the same values to the same addresses.
+    for (int64_t e0 = ((int64_t)blockIdx.x * (TPB / 32) + (tid >> 5)) * W; e0 < P.n_evals; e0 += (int64_t)gridDim.x * (TPB / 32) * W)
     {
+        const int n_valid = (int)((P.n_evals - e0) < W ? (P.n_evals - e0) : W);  // evaluations of this warp's tile
+        const int slot = lane & (W - 1);
+        const int64_t e = e0 + (slot < n_valid ? slot : n_valid - 1);
         // ---- stage this evaluation's state (N independent loads in flight) --------------------------------
         {
             const double* xe = P.x + e * P.x_se;
-            for (int i = 0; i < N; ++i) qs[i * TPB] = xe[i * P.x_sk];
+            for (int i = 0; i < N; ++i) qs[i * CS] = xe[i * P.x_sk];
         }
         double* phi_e = P.phi + e * P.phi_se;
         double* jac_e = want_j ? P.jac + e * P.j_se : nullptr;
@@ -67,7 +293,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                 if (op.src == SRC_ROOT)
                     cur = fr_identity();
                 else if (op.src >= 0)
-                    cur = fr_load_scratch<TPB>(scr + 12 * op.src * TPB);
+                    cur = fr_load_scratch<CS>(scr + 12 * op.src * CS);
                 const int pre = op.flags & F_PRE_MASK;
                 if (pre == F_PRE_TRANS)
                     fr_translate(cur, c[9], c[10], c[11]);
@@ -85,7 +311,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                 else
                 {
                     double q = c[CJ_QOFF];
-                    if (op.qidx >= 0) q = fma(c[CJ_QMULT], qs[op.qidx * TPB], q);
+                    if (op.qidx >= 0) q = fma(c[CJ_QMULT], qs[op.qidx * CS], q);
                     const int ax = op.flags & F_AXIS_MASK;
                     double wx, wy, wz;  // axis in world coordinates
                     if (op.flags & F_PRISMATIC)
@@ -170,12 +396,12 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                     }
                     if (op.jslot >= 0)
                     {
-                        double* js = scr + (joint_base + 6 * op.jslot) * TPB;
-                        js[0] = wx; js[TPB] = wy; js[2 * TPB] = wz;
-                        js[3 * TPB] = cur.x; js[4 * TPB] = cur.y; js[5 * TPB] = cur.z;
+                        double* js = scr + (joint_base + 6 * op.jslot) * CS;
+                        js[0] = wx; js[CS] = wy; js[2 * CS] = wz;
+                        js[3 * CS] = cur.x; js[4 * CS] = cur.y; js[5 * CS] = cur.z;
                     }
                 }
-                if (op.dst >= 0) fr_store_scratch<TPB>(scr + 12 * op.dst * TPB, cur);
+                if (op.dst >= 0) fr_store_scratch<CS>(scr + 12 * op.dst * CS, cur);
             }
             else if (op.kind == OP_EMIT_FRAME)
             {
@@ -183,7 +409,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                 Fr A;
                 if (op.src == SRC_CUR) A = cur;
                 else if (op.src == SRC_ROOT) A = fr_identity();
-                else A = fr_load_scratch<TPB>(scr + 12 * op.src * TPB);
+                else A = fr_load_scratch<CS>(scr + 12 * op.src * CS);
                 const int offa = op.flags & F_OFFA_MASK;
                 if (offa == F_OFFA_TRANS) fr_translate(A, c[CE_OFFA_P], c[CE_OFFA_P + 1], c[CE_OFFA_P + 2]);
                 else if (offa == F_OFFA_FULL) A = fr_mul(A, fr_load_const(c + CE_OFFA_M));
@@ -199,7 +425,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                     {
                         Fr B;
                         if (op.src_b == SRC_CUR) B = cur;
-                        else B = fr_load_scratch<TPB>(scr + 12 * op.src_b * TPB);
+                        else B = fr_load_scratch<CS>(scr + 12 * op.src_b * CS);
                         B = fr_mul(B, fr_load_const(c + CE_B_M));
                         Binv = fr_inverse(B);
                     }
@@ -219,15 +445,15 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
                         double v0 = 0.0, v1 = 0.0, v2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
                         if (ent >= 0)
                         {
-                            const double* js = scr + (joint_base + 6 * (ent >> 2)) * TPB;
-                            const double ax = js[0], ay = js[TPB], az = js[2 * TPB];
+                            const double* js = scr + (joint_base + 6 * (ent >> 2)) * CS;
+                            const double ax = js[0], ay = js[CS], az = js[2 * CS];
                             if (ent & 2)
                             {
                                 v0 = ax; v1 = ay; v2 = az;
                             }
                             else
                             {
-                                const double dx = A.x - js[3 * TPB], dy = A.y - js[4 * TPB], dz = A.z - js[5 * TPB];
+                                const double dx = A.x - js[3 * CS], dy = A.y - js[4 * CS], dz = A.z - js[5 * CS];
                                 v0 = ay * dz - az * dy;
                                 v1 = az * dx - ax * dz;
                                 v2 = ax * dy - ay * dx;
@@ -262,7 +488,7 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
             }
             else if (op.kind == OP_EMIT_JLIMIT)
             {
-                emit_joint_limit(c, N, qs, TPB, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
+                emit_joint_limit(c, N, qs, CS, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
             }
             else if (op.kind == OP_EMIT_FILL)
             {
@@ -270,131 +496,49 @@ __global__ void __launch_bounds__(TPB) exo_eval_kernel(const KernelParams P)
             }
             else if (op.kind == OP_EMIT_SPHERES)
             {
-                // SphereCollision::Update (sphere_collision.cpp:123-162).  The reference accumulates, per sphere pair
-                // and per column, -(J_i - J_j)^T d / |d|; here the pair loop accumulates unit "forces" per carrying
-                // link (F, M = p x F) and the Jacobian row is recovered per joint as  -w . (sum M - p_joint x sum F)
-                // (same sum, regrouped: O(pairs + joints) instead of O(pairs * joints)).
-                const int32_t* tab = ints + op.tab;
-                const int G = tab[0], n_acc = tab[1];
-                const int32_t* gs = tab + 2;
-                const int32_t* sph = gs + G + 1;
-                const int32_t* cols = sph + SPH_INTS * op.n_items;
-                const double k5 = c[0];
-                const double* sc = c + 1;  // per sphere: ox oy oz radius
-                double* acc = scr + (size_t)acc_base * TPB;
-                int out_idx = 0;
-                for (int ga = 0; ga < G; ++ga)
-                {
-                    for (int gb = ga + 1; gb < G; ++gb, ++out_idx)
-                    {
-                        for (int a = 0; a < 6 * n_acc; ++a) acc[a * TPB] = 0.0;
-                        double phi_sum = 0.0;
-                        for (int i = gs[ga]; i < gs[ga + 1]; ++i)
-                        {
-                            const int src_i = sph[SPH_INTS * i], acc_i = sph[SPH_INTS * i + 1];
-                            double pix = sc[4 * i], piy = sc[4 * i + 1], piz = sc[4 * i + 2];
-                            const double ri = sc[4 * i + 3];
-                            if (src_i != SRC_ROOT)
-                            {
-                                const Fr f = (src_i == SRC_CUR) ? cur : fr_load_scratch<TPB>(scr + 12 * src_i * TPB);
-                                const double tx = f.m0 * pix + f.m1 * piy + f.m2 * piz + f.x;
-                                const double ty = f.m3 * pix + f.m4 * piy + f.m5 * piz + f.y;
-                                const double tz = f.m6 * pix + f.m7 * piy + f.m8 * piz + f.z;
-                                pix = tx; piy = ty; piz = tz;
-                            }
-                            double gx = 0.0, gy = 0.0, gz = 0.0;
-                            for (int j = gs[gb]; j < gs[gb + 1]; ++j)
-                            {
-                                const int src_j = sph[SPH_INTS * j], acc_j = sph[SPH_INTS * j + 1];
-                                double pjx = sc[4 * j], pjy = sc[4 * j + 1], pjz = sc[4 * j + 2];
-                                if (src_j != SRC_ROOT)
-                                {
-                                    const Fr f = (src_j == SRC_CUR) ? cur : fr_load_scratch<TPB>(scr + 12 * src_j * TPB);
-                                    const double tx = f.m0 * pjx + f.m1 * pjy + f.m2 * pjz + f.x;
-                                    const double ty = f.m3 * pjx + f.m4 * pjy + f.m5 * pjz + f.y;
-                                    const double tz = f.m6 * pjx + f.m7 * pjy + f.m8 * pjz + f.z;
-                                    pjx = tx; pjy = ty; pjz = tz;
-                                }
-                                const double dx = pix - pjx, dy = piy - pjy, dz = piz - pjz;
-                                const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
-                                phi_sum += 1.0 / (1.0 + exp(k5 * (nrm - ri - sc[4 * j + 3])));
-                                if (want_j)
-                                {
-                                    const double ux = dx / nrm, uy = dy / nrm, uz = dz / nrm;
-                                    gx += ux; gy += uy; gz += uz;
-                                    if (acc_j >= 0)
-                                    {
-                                        double* aj = acc + 6 * acc_j * TPB;
-                                        aj[0] -= ux; aj[TPB] -= uy; aj[2 * TPB] -= uz;
-                                        aj[3 * TPB] -= pjy * uz - pjz * uy;
-                                        aj[4 * TPB] -= pjz * ux - pjx * uz;
-                                        aj[5 * TPB] -= pjx * uy - pjy * ux;
-                                    }
-                                }
-                            }
-                            if (want_j && acc_i >= 0)
-                            {
-                                double* ai = acc + 6 * acc_i * TPB;
-                                ai[0] += gx; ai[TPB] += gy; ai[2 * TPB] += gz;
-                                ai[3 * TPB] += piy * gz - piz * gy;
-                                ai[4 * TPB] += piz * gx - pix * gz;
-                                ai[5 * TPB] += pix * gy - piy * gx;
-                            }
-                        }
-                        phi_e[(int64_t)(op.phi_off + out_idx) * P.phi_sk] = phi_sum;
-                        if (want_j)
-                        {
-                            double* row = jac_e + (int64_t)(op.jrow_off + out_idx) * P.j_sr;
-                            for (int col = 0; col < N; ++col)
-                            {
-                                const int ent = cols[3 * col];
-                                double val = 0.0;
-                                if (ent >= 0)
-                                {
-                                    const uint32_t mlo = (uint32_t)cols[3 * col + 1], mhi = (uint32_t)cols[3 * col + 2];
-                                    double fx = 0, fy = 0, fz = 0, mx = 0, my = 0, mz = 0;
-                                    for (int a = 0; a < n_acc; ++a)
-                                    {
-                                        const bool in = a < 32 ? ((mlo >> a) & 1u) : ((mhi >> (a - 32)) & 1u);
-                                        if (!in) continue;
-                                        const double* aa = acc + 6 * a * TPB;
-                                        fx += aa[0]; fy += aa[TPB]; fz += aa[2 * TPB];
-                                        mx += aa[3 * TPB]; my += aa[4 * TPB]; mz += aa[5 * TPB];
-                                    }
-                                    const double* js = scr + (joint_base + 6 * (ent >> 2)) * TPB;
-                                    const double ax = js[0], ay = js[TPB], az = js[2 * TPB];
-                                    if (ent & 2)
-                                        val = -(ax * fx + ay * fy + az * fz);
-                                    else
-                                    {
-                                        const double px = js[3 * TPB], py = js[4 * TPB], pz = js[5 * TPB];
-                                        const double tx = mx - (py * fz - pz * fy);
-                                        const double ty = my - (pz * fx - px * fz);
-                                        const double tz = mz - (px * fy - py * fx);
-                                        val = -(ax * tx + ay * ty + az * tz);
-                                    }
-                                }
-                                row[(int64_t)col * P.j_sc] = val;
-                            }
-                        }
-                    }
-                }
+                __syncwarp();  // every lane's frame / joint slots are complete
+                emit_spheres_warp<CS>(op, c, ints + op.tab, N, joint_base, scr - col, warp_smem, lane, (tid >> 5) * W,
+                                       n_valid, e0, P, want_j);
+                __syncwarp();  // slots may be overwritten by the ops that follow
             }
         }
     }
 }
 }  // namespace
 
-template <int TPB>
-cudaError_t try_config(size_t prog, size_t per_thread, int max_smem, int& ctas_per_sm, size_t& smem_bytes)
+template <int TPB, int W>
+cudaError_t try_config(size_t prog, size_t per_column, size_t per_warp, int max_smem, int& ctas_per_sm, size_t& smem_bytes)
 {
-    smem_bytes = prog + per_thread * TPB;
+    smem_bytes = prog + per_column * (TPB / 32 * W) + per_warp * (TPB / 32);
     ctas_per_sm = 0;
     if (smem_bytes > (size_t)max_smem) return cudaSuccess;
-    cudaError_t err = cudaFuncSetAttribute(exo_eval_kernel<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t err = cudaFuncSetAttribute(exo_eval_kernel<TPB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exo_eval_kernel<TPB>, TPB, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exo_eval_kernel<TPB, W>, TPB, smem_bytes);
 }
+
+namespace
+{
+struct EvalConfig
+{
+    int tpb, w;
+};
+// without SphereCollision: one lane per evaluation, pick the CTA size that keeps most lanes resident;
+// with SphereCollision (one warp per evaluation in the pair loops): pick the configuration that keeps most WARPS resident.
+const EvalConfig kPlain[] = {{128, 32}, {64, 32}, {32, 32}};
+const EvalConfig kSpheres[] = {{64, 8}, {64, 16}, {128, 8}, {64, 32}, {32, 32}};
+
+cudaError_t try_any(const EvalConfig& c, size_t prog, size_t per_column, size_t per_warp, int max_smem, int& ctas, size_t& smem_bytes)
+{
+    if (c.tpb == 128 && c.w == 32) return try_config<128, 32>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    if (c.tpb == 64 && c.w == 32) return try_config<64, 32>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    if (c.tpb == 32 && c.w == 32) return try_config<32, 32>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    if (c.tpb == 64 && c.w == 8) return try_config<64, 8>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    if (c.tpb == 64 && c.w == 16) return try_config<64, 16>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    if (c.tpb == 128 && c.w == 8) return try_config<128, 8>(prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+    return cudaErrorInvalidConfiguration;
+}
+}  // namespace
 
 cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params)
 {
@@ -406,32 +550,37 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (err != cudaSuccess) return err;
     const size_t prog = ((size_t)program_bytes + 15) & ~(size_t)15;
-    const size_t per_thread = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * sizeof(double);
+    const size_t per_column = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * sizeof(double);
+    const bool spheres = hdr.max_spheres > 0;
+    const size_t per_warp = spheres ? (size_t)(4 * hdr.max_spheres + hdr.n_ctrl) * sizeof(double) : 0;
     params.scratch_offset = (int32_t)prog;
-    // pick the CTA size that keeps the most threads resident per SM (per-thread scratch lives in shared memory)
-    int best_threads = 0, best_tpb = 0, best_ctas = 0;
+    const EvalConfig* cands = spheres ? kSpheres : kPlain;
+    const int n_cands = spheres ? (int)(sizeof(kSpheres) / sizeof(kSpheres[0])) : (int)(sizeof(kPlain) / sizeof(kPlain[0]));
+    int best_score = 0, best_ctas = 0;
+    EvalConfig best = {0, 0};
     size_t best_smem = 0;
-    const int sizes[3] = {128, 64, 32};
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < n_cands; ++k)
     {
         int ctas = 0;
         size_t smem_bytes = 0;
-        if (sizes[k] == 128) err = try_config<128>(prog, per_thread, max_smem, ctas, smem_bytes);
-        else if (sizes[k] == 64) err = try_config<64>(prog, per_thread, max_smem, ctas, smem_bytes);
-        else err = try_config<32>(prog, per_thread, max_smem, ctas, smem_bytes);
+        err = try_any(cands[k], prog, per_column, per_warp, max_smem, ctas, smem_bytes);
         if (err != cudaSuccess) return err;
-        if (ctas * sizes[k] > best_threads)
+        // spheres: resident warps first, wider tiles break ties; plain: resident lanes
+        const int score = spheres ? ctas * (cands[k].tpb / 32) * 64 + cands[k].w : ctas * cands[k].tpb;
+        if (ctas > 0 && score > best_score)
         {
-            best_threads = ctas * sizes[k];
-            best_tpb = sizes[k];
+            best_score = score;
+            best = cands[k];
             best_ctas = ctas;
             best_smem = smem_bytes;
         }
     }
-    if (best_threads == 0) return cudaErrorInvalidConfiguration;
-    cfg.threads = best_tpb;
+    if (best_score == 0) return cudaErrorInvalidConfiguration;
+    cfg.threads = best.tpb;
+    cfg.tile = best.w;
     cfg.smem_bytes = best_smem;
-    const int64_t want = (n_evals + best_tpb - 1) / best_tpb;
+    const int64_t per_cta = (int64_t)(best.tpb / 32) * best.w;
+    const int64_t want = (n_evals + per_cta - 1) / per_cta;
     const int64_t resident = (int64_t)sms * best_ctas;
     cfg.blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
     return cudaSuccess;
@@ -439,9 +588,15 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
 
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream)
 {
-    if (cfg.threads == 128) exo_eval_kernel<128><<<cfg.blocks, 128, cfg.smem_bytes, stream>>>(params);
-    else if (cfg.threads == 64) exo_eval_kernel<64><<<cfg.blocks, 64, cfg.smem_bytes, stream>>>(params);
-    else exo_eval_kernel<32><<<cfg.blocks, 32, cfg.smem_bytes, stream>>>(params);
+#define EXO_LAUNCH(T, WW) exo_eval_kernel<T, WW><<<cfg.blocks, T, cfg.smem_bytes, stream>>>(params)
+    if (cfg.threads == 128 && cfg.tile == 32) EXO_LAUNCH(128, 32);
+    else if (cfg.threads == 64 && cfg.tile == 32) EXO_LAUNCH(64, 32);
+    else if (cfg.threads == 32 && cfg.tile == 32) EXO_LAUNCH(32, 32);
+    else if (cfg.threads == 64 && cfg.tile == 8) EXO_LAUNCH(64, 8);
+    else if (cfg.threads == 64 && cfg.tile == 16) EXO_LAUNCH(64, 16);
+    else if (cfg.threads == 128 && cfg.tile == 8) EXO_LAUNCH(128, 8);
+    else return cudaErrorInvalidConfiguration;
+#undef EXO_LAUNCH
     return cudaGetLastError();
 }
 

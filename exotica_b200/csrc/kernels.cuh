@@ -28,6 +28,7 @@ struct KernelParams
 struct LaunchConfig
 {
     int threads = 128;
+    int tile = 32;  // evaluations per warp
     int blocks = 0;
     size_t smem_bytes = 0;
 };

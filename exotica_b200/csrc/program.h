@@ -133,12 +133,13 @@ struct ProgramHeader
     int32_t length_phi;
     int32_t length_jac;
     int32_t n_generated;
-    int32_t n_acc;        // sphere wrench accumulators (per-thread scratch, 6 doubles each)
+    int32_t n_acc;        // distinct moving links that carry spheres (SphereCollision Jacobian masks)
     int32_t scratch_doubles;  // per-thread scratch size in doubles (excluding the q staging)
     int32_t chain_joints;     // > 0: the program is a serial chain of that many joint ops and qualifies for the
                               // register-resident chain kernel (chain_kernel.cu); 0 otherwise
     int32_t chain_tab;        // offset into the int pool of the op index of every joint ordinal (chain programs)
-    int32_t pad[3];
+    int32_t max_spheres;      // largest sphere count of any SphereCollision map (per-warp centre table in shared memory)
+    int32_t pad[2];
 };
 
 }  // namespace exo
