@@ -34,6 +34,10 @@ class TaskMapDesc(ctypes.Structure):
                 ("precision", ctypes.c_double), ("radius", _dp), ("group", _ip), ("is_used", ctypes.c_int32)]
 
 
+class CostDesc(ctypes.Structure):
+    _fields_ = [("T", ctypes.c_int32), ("T_goal", ctypes.c_int32), ("rho", _dp), ("goal", _dp), ("ct", ctypes.c_double), ("W", _dp)]
+
+
 class ExoticaError(RuntimeError):
     """Mirrors exotica::Exception (exotica_core/include/exotica_core/tools/exception.h:36-47)."""
 
@@ -76,6 +80,10 @@ SYMBOLS = [
     ("exo_problem_program_info", ctypes.c_int, [_vp, _ip]),
     ("exo_problem_chain_info", ctypes.c_int, [_vp, _ip]),
     ("exo_problem_set_kernel", ctypes.c_int, [_vp, ctypes.c_int]),
+    ("exo_problem_set_cost", ctypes.c_int, [_vp, ctypes.POINTER(CostDesc)]),
+    ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
+    ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
+    ("exo_trajectory_reduce", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
 ]
 
@@ -303,6 +311,32 @@ class Problem(object):
         out = (ctypes.c_int32 * 4)()
         check(lib().exo_problem_chain_info(self.h, out))
         return {"lowered": bool(out[0]), "joints": out[1], "all_revolute": bool(out[2]), "frames": out[3]}
+
+    def set_cost(self, rho, T=1, goal=None, ct=1.0, W=None):
+        """rho[T][n_maps] (broadcast from [n_maps]); goal[1 or T][length_Phi] or None (SetZero goal); W[N] or None."""
+        n_maps = lib().exo_problem_num_maps(self.h)
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (T, n_maps)))
+        d = CostDesc()
+        d.T, d.T_goal, d.ct = int(T), 1, float(ct)
+        d.rho = _d(rho)
+        keep = [rho]
+        if goal is not None:
+            goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1, self.length_phi)
+            d.T_goal = goal.shape[0]
+            d.goal = _d(goal)
+            keep.append(goal)
+        if W is not None:
+            W = np.ascontiguousarray(W, dtype=np.float64)
+            d.W = _d(W)
+            keep.append(W)
+        check(lib().exo_problem_set_cost(self.h, ctypes.byref(d)))
+        self.cost_T = int(T)
+
+    def cost_batch_device(self, d_x, d_phi, n_traj, d_cost_traj=None, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_cost_batch(self.h, d_x, d_phi, int(n_traj), int(layout), d_cost_traj, d_cost_eval, stream))
+
+    def set_min_distance_output(self, d_ptr):
+        check(lib().exo_problem_set_min_distance_output(self.h, d_ptr))
 
     def set_kernel(self, choice):
         check(lib().exo_problem_set_kernel(self.h, int(choice)))

@@ -55,6 +55,11 @@ struct exo_problem
     int T = 1, n_generated = 0;
     std::vector<double> h_generated;
     double* d_generated = nullptr;
+    // auxiliary outputs and the task cost (rows e / f1)
+    double* d_min_dist = nullptr;  // caller-owned, [n_evals] (exo_problem_set_min_distance_output)
+    bool cost_set = false;
+    CostParams cost;               // constants of the cost kernel; device copies below
+    double *d_rho = nullptr, *d_goal = nullptr, *d_goal_rot = nullptr, *d_W = nullptr;
     // timing / accounting
     int64_t launches = 0;
     int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..3 chain kernel variants (CHAIN_REGS, CHAIN_TWO_PASS)
@@ -305,6 +310,10 @@ int exo_problem_destroy(exo_problem* p)
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
     if (p->d_image) cudaFree(p->d_image);
     if (p->d_generated) cudaFree(p->d_generated);
+    if (p->d_rho) cudaFree(p->d_rho);
+    if (p->d_goal) cudaFree(p->d_goal);
+    if (p->d_goal_rot) cudaFree(p->d_goal_rot);
+    if (p->d_W) cudaFree(p->d_W);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
@@ -517,6 +526,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     k.phi = d_phi;
     k.jac = d_jac;
     k.generated = p->d_generated;
+    k.min_dist = p->d_min_dist;
     k.n_evals = E;
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
@@ -666,6 +676,135 @@ int exo_problem_update_batch_host(exo_problem* p, const double* h_x, int64_t E, 
         }
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+    return EXO_OK;
+}
+
+// ---- auxiliary outputs, task cost, per-trajectory reductions ------------------------------------------------------------
+int exo_problem_set_min_distance_output(exo_problem* p, double* d_min_distance)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (d_min_distance && p->prog.hdr.max_spheres == 0) return fail(EXO_ERR_INVALID, "the problem has no SphereCollision map");
+    p->d_min_dist = d_min_distance;
+    return EXO_OK;
+}
+
+static int upload(double** dst, const double* src, size_t n)
+{
+    if (*dst) cudaFree(*dst);
+    *dst = nullptr;
+    if (n == 0) return EXO_OK;
+    CUDA_TRY(cudaMalloc((void**)dst, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+    return EXO_OK;
+}
+
+int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
+{
+    if (!p || !d) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    const int n_maps = (int)p->maps.size();
+    if (n_maps > COST_MAXMAPS) return fail(EXO_ERR_UNSUPPORTED, "more task maps than the cost kernel supports");
+    if (d->T < 1) return fail(EXO_ERR_INVALID, "T must be >= 1");
+    if (d->T_goal != 1 && d->T_goal != d->T) return fail(EXO_ERR_INVALID, "T_goal must be 1 or T");
+    if (!d->rho) return fail(EXO_ERR_INVALID, "rho is NULL");
+    const int LP = p->prog.hdr.length_phi, N = p->prog.hdr.n_ctrl;
+    CostParams& c = p->cost;
+    memset(&c, 0, sizeof(c));
+    c.T = d->T;
+    c.t_first = d->T > 1 ? 1 : 0;  // GetCost sums t = 1 .. T-1 (abstract_time_indexed_problem.cpp:299-307)
+    c.T_goal = d->T_goal;
+    c.n_maps = n_maps;
+    c.n_ctrl = N;
+    c.length_phi = LP;
+    c.ct = d->ct;
+    // the SetZero goal (task_space_vector.cpp:54-62) unless the caller gives one
+    std::vector<double> goal((size_t)d->T_goal * LP, 0.0), goal_rot;
+    int n_rot = 0;
+    for (int k = 0; k < n_maps; ++k)
+    {
+        const MapSpec& m = p->maps[k];
+        CostMapP& cm = c.map[k];
+        cm.kind = m.kind;
+        cm.start = m.start;
+        cm.length = m.length;
+        cm.n_frames = m.n_frames;
+        cm.rot_type = m.rot_type;
+        cm.stride = m.kind == EXO_MAP_EFF_FRAME ? 3 + rotation_length(m.rot_type) : 0;
+        if (m.kind == EXO_MAP_FRAMES) return fail(EXO_ERR_UNSUPPORTED, "raw-frame maps have no task cost");
+        if (m.kind == EXO_MAP_EFF_FRAME)
+        {
+            n_rot += m.n_frames;
+            for (int t = 0; t < d->T_goal; ++t)
+                for (int f = 0; f < m.n_frames; ++f)
+                {
+                    double* r = &goal[(size_t)t * LP + m.start + f * cm.stride + 3];
+                    if (m.rot_type == EXO_ROT_QUATERNION) r[3] = 1.0;
+                    if (m.rot_type == EXO_ROT_MATRIX) r[0] = r[4] = r[8] = 1.0;
+                }
+        }
+    }
+    if (d->goal) goal.assign(d->goal, d->goal + (size_t)d->T_goal * LP);
+    c.n_rot = n_rot;
+    goal_rot.assign((size_t)d->T_goal * n_rot * 9 + 9, 0.0);
+    for (int t = 0; t < d->T_goal; ++t)
+    {
+        int ri = 0;
+        for (int k = 0; k < n_maps; ++k)
+        {
+            const MapSpec& m = p->maps[k];
+            if (m.kind != EXO_MAP_EFF_FRAME) continue;
+            for (int f = 0; f < m.n_frames; ++f, ++ri)
+                host_get_rotation(&goal[(size_t)t * LP + m.start + f * c.map[k].stride + 3], m.rot_type, &goal_rot[((size_t)t * n_rot + ri) * 9]);
+        }
+    }
+    int rc = upload(&p->d_rho, d->rho, (size_t)d->T * n_maps);
+    if (rc == EXO_OK) rc = upload(&p->d_goal, goal.data(), goal.size());
+    if (rc == EXO_OK) rc = upload(&p->d_goal_rot, goal_rot.data(), goal_rot.size());
+    if (rc == EXO_OK) rc = upload(&p->d_W, d->W, d->W ? (size_t)N : 0);
+    if (rc != EXO_OK) return rc;
+    c.rho = p->d_rho;
+    c.goal = p->d_goal;
+    c.goal_rot = p->d_goal_rot;
+    c.W = p->d_W;
+    p->cost_set = true;
+    return EXO_OK;
+}
+
+int exo_problem_cost_batch(exo_problem* p, const double* d_x, const double* d_phi, int64_t n_traj, int32_t layout, double* d_cost_traj,
+                           double* d_cost_eval, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_x || !d_phi || (!d_cost_traj && !d_cost_eval)) return fail(EXO_ERR_INVALID, "NULL buffer");
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    int rc = fill_strides(p, layout, n_traj * p->cost.T, k);
+    if (rc != EXO_OK) return rc;
+    CostParams c = p->cost;
+    c.x = d_x;
+    c.phi = d_phi;
+    c.cost_traj = d_cost_traj;
+    c.cost_eval = d_cost_eval;
+    c.n_traj = n_traj;
+    c.x_se = k.x_se; c.x_sk = k.x_sk; c.phi_se = k.phi_se; c.phi_sk = k.phi_sk;
+    cudaError_t e = launch_cost(c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cost kernel launch");
+    p->launches++;
+    p->last_kernel = "exo_cost_kernel";
+    return EXO_OK;
+}
+
+int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream)
+{
+    if (n_traj < 0 || T < 1 || t_first < 0 || t_first >= T) return fail(EXO_ERR_INVALID, "bad trajectory shape");
+    if (op != EXO_REDUCE_MIN && op != EXO_REDUCE_SUM) return fail(EXO_ERR_INVALID, "unknown reduction");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_in || !d_out) return fail(EXO_ERR_INVALID, "NULL buffer");
+    cudaError_t e = launch_reduce(d_in, n_traj, T, t_first, op, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
     return EXO_OK;
 }
 

@@ -734,6 +734,12 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             op.jrow_off = m.start_jacobian;
             op.n_rows = G * (G - 1) / 2;
             op.n_items = S;
+            {
+                // bit 0: first SphereCollision op of the program (it initialises the per-evaluation minimum distance)
+                bool first = true;
+                for (const Op& prev : out.ops) first = first && prev.kind != OP_EMIT_SPHERES;
+                op.flags = first ? 1 : 0;
+            }
             // ints: G, n_acc, group_start[G+1], per sphere {src, acc, group, 0}, per column {contrib, mask_lo, mask_hi}
             out.ints.push_back(G);
             out.ints.push_back(n_acc);

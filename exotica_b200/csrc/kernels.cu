@@ -78,7 +78,7 @@ __device__ __forceinline__ double sph_exp(double t)
 // one sphere pair: accumulates weight * sigmoid into phi (if WITH_PHI) and weight * unit vector into (gx, gy, gz)
 template <bool WITH_PHI>
 __device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double rsum, double k5, double weight, double& phi, double& gx, double& gy,
-                                         double& gz)
+                                         double& gz, double& dmin)
 {
     const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
     double y;
@@ -95,7 +95,9 @@ __device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double
     if (WITH_PHI)
     {
         const double n = (n2 == 0.0) ? 0.0 : n2 * y;
-        const double den = 1.0 + sph_exp(k5 * (n - rsum));
+        const double gap = n - rsum;  // surface distance of the pair
+        dmin = (weight != 0.0) ? fmin(dmin, gap) : dmin;
+        const double den = 1.0 + sph_exp(k5 * gap);
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
         double e = fma(-den, r, 1.0);
@@ -141,6 +143,7 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
         __syncwarp();
         const int64_t e = e0 + ev;
         int out_idx = 0;
+        double dmin = CUDART_INF;  // smallest surface distance over all pairs of this evaluation
         for (int ga = 0; ga < G; ++ga)
         {
             for (int gb = ga + 1; gb < G; ++gb, ++out_idx)
@@ -189,10 +192,10 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
                                     const double w = ok ? 1.0 : 0.0;
                                     if (pass == 0)
                                         sph_pair<true>(pix - centre[4 * jj], piy - centre[4 * jj + 1], piz - centre[4 * jj + 2], ri + centre[4 * jj + 3],
-                                                       k5, w, ph, gx, gy, gz);
+                                                       k5, w, ph, gx, gy, gz, dmin);
                                     else
                                         sph_pair<false>(centre[4 * jj] - pix, centre[4 * jj + 1] - piy, centre[4 * jj + 2] - piz, 0.0, k5, w, ph, gx, gy,
-                                                        gz);
+                                                        gz, dmin);
                                 }
                             }
                         }
@@ -231,6 +234,12 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
                 }
                 __syncwarp();
             }
+        }
+        if (P.min_dist)
+        {
+            // new output (not in the reference): what the multi-GPU path all-reduces with min
+            for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+            if (lane == 0) P.min_dist[e] = (op.flags & 1) ? dmin : fmin(P.min_dist[e], dmin);
         }
         __syncwarp();  // the centre table is rewritten for the next evaluation
     }

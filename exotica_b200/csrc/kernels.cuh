@@ -18,6 +18,7 @@ struct KernelParams
     double* phi;
     double* jac;                   // may be NULL
     const double* generated;       // [T][n_generated][12] or NULL
+    double* min_dist;              // [n_evals] minimum of |p_i - p_j| - r_i - r_j over all sphere pairs, or NULL
     int64_t n_evals;
     // element strides (in doubles): addr = e * s_e + k * s_k  (Phi, X)   /  e * s_e + row * s_r + col * s_c  (J)
     int64_t x_se, x_sk;
@@ -106,5 +107,32 @@ bool chain_lower(const Program& prog, ChainParams& P);
 void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64_t n_evals, int64_t x_se, int64_t x_sk, int64_t phi_se,
                 int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
 cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream);
+
+// ---- batched task cost and per-trajectory reductions (cost_kernel.cu) -------------------------------------------------
+constexpr int COST_MAXMAPS = 16;
+struct CostMapP
+{
+    int32_t kind, start, length, n_frames, rot_type, stride, pad0, pad1;  // stride = 3 + rotation length (EffFrame)
+};
+struct CostParams
+{
+    const double* x;
+    const double* phi;
+    double* cost_traj;       // [n_traj] or NULL
+    double* cost_eval;       // [n_traj * T] or NULL
+    const double* rho;       // device, [T][n_maps]
+    const double* goal;      // device, [T_goal][length_phi]
+    const double* goal_rot;  // device, [T_goal][n_rot][9]: GetRotation of every EffFrame frame's goal, map order
+    const double* W;         // device, [n_ctrl] diagonal of W or NULL
+    double ct;
+    int64_t n_traj;
+    int64_t x_se, x_sk, phi_se, phi_sk;
+    int32_t T, t_first, T_goal, n_maps, n_ctrl, length_phi, n_rot, pad;
+    CostMapP map[COST_MAXMAPS];
+};
+cudaError_t launch_cost(const CostParams& P, cudaStream_t stream);
+// op 0: min, 1: sum over t in [t_first, T) of in[b * T + t]
+cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
+void host_get_rotation(const double* data, int type, double* out9);
 
 }  // namespace exo

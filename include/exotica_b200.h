@@ -208,6 +208,37 @@ int exo_problem_program_info(const exo_problem* problem, int32_t out[8]);
  * all joints revolute (0/1), requested frames}.  Host-only (valid after exo_problem_finalize, no device needed). */
 int exo_problem_chain_info(const exo_problem* problem, int32_t out[4]);
 
+/* ---- task cost and per-trajectory reductions (what the multi-GPU path gathers; SURVEY.md section 8 rows e, f1) --------
+ * exo_problem_set_cost   <- EndPoseTask / TimeIndexedTask::Initialize + SetRho + SetGoal (exotica_core/src/tasks.cpp:36-244),
+ *                            ct = 1/tau/T and W (abstract_time_indexed_problem.cpp:105, time_indexed_problem.cpp:43-50)
+ * exo_problem_cost_batch <- TimeIndexedTask::Update's ydiff = Phi - y with TaskSpaceVector::operator- (tasks.cpp:306-314,
+ *                            task_space_vector.cpp:64-91) + GetScalarTaskCost + GetScalarTransitionCost + GetCost
+ *                            (abstract_time_indexed_problem.cpp:299-342); T = 1: UnconstrainedEndPoseProblem::GetScalarCost
+ *                            (unconstrained_end_pose_problem.cpp:79-82).
+ * cost[b] = sum_{t = t_first}^{T-1} ct * ( sum_maps rho[t][map] |ydiff_map[t]|^2 + sum_i W[i] (x[t][i] - x[t-1][i])^2 ),
+ * t_first = 1 for T > 1 (the reference's GetCost skips t = 0), 0 for end-pose problems. */
+typedef struct
+{
+    int32_t T;           /* timesteps per trajectory (1: end-pose problem) */
+    int32_t T_goal;      /* 1 (same goal at every timestep) or T */
+    const double* rho;   /* [T][n_maps]: rho of every task map at every timestep (0: not a cost task) */
+    const double* goal;  /* [T_goal][length_Phi] in the problem's Phi layout, or NULL = TaskSpaceVector::SetZero goal */
+    double ct;           /* 1 / tau / T for time-indexed problems, 1 for end-pose problems */
+    const double* W;     /* [N] diagonal of the transition-cost matrix W, or NULL (no transition cost) */
+} exo_cost_desc;
+int exo_problem_set_cost(exo_problem* problem, const exo_cost_desc* cost);
+/* d_x / d_phi: the buffers of exo_problem_update_batch for n_traj * T evaluations in `layout`.  d_cost_traj[n_traj] and / or
+ * d_cost_eval[n_traj * T] (per-timestep terms; 0 for t < t_first).  Asynchronous on `stream`. */
+int exo_problem_cost_batch(exo_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int32_t layout,
+                           double* d_cost_traj, double* d_cost_eval, void* stream);
+/* New output of SphereCollision (not in the reference): min over all sphere pairs of |p_i - p_j| - r_i - r_j, written per
+ * evaluation to d_min_distance[n_evals] by every following exo_problem_update_batch (NULL switches it off). */
+int exo_problem_set_min_distance_output(exo_problem* problem, double* d_min_distance);
+#define EXO_REDUCE_MIN 0
+#define EXO_REDUCE_SUM 1
+/* d_out[b] = min / sum over t in [t_first, T) of d_in[b * T + t] */
+int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1227,3 +1227,135 @@ int exo_oracle_problem_update_batch(exo_oracle* o, const double* X, long E, int 
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Task cost: TaskSpaceVector difference, scalar task and transition cost */
+/* ------------------------------------------------------------------------------------------- */
+/* KDL::Rotation::EulerZYZ(alfa, beta, gamma) */
+static void rot_from_euler_zyz(double a, double b, double g, double* out)
+{
+    double sa = sin(a), ca = cos(a), sb = sin(b), cb = cos(b), sg = sin(g), cg = cos(g);
+    out[0] = ca * cb * cg - sa * sg;
+    out[1] = -ca * cb * sg - sa * cg;
+    out[2] = ca * sb;
+    out[3] = sa * cb * cg + ca * sg;
+    out[4] = -sa * cb * sg + ca * cg;
+    out[5] = sa * sb;
+    out[6] = -sb * cg;
+    out[7] = sb * sg;
+    out[8] = cb;
+}
+
+/* exotica::GetRotation (exotica_core/src/tools/conversions.cpp:114-148) */
+int exo_oracle_get_rotation(const double* data, int type, double* out)
+{
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    switch (type)
+    {
+        case EXO_ORC_QUATERNION:
+            rot_from_quaternion(data[0], data[1], data[2], data[3], out); /* KDL::Rotation::Quaternion: no normalisation */
+            return 0;
+        case EXO_ORC_RPY:
+            rot_from_rpy(data[0], data[1], data[2], out);
+            return 0;
+        case EXO_ORC_ZYX:
+            rot_from_rpy(data[2], data[1], data[0], out); /* EulerZYX(a,b,c) = RPY(c,b,a) */
+            return 0;
+        case EXO_ORC_ZYZ:
+            rot_from_euler_zyz(data[0], data[1], data[2], out);
+            return 0;
+        case EXO_ORC_ANGLE_AXIS:
+        {
+            double angle = vec_norm_kdl(data);
+            if (fabs(angle) > 1e-10)
+            {
+                /* KDL::Rotation::Rot(axis, angle): normalises the axis, then Rot2 */
+                double ax[3] = {data[0] / angle, data[1] / angle, data[2] / angle};
+                rot_rot2(ax, angle, out);
+            }
+            else
+                memcpy(out, ident, sizeof(ident));
+            return 0;
+        }
+        case EXO_ORC_MATRIX:
+            memcpy(out, data, 9 * sizeof(double));
+            return 0;
+        default:
+            return -1;
+    }
+}
+
+/* TaskSpaceVector::operator- (exotica_core/src/task_space_vector.cpp:64-91) on the problem's Phi layout:
+ * ydiff[length_jacobian]; rotation sub-blocks become rotvec = M1 * (M2^-1 M1).GetRot(). */
+int exo_oracle_problem_ydiff(const exo_oracle* o, const double* phi, const double* goal, double* ydiff)
+{
+    int k, i, f;
+    for (k = 0; k < o->n_maps; ++k)
+    {
+        const taskmap_t* m = &o->maps[k];
+        if (m->kind == EXO_ORC_MAP_EFF_FRAME)
+        {
+            const int rl = rotation_length(m->rot_type), big = 3 + rl;
+            for (f = 0; f < m->n_frames; ++f)
+            {
+                const double* a = phi + m->start + f * big;
+                const double* b = goal + m->start + f * big;
+                double* out = ydiff + m->start_jacobian + 6 * f;
+                double M1[9], M2[9], M2t[9], M[9], rv[3];
+                for (i = 0; i < 3; ++i) out[i] = a[i] - b[i];
+                if (exo_oracle_get_rotation(a + 3, m->rot_type, M1) || exo_oracle_get_rotation(b + 3, m->rot_type, M2)) return -1;
+                rot_transpose(M2, M2t);
+                rot_mul(M2t, M1, M);
+                rot_get_rot(M, rv);
+                rot_vec(M1, rv, out + 3);
+            }
+        }
+        else
+            for (i = 0; i < m->length; ++i) ydiff[m->start_jacobian + i] = phi[m->start + i] - goal[m->start + i];
+    }
+    return 0;
+}
+
+/* Scalar cost of one trajectory X[T][N] (AbstractTimeIndexedProblem::GetCost, abstract_time_indexed_problem.cpp:299-342):
+ *   sum_{t=t_first}^{T-1} ct * ( ydiff[t]^T S[t] ydiff[t] + xdiff[t]^T W xdiff[t] ),  S[t] = diag(rho[t][map] per Jacobian row),
+ * xdiff[t] = x[t] - x[t-1].  End-pose problems: T = 1, t_first = 0, ct = 1, W = NULL
+ * (UnconstrainedEndPoseProblem::GetScalarCost, unconstrained_end_pose_problem.cpp:79-82).
+ * rho[T][n_maps]; goal[T_goal][length_Phi] with T_goal in {1, T}; gen: per-timestep generated frames or NULL. */
+double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
+                                  double ct, const double* W, const double* gen, int n_gen, double* cost_t)
+{
+    const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
+    double* phi = (double*)malloc((size_t)(lp > 0 ? lp : 1) * sizeof(double));
+    double* yd = (double*)malloc((size_t)(lj > 0 ? lj : 1) * sizeof(double));
+    double total = 0.0;
+    int t, k, i, g;
+    for (t = 0; t < T; ++t)
+    {
+        double c = 0.0;
+        if (cost_t) cost_t[t] = 0.0;
+        if (t < t_first) continue;
+        if (gen)
+            for (g = 0; g < n_gen; ++g) exo_oracle_set_generated(o, g, gen + ((size_t)t * n_gen + g) * 12);
+        exo_oracle_problem_update(o, X + (size_t)t * N, phi, NULL);
+        exo_oracle_problem_ydiff(o, phi, goal + (size_t)(T_goal > 1 ? t : 0) * lp, yd);
+        for (k = 0; k < o->n_maps; ++k)
+        {
+            const taskmap_t* m = &o->maps[k];
+            double s = 0.0;
+            for (i = 0; i < m->length_jacobian; ++i) s += yd[m->start_jacobian + i] * yd[m->start_jacobian + i];
+            c += rho[(size_t)t * o->n_maps + k] * s;
+        }
+        if (W && t > 0)
+            for (i = 0; i < N; ++i)
+            {
+                double d = X[(size_t)t * N + i] - X[(size_t)(t - 1) * N + i];
+                c += W[i] * d * d;
+            }
+        c *= ct;
+        if (cost_t) cost_t[t] = c;
+        total += c;
+    }
+    free(phi);
+    free(yd);
+    return total;
+}

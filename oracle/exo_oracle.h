@@ -117,6 +117,14 @@ int exo_oracle_problem_update(exo_oracle* o, const double* x, double* phi, doubl
 int exo_oracle_problem_update_batch(exo_oracle* o, const double* X, long E, int T, const double* gen, int n_gen,
                                     double* phi, double* jac, int n_threads);
 
+/* ---- task cost ----
+ * exotica::GetRotation (tools/conversions.cpp:114-148); TaskSpaceVector::operator- (task_space_vector.cpp:64-91);
+ * AbstractTimeIndexedProblem::GetCost (abstract_time_indexed_problem.cpp:299-342). */
+int exo_oracle_get_rotation(const double* data, int type, double* rot9);
+int exo_oracle_problem_ydiff(const exo_oracle* o, const double* phi, const double* goal, double* ydiff);
+double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
+                                  double ct, const double* W, const double* gen, int n_gen, double* cost_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,11 @@ def lib():
         L.exo_oracle_problem_update.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.exo_oracle_problem_update_batch.argtypes = [ctypes.c_void_p, _dp, ctypes.c_long, ctypes.c_int, _dp, ctypes.c_int,
                                                       _dp, _dp, ctypes.c_int]
+        L.exo_oracle_get_rotation.argtypes = [_dp, ctypes.c_int, _dp]
+        L.exo_oracle_problem_ydiff.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
+        L.exo_oracle_trajectory_cost.restype = ctypes.c_double
+        L.exo_oracle_trajectory_cost.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_double,
+                                                 _dp, _dp, ctypes.c_int, _dp]
         _LIB = L
     return _LIB
 
@@ -83,6 +88,14 @@ def set_rotation(rot9, rot_type):
     out = np.zeros(9)
     n = lib().exo_oracle_set_rotation(_d(rot9), ROTATION_TYPES[rot_type] if isinstance(rot_type, str) else rot_type, _d(out))
     return out[:n]
+
+
+def get_rotation(data, rot_type):
+    """exotica::GetRotation (tools/conversions.cpp:114-148): encoding -> row-major rotation matrix."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    out = np.zeros(9)
+    lib().exo_oracle_get_rotation(_d(data), ROTATION_TYPES[rot_type] if isinstance(rot_type, str) else rot_type, _d(out))
+    return out
 
 
 IDENTITY_FRAME = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
@@ -227,6 +240,56 @@ class Oracle(object):
         jac = np.zeros((E, self.n, self.length_jacobian))
         lib().exo_oracle_problem_update_batch(self.h, _d(X), E, T, gp, n_gen, _d(phi), _d(jac), n_threads)
         return phi, np.ascontiguousarray(jac.transpose(0, 2, 1))
+
+
+    # ---- task cost ---------------------------------------------------------
+    def zero_goal(self):
+        """TaskSpaceVector::SetZero (task_space_vector.cpp:54-62): zeros with identity rotation encodings."""
+        y = np.zeros(self.length_phi)
+        start = 0
+        ident = np.array([1.0, 0, 0, 0, 1, 0, 0, 0, 1])
+        for m in self.maps:
+            kind = MAP_KINDS[m["type"]]
+            nf = len(m.get("EndEffector", []))
+            if kind == 0:
+                rl = ROTATION_LENGTH[ROTATION_TYPES[m.get("Type", "RPY")]]
+                for f in range(nf):
+                    y[start + f * (3 + rl) + 3:start + (f + 1) * (3 + rl)] = set_rotation(ident, m.get("Type", "RPY"))
+                start += nf * (3 + rl)
+            elif kind == 1:
+                start += 3 * nf
+            elif kind == 2:
+                start += self.n
+            else:
+                g = len(set(f.get("Group", "default") for f in m["EndEffector"]))
+                start += g * (g - 1) // 2
+        return y
+
+    def ydiff(self, phi, goal):
+        out = np.zeros(self.length_jacobian)
+        lib().exo_oracle_problem_ydiff(self.h, _d(np.ascontiguousarray(phi, dtype=np.float64)), _d(np.ascontiguousarray(goal, dtype=np.float64)),
+                                       _d(out))
+        return out
+
+    def trajectory_cost(self, X, rho, goal=None, ct=1.0, W=None, t_first=None, generated=None):
+        """Scalar cost of one trajectory X[T][N] and its per-timestep terms (AbstractTimeIndexedProblem::GetCost).
+        rho[T][n_maps]; goal[1 or T][length_Phi] (None: SetZero goal); end-pose problems: T = 1, t_first = 0."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.n)
+        T = X.shape[0]
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (T, len(self.maps))))
+        goal = self.zero_goal() if goal is None else goal
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1, self.length_phi)
+        if t_first is None:
+            t_first = 1 if T > 1 else 0
+        n_gen, gp = 0, None
+        if generated is not None:
+            generated = np.ascontiguousarray(generated, dtype=np.float64).reshape(T, -1, 12)
+            n_gen, gp = generated.shape[1], _d(generated)
+        cost_t = np.zeros(T)
+        Wp = _d(np.ascontiguousarray(W, dtype=np.float64)) if W is not None else None
+        total = lib().exo_oracle_trajectory_cost(self.h, _d(X), T, int(t_first), _d(rho), _d(goal), goal.shape[0], float(ct), Wp, gp, n_gen,
+                                                 _d(cost_t))
+        return total, cost_t
 
 
 def load_robot(urdf_path, srdf_path, joint_group="", add_collision_elements=False):

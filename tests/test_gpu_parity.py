@@ -307,3 +307,97 @@ def test_errors_are_loud(oracle_lib):
         p2.add_task_map(_capi.MAP_EFF_POSITION, elem_a=[999])  # unknown link
     with pytest.raises(_capi.ExoticaError):
         p2.update_batch_device(None, 1, None, None)  # not finalized
+
+
+# ---- task cost and per-trajectory reductions (SURVEY.md section 8 rows e, f1) ------------------------------------------------
+def _gpu_costs(prob, X, B, T, rho, goal=None, ct=1.0, W=None, layout=_capi.LAYOUT_SOA):
+    """Runs the update kernel, then the cost kernel on its device outputs; returns (cost[B], cost_eval[B*T])."""
+    E, N = X.shape
+    LP, LJ = prob.length_phi, prob.length_jacobian
+    dx, dphi, djac = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(E * LP), _capi.DeviceBuffer(E * LJ * N)
+    dct, dce = _capi.DeviceBuffer(B), _capi.DeviceBuffer(E)
+    dx.upload(X.T if layout == _capi.LAYOUT_SOA else X)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T, layout=layout)
+    prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
+    prob.cost_batch_device(dx.ptr, dphi.ptr, B, dct.ptr, dce.ptr, layout=layout)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    return dct.download((B,)), dce.download((E,))
+
+
+@pytest.mark.parametrize("rot", ["RPY", "Quaternion", "ZYZ", "AngleAxis", "Matrix", "ZYX"])
+def test_trajectory_cost_matches_oracle(oracle_lib, rot):
+    # cfg 3 shape with costs: EffFrame + JointLimit, goal with a rotated target, rho per timestep, transition cost W
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": rot, "EndEffector": [{"Link": "lwr_arm_7_link"}, {"Link": "lwr_arm_4_link", "LinkOffset": [0, 0, 0.1]}]},
+            {"type": "JointLimit", "SafePercentage": 0.1}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T = 12, 40
+    rng = np.random.default_rng(5)
+    q0 = random_states(orc, B, seed=6)
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+    rho = np.ones((T, 2))
+    rho[:, 0] = np.linspace(0.0, 10.0, T)
+    rho[3, 1] = 0.0
+    goal = orc.zero_goal()
+    rl = _capi.ROTATION_LENGTH[_capi.ROTATION_TYPES[rot]]
+    target = oracle_lib.get_frame([0.4, 0.1, 0.6, 0.3, -0.2, 0.5])
+    for f in range(2):
+        goal[f * (3 + rl):f * (3 + rl) + 3] = target[9:]
+        goal[f * (3 + rl) + 3:(f + 1) * (3 + rl)] = oracle_lib.set_rotation(target[:9], rot)
+    W = np.linspace(1.0, 2.0, 7)
+    ct = 1.0 / 0.05 / T
+    cost, cost_eval = _gpu_costs(prob, X.reshape(B * T, 7), B, T, rho, goal=goal, ct=ct, W=W)
+    for b in range(B):
+        ref, ref_t = orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)
+        assert np.max(np.abs(cost_eval[b * T:(b + 1) * T] - ref_t)) <= 1e-9 * max(1.0, np.max(ref_t))
+        assert abs(cost[b] - ref) <= 1e-9 * max(1.0, ref)
+        assert cost_eval[b * T] == 0.0  # GetCost starts at t = 1
+
+
+def test_end_pose_cost_and_layouts(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_6_link"}]}]
+    orc.set_problem(maps)
+    X = random_states(orc, 257, seed=9)
+    for layout in (_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR):
+        tree, prob = gpu_problem_from_maps(orc, maps)
+        cost, cost_eval = _gpu_costs(prob, X, 257, 1, [2.0, 0.5], layout=layout)
+        ref = np.array([orc.trajectory_cost(X[e:e + 1], [2.0, 0.5])[0] for e in range(257)])
+        assert np.max(np.abs(cost - ref)) <= 1e-10 * max(1.0, ref.max())
+        assert np.array_equal(cost, cost_eval)
+
+
+def test_min_sphere_distance_and_trajectory_min(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = _lwr_sphere_maps()
+    # obstacle spheres fixed in the world instead of on a trajectory-driven link
+    for f in maps[0]["EndEffector"]:
+        if f["Group"] == "Obstacle":
+            f["Link"] = ""
+            f["LinkOffset"] = [0.45, f["LinkOffset"][1], 0.55]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T = 9, 33
+    X = random_states(orc, B * T, seed=15)
+    E, N = X.shape
+    dx, dphi, djac, dmin, dtraj = (_capi.DeviceBuffer(n) for n in (E * N, E, E * N, E, B))
+    dx.upload(X.T)
+    prob.set_min_distance_output(dmin.ptr)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T)
+    _capi.check(_capi.lib().exo_trajectory_reduce(dmin.ptr, B, T, 0, 0, dtraj.ptr, None))
+    _capi.check(_capi.lib().exo_device_synchronize())
+    got, got_traj = dmin.download((E,)), dtraj.download((B,))
+    # reference: centre distances from the oracle's frames
+    frames = maps[0]["EndEffector"]
+    orc.request_frames([{k: v for k, v in f.items() if k in ("Link", "LinkOffset")} for f in frames])
+    ref = np.zeros(E)
+    rob = [i for i, f in enumerate(frames) if f["Group"] == "Robot"]
+    obs = [i for i, f in enumerate(frames) if f["Group"] == "Obstacle"]
+    for e in range(E):
+        orc.update(X[e])
+        p = orc.phi()[:, 9:]
+        ref[e] = min(np.linalg.norm(p[i] - p[j]) - frames[i]["Radius"] - frames[j]["Radius"] for i in rob for j in obs)
+    assert np.max(np.abs(got - ref)) <= 1e-10
+    assert np.max(np.abs(got_traj - ref.reshape(B, T).min(axis=1))) <= 1e-10
+    orc.set_problem(maps)
