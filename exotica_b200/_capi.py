@@ -82,6 +82,7 @@ SYMBOLS = [
     ("exo_problem_set_kernel", ctypes.c_int, [_vp, ctypes.c_int]),
     ("exo_problem_set_cost", ctypes.c_int, [_vp, ctypes.POINTER(CostDesc)]),
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
+    ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
     ("exo_trajectory_reduce", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
@@ -334,6 +335,14 @@ class Problem(object):
 
     def cost_batch_device(self, d_x, d_phi, n_traj, d_cost_traj=None, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_batch(self.h, d_x, d_phi, int(n_traj), int(layout), d_cost_traj, d_cost_eval, stream))
+
+    def cost_batch_host(self, X):
+        """X[B][T][N] (or [B][N] for end-pose problems) -> cost[B] through the host pipeline."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        B = X.shape[0]
+        out = np.empty(B)
+        check(lib().exo_problem_cost_batch_host(self.h, X.ctypes.data, B, LAYOUT_AOS_ROWMAJOR, out.ctypes.data))
+        return out
 
     def set_min_distance_output(self, d_ptr):
         check(lib().exo_problem_set_min_distance_output(self.h, d_ptr))

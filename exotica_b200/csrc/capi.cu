@@ -77,6 +77,7 @@ struct exo_problem
     double* d_x[NBUF] = {nullptr, nullptr, nullptr};
     double* d_phi[NBUF] = {nullptr, nullptr, nullptr};
     double* d_jac[NBUF] = {nullptr, nullptr, nullptr};
+    double* d_cost[NBUF] = {nullptr, nullptr, nullptr};
     int64_t pipe_chunk = 0;
     bool pipe_has_jac = false;
 };
@@ -297,7 +298,8 @@ static void free_pipeline(exo_problem* p)
         if (p->d_x[i]) cudaFree(p->d_x[i]);
         if (p->d_phi[i]) cudaFree(p->d_phi[i]);
         if (p->d_jac[i]) cudaFree(p->d_jac[i]);
-        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = nullptr;
+        if (p->d_cost[i]) cudaFree(p->d_cost[i]);
+        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = p->d_cost[i] = nullptr;
     }
     p->pipe_chunk = 0;
 }
@@ -626,6 +628,7 @@ static int ensure_pipeline(exo_problem* p, int64_t chunk, bool with_jac)
         CUDA_TRY(cudaMalloc((void**)&p->d_x[i], std::max<size_t>(8, chunk * N * sizeof(double))));
         CUDA_TRY(cudaMalloc((void**)&p->d_phi[i], std::max<size_t>(8, chunk * LP * sizeof(double))));
         if (with_jac) CUDA_TRY(cudaMalloc((void**)&p->d_jac[i], std::max<size_t>(8, chunk * LJ * N * sizeof(double))));
+        CUDA_TRY(cudaMalloc((void**)&p->d_cost[i], std::max<size_t>(8, chunk * sizeof(double))));
     }
     p->pipe_chunk = chunk;
     p->pipe_has_jac = with_jac;
@@ -805,6 +808,38 @@ int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t
     if (!d_in || !d_out) return fail(EXO_ERR_INVALID, "NULL buffer");
     cudaError_t e = launch_reduce(d_in, n_traj, T, t_first, op, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+    return EXO_OK;
+}
+
+int exo_problem_cost_batch_host(exo_problem* p, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!h_x || !h_cost_traj) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (layout != EXO_LAYOUT_AOS_ROWMAJOR && layout != EXO_LAYOUT_AOS_COLMAJOR)
+        return fail(EXO_ERR_UNSUPPORTED, "host cost batches take evaluation-major states X[B][T][N]");
+    const int64_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, T = p->cost.T;
+    // whole trajectories per chunk, ~16 MiB of Phi per buffer; forward kinematics only (no Jacobian is produced or moved)
+    int64_t traj_per_chunk = std::max<int64_t>(1, (16ll << 20) / std::max<int64_t>(1, (N + LP) * T * (int64_t)sizeof(double)));
+    if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
+    int rc = ensure_pipeline(p, traj_per_chunk * T, false);
+    if (rc != EXO_OK) return rc;
+    int b = 0;
+    for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
+    {
+        const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
+        cudaStream_t s = p->streams[b];
+        CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
+        rc = launch(p, p->d_x[b], n, n, (int32_t)T, layout, p->d_phi[b], nullptr, s, false);
+        if (rc != EXO_OK) return rc;
+        rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
+        if (rc != EXO_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
     return EXO_OK;
 }
 

@@ -372,6 +372,8 @@ public:
     virtual int TaskSpaceJacobianDim() { return TaskSpaceDim(); }
     virtual int Kind() const = 0;  // exo_map_kind
     virtual void FillDescriptor(exo_task_map_desc& desc) {}
+    // TaskSpaceVector::SetZero for this map's entries (task_space_vector.cpp:54-62 over GetLieGroupIndices): y is pre-zeroed
+    virtual void FillZeroGoal(double* y) {}
     std::vector<KinematicFrameRequest> GetFrames() const { return frames_; }
     const std::string& GetObjectName() const { return object_name_; }
     // One configuration through the GPU (a private one-map problem): phi[length], jacobian[length_jacobian x N] col-major
@@ -410,6 +412,16 @@ public:
     int TaskSpaceJacobianDim() override { return (int)frames_.size() * 6; }
     int Kind() const override { return EXO_MAP_EFF_FRAME; }
     void FillDescriptor(exo_task_map_desc& desc) override { desc.rotation_type = (int)rotation_type_; }
+    void FillZeroGoal(double* y) override
+    {
+        // identity rotation encodings at the Lie-group entries (eff_frame.cpp:43-51): quaternion 0 0 0 1, matrix I, else zeros
+        for (int f = 0; f < (int)frames_.size(); ++f)
+        {
+            double* r = y + f * big_stride_ + 3;
+            if (rotation_type_ == RotationType::QUATERNION) r[3] = 1.0;
+            if (rotation_type_ == RotationType::MATRIX) r[0] = r[4] = r[8] = 1.0;
+        }
+    }
     const RotationType& get_rotation_type() const { return rotation_type_; }
 
 private:
@@ -510,6 +522,11 @@ public:
     //  host buffers: X/Phi/J in `layout`; device variant takes device pointers + stream.
     void UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian);
     void UpdateBatchDevice(const double* d_x, int64_t n_evals, int layout, double* d_phi, double* d_jacobian, void* stream);
+    // NEW: scalar cost of every trajectory (time-indexed: GetCost, abstract_time_indexed_problem.cpp:299-307; end-pose:
+    // GetScalarCost, unconstrained_end_pose_problem.cpp:79-82) for X[n_trajectories][T][N]; forward kinematics only.
+    void CostBatch(const double* x, int64_t n_trajectories, double* cost);
+    // device variant on the buffers of UpdateBatchDevice; cost_eval (per timestep) may be NULL
+    void CostBatchDevice(const double* d_x, const double* d_phi, int64_t n_trajectories, int layout, double* d_cost, double* d_cost_eval, void* stream);
     exo_problem* GetBackend();
     float LastKernelMs();
     int64_t LaunchCount();
@@ -529,7 +546,12 @@ protected:
     // cost task indexing (Task::Initialize, tasks.cpp:36-66): names of the maps used by Cost
     std::vector<std::string> cost_tasks_;
     std::vector<std::vector<double>> cost_rho_;  // per cost task: rho (1 value, or T values)
+    std::vector<std::vector<double>> cost_goal_; // per cost task: Goal (empty = the SetZero goal)
+    double cost_ct_ = 1.0;                       // 1/tau/T for time-indexed problems
+    std::vector<double> cost_W_;                 // diagonal of W (time-indexed problems), empty = no transition cost
+    bool cost_pushed_ = false;
     void ParseCost(const Initializer& init, int T);
+    void PushCost();
 };
 
 class UnconstrainedEndPoseProblem : public PlanningProblem  // unconstrained_end_pose_problem.cpp

@@ -452,6 +452,17 @@ int exo_host_problem_update_batch_device(exo_host_problem* p, const double* d_x,
     HOST_TRY(p->problem->UpdateBatchDevice(d_x, n_evals, layout, d_phi, d_jac, stream))
 }
 
+int exo_host_problem_cost_batch(exo_host_problem* p, const double* x, int64_t n_traj, double* cost)
+{
+    HOST_TRY(p->problem->CostBatch(x, n_traj, cost))
+}
+
+int exo_host_problem_cost_batch_device(exo_host_problem* p, const double* d_x, const double* d_phi, int64_t n_traj, int layout, double* d_cost,
+                                       double* d_cost_eval, void* stream)
+{
+    HOST_TRY(p->problem->CostBatchDevice(d_x, d_phi, n_traj, layout, d_cost, d_cost_eval, stream))
+}
+
 int exo_host_problem_last_kernel_ms(exo_host_problem* p, float* ms)
 {
     HOST_TRY(*ms = p->problem->LastKernelMs())

@@ -438,6 +438,7 @@ void PlanningProblem::InvalidateBackend()
 {
     if (backend_) exo_problem_destroy(backend_);
     backend_ = nullptr;
+    cost_pushed_ = false;
 }
 
 void PlanningProblem::InstantiateBase(const Initializer& init)
@@ -523,6 +524,8 @@ void PlanningProblem::ParseCost(const Initializer& init, int T)
     // Task::Initialize (tasks.cpp:36-66) + Rho handling (tasks.cpp:68-118,166-244): a map is used iff some rho != 0
     cost_tasks_.clear();
     cost_rho_.clear();
+    cost_goal_.clear();
+    for (TaskMapPtr& m : tasks_) m->is_used = false;
     const char* blocks[3] = {"Cost", "Inequality", "Equality"};
     for (const char* block : blocks)
         for (const Initializer& task : init.List(block))
@@ -535,16 +538,60 @@ void PlanningProblem::ParseCost(const Initializer& init, int T)
                 rho = ParseVector(task.Get("Rho", ""));
                 if (rho.size() != 1 && (int)rho.size() != T) ThrowPretty("Invalid task rho size! Expecting 1 or " + std::to_string(T) + " got " + std::to_string(rho.size()));
             }
+            std::vector<double> goal;
+            if (task.Has("Goal"))
+            {
+                goal = ParseVector(task.Get("Goal", ""));
+                const int len = task_maps_[name]->TaskSpaceDim();
+                if (!goal.empty() && (int)goal.size() != len)
+                    ThrowPretty("Invalid task goal size! Expecting " + std::to_string(len) + " got " + std::to_string(goal.size()));  // tasks.cpp:96
+            }
+            for (double r : rho)
+                if (r != 0.0) task_maps_[name]->is_used = true;
+            if (std::string(block) != "Cost") continue;  // only Cost tasks enter the scalar cost; all blocks drive is_used
             cost_tasks_.push_back(name);
             cost_rho_.push_back(rho);
+            cost_goal_.push_back(goal);
         }
-    for (TaskMapPtr& m : tasks_) m->is_used = false;
-    for (size_t i = 0; i < cost_tasks_.size(); ++i)
+}
+
+void PlanningProblem::PushCost()
+{
+    // EndPoseTask / TimeIndexedTask::Initialize (tasks.cpp:68-118,166-244): rho and goal of every Cost task, per map
+    exo_problem* p = GetBackend();
+    if (cost_pushed_) return;
+    const int T = GetT(), n_maps = (int)tasks_.size();
+    std::vector<double> rho((size_t)T * n_maps, 0.0), goal(length_Phi, 0.0);
+    for (int i = 0; i < n_maps; ++i) tasks_[i]->FillZeroGoal(goal.data() + tasks_[i]->start);  // TaskSpaceVector::SetZero
+    for (size_t c = 0; c < cost_tasks_.size(); ++c)
     {
-        bool nonzero = false;
-        for (double r : cost_rho_[i]) nonzero = nonzero || (r != 0.0);
-        if (nonzero) task_maps_[cost_tasks_[i]]->is_used = true;
+        const TaskMapPtr& m = task_maps_[cost_tasks_[c]];
+        for (int t = 0; t < T; ++t) rho[(size_t)t * n_maps + m->id] = cost_rho_[c].size() == 1 ? cost_rho_[c][0] : cost_rho_[c][t];
+        if (!cost_goal_[c].empty()) std::copy(cost_goal_[c].begin(), cost_goal_[c].end(), goal.begin() + m->start);
     }
+    exo_cost_desc d;
+    d.T = T;
+    d.T_goal = 1;
+    d.rho = rho.data();
+    d.goal = goal.data();
+    d.ct = cost_ct_;
+    d.W = cost_W_.empty() ? nullptr : cost_W_.data();
+    CheckRc(exo_problem_set_cost(p, &d));
+    cost_pushed_ = true;
+}
+
+void PlanningProblem::CostBatch(const double* x, int64_t n_trajectories, double* cost)
+{
+    PushCost();
+    CheckRc(exo_problem_cost_batch_host(GetBackend(), x, n_trajectories, EXO_LAYOUT_AOS_ROWMAJOR, cost));
+    number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
+}
+
+void PlanningProblem::CostBatchDevice(const double* d_x, const double* d_phi, int64_t n_trajectories, int layout, double* d_cost, double* d_cost_eval,
+                                      void* stream)
+{
+    PushCost();
+    CheckRc(exo_problem_cost_batch(GetBackend(), d_x, d_phi, n_trajectories, layout, d_cost, d_cost_eval, stream));
 }
 
 exo_problem* PlanningProblem::GetBackend()
@@ -630,6 +677,25 @@ void TimeIndexedProblem::Instantiate(const Initializer& init)
     if (tau.size() != 1 || tau[0] <= 0.) ThrowPretty("tau_ is expected to be greater than 0. (tau_=" + init.Get("tau", "") + ")");
     tau_ = tau[0];
     ParseCost(init, T_);
+    // ct = 1 / tau / T (abstract_time_indexed_problem.cpp:105); W = I * Wrate, or diag(W) * Wrate (time_indexed_problem.cpp:43-50)
+    cost_ct_ = 1.0 / tau_ / T_;
+    {
+        double wrate = 1.0;
+        if (init.Has("Wrate"))
+        {
+            const std::vector<double> wr = ParseVector(init.Get("Wrate", ""));
+            if (wr.size() == 1) wrate = wr[0];
+        }
+        cost_W_.assign(N, wrate);
+        if (init.Has("W"))
+        {
+            const std::vector<double> w = ParseVector(init.Get("W", ""));
+            if ((int)w.size() == N)
+                for (int i = 0; i < N; ++i) cost_W_[i] = w[i] * wrate;
+            else if (!w.empty())
+                ThrowPretty("W dimension mismatch! Expected " + std::to_string(N) + ", got " + std::to_string(w.size()));
+        }
+    }
     // time_indexed_problem.cpp:57-72
     if (init.Has("LowerBound"))
     {

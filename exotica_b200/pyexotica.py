@@ -402,6 +402,22 @@ class PlanningProblem(object):
         """Same, on device pointers already resident in HBM (asynchronous on `stream`)."""
         _check(_host.lib().exo_host_problem_update_batch_device(self._h, d_x, int(n_evals), int(layout), d_phi, d_jacobian, stream))
 
+    def cost_batch(self, X):
+        """Scalar cost of every trajectory: X[B][T][N] (end-pose problems: X[B][N]) -> cost[B].  Time-indexed problems:
+        AbstractTimeIndexedProblem.get_cost() of each trajectory (sum over t = 1..T-1 of task + transition cost); end-pose
+        problems: get_scalar_cost().  Only X crosses PCIe in, 8 bytes per trajectory come back."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        want = (self.T, self.N) if self.time_indexed else (self.N,)
+        if X.ndim != len(want) + 1 or tuple(X.shape[1:]) != want:
+            raise ExoticaError("Wrong state vector size! Got %s expected (B, %s)" % (X.shape, ", ".join(str(v) for v in want)))
+        cost = np.empty(X.shape[0])
+        _check(_host.lib().exo_host_problem_cost_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data))
+        return cost
+
+    def cost_batch_device(self, d_x, d_phi, n_trajectories, d_cost, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
+        """Same on the device buffers of update_batch_device (asynchronous on `stream`)."""
+        _check(_host.lib().exo_host_problem_cost_batch_device(self._h, d_x, d_phi, int(n_trajectories), int(layout), d_cost, d_cost_eval, stream))
+
     def last_kernel_ms(self):
         ms = ctypes.c_float(0)
         _check(_host.lib().exo_host_problem_last_kernel_ms(self._h, ctypes.byref(ms)))

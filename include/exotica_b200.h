@@ -231,6 +231,9 @@ int exo_problem_set_cost(exo_problem* problem, const exo_cost_desc* cost);
  * d_cost_eval[n_traj * T] (per-timestep terms; 0 for t < t_first).  Asynchronous on `stream`. */
 int exo_problem_cost_batch(exo_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int32_t layout,
                            double* d_cost_traj, double* d_cost_eval, void* stream);
+/* Host buffers: X[n_traj][T][N] (evaluation-major) -> cost[n_traj].  Chunked H2D -> forward kinematics + task maps (no
+ * Jacobian is computed or moved) -> cost kernel -> D2H of 8 bytes per trajectory; returns when h_cost_traj is complete. */
+int exo_problem_cost_batch_host(exo_problem* problem, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj);
 /* New output of SphereCollision (not in the reference): min over all sphere pairs of |p_i - p_j| - r_i - r_j, written per
  * evaluation to d_min_distance[n_evals] by every following exo_problem_update_batch (NULL switches it off). */
 int exo_problem_set_min_distance_output(exo_problem* problem, double* d_min_distance);

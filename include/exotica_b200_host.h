@@ -75,6 +75,11 @@ int exo_host_problem_update(exo_host_problem* problem, const double* x, int n, i
 int exo_host_problem_update_batch(exo_host_problem* problem, const double* x, int64_t n_evals, int layout, double* phi, double* jac);
 int exo_host_problem_update_batch_device(exo_host_problem* problem, const double* d_x, int64_t n_evals, int layout, double* d_phi,
                                          double* d_jac, void* stream);
+/* NEW scalar cost of every trajectory: X[n_traj][T][N] (T = 1: X[n_traj][N]) -> cost[n_traj]
+ * (GetCost, abstract_time_indexed_problem.cpp:299-307; GetScalarCost, unconstrained_end_pose_problem.cpp:79-82). */
+int exo_host_problem_cost_batch(exo_host_problem* problem, const double* x, int64_t n_traj, double* cost);
+int exo_host_problem_cost_batch_device(exo_host_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int layout,
+                                       double* d_cost, double* d_cost_eval, void* stream);
 int exo_host_problem_last_kernel_ms(exo_host_problem* problem, float* ms);
 int64_t exo_host_problem_launch_count(exo_host_problem* problem);
 int64_t exo_host_problem_update_count(exo_host_problem* problem); /* number_of_problem_updates_ */

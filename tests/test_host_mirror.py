@@ -1,0 +1,145 @@
+"""The C++ host mirror (Scene / KinematicTree / task-map and problem factories) through the Python forwarders.
+
+CPU part: the loader reproduces the element order, ids, control ids, names and limits of the reference's
+KinematicTree::BuildTree (kinematic_tree.cpp:164-421) -- checked against the oracle's independent Python restatement
+(oracle/robot_model.py), which is itself pinned by the Valkyrie CoM goldens.  GPU part (-m gpu): problems built from
+initializers / XML the way exotica_examples does evaluate identically to the oracle, batched and one at a time.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import exotica_b200 as exo
+from conftest import ROBOTS, robot_paths
+
+
+def _scene_init(robot, group):
+    urdf, srdf = robot_paths(robot)
+    return ("exotica/Scene", {"Name": "Scene", "JointGroup": group, "URDF": urdf, "SRDF": srdf})
+
+
+@pytest.mark.parametrize("robot,group", [("lwr_simplified", "arm"), ("test_robot", "arm"), ("valkyrie_sim", "whole_body")])
+def test_loader_matches_the_oracle_tree(oracle_lib, robot, group):
+    ref = oracle_lib.load_robot(*robot_paths(robot), joint_group=group)
+    scene = exo.Setup.create_scene(_scene_init(robot, group))
+    tree = scene.get_kinematic_tree().get_tree()
+    flat = ref.flat()
+    n = len(ref.elements)
+    assert len(tree["id"]) == n
+    assert np.array_equal(tree["id"], flat["id"]) and np.array_equal(tree["parent"], flat["parent"])
+    assert np.array_equal(tree["joint_type"], flat["joint_type"]) and np.array_equal(tree["control_id"], flat["control_id"])
+    assert np.max(np.abs(tree["origin"] - flat["origin"].reshape(n, 3))) <= 1e-15
+    assert np.max(np.abs(tree["axis"] - flat["axis"].reshape(n, 3))) <= 1e-15
+    assert np.max(np.abs(tree["f_tip"] - flat["f_tip"].reshape(n, 12))) <= 1e-15
+    lim = scene.get_kinematic_tree().get_joint_limits()
+    assert np.array_equal(lim[:, 0], ref.lower) and np.array_equal(lim[:, 1], ref.upper)
+
+
+def test_lwr_names_and_factories():
+    scene = exo.Setup.create_scene(_scene_init("lwr_simplified", "arm"))
+    assert scene.get_controlled_joint_names() == ["lwr_arm_%d_joint" % i for i in range(7)]
+    assert scene.get_controlled_link_names() == ["lwr_arm_%d_link" % i for i in range(1, 8)]
+    assert scene.get_model_link_names()[:3] == ["world_frame", "base", "lwr_arm_0_link"]
+    assert scene.get_root_frame_name() == "world_frame"
+    assert set(["exotica/EffFrame", "exotica/EffPosition", "exotica/JointLimit", "exotica/SphereCollision"]) <= set(exo.Setup.get_maps())
+    assert set(["exotica/UnconstrainedEndPoseProblem", "exotica/TimeIndexedProblem"]) <= set(exo.Setup.get_problems())
+
+
+def test_problem_indexing_and_errors_without_a_gpu():
+    eff = ("exotica/EffFrame", {"Name": "Eff", "Type": "Quaternion", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
+    jl = ("exotica/JointLimit", {"Name": "JL"})
+    init = ("exotica/TimeIndexedProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff, jl], "T": 10, "tau": 0.1,
+                                           "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "2"}), ("exotica/Task", {"Task": "JL", "Rho": "0"})]})
+    prob = exo.Setup.create_problem(init)
+    assert (prob.N, prob.length_Phi, prob.length_jacobian, prob.T) == (7, 14, 13, 10)
+    tasks = prob.get_task_maps()
+    assert (tasks["Eff"].start, tasks["Eff"].length, tasks["Eff"].startJ, tasks["Eff"].lengthJ) == (0, 7, 0, 6)
+    assert (tasks["JL"].start, tasks["JL"].length, tasks["JL"].startJ, tasks["JL"].lengthJ) == (7, 7, 6, 7)
+    assert tasks["Eff"].is_used and not tasks["JL"].is_used  # rho == 0 everywhere -> unused (tasks.cpp:246-259)
+    bad = ("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"),
+                                                   "Maps": [("exotica/EffPosition", {"Name": "E", "EndEffector": [("exotica/Frame", {"Link": "nope"})]})]})
+    with pytest.raises(exo.ExoticaError):
+        exo.Setup.create_problem(bad)
+    with pytest.raises(exo.ExoticaError, match="Invalid task goal size"):
+        exo.Setup.create_problem(("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff],
+                                                                          "Cost": [("exotica/Task", {"Task": "Eff", "Goal": "1 2 3"})]}))
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------------
+def _oracle_for(oracle_lib, maps):
+    orc = oracle_lib.Oracle(oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm"))
+    orc.set_problem(maps)
+    return orc
+
+
+@pytest.mark.gpu
+def test_end_pose_problem_update_and_batch(oracle_lib):
+    from helpers import angle_entries, max_abs_err
+    # exotica_examples/resources/configs/example_ik.xml shape: EffFrame on link 6 with a quaternion LinkOffset
+    off = [0, 0, 0, 0.7071067811865476, -4.3297802811774664e-17, 0.7071067811865475, 4.3297802811774664e-17]
+    eff = ("exotica/EffFrame", {"Name": "Position", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_6_link", "LinkOffset": off})]})
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "ik", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff],
+                                                    "Cost": [("exotica/Task", {"Task": "Position", "Rho": "3", "Goal": "0.5 0 0.5 0 0 0"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_6_link", "LinkOffset": off}]}]
+    orc = _oracle_for(oracle_lib, maps)
+    rng = np.random.default_rng(3)
+    X = rng.uniform(orc.lower, orc.upper, size=(300, 7))
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    prob.update(X[5])  # the reference's one-configuration entry point
+    assert max_abs_err(prob.Phi, phi_ref[5], angle_entries(maps, orc)) <= 1e-10 and max_abs_err(prob.jacobian, jac_ref[5]) <= 1e-10
+    cost = prob.cost_batch(X)
+    goal = np.array([0.5, 0, 0.5, 0, 0, 0])
+    ref = np.array([orc.trajectory_cost(X[e:e + 1], [3.0], goal=goal)[0] for e in range(300)])
+    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    with pytest.raises(exo.ExoticaError):
+        prob.update_batch(X[:, :6])
+
+
+@pytest.mark.gpu
+def test_time_indexed_problem_trajectories_and_cost(oracle_lib):
+    from helpers import angle_entries, max_abs_err
+    T, tau, B = 20, 0.05, 6
+    eff = ("exotica/EffFrame", {"Name": "Eff", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
+    jl = ("exotica/JointLimit", {"Name": "JL", "SafePercentage": 0.05})
+    init = ("exotica/TimeIndexedProblem", {"Name": "ti", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff, jl], "T": T, "tau": tau,
+                                           "Wrate": 2.0, "W": list(np.linspace(1, 7, 7)),
+                                           "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "10", "Goal": "0.4 0.2 0.7 0.1 0.2 0.3"}),
+                                                    ("exotica/Task", {"Task": "JL", "Rho": "100"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit", "SafePercentage": 0.05}]
+    orc = _oracle_for(oracle_lib, maps)
+    rng = np.random.default_rng(11)
+    q0 = rng.uniform(orc.lower, orc.upper, size=(B, 7))
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.05, orc.upper + 0.05)
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X.reshape(B * T, 7), T=T)
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    cost = prob.cost_batch(X)
+    goal = np.concatenate([[0.4, 0.2, 0.7, 0.1, 0.2, 0.3], np.zeros(7)])
+    W = np.linspace(1, 7, 7) * 2.0
+    ref = np.array([orc.trajectory_cost(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)[0] for b in range(B)])
+    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    # Update(x, t) of one timestep (abstract_time_indexed_problem.cpp:220-292)
+    prob.update(X[2, 7], 7)
+    assert max_abs_err(prob.Phi[7], phi_ref[2 * T + 7], angle_entries(maps, orc)) <= 1e-10
+    assert max_abs_err(prob.jacobian[7], jac_ref[2 * T + 7]) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_scene_update_fk_and_jacobian(oracle_lib):
+    scene = exo.Setup.create_scene(_scene_init("lwr_simplified", "arm"))
+    orc = oracle_lib.Oracle(oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm"))
+    frames = [{"Link": "lwr_arm_7_link"}, {"Link": "lwr_arm_5_link", "LinkOffset": [0.1, 0, 0.05], "Base": "lwr_arm_2_link"}]
+    scene.request_frames(frames)
+    orc.request_frames(frames)
+    x = np.random.default_rng(1).uniform(orc.lower, orc.upper)
+    phi, jac = scene.update(x)
+    orc.update(x)
+    assert np.max(np.abs(phi - orc.phi())) <= 1e-10 and np.max(np.abs(jac - orc.jacobian())) <= 1e-10
+    # LWR at q = 0, fk(lwr_arm_7_link) = (0, 0, 1.1985)
+    scene.update(np.zeros(7))
+    assert np.max(np.abs(scene.fk("lwr_arm_7_link")[9:] - [0, 0, 1.1985])) <= 1e-12
