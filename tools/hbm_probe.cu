@@ -50,6 +50,87 @@ __global__ void soa_pitch(const double* __restrict__ in, double* __restrict__ ou
         for (int k = 0; k < 48; ++k) store<MODE>(out + k * pitch + e, s + k);
     }
 }
+// persistent, but every warp starts its 48 stores at a different row (de-synchronises the rows the GPU writes at any moment)
+__global__ void soa_rotated(const double* __restrict__ in, double* __restrict__ out, int64_t n)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int k0 = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 7 % 48);
+    for (; e < n; e += stride)
+    {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s += in[k * n + e];
+        for (int k = 0; k < 48; ++k)
+        {
+            const int kk = (k + k0) % 48;
+            out[kk * n + e] = s + kk;
+        }
+    }
+}
+// persistent, contiguous block of evaluations per CTA
+__global__ void soa_chunked(const double* __restrict__ in, double* __restrict__ out, int64_t n)
+{
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t e1 = min(n, (int64_t)(blockIdx.x + 1) * per);
+    for (int64_t e = (int64_t)blockIdx.x * per + threadIdx.x; e < e1; e += blockDim.x)
+    {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s += in[k * n + e];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) out[k * n + e] = s + k;
+    }
+}
+// persistent with the next iteration's loads issued before this iteration's stores (register prefetch)
+__global__ void soa_prefetch(const double* __restrict__ in, double* __restrict__ out, int64_t n)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double q[7];
+    if (e < n)
+        for (int k = 0; k < 7; ++k) q[k] = in[k * n + e];
+    for (; e < n; e += stride)
+    {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s += q[k];
+        if (e + stride < n)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) q[k] = in[k * n + e + stride];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) out[k * n + e] = s + k;
+    }
+}
+// persistent CTAs that fetch tiles of TILE evaluations from a global counter (dynamic load balancing), with the next
+// tile's loads in flight while the current tile is stored
+__device__ unsigned int g_counter;
+template <int TILE>
+__global__ void soa_dynamic(const double* __restrict__ in, double* __restrict__ out, int64_t n)
+{
+    __shared__ unsigned int s_tile[2];
+    const int n_tiles = (int)((n + TILE - 1) / TILE);
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(&g_counter, 1u);
+    __syncthreads();
+    unsigned int tile = s_tile[0];
+    int buf = 0;
+    while (tile < (unsigned)n_tiles)
+    {
+        if (threadIdx.x == 0) s_tile[buf ^ 1] = atomicAdd(&g_counter, 1u);
+        for (int64_t e = (int64_t)tile * TILE + threadIdx.x; e < min(n, (int64_t)(tile + 1) * TILE); e += blockDim.x)
+        {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s += in[k * n + e];
+#pragma unroll
+            for (int k = 0; k < 48; ++k) out[k * n + e] = s + k;
+        }
+        __syncthreads();
+        buf ^= 1;
+        tile = s_tile[buf];
+        __syncthreads();
+    }
+}
 // tiles of 32 evaluations: out[e/32][48][32]
 template <int MODE>
 __global__ void tile_like(const double* __restrict__ in, double* __restrict__ out, int64_t n)
@@ -118,7 +199,32 @@ int main()
         ms = time_ms([&] { copy64<<<g, t>>>(out, out + 24 * n, 24 * n); }, 50);
         printf("copy64      grid %5d x%d: %6.1f us  %5.0f GB/s (1:1 copy, 403 MB)\n", g, t, ms * 1e3, 48.0 * n * 8 / ms / 1e6);
     }
-    const int64_t pads[] = {0, 16, 32, 48, 64, 96, 128, 160, 256, 512, 1040, 4112, 65552};
+    for (int g : {148 * 3, 148 * 7, 148 * 16, 148 * 32, 148 * 55, 8192})
+        for (int t : {64, 128})
+        {
+            const int gg = g * 128 / t;
+            float ms = time_ms([&] { soa_like<0><<<gg, t>>>(in, out, n); }, 50);
+            printf("soa plain    grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+            ms = time_ms([&] { soa_rotated<<<gg, t>>>(in, out, n); }, 50);
+            printf("soa rotated  grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+            ms = time_ms([&] { soa_chunked<<<gg, t>>>(in, out, n); }, 50);
+            printf("soa chunked  grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+            ms = time_ms([&] { soa_prefetch<<<gg, t>>>(in, out, n); }, 50);
+            printf("soa prefetch grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+        }
+    for (int g : {148 * 3, 148 * 7, 148 * 16})
+        for (int t : {64, 128})
+        {
+            const int gg = g * 128 / t;
+            unsigned int zero = 0;
+            float ms = time_ms([&] { cudaMemcpyToSymbolAsync(g_counter, &zero, 4, 0, cudaMemcpyHostToDevice, 0); soa_dynamic<128><<<gg, t>>>(in, out, n); }, 50);
+            printf("soa dynamic tile 128 grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+            ms = time_ms([&] { cudaMemcpyToSymbolAsync(g_counter, &zero, 4, 0, cudaMemcpyHostToDevice, 0); soa_dynamic<256><<<gg, t>>>(in, out, n); }, 50);
+            printf("soa dynamic tile 256 grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+            ms = time_ms([&] { cudaMemcpyToSymbolAsync(g_counter, &zero, 4, 0, cudaMemcpyHostToDevice, 0); soa_dynamic<1024><<<gg, t>>>(in, out, n); }, 50);
+            printf("soa dynamic tile 1024 grid %5d x%3d: %6.1f us  %5.0f GB/s\n", gg, t, ms * 1e3, 55.0 * n * 8 / ms / 1e6);
+        }
+    const int64_t pads[] = {0};
     for (int g : {444, 1776, 8192})
         for (int64_t pad : pads)
         {
