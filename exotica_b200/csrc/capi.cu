@@ -62,6 +62,7 @@ struct exo_problem
     double *d_rho = nullptr, *d_goal = nullptr, *d_goal_rot = nullptr, *d_W = nullptr;
     // timing / accounting
     int64_t launches = 0;
+    int compile_mode = COMPILE_AUTO;  // exo_problem_set_kernel choices 4 / 5 force the interpreter's one- / two-pass program
     int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..3 chain kernel variants (CHAIN_REGS, CHAIN_TWO_PASS)
     bool chain_ok = false;        // the compiled program lowered to ChainParams
     ChainParams chain;            // problem constants of the chain kernel (buffers / strides filled per launch)
@@ -371,7 +372,7 @@ static int compile_and_upload(exo_problem* p)
 {
     std::string err;
     Program prog;
-    if (!compile_program(p->tree->model, p->maps, prog, err)) return fail(EXO_ERR_INVALID, err);
+    if (!compile_program(p->tree->model, p->maps, prog, err, p->compile_mode)) return fail(EXO_ERR_INVALID, err);
     p->prog = prog;
     if (p->d_image_bytes < p->prog.image.size())
     {
@@ -602,8 +603,14 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 3) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter) or 2..3 (chain kernel variants)");
-    p->kernel_choice = choice;
+    if (choice < 0 || choice > 5) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants) or 4..5 (interpreter, one- / two-pass program)");
+    const int mode = choice == 4 ? COMPILE_ONE_PASS : (choice == 5 ? COMPILE_TWO_PASS : COMPILE_AUTO);
+    if (mode != p->compile_mode)
+    {
+        p->compile_mode = mode;
+        p->compiled_version = -1;  // recompile at the next launch
+    }
+    p->kernel_choice = choice >= 4 ? 1 : choice;
     return EXO_OK;
 }
 

@@ -219,7 +219,7 @@ struct Producer
 };
 }  // namespace
 
-bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& out, std::string& err)
+bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& out, std::string& err, int mode)
 {
     const int n = t.n;
     const int N = t.n_ctrl;
@@ -580,6 +580,25 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             }
         }
     }
+    // ---- 6b. two-pass mode ------------------------------------------------------------------------------------------
+    // Eligible when every requested frame has a constant base (no frame-B chains, no Binv that depends on the state) and
+    // there is no SphereCollision map (it reads joint slots).  Worth it when the joint slots dominate the scratch.
+    bool two_pass = mode != COMPILE_ONE_PASS && n_joint_slots > 0;
+    int n_pos_slots = 0;
+    std::vector<int> pos_slot_of_emit(emits.size(), -1);
+    for (size_t i = 0; i < emits.size(); ++i)
+    {
+        if (emits[i].kind == OP_EMIT_SPHERES) two_pass = false;
+        if (emits[i].kind == OP_EMIT_FRAME)
+        {
+            if (plans[i].src_b != SRC_ROOT) two_pass = false;
+            pos_slot_of_emit[i] = n_pos_slots++;
+        }
+    }
+    if (mode == COMPILE_AUTO && 6 * n_joint_slots <= 3 * n_pos_slots + 48) two_pass = false;  // < 400 bytes to gain
+    // per joint op: the columns it owns, for every requested frame below it
+    std::vector<std::vector<int32_t>> tp_entries(n_ops);
+    std::vector<int> encoded_index(n_ops, -1);  // producer (joint / table op) -> index in out.ops
     auto patch_src = [&](int v) { return v >= 0 ? prod[v].frame_slot : v; };
     auto patch_contrib = [&](int v) { return v < 0 ? -1 : ((prod[v >> 2].joint_slot << 2) | (v & 3)); };
 
@@ -636,6 +655,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 out.n_joint_ops++;
             }
             op.flags = flags;
+            encoded_index[k] = (int)out.ops.size();
             out.ops.push_back(op);
             continue;
         }
@@ -681,6 +701,16 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 push_frame(pl.off_b);
             }
             op.flags = flags;
+            if (two_pass)
+                for (int c = 0; c < N; ++c)
+                    if (pl.contrib[c] >= 0)
+                    {
+                        const int k = pl.contrib[c] >> 2;
+                        const int tpf = ((pl.contrib[c] & 2) ? TP_F_PRISMATIC : 0) | ((flags & F_B_MASK) == F_B_CONST ? TP_F_BCONST : 0);
+                        const int32_t ent[TP_INTS] = {pos_slot_of_emit[seq[s].second], c, op.jrow_off, op.n_rows, tpf, op.cst + CE_B_M};
+                        tp_entries[k].insert(tp_entries[k].end(), ent, ent + TP_INTS);
+                    }
+            op.n_items = pos_slot_of_emit[seq[s].second];  // two-pass mode: where the frame's position is parked
             for (int c = 0; c < N; ++c) out.ints.push_back(patch_contrib(pl.contrib[c]));
             // the same contributors keyed by joint-op ordinal (used by the chain kernel, whose joint data sits in
             // registers indexed by ordinal): (column << 2) | flags
@@ -807,7 +837,17 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
     h.length_jac = length_jac;
     h.n_generated = t.n_generated;
     h.n_acc = n_acc_max;
-    h.scratch_doubles = 12 * n_frame_slots + 6 * n_joint_slots;
+    h.two_pass = two_pass ? 1 : 0;
+    h.n_pos_slots = n_pos_slots;
+    h.scratch_doubles = 12 * n_frame_slots + (two_pass ? 3 * n_pos_slots : 6 * n_joint_slots);
+    if (two_pass)
+        for (int k = 0; k < n_ops; ++k)
+        {
+            Op& jop = out.ops[encoded_index[k]];
+            jop.tab = (int)out.ints.size();
+            out.ints.push_back((int32_t)(tp_entries[k].size() / TP_INTS));
+            out.ints.insert(out.ints.end(), tp_entries[k].begin(), tp_entries[k].end());
+        }
     for (const Op& op : out.ops)
         if (op.kind == OP_EMIT_SPHERES) h.max_spheres = std::max(h.max_spheres, op.n_items);
     // chain eligibility: [JointLimit / fill emits]* [joint fed by its predecessor]+ [frame emits reading the final frame]*,

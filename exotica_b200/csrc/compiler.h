@@ -67,6 +67,6 @@ struct Program
 int rotation_length(int rot_type);
 // Assigns start/length/... to the maps (planning_problem.cpp:227-238).  Returns false + err on bad sizes.
 bool assign_indexing(const TreeModel& tree, std::vector<MapSpec>& maps, int& length_phi, int& length_jac, std::string& err);
-bool compile_program(const TreeModel& tree, std::vector<MapSpec>& maps, Program& out, std::string& err);
+bool compile_program(const TreeModel& tree, std::vector<MapSpec>& maps, Program& out, std::string& err, int mode = COMPILE_AUTO);
 
 }  // namespace exo

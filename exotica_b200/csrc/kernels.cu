@@ -270,6 +270,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
     double* scr = reinterpret_cast<double*>(smem + P.scratch_offset) + col;  // word k at scr[k * CS]
     const int N = H->n_ctrl;
     const int joint_base = 12 * H->n_frame_slots;
+    const int pos_base = joint_base;  // two-pass programs park 3 doubles per requested frame where the joint slots would be
     double* qs = scr + (size_t)H->scratch_doubles * CS;
     // per-warp area behind the per-thread scratch: sphere centre table (4 doubles per sphere) + Jacobian row accumulators
     double* warp_smem = reinterpret_cast<double*>(smem + P.scratch_offset) + (size_t)(H->scratch_doubles + N) * CS +
@@ -291,11 +292,15 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
         double* phi_e = P.phi + e * P.phi_se;
         double* jac_e = want_j ? P.jac + e * P.j_se : nullptr;
         Fr cur = fr_identity();
-
+        // two-pass programs: pass 0 composes the tree and emits Phi (parking each requested frame's position), pass 1
+        // composes it again and emits every joint's Jacobian columns the moment its axis and origin are known
+        const int n_pass = (H->two_pass && want_j) ? 2 : 1;
+        for (int pass = 0; pass < n_pass; ++pass)
         for (int pc = 0;; ++pc)
         {
             const Op op = ops[pc];
             if (op.kind == OP_END) break;
+            if (pass == 1 && op.kind >= OP_EMIT_FRAME) continue;
             const double* c = dbls + op.cst;
             if (op.kind == OP_JOINT || op.kind == OP_TABLE)
             {
@@ -403,7 +408,53 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                             }
                         }
                     }
-                    if (op.jslot >= 0)
+                    if (H->two_pass)
+                    {
+                        if (pass == 1)
+                        {
+                            // ComputeJ (kinematic_tree.cpp:919-945) for every requested frame below this joint
+                            const int32_t* tp = ints + op.tab;
+                            const int n_ent = tp[0];
+                            for (int k = 0; k < n_ent; ++k)
+                            {
+                                const int32_t* ent = tp + 1 + TP_INTS * k;
+                                const double* ps = scr + (pos_base + 3 * ent[0]) * CS;
+                                double v0, v1, v2, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+                                if (ent[4] & TP_F_PRISMATIC)
+                                {
+                                    v0 = wx; v1 = wy; v2 = wz;
+                                }
+                                else
+                                {
+                                    const double dx = ps[0] - cur.x, dy = ps[CS] - cur.y, dz = ps[2 * CS] - cur.z;
+                                    v0 = wy * dz - wz * dy;
+                                    v1 = wz * dx - wx * dz;
+                                    v2 = wx * dy - wy * dx;
+                                    w0 = wx; w1 = wy; w2 = wz;
+                                }
+                                if (ent[4] & TP_F_BCONST)
+                                {
+                                    const double* b = dbls + ent[5];
+                                    const double t0 = b[0] * v0 + b[1] * v1 + b[2] * v2;
+                                    const double t1 = b[3] * v0 + b[4] * v1 + b[5] * v2;
+                                    const double t2 = b[6] * v0 + b[7] * v1 + b[8] * v2;
+                                    v0 = t0; v1 = t1; v2 = t2;
+                                    const double u0 = b[0] * w0 + b[1] * w1 + b[2] * w2;
+                                    const double u1 = b[3] * w0 + b[4] * w1 + b[5] * w2;
+                                    const double u2 = b[6] * w0 + b[7] * w1 + b[8] * w2;
+                                    w0 = u0; w1 = u1; w2 = u2;
+                                }
+                                double* jc = jac_e + (int64_t)ent[2] * P.j_sr + (int64_t)ent[1] * P.j_sc;
+                                const int64_t sr = P.j_sr;
+                                jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2;
+                                if (ent[3] == 6)
+                                {
+                                    jc[3 * sr] = w0; jc[4 * sr] = w1; jc[5 * sr] = w2;
+                                }
+                            }
+                        }
+                    }
+                    else if (op.jslot >= 0)
                     {
                         double* js = scr + (joint_base + 6 * op.jslot) * CS;
                         js[0] = wx; js[CS] = wy; js[2 * CS] = wz;
@@ -441,7 +492,22 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     Phi = fr_mul(Binv, A);
                 }
                 write_phi(op.map_kind, op.rot_type, Phi, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk);
-                if (want_j)
+                if (want_j && H->two_pass)
+                {
+                    // park temp_A.p for pass 1 and write the structural zeros (columns no joint below this frame owns)
+                    double* ps = scr + (pos_base + 3 * op.n_items) * CS;
+                    ps[0] = A.x; ps[CS] = A.y; ps[2 * CS] = A.z;
+                    const int32_t* tab = ints + op.tab;
+                    double* jr = jac_e + (int64_t)op.jrow_off * P.j_sr;
+                    const int64_t sr = P.j_sr;
+                    for (int col = 0; col < N; ++col)
+                    {
+                        if (tab[col] >= 0) continue;
+                        double* jc = jr + (int64_t)col * P.j_sc;
+                        for (int r = 0; r < op.n_rows; ++r) jc[r * sr] = 0.0;
+                    }
+                }
+                else if (want_j)
                 {
                     // ComputeJ (kinematic_tree.cpp:919-945): column c = temp_B.M^-1 * [ w x (temp_A.p - p_joint) ; w ]
                     const int32_t* tab = ints + op.tab;

@@ -139,7 +139,24 @@ struct ProgramHeader
                               // register-resident chain kernel (chain_kernel.cu); 0 otherwise
     int32_t chain_tab;        // offset into the int pool of the op index of every joint ordinal (chain programs)
     int32_t max_spheres;      // largest sphere count of any SphereCollision map (per-warp centre table in shared memory)
-    int32_t pad[2];
+    int32_t two_pass;         // 1: the interpreter walks the ops twice; pass 2 recomputes each joint and emits its Jacobian
+                              // columns on the fly (per-thread scratch holds 3 doubles per requested frame instead of 6 per joint)
+    int32_t n_pos_slots;      // two-pass mode: requested frames (one position slot each)
+};
+
+// two-pass mode: OP_JOINT's `tab` points at [n, then n x {pos_slot, column, jrow_off, n_rows, flags, cst_b}] in the int pool
+enum
+{
+    TP_INTS = 6,
+    TP_F_PRISMATIC = 1,
+    TP_F_BCONST = 2
+};
+
+enum CompileMode : int32_t
+{
+    COMPILE_AUTO = 0,      // two-pass when eligible and the joint slots would dominate the scratch
+    COMPILE_ONE_PASS = 1,
+    COMPILE_TWO_PASS = 2   // two-pass whenever eligible (tests)
 };
 
 }  // namespace exo

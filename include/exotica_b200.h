@@ -196,7 +196,9 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
 /* Kernel selection: 0 = auto (the Denavit-Hartenberg chain kernel when the compiled program is a serial chain of at
  * most 8 joints whose frames hang off the last link, else the general interpreter), 1 = always the interpreter,
  * 2 / 3 = the chain kernel's variants (joint data kept in registers / chain composed twice; EXO_ERR_UNSUPPORTED at
- * launch if the program is not a chain).  Tests compare all of them. */
+ * launch if the program is not a chain), 4 / 5 = the interpreter with the one-pass program (joint axes and origins parked
+ * in shared memory until a frame needs them) / the two-pass program (the tree is walked twice and Jacobian columns are
+ * emitted on the fly; used automatically for large trees).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
 /* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);

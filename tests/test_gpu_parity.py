@@ -28,10 +28,11 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
     phi_ref, jac_ref = orc.problem_update_batch(X, T=T, generated=generated)
     wrap = angle_entries(maps, orc)
     kernels = set()
-    # 1: general interpreter, 0: auto, 2 / 3: the chain kernel's variants (serial-chain programs only)
-    for choice in (1, 0, 2, 3):
+    # 1: general interpreter, 0: auto, 2 / 3: the chain kernel's variants (serial-chain programs only),
+    # 4 / 5: the interpreter with the one-pass / two-pass program
+    for choice in (1, 0, 2, 3, 4, 5):
         prob.set_kernel(choice)
-        if choice >= 2 and "exo_chain_kernel" not in kernels:
+        if choice in (2, 3) and "exo_chain_kernel" not in kernels:
             continue
         phi, jac = run_gpu(prob, X, layout=layout, T=T)
         kernels.add(prob.last_kernel())

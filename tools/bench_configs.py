@@ -76,7 +76,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 interpreter, 2 chain regs, 3 chain two-pass")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 interpreter, 2 chain regs, 3 chain two-pass, 4 / 5 interpreter one- / two-pass program")
     args = ap.parse_args()
     peak = 6549.4
     try:
