@@ -84,6 +84,39 @@ static Frame rot_axis_angle(const double* u, double q)
     return r;
 }
 
+// Rotation-only frame S with S.M * z = u (u unit): signed permutation matrices for axis-aligned u (exact), Gram-Schmidt
+// otherwise.  With it  Rot(u, q) = S Rz(q) S^-1  and  Trans(u q) = S Tz(q) S^-1.
+static Frame align_z(const double* u)
+{
+    Frame f = frame_identity();
+    double z[3] = {u[0], u[1], u[2]};
+    const double n = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+    if (n > 0)
+        for (int i = 0; i < 3; ++i) z[i] /= n;
+    if (z[0] == 0.0 && z[1] == 0.0)
+    {
+        if (z[2] < 0.0) f.M[4] = f.M[8] = -1.0;  // Rx(pi)
+        return f;
+    }
+    int k = 0;  // seed the x axis with the basis vector least aligned with z
+    if (fabs(z[1]) < fabs(z[k])) k = 1;
+    if (fabs(z[2]) < fabs(z[k])) k = 2;
+    double x[3] = {0, 0, 0};
+    x[k] = 1.0;
+    const double d = x[0] * z[0] + x[1] * z[1] + x[2] * z[2];
+    for (int i = 0; i < 3; ++i) x[i] -= d * z[i];
+    const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    for (int i = 0; i < 3; ++i) x[i] /= nx;
+    const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    for (int i = 0; i < 3; ++i)
+    {
+        f.M[3 * i] = x[i];
+        f.M[3 * i + 1] = y[i];
+        f.M[3 * i + 2] = z[i];
+    }
+    return f;
+}
+
 int rotation_length(int rot_type)
 {
     static const int len[6] = {4, 3, 3, 3, 3, 9};  // conversions.h:94-98
@@ -335,14 +368,20 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             Frame jo = frame_identity();  // (I, origin) * (Rt, 0)
             memcpy(jo.M, tip.M, sizeof(jo.M));
             for (int k = 0; k < 3; ++k) jo.p[k] = g.origin[k];
-            pre[e] = frame_mul(Cp, jo);
             // u = Rt^T a,  trailing translation t' = Rt^T pt
             Frame trail = frame_identity();
+            double ue[3];
             for (int k = 0; k < 3; ++k)
             {
-                u[3 * e + k] = tip.M[k] * g.axis[0] + tip.M[3 + k] * g.axis[1] + tip.M[6 + k] * g.axis[2];
+                ue[k] = tip.M[k] * g.axis[0] + tip.M[3 + k] * g.axis[1] + tip.M[6 + k] * g.axis[2];
                 trail.p[k] = tip.M[k] * tip.p[0] + tip.M[3 + k] * tip.p[1] + tip.M[6 + k] * tip.p[2];
             }
+            // z-canonical form: the stored frame is H = G * S with S.M z = u, so that the joint moves about / along its own
+            // z axis whatever the URDF axis is:  H_m = H_a * (pre * S) * Rz(q),  and everything that hangs off m sees S^-1 first
+            const Frame S = align_z(ue);
+            pre[e] = frame_mul(frame_mul(Cp, jo), S);
+            trail = frame_mul(frame_inverse(S), trail);
+            u[3 * e] = 0.0; u[3 * e + 1] = 0.0; u[3 * e + 2] = 1.0;
             src_anchor[e] = ap;
             anchor[e] = e;
             C[e] = trail;
@@ -719,6 +758,15 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 for (int c = 0; c < N; ++c)
                     if (pl.contrib[c] >= 0) by_ord[pl.contrib[c] >> 2] = (c << 2) | (pl.contrib[c] & 3);
                 for (int k = 0; k < n_ops; ++k) out.ints.push_back(by_ord[k]);
+            }
+            // columns no joint below this frame owns (structural zeros of the Jacobian): [count, columns...]
+            op.pad = (int)out.ints.size();
+            {
+                std::vector<int32_t> zeros;
+                for (int c = 0; c < N; ++c)
+                    if (pl.contrib[c] < 0) zeros.push_back(c);
+                out.ints.push_back((int32_t)zeros.size());
+                out.ints.insert(out.ints.end(), zeros.begin(), zeros.end());
             }
         }
         else if (em.kind == OP_EMIT_JLIMIT)

@@ -294,7 +294,9 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
         Fr cur = fr_identity();
         // two-pass programs: pass 0 composes the tree and emits Phi (parking each requested frame's position), pass 1
         // composes it again and emits every joint's Jacobian columns the moment its axis and origin are known
-        const int n_pass = (H->two_pass && want_j) ? 2 : 1;
+        constexpr bool TP = W == 32;  // narrow tiles serve SphereCollision programs, which are never two-pass: compile it out
+        const bool two_pass = TP && H->two_pass;
+        const int n_pass = (two_pass && want_j) ? 2 : 1;
         for (int pass = 0; pass < n_pass; ++pass)
         for (int pc = 0;; ++pc)
         {
@@ -324,26 +326,13 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                 }
                 else
                 {
+                    // z-canonical joint (compiler.cpp): the joint moves about / along the z axis of the frame in front of it,
+                    // so its world axis is the z column and its origin the translation, whatever the URDF axis was
                     double q = c[CJ_QOFF];
                     if (op.qidx >= 0) q = fma(c[CJ_QMULT], qs[op.qidx * CS], q);
-                    const int ax = op.flags & F_AXIS_MASK;
-                    double wx, wy, wz;  // axis in world coordinates
+                    const double wx = cur.m2, wy = cur.m5, wz = cur.m8;
                     if (op.flags & F_PRISMATIC)
                     {
-                        if (ax == F_AXIS_GENERAL)
-                        {
-                            const double ux = c[CJ_AXIS], uy = c[CJ_AXIS + 1], uz = c[CJ_AXIS + 2];
-                            wx = cur.m0 * ux + cur.m1 * uy + cur.m2 * uz;
-                            wy = cur.m3 * ux + cur.m4 * uy + cur.m5 * uz;
-                            wz = cur.m6 * ux + cur.m7 * uy + cur.m8 * uz;
-                        }
-                        else
-                        {
-                            const double sg = (op.flags & F_AXIS_NEG) ? -1.0 : 1.0;
-                            if (ax == F_AXIS_X) { wx = sg * cur.m0; wy = sg * cur.m3; wz = sg * cur.m6; }
-                            else if (ax == F_AXIS_Y) { wx = sg * cur.m1; wy = sg * cur.m4; wz = sg * cur.m7; }
-                            else { wx = sg * cur.m2; wy = sg * cur.m5; wz = sg * cur.m8; }
-                        }
                         cur.x = fma(wx, q, cur.x);
                         cur.y = fma(wy, q, cur.y);
                         cur.z = fma(wz, q, cur.z);
@@ -351,64 +340,17 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     else
                     {
                         double s, cs;
-                        sincos(q, &s, &cs);
-                        if (ax == F_AXIS_GENERAL)
-                        {
-                            const double ux = c[CJ_AXIS], uy = c[CJ_AXIS + 1], uz = c[CJ_AXIS + 2];
-                            const double vt = 1.0 - cs;
-                            Fr r;
-                            r.m0 = cs + vt * ux * ux;
-                            r.m1 = -uz * s + vt * ux * uy;
-                            r.m2 = uy * s + vt * ux * uz;
-                            r.m3 = uz * s + vt * ux * uy;
-                            r.m4 = cs + vt * uy * uy;
-                            r.m5 = -ux * s + vt * uy * uz;
-                            r.m6 = -uy * s + vt * ux * uz;
-                            r.m7 = ux * s + vt * uy * uz;
-                            r.m8 = cs + vt * uz * uz;
-                            r.x = r.y = r.z = 0.0;
-                            const double px = cur.x, py = cur.y, pz = cur.z;
-                            cur = fr_mul(cur, r);
-                            cur.x = px; cur.y = py; cur.z = pz;
-                            wx = cur.m0 * ux + cur.m1 * uy + cur.m2 * uz;
-                            wy = cur.m3 * ux + cur.m4 * uy + cur.m5 * uz;
-                            wz = cur.m6 * ux + cur.m7 * uy + cur.m8 * uz;
-                        }
+                        if (fabs(q) <= 1.0e5)
+                            fast_sincos(q, s, cs);
                         else
-                        {
-                            const bool neg = (op.flags & F_AXIS_NEG) != 0;
-                            if (neg) s = -s;
-                            const double sg = neg ? -1.0 : 1.0;
-                            if (ax == F_AXIS_X)
-                            {
-                                // M * Rx: col1' = c col1 + s col2, col2' = -s col1 + c col2
-                                const double a1 = cur.m1, a4 = cur.m4, a7 = cur.m7;
-                                cur.m1 = cs * a1 + s * cur.m2; cur.m2 = cs * cur.m2 - s * a1;
-                                cur.m4 = cs * a4 + s * cur.m5; cur.m5 = cs * cur.m5 - s * a4;
-                                cur.m7 = cs * a7 + s * cur.m8; cur.m8 = cs * cur.m8 - s * a7;
-                                wx = sg * cur.m0; wy = sg * cur.m3; wz = sg * cur.m6;
-                            }
-                            else if (ax == F_AXIS_Y)
-                            {
-                                // M * Ry: col0' = c col0 - s col2, col2' = s col0 + c col2
-                                const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;
-                                cur.m0 = cs * a0 - s * cur.m2; cur.m2 = s * a0 + cs * cur.m2;
-                                cur.m3 = cs * a3 - s * cur.m5; cur.m5 = s * a3 + cs * cur.m5;
-                                cur.m6 = cs * a6 - s * cur.m8; cur.m8 = s * a6 + cs * cur.m8;
-                                wx = sg * cur.m1; wy = sg * cur.m4; wz = sg * cur.m7;
-                            }
-                            else
-                            {
-                                // M * Rz: col0' = c col0 + s col1, col1' = -s col0 + c col1
-                                const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;
-                                cur.m0 = cs * a0 + s * cur.m1; cur.m1 = cs * cur.m1 - s * a0;
-                                cur.m3 = cs * a3 + s * cur.m4; cur.m4 = cs * cur.m4 - s * a3;
-                                cur.m6 = cs * a6 + s * cur.m7; cur.m7 = cs * cur.m7 - s * a6;
-                                wx = sg * cur.m2; wy = sg * cur.m5; wz = sg * cur.m8;
-                            }
-                        }
+                            sincos(q, &s, &cs);  // Payne-Hanek territory: never for real joint angles
+                        // M * Rz: col0' = c col0 + s col1, col1' = -s col0 + c col1
+                        const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;
+                        cur.m0 = fma(cs, a0, s * cur.m1); cur.m1 = fma(cs, cur.m1, -(s * a0));
+                        cur.m3 = fma(cs, a3, s * cur.m4); cur.m4 = fma(cs, cur.m4, -(s * a3));
+                        cur.m6 = fma(cs, a6, s * cur.m7); cur.m7 = fma(cs, cur.m7, -(s * a6));
                     }
-                    if (H->two_pass)
+                    if (two_pass)
                     {
                         if (pass == 1)
                         {
@@ -444,12 +386,16 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                                     const double u2 = b[6] * w0 + b[7] * w1 + b[8] * w2;
                                     w0 = u0; w1 = u1; w2 = u2;
                                 }
-                                double* jc = jac_e + (int64_t)ent[2] * P.j_sr + (int64_t)ent[1] * P.j_sc;
                                 const int64_t sr = P.j_sr;
-                                jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2;
+                                double* jc = jac_e + (int64_t)ent[2] * sr + (int64_t)ent[1] * P.j_sc;
+                                jc[0] = v0; jc += sr;
+                                jc[0] = v1; jc += sr;
+                                jc[0] = v2;
                                 if (ent[3] == 6)
                                 {
-                                    jc[3 * sr] = w0; jc[4 * sr] = w1; jc[5 * sr] = w2;
+                                    jc += sr; jc[0] = w0;
+                                    jc += sr; jc[0] = w1;
+                                    jc += sr; jc[0] = w2;
                                 }
                             }
                         }
@@ -492,19 +438,28 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     Phi = fr_mul(Binv, A);
                 }
                 write_phi(op.map_kind, op.rot_type, Phi, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk);
-                if (want_j && H->two_pass)
+                if (want_j && two_pass)
                 {
                     // park temp_A.p for pass 1 and write the structural zeros (columns no joint below this frame owns)
                     double* ps = scr + (pos_base + 3 * op.n_items) * CS;
                     ps[0] = A.x; ps[CS] = A.y; ps[2 * CS] = A.z;
-                    const int32_t* tab = ints + op.tab;
-                    double* jr = jac_e + (int64_t)op.jrow_off * P.j_sr;
-                    const int64_t sr = P.j_sr;
-                    for (int col = 0; col < N; ++col)
+                    const int32_t* zl = ints + op.pad;
+                    const int n_zero = zl[0];
+                    const int64_t sr = P.j_sr, sc = P.j_sc;
+                    double* jr = jac_e + (int64_t)op.jrow_off * sr;
+                    const bool six = op.n_rows == 6;
+                    for (int k = 1; k <= n_zero; ++k)
                     {
-                        if (tab[col] >= 0) continue;
-                        double* jc = jr + (int64_t)col * P.j_sc;
-                        for (int r = 0; r < op.n_rows; ++r) jc[r * sr] = 0.0;
+                        double* jc = jr + (int64_t)zl[k] * sc;
+                        jc[0] = 0.0; jc += sr;
+                        jc[0] = 0.0; jc += sr;
+                        jc[0] = 0.0;
+                        if (six)
+                        {
+                            jc += sr; jc[0] = 0.0;
+                            jc += sr; jc[0] = 0.0;
+                            jc += sr; jc[0] = 0.0;
+                        }
                     }
                 }
                 else if (want_j)

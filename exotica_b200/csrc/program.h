@@ -81,8 +81,8 @@ struct Op
     int32_t jrow_off; // first Jacobian row written
     int32_t n_rows;   // EMIT_FILL: Jacobian rows to zero;  EMIT_SPHERES: number of group pairs
     int32_t tab;      // offset into the int pool (contributor table, fill table, sphere tables)
-    int32_t n_items;  // EMIT_FILL: number of Phi entries; EMIT_SPHERES: number of spheres
-    int32_t pad;
+    int32_t n_items;  // EMIT_FILL: number of Phi entries; EMIT_SPHERES: number of spheres; EMIT_FRAME: position slot (two-pass)
+    int32_t pad;      // EMIT_FRAME: offset into the int pool of [count, columns without a contributor...]
 };
 
 // OP_JOINT double constants
