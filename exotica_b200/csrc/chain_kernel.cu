@@ -384,16 +384,18 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
     char* jac_e = P.jac ? reinterpret_cast<char*>(P.jac) + e * P.j_se_b : nullptr;
     const int64_t x_step = stride * P.x_se_b, phi_step = stride * P.phi_se_b, jac_step = P.jac ? stride * P.j_se_b : 0;
     const int64_t sr_b = P.j_sr_b;
+    const int64_t pf_dist = stride < P.n_evals ? stride : P.prefetch_ahead, pf_step = pf_dist * P.x_se_b;
     for (; e < P.n_evals; e += stride, xe += x_step, phi_e += phi_step, jac_e += jac_step)
     {
         double q[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
-        // pull the next evaluation's joint values into L2 while this one is computed (no registers held)
-        if (e + stride < P.n_evals)
+        // pull joint values that will be needed soon into L2 (no registers held): this lane's next evaluation, or -- when
+        // the grid covers the batch and every lane has one evaluation -- those of a CTA a few generations behind
+        if (e + pf_dist < P.n_evals)
         {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) prefetch_l2(xe + x_step + P.joint[j].x_byte_off);
+            for (int j = 0; j < NJ; ++j) prefetch_l2(xe + pf_step + P.joint[j].x_byte_off);
         }
         if (P.has_prefix)
         {
@@ -478,19 +480,34 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
     }
 }
 
-// Grid size in units of "resident CTAs per GPU" (tuning knob, EXO_CHAIN_WAVES; 1 = exactly one persistent wave).
-// Measured on B200 (cfg2a, 2^20 evaluations): 1 wave 98.6 us, 4 waves 90.1 us, 8 waves 88.2 us, one CTA per 64
-// evaluations 94 us -- a few CTA generations per SM de-synchronise the load and store phases of the resident CTAs.
+// Grid size in units of "resident CTAs per GPU" (tuning knob EXO_CHAIN_WAVES).  Measured on B200 (cfg2a, 2^20 evaluations):
+// 1 generation (persistent, static grid-stride split) 98.6 us, 4 generations 90.1 us, 8 generations 88.2 us, and one CTA per
+// 64 evaluations -- the default -- 84.8 us once every CTA pulls the joint values of the CTA 3/4 of a generation behind it
+// into L2 (EXO_CHAIN_PF_QGENS, in quarter generations: 1 -> 86.1, 2 -> 85.9, 3 -> 84.8, 4 -> 85.4, 6 -> 87.9 us).  The
+// hardware CTA scheduler balances the two dies better than any static split, and tiles that advance together keep the
+// DRAM pages of the 48 output rows hot (tools/hbm_probe.cu); a software tile counter (atomicAdd) was slower (94-105 us).
 static int chain_grid_waves()
 {
     static int waves = 0;
     if (waves == 0)
     {
         const char* env = getenv("EXO_CHAIN_WAVES");
-        waves = env ? atoi(env) : 8;
+        waves = env ? atoi(env) : 1 << 16;
         if (waves < 1) waves = 1;
     }
     return waves;
+}
+
+static int chain_prefetch_generations()
+{
+    static int gens = 0;
+    if (gens == 0)
+    {
+        const char* env = getenv("EXO_CHAIN_PF_QGENS");  // in quarters of a generation of resident CTAs
+        gens = env ? atoi(env) : 3;
+        if (gens < 1) gens = 1;
+    }
+    return gens;
 }
 
 template <int NJ, bool ALLREV, int VARIANT>
@@ -508,7 +525,9 @@ cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
     const int64_t want = (P.n_evals + CTPB - 1) / CTPB;
     const int64_t resident = (int64_t)sms * ctas_per_sm * chain_grid_waves();
     const int blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
-    exo_chain_kernel<NJ, ALLREV, VARIANT><<<blocks, CTPB, 0, stream>>>(P);
+    ChainParams Q = P;
+    Q.prefetch_ahead = (int64_t)sms * ctas_per_sm * CTPB * chain_prefetch_generations() / 4;
+    exo_chain_kernel<NJ, ALLREV, VARIANT><<<blocks, CTPB, 0, stream>>>(Q);
     return cudaGetLastError();
 }
 

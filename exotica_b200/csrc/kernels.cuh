@@ -79,6 +79,7 @@ struct ChainParams
     double* phi;
     double* jac;  // may be NULL
     int64_t n_evals;
+    int64_t prefetch_ahead;                        // evaluations between a lane's work and the L2 prefetch it issues (full-grid launches)
     int64_t x_sk, phi_sk, j_sr, j_sc;              // element strides (doubles) of the entry / row / column index
     int64_t x_se_b, phi_se_b, j_se_b, j_sr_b;      // byte strides of the evaluation index and of a Jacobian row
     int64_t jf_byte_off[CH_MAXF][CH_MAXJ];         // byte offset of J(first row of frame f, column of joint j)
