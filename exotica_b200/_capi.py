@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("EXO_B200_LIB") or os.path.join(_HERE, "lib", "libexot
 EXO_OK = 0
 LAYOUT_SOA, LAYOUT_AOS_ROWMAJOR, LAYOUT_AOS_COLMAJOR = 0, 1, 2
 MAP_EFF_FRAME, MAP_EFF_POSITION, MAP_JOINT_LIMIT, MAP_SPHERE_COLLISION, MAP_FRAMES = 0, 1, 2, 3, 4
+MAP_EFF_ORIENTATION, MAP_EFF_POSITION_XY, MAP_DISTANCE, MAP_JOINT_POSE = 5, 6, 7, 8
 ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
 ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
 
@@ -31,7 +32,8 @@ class TreeDesc(ctypes.Structure):
 class TaskMapDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("n_frames", ctypes.c_int32), ("elem_a", _ip), ("off_a", _dp), ("elem_b", _ip),
                 ("off_b", _dp), ("rotation_type", ctypes.c_int32), ("safe_percentage", ctypes.c_double),
-                ("precision", ctypes.c_double), ("radius", _dp), ("group", _ip), ("is_used", ctypes.c_int32)]
+                ("precision", ctypes.c_double), ("radius", _dp), ("group", _ip), ("is_used", ctypes.c_int32),
+                ("n_joint_map", ctypes.c_int32), ("joint_map", _ip), ("joint_ref", _dp)]
 
 
 class CostDesc(ctypes.Structure):
@@ -249,7 +251,7 @@ class Problem(object):
         self.finalized = False
 
     def add_task_map(self, kind, elem_a=None, off_a=None, elem_b=None, off_b=None, rotation_type=1, safe_percentage=0.0,
-                     precision=1.0, radius=None, group=None, is_used=True):
+                     precision=1.0, radius=None, group=None, is_used=True, joint_map=None, joint_ref=None):
         d = TaskMapDesc()
         d.kind = kind
         n = 0 if elem_a is None else len(elem_a)
@@ -272,6 +274,14 @@ class Problem(object):
             keep += [r, g]
             d.radius, d.group = _d(r), _i(g)
         d.is_used = 1 if is_used else 0
+        if joint_map is not None:
+            jm = np.ascontiguousarray(joint_map, dtype=np.int32)
+            keep.append(jm)
+            d.n_joint_map, d.joint_map = int(jm.size), _i(jm)
+        if joint_ref is not None:
+            jr = np.ascontiguousarray(joint_ref, dtype=np.float64)
+            keep.append(jr)
+            d.joint_ref = _d(jr)
         check(lib().exo_problem_add_task_map(self.h, ctypes.byref(d)))
 
     def finalize(self):

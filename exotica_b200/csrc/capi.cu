@@ -328,7 +328,7 @@ int exo_problem_add_task_map(exo_problem* p, const exo_task_map_desc* d)
 {
     if (!p || !d) return fail(EXO_ERR_INVALID, "NULL argument");
     if (p->finalized) return fail(EXO_ERR_STATE, "problem already finalized");
-    if (d->kind < EXO_MAP_EFF_FRAME || d->kind > EXO_MAP_FRAMES) return fail(EXO_ERR_INVALID, "unknown task map kind");
+    if (d->kind < EXO_MAP_EFF_FRAME || d->kind > EXO_MAP_JOINT_POSE) return fail(EXO_ERR_INVALID, "unknown task map kind");
     if (d->n_frames < 0) return fail(EXO_ERR_INVALID, "negative frame count");
     MapSpec m;
     m.kind = d->kind;
@@ -355,7 +355,25 @@ int exo_problem_add_task_map(exo_problem* p, const exo_task_map_desc* d)
             if (m.elem_b[f] < 0 || m.elem_b[f] >= n) return fail(EXO_ERR_INVALID, "No frame_B link exists with index " + std::to_string(m.elem_b[f]));
         }
     }
-    if (m.kind == EXO_MAP_EFF_FRAME && rotation_length(m.rot_type) < 0) return fail(EXO_ERR_INVALID, "Unknown rotation representation type!");
+    if ((m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION) && rotation_length(m.rot_type) < 0)
+        return fail(EXO_ERR_INVALID, "Unknown rotation representation type!");
+    if (m.kind == EXO_MAP_JOINT_POSE)
+    {
+        // JointPose::Initialize (joint_pose.cpp:66-97): JointMap defaults to all controlled joints, JointRef to zeros
+        const int N = p->tree->model.n_ctrl;
+        if (d->n_joint_map < 0) return fail(EXO_ERR_INVALID, "negative JointMap size");
+        if (d->n_joint_map > 0)
+        {
+            if (!d->joint_map) return fail(EXO_ERR_INVALID, "joint_map is NULL");
+            m.joint_map.assign(d->joint_map, d->joint_map + d->n_joint_map);
+            for (int v : m.joint_map)
+                if (v < 0 || v >= N) return fail(EXO_ERR_INVALID, "JointMap index (" + std::to_string(v) + ") is greater than number of controlled joints (" + std::to_string(N) + ")!");
+        }
+        else
+            for (int i = 0; i < N; ++i) m.joint_map.push_back(i);
+        m.joint_ref.assign(m.joint_map.size(), 0.0);
+        if (d->joint_ref) m.joint_ref.assign(d->joint_ref, d->joint_ref + m.joint_map.size());
+    }
     if (m.kind == EXO_MAP_SPHERE_COLLISION)
     {
         if (!d->radius || !d->group) return fail(EXO_ERR_INVALID, "SphereCollision needs radius[] and group[]");
@@ -748,15 +766,17 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
         cm.length = m.length;
         cm.n_frames = m.n_frames;
         cm.rot_type = m.rot_type;
-        cm.stride = m.kind == EXO_MAP_EFF_FRAME ? 3 + rotation_length(m.rot_type) : 0;
+        const bool lie = m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION;  // maps with SO(3) entries
+        const int lead = m.kind == EXO_MAP_EFF_FRAME ? 3 : 0;
+        cm.stride = lie ? lead + rotation_length(m.rot_type) : 0;
         if (m.kind == EXO_MAP_FRAMES) return fail(EXO_ERR_UNSUPPORTED, "raw-frame maps have no task cost");
-        if (m.kind == EXO_MAP_EFF_FRAME)
+        if (lie)
         {
             n_rot += m.n_frames;
             for (int t = 0; t < d->T_goal; ++t)
                 for (int f = 0; f < m.n_frames; ++f)
                 {
-                    double* r = &goal[(size_t)t * LP + m.start + f * cm.stride + 3];
+                    double* r = &goal[(size_t)t * LP + m.start + f * cm.stride + lead];
                     if (m.rot_type == EXO_ROT_QUATERNION) r[3] = 1.0;
                     if (m.rot_type == EXO_ROT_MATRIX) r[0] = r[4] = r[8] = 1.0;
                 }
@@ -771,9 +791,10 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
         for (int k = 0; k < n_maps; ++k)
         {
             const MapSpec& m = p->maps[k];
-            if (m.kind != EXO_MAP_EFF_FRAME) continue;
+            if (m.kind != EXO_MAP_EFF_FRAME && m.kind != EXO_MAP_EFF_ORIENTATION) continue;
+            const int lead = m.kind == EXO_MAP_EFF_FRAME ? 3 : 0;
             for (int f = 0; f < m.n_frames; ++f, ++ri)
-                host_get_rotation(&goal[(size_t)t * LP + m.start + f * c.map[k].stride + 3], m.rot_type, &goal_rot[((size_t)t * n_rot + ri) * 9]);
+                host_get_rotation(&goal[(size_t)t * LP + m.start + f * c.map[k].stride + lead], m.rot_type, &goal_rot[((size_t)t * n_rot + ri) * 9]);
         }
     }
     int rc = upload(&p->d_rho, d->rho, (size_t)d->T * n_maps);

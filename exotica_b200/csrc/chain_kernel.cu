@@ -150,6 +150,42 @@ __device__ __forceinline__ void chain_column(const ChainParams& P, int f, char* 
     }
 }
 
+// Same for the maps that keep other rows of the column (EffOrientation, EffPositionXY, Distance): runtime row mode
+template <int J, bool ALLREV>
+__device__ __forceinline__ void chain_column_g(const ChainParams& P, int f, char* jac_e, int64_t sr_b, double wx, double wy, double wz, double px,
+                                               double py, double pz, double ax, double ay, double az, double ux, double uy, double uz)
+{
+    const ChainJointP& jp = P.joint[J];
+    if (jp.col < 0) return;
+    const ChainFrameP& fp = P.frame[f];
+    double v0, v1, v2, w0, w1, w2;
+    if (!ALLREV && jp.prismatic)
+    {
+        v0 = wx; v1 = wy; v2 = wz;
+        w0 = w1 = w2 = 0.0;
+    }
+    else
+    {
+        const double dx = ax - px, dy = ay - py, dz = az - pz;
+        v0 = wy * dz - wz * dy;
+        v1 = wz * dx - wx * dz;
+        v2 = wx * dy - wy * dx;
+        w0 = wx; w1 = wy; w2 = wz;
+    }
+    if (fp.b_const)
+    {
+        const double t0 = fp.binv[0] * v0 + fp.binv[1] * v1 + fp.binv[2] * v2;
+        const double t1 = fp.binv[3] * v0 + fp.binv[4] * v1 + fp.binv[5] * v2;
+        const double t2 = fp.binv[6] * v0 + fp.binv[7] * v1 + fp.binv[8] * v2;
+        v0 = t0; v1 = t1; v2 = t2;
+        const double u0 = fp.binv[0] * w0 + fp.binv[1] * w1 + fp.binv[2] * w2;
+        const double u1 = fp.binv[3] * w0 + fp.binv[4] * w1 + fp.binv[5] * w2;
+        const double u2 = fp.binv[6] * w0 + fp.binv[7] * w1 + fp.binv[8] * w2;
+        w0 = u0; w1 = u1; w2 = u2;
+    }
+    store_rows(fp.row_mode, reinterpret_cast<double*>(jac_e + P.jf_byte_off[f][J]), sr_b >> 3, v0, v1, v2, w0, w1, w2, ux, uy, uz);
+}
+
 // temp_A = D_{n-1} * K_f
 __device__ __forceinline__ Fr chain_frame_a(const ChainFrameP& fp, const Fr& tip)
 {
@@ -290,15 +326,23 @@ __device__ __noinline__ void chain_slow_eval(const ChainParams& P, const char* x
                 v[2] = W[j][0] * dy - W[j][1] * dx;
                 w[0] = W[j][0]; w[1] = W[j][1]; w[2] = W[j][2];
             }
-            char* jc = jac_e + P.jf_byte_off[f][j];
-            for (int r = 0; r < fp.n_rows; ++r)
+            if (fp.b_const)
             {
-                const double* src = r < 3 ? v : w;
-                double val = src[r % 3];
-                if (fp.b_const) val = fp.binv[3 * (r % 3)] * src[0] + fp.binv[3 * (r % 3) + 1] * src[1] + fp.binv[3 * (r % 3) + 2] * src[2];
-                st(jc, val);
-                jc += P.j_sr_b;
+                const double t[3] = {v[0], v[1], v[2]}, u[3] = {w[0], w[1], w[2]};
+                for (int r = 0; r < 3; ++r)
+                {
+                    v[r] = fp.binv[3 * r] * t[0] + fp.binv[3 * r + 1] * t[1] + fp.binv[3 * r + 2] * t[2];
+                    w[r] = fp.binv[3 * r] * u[0] + fp.binv[3 * r + 1] * u[1] + fp.binv[3 * r + 2] * u[2];
+                }
             }
+            double ux = 0.0, uy = 0.0, uz = 0.0;
+            if (fp.row_mode == ROWS_DIST)
+            {
+                const Fr Ph = fp.b_const ? fr_mul(load_frame(fp.binv), A) : A;
+                const double nrm = norm3_scaled(Ph.x, Ph.y, Ph.z);
+                ux = Ph.x / nrm; uy = Ph.y / nrm; uz = Ph.z / nrm;
+            }
+            store_rows(fp.row_mode, reinterpret_cast<double*>(jac_e + P.jf_byte_off[f][j]), P.j_sr, v[0], v[1], v[2], w[0], w[1], w[2], ux, uy, uz);
         }
     }
 }
@@ -334,6 +378,12 @@ struct ChainUnroll
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
         ChainUnroll<NJ, ALLREV, J + 1>::record(P, cur, q, sn, cs, W, PJ);
     }
+    static __device__ __forceinline__ void columns_g(const ChainParams& P, int f, char* jac_e, int64_t sr_b, const double (&W)[NJ][3],
+                                                     const double (&PJ)[NJ][3], double ax, double ay, double az, double ux, double uy, double uz)
+    {
+        chain_column_g<J, ALLREV>(P, f, jac_e, sr_b, W[J][0], W[J][1], W[J][2], PJ[J][0], PJ[J][1], PJ[J][2], ax, ay, az, ux, uy, uz);
+        ChainUnroll<NJ, ALLREV, J + 1>::columns_g(P, f, jac_e, sr_b, W, PJ, ax, ay, az, ux, uy, uz);
+    }
     template <bool WITHB, bool SIX>
     static __device__ __forceinline__ void columns(const ChainParams& P, int f, char* jac_e, int64_t sr_b, const double (&W)[NJ][3],
                                                    const double (&PJ)[NJ][3], double ax, double ay, double az)
@@ -351,6 +401,8 @@ struct ChainUnroll<NJ, ALLREV, NJ>
                                                 const double (&)[NJ], double, double, double) {}
     static __device__ __forceinline__ void record(const ChainParams&, Fr&, const double (&)[NJ], const double (&)[NJ], const double (&)[NJ],
                                                   double (&)[NJ][3], double (&)[NJ][3]) {}
+    static __device__ __forceinline__ void columns_g(const ChainParams&, int, char*, int64_t, const double (&)[NJ][3], const double (&)[NJ][3], double,
+                                                     double, double, double, double, double) {}
     template <bool WITHB, bool SIX>
     static __device__ __forceinline__ void columns(const ChainParams&, int, char*, int64_t, const double (&)[NJ][3], const double (&)[NJ][3], double,
                                                    double, double) {}
@@ -425,7 +477,7 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
             continue;
         }
         Fr cur = load_frame(P.base);
-        if (VARIANT == CHAIN_TWO_PASS && P.n_frames == 1)
+        if (VARIANT == CHAIN_TWO_PASS && P.n_frames == 1 && P.frame[0].row_mode <= ROWS_V)
         {
             ChainUnroll<NJ, ALLREV, 0>::compose(P, cur, q, sn, cs);
             const ChainFrameP& fp = P.frame[0];
@@ -433,7 +485,7 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
             if (jac_e)
             {
                 cur = load_frame(P.base);
-                const bool six = fp.n_rows == 6;
+                const bool six = fp.row_mode == ROWS_VW;
                 if (fp.b_const)
                 {
                     if (six) ChainUnroll<NJ, ALLREV, 0>::template emit<true, true>(P, jac_e, sr_b, cur, q, sn, cs, A.x, A.y, A.z);
@@ -456,9 +508,21 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
             {
                 const ChainFrameP& fp = P.frame[f];
                 const Fr A = chain_frame_a(fp, cur);
-                if (jac_e)
+                if (jac_e && fp.row_mode > ROWS_V)
                 {
-                    const bool six = fp.n_rows == 6;
+                    // EffOrientation / EffPositionXY / Distance: the generic emitter; Distance needs Phi.p / |Phi.p|
+                    double ux = 0.0, uy = 0.0, uz = 0.0;
+                    if (fp.row_mode == ROWS_DIST)
+                    {
+                        const Fr Ph = fp.b_const ? fr_mul(load_frame(fp.binv), A) : A;
+                        const double nrm = norm3_scaled(Ph.x, Ph.y, Ph.z);
+                        ux = Ph.x / nrm; uy = Ph.y / nrm; uz = Ph.z / nrm;
+                    }
+                    ChainUnroll<NJ, ALLREV, 0>::columns_g(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z, ux, uy, uz);
+                }
+                else if (jac_e)
+                {
+                    const bool six = fp.row_mode == ROWS_VW;
                     if (fp.b_const)
                     {
                         if (six) ChainUnroll<NJ, ALLREV, 0>::template columns<true, true>(P, f, jac_e, sr_b, W, PJ, A.x, A.y, A.z);

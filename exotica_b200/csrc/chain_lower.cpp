@@ -386,6 +386,7 @@ bool chain_lower(const Program& prog, ChainParams& P)
         fp.phi_off = op.phi_off;
         fp.jrow_off = op.jrow_off;
         fp.n_rows = op.n_rows;
+        fp.row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
         // contributors by joint ordinal: (column << 2) | (prismatic << 1) | negative
         const int32_t* otab = prog.ints.data() + op.tab + h.n_ctrl;
         for (int j = 0; j < n; ++j)

@@ -216,6 +216,24 @@ bool assign_indexing(const TreeModel& tree, std::vector<MapSpec>& maps, int& len
                 m.length = m.n_frames * 12;
                 m.length_jacobian = m.n_frames * 6;
                 break;
+            case EXO_MAP_EFF_ORIENTATION:  // eff_orientation.cpp:36-52, :100-108
+                if (rotation_length(m.rot_type) < 0)
+                {
+                    err = "Unknown rotation representation type!";
+                    return false;
+                }
+                m.length = m.n_frames * rotation_length(m.rot_type);
+                m.length_jacobian = m.n_frames * 3;
+                break;
+            case EXO_MAP_EFF_POSITION_XY:  // eff_position_xy.cpp
+                m.length = m.length_jacobian = m.n_frames * 2;
+                break;
+            case EXO_MAP_DISTANCE:  // distance.cpp
+                m.length = m.length_jacobian = m.n_frames;
+                break;
+            case EXO_MAP_JOINT_POSE:  // joint_pose.cpp:66-103
+                m.length = m.length_jacobian = (int)m.joint_map.size();
+                break;
             default:
                 err = "unknown task map kind";
                 return false;
@@ -414,6 +432,9 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
         {
             case EXO_MAP_JOINT_LIMIT:
                 emits.push_back({OP_EMIT_JLIMIT, mi, 0, -1});
+                break;
+            case EXO_MAP_JOINT_POSE:
+                emits.push_back({OP_EMIT_JPOSE, mi, 0, -1});
                 break;
             case EXO_MAP_SPHERE_COLLISION:
             {
@@ -631,6 +652,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
         if (emits[i].kind == OP_EMIT_FRAME)
         {
             if (plans[i].src_b != SRC_ROOT) two_pass = false;
+            if (maps[emits[i].map].kind == EXO_MAP_DISTANCE) two_pass = false;  // its row needs Phi.p / |Phi.p| at column time
             pos_slot_of_emit[i] = n_pos_slots++;
         }
     }
@@ -711,15 +733,20 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
         {
             const int f = em.frame;
             int rows = 6, stride = 0;
+            int row_mode = ROWS_VW;
             if (m.kind == EXO_MAP_EFF_FRAME) stride = 3 + rotation_length(m.rot_type);
-            if (m.kind == EXO_MAP_EFF_POSITION) stride = 3, rows = 3;
+            if (m.kind == EXO_MAP_EFF_POSITION) stride = 3, rows = 3, row_mode = ROWS_V;
             if (m.kind == EXO_MAP_FRAMES) stride = 12;
+            if (m.kind == EXO_MAP_EFF_ORIENTATION) stride = rotation_length(m.rot_type), rows = 3, row_mode = ROWS_W;
+            if (m.kind == EXO_MAP_EFF_POSITION_XY) stride = 2, rows = 2, row_mode = ROWS_VXY;
+            if (m.kind == EXO_MAP_DISTANCE) stride = 1, rows = 1, row_mode = ROWS_DIST;
             op.phi_off = m.start + f * stride;
             op.jrow_off = m.start_jacobian + f * rows;
             op.n_rows = rows;
             op.src = patch_src(pl.src_a);
             op.src_b = patch_src(pl.src_b);
             int flags = frame_is_identity(pl.off_a) ? F_OFFA_NONE : (rot_is_identity(pl.off_a) ? F_OFFA_TRANS : F_OFFA_FULL);
+            flags |= row_mode << F_ROWS_SHIFT;
             push_frame(pl.off_a);
             if (op.src_b == SRC_ROOT)
             {
@@ -746,7 +773,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                     {
                         const int k = pl.contrib[c] >> 2;
                         const int tpf = ((pl.contrib[c] & 2) ? TP_F_PRISMATIC : 0) | ((flags & F_B_MASK) == F_B_CONST ? TP_F_BCONST : 0);
-                        const int32_t ent[TP_INTS] = {pos_slot_of_emit[seq[s].second], c, op.jrow_off, op.n_rows, tpf, op.cst + CE_B_M};
+                        const int32_t ent[TP_INTS] = {pos_slot_of_emit[seq[s].second], c, op.jrow_off, row_mode, tpf, op.cst + CE_B_M};
                         tp_entries[k].insert(tp_entries[k].end(), ent, ent + TP_INTS);
                     }
             op.n_items = pos_slot_of_emit[seq[s].second];  // two-pass mode: where the frame's position is parked
@@ -778,6 +805,19 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             for (int c = 0; c < N; ++c) out.dbls.push_back(t.lower[c]);
             for (int c = 0; c < N; ++c) out.dbls.push_back(t.upper[c]);
         }
+        else if (em.kind == OP_EMIT_JPOSE)
+        {
+            // JointPose::Update (joint_pose.cpp:36-57): phi_i = q[map_i] - ref_i, J(i, map_i) = 1
+            op.phi_off = m.start;
+            op.jrow_off = m.start_jacobian;
+            op.n_rows = (int)m.joint_map.size();
+            op.n_items = (int)m.joint_map.size();
+            for (size_t i = 0; i < m.joint_map.size(); ++i)
+            {
+                out.ints.push_back(m.joint_map[i]);
+                out.dbls.push_back(i < m.joint_ref.size() ? m.joint_ref[i] : 0.0);
+            }
+        }
         else if (em.kind == OP_EMIT_FILL)
         {
             // Phi.SetZero(): zeros with identity rotation encodings at EffFrame's Lie-group entries
@@ -786,12 +826,13 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             op.n_rows = m.length_jacobian;
             op.n_items = m.length;
             std::vector<double> fill(m.length, 0.0);
-            if (m.kind == EXO_MAP_EFF_FRAME)
+            if (m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION)
             {
                 const int rl = rotation_length(m.rot_type);
+                const int lead = m.kind == EXO_MAP_EFF_FRAME ? 3 : 0;
                 for (int f = 0; f < m.n_frames; ++f)
                 {
-                    double* r = &fill[f * (3 + rl) + 3];
+                    double* r = &fill[f * (lead + rl) + lead];
                     if (m.rot_type == EXO_ROT_QUATERNION) r[3] = 1.0;
                     if (m.rot_type == EXO_ROT_MATRIX) r[0] = r[4] = r[8] = 1.0;
                 }
@@ -910,7 +951,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 if (op.src != (ordinal == 0 ? SRC_ROOT : SRC_CUR)) chain = false;
                 ++ordinal;
             }
-            else if (op.kind == OP_TABLE || op.kind == OP_EMIT_SPHERES)
+            else if (op.kind == OP_TABLE || op.kind == OP_EMIT_SPHERES || op.kind == OP_EMIT_JPOSE)
                 chain = false;
             else if (op.kind == OP_EMIT_FRAME)
             {

@@ -46,6 +46,8 @@ struct MapSpec
     std::vector<double> radius;
     std::vector<int32_t> group;
     int n_groups = 0;
+    std::vector<int32_t> joint_map;  // JointPose
+    std::vector<double> joint_ref;
     bool is_used = true;
     // assigned by the compiler (TaskMap::start / length / start_jacobian / length_jacobian)
     int start = 0, length = 0, start_jacobian = 0, length_jacobian = 0;

@@ -114,25 +114,27 @@ __device__ double eval_cost(const CostParams& P, int64_t e, int t)
     {
         const CostMapP& m = P.map[k];
         const double w = rho[k];
+        const bool lie = m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION;
         if (w == 0.0)
         {
-            if (m.kind == EXO_MAP_EFF_FRAME) rot_i += m.n_frames;
+            if (lie) rot_i += m.n_frames;
             continue;
         }
         double s = 0.0;
-        if (m.kind == EXO_MAP_EFF_FRAME)
+        if (lie)
         {
+            const int lead = m.kind == EXO_MAP_EFF_FRAME ? 3 : 0;  // EffOrientation has no position entries
             for (int f = 0; f < m.n_frames; ++f, ++rot_i)
             {
                 const double* a = ph + (int64_t)(m.start + f * m.stride) * P.phi_sk;
                 const double* g = goal + m.start + f * m.stride;
-                for (int i = 0; i < 3; ++i)
+                for (int i = 0; i < lead; ++i)
                 {
                     const double d = a[i * P.phi_sk] - g[i];
                     s += d * d;
                 }
                 // rotvec = M1 * (M2^-1 M1).GetRot()
-                const Fr M1 = dev_get_rotation(a + 3 * P.phi_sk, P.phi_sk, m.rot_type);
+                const Fr M1 = dev_get_rotation(a + lead * P.phi_sk, P.phi_sk, m.rot_type);
                 const double* M2 = grot + 9 * rot_i;
                 Fr M;
                 M.m0 = M2[0] * M1.m0 + M2[3] * M1.m3 + M2[6] * M1.m6;

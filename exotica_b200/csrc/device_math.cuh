@@ -338,6 +338,46 @@ static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y
 }
 
 
+// Rows of one Jacobian column the map keeps (program.h RowMode); (v, w) = linear / angular part of the frame's column,
+// (ux, uy, uz) = Phi.p / |Phi.p| for ROWS_DIST (distance.cpp:52)
+__device__ __forceinline__ void store_rows(int mode, double* jc, int64_t sr, double v0, double v1, double v2, double w0, double w1, double w2,
+                                           double ux, double uy, double uz)
+{
+    switch (mode)
+    {
+        case ROWS_VW:
+            jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2; jc[3 * sr] = w0; jc[4 * sr] = w1; jc[5 * sr] = w2;
+            break;
+        case ROWS_V:
+            jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2;
+            break;
+        case ROWS_W:
+            jc[0] = w0; jc[sr] = w1; jc[2 * sr] = w2;
+            break;
+        case ROWS_VXY:
+            jc[0] = v0; jc[sr] = v1;
+            break;
+        default:  // ROWS_DIST
+            jc[0] = ux * v0 + uy * v1 + uz * v2;
+            break;
+    }
+}
+
+// JointPose::Update (joint_pose.cpp:36-57); the reference writes only J(i, map_i) = 1 into the caller-zeroed matrix
+__device__ __forceinline__ void emit_joint_pose(const double* ref, const int32_t* map, int n, int N, const double* qs, int qstride, double* ph,
+                                                int64_t phi_sk, double* jr, int64_t j_sr, int64_t j_sc)
+{
+    for (int i = 0; i < n; ++i)
+    {
+        ph[i * phi_sk] = qs[map[i] * qstride] - ref[i];
+        if (jr)
+        {
+            double* row = jr + (int64_t)i * j_sr;
+            for (int col = 0; col < N; ++col) row[(int64_t)col * j_sc] = (col == map[i]) ? 1.0 : 0.0;
+        }
+    }
+}
+
 // Phi entries of one requested frame for EffFrame / EffPosition / raw frames (eff_frame.cpp:63-73, eff_position.cpp:46-55)
 __device__ __forceinline__ void write_phi(int map_kind, int rot_type, const Fr& Phi, double* ph, int64_t sk)
 {
@@ -348,9 +388,22 @@ __device__ __forceinline__ void write_phi(int map_kind, int rot_type, const Fr& 
         ph[9 * sk] = Phi.x; ph[10 * sk] = Phi.y; ph[11 * sk] = Phi.z;
         return;
     }
-    ph[0] = Phi.x; ph[sk] = Phi.y; ph[2 * sk] = Phi.z;
-    if (map_kind != EXO_MAP_EFF_FRAME) return;
-    ph += 3 * sk;
+    if (map_kind == EXO_MAP_DISTANCE)
+    {
+        ph[0] = norm3_scaled(Phi.x, Phi.y, Phi.z);  // distance.cpp:40: Phi.p.Norm()
+        return;
+    }
+    if (map_kind == EXO_MAP_EFF_POSITION_XY)
+    {
+        ph[0] = Phi.x; ph[sk] = Phi.y;
+        return;
+    }
+    if (map_kind != EXO_MAP_EFF_ORIENTATION)
+    {
+        ph[0] = Phi.x; ph[sk] = Phi.y; ph[2 * sk] = Phi.z;
+        if (map_kind != EXO_MAP_EFF_FRAME) return;
+        ph += 3 * sk;
+    }
     switch (rot_type)
     {
         case EXO_ROT_RPY:

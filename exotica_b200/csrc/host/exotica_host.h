@@ -436,6 +436,65 @@ public:
     int Kind() const override { return EXO_MAP_EFF_POSITION; }
 };
 
+// ---- sibling maps on the same frames ----
+class EffOrientation : public TaskMap  // eff_orientation.cpp
+{
+public:
+    void Instantiate(const Initializer& init) override;
+    int TaskSpaceDim() override { return (int)frames_.size() * stride_; }
+    int TaskSpaceJacobianDim() override { return (int)frames_.size() * 3; }
+    int Kind() const override { return EXO_MAP_EFF_ORIENTATION; }
+    void FillDescriptor(exo_task_map_desc& desc) override { desc.rotation_type = (int)rotation_type_; }
+    void FillZeroGoal(double* y) override
+    {
+        for (int f = 0; f < (int)frames_.size(); ++f)
+        {
+            double* r = y + f * stride_;
+            if (rotation_type_ == RotationType::QUATERNION) r[3] = 1.0;
+            if (rotation_type_ == RotationType::MATRIX) r[0] = r[4] = r[8] = 1.0;
+        }
+    }
+
+private:
+    RotationType rotation_type_ = RotationType::RPY;
+    int stride_ = 3;
+};
+
+class EffPositionXY : public TaskMap  // eff_position_xy.cpp
+{
+public:
+    int TaskSpaceDim() override { return (int)frames_.size() * 2; }
+    int Kind() const override { return EXO_MAP_EFF_POSITION_XY; }
+};
+
+class Distance : public TaskMap  // distance.cpp
+{
+public:
+    int TaskSpaceDim() override { return (int)frames_.size(); }
+    int Kind() const override { return EXO_MAP_DISTANCE; }
+};
+
+class JointPose : public TaskMap  // joint_pose.cpp
+{
+public:
+    void Instantiate(const Initializer& init) override;
+    void AssignScene(ScenePtr scene) override;
+    int TaskSpaceDim() override { return (int)joint_map_.size(); }
+    int Kind() const override { return EXO_MAP_JOINT_POSE; }
+    void FillDescriptor(exo_task_map_desc& desc) override
+    {
+        desc.n_joint_map = (int)joint_map_.size();
+        desc.joint_map = joint_map_.data();
+        desc.joint_ref = joint_ref_.data();
+    }
+    const std::vector<int32_t>& get_joint_map() const { return joint_map_; }
+    const std::vector<double>& get_joint_ref() const { return joint_ref_; }
+
+private:
+    std::vector<int32_t> joint_map_, init_map_;
+    std::vector<double> joint_ref_, init_ref_;
+};
+
 class JointLimit : public TaskMap  // joint_limit.cpp
 {
 public:

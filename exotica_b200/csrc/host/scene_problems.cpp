@@ -234,6 +234,47 @@ void EffFrame::Instantiate(const Initializer& init)
     big_stride_ = small_stride_ + 3;
 }
 
+void EffOrientation::Instantiate(const Initializer& init)
+{
+    rotation_type_ = GetRotationTypeFromString(init.Get("Type", "RPY"));  // init/eff_orientation.in
+    stride_ = GetRotationTypeLength(rotation_type_);
+}
+
+void JointPose::Instantiate(const Initializer& init)
+{
+    // init/joint_pose.in: JointRef, JointMap (both optional)
+    init_map_.clear();
+    for (double v : ParseVector(init.Get("JointMap", ""))) init_map_.push_back((int32_t)v);
+    init_ref_ = ParseVector(init.Get("JointRef", ""));
+}
+
+void JointPose::AssignScene(ScenePtr scene)
+{
+    // JointPose::Initialize (joint_pose.cpp:66-97)
+    scene_ = scene;
+    const int n = scene_->GetKinematicTree().GetNumControlledJoints();
+    joint_map_.clear();
+    if (!init_map_.empty())
+    {
+        for (int32_t v : init_map_)
+        {
+            if (v >= n || v < 0)
+                ThrowPretty("JointMap index (" + std::to_string(v) + ") is greater than number of controlled joints (" + std::to_string(n) + ")!");
+            joint_map_.push_back(v);
+        }
+    }
+    else
+        for (int i = 0; i < n; ++i) joint_map_.push_back(i);
+    if (!init_ref_.empty())
+    {
+        if (init_ref_.size() != joint_map_.size())
+            ThrowPretty("Invalid joint reference size! Expecting " + std::to_string(joint_map_.size()) + " but received " + std::to_string(init_ref_.size()));
+        joint_ref_ = init_ref_;
+    }
+    else
+        joint_ref_.assign(joint_map_.size(), 0.0);
+}
+
 void JointLimit::Instantiate(const Initializer& init)
 {
     const std::vector<double> v = ParseVector(init.Get("SafePercentage", "0.0"));  // init/joint_limit.in
@@ -304,6 +345,10 @@ Setup& Setup::Instance()
         s->RegisterMap("exotica/EffPosition", &MakeMap<EffPosition>);
         s->RegisterMap("exotica/JointLimit", &MakeMap<JointLimit>);
         s->RegisterMap("exotica/SphereCollision", &MakeMap<SphereCollision>);
+        s->RegisterMap("exotica/EffOrientation", &MakeMap<EffOrientation>);
+        s->RegisterMap("exotica/EffPositionXY", &MakeMap<EffPositionXY>);
+        s->RegisterMap("exotica/Distance", &MakeMap<Distance>);
+        s->RegisterMap("exotica/JointPose", &MakeMap<JointPose>);
         s->RegisterProblem("exotica/UnconstrainedEndPoseProblem", &MakeProblem<UnconstrainedEndPoseProblem>);
         s->RegisterProblem("exotica/TimeIndexedProblem", &MakeProblem<TimeIndexedProblem>);
         s->RegisterProblem("exotica/UnconstrainedTimeIndexedProblem", &MakeProblem<TimeIndexedProblem>);
@@ -340,7 +385,7 @@ std::vector<std::string> Setup::GetProblems()
 TaskMapPtr Setup::CreateMap(const Initializer& init)
 {
     auto it = Instance().maps_.find(init.name);
-    if (it == Instance().maps_.end()) ThrowPretty("Unable to load task map of type '" + init.name + "' (registered on the GPU path: EffFrame, EffPosition, JointLimit, SphereCollision)");
+    if (it == Instance().maps_.end()) ThrowPretty("Unable to load task map of type '" + init.name + "' (registered on the GPU path: EffFrame, EffPosition, JointLimit, SphereCollision, EffOrientation, EffPositionXY, Distance, JointPose)");
     TaskMapPtr m = it->second();
     m->InstantiateBase(init);  // InstantiateInternal = InstantiateBase + Instantiate (property.h:113-119)
     m->Instantiate(init);

@@ -387,16 +387,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                                     w0 = u0; w1 = u1; w2 = u2;
                                 }
                                 const int64_t sr = P.j_sr;
-                                double* jc = jac_e + (int64_t)ent[2] * sr + (int64_t)ent[1] * P.j_sc;
-                                jc[0] = v0; jc += sr;
-                                jc[0] = v1; jc += sr;
-                                jc[0] = v2;
-                                if (ent[3] == 6)
-                                {
-                                    jc += sr; jc[0] = w0;
-                                    jc += sr; jc[0] = w1;
-                                    jc += sr; jc[0] = w2;
-                                }
+                                store_rows(ent[3], jac_e + (int64_t)ent[2] * sr + (int64_t)ent[1] * P.j_sc, sr, v0, v1, v2, w0, w1, w2, 0.0, 0.0, 0.0);
                             }
                         }
                     }
@@ -447,19 +438,11 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     const int n_zero = zl[0];
                     const int64_t sr = P.j_sr, sc = P.j_sc;
                     double* jr = jac_e + (int64_t)op.jrow_off * sr;
-                    const bool six = op.n_rows == 6;
+                    const int n_rows = op.n_rows;
                     for (int k = 1; k <= n_zero; ++k)
                     {
                         double* jc = jr + (int64_t)zl[k] * sc;
-                        jc[0] = 0.0; jc += sr;
-                        jc[0] = 0.0; jc += sr;
-                        jc[0] = 0.0;
-                        if (six)
-                        {
-                            jc += sr; jc[0] = 0.0;
-                            jc += sr; jc[0] = 0.0;
-                            jc += sr; jc[0] = 0.0;
-                        }
+                        for (int r = 0; r < n_rows; ++r, jc += sr) jc[0] = 0.0;
                     }
                 }
                 else if (want_j)
@@ -468,7 +451,13 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     const int32_t* tab = ints + op.tab;
                     double* jr = jac_e + (int64_t)op.jrow_off * P.j_sr;
                     const int64_t sr = P.j_sr;
-                    const bool three = op.n_rows == 3;
+                    const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
+                    double ux = 0.0, uy = 0.0, uz = 0.0;
+                    if (row_mode == ROWS_DIST)
+                    {
+                        const double nrm = norm3_scaled(Phi.x, Phi.y, Phi.z);
+                        ux = Phi.x / nrm; uy = Phi.y / nrm; uz = Phi.z / nrm;
+                    }
                     for (int col = 0; col < N; ++col)
                     {
                         const int ent = tab[col];
@@ -507,18 +496,17 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                                 w0 = 0.0 - w0; w1 = 0.0 - w1; w2 = 0.0 - w2;
                             }
                         }
-                        double* jc = jr + (int64_t)col * P.j_sc;
-                        jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2;
-                        if (!three)
-                        {
-                            jc[3 * sr] = w0; jc[4 * sr] = w1; jc[5 * sr] = w2;
-                        }
+                        store_rows(row_mode, jr + (int64_t)col * P.j_sc, sr, v0, v1, v2, w0, w1, w2, ux, uy, uz);
                     }
                 }
             }
             else if (op.kind == OP_EMIT_JLIMIT)
             {
                 emit_joint_limit(c, N, qs, CS, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
+            }
+            else if (op.kind == OP_EMIT_JPOSE)
+            {
+                emit_joint_pose(c, ints + op.tab, op.n_items, N, qs, CS, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
             }
             else if (op.kind == OP_EMIT_FILL)
             {

@@ -64,7 +64,7 @@ struct ChainFrameP
     double binv[12];  // inverse of the constant temp_B
     int32_t k_kind;   // F_OFFA_NONE / F_OFFA_TRANS / F_OFFA_FULL
     int32_t b_const;  // 0: temp_B is the identity
-    int32_t map_kind, rot_type, phi_off, jrow_off, n_rows, pad;
+    int32_t map_kind, rot_type, phi_off, jrow_off, n_rows, row_mode;  // row_mode: program.h RowMode
     int64_t phi_byte_off;  // 8 * phi_off * phi_sk     (filled per launch by chain_bind)
 };
 struct ChainFillP

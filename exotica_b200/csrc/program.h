@@ -24,7 +24,8 @@ enum OpKind : int32_t
     OP_EMIT_FRAME = 3,   // EffFrame / EffPosition / raw frame outputs of ONE requested frame
     OP_EMIT_JLIMIT = 4,  // JointLimit
     OP_EMIT_FILL = 5,    // unused map: Phi.SetZero() identity encodings + zero Jacobian rows
-    OP_EMIT_SPHERES = 6  // SphereCollision
+    OP_EMIT_SPHERES = 6, // SphereCollision
+    OP_EMIT_JPOSE = 7    // JointPose
 };
 
 // frame sources
@@ -61,7 +62,18 @@ enum : int32_t
     F_B_IDENTITY = 0 << 2,  // temp_B = identity
     F_B_CONST = 1 << 2,     // temp_B constant: consts hold its INVERSE
     F_B_SLOT = 2 << 2,      // temp_B = slot * offB
-    F_B_MASK = 3 << 2
+    F_B_MASK = 3 << 2,
+    // which rows of the frame's 6 x N Jacobian the map keeps (bits 4-6)
+    F_ROWS_SHIFT = 4,
+    F_ROWS_MASK = 7 << 4
+};
+enum RowMode : int32_t
+{
+    ROWS_VW = 0,    // 6 rows: linear then angular velocity (EffFrame, raw frames)
+    ROWS_V = 1,     // 3 rows: linear (EffPosition)
+    ROWS_W = 2,     // 3 rows: angular (EffOrientation)
+    ROWS_VXY = 3,   // 2 rows: x and y of the linear part (EffPositionXY)
+    ROWS_DIST = 4   // 1 row: (p . J_v) / |p| (Distance)
 };
 
 // One op = 16 int32 (64 B) + a slice of the double constant pool.
@@ -144,7 +156,7 @@ struct ProgramHeader
     int32_t n_pos_slots;      // two-pass mode: requested frames (one position slot each)
 };
 
-// two-pass mode: OP_JOINT's `tab` points at [n, then n x {pos_slot, column, jrow_off, n_rows, flags, cst_b}] in the int pool
+// two-pass mode: OP_JOINT's `tab` points at [n, then n x {pos_slot, column, jrow_off, row mode, flags, cst_b}] in the int pool
 enum
 {
     TP_INTS = 6,

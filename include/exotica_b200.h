@@ -80,7 +80,13 @@ typedef enum
     EXO_MAP_EFF_POSITION = 1,
     EXO_MAP_JOINT_LIMIT = 2,
     EXO_MAP_SPHERE_COLLISION = 3,
-    EXO_MAP_FRAMES = 4
+    EXO_MAP_FRAMES = 4,
+    /* sibling maps that reuse the same frames (exotations/exotica_core_task_maps/src/
+     * {eff_orientation,eff_position_xy,distance,joint_pose}.cpp) */
+    EXO_MAP_EFF_ORIENTATION = 5,
+    EXO_MAP_EFF_POSITION_XY = 6,
+    EXO_MAP_DISTANCE = 7,
+    EXO_MAP_JOINT_POSE = 8
 } exo_map_kind;
 
 typedef struct exo_tree exo_tree;       /* backend of exotica::KinematicTree (scene.h:195 kinematica_) */
@@ -126,6 +132,9 @@ typedef struct
     const int32_t* group;    /* [n_frames] rank of the sphere's Group name in lexicographic order (std::map order) */
     int32_t is_used;         /* TaskMap::is_used (rho != 0 somewhere, tasks.cpp:246-259); unused maps only get the
                                 SetZero fill (task_space_vector.cpp:54-62) */
+    int32_t n_joint_map;     /* JointPose: entries of JointMap (0 = all controlled joints in order, init/joint_pose.in) */
+    const int32_t* joint_map;/* [n_joint_map] controlled-joint indices */
+    const double* joint_ref; /* [n_joint_map or N] JointRef, NULL = zeros */
 } exo_task_map_desc;
 
 /* ---- errors / device ------------------------------------------------------------------------- */

@@ -969,6 +969,33 @@ int exo_oracle_problem_add_map(exo_oracle* o, int kind, int frame_start, int n_f
         case EXO_ORC_MAP_JOINT_LIMIT:
             m->length = m->length_jacobian = o->n_ctrl; /* joint_limit.cpp:58-61 */
             break;
+        case EXO_ORC_MAP_EFF_ORIENTATION:
+            if (rotation_length(rot_type) < 0) return -1;
+            m->length = n_frames * rotation_length(rot_type); /* eff_orientation.cpp:100-103 */
+            m->length_jacobian = n_frames * 3;                /* eff_orientation.cpp:105-108 */
+            break;
+        case EXO_ORC_MAP_EFF_POSITION_XY:
+            m->length = m->length_jacobian = n_frames * 2;
+            break;
+        case EXO_ORC_MAP_DISTANCE:
+            m->length = m->length_jacobian = n_frames;
+            break;
+        case EXO_ORC_MAP_JOINT_POSE:
+        {
+            /* joint_pose.cpp:66-97: sphere_group carries JointMap, sphere_radius JointRef, param their length;
+             * no frames (n_frames must be 0) */
+            const int n = (int)param;
+            m->n_groups = n;
+            m->group = (int*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+            m->radius = (double*)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+            for (i = 0; i < n; ++i)
+            {
+                m->group[i] = sphere_group[i];
+                m->radius[i] = sphere_radius[i];
+            }
+            m->length = m->length_jacobian = n;
+            break;
+        }
         case EXO_ORC_MAP_SPHERE_COLLISION:
             m->group = (int*)malloc((size_t)(n_frames > 0 ? n_frames : 1) * sizeof(int));
             m->radius = (double*)malloc((size_t)(n_frames > 0 ? n_frames : 1) * sizeof(double));
@@ -1034,6 +1061,64 @@ static void map_eff_position(const exo_oracle* o, const taskmap_t* m, double* ph
         if (jac)
             for (c = 0; c < o->n_ctrl; ++c)
                 for (r = 0; r < 3; ++r) jac[(size_t)c * ldj + i * 3 + r] = kj[6 * c + r];
+    }
+}
+
+/* EffOrientation::Update (eff_orientation.cpp:53-71) */
+static void map_eff_orientation(const exo_oracle* o, const taskmap_t* m, double* phi, double* jac, int ldj)
+{
+    int i, r, c;
+    const int stride = rotation_length(m->rot_type);
+    for (i = 0; i < m->n_frames; ++i)
+    {
+        const kframe_t* f = &o->fr[m->frame_start + i];
+        const double* kj = o->jac + (size_t)(m->frame_start + i) * 6 * o->n_ctrl;
+        exo_oracle_set_rotation(f->temp_ab.M, m->rot_type, phi + i * stride);
+        if (jac)
+            for (c = 0; c < o->n_ctrl; ++c)
+                for (r = 0; r < 3; ++r) jac[(size_t)c * ldj + i * 3 + r] = kj[6 * c + 3 + r]; /* bottomRows<3> */
+    }
+}
+
+/* EffPositionXY::Update (eff_position_xy.cpp:36-57) */
+static void map_eff_position_xy(const exo_oracle* o, const taskmap_t* m, double* phi, double* jac, int ldj)
+{
+    int i, r, c;
+    for (i = 0; i < m->n_frames; ++i)
+    {
+        const kframe_t* f = &o->fr[m->frame_start + i];
+        const double* kj = o->jac + (size_t)(m->frame_start + i) * 6 * o->n_ctrl;
+        phi[i * 2 + 0] = f->temp_ab.p[0];
+        phi[i * 2 + 1] = f->temp_ab.p[1];
+        if (jac)
+            for (c = 0; c < o->n_ctrl; ++c)
+                for (r = 0; r < 2; ++r) jac[(size_t)c * ldj + i * 2 + r] = kj[6 * c + r];
+    }
+}
+
+/* Distance::Update (distance.cpp:36-57) */
+static void map_distance(const exo_oracle* o, const taskmap_t* m, double* phi, double* jac, int ldj)
+{
+    int i, c;
+    for (i = 0; i < m->n_frames; ++i)
+    {
+        const kframe_t* f = &o->fr[m->frame_start + i];
+        const double* kj = o->jac + (size_t)(m->frame_start + i) * 6 * o->n_ctrl;
+        const double* p = f->temp_ab.p;
+        phi[i] = vec_norm_kdl(p);
+        if (jac)
+            for (c = 0; c < o->n_ctrl; ++c) jac[(size_t)c * ldj + i] = (p[0] * kj[6 * c] + p[1] * kj[6 * c + 1] + p[2] * kj[6 * c + 2]) / phi[i];
+    }
+}
+
+/* JointPose::Update (joint_pose.cpp:36-57) */
+static void map_joint_pose(const exo_oracle* o, const taskmap_t* m, const double* q, double* phi, double* jac, int ldj)
+{
+    int i;
+    for (i = 0; i < m->n_groups; ++i)
+    {
+        phi[i] = q[m->group[i]] - m->radius[i];
+        if (jac) jac[(size_t)m->group[i] * ldj + i] = 1.0;
     }
 }
 
@@ -1116,11 +1201,13 @@ int exo_oracle_problem_update(exo_oracle* o, const double* x, double* phi, doubl
     for (k = 0; k < o->n_maps; ++k)
     {
         const taskmap_t* m = &o->maps[k];
-        if (m->kind == EXO_ORC_MAP_EFF_FRAME)
+        if (m->kind == EXO_ORC_MAP_EFF_FRAME || m->kind == EXO_ORC_MAP_EFF_ORIENTATION)
         {
+            /* GetLieGroupIndices: eff_frame.cpp:43-51, eff_orientation.cpp:42-51 */
             static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            int big = 3 + rotation_length(m->rot_type);
-            for (i = 0; i < m->n_frames; ++i) exo_oracle_set_rotation(ident, m->rot_type, phi + m->start + i * big + 3);
+            const int lead = m->kind == EXO_ORC_MAP_EFF_FRAME ? 3 : 0;
+            int big = lead + rotation_length(m->rot_type);
+            for (i = 0; i < m->n_frames; ++i) exo_oracle_set_rotation(ident, m->rot_type, phi + m->start + i * big + lead);
         }
     }
     if (jac) memset(jac, 0, (size_t)ldj * (size_t)o->n_ctrl * sizeof(double)); /* jacobian.setZero() */
@@ -1142,6 +1229,18 @@ int exo_oracle_problem_update(exo_oracle* o, const double* x, double* phi, doubl
                 break;
             case EXO_ORC_MAP_SPHERE_COLLISION:
                 map_sphere_collision(o, m, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_EFF_ORIENTATION:
+                map_eff_orientation(o, m, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_EFF_POSITION_XY:
+                map_eff_position_xy(o, m, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_DISTANCE:
+                map_distance(o, m, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_JOINT_POSE:
+                map_joint_pose(o, m, x, phi + m->start, jrows, ldj);
                 break;
             default:
                 return -1;
@@ -1293,21 +1392,22 @@ int exo_oracle_problem_ydiff(const exo_oracle* o, const double* phi, const doubl
     for (k = 0; k < o->n_maps; ++k)
     {
         const taskmap_t* m = &o->maps[k];
-        if (m->kind == EXO_ORC_MAP_EFF_FRAME)
+        if (m->kind == EXO_ORC_MAP_EFF_FRAME || m->kind == EXO_ORC_MAP_EFF_ORIENTATION)
         {
-            const int rl = rotation_length(m->rot_type), big = 3 + rl;
+            const int lead = m->kind == EXO_ORC_MAP_EFF_FRAME ? 3 : 0;
+            const int rl = rotation_length(m->rot_type), big = lead + rl;
             for (f = 0; f < m->n_frames; ++f)
             {
                 const double* a = phi + m->start + f * big;
                 const double* b = goal + m->start + f * big;
-                double* out = ydiff + m->start_jacobian + 6 * f;
+                double* out = ydiff + m->start_jacobian + (lead + 3) * f;
                 double M1[9], M2[9], M2t[9], M[9], rv[3];
-                for (i = 0; i < 3; ++i) out[i] = a[i] - b[i];
-                if (exo_oracle_get_rotation(a + 3, m->rot_type, M1) || exo_oracle_get_rotation(b + 3, m->rot_type, M2)) return -1;
+                for (i = 0; i < lead; ++i) out[i] = a[i] - b[i];
+                if (exo_oracle_get_rotation(a + lead, m->rot_type, M1) || exo_oracle_get_rotation(b + lead, m->rot_type, M2)) return -1;
                 rot_transpose(M2, M2t);
                 rot_mul(M2t, M1, M);
                 rot_get_rot(M, rv);
-                rot_vec(M1, rv, out + 3);
+                rot_vec(M1, rv, out + lead);
             }
         }
         else

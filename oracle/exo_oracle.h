@@ -63,7 +63,12 @@ enum
     EXO_ORC_MAP_EFF_FRAME = 0,
     EXO_ORC_MAP_EFF_POSITION = 1,
     EXO_ORC_MAP_JOINT_LIMIT = 2,
-    EXO_ORC_MAP_SPHERE_COLLISION = 3
+    EXO_ORC_MAP_SPHERE_COLLISION = 3,
+    /* 4 is the C-ABI's raw-frames pseudo map; numbering follows exo_map_kind */
+    EXO_ORC_MAP_EFF_ORIENTATION = 5,
+    EXO_ORC_MAP_EFF_POSITION_XY = 6,
+    EXO_ORC_MAP_DISTANCE = 7,
+    EXO_ORC_MAP_JOINT_POSE = 8
 };
 
 typedef struct exo_oracle exo_oracle;

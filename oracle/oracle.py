@@ -15,7 +15,8 @@ _LIB = None
 
 ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
 ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
-MAP_KINDS = {"EffFrame": 0, "EffPosition": 1, "JointLimit": 2, "SphereCollision": 3}
+MAP_KINDS = {"EffFrame": 0, "EffPosition": 1, "JointLimit": 2, "SphereCollision": 3, "EffOrientation": 5, "EffPositionXY": 6, "Distance": 7,
+             "JointPose": 8}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -201,6 +202,12 @@ class Oracle(object):
             grp = rad = None
             if kind == 2:
                 param = float(m.get("SafePercentage", 0.0))
+            if kind == 8:
+                # JointPose::Initialize (joint_pose.cpp:66-97): JointMap defaults to all controlled joints, JointRef to zeros
+                jm = list(m.get("JointMap", range(self.n)))
+                grp = np.array(jm, dtype=np.int32)
+                rad = np.array(m.get("JointRef", [0.0] * len(jm)), dtype=np.float64)
+                param = float(len(jm))
             if kind == 3:
                 param = float(m["Precision"])
                 names = sorted(set(f.get("Group", "default") for f in m["EndEffector"]))  # std::map order
@@ -251,11 +258,18 @@ class Oracle(object):
         for m in self.maps:
             kind = MAP_KINDS[m["type"]]
             nf = len(m.get("EndEffector", []))
-            if kind == 0:
+            if kind in (0, 5):
                 rl = ROTATION_LENGTH[ROTATION_TYPES[m.get("Type", "RPY")]]
+                lead = 3 if kind == 0 else 0
                 for f in range(nf):
-                    y[start + f * (3 + rl) + 3:start + (f + 1) * (3 + rl)] = set_rotation(ident, m.get("Type", "RPY"))
-                start += nf * (3 + rl)
+                    y[start + f * (lead + rl) + lead:start + (f + 1) * (lead + rl)] = set_rotation(ident, m.get("Type", "RPY"))
+                start += nf * (lead + rl)
+            elif kind == 6:
+                start += 2 * nf
+            elif kind == 7:
+                start += nf
+            elif kind == 8:
+                start += len(m.get("JointMap", range(self.n)))
             elif kind == 1:
                 start += 3 * nf
             elif kind == 2:

@@ -12,13 +12,17 @@ def gpu_problem_from_maps(orc, maps, tree_state=None):
     prob = _capi.Problem(tree)
     for m in maps:
         kind = {"EffFrame": _capi.MAP_EFF_FRAME, "EffPosition": _capi.MAP_EFF_POSITION, "JointLimit": _capi.MAP_JOINT_LIMIT,
-                "SphereCollision": _capi.MAP_SPHERE_COLLISION, "Frames": _capi.MAP_FRAMES}[m["type"]]
+                "SphereCollision": _capi.MAP_SPHERE_COLLISION, "Frames": _capi.MAP_FRAMES, "EffOrientation": _capi.MAP_EFF_ORIENTATION,
+                "EffPositionXY": _capi.MAP_EFF_POSITION_XY, "Distance": _capi.MAP_DISTANCE, "JointPose": _capi.MAP_JOINT_POSE}[m["type"]]
         frames = m.get("EndEffector", [])
         kw = dict(rotation_type=_capi.ROTATION_TYPES[m.get("Type", "RPY")], safe_percentage=m.get("SafePercentage", 0.0),
                   precision=m.get("Precision", 1.0), is_used=m.get("used", True))
         if frames:
             ea, oa, eb, ob = orc.resolve_frames(frames)
             kw.update(elem_a=ea, off_a=oa, elem_b=eb, off_b=ob)
+        if kind == _capi.MAP_JOINT_POSE:
+            kw["joint_map"] = m.get("JointMap")
+            kw["joint_ref"] = m.get("JointRef")
         if kind == _capi.MAP_SPHERE_COLLISION:
             names = sorted(set(f.get("Group", "default") for f in frames))
             kw["group"] = [names.index(f.get("Group", "default")) for f in frames]
@@ -69,6 +73,19 @@ def angle_entries(maps, orc):
                 for f in range(nf):
                     idx += [start + f * (3 + rl) + 3 + k for k in range(3)]
             start += nf * (3 + rl)
+        elif t == "EffOrientation":
+            rot = m.get("Type", "RPY")
+            rl = _capi.ROTATION_LENGTH[_capi.ROTATION_TYPES[rot]]
+            if rot in ("RPY", "ZYX", "ZYZ"):
+                for f in range(nf):
+                    idx += [start + f * rl + k for k in range(3)]
+            start += nf * rl
+        elif t == "EffPositionXY":
+            start += 2 * nf
+        elif t == "Distance":
+            start += nf
+        elif t == "JointPose":
+            start += len(m.get("JointMap", range(orc.n)))
         elif t == "EffPosition":
             start += 3 * nf
         elif t == "JointLimit":

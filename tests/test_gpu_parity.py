@@ -402,3 +402,52 @@ def test_min_sphere_distance_and_trajectory_min(oracle_lib):
     assert np.max(np.abs(got - ref)) <= 1e-10
     assert np.max(np.abs(got_traj - ref.reshape(B, T).min(axis=1))) <= 1e-10
     orc.set_problem(maps)
+
+
+# ---- sibling task maps that reuse the same frames ------------------------------------------------
+@pytest.mark.parametrize("rot", ["RPY", "Quaternion", "AngleAxis", "Matrix"])
+def test_sibling_maps_on_a_chain(oracle_lib, rot):
+    # EffOrientation / EffPositionXY / Distance / JointPose at the chain tip: the DH chain kernel's generic row emitter
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffOrientation", "Type": rot, "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0, 0, 0.05, 0.2, 0.1, -0.3]}]},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link", "BaseOffset": [0.5, 0.2, 0.4]}]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    prob, phi, jac = _check(orc, maps, random_states(orc, 2048, seed=101))
+    assert "exo_chain_kernel" in prob.kernels_used
+
+
+def test_sibling_maps_on_trees_and_joint_pose(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "JointPose", "JointMap": [6, 2, 0], "JointRef": [0.1, -0.2, 0.3]},
+            {"type": "EffOrientation", "EndEffector": [{"Link": "lwr_arm_5_link"}, {"Link": "lwr_arm_7_link", "Base": "lwr_arm_2_link"}]},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link", "Base": "lwr_arm_3_link"}, {"Link": "lwr_arm_4_link"}]},
+            {"type": "JointPose"},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "lwr_arm_6_link", "LinkOffset": [0.1, 0, 0]}]}]
+    _check(orc, maps, random_states(orc, 1024, seed=102))
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffOrientation", "Type": "Matrix", "EndEffector": [{"Link": "leftPalm"}, {"Link": "rightFoot"}]},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "head"}, {"Link": "leftFoot"}]},
+            {"type": "JointPose", "JointMap": list(range(18, 38))},
+            {"type": "EffPosition", "EndEffector": [{"Link": "rightPalm"}]}]
+    X = random_states(orc, 512, seed=103)
+    _check(orc, maps, X)
+    _check(orc, maps + [{"type": "Distance", "EndEffector": [{"Link": "leftPalm", "Base": "rightPalm"}]}], X)
+
+
+def test_sibling_maps_cost_and_unused_fill(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffOrientation", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "EffOrientation", "Type": "Matrix", "used": False, "EndEffector": [{"Link": "lwr_arm_4_link"}]},
+            {"type": "JointPose", "JointRef": list(np.linspace(-0.3, 0.3, 7))},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc.set_problem(maps)
+    X = random_states(orc, 300, seed=104)
+    prob, phi, jac = _check(orc, maps, X)
+    assert np.all(phi[:, 4:13] == np.array([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))  # unused map: identity matrix fill
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    goal = orc.zero_goal()
+    goal[0:4] = oracle_lib.set_rotation(oracle_lib.get_frame([0, 0, 0, 0.4, -0.3, 0.2])[:9], "Quaternion")
+    cost, _ = _gpu_costs(prob, X, 300, 1, [2.0, 0.0, 0.5, 3.0], goal=goal)
+    ref = np.array([orc.trajectory_cost(X[e:e + 1], [2.0, 0.0, 0.5, 3.0], goal=goal)[0] for e in range(300)])
+    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())

@@ -42,7 +42,8 @@ def test_lwr_names_and_factories():
     assert scene.get_controlled_link_names() == ["lwr_arm_%d_link" % i for i in range(1, 8)]
     assert scene.get_model_link_names()[:3] == ["world_frame", "base", "lwr_arm_0_link"]
     assert scene.get_root_frame_name() == "world_frame"
-    assert set(["exotica/EffFrame", "exotica/EffPosition", "exotica/JointLimit", "exotica/SphereCollision"]) <= set(exo.Setup.get_maps())
+    assert set(["exotica/EffFrame", "exotica/EffPosition", "exotica/JointLimit", "exotica/SphereCollision", "exotica/EffOrientation",
+                "exotica/EffPositionXY", "exotica/Distance", "exotica/JointPose"]) <= set(exo.Setup.get_maps())
     assert set(["exotica/UnconstrainedEndPoseProblem", "exotica/TimeIndexedProblem"]) <= set(exo.Setup.get_problems())
 
 
@@ -143,3 +144,33 @@ def test_scene_update_fk_and_jacobian(oracle_lib):
     # LWR at q = 0, fk(lwr_arm_7_link) = (0, 0, 1.1985)
     scene.update(np.zeros(7))
     assert np.max(np.abs(scene.fk("lwr_arm_7_link")[9:] - [0, 0, 1.1985])) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_sibling_maps_through_the_factory(oracle_lib):
+    from helpers import angle_entries, max_abs_err
+    # exotica_examples-style problem with EffOrientation + Distance + JointPose + EffPositionXY built from initializers
+    frame = ("exotica/Frame", {"Link": "lwr_arm_7_link"})
+    maps_init = [("exotica/EffOrientation", {"Name": "Ori", "Type": "Quaternion", "EndEffector": [frame]}),
+                 ("exotica/Distance", {"Name": "Dist", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link", "BaseOffset": [0.4, 0.0, 0.5]})]}),
+                 ("exotica/JointPose", {"Name": "Pose", "JointMap": "1 3 5", "JointRef": "0.1 0.2 0.3"}),
+                 ("exotica/EffPositionXY", {"Name": "XY", "EndEffector": [frame]})]
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": maps_init,
+                                                    "Cost": [("exotica/Task", {"Task": n, "Rho": r}) for n, r in (("Ori", "1"), ("Dist", "2"), ("Pose", "3"), ("XY", "4"))]})
+    prob = exo.Setup.create_problem(init)
+    assert (prob.length_Phi, prob.length_jacobian) == (4 + 1 + 3 + 2, 3 + 1 + 3 + 2)
+    maps = [{"type": "EffOrientation", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link", "BaseOffset": [0.4, 0.0, 0.5]}]},
+            {"type": "JointPose", "JointMap": [1, 3, 5], "JointRef": [0.1, 0.2, 0.3]},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc = _oracle_for(oracle_lib, maps)
+    X = np.random.default_rng(21).uniform(orc.lower, orc.upper, size=(200, 7))
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    cost = prob.cost_batch(X)
+    ref = np.array([orc.trajectory_cost(X[e:e + 1], [1.0, 2.0, 3.0, 4.0])[0] for e in range(200)])
+    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    with pytest.raises(exo.ExoticaError, match="JointMap index"):
+        exo.Setup.create_problem(("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"),
+                                                                          "Maps": [("exotica/JointPose", {"Name": "P", "JointMap": "9"})]}))
