@@ -425,7 +425,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int NJ, bool ALLREV, int VARIANT>
+// GEN: some requested frame belongs to a map that keeps other rows than (v, w) / (v) -- EffOrientation, EffPositionXY,
+// Distance; the plain instantiations do not carry that code (it costs the hot kernel registers)
+template <int NJ, bool ALLREV, int VARIANT, bool GEN>
 __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const __grid_constant__ ChainParams P)
 {
     const int64_t stride = (int64_t)gridDim.x * CTPB;
@@ -477,7 +479,7 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
             continue;
         }
         Fr cur = load_frame(P.base);
-        if (VARIANT == CHAIN_TWO_PASS && P.n_frames == 1 && P.frame[0].row_mode <= ROWS_V)
+        if (VARIANT == CHAIN_TWO_PASS && !GEN && P.n_frames == 1)
         {
             ChainUnroll<NJ, ALLREV, 0>::compose(P, cur, q, sn, cs);
             const ChainFrameP& fp = P.frame[0];
@@ -508,7 +510,7 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
             {
                 const ChainFrameP& fp = P.frame[f];
                 const Fr A = chain_frame_a(fp, cur);
-                if (jac_e && fp.row_mode > ROWS_V)
+                if (GEN && jac_e && fp.row_mode > ROWS_V)
                 {
                     // EffOrientation / EffPositionXY / Distance: the generic emitter; Distance needs Phi.p / |Phi.p|
                     double ux = 0.0, uy = 0.0, uz = 0.0;
@@ -574,14 +576,14 @@ static int chain_prefetch_generations()
     return gens;
 }
 
-template <int NJ, bool ALLREV, int VARIANT>
+template <int NJ, bool ALLREV, int VARIANT, bool GEN>
 cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
 {
     static int ctas_per_sm = 0;  // occupancy is a property of the instantiation: query once
     if (ctas_per_sm == 0)
     {
         int ctas = 0;
-        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_chain_kernel<NJ, ALLREV, VARIANT>, CTPB, 0);
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_chain_kernel<NJ, ALLREV, VARIANT, GEN>, CTPB, 0);
         if (err != cudaSuccess) return err;
         if (ctas < 1) return cudaErrorInvalidConfiguration;
         ctas_per_sm = ctas;
@@ -591,23 +593,23 @@ cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
     const int blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
     ChainParams Q = P;
     Q.prefetch_ahead = (int64_t)sms * ctas_per_sm * CTPB * chain_prefetch_generations() / 4;
-    exo_chain_kernel<NJ, ALLREV, VARIANT><<<blocks, CTPB, 0, stream>>>(Q);
+    exo_chain_kernel<NJ, ALLREV, VARIANT, GEN><<<blocks, CTPB, 0, stream>>>(Q);
     return cudaGetLastError();
 }
 
-template <bool ALLREV, int VARIANT>
+template <bool ALLREV, int VARIANT, bool GEN>
 cudaError_t chain_launch_nj(const ChainParams& P, int sms, cudaStream_t stream)
 {
     switch (P.n_joints)
     {
-        case 1: return chain_launch_t<1, ALLREV, VARIANT>(P, sms, stream);
-        case 2: return chain_launch_t<2, ALLREV, VARIANT>(P, sms, stream);
-        case 3: return chain_launch_t<3, ALLREV, VARIANT>(P, sms, stream);
-        case 4: return chain_launch_t<4, ALLREV, VARIANT>(P, sms, stream);
-        case 5: return chain_launch_t<5, ALLREV, VARIANT>(P, sms, stream);
-        case 6: return chain_launch_t<6, ALLREV, VARIANT>(P, sms, stream);
-        case 7: return chain_launch_t<7, ALLREV, VARIANT>(P, sms, stream);
-        case 8: return chain_launch_t<8, ALLREV, VARIANT>(P, sms, stream);
+        case 1: return chain_launch_t<1, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 2: return chain_launch_t<2, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 3: return chain_launch_t<3, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 4: return chain_launch_t<4, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 5: return chain_launch_t<5, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 6: return chain_launch_t<6, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 7: return chain_launch_t<7, ALLREV, VARIANT, GEN>(P, sms, stream);
+        case 8: return chain_launch_t<8, ALLREV, VARIANT, GEN>(P, sms, stream);
         default: return cudaErrorInvalidConfiguration;
     }
 }
@@ -615,7 +617,11 @@ cudaError_t chain_launch_nj(const ChainParams& P, int sms, cudaStream_t stream)
 template <int VARIANT>
 cudaError_t chain_launch_v(const ChainParams& P, int sms, cudaStream_t stream)
 {
-    return P.all_revolute ? chain_launch_nj<true, VARIANT>(P, sms, stream) : chain_launch_nj<false, VARIANT>(P, sms, stream);
+    bool gen = false;
+    for (int f = 0; f < P.n_frames; ++f) gen = gen || P.frame[f].row_mode > ROWS_V;
+    if (gen)  // the generic row emitter exists in the one-pass variant only
+        return P.all_revolute ? chain_launch_nj<true, CHAIN_REGS, true>(P, sms, stream) : chain_launch_nj<false, CHAIN_REGS, true>(P, sms, stream);
+    return P.all_revolute ? chain_launch_nj<true, VARIANT, false>(P, sms, stream) : chain_launch_nj<false, VARIANT, false>(P, sms, stream);
 }
 }  // namespace
 
