@@ -180,23 +180,30 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
                         if (live)
                         {
                             // four pairs per iteration: straight-line code whose independent Horner / Newton chains the
-                            // scheduler interleaves (the FP64 pipe needs ~5 independent instructions in flight per warp)
-                            for (int j0 = t0 + part; j0 < t1; j0 += 4 * parts)
+                            // scheduler interleaves (the FP64 pipe needs ~5 independent instructions in flight per warp).
+                            // Full groups of four run without masks; the tail (at most three pairs per lane) is masked.
+                            const double2* c2 = reinterpret_cast<const double2*>(centre);  // [S][2]: (x, y), (z, radius)
+                            int j0 = t0 + part;
+                            for (; j0 + 3 * parts < t1; j0 += 4 * parts)
                             {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
                                 {
                                     const int j = j0 + u * parts;
-                                    const bool ok = j < t1;
-                                    const int jj = ok ? j : t0;
-                                    const double w = ok ? 1.0 : 0.0;
+                                    const double2 a = c2[2 * j], b = c2[2 * j + 1];
                                     if (pass == 0)
-                                        sph_pair<true>(pix - centre[4 * jj], piy - centre[4 * jj + 1], piz - centre[4 * jj + 2], ri + centre[4 * jj + 3],
-                                                       k5, w, ph, gx, gy, gz, dmin);
+                                        sph_pair<true>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, 1.0, ph, gx, gy, gz, dmin);
                                     else
-                                        sph_pair<false>(centre[4 * jj] - pix, centre[4 * jj + 1] - piy, centre[4 * jj + 2] - piz, 0.0, k5, w, ph, gx, gy,
-                                                        gz, dmin);
+                                        sph_pair<false>(a.x - pix, a.y - piy, b.x - piz, 0.0, k5, 1.0, ph, gx, gy, gz, dmin);
                                 }
+                            }
+                            for (; j0 < t1; j0 += parts)
+                            {
+                                const double2 a = c2[2 * j0], b = c2[2 * j0 + 1];
+                                if (pass == 0)
+                                    sph_pair<true>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, 1.0, ph, gx, gy, gz, dmin);
+                                else
+                                    sph_pair<false>(a.x - pix, a.y - piy, b.x - piz, 0.0, k5, 1.0, ph, gx, gy, gz, dmin);
                             }
                         }
                         phi_part += ph;
@@ -274,7 +281,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
     double* qs = scr + (size_t)H->scratch_doubles * CS;
     // per-warp area behind the per-thread scratch: sphere centre table (4 doubles per sphere) + Jacobian row accumulators
     double* warp_smem = reinterpret_cast<double*>(smem + P.scratch_offset) + (size_t)(H->scratch_doubles + N) * CS +
-                        (size_t)(tid >> 5) * (4 * H->max_spheres + N);
+                        (size_t)(tid >> 5) * (4 * H->max_spheres + N + (N & 1));  // even number of doubles: 16-byte aligned tables
     const bool want_j = P.jac != nullptr;
 
     // The loop is warp-uniform (SphereCollision is evaluated by the whole warp for one lane's evaluation at a time):
@@ -570,7 +577,7 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     const size_t prog = ((size_t)program_bytes + 15) & ~(size_t)15;
     const size_t per_column = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * sizeof(double);
     const bool spheres = hdr.max_spheres > 0;
-    const size_t per_warp = spheres ? (size_t)(4 * hdr.max_spheres + hdr.n_ctrl) * sizeof(double) : 0;
+    const size_t per_warp = spheres ? (size_t)(4 * hdr.max_spheres + hdr.n_ctrl + (hdr.n_ctrl & 1)) * sizeof(double) : 0;
     params.scratch_offset = (int32_t)prog;
     const EvalConfig* cands = spheres ? kSpheres : kPlain;
     const int n_cands = spheres ? (int)(sizeof(kSpheres) / sizeof(kSpheres[0])) : (int)(sizeof(kPlain) / sizeof(kPlain[0]));
