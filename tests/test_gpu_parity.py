@@ -451,3 +451,79 @@ def test_sibling_maps_cost_and_unused_fill(oracle_lib):
     cost, _ = _gpu_costs(prob, X, 300, 1, [2.0, 0.0, 0.5, 3.0], goal=goal)
     ref = np.array([orc.trajectory_cost(X[e:e + 1], [2.0, 0.0, 0.5, 3.0], goal=goal)[0] for e in range(300)])
     assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+
+
+# ---- BASELINE.json configurations 3, 4, 5 at full size: size-independent properties + sampled oracle parity ---------------------
+def _smooth_trajectories(orc, B, T, seed):
+    rng = np.random.default_rng(seed)
+    q0 = random_states(orc, B, seed=seed + 1)
+    return np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, orc.n)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+
+
+def test_full_size_cfg3_time_indexed(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T = 4096, 100
+    X = _smooth_trajectories(orc, B, T, 1237).reshape(B * T, 7)
+    phi, jac = run_gpu(prob, X, T=T)
+    # JointLimit rows: phi is the signed violation, J is diag(violated) and nothing else
+    viol = np.where(X < orc.lower, X - orc.lower, 0.0) + np.where(X > orc.upper, X - orc.upper, 0.0)
+    assert np.array_equal(phi[:, 6:], viol)
+    Jl = jac[:, 6:, :]
+    assert np.array_equal(Jl, np.eye(7)[None] * ((X < orc.lower) | (X > orc.upper))[:, None, :].astype(float))
+    # the last joint rotates about the tool axis: it cannot move the tool centre point
+    assert np.abs(jac[:, 0:3, 6]).max() < 1e-12
+    # timestep-major batches: evaluating one trajectory alone gives the same bits
+    phi1, jac1 = run_gpu(prob, X[17 * T:18 * T], T=T)
+    assert np.array_equal(phi1, phi[17 * T:18 * T]) and np.array_equal(jac1, jac[17 * T:18 * T])
+    sel = np.random.default_rng(3).integers(0, B * T, 4096)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi[sel], phi_ref, angle_entries(maps, orc)) <= TOL and max_abs_err(jac[sel], jac_ref) <= TOL
+
+
+def test_full_size_cfg4_humanoid(oracle_lib):
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "leftFoot"}, {"Link": "rightFoot"}, {"Link": "leftPalm"}, {"Link": "rightPalm"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    assert prob.program_info()["joint_slots"] > 8  # large tree: the two-pass program is chosen automatically
+    E = 1 << 18
+    X = random_states(orc, E, seed=1238)
+    X[:, 3:6] = np.random.default_rng(1239).uniform(-np.pi, np.pi, size=(E, 3))
+    phi, jac = run_gpu(prob, X)
+    J = jac.reshape(E, 4, 6, 38)
+    # floating base: the three translations move every end-effector rigidly (identity linear block, zero angular block)
+    assert np.array_equal(J[:, :, 0:3, 0:3], np.broadcast_to(np.eye(3), (E, 4, 3, 3))) and not J[:, :, 3:6, 0:3].any()
+    # structural zeros: leg joints (6..17) never move the palms, arm / neck joints never move the feet
+    assert not J[:, 2:4, :, 6:18].any() and not J[:, 0:2, :, 18:38].any()
+    # left-leg joints (6..11) do not move the right foot and vice versa
+    assert not J[:, 1, :, 6:12].any() and not J[:, 0, :, 12:18].any()
+    R = phi.reshape(E, 4, 12)[:, :, 3:12].reshape(E, 4, 3, 3)
+    assert np.abs(np.einsum("efij,efkj->efik", R, R) - np.eye(3)).max() < 1e-11
+    sel = np.random.default_rng(4).integers(0, E, 2048)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi[sel], phi_ref) <= TOL and max_abs_err(jac[sel], jac_ref) <= TOL
+
+
+def test_full_size_cfg5_sphere_collision(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    rng = np.random.default_rng(5)
+    eff = [{"Link": "lwr_arm_%d_link" % (1 + i % 7), "LinkOffset": [0.0, 0.0, 0.02 * (i // 7)], "Radius": 0.05, "Group": "Robot"} for i in range(32)]
+    eff += [{"Link": "", "LinkOffset": list(rng.uniform([-0.8, -0.8, 0.0], [0.8, 0.8, 1.2])), "Radius": 0.05, "Group": "Obstacle"} for _ in range(32)]
+    maps = [{"type": "SphereCollision", "Precision": 0.1, "EndEffector": eff}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T = 4096, 100
+    X = _smooth_trajectories(orc, B, T, 1240).reshape(B * T, 7)
+    phi, jac = run_gpu(prob, X, T=T)
+    # 1024 sigmoids per evaluation, each in (0, 1)
+    assert phi.min() > 0.0 and phi.max() < 1024.0 and np.isfinite(jac).all()
+    # permutation equivariance, bit for bit
+    perm = np.random.default_rng(6).permutation(B * T)[: 1 << 14]
+    phi_p, jac_p = run_gpu(prob, X[perm])
+    assert np.array_equal(phi_p, phi[perm]) and np.array_equal(jac_p, jac[perm])
+    sel = np.random.default_rng(7).integers(0, B * T, 1024)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi[sel], phi_ref) <= 1e-9 and max_abs_err(jac[sel], jac_ref) <= 1e-9  # sums of 1024 terms
