@@ -86,6 +86,7 @@ SYMBOLS = [
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
+    ("exo_problem_hessian_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_trajectory_reduce", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
 ]
@@ -353,6 +354,9 @@ class Problem(object):
         out = np.empty(B)
         check(lib().exo_problem_cost_batch_host(self.h, X.ctypes.data, B, LAYOUT_AOS_ROWMAJOR, out.ctypes.data))
         return out
+
+    def hessian_batch_device(self, d_x, d_jac, n_evals, d_hess, T=1, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_hessian_batch(self.h, d_x, d_jac, int(n_evals), int(T), int(layout), d_hess, stream))
 
     def set_min_distance_output(self, d_ptr):
         check(lib().exo_problem_set_min_distance_output(self.h, d_ptr))

@@ -56,6 +56,11 @@ struct exo_problem
     int T = 1, n_generated = 0;
     std::vector<double> h_generated;
     double* d_generated = nullptr;
+    // raw-frames shadow problem behind exo_problem_hessian_batch (all frames of all maps, full 6 x N Jacobians)
+    exo_problem* shadow = nullptr;
+    std::vector<int> shadow_frame_start;  // per map
+    double *d_shadow_phi = nullptr, *d_shadow_jac = nullptr;
+    int64_t shadow_capacity = 0;
     // auxiliary outputs and the task cost (rows e / f1)
     double* d_min_dist = nullptr;  // caller-owned, [n_evals] (exo_problem_set_min_distance_output)
     bool cost_set = false;
@@ -314,6 +319,9 @@ int exo_problem_destroy(exo_problem* p)
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
     if (p->d_image) cudaFree(p->d_image);
     if (p->d_generated) cudaFree(p->d_generated);
+    if (p->shadow) exo_problem_destroy(p->shadow);
+    if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
+    if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
     if (p->d_rho) cudaFree(p->d_rho);
     if (p->d_goal) cudaFree(p->d_goal);
     if (p->d_goal_rot) cudaFree(p->d_goal_rot);
@@ -876,6 +884,121 @@ int exo_problem_cost_batch_host(exo_problem* p, const double* h_x, int64_t n_tra
         CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+    return EXO_OK;
+}
+
+// ---- task-map Hessians ------------------------------------------------------------------------------------------------------
+static int ensure_shadow(exo_problem* p)
+{
+    if (p->shadow) return EXO_OK;
+    int rc = exo_problem_create(p->tree, &p->shadow);
+    if (rc != EXO_OK) return rc;
+    std::vector<int32_t> ea, eb;
+    std::vector<double> oa, ob;
+    p->shadow_frame_start.clear();
+    for (const MapSpec& m : p->maps)
+    {
+        p->shadow_frame_start.push_back((int)ea.size());
+        if (m.kind == EXO_MAP_SPHERE_COLLISION || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_JOINT_POSE) continue;
+        ea.insert(ea.end(), m.elem_a.begin(), m.elem_a.end());
+        eb.insert(eb.end(), m.elem_b.begin(), m.elem_b.end());
+        oa.insert(oa.end(), m.off_a.begin(), m.off_a.end());
+        ob.insert(ob.end(), m.off_b.begin(), m.off_b.end());
+    }
+    if (!ea.empty())
+    {
+        exo_task_map_desc d;
+        memset(&d, 0, sizeof(d));
+        d.kind = EXO_MAP_FRAMES;
+        d.n_frames = (int)ea.size();
+        d.elem_a = ea.data();
+        d.off_a = oa.data();
+        d.elem_b = eb.data();
+        d.off_b = ob.data();
+        d.is_used = 1;
+        rc = exo_problem_add_task_map(p->shadow, &d);
+        if (rc != EXO_OK) return rc;
+    }
+    rc = exo_problem_finalize(p->shadow);
+    if (rc != EXO_OK) return rc;
+    if (p->n_generated > 0) rc = exo_problem_set_generated(p->shadow, p->T, p->n_generated, p->h_generated.data());
+    return rc;
+}
+
+int exo_problem_hessian_batch(exo_problem* p, const double* d_x, const double* d_jac, int64_t n_evals, int32_t T, int32_t layout, double* d_hess,
+                              void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (n_evals < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_evals == 0) return EXO_OK;
+    if (!d_x || !d_jac || !d_hess) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if ((int)p->maps.size() > COST_MAXMAPS) return fail(EXO_ERR_UNSUPPORTED, "more task maps than the Hessian kernel supports");
+    int rc = ensure_shadow(p);
+    if (rc != EXO_OK) return rc;
+    const int64_t N = p->prog.hdr.n_ctrl, LJ = p->prog.hdr.length_jac;
+    const int64_t FP = p->shadow->prog.hdr.length_phi, FJ = p->shadow->prog.hdr.length_jac;  // 12 F, 6 F
+    if (p->shadow_capacity < n_evals)
+    {
+        if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
+        if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
+        p->d_shadow_phi = p->d_shadow_jac = nullptr;
+        p->shadow_capacity = 0;
+        CUDA_TRY(cudaMalloc((void**)&p->d_shadow_phi, std::max<size_t>(8, (size_t)n_evals * FP * sizeof(double))));
+        CUDA_TRY(cudaMalloc((void**)&p->d_shadow_jac, std::max<size_t>(8, (size_t)n_evals * FJ * N * sizeof(double))));
+        p->shadow_capacity = n_evals;
+    }
+    // frames and their full Jacobians in SoA (coalesced for the Hessian kernel whatever the caller's layout is)
+    if (FP > 0)
+    {
+        rc = launch(p->shadow, d_x, n_evals, n_evals, T, layout, p->d_shadow_phi, p->d_shadow_jac, (cudaStream_t)stream, false);
+        if (rc != EXO_OK) return rc;
+    }
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    rc = fill_strides(p, layout, n_evals, k);
+    if (rc != EXO_OK) return rc;
+    HessParams h;
+    memset(&h, 0, sizeof(h));
+    h.frames_phi = p->d_shadow_phi;
+    h.frames_jac = p->d_shadow_jac;
+    h.map_jac = d_jac;
+    h.hess = d_hess;
+    h.n_evals = n_evals;
+    h.n_maps = (int)p->maps.size();
+    h.n_ctrl = (int)N;
+    h.mj_se = k.j_se; h.mj_sr = k.j_sr; h.mj_sc = k.j_sc;
+    // the shadow problem was launched with the caller's layout for X; its outputs follow the same layout family
+    KernelParams ks;
+    memset(&ks, 0, sizeof(ks));
+    rc = fill_strides(p->shadow, layout, n_evals, ks);
+    if (rc != EXO_OK) return rc;
+    h.fp_se = ks.phi_se; h.fp_sk = ks.phi_sk; h.fj_se = ks.j_se; h.fj_sr = ks.j_sr; h.fj_sc = ks.j_sc;
+    if (layout == EXO_LAYOUT_SOA)
+    {
+        h.h_se = 1; h.h_sr = N * N * n_evals; h.h_si = N * n_evals; h.h_sj = n_evals;  // H[LJ][N][N][E]
+    }
+    else
+    {
+        h.h_se = LJ * N * N; h.h_sr = N * N; h.h_si = N; h.h_sj = 1;  // H[E][LJ][N][N]
+    }
+    for (size_t i = 0; i < p->maps.size(); ++i)
+    {
+        const MapSpec& m = p->maps[i];
+        HessMapP& hm = h.map[i];
+        hm.kind = m.kind;
+        hm.is_used = m.is_used ? 1 : 0;
+        hm.n_frames = m.n_frames;
+        hm.frame_start = p->shadow_frame_start[i];
+        hm.start_jacobian = m.start_jacobian;
+        hm.length_jacobian = m.length_jacobian;
+        hm.rows_per_frame = m.n_frames > 0 ? m.length_jacobian / m.n_frames : 0;
+        if (m.kind == EXO_MAP_FRAMES) return fail(EXO_ERR_UNSUPPORTED, "raw-frame maps have no task-map Hessian");
+    }
+    cudaError_t e = launch_hessian(h, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "Hessian kernel launch");
+    p->launches++;
+    p->last_kernel = "exo_hessian_kernel";
     return EXO_OK;
 }
 

@@ -289,3 +289,123 @@ void host_get_rotation(const double* d, int type, double* out)
 }
 
 }  // namespace exo
+
+// ---- task-map Hessians ---------------------------------------------------------------------------
+// KinematicTree::ComputeH (exotica_core/src/kinematic_tree.cpp:947-978) is a pure function of a frame's 6 x N Jacobian:
+//     H(0..2)(i, j) = H(0..2)(j, i) = w_i x v_j        (i <= j;  v = linear rows, w = angular rows of the column)
+//     H(3..5)(j, i) = w_i x w_j                         (i <  j only: the upper triangle and the diagonal stay zero)
+// and the task maps copy blocks of it (eff_frame.cpp:75-90, eff_position.cpp:57-70, eff_orientation.cpp:73-88,
+// eff_position_xy.cpp:59-75), combine them (distance.cpp:59-91, including its integer-division exponent pow(|p|^2, 3/2 = 1))
+// or, without an overload of their own, fall back to J_row^T J_row (exotica_core/src/task_map.cpp:99-108: JointLimit,
+// SphereCollision; JointPose overrides with zero).  One lane = one evaluation; the frame Jacobians come from a raw-frames
+// shadow problem evaluated on the same states (capi.cu), the map Jacobian from the caller's J.
+namespace exo
+{
+namespace
+{
+__global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant__ HessParams P)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P.n_evals; e += stride)
+    {
+        const double* fj = P.frames_jac + e * P.fj_se;  // frames' Jacobians: row (6 f + r), column c at fj[(6 f + r) * fj_sr + c * fj_sc]
+        const double* fp = P.frames_phi + e * P.fp_se;  // frames: entry k of frame f at fp[(12 f + k) * fp_sk]
+        const double* mj = P.map_jac + e * P.mj_se;     // the problem's own Jacobian
+        double* h = P.hess + e * P.h_se;                 // H(row)(i, j) at h[row * h_sr + i * h_si + j * h_sj]
+        const int N = P.n_ctrl;
+        for (int k = 0; k < P.n_maps; ++k)
+        {
+            const HessMapP& m = P.map[k];
+            double* hm = h + (int64_t)m.start_jacobian * P.h_sr;
+            if (m.kind == EXO_MAP_JOINT_POSE || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_SPHERE_COLLISION || !m.is_used)
+            {
+                // zero (JointPose, unused maps) or the base-class fallback J_row^T J_row
+                const bool outer = m.is_used && m.kind != EXO_MAP_JOINT_POSE;
+                for (int r = 0; r < m.length_jacobian; ++r)
+                {
+                    const double* row = mj + (int64_t)(m.start_jacobian + r) * P.mj_sr;
+                    for (int i = 0; i < N; ++i)
+                    {
+                        const double a = outer ? row[i * P.mj_sc] : 0.0;
+                        for (int j = 0; j < N; ++j) hm[r * P.h_sr + i * P.h_si + j * P.h_sj] = outer ? a * row[j * P.mj_sc] : 0.0;
+                    }
+                }
+                continue;
+            }
+            for (int f = 0; f < m.n_frames; ++f)
+            {
+                const double* J = fj + (int64_t)(6 * (m.frame_start + f)) * P.fj_sr;
+                double* hf = hm + (int64_t)(f * m.rows_per_frame) * P.h_sr;
+                double px = 0.0, py = 0.0, pz = 0.0, nrm = 1.0;
+                if (m.kind == EXO_MAP_DISTANCE)
+                {
+                    const double* ph = fp + (int64_t)(12 * (m.frame_start + f)) * P.fp_sk;
+                    px = ph[9 * P.fp_sk]; py = ph[10 * P.fp_sk]; pz = ph[11 * P.fp_sk];
+                    nrm = norm3_scaled(px, py, pz);
+                }
+                for (int i = 0; i < N; ++i)
+                {
+                    const double wix = J[3 * P.fj_sr + i * P.fj_sc], wiy = J[4 * P.fj_sr + i * P.fj_sc], wiz = J[5 * P.fj_sr + i * P.fj_sc];
+                    const double vix = J[i * P.fj_sc], viy = J[P.fj_sr + i * P.fj_sc], viz = J[2 * P.fj_sr + i * P.fj_sc];
+                    for (int j = i; j < N; ++j)
+                    {
+                        const double vjx = J[j * P.fj_sc], vjy = J[P.fj_sr + j * P.fj_sc], vjz = J[2 * P.fj_sr + j * P.fj_sc];
+                        const double wjx = J[3 * P.fj_sr + j * P.fj_sc], wjy = J[4 * P.fj_sr + j * P.fj_sc], wjz = J[5 * P.fj_sr + j * P.fj_sc];
+                        // Hij = axis * column_j with axis = (0, w_i): vel = w_i x v_j, rot = w_i x w_j
+                        const double l0 = wiy * vjz - wiz * vjy, l1 = wiz * vjx - wix * vjz, l2 = wix * vjy - wiy * vjx;
+                        const double a0 = wiy * wjz - wiz * wjy, a1 = wiz * wjx - wix * wjz, a2 = wix * wjy - wiy * wjx;
+                        double* hij = hf + i * P.h_si + j * P.h_sj;
+                        double* hji = hf + j * P.h_si + i * P.h_sj;
+                        const bool diag = i == j;
+                        switch (m.kind)
+                        {
+                            case EXO_MAP_EFF_FRAME:
+                                hij[0] = l0; hij[P.h_sr] = l1; hij[2 * P.h_sr] = l2;
+                                hji[0] = l0; hji[P.h_sr] = l1; hji[2 * P.h_sr] = l2;
+                                hij[3 * P.h_sr] = 0.0; hij[4 * P.h_sr] = 0.0; hij[5 * P.h_sr] = 0.0;
+                                if (!diag)
+                                {
+                                    hji[3 * P.h_sr] = a0; hji[4 * P.h_sr] = a1; hji[5 * P.h_sr] = a2;
+                                }
+                                break;
+                            case EXO_MAP_EFF_POSITION:
+                                hij[0] = l0; hij[P.h_sr] = l1; hij[2 * P.h_sr] = l2;
+                                hji[0] = l0; hji[P.h_sr] = l1; hji[2 * P.h_sr] = l2;
+                                break;
+                            case EXO_MAP_EFF_POSITION_XY:
+                                hij[0] = l0; hij[P.h_sr] = l1;
+                                hji[0] = l0; hji[P.h_sr] = l1;
+                                break;
+                            case EXO_MAP_EFF_ORIENTATION:
+                                hij[0] = 0.0; hij[P.h_sr] = 0.0; hij[2 * P.h_sr] = 0.0;
+                                if (!diag)
+                                {
+                                    hji[0] = a0; hji[P.h_sr] = a1; hji[2 * P.h_sr] = a2;
+                                }
+                                break;
+                            default:  // EXO_MAP_DISTANCE (distance.cpp:76-90)
+                            {
+                                const double ni = px * vix + py * viy + pz * viz, nj = px * vjx + py * vjy + pz * vjz;
+                                const double part1 = -(ni * nj) / (px * px + py * py + pz * pz);  // pow(., 3 / 2) with integer 3 / 2 == 1
+                                const double part2 = ((px * l0 + py * l1 + pz * l2) + (vix * vjx + viy * vjy + viz * vjz)) / nrm;
+                                hij[0] = part1 + part2;
+                                hji[0] = part1 + part2;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_hessian(const HessParams& P, cudaStream_t stream)
+{
+    if (P.n_evals <= 0) return cudaSuccess;
+    const int64_t blocks = (P.n_evals + 127) / 128;
+    exo_hessian_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+}  // namespace exo

@@ -136,4 +136,22 @@ cudaError_t launch_cost(const CostParams& P, cudaStream_t stream);
 cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
 void host_get_rotation(const double* data, int type, double* out9);
 
+// ---- task-map Hessians (cost_kernel.cu) ----
+struct HessMapP
+{
+    int32_t kind, is_used, n_frames, frame_start, start_jacobian, length_jacobian, rows_per_frame, pad;
+};
+struct HessParams
+{
+    const double* frames_phi;  // raw frames of the shadow problem
+    const double* frames_jac;
+    const double* map_jac;     // the problem's own Jacobian
+    double* hess;
+    int64_t n_evals;
+    int64_t fp_se, fp_sk, fj_se, fj_sr, fj_sc, mj_se, mj_sr, mj_sc, h_se, h_sr, h_si, h_sj;  // element strides
+    int32_t n_maps, n_ctrl;
+    HessMapP map[COST_MAXMAPS];
+};
+cudaError_t launch_hessian(const HessParams& P, cudaStream_t stream);
+
 }  // namespace exo

@@ -253,6 +253,17 @@ int exo_problem_set_min_distance_output(exo_problem* problem, double* d_min_dist
 /* d_out[b] = min / sum over t in [t_first, T) of d_in[b * T + t] */
 int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream);
 
+/* ---- task-map Hessians ---------------------------------------------------------------------------
+ * exo_problem_hessian_batch <- KinematicTree::ComputeH (exotica_core/src/kinematic_tree.cpp:947-978) + the Hessian overloads of
+ *     EffFrame / EffPosition / EffOrientation / EffPositionXY / Distance (exotations/exotica_core_task_maps/src/), the
+ *     zero Hessian of JointPose and the base-class fallback J_row^T J_row of maps without an overload
+ *     (exotica_core/src/task_map.cpp:99-108: JointLimit, SphereCollision).
+ * d_x / d_jac: the state and Jacobian buffers of exo_problem_update_batch for the same n_evals, T and layout.
+ * d_hess: EXO_LAYOUT_SOA  H[length_jacobian][N][N][E];  AoS layouts  H[E][length_jacobian][N][N]  (one N x N matrix per row of
+ * the task-space Jacobian, as exotica::Hessian holds it).  Asynchronous on `stream`. */
+int exo_problem_hessian_batch(exo_problem* problem, const double* d_x, const double* d_jac, int64_t n_evals, int32_t T, int32_t layout,
+                              double* d_hess, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

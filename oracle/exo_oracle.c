@@ -1459,3 +1459,105 @@ double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_f
     free(yd);
     return total;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Task-map Hessians                                                    */
+/* ------------------------------------------------------------------------------------------- */
+/* KinematicTree::ComputeH (kinematic_tree.cpp:947-978): hess[6][N][N] (row-major N x N each) from a 6 x N column-major
+ * Jacobian; Twist * Twist with a zero linear part on the left: (rot x vel, rot x rot). */
+static void compute_h(const double* kj, int N, double* hess)
+{
+    int i, j, k;
+    memset(hess, 0, (size_t)6 * N * N * sizeof(double));
+    for (i = 0; i < N; ++i)
+    {
+        const double* wi = kj + 6 * i + 3;
+        for (j = i; j < N; ++j)
+        {
+            const double* vj = kj + 6 * j;
+            const double* wj = kj + 6 * j + 3;
+            double Hij[6];
+            vec_cross(wi, vj, Hij);
+            vec_cross(wi, wj, Hij + 3);
+            for (k = 0; k < 3; ++k)
+            {
+                hess[(size_t)k * N * N + (size_t)i * N + j] = Hij[k];
+                hess[(size_t)k * N * N + (size_t)j * N + i] = Hij[k];
+            }
+            if (i != j)
+                for (k = 3; k < 6; ++k) hess[(size_t)k * N * N + (size_t)j * N + i] = Hij[k];
+        }
+    }
+}
+
+/* Problem-level Hessian of one configuration: hess[length_jacobian][N][N].  Runs exo_oracle_problem_update first. */
+int exo_oracle_problem_hessian(exo_oracle* o, const double* x, double* hess)
+{
+    const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
+    const size_t NN = (size_t)N * N;
+    double* phi = (double*)malloc((size_t)(lp > 0 ? lp : 1) * sizeof(double));
+    double* jac = (double*)malloc((size_t)(lj > 0 ? lj : 1) * N * sizeof(double));
+    double* fh = (double*)malloc(6 * NN * sizeof(double));
+    int k, f, r, i, j;
+    exo_oracle_problem_update(o, x, phi, jac);
+    memset(hess, 0, (size_t)lj * NN * sizeof(double));
+    for (k = 0; k < o->n_maps; ++k)
+    {
+        const taskmap_t* m = &o->maps[k];
+        double* hm = hess + (size_t)m->start_jacobian * NN;
+        if (!m->is_used || m->kind == EXO_ORC_MAP_JOINT_POSE) continue; /* zero */
+        if (m->kind == EXO_ORC_MAP_JOINT_LIMIT || m->kind == EXO_ORC_MAP_SPHERE_COLLISION)
+        {
+            /* TaskMap::Update(q, phi, J, H) base class (task_map.cpp:99-108): hessian(i) = J_row^T J_row */
+            for (r = 0; r < m->length_jacobian; ++r)
+                for (i = 0; i < N; ++i)
+                    for (j = 0; j < N; ++j)
+                        hm[(size_t)r * NN + (size_t)i * N + j] = jac[(size_t)i * lj + m->start_jacobian + r] * jac[(size_t)j * lj + m->start_jacobian + r];
+            continue;
+        }
+        for (f = 0; f < m->n_frames; ++f)
+        {
+            const kframe_t* fr = &o->fr[m->frame_start + f];
+            const double* kj = o->jac + (size_t)(m->frame_start + f) * 6 * N;
+            compute_h(kj, N, fh);
+            switch (m->kind)
+            {
+                case EXO_ORC_MAP_EFF_FRAME: /* eff_frame.cpp:75-90 */
+                    memcpy(hm + (size_t)(6 * f) * NN, fh, 6 * NN * sizeof(double));
+                    break;
+                case EXO_ORC_MAP_EFF_POSITION: /* eff_position.cpp:57-70 */
+                    memcpy(hm + (size_t)(3 * f) * NN, fh, 3 * NN * sizeof(double));
+                    break;
+                case EXO_ORC_MAP_EFF_POSITION_XY: /* eff_position_xy.cpp:59-75 */
+                    memcpy(hm + (size_t)(2 * f) * NN, fh, 2 * NN * sizeof(double));
+                    break;
+                case EXO_ORC_MAP_EFF_ORIENTATION: /* eff_orientation.cpp:73-88 */
+                    memcpy(hm + (size_t)(3 * f) * NN, fh + 3 * NN, 3 * NN * sizeof(double));
+                    break;
+                case EXO_ORC_MAP_DISTANCE: /* distance.cpp:59-91 */
+                {
+                    const double* p = fr->temp_ab.p;
+                    const double nrm = vec_norm_kdl(p);
+                    const double den = pow(p[0] * p[0] + p[1] * p[1] + p[2] * p[2], (double)(3 / 2)); /* integer division, as written */
+                    for (i = 0; i < N; ++i)
+                        for (j = 0; j < N; ++j)
+                        {
+                            const double ni = p[0] * kj[6 * i] + p[1] * kj[6 * i + 1] + p[2] * kj[6 * i + 2];
+                            const double nj = p[0] * kj[6 * j] + p[1] * kj[6 * j + 1] + p[2] * kj[6 * j + 2];
+                            const double part1 = -(ni * nj) / den;
+                            const double part2 = ((p[0] * fh[(size_t)i * N + j] + p[1] * fh[NN + (size_t)i * N + j] + p[2] * fh[2 * NN + (size_t)i * N + j]) +
+                                                  (kj[6 * i] * kj[6 * j] + kj[6 * i + 1] * kj[6 * j + 1] + kj[6 * i + 2] * kj[6 * j + 2])) / nrm;
+                            hm[(size_t)f * NN + (size_t)i * N + j] = part1 + part2;
+                        }
+                    break;
+                }
+                default:
+                    break;
+            }
+        }
+    }
+    free(phi);
+    free(jac);
+    free(fh);
+    return 0;
+}

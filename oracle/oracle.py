@@ -58,6 +58,7 @@ def lib():
         L.exo_oracle_problem_update.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.exo_oracle_problem_update_batch.argtypes = [ctypes.c_void_p, _dp, ctypes.c_long, ctypes.c_int, _dp, ctypes.c_int,
                                                       _dp, _dp, ctypes.c_int]
+        L.exo_oracle_problem_hessian.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.exo_oracle_get_rotation.argtypes = [_dp, ctypes.c_int, _dp]
         L.exo_oracle_problem_ydiff.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.exo_oracle_trajectory_cost.restype = ctypes.c_double
@@ -248,6 +249,13 @@ class Oracle(object):
         lib().exo_oracle_problem_update_batch(self.h, _d(X), E, T, gp, n_gen, _d(phi), _d(jac), n_threads)
         return phi, np.ascontiguousarray(jac.transpose(0, 2, 1))
 
+
+    def problem_hessian(self, x):
+        """exotica::Hessian of the problem's task maps at x: [length_jacobian][N][N]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros((self.length_jacobian, self.n, self.n))
+        lib().exo_oracle_problem_hessian(self.h, _d(x), _d(out))
+        return out
 
     # ---- task cost (SURVEY.md section 8 f1) ---------------------------------------------------------
     def zero_goal(self):

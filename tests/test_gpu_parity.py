@@ -527,3 +527,55 @@ def test_full_size_cfg5_sphere_collision(oracle_lib):
     sel = np.random.default_rng(7).integers(0, B * T, 1024)
     phi_ref, jac_ref = orc.problem_update_batch(X[sel])
     assert max_abs_err(phi[sel], phi_ref) <= 1e-9 and max_abs_err(jac[sel], jac_ref) <= 1e-9  # sums of 1024 terms
+
+
+# ---- task-map Hessians ---------------------------------------------------------------------------
+def _gpu_hessian(prob, X, layout=_capi.LAYOUT_SOA, T=1):
+    E, N = X.shape
+    LP, LJ = prob.length_phi, prob.length_jacobian
+    dx, dphi, djac, dh = (_capi.DeviceBuffer(max(n, 1)) for n in (E * N, E * LP, E * LJ * N, E * LJ * N * N))
+    dh.fill_bytes(0xFF)
+    dx.upload(X.T if layout == _capi.LAYOUT_SOA else X)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T, layout=layout)
+    prob.hessian_batch_device(dx.ptr, djac.ptr, E, dh.ptr, T=T, layout=layout)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    if layout == _capi.LAYOUT_SOA:
+        return np.ascontiguousarray(dh.download((LJ, N, N, E)).transpose(3, 0, 1, 2))
+    return dh.download((E, LJ, N, N))
+
+
+@pytest.mark.parametrize("layout", [_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR])
+def test_task_map_hessians(oracle_lib, layout):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0.1, 0, 0.05]}, {"Link": "lwr_arm_5_link", "Base": "lwr_arm_2_link"}]},
+            {"type": "JointLimit", "SafePercentage": 0.2},
+            {"type": "EffOrientation", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_6_link"}]},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link", "BaseOffset": [0.3, 0.2, 0.4]}]},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "lwr_arm_4_link"}]},
+            {"type": "JointPose", "JointMap": [0, 3]},
+            {"type": "EffPosition", "used": False, "EndEffector": [{"Link": "lwr_arm_3_link"}]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    X = random_states(orc, 300, seed=201, spread=0.1)
+    H = _gpu_hessian(prob, X, layout=layout)
+    for e in range(0, 300, 7):
+        ref = orc.problem_hessian(X[e])
+        assert np.max(np.abs(H[e] - ref)) <= 1e-10
+    # ComputeH quirk: angular rows of EffFrame are strictly lower triangular (kinematic_tree.cpp:969-974)
+    assert not np.triu(H[:, 3:6]).any() and np.abs(np.tril(H[:, 3:6], -1)).max() > 0.1
+
+
+def test_hessian_matches_finite_differences_of_the_jacobian(oracle_lib):
+    # the linear rows of ComputeH are the true second derivative of the position: check against central differences of J
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0.05, 0.02, 0.1]}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    x = random_states(orc, 1, seed=202)[0]
+    h = 1e-6
+    X = np.array([x] + [x + h * np.eye(7)[i] for i in range(7)] + [x - h * np.eye(7)[i] for i in range(7)])
+    phi, jac = run_gpu(prob, X)
+    H = _gpu_hessian(prob, X[:1])[0]
+    fd = np.stack([(jac[1 + i] - jac[8 + i]) / (2 * h) for i in range(7)], axis=1)  # [row][i][col j] = d J[row][j] / d q_i
+    assert np.max(np.abs(H - fd)) < 1e-8
