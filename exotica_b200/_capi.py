@@ -40,6 +40,11 @@ class CostDesc(ctypes.Structure):
     _fields_ = [("T", ctypes.c_int32), ("T_goal", ctypes.c_int32), ("rho", _dp), ("goal", _dp), ("ct", ctypes.c_double), ("W", _dp)]
 
 
+class IkParams(ctypes.Structure):
+    _fields_ = [("max_iterations", ctypes.c_int32), ("tolerance", ctypes.c_double), ("regularization_rate", ctypes.c_double),
+                ("maximum_regularization", ctypes.c_double), ("gradient_tolerance", ctypes.c_double), ("step_tolerance", ctypes.c_double)]
+
+
 class ExoticaError(RuntimeError):
     """Mirrors exotica::Exception (exotica_core/include/exotica_core/tools/exception.h:36-47)."""
 
@@ -86,6 +91,7 @@ SYMBOLS = [
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
+    ("exo_problem_ik_solve_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(IkParams), _vp, _vp, _vp, _vp]),
     ("exo_problem_hessian_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_trajectory_reduce", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
@@ -357,6 +363,29 @@ class Problem(object):
 
     def hessian_batch_device(self, d_x, d_jac, n_evals, d_hess, T=1, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_hessian_batch(self.h, d_x, d_jac, int(n_evals), int(T), int(layout), d_hess, stream))
+
+    def ik_solve_batch(self, Q0, max_iterations=100, tolerance=1e-5, regularization_rate=1e-9, maximum_regularization=1e9,
+                       gradient_tolerance=1e-9, step_tolerance=1e-5):
+        """Multi-start IK: Q0[E][N] start states -> (Q[E][N], cost[E], iterations[E], termination[E]).  Needs set_cost(T=1)."""
+        Q0 = np.ascontiguousarray(Q0, dtype=np.float64)
+        E, N = Q0.shape
+        dq, dc = DeviceBuffer(E * N), DeviceBuffer(E)
+        di, dt = DeviceBuffer((E + 1) // 2 + 1), DeviceBuffer((E + 1) // 2 + 1)  # int32 arrays in double-sized storage
+        dq.upload(Q0.T)
+        prm = IkParams(int(max_iterations), float(tolerance), float(regularization_rate), float(maximum_regularization),
+                       float(gradient_tolerance), float(step_tolerance))
+        check(lib().exo_problem_ik_solve_batch(self.h, dq.ptr, E, ctypes.byref(prm), dc.ptr, di.ptr, dt.ptr, None))
+        check(lib().exo_device_synchronize())
+        Q = np.ascontiguousarray(dq.download((N, E)).T)
+        cost = dc.download((E,))
+        it = np.zeros(E, dtype=np.int32)
+        tm = np.zeros(E, dtype=np.int32)
+        check(lib().exo_memcpy_d2h(it.ctypes.data, di.ptr, E * 4, None))
+        check(lib().exo_memcpy_d2h(tm.ctypes.data, dt.ptr, E * 4, None))
+        check(lib().exo_stream_synchronize(None))
+        for b in (dq, dc, di, dt):
+            b.free()
+        return Q, cost, it, tm
 
     def set_min_distance_output(self, d_ptr):
         check(lib().exo_problem_set_min_distance_output(self.h, d_ptr))

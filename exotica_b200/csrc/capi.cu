@@ -61,6 +61,12 @@ struct exo_problem
     std::vector<int> shadow_frame_start;  // per map
     double *d_shadow_phi = nullptr, *d_shadow_jac = nullptr;
     int64_t shadow_capacity = 0;
+    // batched IK workspace (exo_problem_ik_solve_batch)
+    double* d_ik = nullptr;     // doubles: phi, jac, q_trial, qd, err_prev, stop, lambda
+    int32_t* d_ik_i = nullptr;  // ints: active, ls_done, n_active
+    int64_t ik_capacity = 0;
+    std::vector<double> cost_rho_t0;  // rho of every map at t = 0 (IK uses end-pose problems)
+    std::vector<double> cost_W;
     // auxiliary outputs and the task cost (rows e / f1)
     double* d_min_dist = nullptr;  // caller-owned, [n_evals] (exo_problem_set_min_distance_output)
     bool cost_set = false;
@@ -319,6 +325,8 @@ int exo_problem_destroy(exo_problem* p)
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
     if (p->d_image) cudaFree(p->d_image);
     if (p->d_generated) cudaFree(p->d_generated);
+    if (p->d_ik) cudaFree(p->d_ik);
+    if (p->d_ik_i) cudaFree(p->d_ik_i);
     if (p->shadow) exo_problem_destroy(p->shadow);
     if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
     if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
@@ -771,6 +779,7 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
         CostMapP& cm = c.map[k];
         cm.kind = m.kind;
         cm.start = m.start;
+        cm.start_jacobian = m.start_jacobian;
         cm.length = m.length;
         cm.n_frames = m.n_frames;
         cm.rot_type = m.rot_type;
@@ -810,6 +819,9 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
     if (rc == EXO_OK) rc = upload(&p->d_goal_rot, goal_rot.data(), goal_rot.size());
     if (rc == EXO_OK) rc = upload(&p->d_W, d->W, d->W ? (size_t)N : 0);
     if (rc != EXO_OK) return rc;
+    p->cost_rho_t0.assign(d->rho, d->rho + n_maps);
+    p->cost_W.clear();
+    if (d->W) p->cost_W.assign(d->W, d->W + N);
     c.rho = p->d_rho;
     c.goal = p->d_goal;
     c.goal_rot = p->d_goal_rot;
@@ -1000,6 +1012,101 @@ int exo_problem_hessian_batch(exo_problem* p, const double* d_x, const double* d
     p->launches++;
     p->last_kernel = "exo_hessian_kernel";
     return EXO_OK;
+}
+
+// ---- batched IK -----------------------------------------------------------------------------------------------------------------
+int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, const exo_ik_params* prm, double* d_cost, int32_t* d_iterations,
+                               int32_t* d_termination, void* stream_)
+{
+    if (!p || !prm) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (p->cost.T != 1) return fail(EXO_ERR_INVALID, "This IKSolver can't solve time-indexed problems (ik_solver.cpp:38-41)");
+    if (n_evals < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_evals == 0) return EXO_OK;
+    if (!d_q || !d_cost || !d_iterations || !d_termination) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (prm->max_iterations < 1) return fail(EXO_ERR_INVALID, "max_iterations must be >= 1");
+    const int N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
+    if (LJ > IK_MAXLJ || N > CH_MAXN) return fail(EXO_ERR_UNSUPPORTED, "batched IK supports up to 16 task-space rows and 16 joints");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t E = n_evals;
+    if (p->ik_capacity < E)
+    {
+        if (p->d_ik) cudaFree(p->d_ik);
+        if (p->d_ik_i) cudaFree(p->d_ik_i);
+        p->d_ik = nullptr;
+        p->d_ik_i = nullptr;
+        p->ik_capacity = 0;
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 3) * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik_i, ((size_t)2 * E + 4) * sizeof(int32_t)));
+        p->ik_capacity = E;
+    }
+    double* w = p->d_ik;
+    double* d_phi = w; w += (size_t)E * LP;
+    double* d_jac = w; w += (size_t)E * LJ * N;
+    IkParams K;
+    memset(&K, 0, sizeof(K));
+    K.n_evals = E;
+    K.n_ctrl = N;
+    K.length_jac = LJ;
+    K.tolerance = prm->tolerance;
+    K.step_tolerance = prm->step_tolerance;
+    K.gradient_tolerance = prm->gradient_tolerance;
+    K.regmax = prm->maximum_regularization;
+    K.jac = d_jac;
+    K.q = d_q;
+    K.q_trial = w; w += (size_t)E * N;
+    K.qd = w; w += (size_t)E * N;
+    K.err_prev = w; w += E;
+    K.stop = w; w += E;
+    K.lambda = w; w += E;
+    K.cost = d_cost;
+    K.active = p->d_ik_i;
+    K.ls_done = p->d_ik_i + E;
+    K.n_active = p->d_ik_i + 2 * E;
+    K.iterations = d_iterations;
+    K.termination = d_termination;
+    for (size_t i = 0; i < p->maps.size(); ++i)
+        for (int r = 0; r < p->maps[i].length_jacobian; ++r) K.row_rho[p->maps[i].start_jacobian + r] = p->cost_rho_t0[i];
+    for (int c = 0; c < N; ++c) K.w_inv[c] = p->cost_W.empty() ? 1.0 : 1.0 / p->cost_W[c];  // W_inv_ = prob_->W.inverse() (ik_solver.cpp:45)
+    // cost parameters bound to the workspace (SoA)
+    CostParams C = p->cost;
+    C.x = d_q;
+    C.phi = d_phi;
+    C.n_traj = E;
+    C.x_se = 1; C.x_sk = E; C.phi_se = 1; C.phi_sk = E;
+    C.W = nullptr;  // end-pose problems have no transition cost
+    CUDA_TRY(launch_ik_init(K, prm->regularization_rate, stream));
+    int rc = EXO_OK;
+    for (int it = 0; it < prm->max_iterations; ++it)
+    {
+        rc = launch(p, d_q, E, E, 1, EXO_LAYOUT_SOA, d_phi, d_jac, stream, false);  // prob_->Update(q_)
+        if (rc != EXO_OK) return rc;
+        CUDA_TRY(launch_ik_step(K, C, stream));
+        for (int ai = 0; ai < 10; ++ai)
+        {
+            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+            CUDA_TRY(launch_ik_trial(K, alpha, stream));
+            rc = launch(p, K.q_trial, E, E, 1, EXO_LAYOUT_SOA, d_phi, nullptr, stream, false);  // prob_->Update(q_tmp): FK only
+            if (rc != EXO_OK) return rc;
+            CUDA_TRY(launch_ik_accept(K, C, alpha, stream));
+        }
+        const bool last = it + 1 == prm->max_iterations;
+        const bool poll = last || (it % 4 == 3);
+        if (poll) CUDA_TRY(cudaMemsetAsync(K.n_active, 0, sizeof(int32_t), stream));
+        CUDA_TRY(launch_ik_finish(K, last ? 1 : 0, stream));
+        if (poll && !last)
+        {
+            int32_t n_active = 0;
+            CUDA_TRY(cudaMemcpyAsync(&n_active, K.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (n_active == 0) break;
+        }
+    }
+    // cost at the returned states
+    rc = launch(p, d_q, E, E, 1, EXO_LAYOUT_SOA, d_phi, nullptr, stream, false);
+    if (rc != EXO_OK) return rc;
+    return exo_problem_cost_batch(p, d_q, d_phi, E, EXO_LAYOUT_SOA, d_cost, nullptr, stream_);
 }
 
 }  // extern "C"

@@ -113,7 +113,7 @@ cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream)
 constexpr int COST_MAXMAPS = 16;
 struct CostMapP
 {
-    int32_t kind, start, length, n_frames, rot_type, stride, pad0, pad1;  // stride = 3 + rotation length (EffFrame)
+    int32_t kind, start, length, n_frames, rot_type, stride, start_jacobian, pad1;  // stride: Phi entries per frame (EffFrame, EffOrientation)
 };
 struct CostParams
 {
@@ -135,6 +135,44 @@ cudaError_t launch_cost(const CostParams& P, cudaStream_t stream);
 // op 0: min, 1: sum over t in [t_first, T) of in[b * T + t]
 cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
 void host_get_rotation(const double* data, int type, double* out9);
+
+// ---- batched IK step (ik_kernel.cu) ----
+constexpr int IK_MAXLJ = 16;  // rows of the task-space Jacobian
+enum
+{
+    // exotica::TerminationCriterion (exotica_core/include/exotica_core/planning_problem.h:49-62)
+    IK_TERM_ITERATION_LIMIT = 0,
+    IK_TERM_STEP_TOLERANCE = 2,
+    IK_TERM_FUNCTION_TOLERANCE = 3,
+    IK_TERM_GRADIENT_TOLERANCE = 4,
+    IK_TERM_DIVERGENCE = 5
+};
+struct IkParams
+{
+    int64_t n_evals;
+    int32_t n_ctrl, length_jac;
+    double tolerance, step_tolerance, gradient_tolerance, regmax;
+    const double* jac;    // [LJ][N][E] of the current states
+    double* q;            // [N][E] current states (in / out)
+    double* q_trial;      // [N][E]
+    double* qd;           // [N][E]
+    double* cost;         // [E] error_
+    double* err_prev;     // [E]
+    double* stop;         // [E] |cJ|_F
+    double* lambda;       // [E]
+    int32_t* active;      // [E]
+    int32_t* ls_done;     // [E]
+    int32_t* iterations;  // [E]
+    int32_t* termination; // [E]
+    int32_t* n_active;    // [1]
+    double row_rho[IK_MAXLJ];  // rho of the map that owns each Jacobian row (S = diag)
+    double w_inv[CH_MAXN];     // 1 / W[c]
+};
+cudaError_t launch_ik_init(const IkParams& K, double lambda0, cudaStream_t s);
+cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);
+cudaError_t launch_ik_trial(const IkParams& K, double alpha, cudaStream_t s);
+cudaError_t launch_ik_accept(const IkParams& K, const CostParams& C, double alpha, cudaStream_t s);
+cudaError_t launch_ik_finish(const IkParams& K, int last_iteration, cudaStream_t s);
 
 // ---- task-map Hessians (cost_kernel.cu) ----
 struct HessMapP

@@ -264,6 +264,27 @@ int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t
 int exo_problem_hessian_batch(exo_problem* problem, const double* d_x, const double* d_jac, int64_t n_evals, int32_t T, int32_t layout,
                               double* d_hess, void* stream);
 
+/* ---- batched IK --------------------------------------------------------------------------------
+ * exo_problem_ik_solve_batch <- IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) on an
+ *     UnconstrainedEndPoseProblem, for n_evals independent start states at once (multi-start IK): damped weighted
+ *     pseudo-inverse step (Cholesky of S J W^-1 J^T S + lambda I, lambda x10 on failure), backtracking line search over
+ *     alpha = linspace(1, 0.1, 10), the reference's termination tests.  Parameters: init/ik_solver.in + MaxIterations of
+ *     exotica_core/init/motion_solver.in.  The MaxStep mode (MaxIterations == 1) is not supported.
+ * Requires exo_problem_set_cost (T = 1: rho, goal, W).  d_q: SoA [N][n_evals] start states in, solutions out.  d_cost[n_evals]:
+ * cost at the returned state; d_iterations[n_evals]; d_termination[n_evals]: exotica::TerminationCriterion values
+ * (planning_problem.h:49-62: 0 IterationLimit, 2 StepTolerance, 3 FunctionTolerance, 4 GradientTolerance, 5 Divergence). */
+typedef struct
+{
+    int32_t max_iterations;          /* MaxIterations = 100 */
+    double tolerance;                /* Tolerance = 1e-5 */
+    double regularization_rate;      /* RegularizationRate = 1e-9 */
+    double maximum_regularization;   /* MaximumRegularization = 1e9 */
+    double gradient_tolerance;       /* GradientToleranceConvergenceThreshold = 1e-9 */
+    double step_tolerance;           /* StepToleranceConvergenceThreshold = 1e-5 */
+} exo_ik_params;
+int exo_problem_ik_solve_batch(exo_problem* problem, double* d_q, int64_t n_evals, const exo_ik_params* params, double* d_cost,
+                               int32_t* d_iterations, int32_t* d_termination, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

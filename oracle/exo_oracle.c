@@ -1561,3 +1561,157 @@ int exo_oracle_problem_hessian(exo_oracle* o, const double* x, double* hess)
     free(fh);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* IKSolver::Solve                                                      */
+/* ------------------------------------------------------------------------------------------- */
+/* Restates exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240 on an UnconstrainedEndPoseProblem whose task maps are
+ * the oracle's maps (rho[n_maps]: S = diag(rho) per Jacobian row; rows of maps with rho 0 do not contribute).  q: start state
+ * in, solution out.  Returns the TerminationCriterion value (planning_problem.h:49-62). */
+static double ik_cost_at(exo_oracle* o, const double* q, const double* rho, const double* goal, double* phi, double* jac, double* yd)
+{
+    double c = 0.0;
+    int k, i;
+    exo_oracle_problem_update(o, q, phi, jac);
+    exo_oracle_problem_ydiff(o, phi, goal, yd);
+    for (k = 0; k < o->n_maps; ++k)
+    {
+        const taskmap_t* m = &o->maps[k];
+        for (i = 0; i < m->length_jacobian; ++i) c += yd[m->start_jacobian + i] * rho[k] * yd[m->start_jacobian + i];
+    }
+    return c;
+}
+
+int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
+                        double lambda, double regmax, double gradient_tolerance, double step_tolerance, double* cost_out, int* iterations_out)
+{
+    const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
+    double* phi = (double*)malloc((size_t)(lp + 1) * sizeof(double));
+    double* jac = (double*)malloc((size_t)(lj + 1) * N * sizeof(double));
+    double* yd = (double*)malloc((size_t)(lj + 1) * sizeof(double));
+    double* cj = (double*)malloc((size_t)(lj + 1) * N * sizeof(double)); /* row-major lj x N */
+    double* A = (double*)malloc((size_t)(lj + 1) * (lj + 1) * sizeof(double));
+    double* L = (double*)malloc((size_t)(lj + 1) * (lj + 1) * sizeof(double));
+    double* z = (double*)malloc((size_t)(lj + 1) * sizeof(double));
+    double* qd = (double*)malloc((size_t)N * sizeof(double));
+    double* qt = (double*)malloc((size_t)N * sizeof(double));
+    double* srow = (double*)malloc((size_t)(lj + 1) * sizeof(double));
+    int term = 0 /* IterationLimit */, it, k, i, j, r, c, ai;
+    double error = 0.0, error_prev;
+    for (k = 0; k < o->n_maps; ++k)
+        for (i = 0; i < o->maps[k].length_jacobian; ++i) srow[o->maps[k].start_jacobian + i] = rho[k];
+    for (it = 0; it < max_iterations; ++it)
+    {
+        double stop2 = 0.0, step = 0.0;
+        int ok = 0, diverged = 0;
+        error = ik_cost_at(o, q, rho, goal, phi, jac, yd);
+        error_prev = error;
+        if (error < tolerance)
+        {
+            term = 3; /* FunctionTolerance */
+            break;
+        }
+        for (r = 0; r < lj; ++r)
+        {
+            yd[r] *= srow[r];
+            for (c = 0; c < N; ++c)
+            {
+                cj[(size_t)r * N + c] = srow[r] * jac[(size_t)c * lj + r]; /* jac is column-major lj x N */
+                stop2 += cj[(size_t)r * N + c] * cj[(size_t)r * N + c];
+            }
+        }
+        for (r = 0; r < lj; ++r)
+            for (j = 0; j < lj; ++j)
+            {
+                double acc = 0.0;
+                for (c = 0; c < N; ++c) acc += cj[(size_t)r * N + c] * (W ? 1.0 / W[c] : 1.0) * cj[(size_t)j * N + c];
+                A[(size_t)r * lj + j] = acc;
+            }
+        while (!ok)
+        {
+            ok = 1;
+            for (j = 0; j < lj && ok; ++j)
+            {
+                double d = A[(size_t)j * lj + j] + lambda;
+                for (k = 0; k < j; ++k) d -= L[(size_t)j * lj + k] * L[(size_t)j * lj + k];
+                if (!(d > 0.0))
+                {
+                    ok = 0;
+                    break;
+                }
+                L[(size_t)j * lj + j] = sqrt(d);
+                for (i = j + 1; i < lj; ++i)
+                {
+                    double v = A[(size_t)i * lj + j];
+                    for (k = 0; k < j; ++k) v -= L[(size_t)i * lj + k] * L[(size_t)j * lj + k];
+                    L[(size_t)i * lj + j] = v / L[(size_t)j * lj + j];
+                }
+            }
+            if (!ok)
+            {
+                lambda *= 10.0;
+                if (lambda > regmax)
+                {
+                    lambda = regmax;
+                    diverged = 1;
+                    break;
+                }
+            }
+        }
+        if (diverged)
+        {
+            term = 5; /* Divergence */
+            break;
+        }
+        for (i = 0; i < lj; ++i)
+        {
+            double v = yd[i];
+            for (k = 0; k < i; ++k) v -= L[(size_t)i * lj + k] * z[k];
+            z[i] = v / L[(size_t)i * lj + i];
+        }
+        for (i = lj - 1; i >= 0; --i)
+        {
+            double v = z[i];
+            for (k = i + 1; k < lj; ++k) v -= L[(size_t)k * lj + i] * z[k];
+            z[i] = v / L[(size_t)i * lj + i];
+        }
+        for (c = 0; c < N; ++c)
+        {
+            double acc = 0.0;
+            for (r = 0; r < lj; ++r) acc += cj[(size_t)r * N + c] * z[r];
+            qd[c] = (W ? 1.0 / W[c] : 1.0) * acc;
+        }
+        for (ai = 0; ai < 10; ++ai)
+        {
+            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0); /* LinSpaced(10, 1.0, 0.1) */
+            for (c = 0; c < N; ++c) qt[c] = q[c] - alpha * qd[c];
+            error = ik_cost_at(o, qt, rho, goal, phi, jac, z /* scratch */);
+            if (error < error_prev)
+            {
+                for (c = 0; c < N; ++c)
+                {
+                    q[c] = qt[c];
+                    qd[c] *= alpha;
+                }
+                break;
+            }
+        }
+        for (c = 0; c < N; ++c) step += qd[c] * qd[c];
+        if (step < step_tolerance)
+        {
+            term = 2; /* StepTolerance */
+            ++it;
+            break;
+        }
+        if (sqrt(stop2) < gradient_tolerance)
+        {
+            term = 4; /* GradientTolerance */
+            ++it;
+            break;
+        }
+    }
+    if (cost_out) *cost_out = ik_cost_at(o, q, rho, goal, phi, jac, yd);
+    if (iterations_out) *iterations_out = it;
+    free(phi); free(jac); free(yd); free(cj); free(A); free(L); free(z); free(qd); free(qt); free(srow);
+    return term;
+}

@@ -134,6 +134,10 @@ double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_f
  * overloads + the base-class fallback (task_map.cpp:99-108).  hess[length_jacobian][N][N]. */
 int exo_oracle_problem_hessian(exo_oracle* o, const double* x, double* hess);
 
+/* ---- IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) ---- */
+int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
+                        double lambda, double regmax, double gradient_tolerance, double step_tolerance, double* cost_out, int* iterations_out);
+
 #ifdef __cplusplus
 }
 #endif

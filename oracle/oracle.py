@@ -59,6 +59,8 @@ def lib():
         L.exo_oracle_problem_update_batch.argtypes = [ctypes.c_void_p, _dp, ctypes.c_long, ctypes.c_int, _dp, ctypes.c_int,
                                                       _dp, _dp, ctypes.c_int]
         L.exo_oracle_problem_hessian.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.exo_oracle_ik_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_double, _dp, _ip]
         L.exo_oracle_get_rotation.argtypes = [_dp, ctypes.c_int, _dp]
         L.exo_oracle_problem_ydiff.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.exo_oracle_trajectory_cost.restype = ctypes.c_double
@@ -249,6 +251,20 @@ class Oracle(object):
         lib().exo_oracle_problem_update_batch(self.h, _d(X), E, T, gp, n_gen, _d(phi), _d(jac), n_threads)
         return phi, np.ascontiguousarray(jac.transpose(0, 2, 1))
 
+
+    def ik_solve(self, q0, rho, goal=None, W=None, max_iterations=100, tolerance=1e-5, regularization_rate=1e-9, maximum_regularization=1e9,
+                 gradient_tolerance=1e-9, step_tolerance=1e-5):
+        """IKSolver::Solve from q0: returns (q, cost, iterations, termination)."""
+        q = np.ascontiguousarray(q0, dtype=np.float64).copy()
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        goal = np.ascontiguousarray(self.zero_goal() if goal is None else goal, dtype=np.float64)
+        Wp = _d(np.ascontiguousarray(W, dtype=np.float64)) if W is not None else None
+        cost = ctypes.c_double(0)
+        iters = ctypes.c_int(0)
+        term = lib().exo_oracle_ik_solve(self.h, _d(q), _d(rho), _d(goal), Wp, int(max_iterations), float(tolerance), float(regularization_rate),
+                                         float(maximum_regularization), float(gradient_tolerance), float(step_tolerance),
+                                         ctypes.byref(cost), ctypes.byref(iters))
+        return q, cost.value, iters.value, term
 
     def problem_hessian(self, x):
         """exotica::Hessian of the problem's task maps at x: [length_jacobian][N][N]."""

@@ -579,3 +579,48 @@ def test_hessian_matches_finite_differences_of_the_jacobian(oracle_lib):
     H = _gpu_hessian(prob, X[:1])[0]
     fd = np.stack([(jac[1 + i] - jac[8 + i]) / (2 * h) for i in range(7)], axis=1)  # [row][i][col j] = d J[row][j] / d q_i
     assert np.max(np.abs(H - fd)) < 1e-8
+
+
+# ---- batched IK -------------------------------------------------------------------------------------
+def test_batched_ik_matches_the_reference_solver(oracle_lib):
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    rng = np.random.default_rng(301)
+    q_goal = rng.uniform(orc.lower, orc.upper) * 0.6
+    goal = orc.zero_goal()
+    goal[:6] = orc.problem_update(q_goal)[0][:6]
+    rho = [1.0, 0.0]  # the JointLimit rows are listed but carry no weight: they must not change the solve
+    W = np.linspace(1.0, 2.0, 7)
+    prob.set_cost(rho, T=1, goal=goal, W=W)
+    E = 96
+    Q0 = np.clip(q_goal + rng.normal(0, 0.5, size=(E, 7)), orc.lower, orc.upper)
+    Q, cost, iters, term = prob.ik_solve_batch(Q0, max_iterations=60)
+    n_same = 0
+    for e in range(E):
+        q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], rho, goal=goal, W=W, max_iterations=60)
+        # the returned cost is the cost of the returned state
+        assert abs(cost[e] - orc.trajectory_cost(Q[e:e + 1], rho, goal=goal)[0]) <= 1e-9 * max(1.0, cost[e])
+        if t_ref == 3:  # the reference converged (FunctionTolerance): same path, same answer
+            assert term[e] == 3 and iters[e] == it_ref
+            assert np.max(np.abs(Q[e] - q_ref)) <= 1e-6 and abs(cost[e] - c_ref) <= 1e-9
+            n_same += 1
+        else:
+            assert term[e] == t_ref or abs(cost[e] - c_ref) <= 1e-3 * max(1.0, c_ref)
+    assert n_same >= E // 2 and (cost[term == 3] < 1e-5).all()
+
+
+def test_batched_ik_position_only_on_the_three_dof_robot(oracle_lib):
+    orc = _oracle(oracle_lib, "test_robot", "arm")
+    maps = [{"type": "EffPosition", "EndEffector": [{"Link": "endeff"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    goal = orc.problem_update(np.array([0.2, -0.1, 0.3]))[0]
+    prob.set_cost([10.0], T=1, goal=goal)
+    Q0 = random_states(orc, 257, seed=302)
+    Q, cost, iters, term = prob.ik_solve_batch(Q0, tolerance=1e-10)
+    for e in range(0, 257, 8):
+        q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], [10.0], goal=goal, tolerance=1e-10)
+        assert term[e] == t_ref and iters[e] == it_ref and np.max(np.abs(Q[e] - q_ref)) <= 1e-7
+    assert np.isin(term, (0, 2, 3)).all() and np.median(cost) < 1e-6  # step / function tolerance (or the iteration limit in a local minimum)
