@@ -463,6 +463,17 @@ int exo_host_problem_cost_batch_device(exo_host_problem* p, const double* d_x, c
     HOST_TRY(p->problem->CostBatchDevice(d_x, d_phi, n_traj, layout, d_cost, d_cost_eval, stream))
 }
 
+int exo_host_problem_ik_solve_batch(exo_host_problem* p, const double* q0, int64_t n, const exo_ik_params* params, double* solutions, double* cost,
+                                    int32_t* iterations, int32_t* termination)
+{
+    HOST_TRY(p->problem->IkSolveBatch(q0, n, *params, solutions, cost, iterations, termination))
+}
+
+int exo_host_problem_hessian_batch(exo_host_problem* p, const double* x, int64_t n_evals, double* hess)
+{
+    HOST_TRY(p->problem->HessianBatch(x, n_evals, hess))
+}
+
 int exo_host_problem_last_kernel_ms(exo_host_problem* p, float* ms)
 {
     HOST_TRY(*ms = p->problem->LastKernelMs())

@@ -632,6 +632,56 @@ void PlanningProblem::CostBatch(const double* x, int64_t n_trajectories, double*
     number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
 }
 
+namespace
+{
+struct DeviceMem  // RAII over the C-ABI allocator
+{
+    void* p = nullptr;
+    explicit DeviceMem(size_t bytes) { CheckRc(exo_device_alloc(&p, bytes)); }
+    ~DeviceMem() { exo_device_free(p); }
+    DeviceMem(const DeviceMem&) = delete;
+    DeviceMem& operator=(const DeviceMem&) = delete;
+};
+}  // namespace
+
+void PlanningProblem::IkSolveBatch(const double* q0, int64_t n, const exo_ik_params& params, double* solutions, double* cost, int32_t* iterations,
+                                   int32_t* termination)
+{
+    if (GetT() != 1) ThrowPretty("This IKSolver can't solve problem of type 'exotica::TimeIndexedProblem'!");  // ik_solver.cpp:38-41
+    if (n <= 0) return;
+    PushCost();
+    // SoA on the device: transpose on the way in and out
+    std::vector<double> soa((size_t)n * N);
+    for (int64_t e = 0; e < n; ++e)
+        for (int c = 0; c < N; ++c) soa[(size_t)c * n + e] = q0[(size_t)e * N + c];
+    DeviceMem dq((size_t)n * N * sizeof(double)), dc((size_t)n * sizeof(double)), di((size_t)n * sizeof(int32_t)), dt((size_t)n * sizeof(int32_t));
+    CheckRc(exo_memcpy_h2d(dq.p, soa.data(), soa.size() * sizeof(double), nullptr));
+    CheckRc(exo_problem_ik_solve_batch(GetBackend(), (double*)dq.p, n, &params, (double*)dc.p, (int32_t*)di.p, (int32_t*)dt.p, nullptr));
+    CheckRc(exo_memcpy_d2h(soa.data(), dq.p, soa.size() * sizeof(double), nullptr));
+    CheckRc(exo_memcpy_d2h(cost, dc.p, (size_t)n * sizeof(double), nullptr));
+    CheckRc(exo_memcpy_d2h(iterations, di.p, (size_t)n * sizeof(int32_t), nullptr));
+    CheckRc(exo_memcpy_d2h(termination, dt.p, (size_t)n * sizeof(int32_t), nullptr));
+    CheckRc(exo_stream_synchronize(nullptr));
+    for (int64_t e = 0; e < n; ++e)
+        for (int c = 0; c < N; ++c) solutions[(size_t)e * N + c] = soa[(size_t)c * n + e];
+}
+
+void PlanningProblem::HessianBatch(const double* x, int64_t n_evals, double* hess)
+{
+    if (n_evals <= 0) return;
+    const int T = GetT();
+    if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
+    exo_problem* p = GetBackend();
+    const size_t n = (size_t)n_evals;
+    DeviceMem dx(n * N * sizeof(double)), dphi(n * std::max(length_Phi, 1) * sizeof(double)), djac(n * std::max(length_jacobian, 1) * N * sizeof(double)),
+        dh(n * std::max(length_jacobian, 1) * N * N * sizeof(double));
+    CheckRc(exo_memcpy_h2d(dx.p, x, n * N * sizeof(double), nullptr));
+    CheckRc(exo_problem_update_batch(p, (const double*)dx.p, n_evals, T, EXO_LAYOUT_AOS_ROWMAJOR, (double*)dphi.p, (double*)djac.p, nullptr));
+    CheckRc(exo_problem_hessian_batch(p, (const double*)dx.p, (const double*)djac.p, n_evals, T, EXO_LAYOUT_AOS_ROWMAJOR, (double*)dh.p, nullptr));
+    CheckRc(exo_memcpy_d2h(hess, dh.p, n * length_jacobian * N * N * sizeof(double), nullptr));
+    CheckRc(exo_stream_synchronize(nullptr));
+}
+
 void PlanningProblem::CostBatchDevice(const double* d_x, const double* d_phi, int64_t n_trajectories, int layout, double* d_cost, double* d_cost_eval,
                                       void* stream)
 {
@@ -698,8 +748,12 @@ void UnconstrainedEndPoseProblem::Instantiate(const Initializer& init)
     ParseCost(init, 1);
     if (init.Has("W"))
     {
+        // unconstrained_end_pose_problem.cpp:56-66: W = I, or diag(W); IKSolver uses W^-1 (ik_solver.cpp:45)
         const std::vector<double> w = ParseVector(init.Get("W", ""));
-        if ((int)w.size() != N && w.size() != 1) ThrowPretty("W dimension mismatch! Expected " + std::to_string(N) + ", got " + std::to_string(w.size()));
+        if ((int)w.size() == N)
+            cost_W_ = w;
+        else if (!w.empty())
+            ThrowPretty("W dimension mismatch! Expected " + std::to_string(N) + ", got " + std::to_string(w.size()));
     }
     Phi.assign(length_Phi, 0.0);
     jacobian.assign((size_t)length_jacobian * N, 0.0);

@@ -414,6 +414,14 @@ class PlanningProblem(object):
         _check(_host.lib().exo_host_problem_cost_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data))
         return cost
 
+    def hessian_batch(self, X):
+        """exotica.Hessian of every evaluation: X[E][N] -> H[E][length_jacobian][N][N] (KinematicTree::ComputeH and the task maps'
+        Hessian overloads)."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.N)
+        H = np.empty((X.shape[0], self.length_jacobian, self.N, self.N))
+        _check(_host.lib().exo_host_problem_hessian_batch(self._h, X.ctypes.data, X.shape[0], H.ctypes.data))
+        return H
+
     def cost_batch_device(self, d_x, d_phi, n_trajectories, d_cost, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
         """Same on the device buffers of update_batch_device (asynchronous on `stream`)."""
         _check(_host.lib().exo_host_problem_cost_batch_device(self._h, d_x, d_phi, int(n_trajectories), int(layout), d_cost, d_cost_eval, stream))
@@ -432,8 +440,59 @@ class PlanningProblem(object):
         return _capi.lib().exo_problem_last_kernel(_host.lib().exo_host_problem_backend(self._h)).decode()
 
 
+class IKSolver(object):
+    """exotica_ik_solver's IKSolver (exotations/solvers/exotica_ik_solver): specify_problem / solve as in pyexotica, plus
+    solve_batch(Q0) for multi-start IK -- every start state is solved independently on the GPU."""
+
+    TERMINATION = {0: "IterationLimit", 2: "StepTolerance", 3: "FunctionTolerance", 4: "GradientTolerance", 5: "Divergence"}
+
+    def __init__(self, props=None):
+        props = dict(props or {})
+        self.max_iterations = int(props.get("MaxIterations", 100))                      # exotica_core/init/motion_solver.in
+        self.tolerance = float(props.get("Tolerance", 1e-5))                            # init/ik_solver.in
+        self.regularization_rate = float(props.get("RegularizationRate", 1e-9))
+        self.maximum_regularization = float(props.get("MaximumRegularization", 1e9))
+        self.gradient_tolerance = float(props.get("GradientToleranceConvergenceThreshold", 1e-9))
+        self.step_tolerance = float(props.get("StepToleranceConvergenceThreshold", 1e-5))
+        if float(props.get("MaxStep", 0.0)) != 0.0:
+            raise ExoticaError("IKSolver: the MaxStep mode is not available on the batched path")
+        self.problem = None
+
+    def specify_problem(self, problem):
+        if problem.time_indexed:
+            raise ExoticaError("This IKSolver can't solve problem of type '%s'!" % problem.type)
+        self.problem = problem
+
+    def solve_batch(self, Q0):
+        """Q0[E][N] -> (solutions[E][N], cost[E], iterations[E], termination[E])."""
+        if self.problem is None:
+            raise ExoticaError("Solver has not been initialized!")
+        Q0 = np.ascontiguousarray(Q0, dtype=np.float64).reshape(-1, self.problem.N)
+        E = Q0.shape[0]
+        prm = _capi.IkParams(self.max_iterations, self.tolerance, self.regularization_rate, self.maximum_regularization,
+                             self.gradient_tolerance, self.step_tolerance)
+        Q, cost = np.empty_like(Q0), np.empty(E)
+        it, term = np.zeros(E, dtype=np.int32), np.zeros(E, dtype=np.int32)
+        _check(_host.lib().exo_host_problem_ik_solve_batch(self.problem._h, Q0.ctypes.data, E, ctypes.byref(prm), Q.ctypes.data, cost.ctypes.data,
+                                                           it.ctypes.data, term.ctypes.data))
+        return Q, cost, it, term
+
+    def solve(self):
+        """pyexotica: solution = solver.solve() from the problem's start state -> [1][N]."""
+        Q, cost, it, term = self.solve_batch(self.problem.start_state[None, :])
+        self.termination_criterion = self.TERMINATION.get(int(term[0]), str(int(term[0])))
+        return Q
+
+
 class Setup(object):
     """pyexotica.Setup (pyexotica.cpp:683-706)."""
+
+    @staticmethod
+    def create_solver(initializer):
+        name, props = initializer
+        if name.split("/")[-1] != "IKSolver":
+            raise ExoticaError("Unable to load solver of type '%s' (available on the GPU path: exotica/IKSolver)" % name)
+        return IKSolver(props)
 
     @staticmethod
     def set_package_path(package, directory):

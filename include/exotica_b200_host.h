@@ -80,6 +80,12 @@ int exo_host_problem_update_batch_device(exo_host_problem* problem, const double
 int exo_host_problem_cost_batch(exo_host_problem* problem, const double* x, int64_t n_traj, double* cost);
 int exo_host_problem_cost_batch_device(exo_host_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int layout,
                                        double* d_cost, double* d_cost_eval, void* stream);
+/* NEW multi-start IK: IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) from n start states
+ * q0[n][N] -> solutions[n][N], cost[n], iterations[n], termination[n] (exotica::TerminationCriterion values). */
+int exo_host_problem_ik_solve_batch(exo_host_problem* problem, const double* q0, int64_t n, const exo_ik_params* params, double* solutions,
+                                    double* cost, int32_t* iterations, int32_t* termination);
+/* NEW exotica::Hessian of every evaluation: x[n][N] -> hess[n][length_jacobian][N][N]. */
+int exo_host_problem_hessian_batch(exo_host_problem* problem, const double* x, int64_t n_evals, double* hess);
 int exo_host_problem_last_kernel_ms(exo_host_problem* problem, float* ms);
 int64_t exo_host_problem_launch_count(exo_host_problem* problem);
 int64_t exo_host_problem_update_count(exo_host_problem* problem); /* number_of_problem_updates_ */

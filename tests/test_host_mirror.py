@@ -174,3 +174,31 @@ def test_sibling_maps_through_the_factory(oracle_lib):
     with pytest.raises(exo.ExoticaError, match="JointMap index"):
         exo.Setup.create_problem(("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"),
                                                                           "Maps": [("exotica/JointPose", {"Name": "P", "JointMap": "9"})]}))
+
+
+@pytest.mark.gpu
+def test_ik_solver_and_hessian_through_the_python_surface(oracle_lib):
+    # exotica_examples/scripts/example_ik_manual_initialization shape: solver + problem from initializers
+    eff = ("exotica/EffFrame", {"Name": "Position", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc = _oracle_for(oracle_lib, maps)
+    rng = np.random.default_rng(31)
+    q_goal = rng.uniform(orc.lower, orc.upper) * 0.5
+    goal = orc.problem_update(q_goal)[0]
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "ik", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff],
+                                                    "StartState": list(q_goal + 0.2), "W": list(np.linspace(1, 2, 7)),
+                                                    "Cost": [("exotica/Task", {"Task": "Position", "Goal": list(goal)})]})
+    problem = exo.Setup.create_problem(init)
+    solver = exo.Setup.create_solver(("exotica/IKSolver", {"Name": "MySolver", "MaxIterations": 50}))
+    solver.specify_problem(problem)
+    Q0 = np.clip(q_goal + rng.normal(0, 0.4, size=(40, 7)), orc.lower, orc.upper)
+    Q, cost, it, term = solver.solve_batch(Q0)
+    for e in range(0, 40, 5):
+        q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], [1.0], goal=goal, W=np.linspace(1, 2, 7), max_iterations=50)
+        if t_ref == 3:
+            assert term[e] == 3 and it[e] == it_ref and np.max(np.abs(Q[e] - q_ref)) <= 1e-6
+    sol = solver.solve()
+    assert sol.shape == (1, 7) and solver.termination_criterion in exo.IKSolver.TERMINATION.values()
+    H = problem.hessian_batch(Q0[:9])
+    for e in range(9):
+        assert np.max(np.abs(H[e] - orc.problem_hessian(Q0[e]))) <= 1e-10
