@@ -78,7 +78,16 @@ struct exo_problem
     int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..3 chain kernel variants (CHAIN_REGS, CHAIN_TWO_PASS)
     bool chain_ok = false;        // the compiled program lowered to ChainParams
     ChainParams chain;            // problem constants of the chain kernel (buffers / strides filled per launch)
-    bool plan_valid = false;      // interpreter launch plan (depends on the program only)
+    bool plan_valid = false;      // interpreter launch plan (depends on the program and on split_spheres only)
+    bool plan_split = false;
+    bool fused_spheres = false;   // exo_problem_set_kernel(6): SphereCollision inside the interpreter (no second launch)
+    struct SphDump                // slots parked between the interpreter and exo_spheres_kernel: one buffer per stream in use
+    {
+        cudaStream_t stream;
+        double* d;
+        int64_t bytes;
+    };
+    std::vector<SphDump> sph_dumps;
     LaunchConfig plan_cfg;
     int32_t plan_scratch_offset = 0;
     const char* last_kernel = "none";
@@ -327,6 +336,8 @@ int exo_problem_destroy(exo_problem* p)
     if (p->d_generated) cudaFree(p->d_generated);
     if (p->d_ik) cudaFree(p->d_ik);
     if (p->d_ik_i) cudaFree(p->d_ik_i);
+    for (auto& sd : p->sph_dumps)
+        if (sd.d) cudaFree(sd.d);
     if (p->shadow) exo_problem_destroy(p->shadow);
     if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
     if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
@@ -541,6 +552,14 @@ static int fill_strides(const exo_problem* p, int layout, int64_t E, KernelParam
     return EXO_OK;
 }
 
+// upper bound of one buffer of parked SphereCollision slots (EXO_SPH_DUMP_MIB, default 1024 MiB)
+static int64_t sph_dump_cap_bytes()
+{
+    const char* s = getenv("EXO_SPH_DUMP_MIB");  // read per launch: tests shrink it to force several chunks
+    const long mib = s ? atol(s) : 0;
+    return (int64_t)(mib > 0 ? mib : 1024) << 20;
+}
+
 static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E, int32_t T, int32_t layout, double* d_phi, double* d_jac,
                   cudaStream_t stream, bool timed)
 {
@@ -571,22 +590,58 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     const bool chain = p->chain_ok && p->kernel_choice != 1;
     if (!chain && p->kernel_choice >= 2) return fail(EXO_ERR_UNSUPPORTED, "the compiled program is not a serial chain: the chain kernel cannot run it");
     LaunchConfig cfg;
+    int n_sph_ops = 0;
+    for (const Op& op : p->prog.ops) n_sph_ops += op.kind == OP_EMIT_SPHERES;
+    const bool split = !chain && n_sph_ops > 0 && n_sph_ops <= SPH_SPLIT_MAX_OPS && !p->fused_spheres;
+    int64_t chunk = E;  // split launches go in chunks whose parked slots fit the dump buffer
+    double* dump = nullptr;
     if (!chain)
     {
-        if (!p->plan_valid)
+        if (!p->plan_valid || p->plan_split != split)
         {
-            cudaError_t e = plan_launch(p->prog.hdr, k.program_bytes, (int64_t)1 << 40, p->plan_cfg, k);
+            cudaError_t e = plan_launch(p->prog.hdr, k.program_bytes, (int64_t)1 << 40, split, p->plan_cfg, k);
             if (e == cudaErrorInvalidConfiguration)
                 return fail(EXO_ERR_UNSUPPORTED, "compiled program needs more shared memory per thread than one CTA can hold");
             if (e != cudaSuccess) return cuda_fail(e, "plan_launch");
             p->plan_scratch_offset = k.scratch_offset;
             p->plan_valid = true;
+            p->plan_split = split;
         }
         cfg = p->plan_cfg;
         k.scratch_offset = p->plan_scratch_offset;
-        const int64_t per_cta = (int64_t)(cfg.threads / 32) * cfg.tile;
-        const int64_t want = (E + per_cta - 1) / per_cta;
-        if (want < cfg.blocks) cfg.blocks = (int)want;
+        if (split)
+        {
+            const int64_t row = (p->prog.hdr.scratch_doubles + 1) & ~1;
+            const int64_t per_eval = (int64_t)n_sph_ops * row * (int64_t)sizeof(double);
+            const int64_t cap_bytes = sph_dump_cap_bytes();
+            int64_t max_chunk = cap_bytes / per_eval / 32 * 32;
+            if (max_chunk < 32) max_chunk = 32;
+            if (k.T > 1 && max_chunk > k.T) max_chunk = max_chunk / k.T * k.T;  // whole trajectories per chunk where they fit
+            if (chunk > max_chunk) chunk = max_chunk;
+            k.sph_row = (int32_t)row;
+            k.sph_block = chunk * row;
+            k.sph_n_ops = n_sph_ops;
+            const int64_t need = per_eval * chunk;
+            exo_problem::SphDump* slot = nullptr;
+            for (auto& sd : p->sph_dumps)
+                if (sd.stream == stream) slot = &sd;
+            if (!slot)
+            {
+                p->sph_dumps.push_back({stream, nullptr, 0});
+                slot = &p->sph_dumps.back();
+            }
+            if (slot->bytes < need)
+            {
+                // the stream may still be reading the old buffer
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                if (slot->d) CUDA_TRY(cudaFree(slot->d));
+                slot->d = nullptr;
+                slot->bytes = 0;
+                CUDA_TRY(cudaMalloc(&slot->d, (size_t)need));
+                slot->bytes = need;
+            }
+            dump = slot->d;
+        }
     }
     if (timed)
     {
@@ -602,17 +657,43 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     {
         chain_bind(p->chain, k.x, k.phi, k.jac, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
         e = chain_launch(p->chain, p->kernel_choice >= 2 ? p->kernel_choice - 2 : CHAIN_DEFAULT, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        p->launches++;
     }
     else
-        e = launch_eval(cfg, k, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    p->last_kernel = chain ? "exo_chain_kernel" : "exo_eval_kernel";
+    {
+        const KernelParams k0 = k;
+        for (int64_t c0 = 0; c0 < E; c0 += chunk)
+        {
+            const int64_t n = E - c0 < chunk ? E - c0 : chunk;
+            k.n_evals = n;
+            k.e_base = c0;
+            k.x = k0.x + c0 * k0.x_se;
+            k.phi = k0.phi + c0 * k0.phi_se;
+            k.jac = k0.jac ? k0.jac + c0 * k0.j_se : nullptr;
+            k.min_dist = k0.min_dist ? k0.min_dist + c0 : nullptr;
+            k.sph_dump = dump;
+            LaunchConfig c = cfg;
+            const int64_t per_cta = (int64_t)(c.threads / 32) * c.tile;
+            const int64_t want = (n + per_cta - 1) / per_cta;
+            if (want < c.blocks) c.blocks = (int)want;
+            e = launch_eval(c, k, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+            p->launches++;
+            if (split)
+            {
+                e = launch_spheres(c, k, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+                p->launches++;
+            }
+        }
+    }
+    p->last_kernel = chain ? "exo_chain_kernel" : (split ? "exo_spheres_kernel" : "exo_eval_kernel");
     if (timed)
     {
         CUDA_TRY(cudaEventRecord(p->ev1, stream));
         p->timed = true;
     }
-    p->launches++;
     return EXO_OK;
 }
 
@@ -638,7 +719,8 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 5) return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants) or 4..5 (interpreter, one- / two-pass program)");
+    if (choice < 0 || choice > 6)
+        return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants), 4..5 (interpreter, one- / two-pass program) or 6 (interpreter with SphereCollision fused in)");
     const int mode = choice == 4 ? COMPILE_ONE_PASS : (choice == 5 ? COMPILE_TWO_PASS : COMPILE_AUTO);
     if (mode != p->compile_mode)
     {
@@ -646,6 +728,7 @@ int exo_problem_set_kernel(exo_problem* p, int choice)
         p->compiled_version = -1;  // recompile at the next launch
     }
     p->kernel_choice = choice >= 4 ? 1 : choice;
+    p->fused_spheres = choice == 6;
     return EXO_OK;
 }
 

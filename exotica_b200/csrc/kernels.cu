@@ -51,13 +51,14 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// exp(t) for the sigmoid: |relative error| < 1e-14 (degree-11 Taylor on |r| <= ln2/2), t clamped to +-700
+// exp(t) for the sigmoid: |relative error| < 1e-14 (degree-11 Taylor on |r| <= ln2/2).  Instead of clamping t (an FP64 min and an
+// FP64 max: a dozen instructions each way on this machine) the power of two is clamped as an integer: beyond 2^+-1000 the sigmoid
+// is 0 or 1 to 300 digits either way.  Valid for |t| < 2^31 ln 2 (t = 5 eps x a surface distance in metres).
 __device__ __forceinline__ double sph_exp(double t)
 {
-    t = fmin(fmax(t, -700.0), 700.0);
     const double magic = 6755399441055744.0;
     const double kf = fma(t, kExp[0], magic);
-    const int k = __double2loint(kf);
+    const int k = max(min(__double2loint(kf), 1000), -1000);
     const double kd = kf - magic;
     double r = fma(-kd, kExp[1], t);
     r = fma(-kd, kExp[2], r);
@@ -75,10 +76,10 @@ __device__ __forceinline__ double sph_exp(double t)
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
-// one sphere pair: accumulates weight * sigmoid into phi (if WITH_PHI) and weight * unit vector into (gx, gy, gz)
+// one sphere pair, d = p_owner - p_other: accumulates the sigmoid into phi (if WITH_PHI) and the unit vector into (gx, gy, gz)
 template <bool WITH_PHI>
-__device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double rsum, double k5, double weight, double& phi, double& gx, double& gy,
-                                         double& gz, double& dmin)
+__device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double rsum, double k5, double& phi, double& gx, double& gy, double& gz,
+                                         double& dmin)
 {
     const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
     double y;
@@ -88,15 +89,14 @@ __device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double
     y = fma(y, t, y);
     t = fma(-(h * y), y, 0.5);
     y = fma(y, t, y);  // 1 / |d|  (inf -> NaN for coincident centres, like the reference's division by zero)
-    const double yw = y * weight;  // weight 0 masks the padding pairs of the unrolled loop
-    gx = fma(dx, yw, gx);
-    gy = fma(dy, yw, gy);
-    gz = fma(dz, yw, gz);
+    gx = fma(dx, y, gx);
+    gy = fma(dy, y, gy);
+    gz = fma(dz, y, gz);
     if (WITH_PHI)
     {
         const double n = (n2 == 0.0) ? 0.0 : n2 * y;
         const double gap = n - rsum;  // surface distance of the pair
-        dmin = (weight != 0.0) ? fmin(dmin, gap) : dmin;
+        dmin = gap < dmin ? gap : dmin;
         const double den = 1.0 + sph_exp(k5 * gap);
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
@@ -104,7 +104,41 @@ __device__ __forceinline__ void sph_pair(double dx, double dy, double dz, double
         r = fma(r, e, r);
         e = fma(-den, r, 1.0);
         r = fma(r, e, r);
-        phi = fma(r, weight, phi);
+        phi += r;
+    }
+}
+
+#ifndef EXO_SPH_UNROLL
+#define EXO_SPH_UNROLL 4
+#endif
+#ifndef EXO_SPHERES_MAXNREG
+#define EXO_SPHERES_MAXNREG 96
+#endif
+#ifndef EXO_SPHERES_EPC
+#define EXO_SPHERES_EPC 4
+#endif
+
+// this lane's share of the other group [t0, t1) (stride parts) against its owner sphere: four pairs per iteration -- straight-line
+// code whose independent Horner / Newton chains the scheduler interleaves (the FP64 pipe needs ~5 independent instructions in
+// flight per warp); the tail (at most three pairs per lane) runs one at a time
+template <bool WITH_PHI>
+__device__ __forceinline__ void sph_pair_loop(const double2* c2, int j0, int t1, int parts, double pix, double piy, double piz, double ri, double k5,
+                                              double& ph, double& gx, double& gy, double& gz, double& dmin)
+{
+    for (; j0 + (EXO_SPH_UNROLL - 1) * parts < t1; j0 += EXO_SPH_UNROLL * parts)
+    {
+#pragma unroll
+        for (int u = 0; u < EXO_SPH_UNROLL; ++u)
+        {
+            const int j = j0 + u * parts;
+            const double2 a = c2[2 * j], b = c2[2 * j + 1];  // (x, y), (z, radius)
+            sph_pair<WITH_PHI>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, ph, gx, gy, gz, dmin);
+        }
+    }
+    for (; j0 < t1; j0 += parts)
+    {
+        const double2 a = c2[2 * j0], b = c2[2 * j0 + 1];
+        sph_pair<WITH_PHI>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, ph, gx, gy, gz, dmin);
     }
 }
 
@@ -141,6 +175,7 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
             centre[4 * s] = px; centre[4 * s + 1] = py; centre[4 * s + 2] = pz; centre[4 * s + 3] = sc[4 * s + 3];
         }
         __syncwarp();
+        const double2* c2 = reinterpret_cast<const double2*>(centre);  // [S][2]: (x, y), (z, radius)
         const int64_t e = e0 + ev;
         int out_idx = 0;
         double dmin = CUDART_INF;  // smallest surface distance over all pairs of this evaluation
@@ -148,22 +183,27 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
         {
             for (int gb = ga + 1; gb < G; ++gb, ++out_idx)
             {
+                // Which of the two groups hang below controlled joints?  Only those contribute Jacobian terms.  With one moving
+                // group (robot against fixed or trajectory-driven obstacles) a single sweep over the pairs, owned by the moving
+                // group's spheres, yields phi and J; with two, a second sweep owned by group B adds its J terms (no sigmoids).
+                bool mov_a = false, mov_b = false;
                 if (want_j)
-                    for (int col = lane; col < N; col += 32) rowacc[col] = 0.0;
-                __syncwarp();
-                double phi_part = 0.0;
-                // pass 0: lanes own spheres of group A (phi and -J_i^T g_i); pass 1: lanes own spheres of group B (+J_j^T h_j)
-                for (int pass = 0; pass < (want_j ? 2 : 1); ++pass)
                 {
-                    const int o0 = pass == 0 ? gs[ga] : gs[gb], o1 = pass == 0 ? gs[ga + 1] : gs[gb + 1];
-                    const int t0 = pass == 0 ? gs[gb] : gs[ga], t1 = pass == 0 ? gs[gb + 1] : gs[ga + 1];
-                    if (pass == 1)
-                    {
-                        // skip when no sphere of group B hangs below a controlled joint (fixed or trajectory-driven obstacles)
-                        bool any = false;
-                        for (int j = o0; j < o1; ++j) any = any || sph[SPH_INTS * j + 1] >= 0;
-                        if (!any) break;
-                    }
+                    for (int j = gs[ga] + lane; j < gs[ga + 1]; j += 32) mov_a = mov_a || sph[SPH_INTS * j + 1] >= 0;
+                    for (int j = gs[gb] + lane; j < gs[gb + 1]; j += 32) mov_b = mov_b || sph[SPH_INTS * j + 1] >= 0;
+                    mov_a = __any_sync(0xffffffffu, mov_a);
+                    mov_b = __any_sync(0xffffffffu, mov_b);
+                    for (int col = lane; col < N; col += 32) rowacc[col] = 0.0;
+                    __syncwarp();
+                }
+                double phi_part = 0.0;
+                const int n_pass = (mov_a && mov_b) ? 2 : 1;
+                for (int pass = 0; pass < n_pass; ++pass)
+                {
+                    const bool own_b = pass == 1 || (mov_b && !mov_a);
+                    const bool with_j = own_b ? mov_b : mov_a;
+                    const int o0 = own_b ? gs[gb] : gs[ga], o1 = own_b ? gs[gb + 1] : gs[ga + 1];
+                    const int t0 = own_b ? gs[ga] : gs[gb], t1 = own_b ? gs[ga + 1] : gs[gb + 1];
                     const int n_own = o1 - o0;
                     // lanes = (owner sphere, share of the other group): parts = how many lanes share one owner sphere
                     int own_p2 = 1;
@@ -175,59 +215,69 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
                         const int part = lane / own_p2;
                         const bool live = i < o1;
                         const int ii = live ? i : o1 - 1;
-                        const double pix = centre[4 * ii], piy = centre[4 * ii + 1], piz = centre[4 * ii + 2], ri = centre[4 * ii + 3];
+                        const double2 pa = c2[2 * ii], pb = c2[2 * ii + 1];
+                        const double pix = pa.x, piy = pa.y, piz = pb.x, ri = pb.y;
+                        // d = p_owner - p_other in both sweeps: for owners in group B that is -u_ij, and the sum over the owner's
+                        // pairs is -h_j, so both sweeps subtract (w_c x (p_owner - p_c)) . g  (J.row = -sum (J_i - J_j)^T u_ij)
                         double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
                         if (live)
                         {
-                            // four pairs per iteration: straight-line code whose independent Horner / Newton chains the
-                            // scheduler interleaves (the FP64 pipe needs ~5 independent instructions in flight per warp).
-                            // Full groups of four run without masks; the tail (at most three pairs per lane) is masked.
-                            const double2* c2 = reinterpret_cast<const double2*>(centre);  // [S][2]: (x, y), (z, radius)
-                            int j0 = t0 + part;
-                            for (; j0 + 3 * parts < t1; j0 += 4 * parts)
-                            {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-                                {
-                                    const int j = j0 + u * parts;
-                                    const double2 a = c2[2 * j], b = c2[2 * j + 1];
-                                    if (pass == 0)
-                                        sph_pair<true>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, 1.0, ph, gx, gy, gz, dmin);
-                                    else
-                                        sph_pair<false>(a.x - pix, a.y - piy, b.x - piz, 0.0, k5, 1.0, ph, gx, gy, gz, dmin);
-                                }
-                            }
-                            for (; j0 < t1; j0 += parts)
-                            {
-                                const double2 a = c2[2 * j0], b = c2[2 * j0 + 1];
-                                if (pass == 0)
-                                    sph_pair<true>(pix - a.x, piy - a.y, piz - b.x, ri + b.y, k5, 1.0, ph, gx, gy, gz, dmin);
-                                else
-                                    sph_pair<false>(a.x - pix, a.y - piy, b.x - piz, 0.0, k5, 1.0, ph, gx, gy, gz, dmin);
-                            }
+                            if (pass == 0)
+                                sph_pair_loop<true>(c2, t0 + part, t1, parts, pix, piy, piz, ri, k5, ph, gx, gy, gz, dmin);
+                            else
+                                sph_pair_loop<false>(c2, t0 + part, t1, parts, pix, piy, piz, ri, k5, ph, gx, gy, gz, dmin);
                         }
                         phi_part += ph;
-                        if (!want_j) continue;
-                        // Jacobian: every column whose joint carries this lane's sphere gets w_c . ((p_i - p_c) x g)
+                        if (!with_j) continue;
+                        // Jacobian: every column whose joint carries this lane's sphere gets w_c . ((p_i - p_c) x g).  Eight columns
+                        // at a time: each lane evaluates its eight terms, then a butterfly that halves the number of live values
+                        // per step (4 + 2 + 1 + 1 + 1 exchanges instead of 8 x 5) leaves column (lane >> 2) in every lane.
                         const int acc_i = live ? sph[SPH_INTS * ii + 1] : -1;
-                        for (int col = 0; col < N; ++col)
+                        for (int col0 = 0; col0 < N; col0 += 8)
                         {
-                            const int ent = cols[3 * col];
-                            if (ent < 0) continue;
-                            const uint32_t mlo = (uint32_t)cols[3 * col + 1], mhi = (uint32_t)cols[3 * col + 2];
-                            const bool in = acc_i >= 0 && (acc_i < 32 ? ((mlo >> acc_i) & 1u) : ((mhi >> (acc_i - 32)) & 1u));
-                            const double* js = scr + (joint_base + 6 * (ent >> 2)) * CS;
-                            const double ax = js[0], ay = js[CS], az = js[2 * CS];
-                            double v;
-                            if (ent & 2)
-                                v = ax * gx + ay * gy + az * gz;
-                            else
+                            double v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
                             {
-                                const double rx = pix - js[3 * CS], ry = piy - js[4 * CS], rz = piz - js[5 * CS];
-                                v = ax * (ry * gz - rz * gy) + ay * (rz * gx - rx * gz) + az * (rx * gy - ry * gx);
+                                v[u] = 0.0;
+                                const int col = col0 + u;
+                                if (col >= N) continue;
+                                const int ent = cols[3 * col];
+                                if (ent < 0) continue;
+                                const uint32_t mlo = (uint32_t)cols[3 * col + 1], mhi = (uint32_t)cols[3 * col + 2];
+                                const bool in = acc_i >= 0 && (acc_i < 32 ? ((mlo >> acc_i) & 1u) : ((mhi >> (acc_i - 32)) & 1u));
+                                if (!in) continue;
+                                const double* js = scr + (joint_base + 6 * (ent >> 2)) * CS;
+                                const double ax = js[0], ay = js[CS], az = js[2 * CS];
+                                if (ent & 2)
+                                    v[u] = ax * gx + ay * gy + az * gz;
+                                else
+                                {
+                                    const double rx = pix - js[3 * CS], ry = piy - js[4 * CS], rz = piz - js[5 * CS];
+                                    v[u] = ax * (ry * gz - rz * gy) + ay * (rz * gx - rx * gz) + az * (rx * gy - ry * gx);
+                                }
                             }
-                            v = warp_sum(in ? v : 0.0);
-                            if (lane == 0) rowacc[col] += (pass == 0 ? -v : v);
+                            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const double send = h16 ? v[u] : v[u + 4], keep = h16 ? v[u + 4] : v[u];
+                                v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; ++u)
+                            {
+                                const double send = h8 ? v[u] : v[u + 2], keep = h8 ? v[u + 2] : v[u];
+                                v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                            {
+                                const double send = h4 ? v[0] : v[1], keep = h4 ? v[1] : v[0];
+                                v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                            }
+                            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+                            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+                            const int mycol = col0 + (lane >> 2);  // bit 2 picked between 2 values, bit 3 between 4, bit 4 between 8
+                            if ((lane & 3) == 0 && mycol < N) rowacc[mycol] -= v[0];
                         }
                     }
                 }
@@ -299,6 +349,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
         double* phi_e = P.phi + e * P.phi_se;
         double* jac_e = want_j ? P.jac + e * P.j_se : nullptr;
         Fr cur = fr_identity();
+        int sph_ord = 0;  // SphereCollision ops seen so far in this evaluation (indexes the dump of the split launch)
         // two-pass programs: pass 0 composes the tree and emits Phi (parking each requested frame's position), pass 1
         // composes it again and emits every joint's Jacobian columns the moment its axis and origin are known
         constexpr bool TP = W == 32;  // narrow tiles serve SphereCollision programs, which are never two-pass: compile it out
@@ -324,7 +375,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     cur = fr_mul(cur, fr_load_const(c));
                 if (op.kind == OP_TABLE)
                 {
-                    const int t = (int)(e % P.T);
+                    const int t = (int)((P.e_base + e) % P.T);
                     const double* g = P.generated + ((size_t)t * H->n_generated + op.qidx) * 12;
                     Fr gf;
                     gf.m0 = g[0]; gf.m1 = g[1]; gf.m2 = g[2]; gf.m3 = g[3]; gf.m4 = g[4]; gf.m5 = g[5];
@@ -519,6 +570,18 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
             {
                 emit_fill(c, op.n_items, op.n_rows, N, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk, want_j ? jac_e + (int64_t)op.jrow_off * P.j_sr : nullptr, P.j_sr, P.j_sc);
             }
+            else if (op.kind == OP_EMIT_SPHERES && P.sph_dump)
+            {
+                // split launch: park this evaluation's slots for exo_spheres_kernel (one row per evaluation; the partial sectors
+                // of neighbouring words merge in L2 before they reach HBM)
+                if (lane < W && slot < n_valid)
+                {
+                    const int words = H->scratch_doubles;
+                    double* d = P.sph_dump + (int64_t)sph_ord * P.sph_block + e * P.sph_row;
+                    for (int k = 0; k < words; ++k) d[k] = scr[k * CS];
+                }
+                ++sph_ord;
+            }
             else if (op.kind == OP_EMIT_SPHERES)
             {
                 __syncwarp();  // every lane's frame / joint slots are complete
@@ -527,6 +590,82 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                 __syncwarp();  // slots may be overwritten by the ops that follow
             }
         }
+    }
+}
+
+// SphereCollision of split programs: one warp per evaluation, WPC independent warps per CTA.  A warp copies its evaluation's row of
+// parked slots into its own shared-memory buffer with 16-byte cp.async while it is still busy with the previous row (two buffers),
+// so no warp ever waits for another; the pair loops are the interpreter's own code with a scratch stride of one column.  Without
+// the tree interpreter around them they need 96 registers instead of 166.
+template <int WPC>
+__global__ void __maxnreg__(EXO_SPHERES_MAXNREG) exo_spheres_kernel(const KernelParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int sph_pc[SPH_SPLIT_MAX_OPS];
+    const int tid = threadIdx.x;
+    {
+        const int n_words = P.program_bytes >> 2;
+        const int32_t* src = reinterpret_cast<const int32_t*>(P.program);
+        int32_t* dst = reinterpret_cast<int32_t*>(smem);
+        for (int i = tid; i < n_words; i += WPC * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ProgramHeader* H = reinterpret_cast<const ProgramHeader*>(smem);
+    const Op* ops = reinterpret_cast<const Op*>(smem + sizeof(ProgramHeader));
+    const int32_t* ints = reinterpret_cast<const int32_t*>(ops + H->n_ops);
+    const double* dbls = reinterpret_cast<const double*>(smem + P.dbl_offset);
+    if (tid == 0)
+    {
+        int k = 0;
+        for (int pc = 0; ops[pc].kind != OP_END; ++pc)
+            if (ops[pc].kind == OP_EMIT_SPHERES && k < SPH_SPLIT_MAX_OPS) sph_pc[k++] = pc;
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int N = H->n_ctrl;
+    const int row = P.sph_row, n_ops = P.sph_n_ops;
+    const int joint_base = 12 * H->n_frame_slots;
+    const int per_warp = 2 * row + 4 * H->max_spheres + N + (N & 1);  // two row buffers, centre table, Jacobian row accumulators
+    double* stage = reinterpret_cast<double*>(smem + P.scratch_offset) + (size_t)warp * per_warp;
+    double* warp_smem = stage + 2 * row;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const bool want_j = P.jac != nullptr;
+    const int64_t stride = (int64_t)gridDim.x * WPC;
+
+    auto fetch = [&](int64_t e, int ord, int buf) {
+        const char* src = reinterpret_cast<const char*>(P.sph_dump + (int64_t)ord * P.sph_block + e * row);
+        const uint32_t dst = stage_s + (uint32_t)(buf * row) * 8u;
+        for (int i = lane; i < (row >> 1); i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int64_t e = (int64_t)blockIdx.x * WPC + warp;
+    int ord = 0, buf = 0;
+    if (e < P.n_evals) fetch(e, 0, 0);
+    while (e < P.n_evals)
+    {
+        int64_t e_next = e;
+        int ord_next = ord + 1;
+        if (ord_next == n_ops)
+        {
+            ord_next = 0;
+            e_next = e + stride;
+        }
+        if (e_next < P.n_evals)
+        {
+            fetch(e_next, ord_next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();  // every lane's copies of this row have landed
+        const Op op = ops[sph_pc[ord]];
+        emit_spheres_warp<1>(op, dbls + op.cst, ints + op.tab, N, joint_base, stage + buf * row, warp_smem, lane, 0, 1, e, P, want_j);
+        __syncwarp();  // the buffer is refilled two rows from now
+        e = e_next;
+        ord = ord_next;
+        buf ^= 1;
     }
 }
 }  // namespace
@@ -565,7 +704,7 @@ cudaError_t try_any(const EvalConfig& c, size_t prog, size_t per_column, size_t 
 }
 }  // namespace
 
-cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params)
+cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, bool split_spheres, LaunchConfig& cfg, KernelParams& params)
 {
     int dev = 0, sms = 0, max_smem = 0;
     cudaError_t err = cudaGetDevice(&dev);
@@ -576,8 +715,8 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     if (err != cudaSuccess) return err;
     const size_t prog = ((size_t)program_bytes + 15) & ~(size_t)15;
     const size_t per_column = (size_t)(hdr.scratch_doubles + hdr.n_ctrl) * sizeof(double);
-    const bool spheres = hdr.max_spheres > 0;
-    const size_t per_warp = spheres ? (size_t)(4 * hdr.max_spheres + hdr.n_ctrl + (hdr.n_ctrl & 1)) * sizeof(double) : 0;
+    const bool spheres = hdr.max_spheres > 0 && !split_spheres;
+    const size_t per_warp = hdr.max_spheres > 0 ? (size_t)(4 * hdr.max_spheres + hdr.n_ctrl + (hdr.n_ctrl & 1)) * sizeof(double) : 0;
     params.scratch_offset = (int32_t)prog;
     const EvalConfig* cands = spheres ? kSpheres : kPlain;
     const int n_cands = spheres ? (int)(sizeof(kSpheres) / sizeof(kSpheres[0])) : (int)(sizeof(kPlain) / sizeof(kPlain[0]));
@@ -588,7 +727,7 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     {
         int ctas = 0;
         size_t smem_bytes = 0;
-        err = try_any(cands[k], prog, per_column, per_warp, max_smem, ctas, smem_bytes);
+        err = try_any(cands[k], prog, per_column, spheres ? per_warp : 0, max_smem, ctas, smem_bytes);
         if (err != cudaSuccess) return err;
         // spheres: resident warps first, wider tiles break ties; plain: resident lanes
         const int score = spheres ? ctas * (cands[k].tpb / 32) * 64 + cands[k].w : ctas * cands[k].tpb;
@@ -608,7 +747,34 @@ cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_e
     const int64_t want = (n_evals + per_cta - 1) / per_cta;
     const int64_t resident = (int64_t)sms * best_ctas;
     cfg.blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
+    cfg.sph_epc = 0;
+    if (hdr.max_spheres > 0 && split_spheres)
+    {
+        constexpr int EPC = EXO_SPHERES_EPC;
+        const size_t row = (size_t)((hdr.scratch_doubles + 1) & ~1);
+        const size_t smem_bytes = prog + (2 * row * sizeof(double) + per_warp) * EPC;
+        if (smem_bytes + 1024 > (size_t)max_smem) return cudaErrorInvalidConfiguration;  // the kernel has a little static shared memory too
+        err = cudaFuncSetAttribute(exo_spheres_kernel<EPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (err != cudaSuccess) return err;
+        int ctas = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_spheres_kernel<EPC>, EPC * 32, smem_bytes);
+        if (err != cudaSuccess) return err;
+        if (ctas < 1) return cudaErrorInvalidConfiguration;
+        cfg.sph_epc = EPC;
+        cfg.sph_blocks = sms * ctas;
+        cfg.sph_smem_bytes = smem_bytes;
+    }
     return cudaSuccess;
+}
+
+cudaError_t launch_spheres(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream)
+{
+    constexpr int EPC = EXO_SPHERES_EPC;
+    if (cfg.sph_epc != EPC) return cudaErrorInvalidConfiguration;
+    const int64_t want = (params.n_evals + EPC - 1) / EPC;
+    const int blocks = (int)(want < cfg.sph_blocks ? (want > 0 ? want : 1) : cfg.sph_blocks);
+    exo_spheres_kernel<EPC><<<blocks, EPC * 32, cfg.sph_smem_bytes, stream>>>(params);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream)

@@ -24,7 +24,16 @@ struct KernelParams
     int64_t x_se, x_sk;
     int64_t phi_se, phi_sk;
     int64_t j_se, j_sr, j_sc;
+    // SphereCollision as its own launch: the interpreter parks every evaluation's frame / joint slots here ([sphere op][e][word],
+    // one contiguous row per evaluation) instead of running the pair loops; exo_spheres_kernel picks them up one warp per row
+    double* sph_dump;              // NULL: the interpreter evaluates SphereCollision itself
+    int64_t sph_block;             // doubles per sphere op (rows of one launch)
+    int32_t sph_row;               // doubles per row: the program's scratch words rounded up to an even count (16-byte rows)
+    int32_t sph_n_ops;             // SphereCollision ops in the program (<= SPH_SPLIT_MAX_OPS)
+    int64_t e_base;                // index of evaluation 0 of this launch in the caller's batch (timestep = (e_base + e) % T)
 };
+
+constexpr int SPH_SPLIT_MAX_OPS = 16;  // programs with more SphereCollision maps evaluate them inside the interpreter
 
 struct LaunchConfig
 {
@@ -32,11 +41,17 @@ struct LaunchConfig
     int tile = 32;  // evaluations per warp
     int blocks = 0;
     size_t smem_bytes = 0;
+    // second launch of split SphereCollision programs (exo_spheres_kernel)
+    int sph_epc = 0;  // warps (= evaluations in flight) per CTA; 0: no second launch
+    int sph_blocks = 0;
+    size_t sph_smem_bytes = 0;
 };
 
-// Computes threads/blocks/shared memory for a program on the current device.
-cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, LaunchConfig& cfg, KernelParams& params);
+// Computes threads/blocks/shared memory for a program on the current device. split_spheres: plan the interpreter without the
+// SphereCollision pair loops (they run in exo_spheres_kernel, planned here too).
+cudaError_t plan_launch(const ProgramHeader& hdr, int program_bytes, int64_t n_evals, bool split_spheres, LaunchConfig& cfg, KernelParams& params);
 cudaError_t launch_eval(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
+cudaError_t launch_spheres(const LaunchConfig& cfg, const KernelParams& params, cudaStream_t stream);
 
 // ---- constant-bank kernel for serial-chain programs (chain_kernel.cu) ------------------------------------------------
 constexpr int CH_MAXJ = 8;       // joints in the chain

@@ -207,9 +207,13 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
  * 2 / 3 = the chain kernel's variants (joint data kept in registers / chain composed twice; EXO_ERR_UNSUPPORTED at
  * launch if the program is not a chain), 4 / 5 = the interpreter with the one-pass program (joint axes and origins parked
  * in shared memory until a frame needs them) / the two-pass program (the tree is walked twice and Jacobian columns are
- * emitted on the fly; used automatically for large trees).  Tests compare all of them. */
+ * emitted on the fly; used automatically for large trees), 6 = the interpreter with SphereCollision evaluated inside it
+ * (by default programs with a SphereCollision map run as two launches: the interpreter parks every evaluation's frames
+ * in a scratch buffer -- at most EXO_SPH_DUMP_MIB MiB, default 1024, larger batches go in chunks -- and
+ * exo_spheres_kernel runs the pair loops one warp per evaluation).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
-/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "none"). */
+/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
+ * second launch of a SphereCollision program) / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);
 
 /* Introspection of the compiled program (tests / DESIGN.md): number of joint ops, emit ops, frame slots,

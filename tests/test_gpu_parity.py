@@ -29,10 +29,14 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
     wrap = angle_entries(maps, orc)
     kernels = set()
     # 1: general interpreter, 0: auto, 2 / 3: the chain kernel's variants (serial-chain programs only),
-    # 4 / 5: the interpreter with the one-pass / two-pass program
-    for choice in (1, 0, 2, 3, 4, 5):
+    # 4 / 5: the interpreter with the one-pass / two-pass program, 6: SphereCollision fused into the interpreter
+    # (the default runs it as a second launch, exo_spheres_kernel)
+    has_spheres = any(m["type"] == "SphereCollision" for m in maps)
+    for choice in (1, 0, 2, 3, 4, 5, 6):
         prob.set_kernel(choice)
         if choice in (2, 3) and "exo_chain_kernel" not in kernels:
+            continue
+        if choice == 6 and not has_spheres:
             continue
         phi, jac = run_gpu(prob, X, layout=layout, T=T)
         kernels.add(prob.last_kernel())
@@ -211,6 +215,36 @@ def test_sphere_collision_lwr_moving_obstacle(oracle_lib):
     maps = _lwr_sphere_maps() + [{"type": "EffPosition", "EndEffector": [{"Link": "Obstacle", "LinkOffset": [0, 0.3, 0]}]}]
     prob, phi, jac = _check(orc, maps, X, T=T, generated=gen)
     assert np.all(jac[:, 1:, :] == 0)  # the obstacle has no controlled ancestors
+
+
+def test_sphere_collision_split_launch_in_chunks(oracle_lib, monkeypatch):
+    # two SphereCollision maps (two parked slot sets per evaluation), a trajectory-driven obstacle, and a scratch buffer so small
+    # that the batch goes through the interpreter + exo_spheres_kernel pair in several chunks of whole trajectories
+    monkeypatch.setenv("EXO_SPH_DUMP_MIB", "1")
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    tree.add_environment_element("Obstacle", generated_slot=0)
+    orc = oracle_lib.Oracle(tree)
+    B, T = 120, 25
+    gen = np.zeros((T, 1, 12))
+    for t in range(T):
+        gen[t, 0] = oracle_lib.get_frame([0.5 - 0.02 * t, 0.1, 0.6 + 0.01 * t, 0, 0, 0.1 * t])
+    X = random_states(orc, B * T - 7, seed=79)  # ragged: the last chunk ends inside a trajectory
+    second = _lwr_sphere_maps()
+    second[0]["Precision"] = 0.02
+    maps = _lwr_sphere_maps() + [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}] + second
+    prob, phi, jac = _check(orc, maps, X, T=T, generated=gen)
+    assert "exo_spheres_kernel" in prob.kernels_used and "exo_eval_kernel" in prob.kernels_used
+    # minimum surface distance per evaluation through the chunked path
+    E = X.shape[0]
+    dmin = _capi.DeviceBuffer(E)
+    prob.set_kernel(0)
+    prob.set_min_distance_output(dmin.ptr)
+    run_gpu(prob, X, T=T)
+    d_split = dmin.download((E,)).copy()
+    prob.set_kernel(6)
+    run_gpu(prob, X, T=T)
+    assert np.array_equal(d_split, dmin.download((E,)))
+    prob.set_min_distance_output(0)
 
 
 def test_sphere_collision_three_groups_robot_vs_robot(oracle_lib):
