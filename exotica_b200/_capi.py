@@ -90,6 +90,8 @@ SYMBOLS = [
     ("exo_problem_set_cost", ctypes.c_int, [_vp, ctypes.POINTER(CostDesc)]),
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("exo_problem_cost_jacobian_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
+    ("exo_problem_cost_jacobian_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
     ("exo_problem_ik_solve_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(IkParams), _vp, _vp, _vp, _vp]),
     ("exo_problem_hessian_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
@@ -360,6 +362,20 @@ class Problem(object):
         out = np.empty(B)
         check(lib().exo_problem_cost_batch_host(self.h, X.ctypes.data, B, LAYOUT_AOS_ROWMAJOR, out.ctypes.data))
         return out
+
+    def cost_jacobian_batch_device(self, d_x, d_phi, d_jac, n_traj, d_grad, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_cost_jacobian_batch(self.h, d_x, d_phi, d_jac, int(n_traj), int(layout), d_grad, stream))
+
+    def cost_jacobian_batch_host(self, X, with_cost=True):
+        """X[B][T][N] (or [B][N] for end-pose problems) -> (cost[B] or None, grad like X) through the host pipeline; Phi and J
+        stay on the device."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        B = X.shape[0]
+        cost = np.empty(B) if with_cost else None
+        grad = np.empty_like(X)
+        check(lib().exo_problem_cost_jacobian_batch_host(self.h, X.ctypes.data, B, LAYOUT_AOS_ROWMAJOR, cost.ctypes.data if with_cost else None,
+                                                         grad.ctypes.data))
+        return cost, grad
 
     def hessian_batch_device(self, d_x, d_jac, n_evals, d_hess, T=1, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_hessian_batch(self.h, d_x, d_jac, int(n_evals), int(T), int(layout), d_hess, stream))

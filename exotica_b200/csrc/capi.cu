@@ -100,6 +100,7 @@ struct exo_problem
     double* d_phi[NBUF] = {nullptr, nullptr, nullptr};
     double* d_jac[NBUF] = {nullptr, nullptr, nullptr};
     double* d_cost[NBUF] = {nullptr, nullptr, nullptr};
+    double* d_grad[NBUF] = {nullptr, nullptr, nullptr};
     int64_t pipe_chunk = 0;
     bool pipe_has_jac = false;
 };
@@ -321,7 +322,8 @@ static void free_pipeline(exo_problem* p)
         if (p->d_phi[i]) cudaFree(p->d_phi[i]);
         if (p->d_jac[i]) cudaFree(p->d_jac[i]);
         if (p->d_cost[i]) cudaFree(p->d_cost[i]);
-        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = p->d_cost[i] = nullptr;
+        if (p->d_grad[i]) cudaFree(p->d_grad[i]);
+        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = p->d_cost[i] = p->d_grad[i] = nullptr;
     }
     p->pipe_chunk = 0;
 }
@@ -754,6 +756,7 @@ static int ensure_pipeline(exo_problem* p, int64_t chunk, bool with_jac)
         CUDA_TRY(cudaMalloc((void**)&p->d_phi[i], std::max<size_t>(8, chunk * LP * sizeof(double))));
         if (with_jac) CUDA_TRY(cudaMalloc((void**)&p->d_jac[i], std::max<size_t>(8, chunk * LJ * N * sizeof(double))));
         CUDA_TRY(cudaMalloc((void**)&p->d_cost[i], std::max<size_t>(8, chunk * sizeof(double))));
+        CUDA_TRY(cudaMalloc((void**)&p->d_grad[i], std::max<size_t>(8, chunk * N * sizeof(double))));
     }
     p->pipe_chunk = chunk;
     p->pipe_has_jac = with_jac;
@@ -863,6 +866,7 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
         cm.kind = m.kind;
         cm.start = m.start;
         cm.start_jacobian = m.start_jacobian;
+        cm.length_jacobian = m.length_jacobian;
         cm.length = m.length;
         cm.n_frames = m.n_frames;
         cm.rot_type = m.rot_type;
@@ -939,6 +943,39 @@ int exo_problem_cost_batch(exo_problem* p, const double* d_x, const double* d_ph
     return EXO_OK;
 }
 
+int exo_problem_cost_jacobian_batch(exo_problem* p, const double* d_x, const double* d_phi, const double* d_jac, int64_t n_traj, int32_t layout,
+                                    double* d_grad, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_x || !d_phi || !d_jac || !d_grad) return fail(EXO_ERR_INVALID, "NULL buffer");
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    const int64_t E = n_traj * p->cost.T;
+    int rc = fill_strides(p, layout, E, k);
+    if (rc != EXO_OK) return rc;
+    CostGradParams g;
+    memset(&g, 0, sizeof(g));
+    g.c = p->cost;
+    g.c.x = d_x;
+    g.c.phi = d_phi;
+    g.c.n_traj = n_traj;
+    g.c.x_se = k.x_se; g.c.x_sk = k.x_sk; g.c.phi_se = k.phi_se; g.c.phi_sk = k.phi_sk;
+    g.jac = d_jac;
+    g.grad = d_grad;
+    g.j_se = k.j_se; g.j_sr = k.j_sr; g.j_sc = k.j_sc;
+    g.g_se = k.x_se; g.g_sk = k.x_sk;  // the gradient has the shape and layout of the states
+    g.length_jac = p->prog.hdr.length_jac;
+    cudaError_t e = launch_cost_gradient(g, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) return fail(EXO_ERR_UNSUPPORTED, "the task-space Jacobian has more rows than the cost-gradient kernel supports (200)");
+    if (e != cudaSuccess) return cuda_fail(e, "cost gradient kernel launch");
+    p->launches++;
+    p->last_kernel = "exo_cost_gradient_kernel";
+    return EXO_OK;
+}
+
 int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream)
 {
     if (n_traj < 0 || T < 1 || t_first < 0 || t_first >= T) return fail(EXO_ERR_INVALID, "bad trajectory shape");
@@ -977,6 +1014,45 @@ int exo_problem_cost_batch_host(exo_problem* p, const double* h_x, int64_t n_tra
         rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
         if (rc != EXO_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+    return EXO_OK;
+}
+
+int exo_problem_cost_jacobian_batch_host(exo_problem* p, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj, double* h_grad)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!h_x || !h_grad) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (layout != EXO_LAYOUT_AOS_ROWMAJOR && layout != EXO_LAYOUT_AOS_COLMAJOR)
+        return fail(EXO_ERR_UNSUPPORTED, "host cost batches take evaluation-major states X[B][T][N]");
+    const int64_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac, T = p->cost.T;
+    // whole trajectories per chunk, ~32 MiB of device-side Phi + J per buffer; Phi and J never leave the device: N doubles per
+    // evaluation (and one cost per trajectory) come back instead of length_jacobian x N
+    int64_t traj_per_chunk = std::max<int64_t>(1, (32ll << 20) / std::max<int64_t>(1, (N + LP + LJ * N) * T * (int64_t)sizeof(double)));
+    if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
+    int rc = ensure_pipeline(p, traj_per_chunk * T, true);
+    if (rc != EXO_OK) return rc;
+    int b = 0;
+    for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
+    {
+        const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
+        cudaStream_t s = p->streams[b];
+        CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
+        rc = launch(p, p->d_x[b], n, n, (int32_t)T, layout, p->d_phi[b], p->d_jac[b], s, false);
+        if (rc != EXO_OK) return rc;
+        if (h_cost_traj)
+        {
+            rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
+            if (rc != EXO_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        rc = exo_problem_cost_jacobian_batch(p, p->d_x[b], p->d_phi[b], p->d_jac[b], nt, layout, p->d_grad[b], s);
+        if (rc != EXO_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_grad + t0 * T * N, p->d_grad[b], n * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
     return EXO_OK;

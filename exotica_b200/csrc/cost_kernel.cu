@@ -40,6 +40,52 @@ __global__ void __launch_bounds__(128) exo_cost_kernel(const __grid_constant__ C
     }
 }
 
+// AbstractTimeIndexedProblem::GetCostJacobian (abstract_time_indexed_problem.cpp:309-318) for every (trajectory, timestep):
+//   grad[t] = 2 ct J[t]^T S[t] ydiff[t] + 2 ct W xdiff[t] - 2 ct W xdiff[t + 1]      (t >= t_first; zero before)
+// and UnconstrainedEndPoseProblem::GetScalarJacobian (unconstrained_end_pose_problem.cpp:84-87) when T = 1.  One lane per
+// evaluation: ydiff (SO(3) log included) goes to shared memory [row][lane], then one pass over the Jacobian (coalesced in SoA).
+__global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_constant__ CostGradParams P)
+{
+    extern __shared__ double yd_s[];  // [length_jac][128]
+    double* yd = yd_s + threadIdx.x;
+    const CostParams& C = P.c;
+    const int N = C.n_ctrl, T = C.T;
+    const int64_t n_evals = C.n_traj * T, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_evals; e += stride)
+    {
+        const int t = (int)(e % T);
+        double* g = P.grad + e * P.g_se;
+        if (t < C.t_first)
+        {
+            for (int n = 0; n < N; ++n) g[n * P.g_sk] = 0.0;
+            continue;
+        }
+        eval_ydiff(C, e, t, yd, 128);
+        const double* rho = C.rho + (int64_t)t * C.n_maps;
+        for (int k = 0; k < C.n_maps; ++k)
+        {
+            const CostMapP& m = C.map[k];
+            for (int i = 0; i < m.length_jacobian; ++i) yd[(m.start_jacobian + i) * 128] *= rho[k];  // S ydiff
+        }
+        const double* J = P.jac + e * P.j_se;
+        const double* x = C.x + e * C.x_se;
+        const double two_ct = 2.0 * C.ct;
+        for (int n = 0; n < N; ++n)
+        {
+            double s = 0.0;
+            for (int r = 0; r < P.length_jac; ++r) s += J[r * P.j_sr + n * P.j_sc] * yd[r * 128];
+            s *= two_ct;
+            if (C.W && t > 0)
+            {
+                const double xn = x[n * C.x_sk];
+                s += two_ct * C.W[n] * (xn - x[n * C.x_sk - C.x_se]);
+                if (t + 1 < T) s -= two_ct * C.W[n] * (x[n * C.x_sk + C.x_se] - xn);
+            }
+            g[n * P.g_sk] = s;
+        }
+    }
+}
+
 // out[b] = min / sum over t in [t_first, T) of in[b * T + t]
 __global__ void __launch_bounds__(128) exo_reduce_kernel(const double* __restrict__ in, int64_t n_traj, int T, int t_first, int op, double* __restrict__ out)
 {
@@ -64,6 +110,22 @@ cudaError_t launch_cost(const CostParams& P, cudaStream_t stream)
     if (P.n_traj <= 0) return cudaSuccess;
     const int64_t blocks = (P.n_traj + 3) / 4;  // 4 warps (trajectories) per CTA
     exo_cost_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cost_gradient(const CostGradParams& P, cudaStream_t stream)
+{
+    const int64_t n_evals = P.c.n_traj * P.c.T;
+    if (n_evals <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(P.length_jac > 0 ? P.length_jac : 1) * 128 * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(exo_cost_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int64_t blocks = (n_evals + 127) / 128;
+    exo_cost_gradient_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, smem, stream>>>(P);
     return cudaGetLastError();
 }
 

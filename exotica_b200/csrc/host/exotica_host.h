@@ -584,6 +584,10 @@ public:
     // NEW: scalar cost of every trajectory (time-indexed: GetCost, abstract_time_indexed_problem.cpp:299-307; end-pose:
     // GetScalarCost, unconstrained_end_pose_problem.cpp:79-82) for X[n_trajectories][T][N]; forward kinematics only.
     void CostBatch(const double* x, int64_t n_trajectories, double* cost);
+    // NEW: gradient of that cost with respect to every state, jacobian[n_trajectories][T][N] (time-indexed: GetCostJacobian,
+    // abstract_time_indexed_problem.cpp:309-318, with a zero row for t = 0; end-pose: GetScalarJacobian,
+    // unconstrained_end_pose_problem.cpp:84-87); cost may be NULL.  Phi and J stay on the device.
+    void CostJacobianBatch(const double* x, int64_t n_trajectories, double* cost, double* jacobian);
     // device variant on the buffers of UpdateBatchDevice; cost_eval (per timestep) may be NULL
     void CostBatchDevice(const double* d_x, const double* d_phi, int64_t n_trajectories, int layout, double* d_cost, double* d_cost_eval, void* stream);
     // NEW: multi-start IK (IKSolver::Solve, exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) from n start states

@@ -457,6 +457,11 @@ int exo_host_problem_cost_batch(exo_host_problem* p, const double* x, int64_t n_
     HOST_TRY(p->problem->CostBatch(x, n_traj, cost))
 }
 
+int exo_host_problem_cost_jacobian_batch(exo_host_problem* p, const double* x, int64_t n_traj, double* cost, double* jacobian)
+{
+    HOST_TRY(p->problem->CostJacobianBatch(x, n_traj, cost, jacobian))
+}
+
 int exo_host_problem_cost_batch_device(exo_host_problem* p, const double* d_x, const double* d_phi, int64_t n_traj, int layout, double* d_cost,
                                        double* d_cost_eval, void* stream)
 {

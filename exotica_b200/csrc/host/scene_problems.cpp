@@ -632,6 +632,13 @@ void PlanningProblem::CostBatch(const double* x, int64_t n_trajectories, double*
     number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
 }
 
+void PlanningProblem::CostJacobianBatch(const double* x, int64_t n_trajectories, double* cost, double* jacobian)
+{
+    PushCost();
+    CheckRc(exo_problem_cost_jacobian_batch_host(GetBackend(), x, n_trajectories, EXO_LAYOUT_AOS_ROWMAJOR, cost, jacobian));
+    number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
+}
+
 namespace
 {
 struct DeviceMem  // RAII over the C-ABI allocator

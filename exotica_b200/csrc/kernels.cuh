@@ -128,7 +128,7 @@ cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream)
 constexpr int COST_MAXMAPS = 16;
 struct CostMapP
 {
-    int32_t kind, start, length, n_frames, rot_type, stride, start_jacobian, pad1;  // stride: Phi entries per frame (EffFrame, EffOrientation)
+    int32_t kind, start, length, n_frames, rot_type, stride, start_jacobian, length_jacobian;  // stride: Phi entries per frame (EffFrame, EffOrientation)
 };
 struct CostParams
 {
@@ -147,6 +147,16 @@ struct CostParams
     CostMapP map[COST_MAXMAPS];
 };
 cudaError_t launch_cost(const CostParams& P, cudaStream_t stream);
+// gradient of the task cost with respect to every state: grad(e, n) at grad[e * g_se + n * g_sk]
+struct CostGradParams
+{
+    CostParams c;
+    const double* jac;
+    double* grad;
+    int64_t j_se, j_sr, j_sc, g_se, g_sk;
+    int32_t length_jac, pad;
+};
+cudaError_t launch_cost_gradient(const CostGradParams& P, cudaStream_t stream);
 // op 0: min, 1: sum over t in [t_first, T) of in[b * T + t]
 cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
 void host_get_rotation(const double* data, int type, double* out9);

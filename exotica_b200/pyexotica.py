@@ -414,6 +414,19 @@ class PlanningProblem(object):
         _check(_host.lib().exo_host_problem_cost_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data))
         return cost
 
+    def cost_jacobian_batch(self, X):
+        """(cost[B], jacobian like X): the gradient of cost_batch with respect to every state.  Time-indexed problems:
+        AbstractTimeIndexedProblem.get_cost_jacobian() of each trajectory reshaped to [T][N] with a zero row for t = 0; end-pose
+        problems: get_scalar_jacobian().  Phi and J stay on the device: N doubles per evaluation come back."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        want = (self.T, self.N) if self.time_indexed else (self.N,)
+        if X.ndim != len(want) + 1 or tuple(X.shape[1:]) != want:
+            raise ExoticaError("Wrong state vector size! Got %s expected (B, %s)" % (X.shape, ", ".join(str(v) for v in want)))
+        cost = np.empty(X.shape[0])
+        jac = np.empty_like(X)
+        _check(_host.lib().exo_host_problem_cost_jacobian_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data, jac.ctypes.data))
+        return cost, jac
+
     def hessian_batch(self, X):
         """exotica.Hessian of every evaluation: X[E][N] -> H[E][length_jacobian][N][N] (KinematicTree::ComputeH and the task maps'
         Hessian overloads)."""

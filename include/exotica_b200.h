@@ -249,6 +249,19 @@ int exo_problem_cost_batch(exo_problem* problem, const double* d_x, const double
 /* Host buffers: X[n_traj][T][N] (evaluation-major) -> cost[n_traj].  Chunked H2D -> forward kinematics + task maps (no
  * Jacobian is computed or moved) -> cost kernel -> D2H of 8 bytes per trajectory; returns when h_cost_traj is complete. */
 int exo_problem_cost_batch_host(exo_problem* problem, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj);
+/* Gradient of the task cost with respect to every state, from Phi and J already on the device (same layout; the gradient has
+ * the shape and layout of d_x): AbstractTimeIndexedProblem::GetCostJacobian with GetScalarTaskJacobian = 2 ct J^T S ydiff
+ * and GetScalarTransitionJacobian = 2 ct W xdiff (abstract_time_indexed_problem.cpp:309-342) --
+ *   grad(b, t) = task(t) + transition(t) - transition(t + 1)   for t >= 1, and grad(b, 0) = 0 (the reference's row vector
+ * starts at t = 1) -- or, for end-pose problems (T = 1), UnconstrainedEndPoseProblem::GetScalarJacobian = 2 J^T S ydiff
+ * (unconstrained_end_pose_problem.cpp:84-87).  N doubles per evaluation leave the device instead of length_jacobian x N. */
+int exo_problem_cost_jacobian_batch(exo_problem* problem, const double* d_x, const double* d_phi, const double* d_jac, int64_t n_traj,
+                                    int32_t layout, double* d_grad, void* stream);
+/* Host buffers, states X[B][T][N] evaluation-major: H2D of the states -> forward kinematics + Jacobians (they stay on the
+ * device) -> cost and cost-gradient kernels -> D2H of h_grad[B][T][N] and, if h_cost_traj is not NULL, one cost per
+ * trajectory.  What a gradient-based solver on the host needs per iteration, at N + 1/T doubles per evaluation over PCIe. */
+int exo_problem_cost_jacobian_batch_host(exo_problem* problem, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj,
+                                         double* h_grad);
 /* New output of SphereCollision (not in the reference): min over all sphere pairs of |p_i - p_j| - r_i - r_j, written per
  * evaluation to d_min_distance[n_evals] by every following exo_problem_update_batch (NULL switches it off). */
 int exo_problem_set_min_distance_output(exo_problem* problem, double* d_min_distance);

@@ -78,6 +78,10 @@ int exo_host_problem_update_batch_device(exo_host_problem* problem, const double
 /* NEW scalar cost of every trajectory: X[n_traj][T][N] (T = 1: X[n_traj][N]) -> cost[n_traj]
  * (GetCost, abstract_time_indexed_problem.cpp:299-307; GetScalarCost, unconstrained_end_pose_problem.cpp:79-82). */
 int exo_host_problem_cost_batch(exo_host_problem* problem, const double* x, int64_t n_traj, double* cost);
+/* NEW gradient of that cost with respect to every state: jacobian[n_traj][T][N], row t = 0 zero (GetCostJacobian,
+ * abstract_time_indexed_problem.cpp:309-318; T = 1: GetScalarJacobian, unconstrained_end_pose_problem.cpp:84-87);
+ * cost[n_traj] may be NULL.  Phi and J stay on the device. */
+int exo_host_problem_cost_jacobian_batch(exo_host_problem* problem, const double* x, int64_t n_traj, double* cost, double* jacobian);
 int exo_host_problem_cost_batch_device(exo_host_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int layout,
                                        double* d_cost, double* d_cost_eval, void* stream);
 /* NEW multi-start IK: IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) from n start states

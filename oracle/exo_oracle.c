@@ -1460,6 +1460,49 @@ double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_f
     return total;
 }
 
+/* AbstractTimeIndexedProblem::GetCostJacobian (abstract_time_indexed_problem.cpp:309-318) with GetScalarTaskJacobian =
+ * 2 ct J^T S ydiff (:326-330) and GetScalarTransitionJacobian = 2 ct W xdiff (:338-342):
+ *   grad[t] = task(t) + transition(t) - transition(t + 1)    for t = 1 .. T-1  (the last timestep has no successor),
+ * written to grad[T][N] with row 0 left at zero (the reference's vector starts at t = 1).  End-pose problems
+ * (UnconstrainedEndPoseProblem::GetScalarJacobian, unconstrained_end_pose_problem.cpp:84-87): T = 1, t_first = 0,
+ * ct = 1, W = NULL -> grad[0] = 2 J^T S ydiff. */
+void exo_oracle_trajectory_cost_jacobian(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
+                                         double ct, const double* W, const double* gen, int n_gen, double* grad)
+{
+    const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
+    double* phi = (double*)malloc((size_t)(lp > 0 ? lp : 1) * sizeof(double));
+    double* jac = (double*)malloc((size_t)(lj > 0 ? lj : 1) * N * sizeof(double));
+    double* yd = (double*)malloc((size_t)(lj > 0 ? lj : 1) * sizeof(double));
+    int t, k, i, g, n;
+    for (i = 0; i < T * N; ++i) grad[i] = 0.0;
+    for (t = t_first; t < T; ++t)
+    {
+        double* gt = grad + (size_t)t * N;
+        if (gen)
+            for (g = 0; g < n_gen; ++g) exo_oracle_set_generated(o, g, gen + ((size_t)t * n_gen + g) * 12);
+        exo_oracle_problem_update(o, X + (size_t)t * N, phi, jac);
+        exo_oracle_problem_ydiff(o, phi, goal + (size_t)(T_goal > 1 ? t : 0) * lp, yd);
+        for (k = 0; k < o->n_maps; ++k)
+        {
+            const taskmap_t* m = &o->maps[k];
+            const double r = rho[(size_t)t * o->n_maps + k];
+            for (i = 0; i < m->length_jacobian; ++i)
+                for (n = 0; n < N; ++n) gt[n] += jac[(size_t)n * lj + (m->start_jacobian + i)] * (r * yd[m->start_jacobian + i]);  /* column-major J */
+        }
+        for (n = 0; n < N; ++n) gt[n] *= 2.0 * ct;
+        if (W && t > 0)
+            for (n = 0; n < N; ++n)
+            {
+                const double tr = 2.0 * ct * W[n] * (X[(size_t)t * N + n] - X[(size_t)(t - 1) * N + n]);
+                gt[n] += tr;
+                if (t > 1) grad[(size_t)(t - 1) * N + n] -= tr;
+            }
+    }
+    free(phi);
+    free(jac);
+    free(yd);
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* Task-map Hessians                                                    */
 /* ------------------------------------------------------------------------------------------- */

@@ -129,6 +129,8 @@ int exo_oracle_get_rotation(const double* data, int type, double* rot9);
 int exo_oracle_problem_ydiff(const exo_oracle* o, const double* phi, const double* goal, double* ydiff);
 double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
                                   double ct, const double* W, const double* gen, int n_gen, double* cost_t);
+void exo_oracle_trajectory_cost_jacobian(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
+                                         double ct, const double* W, const double* gen, int n_gen, double* grad);
 
 /* ---- task-map Hessians: KinematicTree::ComputeH (kinematic_tree.cpp:947-978) + the maps' Hessian
  * overloads + the base-class fallback (task_map.cpp:99-108).  hess[length_jacobian][N][N]. */

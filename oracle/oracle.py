@@ -66,6 +66,9 @@ def lib():
         L.exo_oracle_trajectory_cost.restype = ctypes.c_double
         L.exo_oracle_trajectory_cost.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_double,
                                                  _dp, _dp, ctypes.c_int, _dp]
+        L.exo_oracle_trajectory_cost_jacobian.restype = None
+        L.exo_oracle_trajectory_cost_jacobian.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_double,
+                                                          _dp, _dp, ctypes.c_int, _dp]
         _LIB = L
     return _LIB
 
@@ -328,6 +331,26 @@ class Oracle(object):
         total = lib().exo_oracle_trajectory_cost(self.h, _d(X), T, int(t_first), _d(rho), _d(goal), goal.shape[0], float(ct), Wp, gp, n_gen,
                                                  _d(cost_t))
         return total, cost_t
+
+    def trajectory_cost_jacobian(self, X, rho, goal=None, ct=1.0, W=None, t_first=None, generated=None):
+        """Gradient of trajectory_cost with respect to X as grad[T][N] (AbstractTimeIndexedProblem::GetCostJacobian; row 0 is zero for
+        time-indexed problems; end-pose problems: UnconstrainedEndPoseProblem::GetScalarJacobian)."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.n)
+        T = X.shape[0]
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (T, len(self.maps))))
+        goal = self.zero_goal() if goal is None else goal
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1, self.length_phi)
+        if t_first is None:
+            t_first = 1 if T > 1 else 0
+        n_gen, gp = 0, None
+        if generated is not None:
+            generated = np.ascontiguousarray(generated, dtype=np.float64).reshape(T, -1, 12)
+            n_gen, gp = generated.shape[1], _d(generated)
+        grad = np.zeros((T, self.n))
+        Wp = _d(np.ascontiguousarray(W, dtype=np.float64)) if W is not None else None
+        lib().exo_oracle_trajectory_cost_jacobian(self.h, _d(X), T, int(t_first), _d(rho), _d(goal), goal.shape[0], float(ct), Wp, gp, n_gen,
+                                                  _d(grad))
+        return grad
 
 
 def load_robot(urdf_path, srdf_path, joint_group="", add_collision_elements=False):

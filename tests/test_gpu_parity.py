@@ -403,6 +403,77 @@ def test_end_pose_cost_and_layouts(oracle_lib):
         assert np.array_equal(cost, cost_eval)
 
 
+def _gpu_cost_gradient(prob, X, B, T, rho, goal=None, ct=1.0, W=None, layout=_capi.LAYOUT_SOA):
+    E, N = X.shape
+    LP, LJ = prob.length_phi, prob.length_jacobian
+    dx, dphi, djac, dg = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N))
+    dg.fill_bytes(0xFF)
+    dx.upload(X.T if layout == _capi.LAYOUT_SOA else X)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T, layout=layout)
+    prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
+    prob.cost_jacobian_batch_device(dx.ptr, dphi.ptr, djac.ptr, B, dg.ptr, layout=layout)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    return dg.download((N, E)).T if layout == _capi.LAYOUT_SOA else dg.download((E, N))
+
+
+@pytest.mark.parametrize("layout", [_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR])
+def test_trajectory_cost_jacobian_matches_oracle(oracle_lib, layout):
+    # GetCostJacobian: 2 ct J^T S ydiff + transition terms of t and t + 1, per (trajectory, timestep)
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link"}, {"Link": "lwr_arm_4_link", "LinkOffset": [0, 0, 0.1]}]},
+            {"type": "JointLimit", "SafePercentage": 0.1},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_6_link", "BaseOffset": [0.3, 0.2, 0.4]}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T = 9, 33
+    rng = np.random.default_rng(15)
+    q0 = random_states(orc, B, seed=16)
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+    rho = np.ones((T, 3))
+    rho[:, 0] = np.linspace(0.0, 10.0, T)
+    rho[3, 1] = 0.0
+    rho[:, 2] = 3.0
+    goal = orc.zero_goal()
+    target = oracle_lib.get_frame([0.4, 0.1, 0.6, 0.3, -0.2, 0.5])
+    for f in range(2):
+        goal[f * 7:f * 7 + 3] = target[9:]
+        goal[f * 7 + 3:(f + 1) * 7] = oracle_lib.set_rotation(target[:9], "Quaternion")
+    W = np.linspace(1.0, 2.0, 7)
+    ct = 1.0 / 0.05 / T
+    grad = _gpu_cost_gradient(prob, X.reshape(B * T, 7), B, T, rho, goal=goal, ct=ct, W=W, layout=layout).reshape(B, T, 7)
+    for b in range(B):
+        ref = orc.trajectory_cost_jacobian(X[b], rho, goal=goal, ct=ct, W=W)
+        assert np.max(np.abs(grad[b] - ref)) <= 1e-10 * max(1.0, np.abs(ref).max())
+        assert not grad[b, 0].any()  # the reference's row vector starts at t = 1
+    # the same through the host pipeline: only N doubles per evaluation (and one cost per trajectory) come back
+    cost_h, grad_h = prob.cost_jacobian_batch_host(X)
+    assert np.array_equal(grad_h, grad) or np.max(np.abs(grad_h - grad)) <= 1e-12 * np.abs(grad).max()
+    ref_cost = np.array([orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)[0] for b in range(B)])
+    assert np.max(np.abs(cost_h - ref_cost)) <= 1e-9 * ref_cost.max()
+
+
+def test_end_pose_cost_jacobian_and_finite_differences(oracle_lib):
+    # UnconstrainedEndPoseProblem::GetScalarJacobian = 2 J^T S ydiff; for position-type maps it is the exact gradient of the cost
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_5_link", "BaseOffset": [0.5, 0, 0.3]}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    X = random_states(orc, 300, seed=19)
+    rho = [2.0, 0.5]
+    goal = np.array([0.4, -0.2, 0.7, 0.25])
+    grad = _gpu_cost_gradient(prob, X, 300, 1, rho, goal=goal)
+    ref = np.array([orc.trajectory_cost_jacobian(X[e:e + 1], rho, goal=goal)[0] for e in range(300)])
+    assert np.max(np.abs(grad - ref)) <= 1e-10 * max(1.0, np.abs(ref).max())
+    h = 1e-6
+    for e in range(0, 300, 37):
+        for n in range(7):
+            xp, xm = X[e:e + 1].copy(), X[e:e + 1].copy()
+            xp[0, n] += h
+            xm[0, n] -= h
+            fd = (orc.trajectory_cost(xp, rho, goal=goal)[0] - orc.trajectory_cost(xm, rho, goal=goal)[0]) / (2 * h)
+            assert abs(fd - grad[e, n]) <= 1e-6 * max(1.0, abs(fd))
+
+
 def test_min_sphere_distance_and_trajectory_min(oracle_lib):
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
     maps = _lwr_sphere_maps()

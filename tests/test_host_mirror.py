@@ -124,6 +124,12 @@ def test_time_indexed_problem_trajectories_and_cost(oracle_lib):
     W = np.linspace(1, 7, 7) * 2.0
     ref = np.array([orc.trajectory_cost(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)[0] for b in range(B)])
     assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    # GetCostJacobian of every trajectory (row t = 0 is zero: the reference's vector starts at t = 1)
+    cost2, grad = prob.cost_jacobian_batch(X)
+    assert np.max(np.abs(cost2 - ref)) <= 1e-9 * max(1.0, ref.max()) and grad.shape == X.shape
+    for b in range(B):
+        gref = orc.trajectory_cost_jacobian(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)
+        assert np.max(np.abs(grad[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
     # Update(x, t) of one timestep (abstract_time_indexed_problem.cpp:220-292)
     prob.update(X[2, 7], 7)
     assert max_abs_err(prob.Phi[7], phi_ref[2 * T + 7], angle_entries(maps, orc)) <= 1e-10
