@@ -1,0 +1,125 @@
+#!/usr/bin/env python3
+"""Times the kernels of SURVEY.md section 8 (f) -- task cost, cost gradient, task-map Hessians, batched IK -- and the two
+host-buffer paths of a time-indexed problem (Phi + J back over PCIe vs. cost + gradient back) on BASELINE.json's cfg3
+(LWR, EffFrame + JointLimit, T = 100, 4096 trajectories).
+
+    python tools/bench_next.py [--reps 10]
+
+Device kernels are timed as the mean of `reps` back-to-back launches between two device synchronisations (wall clock; every
+launch is > 50 us of work); host paths by wall clock around the blocking call on pinned-free numpy buffers.  One JSON line each.
+Parity for all of them is covered by tests/; this script only measures.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import exotica_b200 as exo  # noqa: E402
+from exotica_b200 import _capi, _host  # noqa: E402
+from bench_configs import cfg3, frame, scene  # noqa: E402
+
+
+def sync():
+    _capi.check(_capi.lib().exo_device_synchronize())
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    sync()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    peak = 6549.4
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        pass
+
+    init, E, _ = cfg3()
+    prob = exo.Setup.create_problem(init)
+    N, LP, LJ, T = prob.N, prob.length_Phi, prob.length_jacobian, prob.T
+    B = E // T
+    lim = prob.get_scene().get_kinematic_tree().get_joint_limits()
+    rng = np.random.default_rng(7)
+    q0 = rng.uniform(lim[:, 0], lim[:, 1], size=(B, 1, N))
+    X = np.clip(q0 + np.cumsum(rng.normal(0, 0.02, size=(B, T, N)), axis=1), lim[:, 0], lim[:, 1])
+    backend = _capi.Problem.__new__(_capi.Problem)
+    backend.h = _host.lib().exo_host_problem_backend(prob._h)
+    dx, dphi, djac, dg, dc = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N, B))
+    dx.upload(X.reshape(E, N).T)
+    prob.cost_batch(X[:2])  # pushes rho / goal / W of the XML-style initializer to the device
+
+    def line(name, ms, units, unit, bytes_per_unit=None, **kw):
+        d = {"bench": name, "ms": ms, "units": units, unit + "_per_s": units / (ms * 1e-3)}
+        if bytes_per_unit:
+            d["algorithmic_GBps"] = bytes_per_unit * units / (ms * 1e-3) / 1e9
+            d["frac_of_measured_hbm"] = d["algorithmic_GBps"] / peak
+        d.update(kw)
+        print(json.dumps(d), flush=True)
+
+    ms = timed(lambda: prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=exo.LAYOUT_SOA), args.reps)
+    line("update_batch (FK + J), device", ms, E, "evals", 8 * (N + LP + LJ * N))
+    ms = timed(lambda: backend.cost_batch_device(dx.ptr, dphi.ptr, B, dc.ptr, None), args.reps)
+    line("cost kernel (reads x, Phi), device", ms, E, "evals", 8 * (N + LP))
+    ms = timed(lambda: backend.cost_jacobian_batch_device(dx.ptr, dphi.ptr, djac.ptr, B, dg.ptr), args.reps)
+    line("cost-gradient kernel (reads x, Phi, J; writes N per eval), device", ms, E, "evals", 8 * (2 * N + LP + LJ * N))
+
+    # Hessians: length_jacobian x N x N doubles per evaluation
+    EH = 1 << 16
+    dh = _capi.DeviceBuffer(EH * LJ * N * N)
+    ms = timed(lambda: backend.hessian_batch_device(dx.ptr, djac.ptr, EH, dh.ptr, T=1), max(3, args.reps // 2))
+    line("task-map Hessians (raw-frame update + Hessian kernel), device", ms, EH, "evals", 8 * (LJ * N * N + LJ * N + N))
+    dh.free()
+
+    # host-buffer paths of the same problem
+    t0 = time.perf_counter()
+    prob.update_batch(X)
+    t1 = time.perf_counter()
+    prob.update_batch(X)
+    t2 = time.perf_counter()
+    line("host path: X in, Phi + J out", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * E * (LP + LJ * N), first_call_ms=(t1 - t0) * 1e3)
+    prob.cost_jacobian_batch(X)
+    t1 = time.perf_counter()
+    prob.cost_jacobian_batch(X)
+    t2 = time.perf_counter()
+    line("host path: X in, cost + gradient out (Phi, J stay in HBM)", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * (E * N + B))
+    prob.cost_batch(X)
+    t1 = time.perf_counter()
+    prob.cost_batch(X)
+    t2 = time.perf_counter()
+    line("host path: X in, cost out (FK only)", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * B)
+
+    # multi-start IK on example_ik.xml's problem shape
+    maps = [("exotica/EffFrame", {"Name": "Eff", "EndEffector": [frame("lwr_arm_6_link")]})]
+    ik_init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "ik", "PlanningScene": scene("lwr_simplified", "arm"), "Maps": maps,
+                                                       "Cost": [("exotica/Task", {"Task": "Eff", "Goal": "0.4 0.1 0.6 0 0 0"})]})
+    ikp = exo.Setup.create_problem(ik_init)
+    solver = exo.IKSolver({"MaxIterations": 100})
+    solver.specify_problem(ikp)
+    Q0 = rng.uniform(lim[:, 0], lim[:, 1], size=(1 << 16, N))
+    solver.solve_batch(Q0[:1024])
+    t1 = time.perf_counter()
+    Q, cost, it, term = solver.solve_batch(Q0)
+    t2 = time.perf_counter()
+    line("batched IK (host call, 65536 starts, <= 100 iterations)", (t2 - t1) * 1e3, Q0.shape[0], "solves", None,
+         mean_iterations=float(it.mean()), converged=float((cost < 1e-8).mean()))
+
+
+if __name__ == "__main__":
+    main()
