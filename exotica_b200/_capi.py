@@ -91,6 +91,7 @@ SYMBOLS = [
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_problem_cost_jacobian_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
+    ("exo_problem_cost_gradient_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_jacobian_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
     ("exo_problem_ik_solve_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(IkParams), _vp, _vp, _vp, _vp]),
@@ -365,6 +366,9 @@ class Problem(object):
 
     def cost_jacobian_batch_device(self, d_x, d_phi, d_jac, n_traj, d_grad, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_jacobian_batch(self.h, d_x, d_phi, d_jac, int(n_traj), int(layout), d_grad, stream))
+
+    def cost_gradient_batch_device(self, d_x, n_traj, d_grad, d_cost_traj=None, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_cost_gradient_batch(self.h, d_x, int(n_traj), int(layout), d_cost_traj, d_grad, stream))
 
     def cost_jacobian_batch_host(self, X, with_cost=True):
         """X[B][T][N] (or [B][N] for end-pose problems) -> (cost[B] or None, grad like X) through the host pipeline; Phi and J

@@ -66,6 +66,9 @@ struct exo_problem
     int32_t* d_ik_i = nullptr;  // ints: active, ls_done, n_active
     int64_t ik_capacity = 0;
     std::vector<double> cost_rho_t0;  // rho of every map at t = 0 (IK uses end-pose problems)
+    std::vector<double> cost_rho;     // host copy of rho[T][n_maps] (eligibility of the fused cost-gradient kernel)
+    double* d_cg = nullptr;           // scratch of exo_problem_cost_gradient_batch: per-evaluation costs (+ Phi, J when not fused)
+    int64_t cg_bytes = 0;
     std::vector<double> cost_W;
     // auxiliary outputs and the task cost (rows e / f1)
     double* d_min_dist = nullptr;  // caller-owned, [n_evals] (exo_problem_set_min_distance_output)
@@ -340,6 +343,7 @@ int exo_problem_destroy(exo_problem* p)
     if (p->d_ik_i) cudaFree(p->d_ik_i);
     for (auto& sd : p->sph_dumps)
         if (sd.d) cudaFree(sd.d);
+    if (p->d_cg) cudaFree(p->d_cg);
     if (p->shadow) exo_problem_destroy(p->shadow);
     if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
     if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
@@ -907,6 +911,7 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
     if (rc == EXO_OK) rc = upload(&p->d_W, d->W, d->W ? (size_t)N : 0);
     if (rc != EXO_OK) return rc;
     p->cost_rho_t0.assign(d->rho, d->rho + n_maps);
+    p->cost_rho.assign(d->rho, d->rho + (size_t)d->T * n_maps);
     p->cost_W.clear();
     if (d->W) p->cost_W.assign(d->W, d->W + N);
     c.rho = p->d_rho;
@@ -976,6 +981,121 @@ int exo_problem_cost_jacobian_batch(exo_problem* p, const double* d_x, const dou
     return EXO_OK;
 }
 
+// Can exo_chain_costgrad_kernel serve this problem and cost?  Fills the per-frame map / goal-rotation indices if so.
+static bool fused_costgrad_eligible(exo_problem* p, ChainGradParams& g)
+{
+    if (!p->chain_ok || p->kernel_choice == 1) return false;
+    const ChainParams& P = p->chain;
+    const CostParams& c = p->cost;
+    std::vector<char> covered(p->maps.size(), 0);
+    g.jl_map = -1;
+    for (int f = 0; f < P.n_frames; ++f)
+    {
+        const ChainFrameP& fp = P.frame[f];
+        if (fp.row_mode > ROWS_V) return false;
+        int k_of = -1, rot = 0;
+        for (int k = 0; k < c.n_maps && k_of < 0; ++k)
+        {
+            const CostMapP& m = c.map[k];
+            const bool lie = m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION;
+            if (fp.phi_off >= m.start && fp.phi_off < m.start + m.length)
+            {
+                if (m.kind != EXO_MAP_EFF_FRAME && m.kind != EXO_MAP_EFF_POSITION) return false;
+                k_of = k;
+                g.frame_rot[f] = m.kind == EXO_MAP_EFF_FRAME ? rot + (fp.phi_off - m.start) / m.stride : -1;
+            }
+            else if (lie)
+                rot += m.n_frames;
+        }
+        if (k_of < 0) return false;
+        g.frame_map[f] = k_of;
+        covered[k_of] = 1;
+    }
+    for (int k = 0; k < c.n_maps; ++k)
+    {
+        if (covered[k]) continue;
+        if (c.map[k].kind == EXO_MAP_JOINT_LIMIT && P.jl_enabled && c.map[k].start == P.jl_phi_off && g.jl_map < 0)
+        {
+            g.jl_map = k;
+            continue;
+        }
+        // anything else (unused maps filled with their SetZero values) must not carry a cost
+        for (int t = 0; t < c.T; ++t)
+            if (p->cost_rho[(size_t)t * c.n_maps + k] != 0.0) return false;
+    }
+    return true;
+}
+
+int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj, double* d_grad, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_x || !d_grad) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (p->compiled_version != p->tree->version)
+    {
+        int rc = compile_and_upload(p);
+        if (rc != EXO_OK) return rc;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t T = p->cost.T, E = n_traj * T;
+    const int64_t N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
+    if (p->prog.hdr.n_generated > 0 && T != p->T) return fail(EXO_ERR_INVALID, "T of the cost does not match exo_problem_set_generated");
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    int rc = fill_strides(p, layout, E, k);
+    if (rc != EXO_OK) return rc;
+    ChainGradParams g;
+    memset(&g, 0, sizeof(g));
+    const bool fused = fused_costgrad_eligible(p, g);
+    const int64_t need = (E + (fused ? 0 : E * (LP + LJ * N))) * (int64_t)sizeof(double);
+    if (p->cg_bytes < need)
+    {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (p->d_cg) CUDA_TRY(cudaFree(p->d_cg));
+        p->d_cg = nullptr;
+        p->cg_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&p->d_cg, (size_t)need));
+        p->cg_bytes = need;
+    }
+    double* d_cost_eval = p->d_cg;
+    if (fused)
+    {
+        const CostParams& c = p->cost;
+        g.rho = c.rho; g.goal = c.goal; g.goal_rot = c.goal_rot; g.W = c.W;
+        g.grad = d_grad;
+        g.cost_eval = d_cost_traj ? d_cost_eval : nullptr;
+        g.ct = c.ct;
+        g.g_se = k.x_se; g.g_sk = k.x_sk;
+        g.T = c.T; g.t_first = c.t_first; g.T_goal = c.T_goal; g.n_maps = c.n_maps; g.length_phi = c.length_phi; g.n_rot = c.n_rot;
+        chain_bind(p->chain, d_x, nullptr, nullptr, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
+        cudaError_t e = chain_costgrad_launch(p->chain, g, s);
+        if (e != cudaSuccess) return cuda_fail(e, "fused cost-gradient kernel launch");
+        p->launches++;
+        if (d_cost_traj)
+        {
+            e = launch_reduce(d_cost_eval, n_traj, (int)T, 0, 1, d_cost_traj, s);
+            if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+            p->launches++;
+        }
+        p->last_kernel = "exo_chain_costgrad_kernel";
+        return EXO_OK;
+    }
+    // general programs: Phi and J into the scratch buffer, then the cost and cost-gradient kernels
+    double* d_phi = p->d_cg + E;
+    double* d_jac = d_phi + E * LP;
+    rc = launch(p, d_x, E, E, (int32_t)T, layout, d_phi, d_jac, s, false);
+    if (rc != EXO_OK) return rc;
+    if (d_cost_traj)
+    {
+        rc = exo_problem_cost_batch(p, d_x, d_phi, n_traj, layout, d_cost_traj, nullptr, stream);
+        if (rc != EXO_OK) return rc;
+    }
+    return exo_problem_cost_jacobian_batch(p, d_x, d_phi, d_jac, n_traj, layout, d_grad, stream);
+}
+
 int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream)
 {
     if (n_traj < 0 || T < 1 || t_first < 0 || t_first >= T) return fail(EXO_ERR_INVALID, "bad trajectory shape");
@@ -1034,27 +1154,26 @@ int exo_problem_cost_jacobian_batch_host(exo_problem* p, const double* h_x, int6
     // evaluation (and one cost per trajectory) come back instead of length_jacobian x N
     int64_t traj_per_chunk = std::max<int64_t>(1, (32ll << 20) / std::max<int64_t>(1, (N + LP + LJ * N) * T * (int64_t)sizeof(double)));
     if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
-    int rc = ensure_pipeline(p, traj_per_chunk * T, true);
+    int rc = ensure_pipeline(p, traj_per_chunk * T, false);
     if (rc != EXO_OK) return rc;
+    cudaEvent_t prev_done = nullptr;
     int b = 0;
     for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
     {
         const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
         cudaStream_t s = p->streams[b];
         CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        rc = launch(p, p->d_x[b], n, n, (int32_t)T, layout, p->d_phi[b], p->d_jac[b], s, false);
+        // NOTE: one scratch buffer per problem: the chunks' kernels are serialised on it through events below
+        if (prev_done) CUDA_TRY(cudaStreamWaitEvent(s, prev_done, 0));
+        rc = exo_problem_cost_gradient_batch(p, p->d_x[b], nt, layout, h_cost_traj ? p->d_cost[b] : nullptr, p->d_grad[b], s);
         if (rc != EXO_OK) return rc;
-        if (h_cost_traj)
-        {
-            rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
-            if (rc != EXO_OK) return rc;
-            CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
-        }
-        rc = exo_problem_cost_jacobian_batch(p, p->d_x[b], p->d_phi[b], p->d_jac[b], nt, layout, p->d_grad[b], s);
-        if (rc != EXO_OK) return rc;
+        if (!prev_done) CUDA_TRY(cudaEventCreateWithFlags(&prev_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(prev_done, s));
+        if (h_cost_traj) CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(h_grad + t0 * T * N, p->d_grad[b], n * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+    if (prev_done) cudaEventDestroy(prev_done);
     return EXO_OK;
 }
 

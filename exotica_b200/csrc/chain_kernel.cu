@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include "compiler.h"
+#include "cost_device.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
 
@@ -546,6 +547,218 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
     }
 }
 
+// ---- fused forward kinematics + task cost + cost gradient --------------------------------------------------------------------
+// grad[e][n] = 2 ct ( J^T S ydiff )[n] + 2 ct W (xdiff[t] - xdiff[t+1])[n]   (AbstractTimeIndexedProblem::GetCostJacobian,
+// abstract_time_indexed_problem.cpp:309-342; T = 1: UnconstrainedEndPoseProblem::GetScalarJacobian) without ever materialising
+// J: every joint's column (KinematicTree::ComputeJ) is dotted with S ydiff of its frame the moment it exists.  For a frame with
+// a constant base, column = Binv [v; w], so the dot product is taken against Binv^T (S ydiff) instead -- one 3x3 product per frame,
+// not per column.  HBM traffic per evaluation: N doubles in (+ 2 N neighbours from L2 for the transition term), N + 1 out.
+template <int J, bool ALLREV>
+__device__ __forceinline__ double chain_dot(const ChainParams& P, double wx, double wy, double wz, double px, double py, double pz, double ax, double ay,
+                                            double az, const double (&yd)[6], bool six)
+{
+    const ChainJointP& jp = P.joint[J];
+    if (jp.col < 0) return 0.0;
+    if (!ALLREV && jp.prismatic) return wx * yd[0] + wy * yd[1] + wz * yd[2];
+    const double dx = ax - px, dy = ay - py, dz = az - pz;
+    double s = (wy * dz - wz * dy) * yd[0] + (wz * dx - wx * dz) * yd[1] + (wx * dy - wy * dx) * yd[2];
+    if (six) s += wx * yd[3] + wy * yd[4] + wz * yd[5];
+    return s;
+}
+
+template <int NJ, bool ALLREV, int J>
+struct ChainDots
+{
+    static __device__ __forceinline__ void run(const ChainParams& P, const double (&W)[NJ][3], const double (&PJ)[NJ][3], double ax, double ay, double az,
+                                               const double (&yd)[6], bool six, double (&g)[NJ])
+    {
+        g[J] += chain_dot<J, ALLREV>(P, W[J][0], W[J][1], W[J][2], PJ[J][0], PJ[J][1], PJ[J][2], ax, ay, az, yd, six);
+        ChainDots<NJ, ALLREV, J + 1>::run(P, W, PJ, ax, ay, az, yd, six, g);
+    }
+};
+template <int NJ, bool ALLREV>
+struct ChainDots<NJ, ALLREV, NJ>
+{
+    static __device__ __forceinline__ void run(const ChainParams&, const double (&)[NJ][3], const double (&)[NJ][3], double, double, double,
+                                               const double (&)[6], bool, double (&)[NJ]) {}
+};
+
+// JointLimit and transition terms of column n (both diagonal in the joint index): returns their share of the gradient before
+// the factor 2 ct and adds their share of the cost to c
+__device__ __forceinline__ double costgrad_column_extra(const ChainParams& P, const ChainGradParams& G, const char* xe, int t, int n, double rho_jl,
+                                                        const double* goal, double& c)
+{
+    const double xn = *reinterpret_cast<const double*>(xe + (int64_t)n * P.x_sk * 8);
+    double s = 0.0;
+    if (P.jl_enabled && G.jl_map >= 0)
+    {
+        const double lo_t = P.jl_lo_tau[n], hi_t = P.jl_hi_tau[n];
+        double v = 0.0;
+        if (xn < lo_t) v = xn - P.jl_lo[n] - P.jl_tau[n];
+        if (xn > hi_t) v = xn - P.jl_hi[n] + P.jl_tau[n];
+        const double yd = v - goal[P.jl_phi_off + n];
+        c += rho_jl * yd * yd;
+        if (!(xn >= lo_t && xn <= hi_t)) s += rho_jl * yd;
+    }
+    if (G.W && t > 0)
+    {
+        const double w = G.W[n];
+        const double d0 = xn - *reinterpret_cast<const double*>(xe + (int64_t)n * P.x_sk * 8 - P.x_se_b);
+        c += w * d0 * d0;
+        s += w * d0;
+        if (t + 1 < G.T) s -= w * (*reinterpret_cast<const double*>(xe + (int64_t)n * P.x_sk * 8 + P.x_se_b) - xn);
+    }
+    return s;
+}
+
+template <int NJ, bool ALLREV, int J>
+struct ChainGradStore
+{
+    static __device__ __forceinline__ void run(const ChainParams& P, const ChainGradParams& G, const char* xe, int t, double rho_jl, const double* goal,
+                                               const double (&g)[NJ], double* ge, double& c)
+    {
+        const int n = P.joint[J].col;
+        if (n >= 0) ge[(int64_t)n * G.g_sk] = 2.0 * G.ct * (g[J] + costgrad_column_extra(P, G, xe, t, n, rho_jl, goal, c));
+        ChainGradStore<NJ, ALLREV, J + 1>::run(P, G, xe, t, rho_jl, goal, g, ge, c);
+    }
+};
+template <int NJ, bool ALLREV>
+struct ChainGradStore<NJ, ALLREV, NJ>
+{
+    static __device__ __forceinline__ void run(const ChainParams&, const ChainGradParams&, const char*, int, double, const double*, const double (&)[NJ],
+                                               double*, double&) {}
+};
+
+#ifndef EXO_COSTGRAD_MAXNREG
+#define EXO_COSTGRAD_MAXNREG 168
+#endif
+template <int NJ, bool ALLREV>
+__global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G)
+{
+    const int64_t stride = (int64_t)gridDim.x * CTPB;
+    for (int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x; e < P.n_evals; e += stride)
+    {
+        const char* xe = reinterpret_cast<const char*>(P.x) + e * P.x_se_b;
+        double* ge = G.grad + e * G.g_se;
+        const int t = (int)(e % G.T);
+        if (t < G.t_first)
+        {
+            for (int n = 0; n < P.n_ctrl; ++n) ge[(int64_t)n * G.g_sk] = 0.0;
+            if (G.cost_eval) G.cost_eval[e] = 0.0;
+            continue;
+        }
+        double q[NJ], sn[NJ], cs[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+        {
+            const double th = fma(P.joint[j].qmult, q[j], P.joint[j].th0);
+            sn[j] = 0.0;
+            cs[j] = 1.0;
+            if (ALLREV || !P.joint[j].prismatic)
+            {
+                if (fabs(th) <= 1.0e5)
+                    fast_sincos(th, sn[j], cs[j]);
+                else
+                    sincos(th, &sn[j], &cs[j]);
+            }
+        }
+        Fr cur = load_frame(P.base);
+        double W[NJ][3], PJ[NJ][3];
+        ChainUnroll<NJ, ALLREV, 0>::record(P, cur, q, sn, cs, W, PJ);
+        const double* rho = G.rho + (int64_t)t * G.n_maps;
+        const int tg = G.T_goal > 1 ? t : 0;
+        const double* goal = G.goal + (int64_t)tg * G.length_phi;
+        const double* grot = G.goal_rot + (int64_t)tg * G.n_rot * 9;
+        double g[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) g[j] = 0.0;
+        double c = 0.0;
+        for (int f = 0; f < P.n_frames; ++f)
+        {
+            const ChainFrameP& fp = P.frame[f];
+            const Fr A = chain_frame_a(fp, cur);
+            const Fr Ph = fp.b_const ? fr_mul(load_frame(fp.binv), A) : A;
+            const double r = rho[G.frame_map[f]];
+            const double* gl = goal + fp.phi_off;
+            double yd[6];
+            yd[0] = Ph.x - gl[0];
+            yd[1] = Ph.y - gl[1];
+            yd[2] = Ph.z - gl[2];
+            yd[3] = yd[4] = yd[5] = 0.0;
+            const bool six = G.frame_rot[f] >= 0;
+            if (six)
+            {
+                // rotvec = M1 * (M2^-1 M1).GetRot()  (TaskSpaceVector::operator-, task_space_vector.cpp:64-91)
+                const double* M2 = grot + 9 * G.frame_rot[f];
+                Fr M;
+                M.m0 = M2[0] * Ph.m0 + M2[3] * Ph.m3 + M2[6] * Ph.m6;
+                M.m1 = M2[0] * Ph.m1 + M2[3] * Ph.m4 + M2[6] * Ph.m7;
+                M.m2 = M2[0] * Ph.m2 + M2[3] * Ph.m5 + M2[6] * Ph.m8;
+                M.m3 = M2[1] * Ph.m0 + M2[4] * Ph.m3 + M2[7] * Ph.m6;
+                M.m4 = M2[1] * Ph.m1 + M2[4] * Ph.m4 + M2[7] * Ph.m7;
+                M.m5 = M2[1] * Ph.m2 + M2[4] * Ph.m5 + M2[7] * Ph.m8;
+                M.m6 = M2[2] * Ph.m0 + M2[5] * Ph.m3 + M2[8] * Ph.m6;
+                M.m7 = M2[2] * Ph.m1 + M2[5] * Ph.m4 + M2[8] * Ph.m7;
+                M.m8 = M2[2] * Ph.m2 + M2[5] * Ph.m5 + M2[8] * Ph.m8;
+                M.x = M.y = M.z = 0.0;
+                double vx, vy, vz;
+                get_angle_axis(M, vx, vy, vz);
+                yd[3] = Ph.m0 * vx + Ph.m1 * vy + Ph.m2 * vz;
+                yd[4] = Ph.m3 * vx + Ph.m4 * vy + Ph.m5 * vz;
+                yd[5] = Ph.m6 * vx + Ph.m7 * vy + Ph.m8 * vz;
+            }
+            c += r * (yd[0] * yd[0] + yd[1] * yd[1] + yd[2] * yd[2] + yd[3] * yd[3] + yd[4] * yd[4] + yd[5] * yd[5]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) yd[k] *= r;  // S ydiff
+            if (fp.b_const)
+            {
+                // column = Binv [v; w]  ->  dot against Binv^T (S ydiff)
+                const double a0 = fp.binv[0] * yd[0] + fp.binv[3] * yd[1] + fp.binv[6] * yd[2];
+                const double a1 = fp.binv[1] * yd[0] + fp.binv[4] * yd[1] + fp.binv[7] * yd[2];
+                const double a2 = fp.binv[2] * yd[0] + fp.binv[5] * yd[1] + fp.binv[8] * yd[2];
+                const double b0 = fp.binv[0] * yd[3] + fp.binv[3] * yd[4] + fp.binv[6] * yd[5];
+                const double b1 = fp.binv[1] * yd[3] + fp.binv[4] * yd[4] + fp.binv[7] * yd[5];
+                const double b2 = fp.binv[2] * yd[3] + fp.binv[5] * yd[4] + fp.binv[8] * yd[5];
+                yd[0] = a0; yd[1] = a1; yd[2] = a2; yd[3] = b0; yd[4] = b1; yd[5] = b2;
+            }
+            ChainDots<NJ, ALLREV, 0>::run(P, W, PJ, A.x, A.y, A.z, yd, six, g);
+        }
+        const double rho_jl = G.jl_map >= 0 ? rho[G.jl_map] : 0.0;
+        ChainGradStore<NJ, ALLREV, 0>::run(P, G, xe, t, rho_jl, goal, g, ge, c);
+        // columns no joint of the chain owns: JointLimit and transition terms only
+        for (int n = 0; n < P.n_ctrl; ++n)
+            if ((P.zero_cols >> n) & 1u) ge[(int64_t)n * G.g_sk] = 2.0 * G.ct * costgrad_column_extra(P, G, xe, t, n, rho_jl, goal, c);
+        if (G.cost_eval) G.cost_eval[e] = G.ct * c;
+    }
+}
+
+template <int NJ, bool ALLREV>
+cudaError_t chain_costgrad_launch_t(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    const int64_t want = (P.n_evals + CTPB - 1) / CTPB;
+    exo_chain_costgrad_kernel<NJ, ALLREV><<<(int)(want < (1 << 20) ? (want > 0 ? want : 1) : (1 << 20)), CTPB, 0, stream>>>(P, G);
+    return cudaGetLastError();
+}
+
+template <bool ALLREV>
+cudaError_t chain_costgrad_launch_nj(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    switch (P.n_joints)
+    {
+        case 1: return chain_costgrad_launch_t<1, ALLREV>(P, G, stream);
+        case 2: return chain_costgrad_launch_t<2, ALLREV>(P, G, stream);
+        case 3: return chain_costgrad_launch_t<3, ALLREV>(P, G, stream);
+        case 4: return chain_costgrad_launch_t<4, ALLREV>(P, G, stream);
+        case 5: return chain_costgrad_launch_t<5, ALLREV>(P, G, stream);
+        case 6: return chain_costgrad_launch_t<6, ALLREV>(P, G, stream);
+        case 7: return chain_costgrad_launch_t<7, ALLREV>(P, G, stream);
+        case 8: return chain_costgrad_launch_t<8, ALLREV>(P, G, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
 // Grid size in units of "resident CTAs per GPU" (tuning knob EXO_CHAIN_WAVES).  Measured on B200 (cfg2a, 2^20 evaluations):
 // 1 generation (persistent, static grid-stride split) 98.6 us, 4 generations 90.1 us, 8 generations 88.2 us, and one CTA per
 // 64 evaluations -- the default -- 84.8 us once every CTA pulls the joint values of the CTA 3/4 of a generation behind it
@@ -638,6 +851,11 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
         for (int j = 0; j < P.n_joints; ++j)
             P.jf_byte_off[f][j] = (P.frame[f].jrow_off * j_sr + (P.joint[j].col >= 0 ? P.joint[j].col : 0) * j_sc) * 8;
     }
+}
+
+cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    return P.all_revolute ? chain_costgrad_launch_nj<true>(P, G, stream) : chain_costgrad_launch_nj<false>(P, G, stream);
 }
 
 cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream)

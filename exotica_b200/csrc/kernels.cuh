@@ -124,6 +124,25 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
                 int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
 cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream);
 
+// Fused forward kinematics + task cost + cost gradient for chain programs (exo_chain_costgrad_kernel): Phi and J are formed in
+// registers and contracted on the spot, only N doubles per evaluation (and its cost) reach HBM.
+struct ChainGradParams
+{
+    const double* rho;       // device, [T][n_maps]
+    const double* goal;      // device, [T_goal][length_phi]
+    const double* goal_rot;  // device, [T_goal][n_rot][9]
+    const double* W;         // device, [n_ctrl] or NULL
+    double* grad;            // gradient of evaluation e, entry n at grad[e * g_se + n * g_sk]
+    double* cost_eval;       // [n_evals] or NULL
+    double ct;
+    int64_t g_se, g_sk;
+    int32_t T, t_first, T_goal, n_maps, length_phi, n_rot;
+    int32_t jl_map, pad;               // map index of the JointLimit map or -1
+    int32_t frame_map[CH_MAXF];        // map index of every requested frame (its rho)
+    int32_t frame_rot[CH_MAXF];        // index into goal_rot, or -1 for position-only frames (EffPosition)
+};
+cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream);
+
 // ---- batched task cost and per-trajectory reductions (cost_kernel.cu) -------------------------------------------------
 constexpr int COST_MAXMAPS = 16;
 struct CostMapP

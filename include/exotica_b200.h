@@ -257,6 +257,14 @@ int exo_problem_cost_batch_host(exo_problem* problem, const double* h_x, int64_t
  * (unconstrained_end_pose_problem.cpp:84-87).  N doubles per evaluation leave the device instead of length_jacobian x N. */
 int exo_problem_cost_jacobian_batch(exo_problem* problem, const double* d_x, const double* d_phi, const double* d_jac, int64_t n_traj,
                                     int32_t layout, double* d_grad, void* stream);
+/* States in, cost and gradient out: d_cost_traj[n_traj] (may be NULL) and d_grad (shape and layout of d_x) as the two calls
+ * above define them, without caller-side Phi / J buffers.  Serial-chain programs whose cost is made of EffFrame / EffPosition /
+ * JointLimit maps run ONE fused kernel (exo_chain_costgrad_kernel): forward kinematics, ydiff with its SO(3) log, and every
+ * Jacobian column dotted with S ydiff the moment it exists -- J is never materialised, N + 1 doubles per evaluation reach
+ * HBM instead of (1 + N) x length_jacobian.  Other programs go through an internal scratch buffer and the three kernels
+ * (exo_problem_set_kernel(1) forces that path; tests compare the two).  Calls on one problem must be serialised. */
+int exo_problem_cost_gradient_batch(exo_problem* problem, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj,
+                                    double* d_grad, void* stream);
 /* Host buffers, states X[B][T][N] evaluation-major: H2D of the states -> forward kinematics + Jacobians (they stay on the
  * device) -> cost and cost-gradient kernels -> D2H of h_grad[B][T][N] and, if h_cost_traj is not NULL, one cost per
  * trajectory.  What a gradient-based solver on the host needs per iteration, at N + 1/T doubles per evaluation over PCIe. */

@@ -452,6 +452,77 @@ def test_trajectory_cost_jacobian_matches_oracle(oracle_lib, layout):
     assert np.max(np.abs(cost_h - ref_cost)) <= 1e-9 * ref_cost.max()
 
 
+def _gpu_cost_gradient_fused(prob, X, B, T, layout=_capi.LAYOUT_SOA):
+    E, N = X.shape
+    dx, dg, dc = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(B)
+    dg.fill_bytes(0xFF)
+    dx.upload(X.T if layout == _capi.LAYOUT_SOA else X)
+    prob.cost_gradient_batch_device(dx.ptr, B, dg.ptr, dc.ptr, layout=layout)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    grad = dg.download((N, E)).T if layout == _capi.LAYOUT_SOA else dg.download((E, N))
+    return dc.download((B,)), np.ascontiguousarray(grad)
+
+
+@pytest.mark.parametrize("case", ["frame+limit", "base+position", "unused", "end-pose"])
+def test_fused_cost_gradient_kernel(oracle_lib, case):
+    # states in, cost + gradient out: the fused chain kernel (J never reaches HBM) against the oracle and the three-kernel path
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    T = 25
+    if case == "frame+limit":
+        maps = [{"type": "EffFrame", "Type": "RPY", "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0.05, 0, 0.1, 0.9, 0.1, 0.2, 0.3]}]},
+                {"type": "JointLimit", "SafePercentage": 0.2}]
+        rho = np.ones((T, 2)) * [3.0, 50.0]
+        rho[:, 0] = np.linspace(0.0, 5.0, T)
+    elif case == "base+position":
+        maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link", "BaseOffset": [0.1, 0.2, 0.3, 0.5, 0.5, 0.5, 0.5]}]},
+                {"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0, 0.1, 0]}]}]
+        rho = np.ones((T, 2)) * [1.0, 7.0]
+    elif case == "unused":
+        maps = [{"type": "JointLimit", "SafePercentage": 0.1},
+                {"type": "EffFrame", "Type": "ZYX", "used": False, "EndEffector": [{"Link": "lwr_arm_5_link"}]},
+                {"type": "EffFrame", "Type": "AngleAxis", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+        rho = np.ones((T, 3)) * [10.0, 0.0, 2.0]
+    else:
+        T = 1
+        maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+        rho = np.array([[4.0]])
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B = 17 if T > 1 else 700
+    rng = np.random.default_rng(21)
+    q0 = random_states(orc, B, seed=22)
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+    goal = orc.zero_goal()
+    target = oracle_lib.get_frame([0.4, 0.1, 0.6, 0.3, -0.2, 0.5])
+    for k, spec in enumerate(maps):
+        start, length = prob.map_indexing(k)[:2]
+        if spec["type"] == "EffFrame":
+            goal[start:start + 3] = target[9:]
+            goal[start + 3:start + length] = oracle_lib.set_rotation(target[:9], spec.get("Type", "RPY"))
+        elif spec["type"] == "EffPosition":
+            goal[start:start + 3] = [0.3, -0.2, 0.8]
+    W = np.linspace(1.0, 2.0, 7) if T > 1 else None
+    ct = 1.0 / 0.05 / T if T > 1 else 1.0
+    prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
+    results = {}
+    for choice, name in ((0, "exo_chain_costgrad_kernel"), (1, "exo_cost_gradient_kernel")):
+        prob.set_kernel(choice)
+        for layout in (_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR):
+            cost, grad = _gpu_cost_gradient_fused(prob, X.reshape(B * T, 7), B, T, layout=layout)
+            assert prob.last_kernel() == name
+            results[(choice, layout)] = (cost, grad)
+            grad = grad.reshape(B, T, 7)
+            for b in range(B):
+                gref = orc.trajectory_cost_jacobian(X[b], rho, goal=goal, ct=ct, W=W)
+                cref = orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)[0]
+                assert np.max(np.abs(grad[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max()), name
+                assert abs(cost[b] - cref) <= 1e-10 * max(1.0, cref), name
+    # layouts agree bit for bit within a path
+    for choice in (0, 1):
+        a, b = results[(choice, _capi.LAYOUT_SOA)], results[(choice, _capi.LAYOUT_AOS_ROWMAJOR)]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_end_pose_cost_jacobian_and_finite_differences(oracle_lib):
     # UnconstrainedEndPoseProblem::GetScalarJacobian = 2 J^T S ydiff; for position-type maps it is the exact gradient of the cost
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
