@@ -201,6 +201,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not share stdout with the JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     E = args.configs

@@ -36,6 +36,7 @@ def main():
     exo._capi.check(exo._capi.lib().exo_set_device(local))
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
