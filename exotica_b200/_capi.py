@@ -15,6 +15,7 @@ EXO_OK = 0
 LAYOUT_SOA, LAYOUT_AOS_ROWMAJOR, LAYOUT_AOS_COLMAJOR = 0, 1, 2
 MAP_EFF_FRAME, MAP_EFF_POSITION, MAP_JOINT_LIMIT, MAP_SPHERE_COLLISION, MAP_FRAMES = 0, 1, 2, 3, 4
 MAP_EFF_ORIENTATION, MAP_EFF_POSITION_XY, MAP_DISTANCE, MAP_JOINT_POSE = 5, 6, 7, 8
+MAP_EFF_AXIS_ALIGNMENT, MAP_CENTER_OF_MASS = 9, 10
 ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
 ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
 
@@ -33,7 +34,8 @@ class TaskMapDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("n_frames", ctypes.c_int32), ("elem_a", _ip), ("off_a", _dp), ("elem_b", _ip),
                 ("off_b", _dp), ("rotation_type", ctypes.c_int32), ("safe_percentage", ctypes.c_double),
                 ("precision", ctypes.c_double), ("radius", _dp), ("group", _ip), ("is_used", ctypes.c_int32),
-                ("n_joint_map", ctypes.c_int32), ("joint_map", _ip), ("joint_ref", _dp)]
+                ("n_joint_map", ctypes.c_int32), ("joint_map", _ip), ("joint_ref", _dp), ("axis", _dp), ("direction", _dp), ("mass", _dp),
+                ("enable_z", ctypes.c_int32)]
 
 
 class CostDesc(ctypes.Structure):
@@ -261,7 +263,8 @@ class Problem(object):
         self.finalized = False
 
     def add_task_map(self, kind, elem_a=None, off_a=None, elem_b=None, off_b=None, rotation_type=1, safe_percentage=0.0,
-                     precision=1.0, radius=None, group=None, is_used=True, joint_map=None, joint_ref=None):
+                     precision=1.0, radius=None, group=None, is_used=True, joint_map=None, joint_ref=None, axis=None, direction=None, mass=None,
+                     enable_z=True):
         d = TaskMapDesc()
         d.kind = kind
         n = 0 if elem_a is None else len(elem_a)
@@ -292,6 +295,12 @@ class Problem(object):
             jr = np.ascontiguousarray(joint_ref, dtype=np.float64)
             keep.append(jr)
             d.joint_ref = _d(jr)
+        for name, val in (("axis", axis), ("direction", direction), ("mass", mass)):
+            if val is not None:
+                a = np.ascontiguousarray(val, dtype=np.float64)
+                keep.append(a)
+                setattr(d, name, _d(a))
+        d.enable_z = 1 if enable_z else 0
         check(lib().exo_problem_add_task_map(self.h, ctypes.byref(d)))
 
     def finalize(self):

@@ -361,7 +361,7 @@ int exo_problem_add_task_map(exo_problem* p, const exo_task_map_desc* d)
 {
     if (!p || !d) return fail(EXO_ERR_INVALID, "NULL argument");
     if (p->finalized) return fail(EXO_ERR_STATE, "problem already finalized");
-    if (d->kind < EXO_MAP_EFF_FRAME || d->kind > EXO_MAP_JOINT_POSE) return fail(EXO_ERR_INVALID, "unknown task map kind");
+    if (d->kind < EXO_MAP_EFF_FRAME || d->kind > EXO_MAP_CENTER_OF_MASS) return fail(EXO_ERR_INVALID, "unknown task map kind");
     if (d->n_frames < 0) return fail(EXO_ERR_INVALID, "negative frame count");
     MapSpec m;
     m.kind = d->kind;
@@ -406,6 +406,30 @@ int exo_problem_add_task_map(exo_problem* p, const exo_task_map_desc* d)
             for (int i = 0; i < N; ++i) m.joint_map.push_back(i);
         m.joint_ref.assign(m.joint_map.size(), 0.0);
         if (d->joint_ref) m.joint_ref.assign(d->joint_ref, d->joint_ref + m.joint_map.size());
+    }
+    if (m.kind == EXO_MAP_EFF_AXIS_ALIGNMENT)
+    {
+        // EffAxisAlignment::Initialize (eff_axis_alignment.cpp:39-58): Axis and Direction default to (1, 0, 0) and are normalised
+        m.axis.assign(3 * (size_t)d->n_frames, 0.0);
+        m.direction.assign(3 * (size_t)d->n_frames, 0.0);
+        for (int f = 0; f < d->n_frames; ++f)
+        {
+            const double unit_x[3] = {1.0, 0.0, 0.0};
+            const double* a = d->axis ? d->axis + 3 * f : unit_x;
+            const double* b = d->direction ? d->direction + 3 * f : unit_x;
+            const double na = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+            for (int k = 0; k < 3; ++k)
+            {
+                m.axis[3 * f + k] = a[k] / na;  // Eigen's normalized(): division by the norm (NaN for a zero vector, like the reference)
+                m.direction[3 * f + k] = b[k] / nb;
+            }
+        }
+    }
+    if (m.kind == EXO_MAP_CENTER_OF_MASS)
+    {
+        if (d->n_frames > 0 && !d->mass) return fail(EXO_ERR_INVALID, "CenterOfMass needs mass[]");
+        m.mass.assign(d->mass, d->mass + d->n_frames);
+        m.enable_z = d->enable_z != 0;
     }
     if (m.kind == EXO_MAP_SPHERE_COLLISION)
     {
@@ -1189,7 +1213,9 @@ static int ensure_shadow(exo_problem* p)
     for (const MapSpec& m : p->maps)
     {
         p->shadow_frame_start.push_back((int)ea.size());
-        if (m.kind == EXO_MAP_SPHERE_COLLISION || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_JOINT_POSE) continue;
+        if (m.kind == EXO_MAP_SPHERE_COLLISION || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_JOINT_POSE ||
+            m.kind == EXO_MAP_EFF_AXIS_ALIGNMENT || m.kind == EXO_MAP_CENTER_OF_MASS)
+            continue;  // no Hessian overload in the reference: the base-class fallback needs the map's own Jacobian only
         ea.insert(ea.end(), m.elem_a.begin(), m.elem_a.end());
         eb.insert(eb.end(), m.elem_b.begin(), m.elem_b.end());
         oa.insert(oa.end(), m.off_a.begin(), m.off_a.end());

@@ -234,6 +234,12 @@ bool assign_indexing(const TreeModel& tree, std::vector<MapSpec>& maps, int& len
             case EXO_MAP_JOINT_POSE:  // joint_pose.cpp:66-103
                 m.length = m.length_jacobian = (int)m.joint_map.size();
                 break;
+            case EXO_MAP_EFF_AXIS_ALIGNMENT:  // eff_axis_alignment.cpp:171-174
+                m.length = m.length_jacobian = m.n_frames;
+                break;
+            case EXO_MAP_CENTER_OF_MASS:  // center_of_mass.cpp:134-137
+                m.length = m.length_jacobian = m.enable_z ? 3 : 2;
+                break;
             default:
                 err = "unknown task map kind";
                 return false;
@@ -451,6 +457,10 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 emits.push_back({OP_EMIT_SPHERES, mi, 0, r});
                 break;
             }
+            case EXO_MAP_CENTER_OF_MASS:
+                // every frame adds its share to the same rows: zero them first (Phi and J), then accumulate
+                emits.push_back({OP_EMIT_FILL, mi, 0, -1});
+                // fall through
             default:
                 for (int f = 0; f < m.n_frames; ++f)
                     emits.push_back({OP_EMIT_FRAME, mi, f, std::max(ready_of(anchor[m.elem_a[f]]), ready_of(anchor[m.elem_b[f]]))});
@@ -740,8 +750,11 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             if (m.kind == EXO_MAP_EFF_ORIENTATION) stride = rotation_length(m.rot_type), rows = 3, row_mode = ROWS_W;
             if (m.kind == EXO_MAP_EFF_POSITION_XY) stride = 2, rows = 2, row_mode = ROWS_VXY;
             if (m.kind == EXO_MAP_DISTANCE) stride = 1, rows = 1, row_mode = ROWS_DIST;
+            if (m.kind == EXO_MAP_EFF_AXIS_ALIGNMENT) stride = 1, rows = 1, row_mode = ROWS_WDOT;
+            if (m.kind == EXO_MAP_CENTER_OF_MASS) stride = 0, rows = 0, row_mode = m.enable_z ? ROWS_V_ACC : ROWS_VXY_ACC;  // all frames share the rows
             op.phi_off = m.start + f * stride;
             op.jrow_off = m.start_jacobian + f * rows;
+            if (m.kind == EXO_MAP_CENTER_OF_MASS) rows = m.enable_z ? 3 : 2;
             op.n_rows = rows;
             op.src = patch_src(pl.src_a);
             op.src_b = patch_src(pl.src_b);
@@ -767,6 +780,25 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
                 push_frame(pl.off_b);
             }
             op.flags = flags;
+            if (m.kind == EXO_MAP_EFF_AXIS_ALIGNMENT)
+            {
+                // frames_[i + n] is frames_[i] with frame_A_offset.p = axis (eff_axis_alignment.cpp:53-57), so
+                // p_{i+n} - p_i = Phi_i.M * a with a = M_off^T (axis - p_off); then the direction.  pl.off_a is the link's
+                // constant tail C times the LinkOffset, so the same point difference in the anchor frame is C.M axis + C.p - off_a.p
+                const Frame& oa = pl.off_a;
+                const Frame& Cf = C[m.elem_a[f]];
+                const double* ax = &m.axis[3 * f];
+                double d[3];
+                for (int k = 0; k < 3; ++k) d[k] = Cf.M[3 * k] * ax[0] + Cf.M[3 * k + 1] * ax[1] + Cf.M[3 * k + 2] * ax[2] + Cf.p[k] - oa.p[k];
+                for (int k = 0; k < 3; ++k) out.dbls.push_back(oa.M[k] * d[0] + oa.M[3 + k] * d[1] + oa.M[6 + k] * d[2]);
+                for (int k = 0; k < 3; ++k) out.dbls.push_back(m.direction[3 * f + k]);
+            }
+            if (m.kind == EXO_MAP_CENTER_OF_MASS)
+            {
+                double total = 0.0;
+                for (double v : m.mass) total += v;
+                out.dbls.push_back(total != 0.0 ? m.mass[f] / total : 0.0);  // M == 0: Phi and J stay zero (center_of_mass.cpp:41,66)
+            }
             if (two_pass)
                 for (int c = 0; c < N; ++c)
                     if (pl.contrib[c] >= 0)
@@ -791,7 +823,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             {
                 std::vector<int32_t> zeros;
                 for (int c = 0; c < N; ++c)
-                    if (pl.contrib[c] < 0) zeros.push_back(c);
+                    if (pl.contrib[c] < 0 && row_mode < ROWS_V_ACC) zeros.push_back(c);  // accumulated rows were zeroed by their fill op
                 out.ints.push_back((int32_t)zeros.size());
                 out.ints.insert(out.ints.end(), zeros.begin(), zeros.end());
             }
@@ -956,6 +988,7 @@ bool compile_program(const TreeModel& t, std::vector<MapSpec>& maps, Program& ou
             else if (op.kind == OP_EMIT_FRAME)
             {
                 if (op.src != SRC_CUR || op.src_b != SRC_ROOT || ordinal != n_ops) chain = false;
+                if (((op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT) >= ROWS_WDOT) chain = false;  // EffAxisAlignment, CenterOfMass: interpreter only
             }
             else if (op.kind == OP_EMIT_JLIMIT || op.kind == OP_EMIT_FILL)
             {

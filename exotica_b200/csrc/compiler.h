@@ -48,6 +48,9 @@ struct MapSpec
     int n_groups = 0;
     std::vector<int32_t> joint_map;  // JointPose
     std::vector<double> joint_ref;
+    std::vector<double> axis, direction;  // EffAxisAlignment: [n_frames][3], unit vectors
+    std::vector<double> mass;             // CenterOfMass: [n_frames]
+    bool enable_z = true;
     bool is_used = true;
     // assigned by the compiler (TaskMap::start / length / start_jacobian / length_jacobian)
     int start = 0, length = 0, start_jacobian = 0, length_jacobian = 0;

@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant_
         {
             const HessMapP& m = P.map[k];
             double* hm = h + (int64_t)m.start_jacobian * P.h_sr;
-            if (m.kind == EXO_MAP_JOINT_POSE || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_SPHERE_COLLISION || !m.is_used)
+            if (m.kind == EXO_MAP_JOINT_POSE || m.kind == EXO_MAP_JOINT_LIMIT || m.kind == EXO_MAP_SPHERE_COLLISION ||
+                m.kind == EXO_MAP_EFF_AXIS_ALIGNMENT || m.kind == EXO_MAP_CENTER_OF_MASS || !m.is_used)
             {
                 // zero (JointPose, unused maps) or the base-class fallback J_row^T J_row
                 const bool outer = m.is_used && m.kind != EXO_MAP_JOINT_POSE;

@@ -339,7 +339,8 @@ static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y
 
 
 // Rows of one Jacobian column the map keeps (program.h RowMode); (v, w) = linear / angular part of the frame's column,
-// (ux, uy, uz) = Phi.p / |Phi.p| for ROWS_DIST (distance.cpp:52)
+// (ux, uy, uz) = Phi.p / |Phi.p| for ROWS_DIST (distance.cpp:52), (Phi.M a) x direction for ROWS_WDOT
+// (eff_axis_alignment.cpp:140-144), ux = mass share for the accumulating CenterOfMass modes (center_of_mass.cpp:70)
 __device__ __forceinline__ void store_rows(int mode, double* jc, int64_t sr, double v0, double v1, double v2, double w0, double w1, double w2,
                                            double ux, double uy, double uz)
 {
@@ -357,8 +358,17 @@ __device__ __forceinline__ void store_rows(int mode, double* jc, int64_t sr, dou
         case ROWS_VXY:
             jc[0] = v0; jc[sr] = v1;
             break;
-        default:  // ROWS_DIST
+        case ROWS_DIST:
             jc[0] = ux * v0 + uy * v1 + uz * v2;
+            break;
+        case ROWS_WDOT:  // EffAxisAlignment: direction . (w x u) = w . (u x direction); (ux, uy, uz) = u x direction
+            jc[0] = ux * w0 + uy * w1 + uz * w2;
+            break;
+        case ROWS_V_ACC:  // CenterOfMass: ux = mass_i / M
+            jc[0] += ux * v0; jc[sr] += ux * v1; jc[2 * sr] += ux * v2;
+            break;
+        default:  // ROWS_VXY_ACC
+            jc[0] += ux * v0; jc[sr] += ux * v1;
             break;
     }
 }

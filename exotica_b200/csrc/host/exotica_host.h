@@ -474,6 +474,45 @@ public:
     int Kind() const override { return EXO_MAP_DISTANCE; }
 };
 
+class EffAxisAlignment : public TaskMap  // eff_axis_alignment.cpp
+{
+public:
+    void InstantiateBase(const Initializer& init) override;  // EndEffector entries are FrameWithAxisAndDirection initializers
+    int TaskSpaceDim() override { return (int)frames_.size(); }
+    int Kind() const override { return EXO_MAP_EFF_AXIS_ALIGNMENT; }
+    void FillDescriptor(exo_task_map_desc& desc) override
+    {
+        desc.axis = axis_.data();
+        desc.direction = dir_.data();
+    }
+    // eff_axis_alignment.cpp:176-200 (normalised, like the reference)
+    std::vector<double> GetDirection(const std::string& frame_name) const;
+    void SetDirection(const std::string& frame_name, const std::vector<double>& dir);
+
+private:
+    std::vector<double> axis_, dir_;  // [n][3]
+};
+
+class CenterOfMass : public TaskMap  // center_of_mass.cpp
+{
+public:
+    void Instantiate(const Initializer& init) override;
+    void AssignScene(ScenePtr scene) override;  // Initialize(): offsets = centres of gravity, weights = link masses
+    int TaskSpaceDim() override { return dim_; }
+    int Kind() const override { return EXO_MAP_CENTER_OF_MASS; }
+    void FillDescriptor(exo_task_map_desc& desc) override
+    {
+        desc.mass = mass_.data();
+        desc.enable_z = enable_z_ ? 1 : 0;
+    }
+    const std::vector<double>& get_mass() const { return mass_; }
+
+private:
+    bool enable_z_ = true;
+    int dim_ = 3;
+    std::vector<double> mass_;
+};
+
 class JointPose : public TaskMap  // joint_pose.cpp
 {
 public:

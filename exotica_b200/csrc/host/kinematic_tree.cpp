@@ -199,6 +199,18 @@ void KinematicTree::BuildTree()
     };
     Rec::Add(*this, *model_, model_->root_link, (int)tree_.size() - 1);
     num_model_elements_ = (int)tree_.size();
+    // "Set root inertial" (:264-276): the URDF root link's inertial goes to model_tree_[2] (fixed base), [7] (floating) or [4]
+    // (planar).  [7] and [4] are the root link itself; with a FIXED base the root link is model_tree_[1], so the first child
+    // of the root carries the root's inertial instead of its own -- the CenterOfMass goldens of test_maps.cpp:789-827 depend on it.
+    {
+        const size_t k = model_->root_joint_type == "floating" ? 7 : (model_->root_joint_type == "planar" ? 4 : 2);
+        if (k < tree_.size())
+        {
+            const UrdfLink& root = model_->GetLink(model_->root_link);
+            tree_[k].mass = root.mass;
+            memcpy(tree_[k].cog, root.cog, sizeof(root.cog));
+        }
+    }
 
     // UpdateModel (:423-432)
     for (int i = 0; i < (int)tree_.size(); ++i) tree_map_[tree_[i].link_name] = i;

@@ -288,6 +288,89 @@ void JointLimit::AssignScene(ScenePtr scene)
     N_ = scene_->GetKinematicTree().GetNumControlledJoints();  // joint_limit.cpp:42-56 (kinematic case)
 }
 
+// ---- EffAxisAlignment (eff_axis_alignment.cpp:39-58; init/frame_with_axis_and_direction.in) ---------------------------------------
+static void Normalise3(std::vector<double>& v, const char* what)
+{
+    if (v.size() != 3) ThrowPretty(std::string(what) + " must have 3 entries");
+    const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (double& x : v) x /= n;  // Eigen normalized()
+}
+
+void EffAxisAlignment::InstantiateBase(const Initializer& init)
+{
+    TaskMap::InstantiateBase(init);
+    axis_.clear();
+    dir_.clear();
+    for (const Initializer& eff : init.List("EndEffector"))
+    {
+        std::vector<double> a = eff.Has("Axis") ? ParseVector(eff.Get("Axis", "")) : std::vector<double>{1.0, 0.0, 0.0};
+        std::vector<double> d = eff.Has("Direction") ? ParseVector(eff.Get("Direction", "")) : std::vector<double>{1.0, 0.0, 0.0};
+        Normalise3(a, "Axis");
+        Normalise3(d, "Direction");
+        axis_.insert(axis_.end(), a.begin(), a.end());
+        dir_.insert(dir_.end(), d.begin(), d.end());
+    }
+}
+
+std::vector<double> EffAxisAlignment::GetDirection(const std::string& frame_name) const
+{
+    for (size_t i = 0; i < frames_.size(); ++i)
+        if (frames_[i].frame_A_link_name == frame_name) return std::vector<double>(dir_.begin() + 3 * i, dir_.begin() + 3 * i + 3);
+    ThrowPretty("Direction for frame with name " + frame_name + " could not be found.");
+}
+
+void EffAxisAlignment::SetDirection(const std::string& frame_name, const std::vector<double>& dir_in)
+{
+    for (size_t i = 0; i < frames_.size(); ++i)
+        if (frames_[i].frame_A_link_name == frame_name)
+        {
+            std::vector<double> d = dir_in;
+            Normalise3(d, "Direction");
+            std::copy(d.begin(), d.end(), dir_.begin() + 3 * i);
+            ReleaseOwnProblem();
+            return;
+        }
+    ThrowPretty("Could not find frame with name " + frame_name + ".");
+}
+
+// ---- CenterOfMass (center_of_mass.cpp:145-170, 88-117; init/center_of_mass.in) -----------------------------------------------------
+void CenterOfMass::Instantiate(const Initializer& init)
+{
+    const std::string z = init.Get("EnableZ", "1");
+    enable_z_ = !(z == "0" || z == "false" || z == "False");
+    dim_ = enable_z_ ? 3 : 2;
+}
+
+void CenterOfMass::AssignScene(ScenePtr scene)
+{
+    scene_ = scene;
+    const KinematicTree& kt = scene_->GetKinematicTree();
+    mass_.clear();
+    if (!frames_.empty())
+    {
+        // explicit frames: the offset's position becomes the link's centre of gravity, the weight its mass (:160-167)
+        for (KinematicFrameRequest& f : frames_)
+        {
+            if (!f.frame_B_link_name.empty()) ThrowPretty("Requesting CenterOfMass frame with base other than root! '" + f.frame_A_link_name + "'");
+            const KinematicElement& e = kt.GetTree()[kt.ResolveFrame(f.frame_A_link_name, "frame_A")];
+            for (int k = 0; k < 3; ++k) f.frame_A_offset[9 + k] = e.cog[k];
+            mass_.push_back(e.mass);
+        }
+    }
+    else
+    {
+        // no frames: every robot link (and attached object) with mass, at its centre of gravity (:88-117)
+        for (const KinematicElement& e : kt.GetTree())
+            if (e.is_robot_link && e.mass > 0)
+            {
+                Frame off = IdentityFrame();
+                for (int k = 0; k < 3; ++k) off[9 + k] = e.cog[k];
+                frames_.push_back(KinematicFrameRequest(e.link_name, off));
+                mass_.push_back(e.mass);
+            }
+    }
+}
+
 void SphereCollision::InstantiateBase(const Initializer& init)
 {
     TaskMap::InstantiateBase(init);
@@ -348,6 +431,8 @@ Setup& Setup::Instance()
         s->RegisterMap("exotica/EffOrientation", &MakeMap<EffOrientation>);
         s->RegisterMap("exotica/EffPositionXY", &MakeMap<EffPositionXY>);
         s->RegisterMap("exotica/Distance", &MakeMap<Distance>);
+        s->RegisterMap("exotica/EffAxisAlignment", &MakeMap<EffAxisAlignment>);
+        s->RegisterMap("exotica/CenterOfMass", &MakeMap<CenterOfMass>);
         s->RegisterMap("exotica/JointPose", &MakeMap<JointPose>);
         s->RegisterProblem("exotica/UnconstrainedEndPoseProblem", &MakeProblem<UnconstrainedEndPoseProblem>);
         s->RegisterProblem("exotica/TimeIndexedProblem", &MakeProblem<TimeIndexedProblem>);
@@ -385,7 +470,7 @@ std::vector<std::string> Setup::GetProblems()
 TaskMapPtr Setup::CreateMap(const Initializer& init)
 {
     auto it = Instance().maps_.find(init.name);
-    if (it == Instance().maps_.end()) ThrowPretty("Unable to load task map of type '" + init.name + "' (registered on the GPU path: EffFrame, EffPosition, JointLimit, SphereCollision, EffOrientation, EffPositionXY, Distance, JointPose)");
+    if (it == Instance().maps_.end()) ThrowPretty("Unable to load task map of type '" + init.name + "' (registered on the GPU path: EffFrame, EffPosition, JointLimit, SphereCollision, EffOrientation, EffPositionXY, Distance, JointPose, EffAxisAlignment, CenterOfMass)");
     TaskMapPtr m = it->second();
     m->InstantiateBase(init);  // InstantiateInternal = InstantiateBase + Instantiate (property.h:113-119)
     m->Instantiate(init);

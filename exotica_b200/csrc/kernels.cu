@@ -445,7 +445,10 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                                     w0 = u0; w1 = u1; w2 = u2;
                                 }
                                 const int64_t sr = P.j_sr;
-                                store_rows(ent[3], jac_e + (int64_t)ent[2] * sr + (int64_t)ent[1] * P.j_sc, sr, v0, v1, v2, w0, w1, w2, 0.0, 0.0, 0.0);
+                                // EffAxisAlignment parked its vector where the position would be; CenterOfMass's mass share
+                                // sits behind the frame's constants
+                                const double ux = ent[3] >= ROWS_V_ACC ? dbls[ent[5] - CE_B_M + CE_SIZE] : ps[0];
+                                store_rows(ent[3], jac_e + (int64_t)ent[2] * sr + (int64_t)ent[1] * P.j_sc, sr, v0, v1, v2, w0, w1, w2, ux, ps[CS], ps[2 * CS]);
                             }
                         }
                     }
@@ -486,12 +489,44 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     }
                     Phi = fr_mul(Binv, A);
                 }
-                write_phi(op.map_kind, op.rot_type, Phi, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk);
+                const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
+                double ux = 0.0, uy = 0.0, uz = 0.0;  // per-frame vector / weight some row modes need (store_rows)
+                if (row_mode == ROWS_WDOT)
+                {
+                    // EffAxisAlignment::Update (eff_axis_alignment.cpp:116-145): phi = direction . (p_{i+n} - p_i) - 1
+                    const double* k = c + CE_SIZE;  // a (3), direction (3)
+                    const double u0 = Phi.m0 * k[0] + Phi.m1 * k[1] + Phi.m2 * k[2];
+                    const double u1 = Phi.m3 * k[0] + Phi.m4 * k[1] + Phi.m5 * k[2];
+                    const double u2 = Phi.m6 * k[0] + Phi.m7 * k[1] + Phi.m8 * k[2];
+                    phi_e[(int64_t)op.phi_off * P.phi_sk] = (u0 * k[3] + u1 * k[4] + u2 * k[5]) - 1.0;
+                    ux = u1 * k[5] - u2 * k[4];
+                    uy = u2 * k[3] - u0 * k[5];
+                    uz = u0 * k[4] - u1 * k[3];
+                }
+                else if (row_mode >= ROWS_V_ACC)
+                {
+                    // CenterOfMass::Update (center_of_mass.cpp:37-54): com += p_i mass_i / M on rows a fill op zeroed
+                    ux = c[CE_SIZE];
+                    double* ph = phi_e + (int64_t)op.phi_off * P.phi_sk;
+                    ph[0] += ux * Phi.x;
+                    ph[P.phi_sk] += ux * Phi.y;
+                    if (row_mode == ROWS_V_ACC) ph[2 * P.phi_sk] += ux * Phi.z;
+                }
+                else
+                    write_phi(op.map_kind, op.rot_type, Phi, phi_e + (int64_t)op.phi_off * P.phi_sk, P.phi_sk);
                 if (want_j && two_pass)
                 {
-                    // park temp_A.p for pass 1 and write the structural zeros (columns no joint below this frame owns)
+                    // park temp_A.p for pass 1 (EffAxisAlignment: the vector its row is dotted with instead) and write the
+                    // structural zeros (columns no joint below this frame owns)
                     double* ps = scr + (pos_base + 3 * op.n_items) * CS;
-                    ps[0] = A.x; ps[CS] = A.y; ps[2 * CS] = A.z;
+                    if (row_mode == ROWS_WDOT)
+                    {
+                        ps[0] = ux; ps[CS] = uy; ps[2 * CS] = uz;
+                    }
+                    else
+                    {
+                        ps[0] = A.x; ps[CS] = A.y; ps[2 * CS] = A.z;
+                    }
                     const int32_t* zl = ints + op.pad;
                     const int n_zero = zl[0];
                     const int64_t sr = P.j_sr, sc = P.j_sc;
@@ -509,8 +544,6 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     const int32_t* tab = ints + op.tab;
                     double* jr = jac_e + (int64_t)op.jrow_off * P.j_sr;
                     const int64_t sr = P.j_sr;
-                    const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
-                    double ux = 0.0, uy = 0.0, uz = 0.0;
                     if (row_mode == ROWS_DIST)
                     {
                         const double nrm = norm3_scaled(Phi.x, Phi.y, Phi.z);
@@ -519,6 +552,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     for (int col = 0; col < N; ++col)
                     {
                         const int ent = tab[col];
+                        if (ent < 0 && row_mode >= ROWS_V_ACC) continue;  // accumulating rows: nothing to add
                         double v0 = 0.0, v1 = 0.0, v2 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
                         if (ent >= 0)
                         {

@@ -73,7 +73,10 @@ enum RowMode : int32_t
     ROWS_V = 1,     // 3 rows: linear (EffPosition)
     ROWS_W = 2,     // 3 rows: angular (EffOrientation)
     ROWS_VXY = 3,   // 2 rows: x and y of the linear part (EffPositionXY)
-    ROWS_DIST = 4   // 1 row: (p . J_v) / |p| (Distance)
+    ROWS_DIST = 4,  // 1 row: (p . J_v) / |p| (Distance)
+    ROWS_WDOT = 5,  // 1 row: J_w . k with k = (Phi.M a) x direction (EffAxisAlignment)
+    ROWS_V_ACC = 6, // 3 rows: += weight * linear part (CenterOfMass; the rows are zeroed by a fill op first)
+    ROWS_VXY_ACC = 7  // 2 rows: the same without z (CenterOfMass, EnableZ = false)
 };
 
 // One op = 16 int32 (64 B) + a slice of the double constant pool.

@@ -86,7 +86,12 @@ typedef enum
     EXO_MAP_EFF_ORIENTATION = 5,
     EXO_MAP_EFF_POSITION_XY = 6,
     EXO_MAP_DISTANCE = 7,
-    EXO_MAP_JOINT_POSE = 8
+    EXO_MAP_JOINT_POSE = 8,
+    /* exotations/exotica_core_task_maps/src/eff_axis_alignment.cpp:116-145 (one row per frame:
+     * phi = direction . (R_link axis) - 1) and center_of_mass.cpp:37-132 (mass-weighted mean of the frames' positions,
+     * 3 rows, or 2 when EnableZ is false) */
+    EXO_MAP_EFF_AXIS_ALIGNMENT = 9,
+    EXO_MAP_CENTER_OF_MASS = 10
 } exo_map_kind;
 
 typedef struct exo_tree exo_tree;       /* backend of exotica::KinematicTree (scene.h:195 kinematica_) */
@@ -135,6 +140,10 @@ typedef struct
     int32_t n_joint_map;     /* JointPose: entries of JointMap (0 = all controlled joints in order, init/joint_pose.in) */
     const int32_t* joint_map;/* [n_joint_map] controlled-joint indices */
     const double* joint_ref; /* [n_joint_map or N] JointRef, NULL = zeros */
+    const double* axis;      /* EffAxisAlignment: [n_frames][3] Axis (init/frame_with_axis_and_direction.in; normalised here) */
+    const double* direction; /* EffAxisAlignment: [n_frames][3] Direction (normalised here) */
+    const double* mass;      /* CenterOfMass: [n_frames] mass of every frame (center_of_mass.cpp:150-205) */
+    int32_t enable_z;        /* CenterOfMass EnableZ (init/center_of_mass.in): 0 keeps x and y only */
 } exo_task_map_desc;
 
 /* ---- errors / device ------------------------------------------------------------------------- */

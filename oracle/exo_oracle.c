@@ -996,6 +996,18 @@ int exo_oracle_problem_add_map(exo_oracle* o, int kind, int frame_start, int n_f
             m->length = m->length_jacobian = n;
             break;
         }
+        case EXO_ORC_MAP_EFF_AXIS_ALIGNMENT:
+            /* 2n frames; sphere_radius carries the n directions (3 doubles each) */
+            m->radius = (double*)malloc((size_t)(n_frames > 0 ? 3 * (n_frames / 2) : 1) * sizeof(double));
+            for (i = 0; i < 3 * (n_frames / 2); ++i) m->radius[i] = sphere_radius[i];
+            m->length = m->length_jacobian = n_frames / 2; /* eff_axis_alignment.cpp:171-174 */
+            break;
+        case EXO_ORC_MAP_CENTER_OF_MASS:
+            /* sphere_radius carries the masses, param dim_ = EnableZ ? 3 : 2 (center_of_mass.cpp:134-137,196) */
+            m->radius = (double*)malloc((size_t)(n_frames > 0 ? n_frames : 1) * sizeof(double));
+            for (i = 0; i < n_frames; ++i) m->radius[i] = sphere_radius[i];
+            m->length = m->length_jacobian = (int)param;
+            break;
         case EXO_ORC_MAP_SPHERE_COLLISION:
             m->group = (int*)malloc((size_t)(n_frames > 0 ? n_frames : 1) * sizeof(int));
             m->radius = (double*)malloc((size_t)(n_frames > 0 ? n_frames : 1) * sizeof(double));
@@ -1109,6 +1121,50 @@ static void map_distance(const exo_oracle* o, const taskmap_t* m, double* phi, d
         if (jac)
             for (c = 0; c < o->n_ctrl; ++c) jac[(size_t)c * ldj + i] = (p[0] * kj[6 * c] + p[1] * kj[6 * c + 1] + p[2] * kj[6 * c + 2]) / phi[i];
     }
+}
+
+/* EffAxisAlignment::Update (eff_axis_alignment.cpp:116-145): the map holds 2n frames, frame i + n being frame i with
+ * frame_A_offset.p replaced by the (normalised) axis (:53-57); m->radius carries the n normalised directions (3 each). */
+static void map_eff_axis_alignment(const exo_oracle* o, const taskmap_t* m, double* phi, double* jac, int ldj)
+{
+    const int n = m->n_frames / 2;
+    int i, c, k;
+    for (i = 0; i < n; ++i)
+    {
+        const kframe_t* f0 = &o->fr[m->frame_start + i];
+        const kframe_t* f1 = &o->fr[m->frame_start + i + n];
+        const double* j0 = o->jac + (size_t)(m->frame_start + i) * 6 * o->n_ctrl;
+        const double* j1 = o->jac + (size_t)(m->frame_start + i + n) * 6 * o->n_ctrl;
+        const double* dir = m->radius + 3 * i;
+        double a[3];
+        for (k = 0; k < 3; ++k) a[k] = f1->temp_ab.p[k] - f0->temp_ab.p[k];
+        phi[i] = (a[0] * dir[0] + a[1] * dir[1] + a[2] * dir[2]) - 1.0;
+        if (jac)
+            for (c = 0; c < o->n_ctrl; ++c)
+                jac[(size_t)c * ldj + i] = dir[0] * (j1[6 * c] - j0[6 * c]) + dir[1] * (j1[6 * c + 1] - j0[6 * c + 1]) + dir[2] * (j1[6 * c + 2] - j0[6 * c + 2]);
+    }
+}
+
+/* CenterOfMass::Update with explicit frames (center_of_mass.cpp:37-54, 56-86): com = sum_i p_i mass_i / M,
+ * jacobian += mass_i / M * J_i.topRows(dim); m->radius carries the masses, m->param dim_ (3, or 2 without z).
+ * M == 0 returns before anything is written. */
+static void map_center_of_mass(const exo_oracle* o, const taskmap_t* m, double* phi, double* jac, int ldj)
+{
+    const int dim = (int)m->param;
+    double M = 0.0, com[3] = {0.0, 0.0, 0.0};
+    int i, c, k;
+    for (i = 0; i < m->n_frames; ++i) M += m->radius[i];
+    if (M == 0.0) return;
+    for (i = 0; i < m->n_frames; ++i)
+    {
+        const kframe_t* f = &o->fr[m->frame_start + i];
+        const double* kj = o->jac + (size_t)(m->frame_start + i) * 6 * o->n_ctrl;
+        for (k = 0; k < 3; ++k) com[k] += f->temp_ab.p[k] * m->radius[i];
+        if (jac)
+            for (c = 0; c < o->n_ctrl; ++c)
+                for (k = 0; k < dim; ++k) jac[(size_t)c * ldj + k] += m->radius[i] / M * kj[6 * c + k];
+    }
+    for (k = 0; k < dim; ++k) phi[k] = com[k] / M;
 }
 
 /* JointPose::Update (joint_pose.cpp:36-57) */
@@ -1241,6 +1297,12 @@ int exo_oracle_problem_update(exo_oracle* o, const double* x, double* phi, doubl
                 break;
             case EXO_ORC_MAP_JOINT_POSE:
                 map_joint_pose(o, m, x, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_EFF_AXIS_ALIGNMENT:
+                map_eff_axis_alignment(o, m, phi + m->start, jrows, ldj);
+                break;
+            case EXO_ORC_MAP_CENTER_OF_MASS:
+                map_center_of_mass(o, m, phi + m->start, jrows, ldj);
                 break;
             default:
                 return -1;
@@ -1549,7 +1611,8 @@ int exo_oracle_problem_hessian(exo_oracle* o, const double* x, double* hess)
         const taskmap_t* m = &o->maps[k];
         double* hm = hess + (size_t)m->start_jacobian * NN;
         if (!m->is_used || m->kind == EXO_ORC_MAP_JOINT_POSE) continue; /* zero */
-        if (m->kind == EXO_ORC_MAP_JOINT_LIMIT || m->kind == EXO_ORC_MAP_SPHERE_COLLISION)
+        if (m->kind == EXO_ORC_MAP_JOINT_LIMIT || m->kind == EXO_ORC_MAP_SPHERE_COLLISION || m->kind == EXO_ORC_MAP_EFF_AXIS_ALIGNMENT ||
+            m->kind == EXO_ORC_MAP_CENTER_OF_MASS)
         {
             /* TaskMap::Update(q, phi, J, H) base class (task_map.cpp:99-108): hessian(i) = J_row^T J_row */
             for (r = 0; r < m->length_jacobian; ++r)

@@ -68,7 +68,9 @@ enum
     EXO_ORC_MAP_EFF_ORIENTATION = 5,
     EXO_ORC_MAP_EFF_POSITION_XY = 6,
     EXO_ORC_MAP_DISTANCE = 7,
-    EXO_ORC_MAP_JOINT_POSE = 8
+    EXO_ORC_MAP_JOINT_POSE = 8,
+    EXO_ORC_MAP_EFF_AXIS_ALIGNMENT = 9, /* eff_axis_alignment.cpp */
+    EXO_ORC_MAP_CENTER_OF_MASS = 10     /* center_of_mass.cpp */
 };
 
 typedef struct exo_oracle exo_oracle;

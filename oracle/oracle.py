@@ -16,7 +16,7 @@ _LIB = None
 ROTATION_TYPES = {"Quaternion": 0, "RPY": 1, "ZYX": 2, "ZYZ": 3, "AngleAxis": 4, "Matrix": 5}
 ROTATION_LENGTH = [4, 3, 3, 3, 3, 9]
 MAP_KINDS = {"EffFrame": 0, "EffPosition": 1, "JointLimit": 2, "SphereCollision": 3, "EffOrientation": 5, "EffPositionXY": 6, "Distance": 7,
-             "JointPose": 8}
+             "JointPose": 8, "EffAxisAlignment": 9, "CenterOfMass": 10}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -196,6 +196,18 @@ class Oracle(object):
         specs = []
         for m in maps:
             fr = list(m.get("EndEffector", []))
+            if m["type"] == "EffAxisAlignment":
+                # EffAxisAlignment::Initialize (eff_axis_alignment.cpp:39-58): frames_[i + n] = frames_[i] with
+                # frame_A_offset.p = Axis.normalized()
+                extra = []
+                for f in fr:
+                    axis = np.asarray(f.get("Axis", [1.0, 0.0, 0.0]), dtype=np.float64)
+                    axis = axis / np.linalg.norm(axis)
+                    g = dict(f)
+                    off = list(f.get("LinkOffset", [0.0, 0.0, 0.0]))
+                    g["LinkOffset"] = list(axis) + off[3:]
+                    extra.append(g)
+                fr = fr + extra
             specs.append((m, len(frames), len(fr)))
             frames.extend(fr)
         self.request_frames(frames)
@@ -214,6 +226,12 @@ class Oracle(object):
                 grp = np.array(jm, dtype=np.int32)
                 rad = np.array(m.get("JointRef", [0.0] * len(jm)), dtype=np.float64)
                 param = float(len(jm))
+            if kind == 9:
+                dirs = [np.asarray(f.get("Direction", [1.0, 0.0, 0.0]), dtype=np.float64) for f in m["EndEffector"]]
+                rad = np.concatenate([d / np.linalg.norm(d) for d in dirs]) if dirs else np.zeros(0)
+            if kind == 10:
+                param = 3.0 if m.get("EnableZ", True) else 2.0
+                rad = np.array([float(f["Mass"]) for f in m["EndEffector"]], dtype=np.float64)
             if kind == 3:
                 param = float(m["Precision"])
                 names = sorted(set(f.get("Group", "default") for f in m["EndEffector"]))  # std::map order

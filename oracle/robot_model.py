@@ -382,6 +382,13 @@ class RobotTree(object):
                 add(c, idx)
 
         add(self.root_link, len(el) - 1)
+        # "Set root inertial" (kinematic_tree.cpp:264-276): the URDF root link's inertial is written to model_tree_[2] (fixed
+        # base), [7] (floating) or [4] (planar).  [7] and [4] are the root link itself; for a FIXED base the root link is
+        # model_tree_[1], so the FIRST CHILD of the root loses its own inertia to the root's (a reference quirk the
+        # CenterOfMass goldens of test_maps.cpp:789-827 depend on: link1 of the test robot counts as massless).
+        k = {"FIXED": 2, "FLOATING": 7, "PLANAR": 4}[self.base_type]
+        if k < len(el):
+            el[k].mass, el[k].cog = self.root_link.mass, list(self.root_link.cog)
         self.elements = el
         self.n_controlled = len(self.controlled_joint_names)
         if self.n_controlled < 1:

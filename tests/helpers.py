@@ -13,7 +13,8 @@ def gpu_problem_from_maps(orc, maps, tree_state=None):
     for m in maps:
         kind = {"EffFrame": _capi.MAP_EFF_FRAME, "EffPosition": _capi.MAP_EFF_POSITION, "JointLimit": _capi.MAP_JOINT_LIMIT,
                 "SphereCollision": _capi.MAP_SPHERE_COLLISION, "Frames": _capi.MAP_FRAMES, "EffOrientation": _capi.MAP_EFF_ORIENTATION,
-                "EffPositionXY": _capi.MAP_EFF_POSITION_XY, "Distance": _capi.MAP_DISTANCE, "JointPose": _capi.MAP_JOINT_POSE}[m["type"]]
+                "EffPositionXY": _capi.MAP_EFF_POSITION_XY, "Distance": _capi.MAP_DISTANCE, "JointPose": _capi.MAP_JOINT_POSE,
+                "EffAxisAlignment": _capi.MAP_EFF_AXIS_ALIGNMENT, "CenterOfMass": _capi.MAP_CENTER_OF_MASS}[m["type"]]
         frames = m.get("EndEffector", [])
         kw = dict(rotation_type=_capi.ROTATION_TYPES[m.get("Type", "RPY")], safe_percentage=m.get("SafePercentage", 0.0),
                   precision=m.get("Precision", 1.0), is_used=m.get("used", True))
@@ -23,6 +24,12 @@ def gpu_problem_from_maps(orc, maps, tree_state=None):
         if kind == _capi.MAP_JOINT_POSE:
             kw["joint_map"] = m.get("JointMap")
             kw["joint_ref"] = m.get("JointRef")
+        if kind == _capi.MAP_EFF_AXIS_ALIGNMENT:
+            kw["axis"] = [f.get("Axis", [1.0, 0.0, 0.0]) for f in frames]
+            kw["direction"] = [f.get("Direction", [1.0, 0.0, 0.0]) for f in frames]
+        if kind == _capi.MAP_CENTER_OF_MASS:
+            kw["mass"] = [float(f["Mass"]) for f in frames]
+            kw["enable_z"] = m.get("EnableZ", True)
         if kind == _capi.MAP_SPHERE_COLLISION:
             names = sorted(set(f.get("Group", "default") for f in frames))
             kw["group"] = [names.index(f.get("Group", "default")) for f in frames]
@@ -82,8 +89,10 @@ def angle_entries(maps, orc):
             start += nf * rl
         elif t == "EffPositionXY":
             start += 2 * nf
-        elif t == "Distance":
+        elif t in ("Distance", "EffAxisAlignment"):
             start += nf
+        elif t == "CenterOfMass":
+            start += 3 if m.get("EnableZ", True) else 2
         elif t == "JointPose":
             start += len(m.get("JointMap", range(orc.n)))
         elif t == "EffPosition":

@@ -611,6 +611,47 @@ def test_sibling_maps_on_trees_and_joint_pose(oracle_lib):
     _check(orc, maps + [{"type": "Distance", "EndEffector": [{"Link": "leftPalm", "Base": "rightPalm"}]}], X)
 
 
+def test_eff_axis_alignment(oracle_lib):
+    # eff_axis_alignment.cpp: one row per frame, direction . (R axis) - 1; offsets with rotation and position, a relative base,
+    # non-unit Axis / Direction (normalised by Initialize), chain and tree robots, all interpreter program shapes
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffAxisAlignment", "EndEffector": [
+                {"Link": "lwr_arm_7_link", "Axis": [1, 0, 0], "Direction": [0, 0, 1]},
+                {"Link": "lwr_arm_5_link", "LinkOffset": [0.1, -0.05, 0.2, 0.1, 0.2, 0.3, 0.9], "Axis": [0, 2, 1], "Direction": [1, 1, 0]},
+                {"Link": "lwr_arm_6_link", "Base": "lwr_arm_2_link", "BaseOffset": [0.0, 0.1, 0.0, 0.5, 0.5, 0.5, 0.5], "Axis": [0, 0, 1], "Direction": [0, -1, 0]}]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    X = random_states(orc, 777, seed=31)
+    prob, phi, jac = _check(orc, maps, X)
+    assert phi[:, :3].min() >= -2.0 - 1e-12 and phi[:, :3].max() <= 1e-12  # cos(angle) - 1 for unit vectors without position offsets...
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffAxisAlignment", "EndEffector": [{"Link": "leftPalm", "Axis": [0, 0, 1], "Direction": [0, 0, -1]},
+                                                          {"Link": "rightFoot", "Axis": [1, 0, 0], "Direction": [1, 0, 0]}]}]
+    _check(orc, maps, random_states(orc, 300, seed=32))
+
+
+@pytest.mark.parametrize("enable_z", [True, False])
+def test_center_of_mass_map(oracle_lib, enable_z):
+    # center_of_mass.cpp with explicit frames: mass-weighted mean of the frames' positions and of their position Jacobians
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    frames = []
+    for e in orc.tree.elements:
+        if e.is_robot_link and e.mass > 0:
+            frames.append({"Link": e.link_name, "LinkOffset": list(e.cog), "Mass": e.mass})
+    assert len(frames) > 20
+    maps = [{"type": "CenterOfMass", "EnableZ": enable_z, "EndEffector": frames},
+            {"type": "EffPosition", "EndEffector": [{"Link": "leftPalm"}]}]
+    X = random_states(orc, 400, seed=33)
+    prob, phi, jac = _check(orc, maps, X)
+    assert phi.shape[1] == (3 if enable_z else 2) + 3
+    # a chain robot too (one-pass program), with an unused CoM map next to it
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    frames = [{"Link": "lwr_arm_%d_link" % k, "LinkOffset": [0.0, 0.01 * k, 0.05], "Mass": 1.0 + 0.5 * k} for k in range(1, 8)]
+    maps = [{"type": "CenterOfMass", "EnableZ": enable_z, "EndEffector": frames},
+            {"type": "CenterOfMass", "used": False, "EndEffector": frames[:2]},
+            {"type": "JointLimit"}]
+    _check(orc, maps, random_states(orc, 333, seed=34), layout=_capi.LAYOUT_AOS_ROWMAJOR)
+
+
 def test_sibling_maps_cost_and_unused_fill(oracle_lib):
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
     maps = [{"type": "EffOrientation", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
