@@ -37,6 +37,9 @@ BYTES_PER_EVAL = 56 + 48 + 336  # read q (7 f64) + write Phi (6 f64) + write J (
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
 
 
+_emit = print  # replaced in main(): the JSON line goes to the original stdout
+
+
 def workload_name(E):
     return "cfg2a: LWR 7-DoF EffFrame(RPY) lwr_arm_7_link, %d random configurations per GPU per step" % E
 
@@ -183,7 +186,7 @@ def run_reference(args):
                        "each step evaluates a bounded sample of the step's batch on all host threads; value = median evals/s"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": samples[-1]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def run_ours(args):
@@ -308,7 +311,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample,
                              "single_thread_value": cpu1_value}}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -326,6 +329,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--configs", type=int, default=1 << 20, help="configurations per GPU per step")
     args = ap.parse_args()
+    # stdout carries exactly one line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version banner there at communicator creation) are sent to stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(json_fd, (text + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
