@@ -93,6 +93,7 @@ SYMBOLS = [
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_problem_cost_jacobian_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
+    ("exo_problem_aico_task_messages_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
     ("exo_problem_cost_gradient_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_jacobian_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
@@ -375,6 +376,9 @@ class Problem(object):
 
     def cost_jacobian_batch_device(self, d_x, d_phi, d_jac, n_traj, d_grad, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_jacobian_batch(self.h, d_x, d_phi, d_jac, int(n_traj), int(layout), d_grad, stream))
+
+    def aico_task_messages_device(self, d_qhat, d_phi, d_jac, n_traj, d_R, d_r, d_rhat, d_cost, layout=LAYOUT_SOA, stream=None):
+        check(lib().exo_problem_aico_task_messages_batch(self.h, d_qhat, d_phi, d_jac, int(n_traj), int(layout), d_R, d_r, d_rhat, d_cost, stream))
 
     def cost_gradient_batch_device(self, d_x, n_traj, d_grad, d_cost_traj=None, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_gradient_batch(self.h, d_x, int(n_traj), int(layout), d_cost_traj, d_grad, stream))

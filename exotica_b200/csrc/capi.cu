@@ -1120,6 +1120,47 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
     return exo_problem_cost_jacobian_batch(p, d_x, d_phi, d_jac, n_traj, layout, d_grad, stream);
 }
 
+int exo_problem_aico_task_messages_batch(exo_problem* p, const double* d_qhat, const double* d_phi, const double* d_jac, int64_t n_traj, int32_t layout,
+                                         double* d_R, double* d_r, double* d_rhat, double* d_cost, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_qhat || !d_phi || !d_jac || !d_R || !d_r || !d_rhat || !d_cost) return fail(EXO_ERR_INVALID, "NULL buffer");
+    KernelParams k;
+    memset(&k, 0, sizeof(k));
+    const int64_t E = n_traj * p->cost.T, N = p->prog.hdr.n_ctrl;
+    int rc = fill_strides(p, layout, E, k);
+    if (rc != EXO_OK) return rc;
+    AicoParams a;
+    memset(&a, 0, sizeof(a));
+    a.c = p->cost;
+    a.c.x = d_qhat;
+    a.c.phi = d_phi;
+    a.c.n_traj = n_traj;
+    a.c.x_se = k.x_se; a.c.x_sk = k.x_sk; a.c.phi_se = k.phi_se; a.c.phi_sk = k.phi_sk;
+    a.jac = d_jac;
+    a.j_se = k.j_se; a.j_sr = k.j_sr; a.j_sc = k.j_sc;
+    a.R = d_R; a.r = d_r; a.rhat = d_rhat; a.cost = d_cost;
+    a.r_se = k.x_se; a.r_sk = k.x_sk;
+    if (layout == EXO_LAYOUT_SOA)
+    {
+        a.R_se = 1; a.R_si = N * E; a.R_sj = E;  // R[N][N][E]
+    }
+    else
+    {
+        a.R_se = N * N; a.R_si = N; a.R_sj = 1;  // R[E][N][N] (symmetric: row- and column-major coincide)
+    }
+    a.length_jac = p->prog.hdr.length_jac;
+    cudaError_t e = launch_aico_messages(a, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) return fail(EXO_ERR_UNSUPPORTED, "the task-space Jacobian has more rows than the AICO message kernel supports (100)");
+    if (e != cudaSuccess) return cuda_fail(e, "AICO message kernel launch");
+    p->launches++;
+    p->last_kernel = "exo_aico_messages_kernel";
+    return EXO_OK;
+}
+
 int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream)
 {
     if (n_traj < 0 || T < 1 || t_first < 0 || t_first >= T) return fail(EXO_ERR_INVALID, "bad trajectory shape");

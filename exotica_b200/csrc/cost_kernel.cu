@@ -86,6 +86,61 @@ __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_con
     }
 }
 
+// AICOSolver::GetTaskCosts (aico_solver.cpp:364-386) for every (trajectory, timestep), on the Phi / J of prob_->Update(qhat[t], t):
+// tasks with precision rho > 0 add  C += rho |ydiff|^2,  R += rho J^T J,  v = -ydiff + J qhat,  r += rho J^T v,  rhat += rho |v|^2.
+// One lane per evaluation; per row the precision and v sit in shared memory [row][lane]; J is re-read from L1 / L2 for the
+// N (N + 1) / 2 distinct entries of the symmetric R.
+__global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_constant__ AicoParams P)
+{
+    extern __shared__ double sh[];  // [2][length_jac][128]
+    const CostParams& C = P.c;
+    const int N = C.n_ctrl, T = C.T, LJ = P.length_jac;
+    double* v = sh + threadIdx.x;
+    double* a = sh + (size_t)LJ * 128 + threadIdx.x;
+    const int64_t n_evals = C.n_traj * T, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_evals; e += stride)
+    {
+        const int t = (int)(e % T);
+        eval_ydiff(C, e, t, v, 128);
+        const double* rho = C.rho + (int64_t)t * C.n_maps;
+        for (int k = 0; k < C.n_maps; ++k)
+        {
+            const CostMapP& m = C.map[k];
+            const double prec = rho[k] > 0 ? rho[k] : 0.0;  // "if (prec > 0)"
+            for (int i = 0; i < m.length_jacobian; ++i) a[(m.start_jacobian + i) * 128] = prec;
+        }
+        const double* J = P.jac + e * P.j_se;
+        const double* q = C.x + e * C.x_se;
+        double cost = 0.0, rhat = 0.0;
+        for (int r = 0; r < LJ; ++r)
+        {
+            const double yd = v[r * 128], prec = a[r * 128];
+            double s = -yd;
+            for (int n = 0; n < N; ++n) s += J[r * P.j_sr + n * P.j_sc] * q[n * C.x_sk];
+            cost += prec * yd * yd;
+            rhat += prec * s * s;
+            v[r * 128] = s;
+        }
+        P.cost[e] = C.ct * cost;
+        P.rhat[e] = rhat;
+        double* Re = P.R + e * P.R_se;
+        double* re = P.r + e * P.r_se;
+        for (int i = 0; i < N; ++i)
+        {
+            double ri = 0.0;
+            for (int r = 0; r < LJ; ++r) ri += a[r * 128] * J[r * P.j_sr + i * P.j_sc] * v[r * 128];
+            re[i * P.r_sk] = ri;
+            for (int j = 0; j <= i; ++j)
+            {
+                double s = 0.0;
+                for (int r = 0; r < LJ; ++r) s += a[r * 128] * J[r * P.j_sr + i * P.j_sc] * J[r * P.j_sr + j * P.j_sc];
+                Re[i * P.R_si + j * P.R_sj] = s;
+                Re[j * P.R_si + i * P.R_sj] = s;
+            }
+        }
+    }
+}
+
 // out[b] = min / sum over t in [t_first, T) of in[b * T + t]
 __global__ void __launch_bounds__(128) exo_reduce_kernel(const double* __restrict__ in, int64_t n_traj, int T, int t_first, int op, double* __restrict__ out)
 {
@@ -126,6 +181,22 @@ cudaError_t launch_cost_gradient(const CostGradParams& P, cudaStream_t stream)
     }
     const int64_t blocks = (n_evals + 127) / 128;
     exo_cost_gradient_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aico_messages(const AicoParams& P, cudaStream_t stream)
+{
+    const int64_t n_evals = P.c.n_traj * P.c.T;
+    if (n_evals <= 0) return cudaSuccess;
+    const size_t smem = (size_t)2 * (P.length_jac > 0 ? P.length_jac : 1) * 128 * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(exo_aico_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int64_t blocks = (n_evals + 127) / 128;
+    exo_aico_messages_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, smem, stream>>>(P);
     return cudaGetLastError();
 }
 

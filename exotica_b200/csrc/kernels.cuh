@@ -176,6 +176,17 @@ struct CostGradParams
     int32_t length_jac, pad;
 };
 cudaError_t launch_cost_gradient(const CostGradParams& P, cudaStream_t stream);
+// AICO task messages of every evaluation (aico_solver.cpp:364-386): R(e)(i, j) at R[e * R_se + i * R_si + j * R_sj], r(e)(i) at
+// r[e * r_se + i * r_sk]
+struct AicoParams
+{
+    CostParams c;          // c.x = qhat
+    const double* jac;
+    double *R, *r, *rhat, *cost;
+    int64_t j_se, j_sr, j_sc, R_se, R_si, R_sj, r_se, r_sk;
+    int32_t length_jac, pad;
+};
+cudaError_t launch_aico_messages(const AicoParams& P, cudaStream_t stream);
 // op 0: min, 1: sum over t in [t_first, T) of in[b * T + t]
 cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
 void host_get_rotation(const double* data, int type, double* out9);

@@ -266,6 +266,14 @@ int exo_problem_cost_batch_host(exo_problem* problem, const double* h_x, int64_t
  * (unconstrained_end_pose_problem.cpp:84-87).  N doubles per evaluation leave the device instead of length_jacobian x N. */
 int exo_problem_cost_jacobian_batch(exo_problem* problem, const double* d_x, const double* d_phi, const double* d_jac, int64_t n_traj,
                                     int32_t layout, double* d_grad, void* stream);
+/* AICO task messages of every (trajectory, timestep) from the Phi / J of an update at the states d_qhat (same layout):
+ * AICOSolver::GetTaskCosts (exotations/solvers/exotica_aico_solver/src/aico_solver.cpp:364-386) -- for every task with
+ * precision rho > 0:  C += rho |ydiff|^2,  R += rho J^T J,  v = -ydiff + J qhat,  r += rho J^T v,  rhat += rho |v|^2;
+ * d_cost[e] = ct * C.  EXO_LAYOUT_SOA: R[N][N][E], r[N][E]; evaluation-major layouts: R[E][N][N], r[E][N]; rhat[E], cost[E].
+ * Together with exo_problem_cost_batch (GetScalarTaskCost + GetScalarTransitionCost per timestep = the solver's roll-out
+ * cost, aico_solver.cpp:440-470) this is what AICO needs from the problem per sweep. */
+int exo_problem_aico_task_messages_batch(exo_problem* problem, const double* d_qhat, const double* d_phi, const double* d_jac, int64_t n_traj,
+                                         int32_t layout, double* d_R, double* d_r, double* d_rhat, double* d_cost, void* stream);
 /* States in, cost and gradient out: d_cost_traj[n_traj] (may be NULL) and d_grad (shape and layout of d_x) as the two calls
  * above define them, without caller-side Phi / J buffers.  Serial-chain programs whose cost is made of EffFrame / EffPosition /
  * JointLimit maps run ONE fused kernel (exo_chain_costgrad_kernel): forward kinematics, ydiff with its SO(3) log, and every

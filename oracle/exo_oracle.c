@@ -1565,6 +1565,57 @@ void exo_oracle_trajectory_cost_jacobian(exo_oracle* o, const double* X, int T, 
     free(yd);
 }
 
+/* AICOSolver::GetTaskCosts (exotations/solvers/exotica_aico_solver/src/aico_solver.cpp:364-386) after prob_->Update(qhat[t], t)
+ * for every timestep of one trajectory: for each task with precision rho > 0
+ *   C += rho |ydiff_i|^2,  R += rho J_i^T J_i,  v = -ydiff_i + J_i qhat,  r += rho J_i^T v,  rhat += rho |v|^2,
+ * cost[t] = ct * C.  R[T][N][N] row-major (symmetric), r[T][N], rhat[T], cost[T]. */
+void exo_oracle_aico_task_messages(exo_oracle* o, const double* Q, int T, const double* rho, const double* goal, int T_goal, double ct,
+                                   const double* gen, int n_gen, double* R, double* r, double* rhat, double* cost)
+{
+    const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
+    double* phi = (double*)malloc((size_t)(lp > 0 ? lp : 1) * sizeof(double));
+    double* jac = (double*)malloc((size_t)(lj > 0 ? lj : 1) * N * sizeof(double));
+    double* yd = (double*)malloc((size_t)(lj > 0 ? lj : 1) * sizeof(double));
+    int t, k, i, a, b, g;
+    for (t = 0; t < T; ++t)
+    {
+        const double* q = Q + (size_t)t * N;
+        double* Rt = R + (size_t)t * N * N;
+        double* rt = r + (size_t)t * N;
+        double C = 0.0;
+        if (gen)
+            for (g = 0; g < n_gen; ++g) exo_oracle_set_generated(o, g, gen + ((size_t)t * n_gen + g) * 12);
+        exo_oracle_problem_update(o, q, phi, jac);
+        exo_oracle_problem_ydiff(o, phi, goal + (size_t)(T_goal > 1 ? t : 0) * lp, yd);
+        for (i = 0; i < N * N; ++i) Rt[i] = 0.0;
+        for (i = 0; i < N; ++i) rt[i] = 0.0;
+        rhat[t] = 0.0;
+        for (k = 0; k < o->n_maps; ++k)
+        {
+            const taskmap_t* m = &o->maps[k];
+            const double prec = rho[(size_t)t * o->n_maps + k];
+            if (!(prec > 0)) continue;
+            for (i = 0; i < m->length_jacobian; ++i)
+            {
+                const int row = m->start_jacobian + i;
+                double v = -yd[row];
+                for (a = 0; a < N; ++a) v += jac[(size_t)a * lj + row] * q[a];
+                C += prec * yd[row] * yd[row];
+                rhat[t] += prec * v * v;
+                for (a = 0; a < N; ++a)
+                {
+                    rt[a] += prec * jac[(size_t)a * lj + row] * v;
+                    for (b = 0; b < N; ++b) Rt[(size_t)a * N + b] += prec * jac[(size_t)a * lj + row] * jac[(size_t)b * lj + row];
+                }
+            }
+        }
+        cost[t] = ct * C;
+    }
+    free(phi);
+    free(jac);
+    free(yd);
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* Task-map Hessians                                                    */
 /* ------------------------------------------------------------------------------------------- */

@@ -133,6 +133,8 @@ double exo_oracle_trajectory_cost(exo_oracle* o, const double* X, int T, int t_f
                                   double ct, const double* W, const double* gen, int n_gen, double* cost_t);
 void exo_oracle_trajectory_cost_jacobian(exo_oracle* o, const double* X, int T, int t_first, const double* rho, const double* goal, int T_goal,
                                          double ct, const double* W, const double* gen, int n_gen, double* grad);
+void exo_oracle_aico_task_messages(exo_oracle* o, const double* Q, int T, const double* rho, const double* goal, int T_goal, double ct,
+                                   const double* gen, int n_gen, double* R, double* r, double* rhat, double* cost);
 
 /* ---- task-map Hessians: KinematicTree::ComputeH (kinematic_tree.cpp:947-978) + the maps' Hessian
  * overloads + the base-class fallback (task_map.cpp:99-108).  hess[length_jacobian][N][N]. */

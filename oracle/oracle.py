@@ -69,6 +69,9 @@ def lib():
         L.exo_oracle_trajectory_cost_jacobian.restype = None
         L.exo_oracle_trajectory_cost_jacobian.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_double,
                                                           _dp, _dp, ctypes.c_int, _dp]
+        L.exo_oracle_aico_task_messages.restype = None
+        L.exo_oracle_aico_task_messages.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int,
+                                                    _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
 
@@ -349,6 +352,21 @@ class Oracle(object):
         total = lib().exo_oracle_trajectory_cost(self.h, _d(X), T, int(t_first), _d(rho), _d(goal), goal.shape[0], float(ct), Wp, gp, n_gen,
                                                  _d(cost_t))
         return total, cost_t
+
+    def aico_task_messages(self, Q, rho, goal=None, ct=1.0, generated=None):
+        """AICOSolver::GetTaskCosts for every timestep of one trajectory Q[T][N] (= qhat): (R[T][N][N], r[T][N], rhat[T], cost[T])."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, self.n)
+        T = Q.shape[0]
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (T, len(self.maps))))
+        goal = self.zero_goal() if goal is None else goal
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1, self.length_phi)
+        n_gen, gp = 0, None
+        if generated is not None:
+            generated = np.ascontiguousarray(generated, dtype=np.float64).reshape(T, -1, 12)
+            n_gen, gp = generated.shape[1], _d(generated)
+        R, r, rhat, cost = np.zeros((T, self.n, self.n)), np.zeros((T, self.n)), np.zeros(T), np.zeros(T)
+        lib().exo_oracle_aico_task_messages(self.h, _d(Q), T, _d(rho), _d(goal), goal.shape[0], float(ct), gp, n_gen, _d(R), _d(r), _d(rhat), _d(cost))
+        return R, r, rhat, cost
 
     def trajectory_cost_jacobian(self, X, rho, goal=None, ct=1.0, W=None, t_first=None, generated=None):
         """Gradient of trajectory_cost with respect to X as grad[T][N] (AbstractTimeIndexedProblem::GetCostJacobian; row 0 is zero for

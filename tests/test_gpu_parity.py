@@ -523,6 +523,51 @@ def test_fused_cost_gradient_kernel(oracle_lib, case):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("layout", [_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR])
+def test_aico_task_messages(oracle_lib, layout):
+    # AICOSolver::GetTaskCosts: R = sum rho J^T J, r = sum rho J^T (-ydiff + J qhat), rhat, and the task cost per timestep
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "RPY", "EndEffector": [{"Link": "lwr_arm_7_link"}]},
+            {"type": "JointLimit", "SafePercentage": 0.1},
+            {"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_4_link"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    B, T, N = 7, 21, 7
+    rng = np.random.default_rng(51)
+    q0 = random_states(orc, B, seed=52)
+    X = np.clip(q0[:, None, :] + np.cumsum(rng.normal(0, 0.05, size=(B, T, N)), axis=1), orc.lower - 0.1, orc.upper + 0.1)
+    rho = np.ones((T, 3)) * [100.0, 1e3, 0.0]  # the third task has zero precision: skipped
+    rho[:T - 1, 0] = 0.0                       # end-effector goal at the last timestep only, as AICO problems usually have it
+    rho[5, 1] = -1.0                           # "if (prec > 0)": negative precisions are skipped too
+    goal = orc.zero_goal()
+    goal[:6] = [0.4, 0.1, 0.6, 0.3, -0.2, 0.5]
+    ct = 1.0 / 0.05 / T
+    E = B * T
+    LP, LJ = prob.length_phi, prob.length_jacobian
+    dx, dphi, djac, dR, dr, drh, dc = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N * N, E * N, E, E))
+    for b in (dR, dr, drh, dc):
+        b.fill_bytes(0xFF)
+    Xe = X.reshape(E, N)
+    dx.upload(Xe.T if layout == _capi.LAYOUT_SOA else Xe)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T, layout=layout)
+    prob.set_cost(rho, T=T, goal=goal, ct=ct)
+    prob.aico_task_messages_device(dx.ptr, dphi.ptr, djac.ptr, B, dR.ptr, dr.ptr, drh.ptr, dc.ptr, layout=layout)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    if layout == _capi.LAYOUT_SOA:
+        R = dR.download((N, N, E)).transpose(2, 0, 1).reshape(B, T, N, N)
+        r = dr.download((N, E)).T.reshape(B, T, N)
+    else:
+        R = dR.download((E, N, N)).reshape(B, T, N, N)
+        r = dr.download((E, N)).reshape(B, T, N)
+    rhat, cost = drh.download((E,)).reshape(B, T), dc.download((E,)).reshape(B, T)
+    for b in range(B):
+        R_ref, r_ref, rhat_ref, cost_ref = orc.aico_task_messages(X[b], rho, goal=goal, ct=ct)
+        for got, ref in ((R[b], R_ref), (r[b], r_ref), (rhat[b], rhat_ref), (cost[b], cost_ref)):
+            assert np.max(np.abs(got - ref)) <= 1e-10 * max(1.0, np.abs(ref).max())
+        assert np.array_equal(R[b], R[b].transpose(0, 2, 1))
+        assert not R[b, 5, :, :].any() or rho[5, 0] > 0  # timestep 5: JointLimit skipped (negative rho), EffFrame rho 0
+
+
 def test_end_pose_cost_jacobian_and_finite_differences(oracle_lib):
     # UnconstrainedEndPoseProblem::GetScalarJacobian = 2 J^T S ydiff; for position-type maps it is the exact gradient of the cost
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")

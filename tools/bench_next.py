@@ -84,6 +84,12 @@ def main():
     line("fused FK + cost + gradient (exo_chain_costgrad_kernel + per-trajectory sum; J never materialised), device", ms, E, "evals", 8 * (2 * N + 1),
          kernel=backend.last_kernel())
 
+    dR, dr, drh, dcc = (_capi.DeviceBuffer(n) for n in (E * N * N, E * N, E, E))
+    ms = timed(lambda: backend.aico_task_messages_device(dx.ptr, dphi.ptr, djac.ptr, B, dR.ptr, dr.ptr, drh.ptr, dcc.ptr), args.reps)
+    line("AICO task messages R, r, rhat, cost (reads x, Phi, J; writes N^2 + N + 2 per eval), device", ms, E, "evals", 8 * (N + LP + LJ * N + N * N + N + 2))
+    for b in (dR, dr, drh, dcc):
+        b.free()
+
     # Hessians: length_jacobian x N x N doubles per evaluation
     EH = 1 << 16
     dh = _capi.DeviceBuffer(EH * LJ * N * N)
