@@ -307,7 +307,9 @@ __device__ __forceinline__ void emit_spheres_warp(const Op& op, const double* c,
 template <int TPB, int W>
 __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
 {
-    constexpr int CS = TPB / 32 * W;  // scratch columns per CTA
+    // scratch columns per CTA; full-width tiles get one padding column so that a warp can also read one COLUMN (consecutive
+    // words of one evaluation, stride CS doubles) without bank conflicts -- the split SphereCollision launch parks rows that way
+    constexpr int CS = TPB / 32 * W + (W == 32 ? 1 : 0);
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     // ---- stage the program (topology, axes, offsets, tables) once per CTA ---------------------------------
@@ -330,7 +332,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
     const int pos_base = joint_base;  // two-pass programs park 3 doubles per requested frame where the joint slots would be
     double* qs = scr + (size_t)H->scratch_doubles * CS;
     // per-warp area behind the per-thread scratch: sphere centre table (4 doubles per sphere) + Jacobian row accumulators
-    double* warp_smem = reinterpret_cast<double*>(smem + P.scratch_offset) + (size_t)(H->scratch_doubles + N) * CS +
+    double* warp_smem = reinterpret_cast<double*>(smem + P.scratch_offset) + ((((size_t)(H->scratch_doubles + N) * CS) + 1) & ~(size_t)1) +
                         (size_t)(tid >> 5) * (4 * H->max_spheres + N + (N & 1));  // even number of doubles: 16-byte aligned tables
     const bool want_j = P.jac != nullptr;
 
@@ -606,14 +608,20 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
             }
             else if (op.kind == OP_EMIT_SPHERES && P.sph_dump)
             {
-                // split launch: park this evaluation's slots for exo_spheres_kernel (one row per evaluation; the partial sectors
-                // of neighbouring words merge in L2 before they reach HBM)
-                if (lane < W && slot < n_valid)
+                // split launch: park every evaluation's slots for exo_spheres_kernel, one contiguous row each.  The warp transposes
+                // its tile on the way out: for one evaluation at a time, lane k copies words k, k + 32, ... (coalesced 256-byte stores;
+                // the shared-memory side is conflict-free thanks to the padding column)
+                __syncwarp();
                 {
                     const int words = H->scratch_doubles;
-                    double* d = P.sph_dump + (int64_t)sph_ord * P.sph_block + e * P.sph_row;
-                    for (int k = 0; k < words; ++k) d[k] = scr[k * CS];
+                    const double* tile = scr - col + (tid >> 5) * W;  // column of the tile's first evaluation
+                    for (int ev = 0; ev < n_valid; ++ev)
+                    {
+                        double* d = P.sph_dump + (int64_t)sph_ord * P.sph_block + (e0 + ev) * P.sph_row;
+                        for (int k = lane; k < words; k += 32) d[k] = tile[ev + k * CS];
+                    }
                 }
+                __syncwarp();
                 ++sph_ord;
             }
             else if (op.kind == OP_EMIT_SPHERES)
@@ -707,7 +715,8 @@ __global__ void __maxnreg__(EXO_SPHERES_MAXNREG) exo_spheres_kernel(const Kernel
 template <int TPB, int W>
 cudaError_t try_config(size_t prog, size_t per_column, size_t per_warp, int max_smem, int& ctas_per_sm, size_t& smem_bytes)
 {
-    smem_bytes = prog + per_column * (TPB / 32 * W) + per_warp * (TPB / 32);
+    // CS of the kernel (padding column); the per-warp tables behind the scratch start on a 16-byte boundary
+    smem_bytes = prog + ((per_column * (TPB / 32 * W + (W == 32 ? 1 : 0)) + 15) & ~(size_t)15) + per_warp * (TPB / 32);
     ctas_per_sm = 0;
     if (smem_bytes > (size_t)max_smem) return cudaSuccess;
     cudaError_t err = cudaFuncSetAttribute(exo_eval_kernel<TPB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

@@ -59,7 +59,7 @@ def main():
     rng = np.random.default_rng(7)
     q0 = rng.uniform(lim[:, 0], lim[:, 1], size=(B, 1, N))
     X = np.clip(q0 + np.cumsum(rng.normal(0, 0.02, size=(B, T, N)), axis=1), lim[:, 0], lim[:, 1])
-    backend = _capi.Problem.__new__(_capi.Problem)
+    backend = _capi.Problem.__new__(_capi.Problem)  # a view of the host problem's backend handle: borrowed, released below
     backend.h = _host.lib().exo_host_problem_backend(prob._h)
     dx, dphi, djac, dg, dc = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N, B))
     dx.upload(X.reshape(E, N).T)
@@ -117,6 +117,10 @@ def main():
     prob.cost_batch(X)
     t2 = time.perf_counter()
     line("host path: X in, cost out (FK only)", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * B)
+
+    backend.h = None  # borrowed handle: the host problem owns (and destroys) it
+    for b in (dx, dphi, djac, dg, dc):
+        b.free()
 
     # multi-start IK on example_ik.xml's problem shape
     maps = [("exotica/EffFrame", {"Name": "Eff", "EndEffector": [frame("lwr_arm_6_link")]})]
