@@ -182,50 +182,40 @@ def test_sibling_maps_through_the_factory(oracle_lib):
                                                                           "Maps": [("exotica/JointPose", {"Name": "P", "JointMap": "9"})]}))
 
 
+def _golden_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _as_initializer(v):
+    """JSON lists [name, {fields}] -> the (name, dict) tuples Setup.create_problem takes."""
+    if isinstance(v, list) and len(v) == 2 and isinstance(v[0], str) and isinstance(v[1], dict):
+        return (v[0], {k: _as_initializer(x) for k, x in v[1].items()})
+    if isinstance(v, list):
+        return [_as_initializer(x) for x in v]
+    return v
+
+
 @pytest.mark.gpu
-def test_center_of_mass_reference_goldens_on_the_gpu():
-    # test_maps.cpp:789-892 through the factory on the GPU path: the reference's own inputs and expected outputs
-    # (a) all links, (b) EndEffector = link2, endeff, (c) all links on the XY plane
-    cases = [
-        ({"EnableZ": "1"},
-         [-0.281809, 0.10497, 0.15886, -0.0948483, 0.374775, -0.80072, 0.061616, 0.514588, -0.39141, 0.984457, 0.153942, 0.755228, 0.495619,
-          0.25782, -0.929158],
-         [0.081112, -0.0234831, 0.924368, 0.0080578, -0.000766568, 0.895465, 0.157569, 0.00972105, 0.897157, 0.117213, 0.176455, 0.846633,
-          -0.0587457, -0.0317596, 0.877501],
-         [0.0234831, 0.455657, 0.200919, 0.081112, -0.131919, -0.0581688, 0, -0.0844429, -0.0565023, 0.000766568, 0.443462, 0.19642, 0.0080578,
-          -0.0421882, -0.0186862, 0, -0.00809418, 0.0895227, -0.00972105, 0.446309, 0.214617, 0.157569, 0.0275346, 0.0132406, 0, -0.157868,
-          -0.0266211, -0.176455, 0.219463, 0.0736575, 0.117213, 0.330384, 0.110885, 0, -0.211838, -0.170949, 0.0317596, 0.376061, 0.149235,
-          -0.0587457, 0.203309, 0.0806805, 0, 0.0667812, 0.134774]),
-        ({"EnableZ": "1", "EndEffector": [("exotica/Frame", {"Link": "link2"}), ("exotica/Frame", {"Link": "endeff"})]},
-         [0.299414, -0.503912, 0.258959, -0.541726, 0.40124, -0.366266, -0.342446, -0.537144, -0.851678, 0.266144, -0.552687, 0.302264,
-          0.0213719, 0.942931, -0.439916],
-         [-0.167532, -0.0517162, 0.913823, 0.083533, -0.0502684, 0.931962, -0.3632, 0.129477, 0.693081, -0.17971, -0.048991, 0.907923, 0.314586,
-          0.00672432, 0.823106],
-         [0.0517162, 0.443188, 0.254921, -0.167532, 0.13681, 0.0786927, 0, 0.175333, 0.0666905, 0.0502684, 0.412954, 0.235481, 0.083533,
-          -0.248507, -0.141708, 0, -0.0974919, -0.00961589, -0.129477, 0.228967, 0.0468775, -0.3632, -0.0816248, -0.0167114, 0, 0.385588,
-          0.270459, 0.048991, 0.441801, 0.257042, -0.17971, 0.12044, 0.0700725, 0, 0.186268, 0.0681488, -0.00672432, 0.373021, 0.240882,
-          0.314586, 0.00797337, 0.00514888, 0, -0.314658, -0.132569]),
-        ({"EnableZ": "0"},
-         [0.350952, -0.0340994, -0.0361284, -0.390089, 0.424175, -0.634888, 0.243646, -0.918271, -0.172033, 0.391968, 0.347873, 0.27528,
-          -0.305768, -0.630755, 0.218212],
-         [-0.0228141, -0.0083524, 0.0595937, -0.0245025, -0.392081, -0.0974653, 0.200868, 0.0830305, -0.232814, 0.0734919],
-         [0.0083524, 0.453225, 0.202958, -0.0228141, 0.165929, 0.0743046, 0.0245025, 0.420734, 0.195957, 0.0595937, -0.172988, -0.0805696,
-          0.0974653, 0.254325, 0.0971889, -0.392081, 0.0632213, 0.0241597, -0.0830305, 0.394279, 0.162599, 0.200868, 0.162978, 0.0672114,
-          -0.0734919, 0.394649, 0.189283, -0.232814, -0.124578, -0.0597504]),
-    ]
-    for extra, X, Y, J in cases:
-        dim = 2 if extra["EnableZ"] == "0" else 3
-        X, Y, J = np.array(X).reshape(5, 3), np.array(Y).reshape(5, dim), np.array(J).reshape(5, dim, 3)
-        m = {"Name": "MyTask"}
-        m.update(extra)
-        init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("test_robot", "arm"), "Maps": [("exotica/CenterOfMass", m)],
-                                                        "Cost": [("exotica/Task", {"Task": "MyTask"})]})
-        prob = exo.Setup.create_problem(init)
-        assert (prob.length_Phi, prob.length_jacobian) == (dim, dim)
-        phi, jac = prob.update_batch(X)
-        for i in range(5):
-            assert np.linalg.norm(phi[i] - Y[i]) < 1e-5
-            assert np.linalg.norm(jac[i] - J[i]) < 1e-5
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_reference_goldens_on_the_gpu(case):
+    # the reference's own inputs and expected outputs (test_maps.cpp, see tests/golden/reference_goldens.json) through the
+    # task-map factory and the GPU path, with the reference's tolerance
+    X, Y, J = np.array(case["X"]), np.array(case["Y"]), np.array(case["J"])
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init(case["robot"], case["joint_group"]),
+                                                    "Maps": [_as_initializer(case["initializer"])], "Cost": [("exotica/Task", {"Task": "MyTask"})]})
+    prob = exo.Setup.create_problem(init)
+    assert (prob.length_Phi, prob.length_jacobian) == (Y.shape[1], J.shape[1])
+    phi, jac = prob.update_batch(X)
+    for i in range(X.shape[0]):
+        assert np.linalg.norm(phi[i] - Y[i]) < case["tolerance"]
+        assert np.linalg.norm(jac[i] - J[i]) < case["tolerance"]
+
+
+@pytest.mark.gpu
+def test_center_of_mass_rejects_relative_frames():
     with pytest.raises(exo.ExoticaError, match="base other than root"):
         exo.Setup.create_problem(("exotica/UnconstrainedEndPoseProblem", {
             "Name": "p", "PlanningScene": _scene_init("test_robot", "arm"),

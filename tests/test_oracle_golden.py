@@ -1,13 +1,16 @@
 """Pins the CPU oracle against every known-answer vector the reference's own tests hold for this path
 (SURVEY.md section 8c):
 
-  * EffPosition goldens      exotations/exotica_core_task_maps/test/test_maps.cpp:340-347 (eps 1e-5)
-  * SphereCollision goldens  exotations/exotica_core_task_maps/test/test_maps.cpp:651-673 (eps 1e-5)
+  * tests/golden/reference_goldens.json: EffPosition, Distance, SphereCollision, JointPose (3) and CenterOfMass (3) blocks of
+    exotations/exotica_core_task_maps/test/test_maps.cpp (eps 1e-5), extracted by tests/golden/extract_reference_goldens.py
   * Valkyrie centre of mass  exotica_examples/test/test_valkyrie_com:13-120 (Drake, assert_allclose rtol 1e-7)
 
-The golden numbers below are the reference's test data (not code); robots are the kinematics-only fixtures
+The golden numbers are the reference's test data (not code); robots are the kinematics-only fixtures
 written by tests/golden/make_robot_fixtures.py.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -30,51 +33,16 @@ def test_test_robot_structure(test_robot):
     np.testing.assert_allclose(t.upper, 0.4)
 
 
-def test_eff_position_goldens(test_robot):
-    # test_maps.cpp:340-347
-    X = np.array([0.680375, -0.211234, 0.566198, 0.59688, 0.823295, -0.604897, -0.329554, 0.536459, -0.444451, 0.10794,
-                  -0.0452059, 0.257742, -0.270431, 0.0268018, 0.904459]).reshape(5, 3)
-    Y = np.array([0.0645323, 0.0522249, 1.21417, 0.292945, 0.199075, 1.12724, 0.208378, -0.0712708, 1.19893, 0.0786457,
-                  0.00852213, 1.23952, 0.356984, -0.0989639, 1.06844]).reshape(5, 3)
-    J = np.array([-0.0522249, 0.594015, 0.327994, 0.0645323, 0.480726, 0.26544, 0, -0.0830172, -0.156401, -0.199075,
-                  0.560144, 0.363351, 0.292945, 0.380655, 0.246921, 0, -0.354186, -0.0974994, 0.0712708, 0.708627,
-                  0.423983, 0.208378, -0.24237, -0.145014, 0, -0.220229, -0.0413455, -0.00852213, 0.784922, 0.437315,
-                  0.0786457, 0.085055, 0.0473879, 0, -0.0791061, -0.0949228, 0.0989639, 0.595968, 0.258809, 0.356984,
-                  -0.165215, -0.0717477, 0, -0.370448, -0.361068]).reshape(5, 3, 3)
-    test_robot.set_problem([{"type": "EffPosition", "EndEffector": [{"Link": "endeff"}]}])
-    for i in range(5):
-        phi, jac = test_robot.problem_update(X[i])
-        # the reference test uses ||.|| < 1e-5 on 6-significant-figure goldens
-        assert np.linalg.norm(phi - Y[i]) < 1e-5
-        assert np.linalg.norm(jac - J[i]) < 1e-5
-
-
-def test_sphere_collision_goldens(test_robot):
-    # test_maps.cpp:651-673
-    X = np.array([-0.590167, 1.2309, 1.67611, -1.72098, 1.79731, 0.103981, -1.65578, -1.23114, 0.652908, 1.56093,
-                  -0.604428, -1.74331, -1.91991, -0.169193, -1.74762]).reshape(5, 3)
-    Y = np.array([1, 5.71023e-44, 1.83279e-110, 6.87352e-16, 7.26371e-45])
-    J = np.array([0, 0.431392, 0.449344, 0, 0.431735, 0.26014, 0, -0.234475, -0.0135658, 0, -0.349195, -0.447214, 0,
-                  -0.270171, -0.430172]).reshape(5, 1, 3)
-    test_robot.set_problem([{"type": "SphereCollision", "Precision": 1e-2,
-                             "EndEffector": [{"Link": "base", "Radius": 0.3, "Group": "base"},
-                                             {"Link": "endeff", "Radius": 0.3, "Group": "eff"}]}])
-    assert test_robot.length_phi == 1 and test_robot.length_jacobian == 1
-    for i in range(5):
-        phi, jac = test_robot.problem_update(X[i])
-        assert abs(phi[0] - Y[i]) < 1e-5
-        if Y[i] > 1e-300:
-            # x is printed to 6 digits and phi = 1/(1+exp(500*(d-0.6))): a 1e-6 error in d is a 5e-4 relative
-            # error in phi, so the tail values can only be pinned to ~1e-3 relative
-            assert abs(phi[0] - Y[i]) / Y[i] < 2e-3
-        assert np.linalg.norm(jac - J[i]) < 1e-5
+def _golden_cases():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")) as f:
+        return json.load(f)["cases"]
 
 
 def _com_frames(orc, links=None):
     """CenterOfMass::Initialize (center_of_mass.cpp:150-170): the frame offset is the link's centre of gravity, its weight the
     link's mass; without EndEffector entries the map walks every robot link with mass (:88-117).  The masses are the tree's:
     for a fixed base the first child of the root link carries the ROOT's inertial (kinematic_tree.cpp:264-268), so link1 of the
-    test robot is massless in the reference -- the goldens below only come out with that quirk in place."""
+    test robot is massless in the reference -- the CenterOfMass goldens only come out with that quirk in place."""
     out = []
     for e in orc.tree.elements:
         if e.is_robot_link and e.mass > 0 and (links is None or e.link_name in links):
@@ -82,44 +50,30 @@ def _com_frames(orc, links=None):
     return out
 
 
-def test_center_of_mass_goldens(test_robot):
-    # test_maps.cpp:789-892: (a) all links, (b) EndEffector = link2, endeff, (c) all links projected on the XY plane
-    cases = [
-        (None, True,
-         [-0.281809, 0.10497, 0.15886, -0.0948483, 0.374775, -0.80072, 0.061616, 0.514588, -0.39141, 0.984457, 0.153942, 0.755228, 0.495619,
-          0.25782, -0.929158],
-         [0.081112, -0.0234831, 0.924368, 0.0080578, -0.000766568, 0.895465, 0.157569, 0.00972105, 0.897157, 0.117213, 0.176455, 0.846633,
-          -0.0587457, -0.0317596, 0.877501],
-         [0.0234831, 0.455657, 0.200919, 0.081112, -0.131919, -0.0581688, 0, -0.0844429, -0.0565023, 0.000766568, 0.443462, 0.19642, 0.0080578,
-          -0.0421882, -0.0186862, 0, -0.00809418, 0.0895227, -0.00972105, 0.446309, 0.214617, 0.157569, 0.0275346, 0.0132406, 0, -0.157868,
-          -0.0266211, -0.176455, 0.219463, 0.0736575, 0.117213, 0.330384, 0.110885, 0, -0.211838, -0.170949, 0.0317596, 0.376061, 0.149235,
-          -0.0587457, 0.203309, 0.0806805, 0, 0.0667812, 0.134774]),
-        (("link2", "endeff"), True,
-         [0.299414, -0.503912, 0.258959, -0.541726, 0.40124, -0.366266, -0.342446, -0.537144, -0.851678, 0.266144, -0.552687, 0.302264,
-          0.0213719, 0.942931, -0.439916],
-         [-0.167532, -0.0517162, 0.913823, 0.083533, -0.0502684, 0.931962, -0.3632, 0.129477, 0.693081, -0.17971, -0.048991, 0.907923, 0.314586,
-          0.00672432, 0.823106],
-         [0.0517162, 0.443188, 0.254921, -0.167532, 0.13681, 0.0786927, 0, 0.175333, 0.0666905, 0.0502684, 0.412954, 0.235481, 0.083533,
-          -0.248507, -0.141708, 0, -0.0974919, -0.00961589, -0.129477, 0.228967, 0.0468775, -0.3632, -0.0816248, -0.0167114, 0, 0.385588,
-          0.270459, 0.048991, 0.441801, 0.257042, -0.17971, 0.12044, 0.0700725, 0, 0.186268, 0.0681488, -0.00672432, 0.373021, 0.240882,
-          0.314586, 0.00797337, 0.00514888, 0, -0.314658, -0.132569]),
-        (None, False,
-         [0.350952, -0.0340994, -0.0361284, -0.390089, 0.424175, -0.634888, 0.243646, -0.918271, -0.172033, 0.391968, 0.347873, 0.27528,
-          -0.305768, -0.630755, 0.218212],
-         [-0.0228141, -0.0083524, 0.0595937, -0.0245025, -0.392081, -0.0974653, 0.200868, 0.0830305, -0.232814, 0.0734919],
-         [0.0083524, 0.453225, 0.202958, -0.0228141, 0.165929, 0.0743046, 0.0245025, 0.420734, 0.195957, 0.0595937, -0.172988, -0.0805696,
-          0.0974653, 0.254325, 0.0971889, -0.392081, 0.0632213, 0.0241597, -0.0830305, 0.394279, 0.162599, 0.200868, 0.162978, 0.0672114,
-          -0.0734919, 0.394649, 0.189283, -0.232814, -0.124578, -0.0597504]),
-    ]
-    for links, enable_z, X, Y, J in cases:
-        dim = 3 if enable_z else 2
-        X, Y, J = np.array(X).reshape(5, 3), np.array(Y).reshape(5, dim), np.array(J).reshape(5, dim, 3)
-        test_robot.set_problem([{"type": "CenterOfMass", "EnableZ": enable_z, "EndEffector": _com_frames(test_robot, links)}])
-        assert test_robot.length_phi == dim and test_robot.length_jacobian == dim
-        for i in range(5):
-            phi, jac = test_robot.problem_update(X[i])
-            assert np.linalg.norm(phi - Y[i]) < 1e-5
-            assert np.linalg.norm(jac - J[i]) < 1e-5
+def oracle_map_spec(orc, spec):
+    """tests/golden/reference_goldens.json "map" entry -> the dict oracle.set_problem takes."""
+    spec = dict(spec)
+    if spec["type"] == "CenterOfMass":
+        spec["EndEffector"] = _com_frames(orc, spec.pop("links"))
+    return spec
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_reference_goldens(test_robot, case):
+    """Every golden vector the reference's test_maps.cpp holds for maps on the hot path (tests/golden/reference_goldens.json,
+    extracted by tests/golden/extract_reference_goldens.py): EffPosition :340-347, Distance :493-500, SphereCollision :651-673,
+    JointPose :700-780, CenterOfMass :789-892.  The reference's test_values() uses ||.|| < 1e-5 on 6-significant-figure numbers."""
+    X, Y, J = np.array(case["X"]), np.array(case["Y"]), np.array(case["J"])
+    test_robot.set_problem([oracle_map_spec(test_robot, case["map"])])
+    assert test_robot.length_phi == Y.shape[1] and test_robot.length_jacobian == J.shape[1]
+    for i in range(X.shape[0]):
+        phi, jac = test_robot.problem_update(X[i])
+        assert np.linalg.norm(phi - Y[i]) < case["tolerance"]
+        assert np.linalg.norm(jac - J[i]) < case["tolerance"]
+        if case["map"]["type"] == "SphereCollision" and Y[i][0] > 1e-300:
+            # x is printed to 6 digits and phi = 1/(1+exp(500*(d-0.6))): a 1e-6 error in d is a 5e-4 relative error in phi,
+            # so the tail values can only be pinned to ~1e-3 relative
+            assert abs(phi[0] - Y[i][0]) / Y[i][0] < 2e-3
 
 
 VALKYRIE_COM = [
