@@ -39,21 +39,31 @@ def gpu_problem_from_maps(orc, maps, tree_state=None):
     return tree, prob
 
 
+GUARD = 64  # doubles behind every output buffer that the kernels must leave untouched
+
+
+def _guard_intact(buf, n):
+    tail = buf.download((n + GUARD,))[n:]
+    return bool((tail.view(np.uint64) == np.uint64(0xFFFFFFFFFFFFFFFF)).all())
+
+
 def run_gpu(prob, X, layout=_capi.LAYOUT_SOA, T=1, want_jacobian=True):
     """X[E][N] (always evaluation-major here) -> Phi[E][LP], J[E][LJ][N] via device buffers in `layout`."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     E, N = X.shape
     LP, LJ = prob.length_phi, prob.length_jacobian
     dx = _capi.DeviceBuffer(max(E * N, 1))
-    dphi = _capi.DeviceBuffer(max(E * LP, 1))
-    djac = _capi.DeviceBuffer(max(E * LJ * N, 1)) if want_jacobian else None
-    # poison the outputs: the kernel must write every entry itself
+    dphi = _capi.DeviceBuffer(E * LP + GUARD)
+    djac = _capi.DeviceBuffer(E * LJ * N + GUARD) if want_jacobian else None
+    # poison the outputs: the kernel must write every entry itself -- and nothing behind the end of the buffers
     dphi.fill_bytes(0xFF)
     if djac is not None:
         djac.fill_bytes(0xFF)
     dx.upload(X.T if layout == _capi.LAYOUT_SOA else X)
     prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr if djac is not None else None, T=T, layout=layout)
     _capi.check(_capi.lib().exo_device_synchronize())
+    assert _guard_intact(dphi, E * LP), "write behind the end of Phi"
+    assert djac is None or _guard_intact(djac, E * LJ * N), "write behind the end of J"
     if layout == _capi.LAYOUT_SOA:
         phi = dphi.download((LP, E)).T
         jac = djac.download((LJ, N, E)).transpose(2, 0, 1) if want_jacobian else None
