@@ -43,6 +43,10 @@ struct exo_tree
     int64_t version = 0;  // bumped when model state / limits change, so problems recompile
 };
 
+#ifndef EXO_PIPE_NBUF
+#define EXO_PIPE_NBUF 8  // chunks in flight (measured on cfg2a, 64 MiB chunks: 3 -> 8.35 ms, 4 -> 8.03, 6 -> 8.05, 8 -> 7.96 ms per 461 MB step); in the host-buffer pipelines (one stream and one buffer set each)
+#endif
+
 struct exo_problem
 {
     exo_tree* tree = nullptr;
@@ -97,13 +101,13 @@ struct exo_problem
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     // host pipeline
-    static const int NBUF = 3;
-    cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
-    double* d_x[NBUF] = {nullptr, nullptr, nullptr};
-    double* d_phi[NBUF] = {nullptr, nullptr, nullptr};
-    double* d_jac[NBUF] = {nullptr, nullptr, nullptr};
-    double* d_cost[NBUF] = {nullptr, nullptr, nullptr};
-    double* d_grad[NBUF] = {nullptr, nullptr, nullptr};
+    static const int NBUF = EXO_PIPE_NBUF;
+    cudaStream_t streams[NBUF] = {};
+    double* d_x[NBUF] = {};
+    double* d_phi[NBUF] = {};
+    double* d_jac[NBUF] = {};
+    double* d_cost[NBUF] = {};
+    double* d_grad[NBUF] = {};
     int64_t pipe_chunk = 0;
     bool pipe_has_jac = false;
 };
