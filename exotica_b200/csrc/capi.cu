@@ -1427,11 +1427,50 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     C.W = nullptr;  // end-pose problems have no transition cost
     CUDA_TRY(launch_ik_init(K, prm->regularization_rate, stream));
     int rc = EXO_OK;
-    for (int it = 0; it < prm->max_iterations; ++it)
+    if (p->compiled_version != p->tree->version)
+    {
+        rc = compile_and_upload(p);
+        if (rc != EXO_OK) return rc;
+    }
+    // fused line search where the fused cost kernel applies (serial chains, EffFrame / EffPosition / JointLimit costs)
+    ChainGradParams G;
+    memset(&G, 0, sizeof(G));
+    const bool fused_ls = fused_costgrad_eligible(p, G);
+    ChainLineSearchParams LS;
+    memset(&LS, 0, sizeof(LS));
+    if (fused_ls)
+    {
+        G.rho = C.rho; G.goal = C.goal; G.goal_rot = C.goal_rot; G.W = nullptr;
+        G.ct = C.ct;
+        G.T = 1; G.t_first = 0; G.T_goal = C.T_goal; G.n_maps = C.n_maps; G.length_phi = C.length_phi; G.n_rot = C.n_rot;
+        LS.q = d_q; LS.q_trial = K.q_trial; LS.qd = K.qd; LS.err_prev = K.err_prev; LS.cost = d_cost; LS.active = K.active; LS.ls_done = K.ls_done;
+    }
+    // Chain programs: the line search of every iteration is one fused kernel (exo_problem_set_kernel(1) takes the trial /
+    // update / accept launches instead).  EXO_IK_ONE_LAUNCH=1 runs the WHOLE solve as one launch, every lane iterating on its
+    // own -- no host round trips, but a lane's 100 iterations are one serial instruction stream at 12 warps/SM: measured
+    // 24.7 ms against 16.5 ms for 65 536 LWR starts, so it is opt-in (useful where the host must not be involved, e.g. inside
+    // a captured graph).
+    const char* one_env = getenv("EXO_IK_ONE_LAUNCH");
+    const bool one_launch = fused_ls && one_env && one_env[0] == '1';
+    if (one_launch)
+    {
+        chain_bind(p->chain, d_q, d_phi, d_jac, E, 1, E, 1, E, 1, (int64_t)N * E, E);
+        CUDA_TRY(chain_ik_solve_launch(p->chain, G, LS, K, C, prm->max_iterations, stream));
+        p->launches++;
+    }
+    for (int it = 0; it < (one_launch ? 0 : prm->max_iterations); ++it)
     {
         rc = launch(p, d_q, E, E, 1, EXO_LAYOUT_SOA, d_phi, d_jac, stream, false);  // prob_->Update(q_)
         if (rc != EXO_OK) return rc;
         CUDA_TRY(launch_ik_step(K, C, stream));
+        if (fused_ls)
+        {
+            // chain programs: the ten trial states are evaluated in registers by one kernel
+            chain_bind(p->chain, K.q_trial, nullptr, nullptr, E, 1, E, 1, E, 1, (int64_t)N * E, E);
+            CUDA_TRY(chain_ik_linesearch_launch(p->chain, G, LS, stream));
+            p->launches++;
+        }
+        else
         for (int ai = 0; ai < 10; ++ai)
         {
             const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)

@@ -31,6 +31,7 @@
 
 #include "compiler.h"
 #include "cost_device.cuh"
+#include "ik_device.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
 
@@ -734,6 +735,249 @@ __global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(cons
     }
 }
 
+// ct * (ydiff^T S ydiff + transition term) of the state at xe, formed in registers (the cost half of the kernel above)
+template <int NJ, bool ALLREV>
+__device__ __forceinline__ double chain_cost_only(const ChainParams& P, const ChainGradParams& G, const char* xe, int t)
+{
+    double q[NJ], sn[NJ], cs[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+    {
+        const double th = fma(P.joint[j].qmult, q[j], P.joint[j].th0);
+        sn[j] = 0.0;
+        cs[j] = 1.0;
+        if (ALLREV || !P.joint[j].prismatic)
+        {
+            if (fabs(th) <= 1.0e5)
+                fast_sincos(th, sn[j], cs[j]);
+            else
+                sincos(th, &sn[j], &cs[j]);
+        }
+    }
+    Fr cur = load_frame(P.base);
+    ChainUnroll<NJ, ALLREV, 0>::compose(P, cur, q, sn, cs);
+    const double* rho = G.rho + (int64_t)t * G.n_maps;
+    const int tg = G.T_goal > 1 ? t : 0;
+    const double* goal = G.goal + (int64_t)tg * G.length_phi;
+    const double* grot = G.goal_rot + (int64_t)tg * G.n_rot * 9;
+    double c = 0.0;
+    for (int f = 0; f < P.n_frames; ++f)
+    {
+        const ChainFrameP& fp = P.frame[f];
+        const Fr A = chain_frame_a(fp, cur);
+        const Fr Ph = fp.b_const ? fr_mul(load_frame(fp.binv), A) : A;
+        const double* gl = goal + fp.phi_off;
+        const double d0 = Ph.x - gl[0], d1 = Ph.y - gl[1], d2 = Ph.z - gl[2];
+        double s = d0 * d0 + d1 * d1 + d2 * d2;
+        if (G.frame_rot[f] >= 0)
+        {
+            const double* M2 = grot + 9 * G.frame_rot[f];
+            Fr M;
+            M.m0 = M2[0] * Ph.m0 + M2[3] * Ph.m3 + M2[6] * Ph.m6;
+            M.m1 = M2[0] * Ph.m1 + M2[3] * Ph.m4 + M2[6] * Ph.m7;
+            M.m2 = M2[0] * Ph.m2 + M2[3] * Ph.m5 + M2[6] * Ph.m8;
+            M.m3 = M2[1] * Ph.m0 + M2[4] * Ph.m3 + M2[7] * Ph.m6;
+            M.m4 = M2[1] * Ph.m1 + M2[4] * Ph.m4 + M2[7] * Ph.m7;
+            M.m5 = M2[1] * Ph.m2 + M2[4] * Ph.m5 + M2[7] * Ph.m8;
+            M.m6 = M2[2] * Ph.m0 + M2[5] * Ph.m3 + M2[8] * Ph.m6;
+            M.m7 = M2[2] * Ph.m1 + M2[5] * Ph.m4 + M2[8] * Ph.m7;
+            M.m8 = M2[2] * Ph.m2 + M2[5] * Ph.m5 + M2[8] * Ph.m8;
+            M.x = M.y = M.z = 0.0;
+            double vx, vy, vz;
+            get_angle_axis(M, vx, vy, vz);
+            const double r0 = Ph.m0 * vx + Ph.m1 * vy + Ph.m2 * vz;
+            const double r1 = Ph.m3 * vx + Ph.m4 * vy + Ph.m5 * vz;
+            const double r2 = Ph.m6 * vx + Ph.m7 * vy + Ph.m8 * vz;
+            s += r0 * r0 + r1 * r1 + r2 * r2;
+        }
+        c += rho[G.frame_map[f]] * s;
+    }
+    const double rho_jl = G.jl_map >= 0 ? rho[G.jl_map] : 0.0;
+    for (int n = 0; n < P.n_ctrl; ++n) costgrad_column_extra(P, G, xe, t, n, rho_jl, goal, c);
+    return G.ct * c;
+}
+
+// IKSolver::Solve's backtracking line search (ik_solver.cpp:146-161) for every active start state: the first of the ten steps
+// alpha = 1, 0.9, ..., 0.1 whose cost is below the current one is taken (q <- q - alpha qd, qd <- alpha qd).
+template <int NJ, bool ALLREV>
+__global__ void __maxnreg__(128) exo_chain_ik_linesearch_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G,
+                                                                const __grid_constant__ ChainLineSearchParams L)
+{
+    const int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x;
+    if (e >= P.n_evals || !L.active[e] || L.ls_done[e]) return;
+    const int N = P.n_ctrl;
+    const int64_t E = P.n_evals;
+    const char* xe = reinterpret_cast<const char*>(L.q_trial) + e * P.x_se_b;
+    const double err_prev = L.err_prev[e];
+    for (int ai = 0; ai < 10; ++ai)
+    {
+        const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+        for (int c = 0; c < N; ++c) L.q_trial[(int64_t)c * E + e] = L.q[(int64_t)c * E + e] - alpha * L.qd[(int64_t)c * E + e];
+        const double error = chain_cost_only<NJ, ALLREV>(P, G, xe, 0);
+        L.cost[e] = error;  // error_: the cost at the last state evaluated
+        if (error < err_prev)
+        {
+            for (int c = 0; c < N; ++c)
+            {
+                L.q[(int64_t)c * E + e] = L.q_trial[(int64_t)c * E + e];
+                L.qd[(int64_t)c * E + e] *= alpha;
+            }
+            L.ls_done[e] = 1;
+            break;
+        }
+    }
+}
+
+// One evaluation (Phi and J of every map of the program) with the generic row emitter: what exo_chain_kernel computes, without
+// its streaming machinery -- used inside the single-launch IK solve, where Phi and J go to an L2-resident workspace
+template <int NJ, bool ALLREV>
+__device__ __forceinline__ void chain_eval_one(const ChainParams& P, const char* xe, char* phi_e, char* jac_e)
+{
+    if (P.has_prefix)
+    {
+        Sink o;
+        o.phi = reinterpret_cast<double*>(phi_e);
+        o.jac = reinterpret_cast<double*>(jac_e);
+        o.phi_sk = P.phi_sk;
+        o.j_sr = P.j_sr;
+        o.j_sc = P.j_sc;
+        chain_prefix(P, o, reinterpret_cast<const double*>(xe), P.x_sk);
+    }
+    double q[NJ], sn[NJ], cs[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+    {
+        const double th = fma(P.joint[j].qmult, q[j], P.joint[j].th0);
+        sn[j] = 0.0;
+        cs[j] = 1.0;
+        if (ALLREV || !P.joint[j].prismatic)
+        {
+            if (fabs(th) <= 1.0e5)
+                fast_sincos(th, sn[j], cs[j]);
+            else
+                sincos(th, &sn[j], &cs[j]);
+        }
+    }
+    Fr cur = load_frame(P.base);
+    double W[NJ][3], PJ[NJ][3];
+    ChainUnroll<NJ, ALLREV, 0>::record(P, cur, q, sn, cs, W, PJ);
+    for (int f = 0; f < P.n_frames; ++f)
+    {
+        const ChainFrameP& fp = P.frame[f];
+        const Fr A = chain_frame_a(fp, cur);
+        if (jac_e)
+        {
+            double ux = 0.0, uy = 0.0, uz = 0.0;
+            if (fp.row_mode == ROWS_DIST)
+            {
+                const Fr Ph = fp.b_const ? fr_mul(load_frame(fp.binv), A) : A;
+                const double nrm = norm3_scaled(Ph.x, Ph.y, Ph.z);
+                ux = Ph.x / nrm; uy = Ph.y / nrm; uz = Ph.z / nrm;
+            }
+            ChainUnroll<NJ, ALLREV, 0>::columns_g(P, f, jac_e, P.j_sr_b, W, PJ, A.x, A.y, A.z, ux, uy, uz);
+        }
+        chain_frame_phi(fp, A, phi_e, P.phi_sk);
+    }
+}
+
+// IKSolver::Solve (ik_solver.cpp:73-240) of one start state per lane, start to finish: prob_->Update(q), the damped
+// pseudo-inverse step, the backtracking line search and the termination tests, iterated in registers / on the lane's own column
+// of the SoA workspace.  Lanes that stop wait for the slowest lane of their warp; nothing waits for the host.
+template <int NJ, bool ALLREV>
+__global__ void __maxnreg__(168) exo_chain_ik_solve_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G,
+                                                           const __grid_constant__ ChainLineSearchParams L, const __grid_constant__ IkParams K,
+                                                           const __grid_constant__ CostParams C, int max_iterations)
+{
+    const int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x;
+    if (e >= P.n_evals) return;
+    const int N = P.n_ctrl;
+    const int64_t E = P.n_evals;
+    const char* xe = reinterpret_cast<const char*>(P.x) + e * P.x_se_b;
+    const char* xt = reinterpret_cast<const char*>(L.q_trial) + e * P.x_se_b;
+    char* phi_e = reinterpret_cast<char*>(P.phi) + e * P.phi_se_b;
+    char* jac_e = reinterpret_cast<char*>(P.jac) + e * P.j_se_b;
+    for (int it = 0; it < max_iterations; ++it)
+    {
+        chain_eval_one<NJ, ALLREV>(P, xe, phi_e, jac_e);  // prob_->Update(q_)
+        if (!ik_step_one(K, C, e)) break;
+        const double err_prev = L.err_prev[e];
+        for (int ai = 0; ai < 10; ++ai)
+        {
+            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+            for (int c = 0; c < N; ++c) L.q_trial[(int64_t)c * E + e] = L.q[(int64_t)c * E + e] - alpha * L.qd[(int64_t)c * E + e];
+            const double error = chain_cost_only<NJ, ALLREV>(P, G, xt, 0);
+            L.cost[e] = error;
+            if (error < err_prev)
+            {
+                for (int c = 0; c < N; ++c)
+                {
+                    L.q[(int64_t)c * E + e] = L.q_trial[(int64_t)c * E + e];
+                    L.qd[(int64_t)c * E + e] *= alpha;
+                }
+                L.ls_done[e] = 1;
+                break;
+            }
+        }
+        if (!ik_finish_one(K, e, it + 1 == max_iterations)) break;
+    }
+}
+
+template <int NJ, bool ALLREV>
+cudaError_t chain_ik_solve_launch_t(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
+                                    const CostParams& C, int max_iterations, cudaStream_t stream)
+{
+    const int64_t blocks = (P.n_evals + CTPB - 1) / CTPB;
+    exo_chain_ik_solve_kernel<NJ, ALLREV><<<(int)(blocks > 0 ? blocks : 1), CTPB, 0, stream>>>(P, G, L, K, C, max_iterations);
+    return cudaGetLastError();
+}
+
+template <bool ALLREV>
+cudaError_t chain_ik_solve_launch_nj(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
+                                     const CostParams& C, int max_iterations, cudaStream_t stream)
+{
+    switch (P.n_joints)
+    {
+        case 1: return chain_ik_solve_launch_t<1, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 2: return chain_ik_solve_launch_t<2, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 3: return chain_ik_solve_launch_t<3, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 4: return chain_ik_solve_launch_t<4, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 5: return chain_ik_solve_launch_t<5, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 6: return chain_ik_solve_launch_t<6, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 7: return chain_ik_solve_launch_t<7, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        case 8: return chain_ik_solve_launch_t<8, ALLREV>(P, G, L, K, C, max_iterations, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+template <int NJ, bool ALLREV>
+cudaError_t chain_ik_linesearch_launch_t(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)
+{
+    const int64_t blocks = (P.n_evals + CTPB - 1) / CTPB;
+    exo_chain_ik_linesearch_kernel<NJ, ALLREV><<<(int)(blocks > 0 ? blocks : 1), CTPB, 0, stream>>>(P, G, L);
+    return cudaGetLastError();
+}
+
+template <bool ALLREV>
+cudaError_t chain_ik_linesearch_launch_nj(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)
+{
+    switch (P.n_joints)
+    {
+        case 1: return chain_ik_linesearch_launch_t<1, ALLREV>(P, G, L, stream);
+        case 2: return chain_ik_linesearch_launch_t<2, ALLREV>(P, G, L, stream);
+        case 3: return chain_ik_linesearch_launch_t<3, ALLREV>(P, G, L, stream);
+        case 4: return chain_ik_linesearch_launch_t<4, ALLREV>(P, G, L, stream);
+        case 5: return chain_ik_linesearch_launch_t<5, ALLREV>(P, G, L, stream);
+        case 6: return chain_ik_linesearch_launch_t<6, ALLREV>(P, G, L, stream);
+        case 7: return chain_ik_linesearch_launch_t<7, ALLREV>(P, G, L, stream);
+        case 8: return chain_ik_linesearch_launch_t<8, ALLREV>(P, G, L, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
 template <int NJ, bool ALLREV>
 cudaError_t chain_costgrad_launch_t(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
@@ -856,6 +1100,18 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
 cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
     return P.all_revolute ? chain_costgrad_launch_nj<true>(P, G, stream) : chain_costgrad_launch_nj<false>(P, G, stream);
+}
+
+cudaError_t chain_ik_linesearch_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)
+{
+    return P.all_revolute ? chain_ik_linesearch_launch_nj<true>(P, G, L, stream) : chain_ik_linesearch_launch_nj<false>(P, G, L, stream);
+}
+
+cudaError_t chain_ik_solve_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
+                                  const CostParams& C, int max_iterations, cudaStream_t stream)
+{
+    return P.all_revolute ? chain_ik_solve_launch_nj<true>(P, G, L, K, C, max_iterations, stream)
+                          : chain_ik_solve_launch_nj<false>(P, G, L, K, C, max_iterations, stream);
 }
 
 cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream)

@@ -1,0 +1,145 @@
+// ik_device.cuh -- per-configuration pieces of IKSolver::Solve's inner loop (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:
+// 92-197), shared by the one-launch-per-stage kernels (ik_kernel.cu) and the single-launch solve of chain programs
+// (exo_chain_ik_solve_kernel, chain_kernel.cu).  One lane = one configuration, everything SoA ([k][E]).
+#pragma once
+#include "cost_device.cuh"
+
+namespace exo
+{
+namespace dev
+{
+// error, damped weighted pseudo-inverse step qd (Cholesky; lambda x10 on failure), |cJ|_F -- from the Phi / J of the current state.
+// Returns false when the configuration stops here (FunctionTolerance or Divergence).
+static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const CostParams& C, int64_t e)
+{
+    const int LJ = K.length_jac, N = K.n_ctrl;
+    double yd[IK_MAXLJ], A[IK_MAXLJ * IK_MAXLJ], Ainv[IK_MAXLJ * IK_MAXLJ], cj[IK_MAXLJ], z[IK_MAXLJ];
+    eval_ydiff(C, e, 0, yd, 1);
+    // S = diag(rho of the row's map); error = ydiff^T S ydiff
+    double error = 0.0;
+    for (int r = 0; r < LJ; ++r)
+    {
+        const double s = K.row_rho[r];
+        error += yd[r] * s * yd[r];
+        yd[r] *= s;
+    }
+    K.cost[e] = error;
+    K.err_prev[e] = error;
+    K.ls_done[e] = 0;
+    if (error < K.tolerance)
+    {
+        K.termination[e] = IK_TERM_FUNCTION_TOLERANCE;
+        K.active[e] = 0;
+        return false;
+    }
+    // cJ = S J (row r, column c at jac[(r * N + c) * E + e]);  A = cJ W^-1 cJ^T + lambda I;  stop = |cJ|_F
+    const double* J = K.jac + e;
+    const int64_t E = K.n_evals;
+    double stop2 = 0.0;
+    for (int r = 0; r < LJ; ++r)
+        for (int s2 = 0; s2 <= r; ++s2)
+        {
+            double acc = 0.0;
+            for (int c = 0; c < N; ++c)
+            {
+                const double a = K.row_rho[r] * J[(int64_t)(r * N + c) * E], b = K.row_rho[s2] * J[(int64_t)(s2 * N + c) * E];
+                acc += a * K.w_inv[c] * b;
+                if (s2 == r) stop2 += a * a;
+            }
+            A[r * LJ + s2] = acc;
+            A[s2 * LJ + r] = acc;
+        }
+    double lambda = K.lambda[e];
+    bool ok = false;
+    while (!ok)
+    {
+        // Eigen::LLT (lower Cholesky of A + lambda I); fails on a non-positive pivot
+        ok = true;
+        for (int j = 0; j < LJ && ok; ++j)
+        {
+            double d = A[j * LJ + j] + lambda;
+            for (int k = 0; k < j; ++k) d -= Ainv[j * LJ + k] * Ainv[j * LJ + k];
+            if (!(d > 0.0))
+            {
+                ok = false;
+                break;
+            }
+            const double ljj = sqrt(d);
+            Ainv[j * LJ + j] = ljj;  // Ainv holds L for now
+            for (int i = j + 1; i < LJ; ++i)
+            {
+                double v = A[i * LJ + j];
+                for (int k = 0; k < j; ++k) v -= Ainv[i * LJ + k] * Ainv[j * LJ + k];
+                Ainv[i * LJ + j] = v / ljj;
+            }
+        }
+        if (!ok)
+        {
+            lambda *= 10.0;  // IncreaseRegularization (ik_solver.h: regfactor_ = 10)
+            if (lambda > K.regmax)
+            {
+                K.lambda[e] = K.regmax;
+                K.termination[e] = IK_TERM_DIVERGENCE;
+                K.active[e] = 0;
+                return false;
+            }
+        }
+    }
+    K.lambda[e] = lambda;
+    // z = (A + lambda I)^-1 yd by forward / backward substitution with L (the reference forms the explicit inverse and
+    // multiplies; same result up to rounding)
+    for (int i = 0; i < LJ; ++i)
+    {
+        double v = yd[i];
+        for (int k = 0; k < i; ++k) v -= Ainv[i * LJ + k] * z[k];
+        z[i] = v / Ainv[i * LJ + i];
+    }
+    for (int i = LJ - 1; i >= 0; --i)
+    {
+        double v = z[i];
+        for (int k = i + 1; k < LJ; ++k) v -= Ainv[k * LJ + i] * z[k];
+        z[i] = v / Ainv[i * LJ + i];
+    }
+    // qd = W^-1 cJ^T z
+    for (int c = 0; c < N; ++c)
+    {
+        double acc = 0.0;
+        for (int r = 0; r < LJ; ++r) acc += K.row_rho[r] * J[(int64_t)(r * N + c) * E] * z[r];
+        K.qd[(int64_t)c * E + e] = K.w_inv[c] * acc;
+    }
+    (void)cj;
+    K.stop[e] = sqrt(stop2);
+    return true;
+}
+
+// step / gradient tolerance checks and the iteration counter (ik_solver.cpp:164-186); false when the configuration stops
+static __device__ __forceinline__ bool ik_finish_one(const IkParams& K, int64_t e, bool last_iteration)
+{
+    K.iterations[e] += 1;
+    double step = 0.0;
+    for (int c = 0; c < K.n_ctrl; ++c)
+    {
+        const double v = K.qd[(int64_t)c * K.n_evals + e];
+        step += v * v;
+    }
+    if (step < K.step_tolerance)
+    {
+        K.termination[e] = IK_TERM_STEP_TOLERANCE;
+        K.active[e] = 0;
+        return false;
+    }
+    if (K.stop[e] < K.gradient_tolerance)
+    {
+        K.termination[e] = IK_TERM_GRADIENT_TOLERANCE;
+        K.active[e] = 0;
+        return false;
+    }
+    if (last_iteration)
+    {
+        K.termination[e] = IK_TERM_ITERATION_LIMIT;
+        return false;
+    }
+    return true;
+}
+}  // namespace dev
+}  // namespace exo

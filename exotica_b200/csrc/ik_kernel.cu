@@ -9,7 +9,7 @@
 // The forward kinematics / Jacobian evaluations are the batched kernels of this library (one launch per iteration for (Phi, J),
 // one FK-only launch per line-search step); the kernels here are the per-configuration linear algebra and bookkeeping between
 // them.  One lane = one configuration, everything SoA ([k][E]); converged configurations keep their state and idle.
-#include "cost_device.cuh"
+#include "ik_device.cuh"
 
 namespace exo
 {
@@ -27,103 +27,7 @@ __global__ void __launch_bounds__(128) exo_ik_step_kernel(const __grid_constant_
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= K.n_evals || !K.active[e]) return;
-    const int LJ = K.length_jac, N = K.n_ctrl;
-    double yd[IK_MAXLJ], A[IK_MAXLJ * IK_MAXLJ], Ainv[IK_MAXLJ * IK_MAXLJ], cj[IK_MAXLJ], z[IK_MAXLJ];
-    eval_ydiff(C, e, 0, yd, 1);
-    // S = diag(rho of the row's map); error = ydiff^T S ydiff
-    double error = 0.0;
-    for (int r = 0; r < LJ; ++r)
-    {
-        const double s = K.row_rho[r];
-        error += yd[r] * s * yd[r];
-        yd[r] *= s;
-    }
-    K.cost[e] = error;
-    K.err_prev[e] = error;
-    K.ls_done[e] = 0;
-    if (error < K.tolerance)
-    {
-        K.termination[e] = IK_TERM_FUNCTION_TOLERANCE;
-        K.active[e] = 0;
-        return;
-    }
-    // cJ = S J (row r, column c at jac[(r * N + c) * E + e]);  A = cJ W^-1 cJ^T + lambda I;  stop = |cJ|_F
-    const double* J = K.jac + e;
-    const int64_t E = K.n_evals;
-    double stop2 = 0.0;
-    for (int r = 0; r < LJ; ++r)
-        for (int s2 = 0; s2 <= r; ++s2)
-        {
-            double acc = 0.0;
-            for (int c = 0; c < N; ++c)
-            {
-                const double a = K.row_rho[r] * J[(int64_t)(r * N + c) * E], b = K.row_rho[s2] * J[(int64_t)(s2 * N + c) * E];
-                acc += a * K.w_inv[c] * b;
-                if (s2 == r) stop2 += a * a;
-            }
-            A[r * LJ + s2] = acc;
-            A[s2 * LJ + r] = acc;
-        }
-    double lambda = K.lambda[e];
-    bool ok = false;
-    while (!ok)
-    {
-        // Eigen::LLT (lower Cholesky of A + lambda I); fails on a non-positive pivot
-        ok = true;
-        for (int j = 0; j < LJ && ok; ++j)
-        {
-            double d = A[j * LJ + j] + lambda;
-            for (int k = 0; k < j; ++k) d -= Ainv[j * LJ + k] * Ainv[j * LJ + k];
-            if (!(d > 0.0))
-            {
-                ok = false;
-                break;
-            }
-            const double ljj = sqrt(d);
-            Ainv[j * LJ + j] = ljj;  // Ainv holds L for now
-            for (int i = j + 1; i < LJ; ++i)
-            {
-                double v = A[i * LJ + j];
-                for (int k = 0; k < j; ++k) v -= Ainv[i * LJ + k] * Ainv[j * LJ + k];
-                Ainv[i * LJ + j] = v / ljj;
-            }
-        }
-        if (!ok)
-        {
-            lambda *= 10.0;  // IncreaseRegularization (ik_solver.h: regfactor_ = 10)
-            if (lambda > K.regmax)
-            {
-                K.lambda[e] = K.regmax;
-                K.termination[e] = IK_TERM_DIVERGENCE;
-                K.active[e] = 0;
-                return;
-            }
-        }
-    }
-    K.lambda[e] = lambda;
-    // z = (A + lambda I)^-1 yd by forward / backward substitution with L (the reference forms the explicit inverse and
-    // multiplies; same result up to rounding)
-    for (int i = 0; i < LJ; ++i)
-    {
-        double v = yd[i];
-        for (int k = 0; k < i; ++k) v -= Ainv[i * LJ + k] * z[k];
-        z[i] = v / Ainv[i * LJ + i];
-    }
-    for (int i = LJ - 1; i >= 0; --i)
-    {
-        double v = z[i];
-        for (int k = i + 1; k < LJ; ++k) v -= Ainv[k * LJ + i] * z[k];
-        z[i] = v / Ainv[i * LJ + i];
-    }
-    // qd = W^-1 cJ^T z
-    for (int c = 0; c < N; ++c)
-    {
-        double acc = 0.0;
-        for (int r = 0; r < LJ; ++r) acc += K.row_rho[r] * J[(int64_t)(r * N + c) * E] * z[r];
-        K.qd[(int64_t)c * E + e] = K.w_inv[c] * acc;
-    }
-    (void)cj;
-    K.stop[e] = sqrt(stop2);
+    ik_step_one(K, C, e);
 }
 
 // q_trial = q - alpha qd for the configurations still searching; the others keep q (their evaluation is ignored)
@@ -163,27 +67,7 @@ __global__ void __launch_bounds__(128) exo_ik_finish_kernel(const __grid_constan
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= K.n_evals || !K.active[e]) return;
-    K.iterations[e] += 1;
-    double step = 0.0;
-    for (int c = 0; c < K.n_ctrl; ++c)
-    {
-        const double v = K.qd[(int64_t)c * K.n_evals + e];
-        step += v * v;
-    }
-    if (step < K.step_tolerance)
-    {
-        K.termination[e] = IK_TERM_STEP_TOLERANCE;
-        K.active[e] = 0;
-    }
-    else if (K.stop[e] < K.gradient_tolerance)
-    {
-        K.termination[e] = IK_TERM_GRADIENT_TOLERANCE;
-        K.active[e] = 0;
-    }
-    else if (last_iteration)
-        K.termination[e] = IK_TERM_ITERATION_LIMIT;
-    else
-        atomicAdd(K.n_active, 1);  // read by the host every few iterations to stop early
+    if (ik_finish_one(K, e, last_iteration != 0)) atomicAdd(K.n_active, 1);  // read by the host every few iterations to stop early
 }
 
 __global__ void __launch_bounds__(128) exo_ik_init_kernel(const __grid_constant__ IkParams K, double lambda0)

@@ -143,6 +143,28 @@ struct ChainGradParams
 };
 cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream);
 
+// Fused line search of the batched IK step for chain programs (exo_chain_ik_linesearch_kernel): the ten trial states
+// q - alpha qd, alpha = 1 ... 0.1 (ik_solver.cpp:146-161), are evaluated in registers (forward kinematics + cost) until the cost
+// drops; replaces ten trial / update / accept launch triples.  All arrays are [.][E] (SoA); P.x must be bound to q_trial.
+struct ChainLineSearchParams
+{
+    double* q;               // [N][E] in / out
+    double* q_trial;         // [N][E] scratch (= P.x)
+    double* qd;              // [N][E] in / out
+    const double* err_prev;  // [E]
+    double* cost;            // [E] error at the last state evaluated
+    const int32_t* active;   // [E]
+    int32_t* ls_done;        // [E]
+};
+cudaError_t chain_ik_linesearch_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream);
+struct IkParams;
+struct CostParams;
+// The whole IKSolver::Solve loop of every start state in ONE launch (exo_chain_ik_solve_kernel): each lane iterates update ->
+// step -> line search -> termination tests on its own column of the SoA workspace until it stops; no host round trips.
+// P must be bound to (q, workspace Phi, workspace J); K / C as for the staged kernels.
+cudaError_t chain_ik_solve_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
+                                  const CostParams& C, int max_iterations, cudaStream_t stream);
+
 // ---- batched task cost and per-trajectory reductions (cost_kernel.cu) -------------------------------------------------
 constexpr int COST_MAXMAPS = 16;
 struct CostMapP

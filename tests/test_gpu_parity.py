@@ -844,7 +844,7 @@ def test_hessian_matches_finite_differences_of_the_jacobian(oracle_lib):
 
 
 # ---- batched IK -------------------------------------------------------------------------------------
-def test_batched_ik_matches_the_reference_solver(oracle_lib):
+def test_batched_ik_matches_the_reference_solver(oracle_lib, monkeypatch):
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
     maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
     orc.set_problem(maps)
@@ -858,7 +858,22 @@ def test_batched_ik_matches_the_reference_solver(oracle_lib):
     prob.set_cost(rho, T=1, goal=goal, W=W)
     E = 96
     Q0 = np.clip(q_goal + rng.normal(0, 0.5, size=(E, 7)), orc.lower, orc.upper)
+    # three ways through the same algorithm: (1) one launch per stage with trial / update / accept launches for the line search,
+    # (default) the same with the ten trials fused in registers (exo_chain_ik_linesearch_kernel), and (EXO_IK_ONE_LAUNCH=1) the
+    # whole solve of every start state in ONE launch (exo_chain_ik_solve_kernel).  All must walk the reference's path.
+    prob.set_kernel(1)
+    Q1, cost1, iters1, term1 = prob.ik_solve_batch(Q0, max_iterations=60)
+    prob.set_kernel(0)
+    monkeypatch.setenv("EXO_IK_ONE_LAUNCH", "1")
+    n0 = prob.launch_count()
+    Q2, cost2, iters2, term2 = prob.ik_solve_batch(Q0, max_iterations=60)
+    assert prob.launch_count() - n0 <= 4  # the solve kernel + the final FK and cost launches
+    monkeypatch.delenv("EXO_IK_ONE_LAUNCH")
     Q, cost, iters, term = prob.ik_solve_batch(Q0, max_iterations=60)
+    for Qx, itx, tx in ((Q1, iters1, term1), (Q2, iters2, term2)):
+        same = (iters == itx) & (term == tx)
+        conv = same & (term == 3)  # non-converged solves amplify rounding differences over their 60 iterations
+        assert same.mean() >= 0.95 and conv.sum() >= E // 2 and np.max(np.abs(Q[conv] - Qx[conv])) <= 1e-6
     n_same = 0
     for e in range(E):
         q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], rho, goal=goal, W=W, max_iterations=60)
