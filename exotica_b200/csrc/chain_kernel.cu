@@ -903,7 +903,7 @@ __global__ void __maxnreg__(168) exo_chain_ik_solve_kernel(const __grid_constant
     for (int it = 0; it < max_iterations; ++it)
     {
         chain_eval_one<NJ, ALLREV>(P, xe, phi_e, jac_e);  // prob_->Update(q_)
-        if (!ik_step_one(K, C, e)) break;
+        if (!ik_step_one<0>(K, C, e)) break;
         const double err_prev = L.err_prev[e];
         for (int ai = 0; ai < 10; ++ai)
         {

@@ -40,6 +40,18 @@ __global__ void __launch_bounds__(128) exo_cost_kernel(const __grid_constant__ C
     }
 }
 
+// End-pose problems (T = 1): one lane per configuration instead of one warp per single-timestep "trajectory"
+__global__ void __launch_bounds__(128) exo_cost_endpose_kernel(const __grid_constant__ CostParams P)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P.n_traj; e += stride)
+    {
+        const double c = P.t_first <= 0 ? eval_cost(P, e, 0) : 0.0;
+        if (P.cost_eval) P.cost_eval[e] = c;
+        if (P.cost_traj) P.cost_traj[e] = c;
+    }
+}
+
 // AbstractTimeIndexedProblem::GetCostJacobian (abstract_time_indexed_problem.cpp:309-318) for every (trajectory, timestep):
 //   grad[t] = 2 ct J[t]^T S[t] ydiff[t] + 2 ct W xdiff[t] - 2 ct W xdiff[t + 1]      (t >= t_first; zero before)
 // and UnconstrainedEndPoseProblem::GetScalarJacobian (unconstrained_end_pose_problem.cpp:84-87) when T = 1.  One lane per
@@ -163,6 +175,12 @@ __global__ void __launch_bounds__(128) exo_reduce_kernel(const double* __restric
 cudaError_t launch_cost(const CostParams& P, cudaStream_t stream)
 {
     if (P.n_traj <= 0) return cudaSuccess;
+    if (P.T == 1)
+    {
+        const int64_t b1 = (P.n_traj + 127) / 128;
+        exo_cost_endpose_kernel<<<(int)(b1 < 148 * 16 ? b1 : 148 * 16), 128, 0, stream>>>(P);
+        return cudaGetLastError();
+    }
     const int64_t blocks = (P.n_traj + 3) / 4;  // 4 warps (trajectories) per CTA
     exo_cost_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, 0, stream>>>(P);
     return cudaGetLastError();

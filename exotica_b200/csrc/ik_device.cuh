@@ -10,13 +10,23 @@ namespace dev
 {
 // error, damped weighted pseudo-inverse step qd (Cholesky; lambda x10 on failure), |cJ|_F -- from the Phi / J of the current state.
 // Returns false when the configuration stops here (FunctionTolerance or Divergence).
+// LJT > 0: the task space has exactly LJT rows (6: one EffFrame, the usual IK problem) -- every loop unrolls and the LJT x LJT
+// system lives in registers; LJT = 0: any size up to IK_MAXLJ, arrays in local memory.
+template <int LJT>
 static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const CostParams& C, int64_t e)
 {
-    const int LJ = K.length_jac, N = K.n_ctrl;
-    double yd[IK_MAXLJ], A[IK_MAXLJ * IK_MAXLJ], Ainv[IK_MAXLJ * IK_MAXLJ], cj[IK_MAXLJ], z[IK_MAXLJ];
-    eval_ydiff(C, e, 0, yd, 1);
+    constexpr int CAP = LJT > 0 ? LJT : IK_MAXLJ;
+    const int LJ = LJT > 0 ? LJT : K.length_jac, N = K.n_ctrl;
+    double yd[CAP], A[CAP * CAP], Ainv[CAP * CAP], z[CAP];
+    {
+        double yd_any[IK_MAXLJ];  // eval_ydiff indexes by map: runtime subscripts
+        eval_ydiff(C, e, 0, yd_any, 1);
+#pragma unroll
+        for (int r = 0; r < CAP; ++r) yd[r] = r < LJ ? yd_any[r] : 0.0;
+    }
     // S = diag(rho of the row's map); error = ydiff^T S ydiff
     double error = 0.0;
+#pragma unroll
     for (int r = 0; r < LJ; ++r)
     {
         const double s = K.row_rho[r];
@@ -36,7 +46,9 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
     const double* J = K.jac + e;
     const int64_t E = K.n_evals;
     double stop2 = 0.0;
+#pragma unroll
     for (int r = 0; r < LJ; ++r)
+#pragma unroll
         for (int s2 = 0; s2 <= r; ++s2)
         {
             double acc = 0.0;
@@ -55,20 +67,25 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
     {
         // Eigen::LLT (lower Cholesky of A + lambda I); fails on a non-positive pivot
         ok = true;
-        for (int j = 0; j < LJ && ok; ++j)
+#pragma unroll
+        for (int j = 0; j < LJ; ++j)
         {
+            if (!ok) continue;  // (a break would keep the loop from unrolling)
             double d = A[j * LJ + j] + lambda;
+#pragma unroll
             for (int k = 0; k < j; ++k) d -= Ainv[j * LJ + k] * Ainv[j * LJ + k];
             if (!(d > 0.0))
             {
                 ok = false;
-                break;
+                continue;
             }
             const double ljj = sqrt(d);
             Ainv[j * LJ + j] = ljj;  // Ainv holds L for now
+#pragma unroll
             for (int i = j + 1; i < LJ; ++i)
             {
                 double v = A[i * LJ + j];
+#pragma unroll
                 for (int k = 0; k < j; ++k) v -= Ainv[i * LJ + k] * Ainv[j * LJ + k];
                 Ainv[i * LJ + j] = v / ljj;
             }
@@ -88,15 +105,19 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
     K.lambda[e] = lambda;
     // z = (A + lambda I)^-1 yd by forward / backward substitution with L (the reference forms the explicit inverse and
     // multiplies; same result up to rounding)
+#pragma unroll
     for (int i = 0; i < LJ; ++i)
     {
         double v = yd[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) v -= Ainv[i * LJ + k] * z[k];
         z[i] = v / Ainv[i * LJ + i];
     }
+#pragma unroll
     for (int i = LJ - 1; i >= 0; --i)
     {
         double v = z[i];
+#pragma unroll
         for (int k = i + 1; k < LJ; ++k) v -= Ainv[k * LJ + i] * z[k];
         z[i] = v / Ainv[i * LJ + i];
     }
@@ -104,10 +125,10 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
     for (int c = 0; c < N; ++c)
     {
         double acc = 0.0;
+#pragma unroll
         for (int r = 0; r < LJ; ++r) acc += K.row_rho[r] * J[(int64_t)(r * N + c) * E] * z[r];
         K.qd[(int64_t)c * E + e] = K.w_inv[c] * acc;
     }
-    (void)cj;
     K.stop[e] = sqrt(stop2);
     return true;
 }

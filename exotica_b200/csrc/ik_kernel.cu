@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(128) exo_ik_step_kernel(const __grid_constant_
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= K.n_evals || !K.active[e]) return;
-    ik_step_one(K, C, e);
+    if (K.length_jac == 6)
+        ik_step_one<6>(K, C, e);
+    else
+        ik_step_one<0>(K, C, e);
 }
 
 // q_trial = q - alpha qd for the configurations still searching; the others keep q (their evaluation is ignored)
