@@ -30,6 +30,9 @@ HOST_SYMBOLS = [
     ("exo_host_scene_num_model_joints", ctypes.c_int, [_vp]),
     ("exo_host_scene_add_object", ctypes.c_int, [_vp, _cp, _dp, _cp]),
     ("exo_host_scene_add_trajectory", ctypes.c_int, [_vp, _cp, ctypes.c_int, _dp]),
+    ("exo_host_scene_add_trajectory_string", ctypes.c_int, [_vp, _cp, _cp]),
+    ("exo_host_scene_get_trajectory", ctypes.c_int, [_vp, _cp, ctypes.c_char_p, ctypes.c_int]),
+    ("exo_host_trajectory_sample", ctypes.c_int, [_cp, ctypes.c_int, _dp, _dp, _dp]),
     ("exo_host_scene_request_frames", ctypes.c_int, [_vp, ctypes.c_int, _cp, _dp, _cp, _dp, ctypes.c_int]),
     ("exo_host_scene_update", ctypes.c_int, [_vp, _dp, ctypes.c_int, _dp, _dp]),
     ("exo_host_scene_update_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),

@@ -265,6 +265,7 @@ public:
     // Scene objects (KinematicTree::AddEnvironmentElement / AddElement, kinematic_tree.cpp:434-578, reduced to frames)
     int AddEnvironmentElement(const std::string& name, const Frame& transform, const std::string& parent = "", bool trajectory_generated = false);
     int AddElement(const std::string& name, const Frame& transform, const std::string& parent = "");
+    int MakeTrajectoryGenerated(int element_index);  // returns the element's slot in the per-timestep frame table
     int GetNumGenerated() const { return num_generated_; }
 
     const std::vector<KinematicElement>& GetTree() const { return tree_; }
@@ -320,6 +321,36 @@ struct Initializer
 // with element children become lists of initializers.
 Initializer InitializerFromXml(const xml::Element& e, const std::string& prefix = "exotica/");
 
+// exotica::Trajectory (exotica_core/include/exotica_core/trajectory.h, src/trajectory.cpp): piecewise Cartesian trajectory with
+// KDL's line path / single-axis rotation / cubic velocity profile semantics (restated in host/trajectory.cpp)
+class Trajectory
+{
+public:
+    Trajectory() {}
+    explicit Trajectory(const std::string& data);  // "radius\n rows cols\n time x y z [rotation]..."
+    Trajectory(const std::vector<std::vector<double>>& data, double radius = 1.0);
+    Frame GetPosition(double t) const;
+    double GetDuration() const;
+    const std::vector<std::vector<double>>& GetData() const { return data_; }
+    double GetRadius() const { return radius_; }
+    std::string ToString() const;
+
+private:
+    struct Segment
+    {
+        Frame start, end;
+        double duration = 0.0;
+        bool stationary = true;
+        double dir[3] = {0, 0, 0}, axis[3] = {0, 0, 1};
+        double path_length = 0.0, scale_rot = 1.0, scale_lin = 1.0;
+    };
+    void ConstructFromData(const std::vector<std::vector<double>>& data, double radius);
+    Frame SegmentPos(const Segment& s, double time) const;
+    std::vector<Segment> segments_;
+    std::vector<std::vector<double>> data_;
+    double radius_ = 1.0;
+};
+
 // ---- Scene -------------------------------------------------------------------------------------------------------
 class Scene
 {
@@ -348,6 +379,12 @@ public:
     void AddObject(const std::string& name, const Frame& transform = IdentityFrame(), const std::string& parent = "");
     // Scene::AddTrajectory (scene.cpp:917-935) replaced by an explicit per-timestep frame table [T][12]
     void AddTrajectoryFrames(const std::string& link, const std::vector<Frame>& frames_per_timestep);
+    // Scene::AddTrajectory(link, traj) (scene.cpp:922-935): the link follows the trajectory; time-indexed problems sample it at
+    // t * tau for every timestep (AbstractTimeIndexedProblem::Update -> Scene::Update(x, t * tau), scene.cpp:337-348)
+    void AddTrajectory(const std::string& link, const std::string& traj);
+    void AddTrajectory(const std::string& link, std::shared_ptr<Trajectory> traj);
+    std::shared_ptr<Trajectory> GetTrajectory(const std::string& link) const;
+    void SampleTrajectories(int T, double tau);
     // generated frames [T][n_generated][12] (empty if no link is trajectory driven)
     const std::vector<double>& GetGeneratedTable(int& T, int& n_generated) const;
 
@@ -356,6 +393,7 @@ private:
     KinematicTree kinematica_;
     int num_positions_ = 0;
     std::map<int, std::vector<Frame>> trajectories_;  // generated slot -> frames per timestep
+    std::map<std::string, std::pair<int, std::shared_ptr<Trajectory>>> trajectory_generators_;  // link -> (slot, trajectory)
     mutable std::vector<double> generated_table_;
 };
 typedef std::shared_ptr<Scene> ScenePtr;

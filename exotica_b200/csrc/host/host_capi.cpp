@@ -281,6 +281,33 @@ int exo_host_scene_add_trajectory(exo_host_scene* s, const char* link, int T, co
     })
 }
 
+int exo_host_scene_add_trajectory_string(exo_host_scene* s, const char* link, const char* trajectory)
+{
+    HOST_TRY(s->scene->AddTrajectory(link, std::string(trajectory ? trajectory : "")))
+}
+
+int exo_host_scene_get_trajectory(exo_host_scene* s, const char* link, char* out, int capacity)
+{
+    HOST_TRY({
+        const std::string text = s->scene->GetTrajectory(link)->ToString();
+        if ((int)text.size() + 1 > capacity) ThrowPretty("trajectory text does not fit the buffer");
+        memcpy(out, text.c_str(), text.size() + 1);
+    })
+}
+
+int exo_host_trajectory_sample(const char* trajectory, int n, const double* times, double* frames, double* duration)
+{
+    HOST_TRY({
+        exotica::Trajectory traj(std::string(trajectory ? trajectory : ""));
+        for (int i = 0; i < n; ++i)
+        {
+            const Frame f = traj.GetPosition(times[i]);
+            memcpy(frames + 12 * i, f.data(), 12 * sizeof(double));
+        }
+        if (duration) *duration = traj.GetDuration();
+    })
+}
+
 int exo_host_scene_request_frames(exo_host_scene* s, int n_frames, const char* links_a, const double* off_a, const char* links_b, const double* off_b, int with_jacobian)
 {
     HOST_TRY({

@@ -467,6 +467,21 @@ int KinematicTree::AddEnvironmentElement(const std::string& name, const Frame& t
     return (int)tree_.size() - 1;
 }
 
+int KinematicTree::MakeTrajectoryGenerated(int index)
+{
+    // Scene::AddTrajectory (scene.cpp:927-935): is_trajectory_generated = true; UpdateTree then takes generated_offset for the
+    // element's pose (kinematic_tree.cpp:711-714)
+    if (index < 0 || index >= (int)tree_.size()) ThrowPretty("No such element");
+    KinematicElement& e = tree_[index];
+    if (!e.is_trajectory_generated)
+    {
+        e.is_trajectory_generated = true;
+        e.generated_slot = num_generated_++;
+        InvalidateBackend();
+    }
+    return e.generated_slot;
+}
+
 int KinematicTree::AddElement(const std::string& name, const Frame& transform, const std::string& parent)
 {
     return AddEnvironmentElement(name, transform, parent, false);

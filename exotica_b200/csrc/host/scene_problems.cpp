@@ -83,6 +83,19 @@ void Scene::Instantiate(const Initializer& init)
     // scene.cpp:292-303
     if (init.Has("JointPositionLimitsLower")) kinematica_.SetJointLimitsLower(ParseVector(init.Get("JointPositionLimitsLower", "")));
     if (init.Has("JointPositionLimitsUpper")) kinematica_.SetJointLimitsUpper(ParseVector(init.Get("JointPositionLimitsUpper", "")));
+    // custom links (scene.cpp:114-170; init/link.in: Name, Transform, Parent -- shapes belong to the collision scene, out of scope)
+    for (const Initializer& link : init.List("Links"))
+    {
+        Frame tf = IdentityFrame();
+        if (link.Has("Transform")) tf = GetFrame(ParseVector(link.Get("Transform", "")));
+        AddObject(link.Require("Name"), tf, link.Get("Parent", ""));
+    }
+    // trajectory generators (scene.cpp:247-259; init/trajectory.in: Link, File | Trajectory)
+    for (const Initializer& tr : init.List("Trajectories"))
+    {
+        const std::string file = tr.Get("File", "");
+        AddTrajectory(tr.Require("Link"), file.empty() ? tr.Get("Trajectory", "") : Setup::LoadFile(Setup::ParsePath(file)));
+    }
 }
 
 void Scene::Update(const std::vector<double>& x, double t)
@@ -101,9 +114,38 @@ void Scene::AddTrajectoryFrames(const std::string& link, const std::vector<Frame
     if (frames_per_timestep.empty()) ThrowPretty("Trajectory for '" + link + "' is empty");
     int idx = kinematica_.GetElementIndex(link);
     if (idx < 0) idx = kinematica_.AddEnvironmentElement(link, IdentityFrame(), "", true);
-    const KinematicElement& e = kinematica_.GetTree()[idx];
-    if (!e.is_trajectory_generated) ThrowPretty("Link '" + link + "' exists and is not trajectory driven; add it with AddTrajectoryFrames only");
-    trajectories_[e.generated_slot] = frames_per_timestep;
+    trajectories_[kinematica_.MakeTrajectoryGenerated(idx)] = frames_per_timestep;
+}
+
+void Scene::AddTrajectory(const std::string& link, const std::string& traj)
+{
+    AddTrajectory(link, std::shared_ptr<Trajectory>(new Trajectory(traj)));
+}
+
+void Scene::AddTrajectory(const std::string& link, std::shared_ptr<Trajectory> traj)
+{
+    if (!traj || traj->GetDuration() == 0.0) ThrowPretty("The trajectory is empty!");
+    const int idx = kinematica_.GetElementIndex(link);
+    if (idx < 0) ThrowPretty("Can't find link '" + link + "'!");
+    trajectory_generators_[link] = std::make_pair(kinematica_.MakeTrajectoryGenerated(idx), traj);
+}
+
+std::shared_ptr<Trajectory> Scene::GetTrajectory(const std::string& link) const
+{
+    const auto it = trajectory_generators_.find(link);
+    if (it == trajectory_generators_.end()) ThrowPretty("No trajectory generator defined for link '" + link + "'!");
+    return it->second.second;
+}
+
+void Scene::SampleTrajectories(int T, double tau)
+{
+    // Scene::UpdateTrajectoryGenerators(t * tau) for every timestep at once
+    for (const auto& kv : trajectory_generators_)
+    {
+        std::vector<Frame> frames(T);
+        for (int t = 0; t < T; ++t) frames[t] = kv.second.second->GetPosition((double)t * tau);
+        trajectories_[kv.second.first] = frames;
+    }
 }
 
 const std::vector<double>& Scene::GetGeneratedTable(int& T, int& n_generated) const
@@ -908,6 +950,7 @@ void TimeIndexedProblem::Instantiate(const Initializer& init)
 void TimeIndexedProblem::PushGenerated()
 {
     int T = 0, n_gen = 0;
+    scene_->SampleTrajectories(T_, tau_);
     const std::vector<double>& table = scene_->GetGeneratedTable(T, n_gen);
     if (n_gen == 0) return;
     if (T != T_) ThrowPretty("Trajectory tables have " + std::to_string(T) + " timesteps, the problem has T=" + std::to_string(T_));

@@ -2,6 +2,7 @@
 // EXOTica XML configs.  The reference uses tinyxml2 (exotica_core/include/exotica_core/loaders/xml_loader.h)
 // and urdfdom; neither is available here, and this subset is all those formats need.
 #pragma once
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -118,6 +119,24 @@ private:
                     out += rep[e];
                     k += n - 1;
                     hit = true;
+                }
+            }
+            if (!hit && k + 2 < in.size() && in[k + 1] == '#')
+            {
+                // numeric character reference &#NN; / &#xHH; (ASCII range: what attribute values use for tabs and newlines)
+                const size_t semi = in.find(';', k);
+                if (semi != std::string::npos && semi - k <= 8)
+                {
+                    const bool hex = in[k + 2] == 'x' || in[k + 2] == 'X';
+                    const std::string digits = in.substr(k + (hex ? 3 : 2), semi - k - (hex ? 3 : 2));
+                    char* end = nullptr;
+                    const long code = strtol(digits.c_str(), &end, hex ? 16 : 10);
+                    if (end && *end == 0 && !digits.empty() && code > 0 && code < 128)
+                    {
+                        out += (char)code;
+                        k = semi;
+                        hit = true;
+                    }
                 }
             }
             if (!hit) out += '&';

@@ -243,9 +243,19 @@ class Scene(object):
         _check(_host.lib().exo_host_scene_add_object(self._h, _s(name), _d(_offset(transform)), _s(parent)))
 
     def add_trajectory(self, link, frames):
-        """frames: [T][12] frames or [T][3|6|7] vectors (GetFrame forms) for each timestep."""
+        """Scene::AddTrajectory: `frames` is either the reference's trajectory text ("radius\\n rows cols\\n time x y z [rot]...",
+        sampled at t * tau by time-indexed problems) or an explicit table of [T][12] frames / [T][3|6|7] GetFrame vectors."""
+        if isinstance(frames, str):
+            _check(_host.lib().exo_host_scene_add_trajectory_string(self._h, _s(link), _s(frames)))
+            return
         fr = np.array([_offset(f) for f in frames], dtype=np.float64)
         _check(_host.lib().exo_host_scene_add_trajectory(self._h, _s(link), fr.shape[0], _d(fr)))
+
+    def get_trajectory(self, link):
+        """Scene::GetTrajectory: the Trajectory attached to `link` (a copy built from its text form)."""
+        buf = ctypes.create_string_buffer(1 << 20)
+        _check(_host.lib().exo_host_scene_get_trajectory(self._h, _s(link), buf, len(buf)))
+        return Trajectory(buf.value.decode())
 
     def request_frames(self, frames, with_jacobian=True):
         """frames: list of dicts with the Frame initializer fields (Link, LinkOffset, Base, BaseOffset)."""
@@ -451,6 +461,31 @@ class PlanningProblem(object):
         """Name of the CUDA kernel the most recent batched update launched (bench.py's roofline names it)."""
         from . import _capi
         return _capi.lib().exo_problem_last_kernel(_host.lib().exo_host_problem_backend(self._h)).decode()
+
+
+class Trajectory(object):
+    """exotica::Trajectory (exotica_core/src/trajectory.cpp): get_position(t) -> frame[12] (rotation row-major, then position),
+    get_duration().  Built from the reference's text format or from (data[n][4|7|8], radius)."""
+
+    def __init__(self, data, radius=1.0):
+        if not isinstance(data, str):
+            data = np.asarray(data, dtype=np.float64)
+            data = "%r\n%d %d\n%s" % (float(radius), data.shape[0], data.shape[1], "\n".join(" ".join(repr(float(v)) for v in row) for row in data))
+        self.text = data
+        self._duration = None
+
+    def get_position(self, t):
+        times = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        out = np.empty((times.size, 12))
+        dur = ctypes.c_double(0.0)
+        _check(_host.lib().exo_host_trajectory_sample(_s(self.text), int(times.size), _d(times), _d(out), ctypes.byref(dur)))
+        self._duration = dur.value
+        return out if np.ndim(t) else out[0]
+
+    def get_duration(self):
+        if self._duration is None:
+            self.get_position(0.0)
+        return self._duration
 
 
 class IKSolver(object):

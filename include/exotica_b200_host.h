@@ -49,6 +49,14 @@ int exo_host_scene_set_model_state(exo_host_scene* scene, const double* state, i
 int exo_host_scene_num_model_joints(exo_host_scene* scene);
 int exo_host_scene_add_object(exo_host_scene* scene, const char* name, const double frame12[12], const char* parent);
 int exo_host_scene_add_trajectory(exo_host_scene* scene, const char* link, int T, const double* frames /*[T][12]*/);
+/* Scene::AddTrajectory(link, traj) (scene.cpp:922-935) with the reference's trajectory text format
+ * ("radius\n rows cols\n time x y z [rotation]..." -- exotica_core/src/trajectory.cpp:51-68); time-indexed problems sample it
+ * at t * tau for every timestep */
+int exo_host_scene_add_trajectory_string(exo_host_scene* scene, const char* link, const char* trajectory);
+/* Scene::GetTrajectory(link)->ToString() into out[capacity] */
+int exo_host_scene_get_trajectory(exo_host_scene* scene, const char* link, char* out, int capacity);
+/* exotica::Trajectory::GetPosition at n times -> frames[n][12]; duration may be NULL */
+int exo_host_trajectory_sample(const char* trajectory, int n, const double* times, double* frames, double* duration);
 /* KinematicTree::RequestFrames / Update / UpdateBatch: link names '\n'-joined, offsets [F][12] (NULL = identity) */
 int exo_host_scene_request_frames(exo_host_scene* scene, int n_frames, const char* links_a, const double* off_a,
                                   const char* links_b, const double* off_b, int with_jacobian);

@@ -90,3 +90,41 @@ def test_errors_use_the_status_and_message_channel(oracle_lib):
     x = np.zeros(7)
     rc = _capi.lib().exo_problem_update_batch(prob.h, x.ctypes.data, -1, 1, 0, x.ctypes.data, None, None)
     assert rc != 0 and b"negative" in _capi.lib().exo_last_error()
+
+
+def test_trajectory_matches_the_independent_restatement():
+    """exotica::Trajectory (host C++, exotica_b200/csrc/host/trajectory.cpp) against oracle/trajectory.py, plus the properties KDL's
+    line path / single-axis rotation / cubic profile guarantee: knots are hit exactly, stationary segments hold, the end frame
+    persists after the duration, the start frame before t = 0, and the rotation stays about one axis."""
+    import exotica_b200 as exo
+    from oracle.trajectory import Trajectory as RefTrajectory
+    from oracle.oracle import get_frame
+
+    text = "0.5\n5 7\n" + "\n".join([
+        "0.0  0.5 0.1 0.6   0 0 0",
+        "1.0  0.5 0.1 0.6   0 0 0",          # stationary
+        "2.5  0.3 0.4 0.7   0.2 -0.1 0.4",   # translation-limited (radius * angle < distance)
+        "3.0  0.3 0.4 0.7   1.2 0.3 -0.5",   # pure rotation (rotation-limited)
+        "4.0  0.31 0.4 0.7  -1.0 0.8 0.9"])  # rotation-limited with a small translation
+    traj = exo.Trajectory(text)
+    ref = RefTrajectory(text)
+    assert abs(traj.get_duration() - 4.0) < 1e-15 and abs(ref.get_duration() - 4.0) < 1e-15
+    times = np.concatenate([np.linspace(-0.5, 4.5, 201), [0.0, 1.0, 2.5, 3.0, 4.0]])
+    got = traj.get_position(times)
+    want = np.array([ref.get_position(t) for t in times])
+    assert np.max(np.abs(got - want)) <= 1e-12
+    knots = {0.0: [0.5, 0.1, 0.6, 0, 0, 0], 1.0: [0.5, 0.1, 0.6, 0, 0, 0], 2.5: [0.3, 0.4, 0.7, 0.2, -0.1, 0.4], 3.0: [0.3, 0.4, 0.7, 1.2, 0.3, -0.5]}
+    for t, v in knots.items():
+        assert np.max(np.abs(traj.get_position(t) - np.asarray(get_frame(v)))) <= 1e-12
+    assert np.max(np.abs(traj.get_position(9.0) - np.asarray(get_frame([0.31, 0.4, 0.7, -1.0, 0.8, 0.9])))) <= 1e-12
+    assert np.array_equal(traj.get_position(-3.0), traj.get_position(0.0)) and np.array_equal(traj.get_position(0.4), traj.get_position(0.9))
+    R = got[:, :9].reshape(-1, 3, 3)
+    assert np.max(np.abs(np.einsum("eij,ekj->eik", R, R) - np.eye(3))) <= 1e-12
+    # matrix form (data, radius) and the reference's error messages
+    data = np.array([[0, 0, 0, 0], [2, 1, 0, 0]], dtype=np.float64)
+    mid = exo.Trajectory(data, radius=1.0).get_position(1.0)
+    assert np.max(np.abs(mid[9:] - [0.5, 0, 0])) <= 1e-15  # the cubic profile is symmetric
+    with pytest.raises(exo.ExoticaError, match="monotonically increasing"):
+        exo.Trajectory("1\n2 4\n0 0 0 0\n0 1 0 0").get_position(0.0)
+    with pytest.raises(exo.ExoticaError, match="Invalid trajectory data size"):
+        exo.Trajectory("1\n2 5\n0 0 0 0 0\n1 1 0 0 0").get_position(0.0)

@@ -256,6 +256,46 @@ def test_eff_axis_alignment_and_valkyrie_com_through_the_factory(oracle_lib):
 
 
 @pytest.mark.gpu
+def test_scene_trajectory_drives_an_obstacle(oracle_lib):
+    from helpers import max_abs_err
+    from oracle.trajectory import Trajectory as RefTrajectory
+    # example_sphere_collision.xml shape: a scene link follows a Cartesian trajectory (Scene Links + Trajectories initializers,
+    # scene.cpp:114-170,247-259), SphereCollision against it and an EffPosition map on the moving link itself
+    T, tau, B = 30, 0.1, 5
+    text = "0.4\n4 7\n0 0.6 -0.3 0.5 0 0 0\n1 0.6 -0.3 0.5 0 0 0\n2 0.5 0.2 0.7 0.0 0.0 1.2\n3.5 0.4 0.3 0.4 0.3 -0.2 2.0"
+    scene_init = ("exotica/Scene", dict(_scene_init("lwr_simplified", "arm")[1],
+                                        Links=[("exotica/Link", {"Name": "Obstacle", "Transform": "1 1 1"})],
+                                        Trajectories=[("exotica/Trajectory", {"Link": "Obstacle", "Trajectory": text})]))
+    robot = [("exotica/Sphere", {"Link": "lwr_arm_%d_link" % k, "Radius": "0.1", "Group": "Robot"}) for k in range(3, 8)]
+    obst = [("exotica/Sphere", {"Link": "Obstacle", "LinkOffset": "0 %g 0" % y, "Radius": "0.15", "Group": "Obstacle"}) for y in (-0.1, 0.0, 0.1)]
+    maps_init = [("exotica/SphereCollision", {"Name": "Col", "Precision": "0.1", "EndEffector": robot + obst}),
+                 ("exotica/EffPosition", {"Name": "Obs", "EndEffector": [("exotica/Frame", {"Link": "Obstacle", "LinkOffset": "0 0.2 0"})]})]
+    init = ("exotica/TimeIndexedProblem", {"Name": "ti", "PlanningScene": scene_init, "Maps": maps_init, "T": T, "tau": tau,
+                                           "Cost": [("exotica/Task", {"Task": "Col"}), ("exotica/Task", {"Task": "Obs"})]})
+    prob = exo.Setup.create_problem(init)
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    tree.add_environment_element("Obstacle", generated_slot=0)
+    orc = oracle_lib.Oracle(tree)
+    maps = [{"type": "SphereCollision", "Precision": 0.1,
+             "EndEffector": [{"Link": "lwr_arm_%d_link" % k, "Radius": 0.1, "Group": "Robot"} for k in range(3, 8)] +
+                            [{"Link": "Obstacle", "LinkOffset": [0, y, 0], "Radius": 0.15, "Group": "Obstacle"} for y in (-0.1, 0.0, 0.1)]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "Obstacle", "LinkOffset": [0, 0.2, 0]}]}]
+    orc.set_problem(maps)
+    ref_traj = RefTrajectory(text)
+    gen = np.array([ref_traj.get_position(t * tau) for t in range(T)]).reshape(T, 1, 12)  # Scene::Update(x, t * tau)
+    rng = np.random.default_rng(61)
+    X = rng.uniform(orc.lower, orc.upper, size=(B, T, 7))
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X.reshape(B * T, 7), T=T, generated=gen)
+    assert max_abs_err(phi, phi_ref) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    # the moving link really moves: its EffPosition entries differ between the first and the last timestep
+    assert np.abs(phi.reshape(B, T, -1)[0, 0, 1:] - phi.reshape(B, T, -1)[0, -1, 1:]).max() > 0.1
+    assert abs(prob.get_scene().get_trajectory("Obstacle").get_duration() - 3.5) < 1e-12
+    with pytest.raises(exo.ExoticaError, match="Can't find link"):
+        prob.get_scene().add_trajectory("NoSuchLink", text)
+
+
+@pytest.mark.gpu
 def test_ik_solver_and_hessian_through_the_python_surface(oracle_lib):
     # exotica_examples/scripts/example_ik_manual_initialization shape: solver + problem from initializers
     eff = ("exotica/EffFrame", {"Name": "Position", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
