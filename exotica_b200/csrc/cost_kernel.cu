@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(128) exo_cost_endpose_kernel(const __grid_cons
 //   grad[t] = 2 ct J[t]^T S[t] ydiff[t] + 2 ct W xdiff[t] - 2 ct W xdiff[t + 1]      (t >= t_first; zero before)
 // and UnconstrainedEndPoseProblem::GetScalarJacobian (unconstrained_end_pose_problem.cpp:84-87) when T = 1.  One lane per
 // evaluation: ydiff (SO(3) log included) goes to shared memory [row][lane], then one pass over the Jacobian (coalesced in SoA).
+template <int NT>  // NT = 8: at most 8 controlled joints (register accumulators); NT = 0: any N
 __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_constant__ CostGradParams P)
 {
     extern __shared__ double yd_s[];  // [length_jac][128]
@@ -82,10 +83,29 @@ __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_con
         const double* J = P.jac + e * P.j_se;
         const double* x = C.x + e * C.x_se;
         const double two_ct = 2.0 * C.ct;
-        for (int n = 0; n < N; ++n)
+        double acc[NT > 0 ? NT : 1];
+        if (NT > 0)
         {
+            // N <= NT: rows outermost, N independent accumulators in registers (one shared-memory read per row, N loads in flight)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[n] = 0.0;
+            for (int r = 0; r < P.length_jac; ++r)
+            {
+                const double y = yd[r * 128];
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                    if (n < N) acc[n] += J[r * P.j_sr + n * P.j_sc] * y;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < (NT > 0 ? NT : N); ++n)
+        {
+            if (n >= N) continue;
             double s = 0.0;
-            for (int r = 0; r < P.length_jac; ++r) s += J[r * P.j_sr + n * P.j_sc] * yd[r * 128];
+            if (NT > 0)
+                s = acc[n];
+            else
+                for (int r = 0; r < P.length_jac; ++r) s += J[r * P.j_sr + n * P.j_sc] * yd[r * 128];
             s *= two_ct;
             if (C.W && t > 0)
             {
@@ -102,6 +122,7 @@ __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_con
 // tasks with precision rho > 0 add  C += rho |ydiff|^2,  R += rho J^T J,  v = -ydiff + J qhat,  r += rho J^T v,  rhat += rho |v|^2.
 // One lane per evaluation; per row the precision and v sit in shared memory [row][lane]; J is re-read from L1 / L2 for the
 // N (N + 1) / 2 distinct entries of the symmetric R.
+template <int NT>  // NT = 8: at most 8 controlled joints, R and r accumulate in registers; NT = 0: any N
 __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_constant__ AicoParams P)
 {
     extern __shared__ double sh[];  // [2][length_jac][128]
@@ -124,6 +145,57 @@ __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_con
         const double* J = P.jac + e * P.j_se;
         const double* q = C.x + e * C.x_se;
         double cost = 0.0, rhat = 0.0;
+        double* Re = P.R + e * P.R_se;
+        double* re = P.r + e * P.r_se;
+        if (NT > 0)
+        {
+            // N <= NT: one pass over J -- each row is loaded once into registers and added to R and r as a rank-one update
+            constexpr int NR = NT > 0 ? NT : 1;  // (the NT = 0 instantiation never runs this block)
+            double qn[NR], Racc[NR * (NR + 1) / 2], racc[NR];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+            {
+                qn[n] = n < N ? q[n * C.x_sk] : 0.0;
+                racc[n] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < NT * (NT + 1) / 2; ++k) Racc[k] = 0.0;
+            for (int r = 0; r < LJ; ++r)
+            {
+                const double yd = v[r * 128], prec = a[r * 128];
+                double Jr[NR];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) Jr[n] = n < N ? J[r * P.j_sr + n * P.j_sc] : 0.0;
+                double s = -yd;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) s += Jr[n] * qn[n];
+                cost += prec * yd * yd;
+                rhat += prec * s * s;
+#pragma unroll
+                for (int i = 0; i < NT; ++i)
+                {
+                    const double w = prec * Jr[i];
+                    racc[i] += w * s;
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) Racc[i * (i + 1) / 2 + j] += w * Jr[j];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+            {
+                if (i >= N) continue;
+                re[i * P.r_sk] = racc[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                {
+                    Re[i * P.R_si + j * P.R_sj] = Racc[i * (i + 1) / 2 + j];
+                    Re[j * P.R_si + i * P.R_sj] = Racc[i * (i + 1) / 2 + j];
+                }
+            }
+            P.cost[e] = C.ct * cost;
+            P.rhat[e] = rhat;
+            continue;
+        }
         for (int r = 0; r < LJ; ++r)
         {
             const double yd = v[r * 128], prec = a[r * 128];
@@ -135,8 +207,6 @@ __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_con
         }
         P.cost[e] = C.ct * cost;
         P.rhat[e] = rhat;
-        double* Re = P.R + e * P.R_se;
-        double* re = P.r + e * P.r_se;
         for (int i = 0; i < N; ++i)
         {
             double ri = 0.0;
@@ -194,11 +264,17 @@ cudaError_t launch_cost_gradient(const CostGradParams& P, cudaStream_t stream)
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024)
     {
-        cudaError_t e = cudaFuncSetAttribute(exo_cost_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(exo_cost_gradient_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(exo_cost_gradient_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int64_t blocks = (n_evals + 127) / 128;
-    exo_cost_gradient_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, smem, stream>>>(P);
+    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    if (P.c.n_ctrl <= 8)
+        exo_cost_gradient_kernel<8><<<grid, 128, smem, stream>>>(P);
+    else
+        exo_cost_gradient_kernel<0><<<grid, 128, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -210,11 +286,17 @@ cudaError_t launch_aico_messages(const AicoParams& P, cudaStream_t stream)
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024)
     {
-        cudaError_t e = cudaFuncSetAttribute(exo_aico_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(exo_aico_messages_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(exo_aico_messages_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int64_t blocks = (n_evals + 127) / 128;
-    exo_aico_messages_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 128, smem, stream>>>(P);
+    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    if (P.c.n_ctrl <= 8)
+        exo_aico_messages_kernel<8><<<grid, 128, smem, stream>>>(P);
+    else
+        exo_aico_messages_kernel<0><<<grid, 128, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
