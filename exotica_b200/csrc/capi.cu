@@ -1225,24 +1225,31 @@ int exo_problem_cost_jacobian_batch_host(exo_problem* p, const double* h_x, int6
     if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
     int rc = ensure_pipeline(p, traj_per_chunk * T, false);
     if (rc != EXO_OK) return rc;
-    cudaEvent_t prev_done = nullptr;
+    struct EventGuard  // destroyed on every return path
+    {
+        cudaEvent_t ev = nullptr;
+        ~EventGuard()
+        {
+            if (ev) cudaEventDestroy(ev);
+        }
+    } prev_done;
     int b = 0;
     for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
     {
         const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
         cudaStream_t s = p->streams[b];
         CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        // NOTE: one scratch buffer per problem: the chunks' kernels are serialised on it through events below
-        if (prev_done) CUDA_TRY(cudaStreamWaitEvent(s, prev_done, 0));
+        // one scratch buffer per problem (exo_problem_cost_gradient_batch): the chunks' kernels are serialised on it through an
+        // event, their copies still overlap
+        if (prev_done.ev) CUDA_TRY(cudaStreamWaitEvent(s, prev_done.ev, 0));
         rc = exo_problem_cost_gradient_batch(p, p->d_x[b], nt, layout, h_cost_traj ? p->d_cost[b] : nullptr, p->d_grad[b], s);
         if (rc != EXO_OK) return rc;
-        if (!prev_done) CUDA_TRY(cudaEventCreateWithFlags(&prev_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(prev_done, s));
+        if (!prev_done.ev) CUDA_TRY(cudaEventCreateWithFlags(&prev_done.ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(prev_done.ev, s));
         if (h_cost_traj) CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(h_grad + t0 * T * N, p->d_grad[b], n * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
-    if (prev_done) cudaEventDestroy(prev_done);
     return EXO_OK;
 }
 
