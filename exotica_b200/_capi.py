@@ -341,7 +341,7 @@ class Problem(object):
     def chain_info(self):
         out = (ctypes.c_int32 * 4)()
         check(lib().exo_problem_chain_info(self.h, out))
-        return {"lowered": bool(out[0]), "joints": out[1], "all_revolute": bool(out[2]), "frames": out[3]}
+        return {"lowered": bool(out[0]), "joints": out[1], "all_revolute": bool(out[2] & 1), "orthogonal_links": bool(out[2] & 2), "frames": out[3]}
 
     def set_cost(self, rho, T=1, goal=None, ct=1.0, W=None):
         """rho[T][n_maps] (broadcast from [n_maps]); goal[1 or T][length_Phi] or None (SetZero goal); W[N] or None."""

@@ -533,7 +533,7 @@ int exo_problem_chain_info(const exo_problem* p, int32_t out[4])
     if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
     out[0] = p->chain_ok ? 1 : 0;
     out[1] = p->chain_ok ? p->chain.n_joints : 0;
-    out[2] = p->chain_ok ? p->chain.all_revolute : 0;
+    out[2] = p->chain_ok ? (p->chain.all_revolute | (p->chain.ortho << 1)) : 0;
     out[3] = p->chain_ok ? p->chain.n_frames : 0;
     return EXO_OK;
 }

@@ -66,23 +66,34 @@ __device__ __forceinline__ void st(char* p, double v)
     *reinterpret_cast<double*>(p) = v;
 }
 
-// Rx(alpha_J) * Tx(a_J) applied on the right of cur (joint 0: already part of the base frame)
-template <int J>
+// Rx(alpha_J) * Tx(a_J) applied on the right of cur (joint 0: already part of the base frame).
+// ORTHO: every link of the chain has alpha = +-90 degrees and a = 0 (consecutive axes perpendicular and intersecting: the LWR,
+// most 7-DoF arms) -- the rotation is a signed swap of the y and z columns, 6 multiplications instead of 15 FP64 operations.
+// Same bits as the general form: fma(0, y, s * z) = s * z and a * x contributes an exact zero.
+template <int J, bool ORTHO>
 __device__ __forceinline__ void dh_link(const ChainParams& P, Fr& cur)
 {
     if (J == 0) return;
-    const double ca = P.joint[J].ca, sa = P.joint[J].sa, a = P.joint[J].a;
+    const double sa = P.joint[J].sa;
+    const double y0 = cur.m1, y1 = cur.m4, y2 = cur.m7;
+    if (ORTHO)
+    {
+        cur.m1 = sa * cur.m2; cur.m2 = -(sa * y0);
+        cur.m4 = sa * cur.m5; cur.m5 = -(sa * y1);
+        cur.m7 = sa * cur.m8; cur.m8 = -(sa * y2);
+        return;
+    }
+    const double ca = P.joint[J].ca, a = P.joint[J].a;
     cur.x = fma(a, cur.m0, cur.x);
     cur.y = fma(a, cur.m3, cur.y);
     cur.z = fma(a, cur.m6, cur.z);
-    const double y0 = cur.m1, y1 = cur.m4, y2 = cur.m7;
     cur.m1 = fma(ca, y0, sa * cur.m2); cur.m2 = fma(ca, cur.m2, -(sa * y0));
     cur.m4 = fma(ca, y1, sa * cur.m5); cur.m5 = fma(ca, cur.m5, -(sa * y1));
     cur.m7 = fma(ca, y2, sa * cur.m8); cur.m8 = fma(ca, cur.m8, -(sa * y2));
 }
 
 // Rz(theta) * Tz(d) applied on the right of cur; xq is the state entry feeding the joint
-template <int J, bool ALLREV>
+template <int J, int ALLREV>
 __device__ __forceinline__ void dh_joint(const ChainParams& P, Fr& cur, double sn, double cs, double xq)
 {
     const ChainJointP& jp = P.joint[J];
@@ -105,7 +116,7 @@ __device__ __forceinline__ void dh_joint(const ChainParams& P, Fr& cur, double s
 // Jacobian column of joint J for requested frame F (KinematicTree::ComputeJ, kinematic_tree.cpp:919-945):
 //   column = temp_B.M^-1 * [ w x (temp_A.p - p_joint) ; w ]   (revolute)   |   temp_B.M^-1 * [ w ; 0 ]   (prismatic)
 // WITHB / SIX are per-frame facts hoisted out of the joint loop by the caller.
-template <int J, bool ALLREV, bool WITHB, bool SIX>
+template <int J, int ALLREV, bool WITHB, bool SIX>
 __device__ __forceinline__ void chain_column(const ChainParams& P, int f, char* jac_e, int64_t sr_b, double wx, double wy, double wz, double px,
                                              double py, double pz, double ax, double ay, double az)
 {
@@ -153,7 +164,7 @@ __device__ __forceinline__ void chain_column(const ChainParams& P, int f, char* 
 }
 
 // Same for the maps that keep other rows of the column (EffOrientation, EffPositionXY, Distance): runtime row mode
-template <int J, bool ALLREV>
+template <int J, int ALLREV>
 __device__ __forceinline__ void chain_column_g(const ChainParams& P, int f, char* jac_e, int64_t sr_b, double wx, double wy, double wz, double px,
                                                double py, double pz, double ax, double ay, double az, double ux, double uy, double uz)
 {
@@ -349,14 +360,14 @@ __device__ __noinline__ void chain_slow_eval(const ChainParams& P, const char* x
     }
 }
 
-template <int NJ, bool ALLREV, int J>
+template <int NJ, int ALLREV, int J>
 struct ChainUnroll
 {
     // compose only (first pass of CHAIN_TWO_PASS)
     static __device__ __forceinline__ void compose(const ChainParams& P, Fr& cur, const double (&q)[NJ], const double (&sn)[NJ],
                                                    const double (&cs)[NJ])
     {
-        dh_link<J>(P, cur);
+        dh_link<J, (ALLREV & 2) != 0>(P, cur);
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
         ChainUnroll<NJ, ALLREV, J + 1>::compose(P, cur, q, sn, cs);
     }
@@ -365,7 +376,7 @@ struct ChainUnroll
     static __device__ __forceinline__ void emit(const ChainParams& P, char* jac_e, int64_t sr_b, Fr& cur, const double (&q)[NJ],
                                                 const double (&sn)[NJ], const double (&cs)[NJ], double ax, double ay, double az)
     {
-        dh_link<J>(P, cur);
+        dh_link<J, (ALLREV & 2) != 0>(P, cur);
         chain_column<J, ALLREV, WITHB, SIX>(P, 0, jac_e, sr_b, cur.m2, cur.m5, cur.m8, cur.x, cur.y, cur.z, ax, ay, az);
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
         ChainUnroll<NJ, ALLREV, J + 1>::template emit<WITHB, SIX>(P, jac_e, sr_b, cur, q, sn, cs, ax, ay, az);
@@ -374,7 +385,7 @@ struct ChainUnroll
     static __device__ __forceinline__ void record(const ChainParams& P, Fr& cur, const double (&q)[NJ], const double (&sn)[NJ],
                                                   const double (&cs)[NJ], double (&W)[NJ][3], double (&PJ)[NJ][3])
     {
-        dh_link<J>(P, cur);
+        dh_link<J, (ALLREV & 2) != 0>(P, cur);
         W[J][0] = cur.m2; W[J][1] = cur.m5; W[J][2] = cur.m8;
         PJ[J][0] = cur.x; PJ[J][1] = cur.y; PJ[J][2] = cur.z;
         dh_joint<J, ALLREV>(P, cur, sn[J], cs[J], q[J]);
@@ -394,7 +405,7 @@ struct ChainUnroll
         ChainUnroll<NJ, ALLREV, J + 1>::template columns<WITHB, SIX>(P, f, jac_e, sr_b, W, PJ, ax, ay, az);
     }
 };
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 struct ChainUnroll<NJ, ALLREV, NJ>
 {
     static __device__ __forceinline__ void compose(const ChainParams&, Fr&, const double (&)[NJ], const double (&)[NJ], const double (&)[NJ]) {}
@@ -429,7 +440,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
 
 // GEN: some requested frame belongs to a map that keeps other rows than (v, w) / (v) -- EffOrientation, EffPositionXY,
 // Distance; the plain instantiations do not carry that code (it costs the hot kernel registers)
-template <int NJ, bool ALLREV, int VARIANT, bool GEN>
+template <int NJ, int ALLREV, int VARIANT, bool GEN>
 __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const __grid_constant__ ChainParams P)
 {
     const int64_t stride = (int64_t)gridDim.x * CTPB;
@@ -554,7 +565,7 @@ __global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const _
 // J: every joint's column (KinematicTree::ComputeJ) is dotted with S ydiff of its frame the moment it exists.  For a frame with
 // a constant base, column = Binv [v; w], so the dot product is taken against Binv^T (S ydiff) instead -- one 3x3 product per frame,
 // not per column.  HBM traffic per evaluation: N doubles in (+ 2 N neighbours from L2 for the transition term), N + 1 out.
-template <int J, bool ALLREV>
+template <int J, int ALLREV>
 __device__ __forceinline__ double chain_dot(const ChainParams& P, double wx, double wy, double wz, double px, double py, double pz, double ax, double ay,
                                             double az, const double (&yd)[6], bool six)
 {
@@ -567,7 +578,7 @@ __device__ __forceinline__ double chain_dot(const ChainParams& P, double wx, dou
     return s;
 }
 
-template <int NJ, bool ALLREV, int J>
+template <int NJ, int ALLREV, int J>
 struct ChainDots
 {
     static __device__ __forceinline__ void run(const ChainParams& P, const double (&W)[NJ][3], const double (&PJ)[NJ][3], double ax, double ay, double az,
@@ -577,7 +588,7 @@ struct ChainDots
         ChainDots<NJ, ALLREV, J + 1>::run(P, W, PJ, ax, ay, az, yd, six, g);
     }
 };
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 struct ChainDots<NJ, ALLREV, NJ>
 {
     static __device__ __forceinline__ void run(const ChainParams&, const double (&)[NJ][3], const double (&)[NJ][3], double, double, double,
@@ -612,7 +623,7 @@ __device__ __forceinline__ double costgrad_column_extra(const ChainParams& P, co
     return s;
 }
 
-template <int NJ, bool ALLREV, int J>
+template <int NJ, int ALLREV, int J>
 struct ChainGradStore
 {
     static __device__ __forceinline__ void run(const ChainParams& P, const ChainGradParams& G, const char* xe, int t, double rho_jl, const double* goal,
@@ -623,7 +634,7 @@ struct ChainGradStore
         ChainGradStore<NJ, ALLREV, J + 1>::run(P, G, xe, t, rho_jl, goal, g, ge, c);
     }
 };
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 struct ChainGradStore<NJ, ALLREV, NJ>
 {
     static __device__ __forceinline__ void run(const ChainParams&, const ChainGradParams&, const char*, int, double, const double*, const double (&)[NJ],
@@ -633,7 +644,7 @@ struct ChainGradStore<NJ, ALLREV, NJ>
 #ifndef EXO_COSTGRAD_MAXNREG
 #define EXO_COSTGRAD_MAXNREG 168
 #endif
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 __global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G)
 {
     const int64_t stride = (int64_t)gridDim.x * CTPB;
@@ -736,7 +747,7 @@ __global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(cons
 }
 
 // ct * (ydiff^T S ydiff + transition term) of the state at xe, formed in registers (the cost half of the kernel above)
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 __device__ __forceinline__ double chain_cost_only(const ChainParams& P, const ChainGradParams& G, const char* xe, int t)
 {
     double q[NJ], sn[NJ], cs[NJ];
@@ -801,7 +812,7 @@ __device__ __forceinline__ double chain_cost_only(const ChainParams& P, const Ch
 
 // IKSolver::Solve's backtracking line search (ik_solver.cpp:146-161) for every active start state: the first of the ten steps
 // alpha = 1, 0.9, ..., 0.1 whose cost is below the current one is taken (q <- q - alpha qd, qd <- alpha qd).
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 __global__ void __maxnreg__(128) exo_chain_ik_linesearch_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G,
                                                                 const __grid_constant__ ChainLineSearchParams L)
 {
@@ -832,7 +843,7 @@ __global__ void __maxnreg__(128) exo_chain_ik_linesearch_kernel(const __grid_con
 
 // One evaluation (Phi and J of every map of the program) with the generic row emitter: what exo_chain_kernel computes, without
 // its streaming machinery -- used inside the single-launch IK solve, where Phi and J go to an L2-resident workspace
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 __device__ __forceinline__ void chain_eval_one(const ChainParams& P, const char* xe, char* phi_e, char* jac_e)
 {
     if (P.has_prefix)
@@ -887,7 +898,7 @@ __device__ __forceinline__ void chain_eval_one(const ChainParams& P, const char*
 // IKSolver::Solve (ik_solver.cpp:73-240) of one start state per lane, start to finish: prob_->Update(q), the damped
 // pseudo-inverse step, the backtracking line search and the termination tests, iterated in registers / on the lane's own column
 // of the SoA workspace.  Lanes that stop wait for the slowest lane of their warp; nothing waits for the host.
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 __global__ void __maxnreg__(168) exo_chain_ik_solve_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G,
                                                            const __grid_constant__ ChainLineSearchParams L, const __grid_constant__ IkParams K,
                                                            const __grid_constant__ CostParams C, int max_iterations)
@@ -926,7 +937,7 @@ __global__ void __maxnreg__(168) exo_chain_ik_solve_kernel(const __grid_constant
     }
 }
 
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 cudaError_t chain_ik_solve_launch_t(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
                                     const CostParams& C, int max_iterations, cudaStream_t stream)
 {
@@ -935,7 +946,7 @@ cudaError_t chain_ik_solve_launch_t(const ChainParams& P, const ChainGradParams&
     return cudaGetLastError();
 }
 
-template <bool ALLREV>
+template <int ALLREV>
 cudaError_t chain_ik_solve_launch_nj(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, const IkParams& K,
                                      const CostParams& C, int max_iterations, cudaStream_t stream)
 {
@@ -953,7 +964,7 @@ cudaError_t chain_ik_solve_launch_nj(const ChainParams& P, const ChainGradParams
     }
 }
 
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 cudaError_t chain_ik_linesearch_launch_t(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)
 {
     const int64_t blocks = (P.n_evals + CTPB - 1) / CTPB;
@@ -961,7 +972,7 @@ cudaError_t chain_ik_linesearch_launch_t(const ChainParams& P, const ChainGradPa
     return cudaGetLastError();
 }
 
-template <bool ALLREV>
+template <int ALLREV>
 cudaError_t chain_ik_linesearch_launch_nj(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)
 {
     switch (P.n_joints)
@@ -978,7 +989,7 @@ cudaError_t chain_ik_linesearch_launch_nj(const ChainParams& P, const ChainGradP
     }
 }
 
-template <int NJ, bool ALLREV>
+template <int NJ, int ALLREV>
 cudaError_t chain_costgrad_launch_t(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
     const int64_t want = (P.n_evals + CTPB - 1) / CTPB;
@@ -986,7 +997,7 @@ cudaError_t chain_costgrad_launch_t(const ChainParams& P, const ChainGradParams&
     return cudaGetLastError();
 }
 
-template <bool ALLREV>
+template <int ALLREV>
 cudaError_t chain_costgrad_launch_nj(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
     switch (P.n_joints)
@@ -1033,7 +1044,7 @@ static int chain_prefetch_generations()
     return gens;
 }
 
-template <int NJ, bool ALLREV, int VARIANT, bool GEN>
+template <int NJ, int ALLREV, int VARIANT, bool GEN>
 cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
 {
     static int ctas_per_sm = 0;  // occupancy is a property of the instantiation: query once
@@ -1054,7 +1065,7 @@ cudaError_t chain_launch_t(const ChainParams& P, int sms, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-template <bool ALLREV, int VARIANT, bool GEN>
+template <int ALLREV, int VARIANT, bool GEN>
 cudaError_t chain_launch_nj(const ChainParams& P, int sms, cudaStream_t stream)
 {
     switch (P.n_joints)
@@ -1078,6 +1089,7 @@ cudaError_t chain_launch_v(const ChainParams& P, int sms, cudaStream_t stream)
     for (int f = 0; f < P.n_frames; ++f) gen = gen || P.frame[f].row_mode > ROWS_V;
     if (gen)  // the generic row emitter exists in the one-pass variant only
         return P.all_revolute ? chain_launch_nj<true, CHAIN_REGS, true>(P, sms, stream) : chain_launch_nj<false, CHAIN_REGS, true>(P, sms, stream);
+    if (P.all_revolute && P.ortho && VARIANT == CHAIN_REGS) return chain_launch_nj<3, CHAIN_REGS, false>(P, sms, stream);  // bit 1: ORTHO links
     return P.all_revolute ? chain_launch_nj<true, VARIANT, false>(P, sms, stream) : chain_launch_nj<false, VARIANT, false>(P, sms, stream);
 }
 }  // namespace

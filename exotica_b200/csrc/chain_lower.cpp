@@ -237,6 +237,7 @@ bool chain_lower(const Program& prog, ChainParams& P)
     P.n_joints = n;
     P.n_ctrl = h.n_ctrl;
     P.all_revolute = 1;
+    P.ortho = 1;
 
     std::vector<const Op*> jop, fop;
     for (const Op& op : prog.ops)
@@ -333,6 +334,14 @@ bool chain_lower(const Program& prog, ChainParams& P)
             lead_th1[j - 1] = th1;
             lead_d1[j - 1] = d1;
             jp.ca = (double)ca; jp.sa = (double)sa; jp.a = (double)a;
+            // perpendicular, intersecting axes up to rounding: make it exact (the verification below still has the last word)
+            if (fabs(jp.ca) < 1e-15)
+            {
+                jp.ca = 0.0;
+                jp.sa = jp.sa > 0 ? 1.0 : -1.0;
+            }
+            if (fabs(jp.a) < 1e-15) jp.a = 0.0;
+            if (jp.ca != 0.0 || jp.a != 0.0) P.ortho = 0;
             // S_j = S0_j * (Rz(th2) Tz(d2))^-1
             LFrame tail = l_rotz(th2);
             tail.p[2] = d2;

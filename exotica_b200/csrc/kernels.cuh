@@ -102,6 +102,7 @@ struct ChainParams
     int32_t has_prefix, jl_enabled, jl_phi_off, jl_jrow_off;
     uint32_t zero_cols;
     int32_t all_revolute;
+    int32_t ortho, pad_ortho;  // every link has alpha = +-90 degrees and a = 0 (exact): dh_link's signed-swap form applies
     double base[12];  // frame in front of joint 0, z axis = joint 0's axis
     ChainJointP joint[CH_MAXJ];
     ChainFrameP frame[CH_MAXF];

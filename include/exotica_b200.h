@@ -229,7 +229,8 @@ const char* exo_problem_last_kernel(const exo_problem* problem);
  * joint slots, shared-memory bytes per thread. */
 int exo_problem_program_info(const exo_problem* problem, int32_t out[8]);
 /* Whether the program was lowered to the Denavit-Hartenberg chain kernel: out = {lowered (0/1), joints in the chain,
- * all joints revolute (0/1), requested frames}.  Host-only (valid after exo_problem_finalize, no device needed). */
+ * bit 0: all joints revolute, bit 1: every link has alpha = +-90 degrees and a = 0 (the signed-swap link form applies),
+ * requested frames}.  Host-only (valid after exo_problem_finalize, no device needed). */
 int exo_problem_chain_info(const exo_problem* problem, int32_t out[4]);
 
 /* ---- task cost and per-trajectory reductions (what the multi-GPU path gathers; SURVEY.md section 8 rows e, f1) --------

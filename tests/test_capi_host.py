@@ -55,7 +55,9 @@ def test_serial_chains_lower_to_dh(oracle_lib, robot, group, link, joints):
     orc.set_problem(maps)
     tree, prob = gpu_problem_from_maps(orc, maps)
     info = prob.chain_info()
-    assert info == {"lowered": True, "joints": joints, "all_revolute": True, "frames": 1}
+    # the LWR's consecutive axes are perpendicular and intersect (alpha = +-90 degrees, a = 0 exactly): the signed-swap link form
+    # applies; the test robot has two parallel axes in a row
+    assert info == {"lowered": True, "joints": joints, "all_revolute": True, "orthogonal_links": robot == "lwr_simplified", "frames": 1}
 
 
 def test_trees_and_relative_frames_stay_on_the_interpreter(oracle_lib):
