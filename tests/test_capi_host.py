@@ -92,6 +92,19 @@ def test_errors_use_the_status_and_message_channel(oracle_lib):
     x = np.zeros(7)
     rc = _capi.lib().exo_problem_update_batch(prob.h, x.ctypes.data, -1, 1, 0, x.ctypes.data, None, None)
     assert rc != 0 and b"negative" in _capi.lib().exo_last_error()
+    # the solver-facing entry points need a cost first (all of this is checked before any CUDA call)
+    p = x.ctypes.data
+    L = _capi.lib()
+    for rc in (L.exo_problem_cost_batch(prob.h, p, p, 1, 0, p, None, None),
+               L.exo_problem_cost_jacobian_batch(prob.h, p, p, p, 1, 0, p, None),
+               L.exo_problem_cost_gradient_batch(prob.h, p, 1, 0, None, p, None),
+               L.exo_problem_aico_task_messages_batch(prob.h, p, p, p, 1, 0, p, p, p, p, None)):
+        assert rc != 0 and b"exo_problem_set_cost has not been called" in L.exo_last_error()
+    with pytest.raises(_capi.ExoticaError, match="CenterOfMass needs mass"):
+        prob2 = _capi.Problem(tree)
+        prob2.add_task_map(_capi.MAP_CENTER_OF_MASS, elem_a=[3])
+    with pytest.raises(_capi.ExoticaError, match="kernel choice"):
+        prob.set_kernel(9)
 
 
 def test_trajectory_matches_the_independent_restatement():
