@@ -89,7 +89,23 @@ __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_con
             // N <= NT: rows outermost, N independent accumulators in registers (one shared-memory read per row, N loads in flight)
 #pragma unroll
             for (int n = 0; n < NT; ++n) acc[n] = 0.0;
-            for (int r = 0; r < P.length_jac; ++r)
+            // two rows per iteration: 2 N loads in flight per lane (the kernel is a stream of J: 365 MB per 409 600 evaluations;
+            // measured 120 us with one row per iteration, 109 us with two, 117 us with four)
+            int r = 0;
+            for (; r + 1 < P.length_jac; r += 2)
+            {
+                double j0[NT > 0 ? NT : 1], j1[NT > 0 ? NT : 1];
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                {
+                    j0[n] = n < N ? J[r * P.j_sr + n * P.j_sc] : 0.0;
+                    j1[n] = n < N ? J[(r + 1) * P.j_sr + n * P.j_sc] : 0.0;
+                }
+                const double y0 = yd[r * 128], y1 = yd[(r + 1) * 128];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) acc[n] += j0[n] * y0 + j1[n] * y1;
+            }
+            for (; r < P.length_jac; ++r)
             {
                 const double y = yd[r * 128];
 #pragma unroll

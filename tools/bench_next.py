@@ -29,8 +29,11 @@ def sync():
     _capi.check(_capi.lib().exo_device_synchronize())
 
 
+WARMUPS = 3
+
+
 def timed(fn, reps):
-    for _ in range(3):
+    for _ in range(WARMUPS):
         fn()
     sync()
     t0 = time.perf_counter()
@@ -43,7 +46,11 @@ def timed(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--profile", action="store_true", help="one warm-up and one launch per kernel, no host paths, 4 IK iterations (for ncu)")
     args = ap.parse_args()
+    if args.profile:
+        global WARMUPS
+        WARMUPS, args.reps = 1, 1
     peak = 6549.4
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -96,6 +103,16 @@ def main():
     ms = timed(lambda: backend.hessian_batch_device(dx.ptr, djac.ptr, EH, dh.ptr, T=1), max(3, args.reps // 2))
     line("task-map Hessians (raw-frame update + Hessian kernel), device", ms, EH, "evals", 8 * (LJ * N * N + LJ * N + N))
     dh.free()
+
+    if args.profile:
+        maps = [("exotica/EffFrame", {"Name": "Eff", "EndEffector": [frame("lwr_arm_6_link")]})]
+        ik_init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "ik", "PlanningScene": scene("lwr_simplified", "arm"), "Maps": maps,
+                                                           "Cost": [("exotica/Task", {"Task": "Eff", "Goal": "0.4 0.1 0.6 0 0 0"})]})
+        solver = exo.IKSolver({"MaxIterations": 4})
+        solver.specify_problem(exo.Setup.create_problem(ik_init))
+        solver.solve_batch(rng.uniform(lim[:, 0], lim[:, 1], size=(1 << 16, N)))
+        backend.h = None
+        return
 
     # host-buffer paths of the same problem
     px, pphi, pjac = exo.PinnedArray((B, T, N)), exo.PinnedArray((E, LP)), exo.PinnedArray((E, LJ, N))
