@@ -662,6 +662,12 @@ __global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(cons
         double q[NJ], sn[NJ], cs[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) q[j] = *reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off);
+        // as in exo_chain_kernel: pull the joint values of a CTA most of a resident generation ahead into L2
+        if (e + P.prefetch_ahead < P.n_evals)
+        {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) prefetch_l2(xe + P.prefetch_ahead * P.x_se_b + P.joint[j].x_byte_off);
+        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
         {
@@ -989,11 +995,25 @@ cudaError_t chain_ik_linesearch_launch_nj(const ChainParams& P, const ChainGradP
     }
 }
 
+static int chain_prefetch_generations();
+
 template <int NJ, int ALLREV>
 cudaError_t chain_costgrad_launch_t(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
+    static int resident = 0;  // threads resident on the device for this instantiation: query once
+    if (resident == 0)
+    {
+        int dev = 0, sms = 0, ctas = 0;
+        cudaError_t err = cudaGetDevice(&dev);
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, exo_chain_costgrad_kernel<NJ, ALLREV>, CTPB, 0);
+        if (err != cudaSuccess) return err;
+        resident = sms * (ctas > 0 ? ctas : 1) * CTPB;
+    }
     const int64_t want = (P.n_evals + CTPB - 1) / CTPB;
-    exo_chain_costgrad_kernel<NJ, ALLREV><<<(int)(want < (1 << 20) ? (want > 0 ? want : 1) : (1 << 20)), CTPB, 0, stream>>>(P, G);
+    ChainParams Q = P;
+    Q.prefetch_ahead = (int64_t)resident * chain_prefetch_generations() / 4;
+    exo_chain_costgrad_kernel<NJ, ALLREV><<<(int)(want < (1 << 20) ? (want > 0 ? want : 1) : (1 << 20)), CTPB, 0, stream>>>(Q, G);
     return cudaGetLastError();
 }
 
