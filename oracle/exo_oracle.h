@@ -17,11 +17,13 @@
  * in the reference, unpinned in exotica_core/package.xml:22-23) and Eigen's Quaternion(Matrix3)
  * conversion are restated from their published algorithms.
  *
- * Parity status: pinned against the reference's own known-answer tests (EffPosition goldens
- * test_maps.cpp:340-347, SphereCollision goldens test_maps.cpp:662-673, ten Valkyrie centre-of-mass
- * goldens exotica_examples/test/test_valkyrie_com:13-120) in tests/test_oracle_golden.py.  EffFrame
- * rotation encodings and JointLimit have no goldens in the reference ("parity unpinned" beyond the
- * reference's own finite-difference tests, which tests/test_oracle_fd.py reproduces).
+ * Parity status: pinned against every known-answer vector the reference's tests hold for maps on this path
+ * (tests/golden/reference_goldens.json, extracted from exotations/exotica_core_task_maps/test/test_maps.cpp: EffPosition
+ * :340-347, Distance :493-500, SphereCollision :651-673, JointPose :700-780, CenterOfMass :789-892) and the ten Valkyrie
+ * centre-of-mass goldens of exotica_examples/test/test_valkyrie_com:13-120, in tests/test_oracle_golden.py.  EffFrame /
+ * EffOrientation rotation encodings, EffAxisAlignment, EffPositionXY and JointLimit have no golden values in the reference:
+ * "parity unpinned" beyond the reference's own finite-difference tests (test_maps.cpp:115-200), which
+ * tests/test_oracle_fd.py reproduces on this oracle.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use
  * this library.  The product (exotica_b200/) never links, loads or calls it.
