@@ -1061,7 +1061,7 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
     if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
     if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
     if (n_traj == 0) return EXO_OK;
-    if (!d_x || !d_grad) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (!d_x || (!d_grad && !d_cost_traj)) return fail(EXO_ERR_INVALID, "NULL buffer");
     if (p->compiled_version != p->tree->version)
     {
         int rc = compile_and_upload(p);
@@ -1099,7 +1099,7 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
         g.g_se = k.x_se; g.g_sk = k.x_sk;
         g.T = c.T; g.t_first = c.t_first; g.T_goal = c.T_goal; g.n_maps = c.n_maps; g.length_phi = c.length_phi; g.n_rot = c.n_rot;
         chain_bind(p->chain, d_x, nullptr, nullptr, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
-        cudaError_t e = chain_costgrad_launch(p->chain, g, s);
+        cudaError_t e = d_grad ? chain_costgrad_launch(p->chain, g, s) : chain_cost_launch(p->chain, g, s);  // d_grad NULL: cost only
         if (e != cudaSuccess) return cuda_fail(e, "fused cost-gradient kernel launch");
         p->launches++;
         if (d_cost_traj)
@@ -1108,12 +1108,12 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
             if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
             p->launches++;
         }
-        p->last_kernel = "exo_chain_costgrad_kernel";
+        p->last_kernel = d_grad ? "exo_chain_costgrad_kernel" : "exo_chain_cost_kernel";
         return EXO_OK;
     }
     // general programs: Phi and J into the scratch buffer, then the cost and cost-gradient kernels
     double* d_phi = p->d_cg + E;
-    double* d_jac = d_phi + E * LP;
+    double* d_jac = d_grad ? d_phi + E * LP : nullptr;  // cost only: forward kinematics without Jacobians
     rc = launch(p, d_x, E, E, (int32_t)T, layout, d_phi, d_jac, s, false);
     if (rc != EXO_OK) return rc;
     if (d_cost_traj)
@@ -1121,6 +1121,7 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
         rc = exo_problem_cost_batch(p, d_x, d_phi, n_traj, layout, d_cost_traj, nullptr, stream);
         if (rc != EXO_OK) return rc;
     }
+    if (!d_grad) return EXO_OK;
     return exo_problem_cost_jacobian_batch(p, d_x, d_phi, d_jac, n_traj, layout, d_grad, stream);
 }
 
@@ -1176,6 +1177,18 @@ int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t
     return EXO_OK;
 }
 
+namespace
+{
+struct EventGuard  // a CUDA event destroyed on every return path
+{
+    cudaEvent_t ev = nullptr;
+    ~EventGuard()
+    {
+        if (ev) cudaEventDestroy(ev);
+    }
+};
+}  // namespace
+
 int exo_problem_cost_batch_host(exo_problem* p, const double* h_x, int64_t n_traj, int32_t layout, double* h_cost_traj)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
@@ -1192,16 +1205,37 @@ int exo_problem_cost_batch_host(exo_problem* p, const double* h_x, int64_t n_tra
     if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
     int rc = ensure_pipeline(p, traj_per_chunk * T, false);
     if (rc != EXO_OK) return rc;
+    if (p->compiled_version != p->tree->version)
+    {
+        rc = compile_and_upload(p);
+        if (rc != EXO_OK) return rc;
+    }
+    EventGuard prev_done;
     int b = 0;
     for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
     {
         const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
         cudaStream_t s = p->streams[b];
         CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        rc = launch(p, p->d_x[b], n, n, (int32_t)T, layout, p->d_phi[b], nullptr, s, false);
-        if (rc != EXO_OK) return rc;
-        rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
-        if (rc != EXO_OK) return rc;
+        ChainGradParams probe;
+        memset(&probe, 0, sizeof(probe));
+        if (fused_costgrad_eligible(p, probe))
+        {
+            // chain programs: one kernel, forward kinematics and cost in registers (its per-evaluation scratch is shared by the
+            // chunks: serialise the kernels through an event, the copies still overlap)
+            if (prev_done.ev) CUDA_TRY(cudaStreamWaitEvent(s, prev_done.ev, 0));
+            rc = exo_problem_cost_gradient_batch(p, p->d_x[b], nt, layout, p->d_cost[b], nullptr, s);
+            if (rc != EXO_OK) return rc;
+            if (!prev_done.ev) CUDA_TRY(cudaEventCreateWithFlags(&prev_done.ev, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(prev_done.ev, s));
+        }
+        else
+        {
+            rc = launch(p, p->d_x[b], n, n, (int32_t)T, layout, p->d_phi[b], nullptr, s, false);
+            if (rc != EXO_OK) return rc;
+            rc = exo_problem_cost_batch(p, p->d_x[b], p->d_phi[b], nt, layout, p->d_cost[b], nullptr, s);
+            if (rc != EXO_OK) return rc;
+        }
         CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < exo_problem::NBUF; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
@@ -1225,14 +1259,7 @@ int exo_problem_cost_jacobian_batch_host(exo_problem* p, const double* h_x, int6
     if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
     int rc = ensure_pipeline(p, traj_per_chunk * T, false);
     if (rc != EXO_OK) return rc;
-    struct EventGuard  // destroyed on every return path
-    {
-        cudaEvent_t ev = nullptr;
-        ~EventGuard()
-        {
-            if (ev) cudaEventDestroy(ev);
-        }
-    } prev_done;
+    EventGuard prev_done;
     int b = 0;
     for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
     {

@@ -816,6 +816,43 @@ __device__ __forceinline__ double chain_cost_only(const ChainParams& P, const Ch
     return G.ct * c;
 }
 
+// Task cost only (GetScalarTaskCost + GetScalarTransitionCost per timestep / GetScalarCost): forward kinematics and cost in
+// registers, one double per evaluation leaves the SM
+template <int NJ, int ALLREV>
+__global__ void __maxnreg__(128) exo_chain_cost_kernel(const __grid_constant__ ChainParams P, const __grid_constant__ ChainGradParams G)
+{
+    const int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x;
+    if (e >= P.n_evals) return;
+    const int t = (int)(e % G.T);
+    const char* xe = reinterpret_cast<const char*>(P.x) + e * P.x_se_b;
+    G.cost_eval[e] = t < G.t_first ? 0.0 : chain_cost_only<NJ, ALLREV>(P, G, xe, t);
+}
+
+template <int NJ, int ALLREV>
+cudaError_t chain_cost_launch_t(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    const int64_t blocks = (P.n_evals + CTPB - 1) / CTPB;
+    exo_chain_cost_kernel<NJ, ALLREV><<<(int)(blocks > 0 ? blocks : 1), CTPB, 0, stream>>>(P, G);
+    return cudaGetLastError();
+}
+
+template <int ALLREV>
+cudaError_t chain_cost_launch_nj(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    switch (P.n_joints)
+    {
+        case 1: return chain_cost_launch_t<1, ALLREV>(P, G, stream);
+        case 2: return chain_cost_launch_t<2, ALLREV>(P, G, stream);
+        case 3: return chain_cost_launch_t<3, ALLREV>(P, G, stream);
+        case 4: return chain_cost_launch_t<4, ALLREV>(P, G, stream);
+        case 5: return chain_cost_launch_t<5, ALLREV>(P, G, stream);
+        case 6: return chain_cost_launch_t<6, ALLREV>(P, G, stream);
+        case 7: return chain_cost_launch_t<7, ALLREV>(P, G, stream);
+        case 8: return chain_cost_launch_t<8, ALLREV>(P, G, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
 // IKSolver::Solve's backtracking line search (ik_solver.cpp:146-161) for every active start state: the first of the ten steps
 // alpha = 1, 0.9, ..., 0.1 whose cost is below the current one is taken (q <- q - alpha qd, qd <- alpha qd).
 template <int NJ, int ALLREV>
@@ -1132,6 +1169,11 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
 cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
 {
     return P.all_revolute ? chain_costgrad_launch_nj<true>(P, G, stream) : chain_costgrad_launch_nj<false>(P, G, stream);
+}
+
+cudaError_t chain_cost_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream)
+{
+    return P.all_revolute ? chain_cost_launch_nj<true>(P, G, stream) : chain_cost_launch_nj<false>(P, G, stream);
 }
 
 cudaError_t chain_ik_linesearch_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream)

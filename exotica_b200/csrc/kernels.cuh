@@ -143,6 +143,8 @@ struct ChainGradParams
     int32_t frame_rot[CH_MAXF];        // index into goal_rot, or -1 for position-only frames (EffPosition)
 };
 cudaError_t chain_costgrad_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream);
+// cost only: G.cost_eval[e] for every evaluation (G.grad unused)
+cudaError_t chain_cost_launch(const ChainParams& P, const ChainGradParams& G, cudaStream_t stream);
 
 // Fused line search of the batched IK step for chain programs (exo_chain_ik_linesearch_kernel): the ten trial states
 // q - alpha qd, alpha = 1 ... 0.1 (ik_solver.cpp:146-161), are evaluated in registers (forward kinematics + cost) until the cost

@@ -280,7 +280,9 @@ int exo_problem_aico_task_messages_batch(exo_problem* problem, const double* d_q
  * JointLimit maps run ONE fused kernel (exo_chain_costgrad_kernel): forward kinematics, ydiff with its SO(3) log, and every
  * Jacobian column dotted with S ydiff the moment it exists -- J is never materialised, N + 1 doubles per evaluation reach
  * HBM instead of (1 + N) x length_jacobian.  Other programs go through an internal scratch buffer and the three kernels
- * (exo_problem_set_kernel(1) forces that path; tests compare the two).  Calls on one problem must be serialised. */
+ * (exo_problem_set_kernel(1) forces that path; tests compare the two).  d_grad may be NULL: cost only (one kernel for chain
+ * programs, exo_chain_cost_kernel; forward kinematics without Jacobians + the cost kernel otherwise).  Calls on one problem
+ * must be serialised. */
 int exo_problem_cost_gradient_batch(exo_problem* problem, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj,
                                     double* d_grad, void* stream);
 /* Host buffers, states X[B][T][N] evaluation-major: H2D of the states -> forward kinematics + Jacobians (they stay on the

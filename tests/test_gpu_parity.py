@@ -521,6 +521,19 @@ def test_fused_cost_gradient_kernel(oracle_lib, case):
     for choice in (0, 1):
         a, b = results[(choice, _capi.LAYOUT_SOA)], results[(choice, _capi.LAYOUT_AOS_ROWMAJOR)]
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # cost only (no gradient buffer): one kernel for chain programs, FK + cost kernel otherwise; same costs
+    E = B * T
+    dx, dc = _capi.DeviceBuffer(E * 7), _capi.DeviceBuffer(B)
+    dx.upload(X.reshape(E, 7).T)
+    for choice, name in ((0, "exo_chain_cost_kernel"), (1, "exo_cost_kernel" if T > 1 else "exo_cost_kernel")):
+        prob.set_kernel(choice)
+        prob.cost_gradient_batch_device(dx.ptr, B, None, dc.ptr)
+        _capi.check(_capi.lib().exo_device_synchronize())
+        assert prob.last_kernel() == name
+        assert np.max(np.abs(dc.download((B,)) - results[(choice, _capi.LAYOUT_SOA)][0])) <= 1e-12 * max(1.0, np.abs(results[(choice, _capi.LAYOUT_SOA)][0]).max())
+    prob.set_kernel(0)
+    cost_h = prob.cost_batch_host(X if T > 1 else X.reshape(B, 7))
+    assert np.max(np.abs(cost_h - results[(0, _capi.LAYOUT_SOA)][0])) <= 1e-12 * max(1.0, np.abs(cost_h).max())
 
 
 @pytest.mark.parametrize("layout", [_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR])
