@@ -438,10 +438,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ALLREV is a bit set: 1 = every joint revolute, 2 = signed-swap link step (dh_link), 4 = 128-register build of the signed-swap
+// kernel (16 instead of 14 warps per SM).  Measured: the extra warps pay where arithmetic bounds the kernel (cfg2b, EffPosition
+// only: 60.5 -> 55.2 us) and cost 1.5-2 us where the store pattern does (cfg2a 86.1 -> 87.6 us, cfg3 76 -> 78.5 us), so the launcher
+// picks bit 4 only for position-only frames.
+#ifndef EXO_CHAIN_DENSE_MAXNREG
+#define EXO_CHAIN_DENSE_MAXNREG 128
+#endif
 // GEN: some requested frame belongs to a map that keeps other rows than (v, w) / (v) -- EffOrientation, EffPositionXY,
 // Distance; the plain instantiations do not carry that code (it costs the hot kernel registers)
 template <int NJ, int ALLREV, int VARIANT, bool GEN>
-__global__ void __maxnreg__(ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const __grid_constant__ ChainParams P)
+__global__ void __maxnreg__((ALLREV & 4) ? EXO_CHAIN_DENSE_MAXNREG : ChainOcc<VARIANT>::maxnreg) exo_chain_kernel(const __grid_constant__ ChainParams P)
 {
     const int64_t stride = (int64_t)gridDim.x * CTPB;
     int64_t e = (int64_t)blockIdx.x * CTPB + threadIdx.x;
@@ -1146,7 +1153,12 @@ cudaError_t chain_launch_v(const ChainParams& P, int sms, cudaStream_t stream)
     for (int f = 0; f < P.n_frames; ++f) gen = gen || P.frame[f].row_mode > ROWS_V;
     if (gen)  // the generic row emitter exists in the one-pass variant only
         return P.all_revolute ? chain_launch_nj<true, CHAIN_REGS, true>(P, sms, stream) : chain_launch_nj<false, CHAIN_REGS, true>(P, sms, stream);
-    if (P.all_revolute && P.ortho && VARIANT == CHAIN_REGS) return chain_launch_nj<3, CHAIN_REGS, false>(P, sms, stream);  // bit 1: ORTHO links
+    if (P.all_revolute && P.ortho && VARIANT == CHAIN_REGS)
+    {
+        bool position_only = !P.jl_enabled;
+        for (int f = 0; f < P.n_frames; ++f) position_only = position_only && P.frame[f].row_mode == ROWS_V;
+        return position_only ? chain_launch_nj<7, CHAIN_REGS, false>(P, sms, stream) : chain_launch_nj<3, CHAIN_REGS, false>(P, sms, stream);
+    }
     return P.all_revolute ? chain_launch_nj<true, VARIANT, false>(P, sms, stream) : chain_launch_nj<false, VARIANT, false>(P, sms, stream);
 }
 }  // namespace
