@@ -338,6 +338,13 @@ static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y
 }
 
 
+// Output stores: streaming (st.global.cs) when EXO_STORE_CS is defined -- Phi / J are written once and not re-read by the kernel
+#ifdef EXO_STORE_CS
+#define EXO_ST(ptr, v) __stcs((ptr), (v))
+#else
+#define EXO_ST(ptr, v) (*(ptr) = (v))
+#endif
+
 // Rows of one Jacobian column the map keeps (program.h RowMode); (v, w) = linear / angular part of the frame's column,
 // (ux, uy, uz) = Phi.p / |Phi.p| for ROWS_DIST (distance.cpp:52), (Phi.M a) x direction for ROWS_WDOT
 // (eff_axis_alignment.cpp:140-144), ux = mass share for the accumulating CenterOfMass modes (center_of_mass.cpp:70)
@@ -347,22 +354,22 @@ __device__ __forceinline__ void store_rows(int mode, double* jc, int64_t sr, dou
     switch (mode)
     {
         case ROWS_VW:
-            jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2; jc[3 * sr] = w0; jc[4 * sr] = w1; jc[5 * sr] = w2;
+            EXO_ST(&jc[0], v0); EXO_ST(&jc[sr], v1); EXO_ST(&jc[2 * sr], v2); EXO_ST(&jc[3 * sr], w0); EXO_ST(&jc[4 * sr], w1); EXO_ST(&jc[5 * sr], w2);
             break;
         case ROWS_V:
-            jc[0] = v0; jc[sr] = v1; jc[2 * sr] = v2;
+            EXO_ST(&jc[0], v0); EXO_ST(&jc[sr], v1); EXO_ST(&jc[2 * sr], v2);
             break;
         case ROWS_W:
-            jc[0] = w0; jc[sr] = w1; jc[2 * sr] = w2;
+            EXO_ST(&jc[0], w0); EXO_ST(&jc[sr], w1); EXO_ST(&jc[2 * sr], w2);
             break;
         case ROWS_VXY:
-            jc[0] = v0; jc[sr] = v1;
+            EXO_ST(&jc[0], v0); EXO_ST(&jc[sr], v1);
             break;
         case ROWS_DIST:
-            jc[0] = ux * v0 + uy * v1 + uz * v2;
+            EXO_ST(&jc[0], ux * v0 + uy * v1 + uz * v2);
             break;
         case ROWS_WDOT:  // EffAxisAlignment: direction . (w x u) = w . (u x direction); (ux, uy, uz) = u x direction
-            jc[0] = ux * w0 + uy * w1 + uz * w2;
+            EXO_ST(&jc[0], ux * w0 + uy * w1 + uz * w2);
             break;
         case ROWS_V_ACC:  // CenterOfMass: ux = mass_i / M
             jc[0] += ux * v0; jc[sr] += ux * v1; jc[2 * sr] += ux * v2;

@@ -537,7 +537,7 @@ __global__ void __maxnreg__(168) exo_eval_kernel(const KernelParams P)
                     for (int k = 1; k <= n_zero; ++k)
                     {
                         double* jc = jr + (int64_t)zl[k] * sc;
-                        for (int r = 0; r < n_rows; ++r, jc += sr) jc[0] = 0.0;
+                        for (int r = 0; r < n_rows; ++r, jc += sr) EXO_ST(jc, 0.0);
                     }
                 }
                 else if (want_j)
