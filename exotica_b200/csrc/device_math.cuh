@@ -345,6 +345,12 @@ static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y
 #define EXO_ST(ptr, v) (*(ptr) = (v))
 #endif
 
+#ifdef EXO_PHI_STREAMING
+#define EXO_ST_PHI(ptr, v) __stcs((ptr), (v))
+#else
+#define EXO_ST_PHI(ptr, v) (*(ptr) = (v))
+#endif
+
 // Rows of one Jacobian column the map keeps (program.h RowMode); (v, w) = linear / angular part of the frame's column,
 // (ux, uy, uz) = Phi.p / |Phi.p| for ROWS_DIST (distance.cpp:52), (Phi.M a) x direction for ROWS_WDOT
 // (eff_axis_alignment.cpp:140-144), ux = mass share for the accumulating CenterOfMass modes (center_of_mass.cpp:70)
@@ -400,24 +406,24 @@ __device__ __forceinline__ void write_phi(int map_kind, int rot_type, const Fr& 
 {
     if (map_kind == EXO_MAP_FRAMES)
     {
-        ph[0] = Phi.m0; ph[sk] = Phi.m1; ph[2 * sk] = Phi.m2; ph[3 * sk] = Phi.m3; ph[4 * sk] = Phi.m4;
-        ph[5 * sk] = Phi.m5; ph[6 * sk] = Phi.m6; ph[7 * sk] = Phi.m7; ph[8 * sk] = Phi.m8;
-        ph[9 * sk] = Phi.x; ph[10 * sk] = Phi.y; ph[11 * sk] = Phi.z;
+        EXO_ST_PHI(&ph[0], Phi.m0); EXO_ST_PHI(&ph[sk], Phi.m1); EXO_ST_PHI(&ph[2 * sk], Phi.m2); EXO_ST_PHI(&ph[3 * sk], Phi.m3); EXO_ST_PHI(&ph[4 * sk], Phi.m4);
+        EXO_ST_PHI(&ph[5 * sk], Phi.m5); EXO_ST_PHI(&ph[6 * sk], Phi.m6); EXO_ST_PHI(&ph[7 * sk], Phi.m7); EXO_ST_PHI(&ph[8 * sk], Phi.m8);
+        EXO_ST_PHI(&ph[9 * sk], Phi.x); EXO_ST_PHI(&ph[10 * sk], Phi.y); EXO_ST_PHI(&ph[11 * sk], Phi.z);
         return;
     }
     if (map_kind == EXO_MAP_DISTANCE)
     {
-        ph[0] = norm3_scaled(Phi.x, Phi.y, Phi.z);  // distance.cpp:40: Phi.p.Norm()
+        EXO_ST_PHI(&ph[0], norm3_scaled(Phi.x, Phi.y, Phi.z));  // distance.cpp:40: Phi.p.Norm()
         return;
     }
     if (map_kind == EXO_MAP_EFF_POSITION_XY)
     {
-        ph[0] = Phi.x; ph[sk] = Phi.y;
+        EXO_ST_PHI(&ph[0], Phi.x); EXO_ST_PHI(&ph[sk], Phi.y);
         return;
     }
     if (map_kind != EXO_MAP_EFF_ORIENTATION)
     {
-        ph[0] = Phi.x; ph[sk] = Phi.y; ph[2 * sk] = Phi.z;
+        EXO_ST_PHI(&ph[0], Phi.x); EXO_ST_PHI(&ph[sk], Phi.y); EXO_ST_PHI(&ph[2 * sk], Phi.z);
         if (map_kind != EXO_MAP_EFF_FRAME) return;
         ph += 3 * sk;
     }
@@ -429,33 +435,33 @@ __device__ __forceinline__ void write_phi(int map_kind, int rot_type, const Fr& 
             double r, p, y;
             get_rpy(Phi, r, p, y);  // GetEulerZYX(a,b,c) == GetRPY(c,b,a)
             const bool zyx = rot_type == EXO_ROT_ZYX;
-            ph[0] = zyx ? y : r; ph[sk] = p; ph[2 * sk] = zyx ? r : y;
+            EXO_ST_PHI(&ph[0], zyx ? y : r); EXO_ST_PHI(&ph[sk], p); EXO_ST_PHI(&ph[2 * sk], zyx ? r : y);
             break;
         }
         case EXO_ROT_ZYZ:
         {
             double a, b, g;
             get_zyz(Phi, a, b, g);
-            ph[0] = a; ph[sk] = b; ph[2 * sk] = g;
+            EXO_ST_PHI(&ph[0], a); EXO_ST_PHI(&ph[sk], b); EXO_ST_PHI(&ph[2 * sk], g);
             break;
         }
         case EXO_ROT_ANGLE_AXIS:
         {
             double a, b, g;
             get_angle_axis(Phi, a, b, g);
-            ph[0] = a; ph[sk] = b; ph[2 * sk] = g;
+            EXO_ST_PHI(&ph[0], a); EXO_ST_PHI(&ph[sk], b); EXO_ST_PHI(&ph[2 * sk], g);
             break;
         }
         case EXO_ROT_QUATERNION:
         {
             double q[4];
             get_quaternion(Phi, q);
-            ph[0] = q[0]; ph[sk] = q[1]; ph[2 * sk] = q[2]; ph[3 * sk] = q[3];
+            EXO_ST_PHI(&ph[0], q[0]); EXO_ST_PHI(&ph[sk], q[1]); EXO_ST_PHI(&ph[2 * sk], q[2]); EXO_ST_PHI(&ph[3 * sk], q[3]);
             break;
         }
         default:  // EXO_ROT_MATRIX
-            ph[0] = Phi.m0; ph[sk] = Phi.m1; ph[2 * sk] = Phi.m2; ph[3 * sk] = Phi.m3; ph[4 * sk] = Phi.m4;
-            ph[5 * sk] = Phi.m5; ph[6 * sk] = Phi.m6; ph[7 * sk] = Phi.m7; ph[8 * sk] = Phi.m8;
+            EXO_ST_PHI(&ph[0], Phi.m0); EXO_ST_PHI(&ph[sk], Phi.m1); EXO_ST_PHI(&ph[2 * sk], Phi.m2); EXO_ST_PHI(&ph[3 * sk], Phi.m3); EXO_ST_PHI(&ph[4 * sk], Phi.m4);
+            EXO_ST_PHI(&ph[5 * sk], Phi.m5); EXO_ST_PHI(&ph[6 * sk], Phi.m6); EXO_ST_PHI(&ph[7 * sk], Phi.m7); EXO_ST_PHI(&ph[8 * sk], Phi.m8);
             break;
     }
 }
