@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_con
             for (int i = 0; i < NT; ++i)
             {
                 if (i >= N) continue;
-                re[i * P.r_sk] = racc[i];
+                __stcs(&re[i * P.r_sk], racc[i]);
 #pragma unroll
                 for (int j = 0; j <= i; ++j)
                 {
-                    Re[i * P.R_si + j * P.R_sj] = Racc[i * (i + 1) / 2 + j];
-                    Re[j * P.R_si + i * P.R_sj] = Racc[i * (i + 1) / 2 + j];
+                    __stcs(&Re[i * P.R_si + j * P.R_sj], Racc[i * (i + 1) / 2 + j]);
+                    __stcs(&Re[j * P.R_si + i * P.R_sj], Racc[i * (i + 1) / 2 + j]);
                 }
             }
             P.cost[e] = C.ct * cost;
@@ -227,13 +227,13 @@ __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_con
         {
             double ri = 0.0;
             for (int r = 0; r < LJ; ++r) ri += a[r * 128] * J[r * P.j_sr + i * P.j_sc] * v[r * 128];
-            re[i * P.r_sk] = ri;
+            __stcs(&re[i * P.r_sk], ri);
             for (int j = 0; j <= i; ++j)
             {
                 double s = 0.0;
                 for (int r = 0; r < LJ; ++r) s += a[r * 128] * J[r * P.j_sr + i * P.j_sc] * J[r * P.j_sr + j * P.j_sc];
-                Re[i * P.R_si + j * P.R_sj] = s;
-                Re[j * P.R_si + i * P.R_sj] = s;
+                __stcs(&Re[i * P.R_si + j * P.R_sj], s);
+                __stcs(&Re[j * P.R_si + i * P.R_sj], s);
             }
         }
     }
@@ -393,6 +393,12 @@ namespace exo
 {
 namespace
 {
+// Hessian entries are written once and never re-read by this library: streaming stores (EXO_HESS_PLAIN_STORES restores plain ones)
+#ifndef EXO_HESS_PLAIN_STORES
+#define HST(ptr, v) __stcs((ptr), (v))
+#else
+#define HST(ptr, v) (*(ptr) = (v))
+#endif
 __global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant__ HessParams P)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant_
                     for (int i = 0; i < N; ++i)
                     {
                         const double a = outer ? row[i * P.mj_sc] : 0.0;
-                        for (int j = 0; j < N; ++j) hm[r * P.h_sr + i * P.h_si + j * P.h_sj] = outer ? a * row[j * P.mj_sc] : 0.0;
+                        for (int j = 0; j < N; ++j) HST(&hm[r * P.h_sr + i * P.h_si + j * P.h_sj], outer ? a * row[j * P.mj_sc] : 0.0);
                     }
                 }
                 continue;
@@ -451,27 +457,27 @@ __global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant_
                         switch (m.kind)
                         {
                             case EXO_MAP_EFF_FRAME:
-                                hij[0] = l0; hij[P.h_sr] = l1; hij[2 * P.h_sr] = l2;
-                                hji[0] = l0; hji[P.h_sr] = l1; hji[2 * P.h_sr] = l2;
-                                hij[3 * P.h_sr] = 0.0; hij[4 * P.h_sr] = 0.0; hij[5 * P.h_sr] = 0.0;
+                                HST(&hij[0], l0); HST(&hij[P.h_sr], l1); HST(&hij[2 * P.h_sr], l2);
+                                HST(&hji[0], l0); HST(&hji[P.h_sr], l1); HST(&hji[2 * P.h_sr], l2);
+                                HST(&hij[3 * P.h_sr], 0.0); HST(&hij[4 * P.h_sr], 0.0); HST(&hij[5 * P.h_sr], 0.0);
                                 if (!diag)
                                 {
-                                    hji[3 * P.h_sr] = a0; hji[4 * P.h_sr] = a1; hji[5 * P.h_sr] = a2;
+                                    HST(&hji[3 * P.h_sr], a0); HST(&hji[4 * P.h_sr], a1); HST(&hji[5 * P.h_sr], a2);
                                 }
                                 break;
                             case EXO_MAP_EFF_POSITION:
-                                hij[0] = l0; hij[P.h_sr] = l1; hij[2 * P.h_sr] = l2;
-                                hji[0] = l0; hji[P.h_sr] = l1; hji[2 * P.h_sr] = l2;
+                                HST(&hij[0], l0); HST(&hij[P.h_sr], l1); HST(&hij[2 * P.h_sr], l2);
+                                HST(&hji[0], l0); HST(&hji[P.h_sr], l1); HST(&hji[2 * P.h_sr], l2);
                                 break;
                             case EXO_MAP_EFF_POSITION_XY:
-                                hij[0] = l0; hij[P.h_sr] = l1;
-                                hji[0] = l0; hji[P.h_sr] = l1;
+                                HST(&hij[0], l0); HST(&hij[P.h_sr], l1);
+                                HST(&hji[0], l0); HST(&hji[P.h_sr], l1);
                                 break;
                             case EXO_MAP_EFF_ORIENTATION:
-                                hij[0] = 0.0; hij[P.h_sr] = 0.0; hij[2 * P.h_sr] = 0.0;
+                                HST(&hij[0], 0.0); HST(&hij[P.h_sr], 0.0); HST(&hij[2 * P.h_sr], 0.0);
                                 if (!diag)
                                 {
-                                    hji[0] = a0; hji[P.h_sr] = a1; hji[2 * P.h_sr] = a2;
+                                    HST(&hji[0], a0); HST(&hji[P.h_sr], a1); HST(&hji[2 * P.h_sr], a2);
                                 }
                                 break;
                             default:  // EXO_MAP_DISTANCE (distance.cpp:76-90)
@@ -479,8 +485,8 @@ __global__ void __launch_bounds__(128) exo_hessian_kernel(const __grid_constant_
                                 const double ni = px * vix + py * viy + pz * viz, nj = px * vjx + py * vjy + pz * vjz;
                                 const double part1 = -(ni * nj) / (px * px + py * py + pz * pz);  // pow(., 3 / 2) with integer 3 / 2 == 1
                                 const double part2 = ((px * l0 + py * l1 + pz * l2) + (vix * vjx + viy * vjy + viz * vjz)) / nrm;
-                                hij[0] = part1 + part2;
-                                hji[0] = part1 + part2;
+                                HST(&hij[0], part1 + part2);
+                                HST(&hji[0], part1 + part2);
                                 break;
                             }
                         }
