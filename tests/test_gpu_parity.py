@@ -581,6 +581,49 @@ def test_aico_task_messages(oracle_lib, layout):
         assert not R[b, 5, :, :].any() or rho[5, 0] > 0  # timestep 5: JointLimit skipped (negative rho), EffFrame rho 0
 
 
+def test_cost_gradient_and_aico_messages_on_a_tree_robot(oracle_lib):
+    # 38 controlled joints: the general (any N) instantiations of the cost-gradient and AICO kernels, and the three-kernel path of
+    # exo_problem_cost_gradient_batch (tree programs have no fused kernel)
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "leftPalm"}, {"Link": "rightFoot", "LinkOffset": [0.0, 0.0, -0.05]}]},
+            {"type": "JointLimit", "SafePercentage": 0.1},
+            {"type": "EffPosition", "EndEffector": [{"Link": "torso"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    N = orc.n
+    B, T = 3, 6
+    rng = np.random.default_rng(71)
+    lo, hi = np.maximum(orc.lower, -1.0), np.minimum(orc.upper, 1.0)
+    X = np.clip(rng.uniform(lo, hi, size=(B, 1, N)) + np.cumsum(rng.normal(0, 0.03, size=(B, T, N)), axis=1), lo - 0.05, hi + 0.05)
+    rho = np.ones((T, 3)) * [5.0, 100.0, 2.0]
+    goal = orc.zero_goal()
+    goal[:3] = [0.3, 0.4, 0.2]
+    W = np.linspace(1.0, 3.0, N)
+    ct = 1.0 / 0.1 / T
+    prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
+    E = B * T
+    cost, grad = _gpu_cost_gradient_fused(prob, X.reshape(E, N), B, T)
+    assert prob.last_kernel() == "exo_cost_gradient_kernel"
+    grad = grad.reshape(B, T, N)
+    LP, LJ = prob.length_phi, prob.length_jacobian
+    dx, dphi, djac, dR, dr, drh, dc = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N * N, E * N, E, E))
+    dx.upload(X.reshape(E, N).T)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T)
+    prob.aico_task_messages_device(dx.ptr, dphi.ptr, djac.ptr, B, dR.ptr, dr.ptr, drh.ptr, dc.ptr)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    R = dR.download((N, N, E)).transpose(2, 0, 1).reshape(B, T, N, N)
+    r = dr.download((N, E)).T.reshape(B, T, N)
+    rhat = drh.download((E,)).reshape(B, T)
+    for b in range(B):
+        gref = orc.trajectory_cost_jacobian(X[b], rho, goal=goal, ct=ct, W=W)
+        cref = orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)[0]
+        assert np.max(np.abs(grad[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+        assert abs(cost[b] - cref) <= 1e-10 * max(1.0, cref)
+        R_ref, r_ref, rhat_ref, _ = orc.aico_task_messages(X[b], rho, goal=goal, ct=ct)
+        for got, ref in ((R[b], R_ref), (r[b], r_ref), (rhat[b], rhat_ref)):
+            assert np.max(np.abs(got - ref)) <= 1e-10 * max(1.0, np.abs(ref).max())
+
+
 def test_end_pose_cost_jacobian_and_finite_differences(oracle_lib):
     # UnconstrainedEndPoseProblem::GetScalarJacobian = 2 J^T S ydiff; for position-type maps it is the exact gradient of the cost
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
