@@ -285,6 +285,49 @@ def test_mimic_and_uncontrolled_joints(oracle_lib):
     assert prob.program_info()["joint_ops"] == 6
 
 
+def test_prismatic_joints(oracle_lib, monkeypatch):
+    # no fixture robot has a sliding joint: turn two LWR joints (and the test robot's middle joint) into prismatic ones.  Covers the
+    # not-all-revolute instantiations of the chain kernels (update, fused cost / gradient, IK line search) and the interpreter's
+    # prismatic branch, including Jacobian columns (w = 0, v = axis) and the Hessian of a mixed chain.
+    from oracle import robot_model
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    for name in ("lwr_arm_3_link", "lwr_arm_6_link"):
+        tree.elements[tree.link_index[name]].joint_type = robot_model.TRANS_AXIS
+    tree.lower = np.where(np.isin(np.arange(7), (2, 5)), -0.2, tree.lower)
+    tree.upper = np.where(np.isin(np.arange(7), (2, 5)), 0.2, tree.upper)
+    orc = oracle_lib.Oracle(tree)
+    maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link", "LinkOffset": [0.0, 0.05, 0.1]}]},
+            {"type": "JointLimit", "SafePercentage": 0.1},
+            {"type": "Distance", "EndEffector": [{"Link": "lwr_arm_7_link", "BaseOffset": [0.3, 0.2, 0.4]}]}]
+    X = random_states(orc, 500, seed=81)
+    prob, phi, jac = _check(orc, maps, X)
+    assert "exo_chain_kernel" in prob.kernels_used and prob.chain_info()["all_revolute"] is False
+    assert not jac[:, 3:6, 2].any() and not jac[:, 3:6, 5].any()  # a sliding joint does not rotate the end-effector
+    # fused cost + gradient against the oracle on the same mixed chain
+    maps2 = maps[:2]
+    orc.set_problem(maps2)
+    tree2, prob2 = gpu_problem_from_maps(orc, maps2)
+    B, T = 6, 9
+    Xt = np.clip(random_states(orc, B, seed=82)[:, None, :] + np.cumsum(np.random.default_rng(83).normal(0, 0.03, size=(B, T, 7)), axis=1), orc.lower, orc.upper)
+    rho = np.ones((T, 2)) * [4.0, 30.0]
+    goal = orc.zero_goal()
+    goal[:7] = [0.3, 0.1, 0.7, 0.0, 0.0, 0.0, 1.0]
+    W = np.linspace(1.0, 2.0, 7)
+    prob2.set_cost(rho, T=T, goal=goal, ct=0.5, W=W)
+    cost, grad = _gpu_cost_gradient_fused(prob2, Xt.reshape(B * T, 7), B, T)
+    assert prob2.last_kernel() == "exo_chain_costgrad_kernel"
+    for b in range(B):
+        gref = orc.trajectory_cost_jacobian(Xt[b], rho, goal=goal, ct=0.5, W=W)
+        assert np.max(np.abs(grad.reshape(B, T, 7)[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+        assert abs(cost[b] - orc.trajectory_cost(Xt[b], rho, goal=goal, ct=0.5, W=W)[0]) <= 1e-10 * max(1.0, cost[b])
+    # Hessians of the mixed chain
+    orc.set_problem(maps[:1])
+    tree3, prob3 = gpu_problem_from_maps(orc, maps[:1])
+    Hs = _gpu_hessian(prob3, X[:40])
+    for e in range(40):
+        assert np.max(np.abs(Hs[e] - orc.problem_hessian(X[e]))) <= 1e-10
+
+
 def test_host_pipeline_matches_device_path(oracle_lib):
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
     maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
