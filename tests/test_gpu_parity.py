@@ -285,6 +285,26 @@ def test_mimic_and_uncontrolled_joints(oracle_lib):
     assert prob.program_info()["joint_ops"] == 6
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7])
+def test_chain_kernels_of_every_length(oracle_lib, k):
+    # a frame on link k of the LWR makes a chain of k joints: every NJ instantiation of the chain kernel and of the fused
+    # cost-gradient kernel (the columns of the joints above link k are structural zeros)
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "ZYX", "EndEffector": [{"Link": "lwr_arm_%d_link" % k, "LinkOffset": [0.02, 0.0, 0.05]}]}]
+    X = random_states(orc, 257, seed=90 + k)
+    prob, phi, jac = _check(orc, maps, X)
+    assert prob.chain_info()["joints"] == k and not jac[:, :, k:].any()
+    rho, goal = [3.0], np.array([0.2, 0.1, 0.5, 0.1, -0.2, 0.3])
+    prob.set_kernel(0)
+    prob.set_cost(rho, T=1, goal=goal)
+    cost, grad = _gpu_cost_gradient_fused(prob, X, 257, 1)
+    assert prob.last_kernel() == "exo_chain_costgrad_kernel"
+    for e in range(0, 257, 16):
+        gref = orc.trajectory_cost_jacobian(X[e:e + 1], rho, goal=goal)[0]
+        assert np.max(np.abs(grad[e] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+        assert abs(cost[e] - orc.trajectory_cost(X[e:e + 1], rho, goal=goal)[0]) <= 1e-10 * max(1.0, cost[e])
+
+
 def test_prismatic_joints(oracle_lib, monkeypatch):
     # no fixture robot has a sliding joint: turn two LWR joints (and the test robot's middle joint) into prismatic ones.  Covers the
     # not-all-revolute instantiations of the chain kernels (update, fused cost / gradient, IK line search) and the interpreter's
