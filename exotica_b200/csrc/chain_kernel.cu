@@ -72,6 +72,16 @@ __device__ __forceinline__ void st(char* p, double v)
 #endif
 }
 
+// sin / cos of (theta0 + qm) for |angle| > 1e5 rad: adding the constant first would round it away at that magnitude (ulp(1e9) =
+// 1.2e-7), so the two angles are combined after the (Payne-Hanek) sincos of the state-dependent part
+__device__ __forceinline__ void big_sincos(double qm, double c0, double s0, double& sn, double& cs)
+{
+    double sq, cq;
+    sincos(qm, &sq, &cq);
+    sn = fma(sq, c0, cq * s0);
+    cs = fma(cq, c0, -(sq * s0));
+}
+
 // Rx(alpha_J) * Tx(a_J) applied on the right of cur (joint 0: already part of the base frame).
 // ORTHO: every link of the chain has alpha = +-90 degrees and a = 0 (consecutive axes perpendicular and intersecting: the LWR,
 // most 7-DoF arms) -- the rotation is a signed swap of the y and z columns, 6 multiplications instead of 15 FP64 operations.
@@ -316,7 +326,7 @@ __device__ __noinline__ void chain_slow_eval(const ChainParams& P, const char* x
         if (jp.prismatic)
             d = fma(jp.qmult, xq, d);
         else
-            sincos(fma(jp.qmult, xq, jp.th0), &sn, &cs);
+            big_sincos(jp.qmult * xq, jp.c0, jp.s0, sn, cs);
         Fr r = fr_identity();
         r.m0 = cs; r.m1 = -sn; r.m3 = sn; r.m4 = cs;
         r.z = d;
@@ -692,7 +702,7 @@ __global__ void __maxnreg__(EXO_COSTGRAD_MAXNREG) exo_chain_costgrad_kernel(cons
                 if (fabs(th) <= 1.0e5)
                     fast_sincos(th, sn[j], cs[j]);
                 else
-                    sincos(th, &sn[j], &cs[j]);
+                    big_sincos(P.joint[j].qmult * q[j], P.joint[j].c0, P.joint[j].s0, sn[j], cs[j]);
             }
         }
         Fr cur = load_frame(P.base);
@@ -783,7 +793,7 @@ __device__ __forceinline__ double chain_cost_only(const ChainParams& P, const Ch
             if (fabs(th) <= 1.0e5)
                 fast_sincos(th, sn[j], cs[j]);
             else
-                sincos(th, &sn[j], &cs[j]);
+                big_sincos(P.joint[j].qmult * q[j], P.joint[j].c0, P.joint[j].s0, sn[j], cs[j]);
         }
     }
     Fr cur = load_frame(P.base);
@@ -926,7 +936,7 @@ __device__ __forceinline__ void chain_eval_one(const ChainParams& P, const char*
             if (fabs(th) <= 1.0e5)
                 fast_sincos(th, sn[j], cs[j]);
             else
-                sincos(th, &sn[j], &cs[j]);
+                big_sincos(P.joint[j].qmult * q[j], P.joint[j].c0, P.joint[j].s0, sn[j], cs[j]);
         }
     }
     Fr cur = load_frame(P.base);

@@ -305,6 +305,26 @@ def test_chain_kernels_of_every_length(oracle_lib, k):
         assert abs(cost[e] - orc.trajectory_cost(X[e:e + 1], rho, goal=goal)[0]) <= 1e-10 * max(1.0, cost[e])
 
 
+def test_joint_angles_far_outside_the_fast_trig_range(oracle_lib):
+    # |theta| > 1e5 rad leaves the Cody-Waite reduction of the kernels' own sincos: the chain kernel takes its cold path through
+    # CUDA's sincos (Payne-Hanek), the interpreter and the fused kernels branch per joint.  Mixed batch: every 7th state is huge.
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
+    X = random_states(orc, 700, seed=95)
+    X[::7] += np.random.default_rng(96).choice([-1.0, 1.0], size=X[::7].shape) * 10.0 ** np.random.default_rng(97).uniform(5.2, 9.0, size=X[::7].shape)
+    # sin / cos of a 1e9 argument amplify the last bit of q: absolute parity holds because both sides see the same doubles
+    prob, phi, jac = _check(orc, maps, X, tol=1e-9)
+    orc.set_problem(maps)
+    rho, goal = [2.0, 0.0], orc.zero_goal()
+    prob.set_kernel(0)
+    prob.set_cost(rho, T=1, goal=goal)
+    cost, grad = _gpu_cost_gradient_fused(prob, X, 700, 1)
+    assert prob.last_kernel() == "exo_chain_costgrad_kernel"
+    for e in range(0, 700, 7):
+        gref = orc.trajectory_cost_jacobian(X[e:e + 1], rho, goal=goal)[0]
+        assert np.max(np.abs(grad[e] - gref)) <= 1e-8 * max(1.0, np.abs(gref).max())
+
+
 def test_prismatic_joints(oracle_lib, monkeypatch):
     # no fixture robot has a sliding joint: turn two LWR joints (and the test robot's middle joint) into prismatic ones.  Covers the
     # not-all-revolute instantiations of the chain kernels (update, fused cost / gradient, IK line search) and the interpreter's
