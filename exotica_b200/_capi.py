@@ -101,7 +101,30 @@ SYMBOLS = [
     ("exo_problem_hessian_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_trajectory_reduce", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_last_kernel", ctypes.c_char_p, [_vp]),
+    ("exo_event_create", ctypes.c_int, [ctypes.POINTER(_vp)]),
+    ("exo_event_destroy", ctypes.c_int, [_vp]),
+    ("exo_event_record", ctypes.c_int, [_vp, _vp]),
+    ("exo_event_synchronize", ctypes.c_int, [_vp]),
+    ("exo_event_elapsed_ms", ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    ("exo_graph_begin_capture", ctypes.c_int, [_vp]),
+    ("exo_graph_end_capture", ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    ("exo_graph_launch", ctypes.c_int, [_vp, _vp]),
+    ("exo_graph_destroy", ctypes.c_int, [_vp]),
+    ("exo_comm_nccl_version", ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    ("exo_comm_get_unique_id", ctypes.c_int, [ctypes.c_char_p]),
+    ("exo_comm_create", ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    ("exo_comm_destroy", ctypes.c_int, [_vp]),
+    ("exo_comm_rank", ctypes.c_int, [_vp]),
+    ("exo_comm_world_size", ctypes.c_int, [_vp]),
+    ("exo_comm_collective_count", ctypes.c_int64, [_vp]),
+    ("exo_comm_allgather", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
+    ("exo_comm_allreduce", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
+    ("exo_comm_barrier", ctypes.c_int, [_vp, _vp]),
+    ("exo_problem_cost_allgather", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
+    ("exo_min_distance_allgather", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _vp, _vp, _vp]),
 ]
+COMM_ID_BYTES = 128
+REDUCE_MIN, REDUCE_SUM, REDUCE_MAX = 0, 1, 2
 
 _LIB = None
 
@@ -131,6 +154,20 @@ def _d(a):
 
 def _i(a):
     return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def checked_output(arr, shape, name):
+    """A caller-supplied output array goes to C as a bare pointer: it must be float64, C-contiguous, writeable and of the exact
+    shape, or the library would scribble over foreign memory / write through a temporary copy."""
+    if not isinstance(arr, np.ndarray):
+        raise ExoticaError("%s must be a numpy array" % name)
+    if arr.dtype != np.float64:
+        raise ExoticaError("%s must be float64, got %s" % (name, arr.dtype))
+    if tuple(arr.shape) != tuple(int(v) for v in shape):
+        raise ExoticaError("%s has shape %s, expected %s" % (name, tuple(arr.shape), tuple(shape)))
+    if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
+        raise ExoticaError("%s must be C-contiguous and writeable" % name)
+    return arr
 
 
 def device_count():
@@ -174,6 +211,153 @@ class DeviceBuffer(object):
             self.free()
         except Exception:
             pass
+
+
+class Stream(object):
+    """A non-blocking CUDA stream (exo_stream_create)."""
+
+    def __init__(self):
+        p = _vp()
+        check(lib().exo_stream_create(ctypes.byref(p)))
+        self.ptr = _vp(p.value)
+
+    def synchronize(self):
+        check(lib().exo_stream_synchronize(self.ptr))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().exo_stream_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Event(object):
+    """A CUDA event for device-side timing on the launching stream."""
+
+    def __init__(self):
+        p = _vp()
+        check(lib().exo_event_create(ctypes.byref(p)))
+        self.ptr = _vp(p.value)
+
+    def record(self, stream=None):
+        check(lib().exo_event_record(self.ptr, stream.ptr if isinstance(stream, Stream) else stream))
+
+    def synchronize(self):
+        check(lib().exo_event_synchronize(self.ptr))
+
+    def elapsed_ms(self, later):
+        ms = ctypes.c_float(0)
+        check(lib().exo_event_elapsed_ms(self.ptr, later.ptr, ctypes.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().exo_event_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Graph(object):
+    """Stream capture into a CUDA graph: `with Graph.capture(stream) as g: ...calls on stream...`, then g.launch(stream)."""
+
+    def __init__(self):
+        self.ptr = None
+        self._stream = None
+
+    @classmethod
+    def capture(cls, stream):
+        g = cls()
+        g._stream = stream
+        return g
+
+    def __enter__(self):
+        check(lib().exo_graph_begin_capture(self._stream.ptr))
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        p = _vp()
+        rc = lib().exo_graph_end_capture(self._stream.ptr, ctypes.byref(p))
+        if exc_type is None:
+            check(rc)
+            self.ptr = _vp(p.value)
+        return False
+
+    def launch(self, stream):
+        check(lib().exo_graph_launch(self.ptr, stream.ptr if isinstance(stream, Stream) else stream))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().exo_graph_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Comm(object):
+    """exo_comm: NCCL communicator of this process' GPU (one process per GPU).  `unique_id`: the 128 bytes rank 0 obtained from
+    Comm.unique_id(), shipped to every rank by the launcher (exotica_b200.distributed.init_from_env does it for torchrun-style
+    environments)."""
+
+    def __init__(self, rank, world, unique_id=None):
+        if world > 1 and (unique_id is None or len(unique_id) != COMM_ID_BYTES):
+            raise ExoticaError("a %d-rank communicator needs the %d-byte unique id of rank 0" % (world, COMM_ID_BYTES))
+        h = _vp()
+        check(lib().exo_comm_create(int(rank), int(world), bytes(unique_id) if unique_id is not None else None, ctypes.byref(h)))
+        self.h = _vp(h.value)
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        check(lib().exo_comm_get_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def nccl_version():
+        v = ctypes.c_int(0)
+        check(lib().exo_comm_nccl_version(ctypes.byref(v)))
+        return v.value
+
+    def allgather(self, d_send, d_recv, count_per_rank, stream=None):
+        check(lib().exo_comm_allgather(self.h, d_send, d_recv, int(count_per_rank), _sptr(stream)))
+
+    def allreduce(self, d_send, d_recv, count, op, stream=None):
+        check(lib().exo_comm_allreduce(self.h, d_send, d_recv, int(count), int(op), _sptr(stream)))
+
+    def barrier(self, stream=None):
+        check(lib().exo_comm_barrier(self.h, _sptr(stream)))
+
+    def collective_count(self):
+        return int(lib().exo_comm_collective_count(self.h))
+
+    def cost_allgather(self, problem, d_x, n_traj_local, n_traj_per_rank, d_cost_all, layout=LAYOUT_SOA, stream=None):
+        """problem: a _capi.Problem or raw exo_problem handle."""
+        h = problem.h if hasattr(problem, "h") else problem
+        check(lib().exo_problem_cost_allgather(h, self.h, d_x, int(n_traj_local), int(n_traj_per_rank), int(layout), d_cost_all, _sptr(stream)))
+
+    def min_distance_allgather(self, d_min_eval, n_traj_local, T, n_traj_per_rank, d_min_traj_all=None, d_min_global=None, stream=None):
+        check(lib().exo_min_distance_allgather(self.h, d_min_eval, int(n_traj_local), int(T), int(n_traj_per_rank), d_min_traj_all, d_min_global,
+                                               _sptr(stream)))
+
+    def destroy(self):
+        if self.h:
+            lib().exo_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _sptr(stream):
+    return stream.ptr if isinstance(stream, Stream) else stream
 
 
 class PinnedArray(object):
@@ -363,12 +547,23 @@ class Problem(object):
         check(lib().exo_problem_set_cost(self.h, ctypes.byref(d)))
         self.cost_T = int(T)
 
+    def _check_trajectories(self, X):
+        T = getattr(self, "cost_T", None)
+        if T is None:
+            raise ExoticaError("exo_problem_set_cost has not been called")
+        want = (T, self.n) if T > 1 else (self.n,)
+        if X.ndim == 3 and T == 1 and X.shape[1:] == (1, self.n):
+            return
+        if X.ndim != len(want) + 1 or tuple(X.shape[1:]) != want:
+            raise ExoticaError("Wrong state vector size! Got %s expected (B, %s)" % (X.shape, ", ".join(str(v) for v in want)))
+
     def cost_batch_device(self, d_x, d_phi, n_traj, d_cost_traj=None, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_batch(self.h, d_x, d_phi, int(n_traj), int(layout), d_cost_traj, d_cost_eval, stream))
 
     def cost_batch_host(self, X):
         """X[B][T][N] (or [B][N] for end-pose problems) -> cost[B] through the host pipeline."""
         X = np.ascontiguousarray(X, dtype=np.float64)
+        self._check_trajectories(X)
         B = X.shape[0]
         out = np.empty(B)
         check(lib().exo_problem_cost_batch_host(self.h, X.ctypes.data, B, LAYOUT_AOS_ROWMAJOR, out.ctypes.data))
@@ -387,6 +582,7 @@ class Problem(object):
         """X[B][T][N] (or [B][N] for end-pose problems) -> (cost[B] or None, grad like X) through the host pipeline; Phi and J
         stay on the device."""
         X = np.ascontiguousarray(X, dtype=np.float64)
+        self._check_trajectories(X)
         B = X.shape[0]
         cost = np.empty(B) if with_cost else None
         grad = np.empty_like(X)
@@ -446,10 +642,10 @@ class Problem(object):
             E = X.shape[0]
             pshape = (E, LP)
             jshape = (E, LJ, N) if layout == LAYOUT_AOS_ROWMAJOR else (E, N, LJ)
-        phi = out_phi if out_phi is not None else np.empty(pshape, dtype=np.float64)
+        phi = checked_output(out_phi, pshape, "out_phi") if out_phi is not None else np.empty(pshape, dtype=np.float64)
         jac = None
         if want_jacobian:
-            jac = out_jac if out_jac is not None else np.empty(jshape, dtype=np.float64)
+            jac = checked_output(out_jac, jshape, "out_jac") if out_jac is not None else np.empty(jshape, dtype=np.float64)
         check(lib().exo_problem_update_batch_host(self.h, X.ctypes.data, E, int(T), int(layout), phi.ctypes.data,
                                                   jac.ctypes.data if jac is not None else None))
         return phi, jac

@@ -1,5 +1,6 @@
 // capi.cu -- implementation of the C-ABI declared in include/exotica_b200.h.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -461,6 +462,10 @@ static int compile_and_upload(exo_problem* p)
         CUDA_TRY(cudaMalloc((void**)&p->d_image, p->prog.image.size()));
         p->d_image_bytes = p->prog.image.size();
     }
+    // Kernels of earlier launches may still be staging / reading the old image on non-blocking streams (the library's own
+    // pipeline streams, exo_stream_create): a legacy-stream cudaMemcpy does not order against those.  Recompiles are rare
+    // (model state / joint limits changed), so drain the device before overwriting.
+    CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(p->d_image, p->prog.image.data(), p->prog.image.size(), cudaMemcpyHostToDevice));
     p->chain_ok = chain_lower(p->prog, p->chain);
     p->plan_valid = false;
@@ -594,8 +599,10 @@ static int64_t sph_dump_cap_bytes()
     return (int64_t)(mib > 0 ? mib : 1024) << 20;
 }
 
+// e_offset: index of this launch's first evaluation in the caller's batch (the host pipeline launches chunk by chunk; per-evaluation
+// side outputs such as the minimum sphere distance are indexed by the caller's evaluation number)
 static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E, int32_t T, int32_t layout, double* d_phi, double* d_jac,
-                  cudaStream_t stream, bool timed)
+                  cudaStream_t stream, bool timed, int64_t e_offset = 0)
 {
     if (p->compiled_version != p->tree->version)
     {
@@ -617,7 +624,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     k.phi = d_phi;
     k.jac = d_jac;
     k.generated = p->d_generated;
-    k.min_dist = p->d_min_dist;
+    k.min_dist = p->d_min_dist ? p->d_min_dist + e_offset : nullptr;
     k.n_evals = E;
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
@@ -831,7 +838,7 @@ int exo_problem_update_batch_host(exo_problem* p, const double* h_x, int64_t E, 
         }
         else
             CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + e0 * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        rc = launch(p, p->d_x[b], n, n, T, layout, p->d_phi[b], h_jac ? p->d_jac[b] : nullptr, s, false);
+        rc = launch(p, p->d_x[b], n, n, T, layout, p->d_phi[b], h_jac ? p->d_jac[b] : nullptr, s, false, e0);
         if (rc != EXO_OK) return rc;
         if (layout == EXO_LAYOUT_SOA)
         {
@@ -1175,6 +1182,62 @@ int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t
     cudaError_t e = launch_reduce(d_in, n_traj, T, t_first, op, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
     return EXO_OK;
+}
+
+// ---- kernel + collective in one call (row e) ---------------------------------------------------------------------------------
+int exo_problem_cost_allgather(exo_problem* p, exo_comm* comm, const double* d_x, int64_t n_traj_local, int64_t n_traj_per_rank, int32_t layout,
+                               double* d_cost_all, void* stream)
+{
+    if (!p || !comm) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (n_traj_local < 0 || n_traj_per_rank < n_traj_local) return fail(EXO_ERR_INVALID, "a rank holds at most n_traj_per_rank trajectories");
+    if (n_traj_per_rank == 0) return EXO_OK;
+    if (!d_cost_all) return fail(EXO_ERR_INVALID, "NULL buffer");
+    double* mine = d_cost_all + (int64_t)exo_comm_rank(comm) * n_traj_per_rank;
+    if (n_traj_local > 0)
+    {
+        int rc = exo_problem_cost_gradient_batch(p, d_x, n_traj_local, layout, mine, nullptr, stream);
+        if (rc != EXO_OK) return rc;
+    }
+    if (n_traj_local < n_traj_per_rank)
+        CUDA_TRY(cudaMemsetAsync(mine + n_traj_local, 0, (size_t)(n_traj_per_rank - n_traj_local) * sizeof(double), (cudaStream_t)stream));
+    return exo_comm_allgather(comm, mine, d_cost_all, n_traj_per_rank, stream);
+}
+
+int exo_min_distance_allgather(exo_comm* comm, const double* d_min_eval, int64_t n_traj_local, int32_t T, int64_t n_traj_per_rank, double* d_min_traj_all,
+                               double* d_min_global, void* stream)
+{
+    if (!comm) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (T < 1 || n_traj_local < 0 || n_traj_per_rank < n_traj_local) return fail(EXO_ERR_INVALID, "a rank holds at most n_traj_per_rank trajectories of T >= 1 timesteps");
+    if (!d_min_traj_all && !d_min_global) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (n_traj_local > 0 && !d_min_eval) return fail(EXO_ERR_INVALID, "NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (d_min_traj_all && n_traj_per_rank > 0)
+    {
+        double* mine = d_min_traj_all + (int64_t)exo_comm_rank(comm) * n_traj_per_rank;
+        e = launch_reduce(d_min_eval, n_traj_local, T, 0, EXO_REDUCE_MIN, mine, s);
+        if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+        e = launch_fill(mine + n_traj_local, n_traj_per_rank - n_traj_local, (double)INFINITY, s);
+        if (e != cudaSuccess) return cuda_fail(e, "fill kernel launch");
+        int rc = exo_comm_allgather(comm, mine, d_min_traj_all, n_traj_per_rank, stream);
+        if (rc != EXO_OK) return rc;
+        if (d_min_global)
+        {
+            // every rank holds every trajectory's minimum now: the global one is a local reduction, no second collective
+            e = launch_reduce(d_min_traj_all, 1, (int)std::min<int64_t>((int64_t)exo_comm_world_size(comm) * n_traj_per_rank, INT32_MAX), 0, EXO_REDUCE_MIN,
+                              d_min_global, s);
+            if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+        }
+        return EXO_OK;
+    }
+    // global minimum only: local min over all evaluations, then all-reduce(min) of one double
+    if (n_traj_local * (int64_t)T > INT32_MAX) return fail(EXO_ERR_UNSUPPORTED, "more than 2^31 evaluations per rank");
+    if (n_traj_local > 0)
+        e = launch_reduce(d_min_eval, 1, (int)(n_traj_local * T), 0, EXO_REDUCE_MIN, d_min_global, s);
+    else
+        e = launch_fill(d_min_global, 1, (double)INFINITY, s);
+    if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+    return exo_comm_allreduce(comm, d_min_global, d_min_global, 1, EXO_REDUCE_MIN, stream);
 }
 
 namespace

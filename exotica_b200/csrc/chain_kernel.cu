@@ -12,9 +12,10 @@
 // and its origin lies on the axis, which is all a Jacobian column needs (KinematicTree::ComputeJ,
 // exotica_core/src/kinematic_tree.cpp:919-945).
 //
-// One lane = one evaluation; the kernel is persistent (grid = SMs x resident CTAs) and prefetches the next evaluation's
-// joint values while it works on the current one, so the only exposed memory operations are coalesced 8-byte stores of
-// Phi and J.  sin/cos use a Cody-Waite reduction and fdlibm's minimax kernels with their coefficients in __constant__
+// One lane = one evaluation, one 64-thread CTA per 64 evaluations (the hardware CTA scheduler balances the two dies better
+// than a persistent grid with a static split, tools/hbm_probe.cu); every CTA pulls the joint values of a CTA 3/4 of a
+// resident generation behind it into L2 (prefetch.global.L2), so the only exposed memory operations are coalesced
+// streaming stores of Phi and J.  sin/cos use a Cody-Waite reduction and fdlibm's minimax kernels with their coefficients in __constant__
 // memory (CUDA's sincos spends most of its instructions materialising 64-bit immediates and on int<->double
 // conversions).  HBM-bound FP64 streaming work: no tensor cores.
 //

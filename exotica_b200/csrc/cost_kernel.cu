@@ -256,7 +256,20 @@ __global__ void __launch_bounds__(128) exo_reduce_kernel(const double* __restric
         if (lane == 0) out[b] = acc;
     }
 }
+__global__ void __launch_bounds__(128) exo_fill_kernel(double* __restrict__ out, int64_t n, double value)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = value;
+}
 }  // namespace
+
+cudaError_t launch_fill(double* out, int64_t n, double value, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int64_t blocks = (n + 127) / 128;
+    exo_fill_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 128, 0, stream>>>(out, n, value);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_cost(const CostParams& P, cudaStream_t stream)
 {

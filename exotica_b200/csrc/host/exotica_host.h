@@ -272,6 +272,9 @@ public:
     int GetElementIndex(const std::string& link_name) const;  // tree_map_ lookup, -1 if missing
     int ResolveFrame(const std::string& link_name, const char* what) const;
     exo_tree* GetBackend();  // builds / rebuilds the C-ABI tree when the structure changed
+    // Bumped whenever the C-ABI tree is destroyed (scene objects / trajectories added, tree rebuilt): every exo_problem built on
+    // the old tree is stale and its owner (PlanningProblem, TaskMap, the frames problem here) rebuilds it on the next call.
+    uint64_t GetBackendGeneration() const { return backend_generation_; }
 
 private:
     void BuildTree();
@@ -297,7 +300,10 @@ private:
     std::vector<std::uniform_real_distribution<double>> random_state_distributions_;
 
     exo_tree* backend_ = nullptr;
+    uint64_t backend_generation_ = 0;
     exo_problem* frames_problem_ = nullptr;  // EXO_MAP_FRAMES problem behind RequestFrames/Update
+    bool frames_requested_ = false;
+    void EnsureFramesProblem();              // (re)builds frames_problem_ from request_ after the tree changed
     KinematicsRequest request_;
     std::shared_ptr<KinematicResponse> solution_;
 };
@@ -395,6 +401,10 @@ private:
     std::map<int, std::vector<Frame>> trajectories_;  // generated slot -> frames per timestep
     std::map<std::string, std::pair<int, std::shared_ptr<Trajectory>>> trajectory_generators_;  // link -> (slot, trajectory)
     mutable std::vector<double> generated_table_;
+    uint64_t trajectory_version_ = 0;  // bumped by AddTrajectory / AddTrajectoryFrames (problems re-push their frame tables)
+
+public:
+    uint64_t GetTrajectoryVersion() const { return trajectory_version_; }
 };
 typedef std::shared_ptr<Scene> ScenePtr;
 
@@ -435,6 +445,7 @@ protected:
     std::vector<double> off_a_, off_b_;
     void ResolveFrames();
     exo_problem* own_problem_ = nullptr;
+    uint64_t own_problem_generation_ = 0;  // KinematicTree::GetBackendGeneration() own_problem_ was built against
     void EnsureOwnProblem();
 
 public:
@@ -680,6 +691,11 @@ public:
 protected:
     void UpdateUsage(const std::vector<std::vector<double>>& rho_per_task);  // TaskMap::is_used from rho (tasks.cpp:246-259)
     void InvalidateBackend();
+    // Called by every batched entry point after GetBackend(): state the backend needs beyond its maps (time-indexed problems
+    // push the per-timestep frames of trajectory-driven links here).
+    virtual void PrepareBackend() {}
+    uint64_t backend_generation_ = 0;  // KinematicTree::GetBackendGeneration() backend_ was built against
+    uint64_t backend_serial_ = 0;      // counts the exo_problem handles this problem has built (a new one needs every push again)
     std::string object_name_;
     ScenePtr scene_;
     std::vector<TaskMapPtr> tasks_;
@@ -727,6 +743,9 @@ private:
     int T_ = 0;
     double tau_ = 0.0;
     void PushGenerated();
+    void PrepareBackend() override { PushGenerated(); }
+    uint64_t pushed_serial_ = 0;            // backend serial / trajectory version the frame table was last pushed for
+    uint64_t pushed_version_ = ~0ull;
 };
 
 }  // namespace exotica

@@ -48,6 +48,7 @@ void KinematicTree::InvalidateBackend()
     frames_problem_ = nullptr;
     if (backend_) exo_tree_destroy(backend_);
     backend_ = nullptr;
+    ++backend_generation_;  // dependants (PlanningProblem::GetBackend, TaskMap::EnsureOwnProblem) rebuild their exo_problem
 }
 
 // kinematic_tree.cpp:101-162
@@ -530,24 +531,22 @@ exo_tree* KinematicTree::GetBackend()
     return backend_;
 }
 
-// kinematic_tree.cpp:628-676
-std::shared_ptr<KinematicResponse> KinematicTree::RequestFrames(const KinematicsRequest& request)
+void KinematicTree::EnsureFramesProblem()
 {
-    request_ = request;
-    if (request_.flags & KIN_H) ThrowPretty("KIN_H (kinematic Hessian) is outside the GPU hot path");
-    const int F = (int)request.frames.size();
+    if (frames_problem_) return;
+    if (!frames_requested_) ThrowPretty("RequestFrames must be called before Update");
+    const int F = (int)request_.frames.size();
     std::vector<int32_t> ea(F), eb(F);
     std::vector<double> oa(12 * (size_t)F), ob(12 * (size_t)F);
     for (int i = 0; i < F; ++i)
     {
-        ea[i] = ResolveFrame(request.frames[i].frame_A_link_name, "frame_A");
-        eb[i] = ResolveFrame(request.frames[i].frame_B_link_name, "frame_B");
-        memcpy(&oa[12 * i], request.frames[i].frame_A_offset.data(), 12 * sizeof(double));
-        memcpy(&ob[12 * i], request.frames[i].frame_B_offset.data(), 12 * sizeof(double));
+        ea[i] = ResolveFrame(request_.frames[i].frame_A_link_name, "frame_A");
+        eb[i] = ResolveFrame(request_.frames[i].frame_B_link_name, "frame_B");
+        memcpy(&oa[12 * i], request_.frames[i].frame_A_offset.data(), 12 * sizeof(double));
+        memcpy(&ob[12 * i], request_.frames[i].frame_B_offset.data(), 12 * sizeof(double));
     }
-    if (frames_problem_) exo_problem_destroy(frames_problem_);
-    frames_problem_ = nullptr;
-    CheckRc(exo_problem_create(GetBackend(), &frames_problem_));
+    exo_tree* tree = GetBackend();
+    CheckRc(exo_problem_create(tree, &frames_problem_));
     exo_task_map_desc d;
     memset(&d, 0, sizeof(d));
     d.kind = EXO_MAP_FRAMES;
@@ -559,6 +558,18 @@ std::shared_ptr<KinematicResponse> KinematicTree::RequestFrames(const Kinematics
     d.is_used = 1;
     CheckRc(exo_problem_add_task_map(frames_problem_, &d));
     CheckRc(exo_problem_finalize(frames_problem_));
+}
+
+// kinematic_tree.cpp:628-676
+std::shared_ptr<KinematicResponse> KinematicTree::RequestFrames(const KinematicsRequest& request)
+{
+    request_ = request;
+    if (request_.flags & KIN_H) ThrowPretty("KIN_H (kinematic Hessian) is outside the GPU hot path");
+    const int F = (int)request.frames.size();
+    frames_requested_ = true;
+    if (frames_problem_) exo_problem_destroy(frames_problem_);
+    frames_problem_ = nullptr;
+    EnsureFramesProblem();
     solution_.reset(new KinematicResponse());
     solution_->flags = request.flags;
     solution_->x.assign(num_controlled_joints_, 0.0);
@@ -569,7 +580,7 @@ std::shared_ptr<KinematicResponse> KinematicTree::RequestFrames(const Kinematics
 
 void KinematicTree::UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian)
 {
-    if (!frames_problem_) ThrowPretty("RequestFrames must be called before Update");
+    EnsureFramesProblem();
     if (num_generated_ > 0) ThrowPretty("Trajectory-driven links need a time-indexed problem (Scene::Update(x, t) per timestep)");
     CheckRc(exo_problem_update_batch_host(frames_problem_, x, n_evals, 1, layout, phi, jacobian));
 }
@@ -578,7 +589,7 @@ void KinematicTree::UpdateBatch(const double* x, int64_t n_evals, int layout, do
 void KinematicTree::Update(const std::vector<double>& x)
 {
     if ((int)x.size() != num_controlled_joints_) ThrowPretty("Wrong state vector size! Got " + std::to_string(x.size()) + " expected " + std::to_string(num_controlled_joints_));
-    if (!frames_problem_) ThrowPretty("RequestFrames must be called before Update");
+    EnsureFramesProblem();
     for (int i = 0; i < num_controlled_joints_; ++i) tree_state_[controlled_joints_[i]] = x[i];
     const int F = (int)solution_->Phi.size();
     std::vector<double> phi(12 * (size_t)F), jac;

@@ -115,6 +115,7 @@ void Scene::AddTrajectoryFrames(const std::string& link, const std::vector<Frame
     int idx = kinematica_.GetElementIndex(link);
     if (idx < 0) idx = kinematica_.AddEnvironmentElement(link, IdentityFrame(), "", true);
     trajectories_[kinematica_.MakeTrajectoryGenerated(idx)] = frames_per_timestep;
+    ++trajectory_version_;
 }
 
 void Scene::AddTrajectory(const std::string& link, const std::string& traj)
@@ -128,6 +129,7 @@ void Scene::AddTrajectory(const std::string& link, std::shared_ptr<Trajectory> t
     const int idx = kinematica_.GetElementIndex(link);
     if (idx < 0) ThrowPretty("Can't find link '" + link + "'!");
     trajectory_generators_[link] = std::make_pair(kinematica_.MakeTrajectoryGenerated(idx), traj);
+    ++trajectory_version_;
 }
 
 std::shared_ptr<Trajectory> Scene::GetTrajectory(const std::string& link) const
@@ -226,9 +228,15 @@ void TaskMap::ReleaseOwnProblem()
 
 void TaskMap::EnsureOwnProblem()
 {
+    if (!scene_) ThrowPretty("Scene is not initialised!");
+    KinematicTree& kt = scene_->GetKinematicTree();
+    // the C-ABI tree is rebuilt when scene objects / trajectories are added: a problem built on the old one is stale
+    if (own_problem_ && own_problem_generation_ != kt.GetBackendGeneration()) ReleaseOwnProblem();
     if (own_problem_) return;
     ResolveFrames();
-    CheckRc(exo_problem_create(scene_->GetKinematicTree().GetBackend(), &own_problem_));
+    exo_tree* tree = kt.GetBackend();
+    own_problem_generation_ = kt.GetBackendGeneration();
+    CheckRc(exo_problem_create(tree, &own_problem_));
     const bool used = is_used;
     is_used = true;
     try
@@ -755,6 +763,7 @@ void PlanningProblem::PushCost()
 void PlanningProblem::CostBatch(const double* x, int64_t n_trajectories, double* cost)
 {
     PushCost();
+    PrepareBackend();
     CheckRc(exo_problem_cost_batch_host(GetBackend(), x, n_trajectories, EXO_LAYOUT_AOS_ROWMAJOR, cost));
     number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
 }
@@ -762,6 +771,7 @@ void PlanningProblem::CostBatch(const double* x, int64_t n_trajectories, double*
 void PlanningProblem::CostJacobianBatch(const double* x, int64_t n_trajectories, double* cost, double* jacobian)
 {
     PushCost();
+    PrepareBackend();
     CheckRc(exo_problem_cost_jacobian_batch_host(GetBackend(), x, n_trajectories, EXO_LAYOUT_AOS_ROWMAJOR, cost, jacobian));
     number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
 }
@@ -784,6 +794,7 @@ void PlanningProblem::IkSolveBatch(const double* q0, int64_t n, const exo_ik_par
     if (GetT() != 1) ThrowPretty("This IKSolver can't solve problem of type 'exotica::TimeIndexedProblem'!");  // ik_solver.cpp:38-41
     if (n <= 0) return;
     PushCost();
+    PrepareBackend();
     // SoA on the device: transpose on the way in and out
     std::vector<double> soa((size_t)n * N);
     for (int64_t e = 0; e < n; ++e)
@@ -806,6 +817,7 @@ void PlanningProblem::HessianBatch(const double* x, int64_t n_evals, double* hes
     const int T = GetT();
     if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
     exo_problem* p = GetBackend();
+    PrepareBackend();
     const size_t n = (size_t)n_evals;
     DeviceMem dx(n * N * sizeof(double)), dphi(n * std::max(length_Phi, 1) * sizeof(double)), djac(n * std::max(length_jacobian, 1) * N * sizeof(double)),
         dh(n * std::max(length_jacobian, 1) * N * N * sizeof(double));
@@ -820,13 +832,21 @@ void PlanningProblem::CostBatchDevice(const double* d_x, const double* d_phi, in
                                       void* stream)
 {
     PushCost();
+    PrepareBackend();
     CheckRc(exo_problem_cost_batch(GetBackend(), d_x, d_phi, n_trajectories, layout, d_cost, d_cost_eval, stream));
 }
 
 exo_problem* PlanningProblem::GetBackend()
 {
+    KinematicTree& kt = scene_->GetKinematicTree();
+    // Scene::AddObject / AddTrajectory after a first Update destroy the C-ABI tree (KinematicTree::InvalidateBackend): the problem
+    // handle built on it is stale -- rebuild it (and push the cost again) instead of dereferencing a freed tree
+    if (backend_ && backend_generation_ != kt.GetBackendGeneration()) InvalidateBackend();
     if (backend_) return backend_;
-    CheckRc(exo_problem_create(scene_->GetKinematicTree().GetBackend(), &backend_));
+    exo_tree* tree = kt.GetBackend();
+    backend_generation_ = kt.GetBackendGeneration();
+    CheckRc(exo_problem_create(tree, &backend_));
+    ++backend_serial_;
     try
     {
         for (TaskMapPtr& m : tasks_)
@@ -849,6 +869,7 @@ exo_problem* PlanningProblem::GetBackend()
 void PlanningProblem::UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian)
 {
     exo_problem* p = GetBackend();
+    PrepareBackend();
     const int T = GetT();
     if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
     CheckRc(exo_problem_update_batch_host(p, x, n_evals, T, layout, phi, (flags_ & KIN_J) ? jacobian : nullptr));
@@ -858,6 +879,7 @@ void PlanningProblem::UpdateBatch(const double* x, int64_t n_evals, int layout, 
 void PlanningProblem::UpdateBatchDevice(const double* d_x, int64_t n_evals, int layout, double* d_phi, double* d_jacobian, void* stream)
 {
     exo_problem* p = GetBackend();
+    PrepareBackend();
     const int T = GetT();
     if (T > 1 && n_evals % T != 0) ThrowPretty("Batch of " + std::to_string(n_evals) + " evaluations is not a whole number of trajectories (T=" + std::to_string(T) + ")");
     CheckRc(exo_problem_update_batch(p, d_x, n_evals, T, layout, d_phi, (flags_ & KIN_J) ? d_jacobian : nullptr, stream));
@@ -950,11 +972,19 @@ void TimeIndexedProblem::Instantiate(const Initializer& init)
 void TimeIndexedProblem::PushGenerated()
 {
     int T = 0, n_gen = 0;
+    exo_problem* p = GetBackend();
+    // nothing changed since the last push to this backend (Scene::AddTrajectory* bump the version; a Trajectory object edited in
+    // place after get_trajectory() is the caller's to re-add, as Scene::AddTrajectory is the reference's only way to install one)
+    if (pushed_serial_ == backend_serial_ && pushed_version_ == scene_->GetTrajectoryVersion()) return;
     scene_->SampleTrajectories(T_, tau_);
     const std::vector<double>& table = scene_->GetGeneratedTable(T, n_gen);
-    if (n_gen == 0) return;
-    if (T != T_) ThrowPretty("Trajectory tables have " + std::to_string(T) + " timesteps, the problem has T=" + std::to_string(T_));
-    CheckRc(exo_problem_set_generated(GetBackend(), T_, n_gen, table.data()));
+    if (n_gen > 0)
+    {
+        if (T != T_) ThrowPretty("Trajectory tables have " + std::to_string(T) + " timesteps, the problem has T=" + std::to_string(T_));
+        CheckRc(exo_problem_set_generated(p, T_, n_gen, table.data()));
+    }
+    pushed_serial_ = backend_serial_;
+    pushed_version_ = scene_->GetTrajectoryVersion();
 }
 
 void TimeIndexedProblem::Update(const std::vector<double>& x_in, int t)
@@ -1002,8 +1032,6 @@ void TimeIndexedProblem::Update(const std::vector<double>& x_trajectory_in)
 
 void TimeIndexedProblem::UpdateTrajectories(const double* xin, int64_t n_trajectories, int layout, double* phi, double* jac)
 {
-    GetBackend();
-    PushGenerated();
     UpdateBatch(xin, n_trajectories * T_, layout, phi, jac);
 }
 

@@ -214,6 +214,7 @@ struct AicoParams
 cudaError_t launch_aico_messages(const AicoParams& P, cudaStream_t stream);
 // op 0: min, 1: sum over t in [t_first, T) of in[b * T + t]
 cudaError_t launch_reduce(const double* in, int64_t n_traj, int T, int t_first, int op, double* out, cudaStream_t stream);
+cudaError_t launch_fill(double* out, int64_t n, double value, cudaStream_t stream);
 void host_get_rotation(const double* data, int type, double* out9);
 
 // ---- batched IK step (ik_kernel.cu) ----

@@ -1,11 +1,16 @@
-"""Sharding and gathers for the multi-GPU path.
+"""Sharding and rendezvous for the multi-GPU path.  No torch: the collectives are the C-ABI's
+(exo_comm_* in include/exotica_b200.h, NCCL over NVLink / NVSwitch on the caller's stream), this module only decides which
+rank evaluates what and gets the NCCL unique id from rank 0 to the other ranks.
 
 The hot path shards with no exchange: every configuration / trajectory is independent and the robot constants are a few
 KB, so each rank (one process per GPU) evaluates a contiguous block of whole trajectories.  Collectives appear only where
 the path has a real exchange step: gathering the per-trajectory costs (all-gather, ceil(B/G) doubles per rank) and the
-minimum sphere distance (all-reduce(min)).  torch.distributed is plumbing here (NCCL over NVLink on the GPUs, gloo in the
-CPU tests); the tensors handed in wrap the device buffers the C-ABI wrote.
+minimum sphere distance (all-gather / all-reduce(min)).
 """
+import os
+import tempfile
+import time
+
 import numpy as np
 
 
@@ -19,40 +24,16 @@ def shard_range(n_units, rank, world_size):
     return begin, min(int(n_units), begin + per)
 
 
+def units_per_rank(n_units, world_size):
+    """Slot size of the gathered arrays: every rank owns ceil(n / world) entries (trailing ranks pad)."""
+    return -(-int(n_units) // int(world_size))
+
+
 def shard_evaluations(n_traj, T, rank, world_size):
     """Evaluation range [e0, e1) of a rank for trajectories of T timesteps: trajectories are never split, so the
     transition term x[t] - x[t-1] stays local to a rank."""
     b0, b1 = shard_range(n_traj, rank, world_size)
     return b0 * T, b1 * T
-
-
-def gather_per_trajectory(local, n_traj, group=None):
-    """All-gather the per-trajectory values (costs) of every rank into one [n_traj] tensor on every rank.
-    `local`: 1-D torch tensor with this rank's block (device tensor under NCCL, CPU tensor under gloo)."""
-    import torch
-    import torch.distributed as dist
-
-    if not dist.is_available() or not dist.is_initialized():
-        return local.clone()
-    world = dist.get_world_size(group)
-    per = -(-int(n_traj) // world)
-    padded = torch.zeros(per, dtype=local.dtype, device=local.device)
-    padded[:local.numel()] = local
-    out = torch.empty(per * world, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return out[:n_traj]
-
-
-def allreduce_min(local_min, group=None):
-    """Global minimum (e.g. of the sphere distance) over all ranks; ranks without data pass +inf."""
-    import torch
-    import torch.distributed as dist
-
-    t = local_min if isinstance(local_min, torch.Tensor) else torch.tensor([float(local_min)], dtype=torch.float64)
-    t = t.clone()
-    if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-    return t
 
 
 def split_states(X, T, rank, world_size):
@@ -61,3 +42,71 @@ def split_states(X, T, rank, world_size):
     flat = X.reshape(-1, X.shape[-1])
     e0, e1 = shard_evaluations(flat.shape[0] // T, T, rank, world_size)
     return flat[e0:e1]
+
+
+# ---- rendezvous: ship rank 0's unique id to the other ranks of one node ---------------------------------------------------
+def _launch_token():
+    """Something all ranks of one launch share and no other launch does: the launcher process (torchrun's agent, mpirun,
+    a test's parent) with its start time, plus the rendezvous port."""
+    ppid = os.getppid()
+    start = "0"
+    try:
+        with open("/proc/%d/stat" % ppid) as f:
+            start = f.read().rsplit(")", 1)[1].split()[19]  # field 22: start time in clock ticks since boot
+    except Exception:
+        pass
+    return "%d_%s_%s_%s" % (ppid, start, os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RESTART_COUNT", "0"))
+
+
+def exchange_unique_id(rank, world_size, make_id, token=None, directory=None, timeout=300.0):
+    """Rank 0 calls make_id() and publishes the bytes through a file (atomic rename) that the other ranks of the same launch
+    poll for; returns the id on every rank.  One node only (the ranks share a filesystem), which is what one process per GPU
+    of one box needs; multi-node launchers pass the id themselves (MPI_Bcast ...) to _capi.Comm."""
+    if world_size == 1:
+        return None
+    directory = directory or os.environ.get("EXO_RENDEZVOUS_DIR") or tempfile.gettempdir()
+    path = os.path.join(directory, "exotica_b200_ncclid_%s" % (token or _launch_token()))
+    if rank == 0:
+        uid = make_id()
+        tmp = "%s.%d.tmp" % (path, os.getpid())
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, path)
+        return uid
+    deadline = time.time() + timeout
+    while time.time() < deadline:
+        try:
+            with open(path, "rb") as f:
+                uid = f.read()
+            if len(uid) >= 128:
+                return uid[:128]
+        except FileNotFoundError:
+            pass
+        time.sleep(0.01)
+    raise RuntimeError("rank %d: no unique id from rank 0 after %.0f s (%s)" % (rank, timeout, path))
+
+
+def release_unique_id(rank, token=None, directory=None):
+    """Rank 0 removes the rendezvous file once every rank has its communicator (after the first barrier)."""
+    if rank != 0:
+        return
+    directory = directory or os.environ.get("EXO_RENDEZVOUS_DIR") or tempfile.gettempdir()
+    try:
+        os.remove(os.path.join(directory, "exotica_b200_ncclid_%s" % (token or _launch_token())))
+    except OSError:
+        pass
+
+
+def init_from_env():
+    """One process per GPU, launched torchrun-style (RANK, WORLD_SIZE, LOCAL_RANK in the environment; a plain `python` run is
+    rank 0 of 1): selects the rank's device, builds the communicator, returns (comm, rank, world, local_rank)."""
+    from . import _capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    _capi.check(_capi.lib().exo_set_device(local_rank))
+    uid = exchange_unique_id(rank, world, _capi.Comm.unique_id)
+    comm = _capi.Comm(rank, world, uid)
+    comm.barrier()
+    release_unique_id(rank)
+    return comm, rank, world, local_rank

@@ -403,8 +403,8 @@ class PlanningProblem(object):
         E = B*T, timestep innermost) -> Phi[E][length_Phi], J[E][length_jacobian][N]."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         E, pshape, jshape = self._shapes(X, layout)
-        phi = out_phi if out_phi is not None else np.empty(pshape)
-        jac = out_jacobian if out_jacobian is not None else np.empty(jshape)
+        phi = _capi.checked_output(out_phi, pshape, "out_phi") if out_phi is not None else np.empty(pshape)
+        jac = _capi.checked_output(out_jacobian, jshape, "out_jacobian") if out_jacobian is not None else np.empty(jshape)
         _check(_host.lib().exo_host_problem_update_batch(self._h, X.ctypes.data, E, int(layout), phi.ctypes.data, jac.ctypes.data))
         return phi, jac
 

@@ -164,6 +164,19 @@ int exo_stream_create(void** stream);
 int exo_stream_destroy(void* stream);
 int exo_stream_synchronize(void* stream); /* NULL = default stream */
 int exo_device_synchronize(void);
+/* CUDA events (device-side timing on the launching stream) and stream capture into a CUDA graph, for callers without their
+ * own CUDA runtime binding.  A batched call and the collective behind it (exo_comm_*) capture into one graph once their
+ * scratch buffers exist, i.e. after one ordinary call of the same shape. */
+int exo_event_create(void** event);
+int exo_event_destroy(void* event);
+int exo_event_record(void* event, void* stream);
+int exo_event_synchronize(void* event);
+int exo_event_elapsed_ms(void* start, void* stop, float* ms);
+typedef struct exo_graph exo_graph;
+int exo_graph_begin_capture(void* stream); /* a stream from exo_stream_create */
+int exo_graph_end_capture(void* stream, exo_graph** out);
+int exo_graph_launch(exo_graph* graph, void* stream);
+int exo_graph_destroy(exo_graph* graph);
 
 /* ---- KinematicTree backend ----------------------------------------------------------------------
  * exo_tree_create        <- end of KinematicTree::BuildTree / UpdateModel (kinematic_tree.cpp:164-421,423-432)
@@ -295,8 +308,48 @@ int exo_problem_cost_jacobian_batch_host(exo_problem* problem, const double* h_x
 int exo_problem_set_min_distance_output(exo_problem* problem, double* d_min_distance);
 #define EXO_REDUCE_MIN 0
 #define EXO_REDUCE_SUM 1
+#define EXO_REDUCE_MAX 2 /* exo_comm_allreduce only */
 /* d_out[b] = min / sum over t in [t_first, T) of d_in[b * T + t] */
 int exo_trajectory_reduce(const double* d_in, int64_t n_traj, int32_t T, int32_t t_first, int32_t op, double* d_out, void* stream);
+
+/* ---- multi-GPU collectives (SURVEY.md section 8 row e) ----------------------------------------------------------------
+ * The reference is single-process; its per-trajectory scalars are AbstractTimeIndexedProblem::GetCost()
+ * (exotica_core/src/problems/abstract_time_indexed_problem.cpp:299-307) and, new here, the minimum SphereCollision surface
+ * distance.  One process per GPU evaluates a contiguous block of whole trajectories (no data-path exchange); these calls are
+ * the only exchange step: NCCL over NVLink / NVSwitch on the CALLER'S stream, right behind the kernel that produced their
+ * input, no host synchronisation.  NCCL (libnccl.so.2, or EXO_NCCL_LIB) is loaded on first use; single-GPU callers never
+ * need it (world == 1 communicators work without NCCL and degrade to device copies).
+ *   exo_comm_get_unique_id  rank 0 creates the 128-byte id; the caller ships it to the other ranks (MPI_Bcast, a file, a
+ *                           TCP store: the rendezvous is the launcher's business, as with ncclGetUniqueId)
+ *   exo_comm_create         ncclCommInitRank on the current device (exo_set_device first); collective over all ranks
+ *   exo_comm_allgather      d_recv[world][count_per_rank] <- every rank's d_send[count_per_rank]; in place when
+ *                           d_send == d_recv + rank * count_per_rank
+ *   exo_comm_allreduce      element-wise EXO_REDUCE_MIN / SUM / MAX over ranks (in place when d_send == d_recv)
+ *   exo_comm_barrier        all ranks' streams meet (1-element all-reduce), then the stream is synchronised */
+typedef struct exo_comm exo_comm;
+#define EXO_COMM_ID_BYTES 128
+int exo_comm_nccl_version(int* version);
+int exo_comm_get_unique_id(unsigned char* id /* [EXO_COMM_ID_BYTES] */);
+int exo_comm_create(int rank, int world, const unsigned char* id /* [EXO_COMM_ID_BYTES], may be NULL when world == 1 */, exo_comm** out);
+int exo_comm_destroy(exo_comm* comm);
+int exo_comm_rank(const exo_comm* comm);
+int exo_comm_world_size(const exo_comm* comm);
+int64_t exo_comm_collective_count(const exo_comm* comm); /* NCCL calls issued so far by this communicator */
+int exo_comm_allgather(exo_comm* comm, const double* d_send, double* d_recv, int64_t count_per_rank, void* stream);
+int exo_comm_allreduce(exo_comm* comm, const double* d_send, double* d_recv, int64_t count, int32_t op, void* stream);
+int exo_comm_barrier(exo_comm* comm, void* stream);
+/* One batched call per step of a sharded multi-start optimisation: the costs of this rank's n_traj_local trajectories
+ * (exo_problem_cost_gradient_batch with a NULL gradient: one fused kernel for chain programs) are written straight into this
+ * rank's slot of d_cost_all[world][n_traj_per_rank] and all-gathered in place on `stream`; slots of ranks holding fewer than
+ * n_traj_per_rank trajectories are zero-padded.  Every rank ends up with every trajectory's GetCost(). */
+int exo_problem_cost_allgather(exo_problem* problem, exo_comm* comm, const double* d_x, int64_t n_traj_local, int64_t n_traj_per_rank,
+                               int32_t layout, double* d_cost_all, void* stream);
+/* SphereCollision: d_min_eval[n_traj_local * T] is the per-evaluation minimum surface distance an update wrote
+ * (exo_problem_set_min_distance_output).  Per-trajectory minima go into this rank's slot of d_min_traj_all[world][n_traj_per_rank]
+ * (padded with +inf) and are all-gathered in place; if d_min_global is not NULL it receives the minimum over all trajectories
+ * of all ranks (all-reduce(min) of one double).  d_min_traj_all may be NULL when only the global minimum is wanted. */
+int exo_min_distance_allgather(exo_comm* comm, const double* d_min_eval, int64_t n_traj_local, int32_t T, int64_t n_traj_per_rank,
+                               double* d_min_traj_all, double* d_min_global, void* stream);
 
 /* ---- task-map Hessians ---------------------------------------------------------------------------
  * exo_problem_hessian_batch <- KinematicTree::ComputeH (exotica_core/src/kinematic_tree.cpp:947-978) + the Hessian overloads of
