@@ -191,10 +191,11 @@ class DeviceBuffer(object):
         check(lib().exo_memcpy_h2d(self.ptr, arr.ctypes.data, arr.size * 8, None))
         check(lib().exo_stream_synchronize(None))
 
-    def download(self, shape):
+    def download(self, shape, offset=0):
+        """offset: first double to read (for sampling slices of a large buffer)."""
         out = np.empty(shape, dtype=np.float64)
-        assert out.size <= self.n
-        check(lib().exo_memcpy_d2h(out.ctypes.data, self.ptr, out.size * 8, None))
+        assert offset >= 0 and offset + out.size <= self.n
+        check(lib().exo_memcpy_d2h(out.ctypes.data, self.ptr + 8 * int(offset), out.size * 8, None))
         check(lib().exo_stream_synchronize(None))
         return out
 

@@ -30,10 +30,29 @@ def build(force=False):
     return so
 
 
+BUILD_FLAGS = "gcc -O3 -ffp-contract=off -std=c99 (generic x86-64)"
+
+
+def use_native_build():
+    """bench.py's CPU-baseline legs: compile the oracle on THIS host with -march=native (oracle/Makefile `native`) and load that
+    copy instead of the generic one.  Must be called before the first lib(); falls back to the generic build if gcc fails."""
+    global BUILD_FLAGS, _NATIVE
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+        _NATIVE = os.path.join(_HERE, "libexo_oracle_native.so")
+        BUILD_FLAGS = "gcc -O3 -march=native -ffp-contract=off -std=c99, built on the measuring host"
+    except Exception:
+        _NATIVE = None
+    return BUILD_FLAGS
+
+
+_NATIVE = None
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libexo_oracle.so")
+        so = _NATIVE or os.path.join(_HERE, "libexo_oracle.so")
         if not os.path.exists(so):
             build()
         L = ctypes.CDLL(so)

@@ -39,6 +39,21 @@ def gpu_problem_from_maps(orc, maps, tree_state=None):
     return tree, prob
 
 
+def record(name, value):
+    """Measured maximum errors of the parity tests, kept next to the other GPU-run artefacts (gpurun_out/parity_measured.jsonl;
+    copied into profiles/ per round) so that tolerances are justified by numbers, not by guesses."""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, "max_err": float(value)}) + "\n")
+    except OSError:
+        pass
+    return float(value)
+
+
 GUARD = 64  # doubles behind every output buffer that the kernels must leave untouched
 
 

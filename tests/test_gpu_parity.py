@@ -9,7 +9,7 @@ import pytest
 
 from conftest import robot_paths
 from exotica_b200 import _capi
-from helpers import angle_entries, gpu_problem_from_maps, max_abs_err, random_states, run_gpu
+from helpers import angle_entries, gpu_problem_from_maps, max_abs_err, random_states, record, run_gpu
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -174,7 +174,7 @@ def test_gimbal_lock_set(oracle_lib):
     # at the singularity roll/yaw are only defined as a sum; both sides take the same branch (roll == 0)
     same_branch = (phi[:, 3] == 0) == (phi_ref[:, 3] == 0)
     assert same_branch.all()
-    assert max_abs_err(phi[:, 3:6], phi_ref[:, 3:6], np.arange(3)) <= 1e-9
+    assert record("gimbal_lock_rpy", max_abs_err(phi[:, 3:6], phi_ref[:, 3:6], np.arange(3))) <= TOL
 
 
 def test_sphere_collision_goldens_and_fixture(oracle_lib):
@@ -468,8 +468,8 @@ def test_trajectory_cost_matches_oracle(oracle_lib, rot):
     cost, cost_eval = _gpu_costs(prob, X.reshape(B * T, 7), B, T, rho, goal=goal, ct=ct, W=W)
     for b in range(B):
         ref, ref_t = orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)
-        assert np.max(np.abs(cost_eval[b * T:(b + 1) * T] - ref_t)) <= 1e-9 * max(1.0, np.max(ref_t))
-        assert abs(cost[b] - ref) <= 1e-9 * max(1.0, ref)
+        assert record("cost_eval_rel_%s" % rot, np.max(np.abs(cost_eval[b * T:(b + 1) * T] - ref_t)) / max(1.0, np.max(ref_t))) <= TOL
+        assert record("cost_traj_rel_%s" % rot, abs(cost[b] - ref) / max(1.0, ref)) <= TOL
         assert cost_eval[b * T] == 0.0  # GetCost starts at t = 1
 
 
@@ -532,7 +532,7 @@ def test_trajectory_cost_jacobian_matches_oracle(oracle_lib, layout):
     cost_h, grad_h = prob.cost_jacobian_batch_host(X)
     assert np.array_equal(grad_h, grad) or np.max(np.abs(grad_h - grad)) <= 1e-12 * np.abs(grad).max()
     ref_cost = np.array([orc.trajectory_cost(X[b], rho, goal=goal, ct=ct, W=W)[0] for b in range(B)])
-    assert np.max(np.abs(cost_h - ref_cost)) <= 1e-9 * ref_cost.max()
+    assert record("cost_host_rel", np.max(np.abs(cost_h - ref_cost)) / ref_cost.max()) <= TOL
 
 
 def _gpu_cost_gradient_fused(prob, X, B, T, layout=_capi.LAYOUT_SOA):
@@ -851,7 +851,7 @@ def test_sibling_maps_cost_and_unused_fill(oracle_lib):
     goal[0:4] = oracle_lib.set_rotation(oracle_lib.get_frame([0, 0, 0, 0.4, -0.3, 0.2])[:9], "Quaternion")
     cost, _ = _gpu_costs(prob, X, 300, 1, [2.0, 0.0, 0.5, 3.0], goal=goal)
     ref = np.array([orc.trajectory_cost(X[e:e + 1], [2.0, 0.0, 0.5, 3.0], goal=goal)[0] for e in range(300)])
-    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    assert record("sibling_cost_rel", np.max(np.abs(cost - ref)) / max(1.0, ref.max())) <= TOL
 
 
 # ---- BASELINE.json configurations 3, 4, 5 at full size: size-independent properties + sampled oracle parity ---------------------
@@ -927,7 +927,8 @@ def test_full_size_cfg5_sphere_collision(oracle_lib):
     assert np.array_equal(phi_p, phi[perm]) and np.array_equal(jac_p, jac[perm])
     sel = np.random.default_rng(7).integers(0, B * T, 1024)
     phi_ref, jac_ref = orc.problem_update_batch(X[sel])
-    assert max_abs_err(phi[sel], phi_ref) <= 1e-9 and max_abs_err(jac[sel], jac_ref) <= 1e-9  # sums of 1024 terms
+    # sums of 1024 sigmoids (values up to a few hundred): the measured difference is recorded, the bar stays 1e-10 absolute
+    assert record("cfg5_full_phi", max_abs_err(phi[sel], phi_ref)) <= TOL and record("cfg5_full_jac", max_abs_err(jac[sel], jac_ref)) <= TOL
 
 
 # ---- task-map Hessians ---------------------------------------------------------------------------
@@ -1017,7 +1018,7 @@ def test_batched_ik_matches_the_reference_solver(oracle_lib, monkeypatch):
     for e in range(E):
         q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], rho, goal=goal, W=W, max_iterations=60)
         # the returned cost is the cost of the returned state
-        assert abs(cost[e] - orc.trajectory_cost(Q[e:e + 1], rho, goal=goal)[0]) <= 1e-9 * max(1.0, cost[e])
+        assert record("ik_cost_rel", abs(cost[e] - orc.trajectory_cost(Q[e:e + 1], rho, goal=goal)[0]) / max(1.0, cost[e])) <= TOL
         if t_ref == 3:  # the reference converged (FunctionTolerance): same path, same answer
             assert term[e] == 3 and iters[e] == it_ref
             assert np.max(np.abs(Q[e] - q_ref)) <= 1e-6 and abs(cost[e] - c_ref) <= 1e-9
@@ -1040,3 +1041,23 @@ def test_batched_ik_position_only_on_the_three_dof_robot(oracle_lib):
         q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], [10.0], goal=goal, tolerance=1e-10)
         assert term[e] == t_ref and iters[e] == it_ref and np.max(np.abs(Q[e] - q_ref)) <= 1e-7
     assert np.isin(term, (0, 2, 3)).all() and np.median(cost) < 1e-6  # step / function tolerance (or the iteration limit in a local minimum)
+
+
+def test_full_size_cfg2a_rpy_1m(oracle_lib):
+    """The benchmark's own workload (bench.py: EffFrame(RPY), 2^20 configurations, seed 1234 + 2): sampled oracle parity at 1e-10 with
+    the Euler angles compared modulo 2 pi, every kernel that can run it."""
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    maps = [{"type": "EffFrame", "Type": "RPY", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    E = 1 << 20
+    X = np.random.default_rng(1234 + 2).uniform(orc.lower, orc.upper, size=(E, 7))
+    sel = np.random.default_rng(8).choice(E, size=8192, replace=False)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    for choice in (0, 3, 1):
+        prob.set_kernel(choice)
+        phi, jac = run_gpu(prob, X)
+        e_phi, e_jac = max_abs_err(phi[sel], phi_ref, np.arange(3, 6)), max_abs_err(jac[sel], jac_ref)
+        assert record("cfg2a_rpy_1m_phi_%s" % prob.last_kernel(), e_phi) <= TOL and record("cfg2a_rpy_1m_jac_%s" % prob.last_kernel(), e_jac) <= TOL
+        # pitch stays inside [-pi/2, pi/2], roll / yaw inside (-pi, pi]: KDL's GetRPY ranges
+        assert np.abs(phi[:, 4]).max() <= np.pi / 2 and np.abs(phi[:, 3]).max() <= np.pi and np.abs(phi[:, 5]).max() <= np.pi

@@ -95,7 +95,7 @@ def test_end_pose_problem_update_and_batch(oracle_lib):
     cost = prob.cost_batch(X)
     goal = np.array([0.5, 0, 0.5, 0, 0, 0])
     ref = np.array([orc.trajectory_cost(X[e:e + 1], [3.0], goal=goal)[0] for e in range(300)])
-    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    assert np.max(np.abs(cost - ref)) <= 1e-10 * max(1.0, ref.max())
     with pytest.raises(exo.ExoticaError):
         prob.update_batch(X[:, :6])
 
@@ -123,10 +123,10 @@ def test_time_indexed_problem_trajectories_and_cost(oracle_lib):
     goal = np.concatenate([[0.4, 0.2, 0.7, 0.1, 0.2, 0.3], np.zeros(7)])
     W = np.linspace(1, 7, 7) * 2.0
     ref = np.array([orc.trajectory_cost(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)[0] for b in range(B)])
-    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    assert np.max(np.abs(cost - ref)) <= 1e-10 * max(1.0, ref.max())
     # GetCostJacobian of every trajectory (row t = 0 is zero: the reference's vector starts at t = 1)
     cost2, grad = prob.cost_jacobian_batch(X)
-    assert np.max(np.abs(cost2 - ref)) <= 1e-9 * max(1.0, ref.max()) and grad.shape == X.shape
+    assert np.max(np.abs(cost2 - ref)) <= 1e-10 * max(1.0, ref.max()) and grad.shape == X.shape
     for b in range(B):
         gref = orc.trajectory_cost_jacobian(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)
         assert np.max(np.abs(grad[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
@@ -176,7 +176,7 @@ def test_sibling_maps_through_the_factory(oracle_lib):
     assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
     cost = prob.cost_batch(X)
     ref = np.array([orc.trajectory_cost(X[e:e + 1], [1.0, 2.0, 3.0, 4.0])[0] for e in range(200)])
-    assert np.max(np.abs(cost - ref)) <= 1e-9 * max(1.0, ref.max())
+    assert np.max(np.abs(cost - ref)) <= 1e-10 * max(1.0, ref.max())
     with pytest.raises(exo.ExoticaError, match="JointMap index"):
         exo.Setup.create_problem(("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"),
                                                                           "Maps": [("exotica/JointPose", {"Name": "P", "JointMap": "9"})]}))
@@ -321,3 +321,161 @@ def test_ik_solver_and_hessian_through_the_python_surface(oracle_lib):
     H = problem.hessian_batch(Q0[:9])
     for e in range(9):
         assert np.max(np.abs(H[e] - orc.problem_hessian(Q0[e]))) <= 1e-10
+
+
+# ---- the product loader -> compiler -> kernel chain at BASELINE.json's sizes (no oracle tree handed to the C-ABI) -----------------
+def _device_update_sampled(prob, X, T, blocks=8, block=512):
+    """Full-size update on device buffers (evaluation-major), then `blocks` contiguous slices of `block` evaluations come back."""
+    from exotica_b200 import _capi
+    E, N = X.shape
+    LP, LJ = prob.length_Phi, prob.length_jacobian
+    dx, dphi, djac = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(E * LP), _capi.DeviceBuffer(E * LJ * N)
+    dx.upload(X)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=exo.LAYOUT_AOS_ROWMAJOR)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    starts = np.linspace(0, E - block, blocks).astype(np.int64) // T * T
+    sel = np.concatenate([np.arange(s, s + block) for s in starts])
+    phi = np.concatenate([dphi.download((block, LP), offset=s * LP) for s in starts])
+    jac = np.concatenate([djac.download((block, LJ, N), offset=s * LJ * N) for s in starts])
+    for b in (dx, dphi, djac):
+        b.free()
+    return sel, phi, jac
+
+
+@pytest.mark.gpu
+def test_cfg3_through_the_product_loader_at_full_size(oracle_lib):
+    from helpers import angle_entries, max_abs_err
+    T, B = 100, 4096
+    eff = ("exotica/EffFrame", {"Name": "Eff", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
+    init = ("exotica/TimeIndexedProblem", {"Name": "cfg3", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff, ("exotica/JointLimit", {"Name": "JL"})],
+                                           "T": T, "tau": 0.05, "Cost": [("exotica/Task", {"Task": "Eff"}), ("exotica/Task", {"Task": "JL"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit"}]
+    orc = _oracle_for(oracle_lib, maps)
+    rng = np.random.default_rng(21)
+    q0 = rng.uniform(orc.lower, orc.upper, size=(B, 1, 7))
+    X = np.clip(q0 + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1).reshape(B * T, 7)
+    sel, phi, jac = _device_update_sampled(prob, X, T)
+    assert prob.last_kernel() == "exo_chain_kernel"
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel], T=T)
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_cfg4_through_the_product_loader_at_full_size(oracle_lib):
+    from helpers import angle_entries, max_abs_err
+    links = ["leftFoot", "rightFoot", "leftPalm", "rightPalm"]
+    eff = ("exotica/EffFrame", {"Name": "Eff", "EndEffector": [("exotica/Frame", {"Link": l}) for l in links]})
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "cfg4", "PlanningScene": _scene_init("valkyrie_sim", "whole_body"), "Maps": [eff],
+                                                    "Cost": [("exotica/Task", {"Task": "Eff"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": l} for l in links]}]
+    orc = oracle_lib.Oracle(oracle_lib.load_robot(*robot_paths("valkyrie_sim"), joint_group="whole_body"))
+    orc.set_problem(maps)
+    E = 1 << 18
+    rng = np.random.default_rng(22)
+    lo, hi = np.where(orc.lower < -1e19, -1.0, orc.lower), np.where(orc.upper > 1e19, 1.0, orc.upper)
+    X = rng.uniform(lo, hi, size=(E, 38))
+    X[:, 3:6] = rng.uniform(-np.pi, np.pi, size=(E, 3))
+    X[:, 4] = np.clip(X[:, 4], -np.pi / 2 + 0.05, np.pi / 2 - 0.05)
+    sel, phi, jac = _device_update_sampled(prob, X, 1, blocks=4, block=256)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_cfg5_through_the_product_loader_at_full_size(oracle_lib):
+    from helpers import max_abs_err, record
+    rng = np.random.default_rng(5)
+    sph = [{"Link": "lwr_arm_%d_link" % (1 + i % 7), "LinkOffset": [0.0, 0.0, 0.02 * (i // 7)], "Radius": 0.05, "Group": "Robot"} for i in range(32)]
+    sph += [{"Link": "", "LinkOffset": [float(v) for v in rng.uniform([-0.8, -0.8, 0.0], [0.8, 0.8, 1.2])], "Radius": 0.05, "Group": "Obstacle"} for _ in range(32)]
+    T, B = 100, 4096
+    col = ("exotica/SphereCollision", {"Name": "Col", "Precision": 0.1, "EndEffector": [("exotica/Frame", s) for s in sph]})
+    init = ("exotica/TimeIndexedProblem", {"Name": "cfg5", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [col], "T": T, "tau": 0.05,
+                                           "Cost": [("exotica/Task", {"Task": "Col"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "SphereCollision", "Precision": 0.1, "EndEffector": sph}]
+    orc = _oracle_for(oracle_lib, maps)
+    q0 = rng.uniform(orc.lower, orc.upper, size=(B, 1, 7))
+    X = np.clip(q0 + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1).reshape(B * T, 7)
+    sel, phi, jac = _device_update_sampled(prob, X, T, blocks=4, block=200)
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel], T=T)
+    assert record("cfg5_loader_phi", max_abs_err(phi, phi_ref)) <= 1e-10 and record("cfg5_loader_jac", max_abs_err(jac, jac_ref)) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_scene_changes_after_the_first_update_rebuild_the_backend(oracle_lib):
+    """Scene::AddObject / AddTrajectory after problem.update() destroy the C-ABI tree: the problem must rebuild its handle
+    (not dereference the freed tree) and see the new object."""
+    from helpers import angle_entries, max_abs_err
+    T = 5
+    eff = ("exotica/EffFrame", {"Name": "Eff", "EndEffector": [("exotica/Frame", {"Link": "lwr_arm_7_link"})]})
+    init = ("exotica/TimeIndexedProblem", {"Name": "p", "PlanningScene": _scene_init("lwr_simplified", "arm"), "Maps": [eff], "T": T, "tau": 0.1,
+                                           "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "2"})]})
+    prob = exo.Setup.create_problem(init)
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_7_link"}]}]
+    orc = _oracle_for(oracle_lib, maps)
+    X = np.random.default_rng(1).uniform(orc.lower, orc.upper, size=(3 * T, 7))
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    cost0 = prob.cost_batch(X.reshape(3, T, 7))
+    scene = prob.get_scene()
+    for round_ in range(2):
+        phi, jac = prob.update_batch(X)
+        assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+        # mutate the scene between updates: a new object, then a trajectory on it
+        scene.add_object("Box%d" % round_, [0.5, 0.1 * round_, 0.3])
+        scene.add_trajectory("Box%d" % round_, [[0.5, 0.1 * t, 0.3] for t in range(T)])
+    phi, jac = prob.update_batch(X)
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    assert np.array_equal(prob.cost_batch(X.reshape(3, T, 7)), cost0)  # the cost description was pushed again
+    prob.update(X[4], 4)
+    assert max_abs_err(prob.Phi[4], phi_ref[4], angle_entries(maps, orc)) <= 1e-10
+    fk = scene.fk("Box1")
+    assert np.allclose(fk[9:], [0.5, 0.1, 0.3])
+
+
+@pytest.mark.gpu
+def test_batched_calls_push_trajectory_tables_without_a_prior_update(oracle_lib):
+    """cost_batch / cost_jacobian_batch / update_batch_device on a fresh time-indexed problem with a trajectory-driven link."""
+    T = 6
+    sph = [("exotica/Frame", {"Link": "lwr_arm_6_link", "Radius": 0.1, "Group": "Robot"}), ("exotica/Frame", {"Link": "Obs", "Radius": 0.2, "Group": "Obstacle"})]
+    col = ("exotica/SphereCollision", {"Name": "Col", "Precision": 0.1, "EndEffector": sph})
+    scene = _scene_init("lwr_simplified", "arm")
+    scene[1]["Links"] = [("exotica/Link", {"Name": "Obs", "Transform": [0.4, 0.0, 0.6]})]
+    init = ("exotica/TimeIndexedProblem", {"Name": "p", "PlanningScene": scene, "Maps": [col], "T": T, "tau": 0.1,
+                                           "Cost": [("exotica/Task", {"Task": "Col"})]})
+    frames = [[0.4, 0.05 * t, 0.6] for t in range(T)]
+    X = np.random.default_rng(2).uniform(-1, 1, size=(4, T, 7))
+    costs = []
+    for entry in ("cost", "grad", "update"):
+        prob = exo.Setup.create_problem(init)
+        prob.get_scene().add_trajectory("Obs", frames)
+        if entry == "cost":
+            costs.append(prob.cost_batch(X))
+        elif entry == "grad":
+            costs.append(prob.cost_jacobian_batch(X)[0])
+        else:
+            prob.update_batch(X)
+            costs.append(prob.cost_batch(X))
+    assert np.allclose(costs[0], costs[1], rtol=0, atol=1e-12) and np.allclose(costs[0], costs[2], rtol=0, atol=1e-12)
+    # replacing the trajectory of an already-generated link changes the cost (no stale table)
+    prob.get_scene().add_trajectory("Obs", [[0.4, -0.05 * t, 0.5] for t in range(T)])
+    assert np.max(np.abs(prob.cost_batch(X) - costs[0])) > 1e-6
+
+
+REFERENCE = "/root/reference/exotica_examples"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout only exists in the build container")
+def test_reference_example_files_load_unmodified():
+    """The reference's own XML configurations and robot files through the product loader (host only: sizes, names, indexing)."""
+    exo.Setup.set_package_path("exotica_examples", REFERENCE)
+    prob = exo.Setup.load_problem(os.path.join(REFERENCE, "resources", "configs", "example_ik.xml"))
+    assert prob.type.endswith("UnconstrainedEndPoseProblem") and (prob.N, prob.length_Phi, prob.length_jacobian) == (7, 6, 6)
+    assert prob.get_scene().get_controlled_joint_names() == ["lwr_arm_%d_joint" % i for i in range(7)]
+    assert [t.name for t in prob.get_tasks()] == ["Position"]
+    for name, dims in (("example_aico.xml", None), ("example_aico_trajectory.xml", None)):
+        path = os.path.join(REFERENCE, "resources", "configs", name)
+        if os.path.exists(path):
+            p = exo.Setup.load_problem(path)
+            assert p.N == 7 and p.T >= 3
