@@ -456,6 +456,9 @@ def run_ours(args):
     if capi.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
     comm, rank, world, local_rank = exd.init_from_env()
+    if rank == 0:
+        from oracle import oracle
+        oracle.use_native_build()  # CPU-baseline build flags; bit-identical results to the generic build
 
     E = args.configs
     problem = exo.Setup.create_problem(lwr_initializer())

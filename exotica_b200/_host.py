@@ -29,12 +29,15 @@ HOST_SYMBOLS = [
     ("exo_host_scene_set_model_state", ctypes.c_int, [_vp, _dp, ctypes.c_int]),
     ("exo_host_scene_num_model_joints", ctypes.c_int, [_vp]),
     ("exo_host_scene_add_object", ctypes.c_int, [_vp, _cp, _dp, _cp]),
+    ("exo_host_scene_load_scene", ctypes.c_int, [_vp, _cp, _dp]),
+    ("exo_host_scene_load_scene_file", ctypes.c_int, [_vp, _cp, _dp]),
+    ("exo_host_scene_clean", ctypes.c_int, [_vp]),
     ("exo_host_scene_add_trajectory", ctypes.c_int, [_vp, _cp, ctypes.c_int, _dp]),
     ("exo_host_scene_add_trajectory_string", ctypes.c_int, [_vp, _cp, _cp]),
     ("exo_host_scene_get_trajectory", ctypes.c_int, [_vp, _cp, ctypes.c_char_p, ctypes.c_int]),
     ("exo_host_trajectory_sample", ctypes.c_int, [_cp, ctypes.c_int, _dp, _dp, _dp]),
     ("exo_host_scene_request_frames", ctypes.c_int, [_vp, ctypes.c_int, _cp, _dp, _cp, _dp, ctypes.c_int]),
-    ("exo_host_scene_update", ctypes.c_int, [_vp, _dp, ctypes.c_int, _dp, _dp]),
+    ("exo_host_scene_update", ctypes.c_int, [_vp, _dp, ctypes.c_int, ctypes.c_double, _dp, _dp]),
     ("exo_host_scene_update_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
     ("exo_host_scene_fk", ctypes.c_int, [_vp, _cp, _dp, _cp, _dp, _dp]),
     ("exo_host_scene_jacobian", ctypes.c_int, [_vp, _cp, _dp, _cp, _dp, _dp]),
@@ -48,6 +51,7 @@ HOST_SYMBOLS = [
     ("exo_host_problem_scene", _vp, [_vp]),
     ("exo_host_problem_start_state", ctypes.c_int, [_vp, _dp]),
     ("exo_host_problem_update", ctypes.c_int, [_vp, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp]),
+    ("exo_host_problem_update_trajectory", ctypes.c_int, [_vp, _dp, ctypes.c_int, _dp, _dp]),
     ("exo_host_problem_update_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
     ("exo_host_problem_update_batch_device", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
     ("exo_host_problem_cost_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),

@@ -266,7 +266,12 @@ public:
     int AddEnvironmentElement(const std::string& name, const Frame& transform, const std::string& parent = "", bool trajectory_generated = false);
     int AddElement(const std::string& name, const Frame& transform, const std::string& parent = "");
     int MakeTrajectoryGenerated(int element_index);  // returns the element's slot in the per-timestep frame table
+    // KinematicTree::ResetModel (kinematic_tree.cpp:436-452): drops every environment element, the robot model stays
+    void ResetModel();
     int GetNumGenerated() const { return num_generated_; }
+    // KinematicElement::generated_offset of a trajectory-driven element (Scene::UpdateTrajectoryGenerators, scene.cpp:329-335): the
+    // pose the one-configuration entry points (Update, FK, Jacobian) use; time-indexed problems push whole per-timestep tables instead
+    void SetGeneratedOffset(int slot, const Frame& frame);
 
     const std::vector<KinematicElement>& GetTree() const { return tree_; }
     int GetElementIndex(const std::string& link_name) const;  // tree_map_ lookup, -1 if missing
@@ -304,6 +309,10 @@ private:
     exo_problem* frames_problem_ = nullptr;  // EXO_MAP_FRAMES problem behind RequestFrames/Update
     bool frames_requested_ = false;
     void EnsureFramesProblem();              // (re)builds frames_problem_ from request_ after the tree changed
+    std::vector<Frame> generated_offsets_;   // by generated slot
+public:
+    void PushCurrentGenerated(exo_problem* p);  // the current generated offsets as a one-timestep table
+private:
     KinematicsRequest request_;
     std::shared_ptr<KinematicResponse> solution_;
 };
@@ -368,6 +377,7 @@ public:
     KinematicTree& GetKinematicTree() { return kinematica_; }
     std::shared_ptr<KinematicResponse> RequestKinematics(const KinematicsRequest& request) { return kinematica_.RequestFrames(request); }
     void Update(const std::vector<double>& x, double t = 0);  // scene.cpp:337-348
+    void UpdateTrajectoryGenerators(double t = 0);            // scene.cpp:329-335
     std::string GetName() const { return name_; }
     std::string GetRootFrameName() { return kinematica_.GetRootFrameName(); }
     std::string GetRootJointName() { return kinematica_.GetRootJointName(); }
@@ -383,6 +393,13 @@ public:
     int get_num_velocities() const { return 0; }
     // Scene::AddObject (scene.cpp:829-...): a named frame attached to `parent` (default: world)
     void AddObject(const std::string& name, const Frame& transform = IdentityFrame(), const std::string& parent = "");
+    // Scene::LoadScene / LoadSceneFile (scene.cpp:610-645): world objects of a MoveIt ".scene" geometry text.  Every object becomes
+    // a frame named after it, posed like its first shape (UpdateSceneFrames, scene.cpp:702-758), with one child frame
+    // "<name>_collision_<i>" per shape; the shapes themselves belong to the collision scene (out of scope) and are skipped.
+    void LoadScene(const std::string& scene_text, const Frame& offset = IdentityFrame());
+    void LoadSceneFile(const std::string& file_name, const Frame& offset = IdentityFrame());
+    void CleanScene();                           // scene.cpp:655-660
+    std::vector<std::string> GetWorldObjectNames() const;
     // Scene::AddTrajectory (scene.cpp:917-935) replaced by an explicit per-timestep frame table [T][12]
     void AddTrajectoryFrames(const std::string& link, const std::vector<Frame>& frames_per_timestep);
     // Scene::AddTrajectory(link, traj) (scene.cpp:922-935): the link follows the trajectory; time-indexed problems sample it at
@@ -402,6 +419,19 @@ private:
     std::map<std::string, std::pair<int, std::shared_ptr<Trajectory>>> trajectory_generators_;  // link -> (slot, trajectory)
     mutable std::vector<double> generated_table_;
     uint64_t trajectory_version_ = 0;  // bumped by AddTrajectory / AddTrajectoryFrames (problems re-push their frame tables)
+    struct WorldObject
+    {
+        std::vector<Frame> shape_poses;  // world pose of every shape
+    };
+    struct CustomLink
+    {
+        std::string name, parent;
+        Frame transform;
+    };
+    std::map<std::string, WorldObject> world_objects_;  // planning_scene::World iterates its objects by name (std::map)
+    std::vector<CustomLink> custom_links_;              // Links initializers / AddObject, in insertion order
+    std::map<std::string, std::vector<Frame>> trajectory_tables_;  // link -> explicit per-timestep frames (AddTrajectoryFrames)
+    void RebuildEnvironment();  // UpdateSceneFrames + UpdateInternalFrames: world objects (by name), custom links, trajectories
 
 public:
     uint64_t GetTrajectoryVersion() const { return trajectory_version_; }

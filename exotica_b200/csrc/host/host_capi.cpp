@@ -271,6 +271,21 @@ int exo_host_scene_add_object(exo_host_scene* s, const char* name, const double 
     HOST_TRY(s->scene->AddObject(name, FrameOr(frame12), parent ? parent : ""))
 }
 
+int exo_host_scene_load_scene(exo_host_scene* s, const char* scene_text, const double offset12[12])
+{
+    HOST_TRY(s->scene->LoadScene(scene_text ? scene_text : "", FrameOr(offset12)))
+}
+
+int exo_host_scene_load_scene_file(exo_host_scene* s, const char* file_name, const double offset12[12])
+{
+    HOST_TRY(s->scene->LoadSceneFile(file_name ? file_name : "", FrameOr(offset12)))
+}
+
+int exo_host_scene_clean(exo_host_scene* s)
+{
+    HOST_TRY(s->scene->CleanScene())
+}
+
 int exo_host_scene_add_trajectory(exo_host_scene* s, const char* link, int T, const double* frames)
 {
     HOST_TRY({
@@ -321,11 +336,12 @@ int exo_host_scene_request_frames(exo_host_scene* s, int n_frames, const char* l
     })
 }
 
-int exo_host_scene_update(exo_host_scene* s, const double* x, int n, double* phi, double* jac)
+int exo_host_scene_update(exo_host_scene* s, const double* x, int n, double t, double* phi, double* jac)
 {
     HOST_TRY({
-        s->scene->Update(std::vector<double>(x, x + n));
+        s->scene->Update(std::vector<double>(x, x + n), t);
         std::shared_ptr<KinematicResponse> r = s->scene->GetKinematicTree().GetKinematicResponse();
+        if (!r) return EXO_OK;  // no frames requested: the state and the trajectory-driven links were updated, nothing to return
         const int N = s->scene->GetKinematicTree().GetNumControlledJoints();
         for (size_t f = 0; f < r->Phi.size(); ++f)
         {
@@ -458,6 +474,21 @@ int exo_host_problem_update(exo_host_problem* p, const double* x, int n, int t, 
         }
         else
             ThrowPretty("unsupported problem type");
+    })
+}
+
+int exo_host_problem_update_trajectory(exo_host_problem* p, const double* x, int n, double* phi, double* jac)
+{
+    HOST_TRY({
+        TimeIndexedProblem* tp = dynamic_cast<TimeIndexedProblem*>(p->problem.get());
+        if (!tp) ThrowPretty("Update(x_trajectory) needs a time-indexed problem");
+        tp->Update(std::vector<double>(x, x + n));
+        const size_t lp = tp->length_Phi, lj = (size_t)tp->length_jacobian * tp->N;
+        for (int t = 0; t < tp->GetT(); ++t)
+        {
+            if (phi) memcpy(phi + (size_t)t * lp, tp->Phi[t].data(), lp * sizeof(double));
+            if (jac) memcpy(jac + (size_t)t * lj, tp->jacobian[t].data(), lj * sizeof(double));
+        }
     })
 }
 

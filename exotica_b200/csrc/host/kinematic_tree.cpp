@@ -468,6 +468,22 @@ int KinematicTree::AddEnvironmentElement(const std::string& name, const Frame& t
     return (int)tree_.size() - 1;
 }
 
+void KinematicTree::ResetModel()
+{
+    tree_.resize(num_model_elements_);
+    tree_state_.resize(num_model_elements_);
+    tree_map_.clear();
+    for (int i = 0; i < (int)tree_.size(); ++i) tree_map_[tree_[i].link_name] = i;
+    num_generated_ = 0;
+    generated_offsets_.clear();
+    for (KinematicElement& e : tree_)
+    {
+        e.is_trajectory_generated = false;
+        e.generated_slot = -1;
+    }
+    InvalidateBackend();
+}
+
 int KinematicTree::MakeTrajectoryGenerated(int index)
 {
     // Scene::AddTrajectory (scene.cpp:927-935): is_trajectory_generated = true; UpdateTree then takes generated_offset for the
@@ -486,6 +502,22 @@ int KinematicTree::MakeTrajectoryGenerated(int index)
 int KinematicTree::AddElement(const std::string& name, const Frame& transform, const std::string& parent)
 {
     return AddEnvironmentElement(name, transform, parent, false);
+}
+
+void KinematicTree::SetGeneratedOffset(int slot, const Frame& frame)
+{
+    if (slot < 0 || slot >= num_generated_) ThrowPretty("No such trajectory-driven element");
+    if ((int)generated_offsets_.size() < num_generated_) generated_offsets_.resize(num_generated_, IdentityFrame());
+    generated_offsets_[slot] = frame;
+}
+
+void KinematicTree::PushCurrentGenerated(exo_problem* p)
+{
+    if (num_generated_ == 0) return;
+    if ((int)generated_offsets_.size() < num_generated_) generated_offsets_.resize(num_generated_, IdentityFrame());
+    std::vector<double> table(12 * (size_t)num_generated_);
+    for (int g = 0; g < num_generated_; ++g) memcpy(&table[12 * (size_t)g], generated_offsets_[g].data(), 12 * sizeof(double));
+    CheckRc(exo_problem_set_generated(p, 1, num_generated_, table.data()));
 }
 
 exo_tree* KinematicTree::GetBackend()
@@ -581,7 +613,7 @@ std::shared_ptr<KinematicResponse> KinematicTree::RequestFrames(const Kinematics
 void KinematicTree::UpdateBatch(const double* x, int64_t n_evals, int layout, double* phi, double* jacobian)
 {
     EnsureFramesProblem();
-    if (num_generated_ > 0) ThrowPretty("Trajectory-driven links need a time-indexed problem (Scene::Update(x, t) per timestep)");
+    PushCurrentGenerated(frames_problem_);  // trajectory-driven links sit where the last Scene::Update(x, t) put them
     CheckRc(exo_problem_update_batch_host(frames_problem_, x, n_evals, 1, layout, phi, jacobian));
 }
 
@@ -589,13 +621,15 @@ void KinematicTree::UpdateBatch(const double* x, int64_t n_evals, int layout, do
 void KinematicTree::Update(const std::vector<double>& x)
 {
     if ((int)x.size() != num_controlled_joints_) ThrowPretty("Wrong state vector size! Got " + std::to_string(x.size()) + " expected " + std::to_string(num_controlled_joints_));
-    EnsureFramesProblem();
     for (int i = 0; i < num_controlled_joints_; ++i) tree_state_[controlled_joints_[i]] = x[i];
+    if (!frames_requested_) return;  // the reference updates the tree whether or not frames were requested (kinematic_tree.cpp:678-693)
+    EnsureFramesProblem();
     const int F = (int)solution_->Phi.size();
     std::vector<double> phi(12 * (size_t)F), jac;
     const bool want_j = (solution_->flags & KIN_J) != 0;
     if (want_j) jac.resize(6 * (size_t)F * num_controlled_joints_);
     // column-major per evaluation == J[N][6F]: rows of frame f are 6f..6f+5
+    PushCurrentGenerated(frames_problem_);
     CheckRc(exo_problem_update_batch_host(frames_problem_, x.data(), 1, 1, EXO_LAYOUT_AOS_COLMAJOR, phi.data(), want_j ? jac.data() : nullptr));
     solution_->x = x;
     for (int f = 0; f < F; ++f)
@@ -626,6 +660,18 @@ static void OneFrame(KinematicTree& kt, exo_tree* backend, int n, int ea, const 
     if (rc == EXO_OK) rc = exo_problem_finalize(p);
     std::vector<double> j(6 * (size_t)n);
     Frame f;
+    if (rc == EXO_OK && kt.GetNumGenerated() > 0)
+    {
+        try
+        {
+            kt.PushCurrentGenerated(p);
+        }
+        catch (...)
+        {
+            exo_problem_destroy(p);
+            throw;
+        }
+    }
     if (rc == EXO_OK) rc = exo_problem_update_batch_host(p, x.data(), 1, 1, EXO_LAYOUT_AOS_COLMAJOR, f.data(), jac ? j.data() : nullptr);
     exo_problem_destroy(p);
     CheckRc(rc);

@@ -83,6 +83,19 @@ void Scene::Instantiate(const Initializer& init)
     // scene.cpp:292-303
     if (init.Has("JointPositionLimitsLower")) kinematica_.SetJointLimitsLower(ParseVector(init.Get("JointPositionLimitsLower", "")));
     if (init.Has("JointPositionLimitsUpper")) kinematica_.SetJointLimitsUpper(ParseVector(init.Get("JointPositionLimitsUpper", "")));
+    // scene.cpp:107-112: LoadScene = ';'-separated list of .scene files, identity offset
+    if (init.Has("LoadScene"))
+    {
+        std::string list = init.Get("LoadScene", "");
+        size_t pos = 0;
+        while (pos <= list.size())
+        {
+            const size_t end = std::min(list.find(';', pos), list.size());
+            const std::string file = xml::Trim(list.substr(pos, end - pos));
+            if (!file.empty()) LoadSceneFile(file);
+            pos = end + 1;
+        }
+    }
     // custom links (scene.cpp:114-170; init/link.in: Name, Transform, Parent -- shapes belong to the collision scene, out of scope)
     for (const Initializer& link : init.List("Links"))
     {
@@ -98,24 +111,214 @@ void Scene::Instantiate(const Initializer& init)
     }
 }
 
+void Scene::UpdateTrajectoryGenerators(double t)
+{
+    // scene.cpp:329-335: generated_offset = trajectory->GetPosition(t) for every trajectory-driven link.  Links driven by an
+    // explicit per-timestep table (AddTrajectoryFrames) have no time base of their own: they show their first frame here; the
+    // time-indexed problems index the table by timestep.
+    for (const auto& kv : trajectories_)
+        if (!kv.second.empty()) kinematica_.SetGeneratedOffset(kv.first, kv.second.front());
+    for (const auto& kv : trajectory_generators_) kinematica_.SetGeneratedOffset(kv.second.first, kv.second.second->GetPosition(t));
+}
+
 void Scene::Update(const std::vector<double>& x, double t)
 {
-    (void)t;  // per-timestep frames are tables indexed by the problem's timestep, see TimeIndexedProblem
+    UpdateTrajectoryGenerators(t);  // scene.cpp:337-348
     kinematica_.Update(x);
 }
 
 void Scene::AddObject(const std::string& name, const Frame& transform, const std::string& parent)
 {
     kinematica_.AddEnvironmentElement(name, transform, parent, false);
+    custom_links_.push_back({name, parent, transform});
+}
+
+// ---- MoveIt ".scene" geometry text (planning_scene::PlanningScene::loadGeometryFromStream, moveit_core -- external to the reference,
+// not vendored: restated from the published file format; the reference's fixtures are exotica_examples/resources/scenes/*.scene) -----
+//   (SceneName)+
+//   * ObjectName
+//   [x y z qx qy qz qw]          object pose, only in the newer format
+//   n_shapes
+//   shape (box: x y z | sphere: r | cylinder: r l | cone: r l | plane: a b c d | mesh: nv nt, nv vertices, nt triangles)
+//   x y z
+//   qx qy qz qw
+//   r g b a
+//   ...
+//   .
+namespace
+{
+Frame PoseFromQuaternion(double x, double y, double z, double qx, double qy, double qz, double qw)
+{
+    // Eigen::Translation3d(x, y, z) * Eigen::Quaterniond(qw, qx, qy, qz): Eigen's toRotationMatrix, no normalisation
+    const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+    const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    Frame f;
+    double* d = f.data();
+    d[0] = 1 - (tyy + tzz); d[1] = txy - twz; d[2] = txz + twy;
+    d[3] = txy + twz; d[4] = 1 - (txx + tzz); d[5] = tyz - twx;
+    d[6] = txz - twy; d[7] = tyz + twx; d[8] = 1 - (txx + tyy);
+    d[9] = x; d[10] = y; d[11] = z;
+    return f;
+}
+
+Frame Compose(const Frame& a, const Frame& b)
+{
+    Frame out;
+    const double *A = a.data(), *B = b.data();
+    double* o = out.data();
+    for (int r = 0; r < 3; ++r)
+    {
+        for (int c = 0; c < 3; ++c) o[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+        o[9 + r] = A[3 * r] * B[9] + A[3 * r + 1] * B[10] + A[3 * r + 2] * B[11] + A[9 + r];
+    }
+    return out;
+}
+
+Frame Inverse(const Frame& a)
+{
+    Frame out;
+    const double* A = a.data();
+    double* o = out.data();
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o[3 * r + c] = A[3 * c + r];
+    for (int r = 0; r < 3; ++r) o[9 + r] = -(o[3 * r] * A[9] + o[3 * r + 1] * A[10] + o[3 * r + 2] * A[11]);
+    return out;
+}
+
+void SkipNumbers(std::istream& in, int n, const std::string& what)
+{
+    double v;
+    for (int i = 0; i < n; ++i)
+        if (!(in >> v)) ThrowPretty("Malformed scene geometry: expected " + std::to_string(n) + " numbers for " + what);
+}
+}  // namespace
+
+void Scene::LoadScene(const std::string& scene_text, const Frame& offset)
+{
+    std::istringstream in(scene_text);
+    std::string line;
+    if (!std::getline(in, line)) ThrowPretty("Bad input stream when loading scene geometry");  // the scene name line
+    std::map<std::string, WorldObject> loaded;
+    while (true)
+    {
+        std::string marker;
+        if (!(in >> marker)) ThrowPretty("Bad input stream when loading marker in scene geometry");
+        if (marker == ".") break;
+        if (marker != "*") ThrowPretty("Unknown marker in scene geometry file: " + marker);
+        std::string name;
+        std::getline(in, name);
+        name = xml::Trim(name);
+        if (name.empty()) ThrowPretty("Bad input stream when loading object name in scene geometry");
+        // newer MoveIt files carry the object pose before the shape count: a line of seven numbers instead of one
+        std::string next;
+        do
+        {
+            if (!std::getline(in, next)) ThrowPretty("Bad input stream when loading shape count of '" + name + "'");
+        } while (xml::Trim(next).empty());
+        Frame object_pose = IdentityFrame();
+        std::vector<double> nums = ParseVector(next);
+        if (nums.size() == 7)
+        {
+            object_pose = PoseFromQuaternion(nums[0], nums[1], nums[2], nums[3], nums[4], nums[5], nums[6]);
+            int count = 0;
+            if (!(in >> count)) ThrowPretty("Bad input stream when loading shape count of '" + name + "'");
+            nums.assign(1, (double)count);
+        }
+        if (nums.size() != 1 || nums[0] < 0) ThrowPretty("Bad shape count for object '" + name + "' in scene geometry");
+        WorldObject obj;
+        for (int i = 0; i < (int)nums[0]; ++i)
+        {
+            std::string type;
+            if (!(in >> type)) ThrowPretty("Bad input stream when loading shape type of '" + name + "'");
+            if (type == "box") SkipNumbers(in, 3, type);
+            else if (type == "sphere") SkipNumbers(in, 1, type);
+            else if (type == "cylinder" || type == "cone") SkipNumbers(in, 2, type);
+            else if (type == "plane") SkipNumbers(in, 4, type);
+            else if (type == "mesh")
+            {
+                long nv = 0, nt = 0;
+                if (!(in >> nv >> nt) || nv < 0 || nt < 0) ThrowPretty("Malformed mesh in scene geometry");
+                SkipNumbers(in, (int)(3 * nv + 3 * nt), type);
+            }
+            else
+                ThrowPretty("Unknown shape type: '" + type + "'");
+            double p[7];
+            for (double& v : p)
+                if (!(in >> v)) ThrowPretty("Failed to read pose of a shape of '" + name + "' from scene geometry");
+            SkipNumbers(in, 4, "the shape colour");
+            obj.shape_poses.push_back(Compose(offset, Compose(object_pose, PoseFromQuaternion(p[0], p[1], p[2], p[3], p[4], p[5], p[6]))));
+        }
+        loaded[name] = obj;
+    }
+    for (auto& kv : loaded) world_objects_[kv.first] = kv.second;
+    RebuildEnvironment();
+}
+
+void Scene::LoadSceneFile(const std::string& file_name, const Frame& offset)
+{
+    LoadScene(Setup::LoadFile(Setup::ParsePath(file_name)), offset);
+}
+
+void Scene::CleanScene()
+{
+    world_objects_.clear();
+    RebuildEnvironment();
+}
+
+std::vector<std::string> Scene::GetWorldObjectNames() const
+{
+    std::vector<std::string> names;
+    for (const auto& kv : world_objects_) names.push_back(kv.first);
+    return names;
+}
+
+void Scene::RebuildEnvironment()
+{
+    // UpdateSceneFrames (scene.cpp:702-758): reset, then every world object in name order -- its frame is the first shape's pose,
+    // every shape hangs below it as "<name>_collision_<i>" -- and UpdateInternalFrames (scene.cpp:662-700): the custom links, then
+    // the trajectory generators again
+    kinematica_.ResetModel();
+    for (const auto& kv : world_objects_)
+    {
+        if (kv.second.shape_poses.empty()) continue;  // "Object with no shapes"
+        const Frame& origin = kv.second.shape_poses[0];
+        kinematica_.AddEnvironmentElement(kv.first, origin, "", false);
+        const Frame inv = Inverse(origin);
+        for (size_t i = 0; i < kv.second.shape_poses.size(); ++i)
+            kinematica_.AddEnvironmentElement(kv.first + "_collision_" + std::to_string(i), Compose(inv, kv.second.shape_poses[i]), kv.first, false);
+    }
+    for (const CustomLink& l : custom_links_) kinematica_.AddEnvironmentElement(l.name, l.transform, l.parent, false);
+    trajectories_.clear();
+    for (auto& kv : trajectory_tables_)
+    {
+        int idx = kinematica_.GetElementIndex(kv.first);
+        if (idx < 0) idx = kinematica_.AddEnvironmentElement(kv.first, IdentityFrame(), "", false);
+        trajectories_[kinematica_.MakeTrajectoryGenerated(idx)] = kv.second;
+    }
+    for (auto& kv : trajectory_generators_)
+    {
+        const int idx = kinematica_.GetElementIndex(kv.first);
+        if (idx < 0) ThrowPretty("Can't find link '" + kv.first + "'!");
+        kv.second.first = kinematica_.MakeTrajectoryGenerated(idx);
+    }
+    ++trajectory_version_;
+    UpdateTrajectoryGenerators(0.0);
 }
 
 void Scene::AddTrajectoryFrames(const std::string& link, const std::vector<Frame>& frames_per_timestep)
 {
     if (frames_per_timestep.empty()) ThrowPretty("Trajectory for '" + link + "' is empty");
     int idx = kinematica_.GetElementIndex(link);
-    if (idx < 0) idx = kinematica_.AddEnvironmentElement(link, IdentityFrame(), "", true);
+    if (idx < 0)
+    {
+        idx = kinematica_.AddEnvironmentElement(link, IdentityFrame(), "", false);
+        custom_links_.push_back({link, "", IdentityFrame()});
+    }
+    trajectory_generators_.erase(link);
+    trajectory_tables_[link] = frames_per_timestep;
     trajectories_[kinematica_.MakeTrajectoryGenerated(idx)] = frames_per_timestep;
     ++trajectory_version_;
+    UpdateTrajectoryGenerators(0.0);
 }
 
 void Scene::AddTrajectory(const std::string& link, const std::string& traj)
@@ -128,8 +331,10 @@ void Scene::AddTrajectory(const std::string& link, std::shared_ptr<Trajectory> t
     if (!traj || traj->GetDuration() == 0.0) ThrowPretty("The trajectory is empty!");
     const int idx = kinematica_.GetElementIndex(link);
     if (idx < 0) ThrowPretty("Can't find link '" + link + "'!");
+    trajectory_tables_.erase(link);
     trajectory_generators_[link] = std::make_pair(kinematica_.MakeTrajectoryGenerated(idx), traj);
     ++trajectory_version_;
+    UpdateTrajectoryGenerators(0.0);
 }
 
 std::shared_ptr<Trajectory> Scene::GetTrajectory(const std::string& link) const

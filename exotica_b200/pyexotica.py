@@ -242,6 +242,17 @@ class Scene(object):
     def add_object(self, name, transform=None, parent=""):
         _check(_host.lib().exo_host_scene_add_object(self._h, _s(name), _d(_offset(transform)), _s(parent)))
 
+    def load_scene(self, scene_text, offset=None):
+        """Scene::LoadScene: world objects from MoveIt ".scene" geometry text (each becomes a named frame)."""
+        _check(_host.lib().exo_host_scene_load_scene(self._h, _s(scene_text), _d(_offset(offset))))
+
+    def load_scene_file(self, file_name, offset=None):
+        """Scene::LoadSceneFile ({package} paths resolve through Setup.set_package_path)."""
+        _check(_host.lib().exo_host_scene_load_scene_file(self._h, _s(file_name), _d(_offset(offset))))
+
+    def clean_scene(self):
+        _check(_host.lib().exo_host_scene_clean(self._h))
+
     def add_trajectory(self, link, frames):
         """Scene::AddTrajectory: `frames` is either the reference's trajectory text ("radius\\n rows cols\\n time x y z [rot]...",
         sampled at t * tau by time-indexed problems) or an explicit table of [T][12] frames / [T][3|6|7] GetFrame vectors."""
@@ -274,7 +285,7 @@ class Scene(object):
         n = self.num_positions
         phi = np.zeros((self._n_frames, 12))
         jac = np.zeros((self._n_frames, n, 6))
-        _check(_host.lib().exo_host_scene_update(self._h, _d(x), int(x.size), _d(phi), _d(jac) if self._with_jacobian else None))
+        _check(_host.lib().exo_host_scene_update(self._h, _d(x), int(x.size), float(t), _d(phi), _d(jac) if self._with_jacobian else None))
         return phi, (np.ascontiguousarray(jac.transpose(0, 2, 1)) if self._with_jacobian else None)
 
     def update_batch(self, X, layout=LAYOUT_AOS_ROWMAJOR):
@@ -372,10 +383,20 @@ class PlanningProblem(object):
     def update(self, x, t=None):
         """UnconstrainedEndPoseProblem.update(x) / TimeIndexedProblem.update(x, t): one evaluation on the GPU."""
         x = np.ascontiguousarray(x, dtype=np.float64)
+        if self.time_indexed and t is None:
+            # AbstractTimeIndexedProblem::Update(x_trajectory) (abstract_time_indexed_problem.cpp:209-218): (T-1)*N values,
+            # timesteps 1..T-1 are evaluated, t = 0 keeps the start state's values
+            if x.size != (self.T - 1) * self.N:
+                raise ExoticaError("To update using the trajectory Update method, please use a trajectory of size N x (T-1) (%d), given: %d"
+                                   % (self.N * (self.T - 1), x.size))
+            phi = np.zeros((self.T, self.length_Phi))
+            jac = np.zeros((self.T, self.N, self.length_jacobian))
+            _check(_host.lib().exo_host_problem_update_trajectory(self._h, _d(x), int(x.size), _d(phi), _d(jac)))
+            self.Phi = [phi[k] for k in range(self.T)]
+            self.jacobian = [np.ascontiguousarray(jac[k].T) for k in range(self.T)]
+            return
         phi = np.zeros(self.length_Phi)
         jac = np.zeros((self.N, self.length_jacobian))
-        if self.time_indexed and t is None:
-            raise ExoticaError("TimeIndexedProblem.update needs a time index; use update_batch for whole trajectories")
         _check(_host.lib().exo_host_problem_update(self._h, _d(x), int(x.size), -1 if t is None else int(t), _d(phi), _d(jac)))
         if self.time_indexed:
             tt = int(t) if t >= 0 else self.T - 1

@@ -48,6 +48,11 @@ int exo_host_scene_get_model_state(exo_host_scene* scene, double* state /* [num 
 int exo_host_scene_set_model_state(exo_host_scene* scene, const double* state, int n);
 int exo_host_scene_num_model_joints(exo_host_scene* scene);
 int exo_host_scene_add_object(exo_host_scene* scene, const char* name, const double frame12[12], const char* parent);
+/* Scene::LoadScene / LoadSceneFile / CleanScene (scene.cpp:610-660): MoveIt ".scene" geometry text; every object becomes a frame
+ * (its first shape's pose) with one "<name>_collision_<i>" child per shape.  offset12 NULL = identity. */
+int exo_host_scene_load_scene(exo_host_scene* scene, const char* scene_text, const double offset12[12]);
+int exo_host_scene_load_scene_file(exo_host_scene* scene, const char* file_name, const double offset12[12]);
+int exo_host_scene_clean(exo_host_scene* scene);
 int exo_host_scene_add_trajectory(exo_host_scene* scene, const char* link, int T, const double* frames /*[T][12]*/);
 /* Scene::AddTrajectory(link, traj) (scene.cpp:922-935) with the reference's trajectory text format
  * ("radius\n rows cols\n time x y z [rotation]..." -- exotica_core/src/trajectory.cpp:51-68); time-indexed problems sample it
@@ -60,7 +65,7 @@ int exo_host_trajectory_sample(const char* trajectory, int n, const double* time
 /* KinematicTree::RequestFrames / Update / UpdateBatch: link names '\n'-joined, offsets [F][12] (NULL = identity) */
 int exo_host_scene_request_frames(exo_host_scene* scene, int n_frames, const char* links_a, const double* off_a,
                                   const char* links_b, const double* off_b, int with_jacobian);
-int exo_host_scene_update(exo_host_scene* scene, const double* x, int n, double* phi /*[F][12]*/, double* jac /*[F][6*N] col-major*/);
+int exo_host_scene_update(exo_host_scene* scene, const double* x, int n, double t, double* phi /*[F][12]*/, double* jac /*[F][6*N] col-major*/);
 int exo_host_scene_update_batch(exo_host_scene* scene, const double* x, int64_t n_evals, int layout, double* phi, double* jac);
 /* Scene.fk / Scene.jacobian at the current model state */
 int exo_host_scene_fk(exo_host_scene* scene, const char* link_a, const double* off_a, const char* link_b, const double* off_b, double out12[12]);
@@ -79,6 +84,10 @@ int exo_host_problem_start_state(exo_host_problem* problem, double* x);
 /* One evaluation: t < 0 -> UnconstrainedEndPoseProblem::Update(x); t >= 0 -> TimeIndexedProblem::Update(x, t).
  * phi[length_Phi], jac[length_jacobian x N] column-major (the Eigen::MatrixXd the reference exposes). */
 int exo_host_problem_update(exo_host_problem* problem, const double* x, int n, int t, double* phi, double* jac);
+/* AbstractTimeIndexedProblem::Update(x_trajectory) (abstract_time_indexed_problem.cpp:209-218): n = (T-1)*N values, timesteps
+ * 1..T-1 are evaluated (one launch); t = 0 keeps what the last Update(x, 0) left.  phi[T][length_Phi], jac[T][length_jacobian x N]
+ * column-major: the problem's Phi / jacobian members after the call. */
+int exo_host_problem_update_trajectory(exo_host_problem* problem, const double* x, int n, double* phi, double* jac);
 /* NEW batched PlanningProblem::Update: E evaluations (E = B*T for time-indexed problems), host buffers. */
 int exo_host_problem_update_batch(exo_host_problem* problem, const double* x, int64_t n_evals, int layout, double* phi, double* jac);
 int exo_host_problem_update_batch_device(exo_host_problem* problem, const double* d_x, int64_t n_evals, int layout, double* d_phi,

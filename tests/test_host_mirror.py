@@ -19,7 +19,8 @@ def _scene_init(robot, group):
     return ("exotica/Scene", {"Name": "Scene", "JointGroup": group, "URDF": urdf, "SRDF": srdf})
 
 
-@pytest.mark.parametrize("robot,group", [("lwr_simplified", "arm"), ("test_robot", "arm"), ("valkyrie_sim", "whole_body")])
+@pytest.mark.parametrize("robot,group", [("lwr_simplified", "arm"), ("test_robot", "arm"), ("valkyrie_sim", "whole_body"),
+                                         ("planar_gripper", "mobile"), ("planar_gripper", "arm_only")])
 def test_loader_matches_the_oracle_tree(oracle_lib, robot, group):
     ref = oracle_lib.load_robot(*robot_paths(robot), joint_group=group)
     scene = exo.Setup.create_scene(_scene_init(robot, group))
@@ -34,6 +35,22 @@ def test_loader_matches_the_oracle_tree(oracle_lib, robot, group):
     assert np.max(np.abs(tree["f_tip"] - flat["f_tip"].reshape(n, 12))) <= 1e-15
     lim = scene.get_kinematic_tree().get_joint_limits()
     assert np.array_equal(lim[:, 0], ref.lower) and np.array_equal(lim[:, 1], ref.upper)
+
+
+def test_planar_base_and_mimic_joints_through_the_product_loader():
+    """kinematic_tree.cpp:241-256 (planar base: virtual x / y / theta elements, root link id 4) and :342-356 (mimic joints)."""
+    scene = exo.Setup.create_scene(_scene_init("planar_gripper", "mobile"))
+    kt = scene.get_kinematic_tree()
+    assert kt.get_model_base_type() == "PLANAR" and kt.get_controlled_base_type() == "PLANAR"
+    assert kt.get_controlled_joint_names() == ["base_joint/x", "base_joint/y", "base_joint/theta", "shoulder", "elbow", "grip"]
+    tree = kt.get_tree()
+    assert tree["link_name"][:5] == ["odom", "base_joint/x", "base_joint/y", "base_joint/theta", "chassis"]
+    assert list(tree["id"][:5]) == [-1, 0, 1, 2, 4]  # id 3 stays unused, like 6 for a floating base
+    lim = kt.get_joint_limits()
+    assert lim[0, 0] == -1e20 and lim[1, 1] == 1e20 and abs(lim[2, 1] - np.pi) < 1e-15 and tuple(lim[5]) == (0.0, 0.04)
+    fixed = exo.Setup.create_scene(_scene_init("planar_gripper", "arm_only")).get_kinematic_tree()
+    assert fixed.get_model_base_type() == "PLANAR" and fixed.get_controlled_base_type() == "FIXED"
+    assert fixed.get_controlled_joint_names() == ["shoulder", "elbow"]
 
 
 def test_lwr_names_and_factories():
@@ -479,3 +496,116 @@ def test_reference_example_files_load_unmodified():
         if os.path.exists(path):
             p = exo.Setup.load_problem(path)
             assert p.N == 7 and p.T >= 3
+
+
+EXAMPLES = os.path.join(os.path.dirname(ROBOTS), "exotica_examples")  # tests/golden/make_config_fixtures.py
+
+
+def test_scene_file_parser_and_environment_order():
+    """Scene::LoadScene (scene.cpp:610-645) + UpdateSceneFrames (:702-758): world objects in name order, each followed by its
+    "<name>_collision_<i>" children, then the custom links; both MoveIt file formats; errors are loud."""
+    scene = exo.Setup.create_scene(_scene_init("lwr_simplified", "arm"))
+    n0 = len(scene.get_kinematic_tree().get_tree()["id"])
+    scene.add_object("Custom", [1, 2, 3])
+    text = ("(S)+\n* Zed\n1\nsphere\n0.1\n1 0 0\n0 0 0 1\n0 0 0 0\n"
+            "* Box two\n2\nbox\n0.1 0.2 0.3\n0 0 0.5\n0 0 0.7071067811865476 0.7071067811865476\n0 0 0 0\n"
+            "cylinder\n0.1 0.4\n0 1 0.5\n0 0 0 1\n1 0 0 1\n.\n")
+    scene.load_scene(text)
+    tree = scene.get_kinematic_tree().get_tree()
+    assert tree["link_name"][n0:] == ["Box two", "Box two_collision_0", "Box two_collision_1", "Zed", "Zed_collision_0", "Custom"]
+    assert list(tree["id"][n0:]) == list(range(n0, n0 + 6))
+    box = tree["link_name"].index("Box two")
+    assert list(tree["parent"][n0:]) == [0, box, box, 0, box + 3, 0]
+    f = tree["f_tip"]
+    assert np.allclose(f[box], [0, -1, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0.5], atol=1e-15)          # Rz(90 deg), first shape's pose
+    assert np.allclose(f[box + 1], [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], atol=1e-15)         # first shape sits at the object frame
+    assert np.allclose(f[box + 2][9:], [1, 0, 0], atol=1e-15)                                # (0, 1, 0) seen from the rotated frame
+    # the newer format carries an object pose line; an offset moves everything
+    scene.load_scene("(S)+\n* New\n0 0 1 0 0 0 1\n1\nbox\n1 1 1\n0.5 0 0\n0 0 0 1\n0 0 0 0\n.\n", offset=[0, 2, 0])
+    tree = scene.get_kinematic_tree().get_tree()
+    assert np.allclose(tree["f_tip"][tree["link_name"].index("New")][9:], [0.5, 2, 1])
+    assert tree["link_name"][-1] == "Custom"
+    scene.clean_scene()
+    assert scene.get_kinematic_tree().get_tree()["link_name"][n0:] == ["Custom"]
+    for bad in ("(S)+\n* A\n1\ntorus\n1\n0 0 0\n0 0 0 1\n0 0 0 0\n.\n", "(S)+\n# A\n.\n", "(S)+\n* A\n1\nbox\n1 1\n"):
+        with pytest.raises(exo.ExoticaError):
+            scene.load_scene(bad)
+
+
+def test_reference_configs_load_through_the_fixture_package():
+    exo.Setup.set_package_path("exotica_examples", EXAMPLES)
+    ik = exo.Setup.load_problem(os.path.join(EXAMPLES, "resources", "configs", "example_ik.xml"))
+    assert (ik.N, ik.length_Phi, ik.length_jacobian, ik.T) == (7, 6, 6, 1)
+    col = exo.Setup.load_problem(os.path.join(EXAMPLES, "resources", "configs", "example_sphere_collision.xml"))
+    assert (col.N, col.length_Phi, col.length_jacobian, col.T) == (7, 8, 8, 100)
+    names = col.get_scene().get_kinematic_tree().get_tree()["link_name"]
+    assert names[-2:] == ["Obstacle", "Obstacle_collision_0"]
+    assert abs(col.get_scene().get_trajectory("Obstacle").get_duration() - 3.0) < 1e-12
+
+
+@pytest.mark.gpu
+def test_example_sphere_collision_xml_matches_the_oracle(oracle_lib):
+    """BASELINE.json configs[4]'s own fixture, unmodified: LoadScene + Trajectory File + JointPose + SphereCollision (19 spheres)."""
+    from helpers import max_abs_err
+    from oracle.trajectory import Trajectory as RefTrajectory
+    exo.Setup.set_package_path("exotica_examples", EXAMPLES)
+    prob = exo.Setup.load_problem(os.path.join(EXAMPLES, "resources", "configs", "example_sphere_collision.xml"))
+    T, tau, B = prob.T, 0.03, 6
+    tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+    tree.add_environment_element("Obstacle", generated_slot=0)
+    orc = oracle_lib.Oracle(tree)
+    robot = [("lwr_arm_7_link", None), ("lwr_arm_6_link", None)]
+    for k in (5, 4, 3, 2, 1):
+        robot += [("lwr_arm_%d_link" % k, [0, 0, 0.1]), ("lwr_arm_%d_link" % k, None)]
+    sph = [dict({"Link": l, "Radius": 0.1, "Group": "Robot"}, **({"LinkOffset": o} if o else {})) for l, o in robot]
+    sph += [{"Link": "Obstacle", "Radius": 0.15, "Group": "Obstacle", "LinkOffset": [0, y, 0]} for y in (-0.3, -0.2, -0.1, 0, 0.1, 0.2, 0.3)]
+    ref = [2.16939, 1.313509, -2.2954, 1.94413, -0.276843, 0.567194, 0]
+    maps = [{"type": "JointPose", "JointRef": ref}, {"type": "SphereCollision", "Precision": 0.1, "EndEffector": sph}]
+    orc.set_problem(maps)
+    with open(os.path.join(EXAMPLES, "resources", "scenes", "example_moving_obstacle.traj")) as f:
+        traj = RefTrajectory(f.read())
+    gen = np.array([traj.get_position(t * tau) for t in range(T)]).reshape(T, 1, 12)
+    X = np.random.default_rng(9).uniform(orc.lower, orc.upper, size=(B, T, 7))
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X.reshape(B * T, 7), T=T, generated=gen)
+    assert max_abs_err(phi, phi_ref) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    # AbstractTimeIndexedProblem::Update(x_trajectory): (T-1)*N values, t = 1..T-1 evaluated, t = 0 untouched (App. C #9)
+    prob.update(X[0, 0], 0)
+    prob.update(X[1, 1:].ravel())
+    for t in range(1, T):
+        assert max_abs_err(prob.Phi[t], phi_ref[T + t]) <= 1e-10 and max_abs_err(prob.jacobian[t], jac_ref[T + t]) <= 1e-10
+    assert max_abs_err(prob.Phi[0], phi_ref[0]) <= 1e-10
+    with pytest.raises(exo.ExoticaError, match="trajectory Update method"):
+        prob.update(X[0].ravel())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["mobile", "arm_only"])
+def test_planar_base_and_mimic_joints_on_the_gpu(oracle_lib, group):
+    """The planar / mimic fixture from the product loader through the compiler and the kernels: mimic joints move in FK but own no
+    Jacobian column, the planar base contributes x, y, theta columns; uncontrolled joints hold the model state."""
+    from helpers import angle_entries, max_abs_err
+    frames = [("exotica/Frame", {"Link": "finger_right", "LinkOffset": "0 0 0.03"}), ("exotica/Frame", {"Link": "palm", "Base": "upper"})]
+    com = ("exotica/CenterOfMass", {"Name": "CoM"})
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "p", "PlanningScene": _scene_init("planar_gripper", group),
+                                                    "Maps": [("exotica/EffFrame", {"Name": "Eff", "Type": "Quaternion", "EndEffector": frames}),
+                                                             ("exotica/JointLimit", {"Name": "JL", "SafePercentage": 0.1}), com],
+                                                    "Cost": [("exotica/Task", {"Task": "Eff"}), ("exotica/Task", {"Task": "JL"}), ("exotica/Task", {"Task": "CoM"})]})
+    prob = exo.Setup.create_problem(init)
+    ref_tree = oracle_lib.load_robot(*robot_paths("planar_gripper"), joint_group=group)
+    orc = oracle_lib.Oracle(ref_tree)
+    maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "finger_right", "LinkOffset": [0, 0, 0.03]}, {"Link": "palm", "Base": "upper"}]},
+            {"type": "JointLimit", "SafePercentage": 0.1}]
+    orc.set_problem(maps)
+    rng = np.random.default_rng(12)
+    lo, hi = np.where(orc.lower < -1e19, -2.0, orc.lower) - 0.05, np.where(orc.upper > 1e19, 2.0, orc.upper) + 0.05
+    X = rng.uniform(lo, hi, size=(257, orc.n))
+    phi, jac = prob.update_batch(X)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    lp, lj = orc.length_phi, orc.length_jacobian
+    assert max_abs_err(phi[:, :lp], phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac[:, :lj], jac_ref) <= 1e-10
+    assert prob.length_Phi == lp + 3 and np.isfinite(phi).all() and np.isfinite(jac).all()
+    if group == "mobile":
+        # the finger's mimic partner moves opposite to grip: d(finger_right)/d(grip) exists only through ... nothing (no column for
+        # the mimic element), while d(palm wrt upper)/d(base) vanishes identically
+        assert not jac[:, 6:12, 0:3].any()
