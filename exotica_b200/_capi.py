@@ -44,7 +44,9 @@ class CostDesc(ctypes.Structure):
 
 class IkParams(ctypes.Structure):
     _fields_ = [("max_iterations", ctypes.c_int32), ("tolerance", ctypes.c_double), ("regularization_rate", ctypes.c_double),
-                ("maximum_regularization", ctypes.c_double), ("gradient_tolerance", ctypes.c_double), ("step_tolerance", ctypes.c_double)]
+                ("maximum_regularization", ctypes.c_double), ("gradient_tolerance", ctypes.c_double), ("step_tolerance", ctypes.c_double),
+                ("max_step", ctypes.c_double), ("threshold_regularization_increase", ctypes.c_double),
+                ("threshold_regularization_decrease", ctypes.c_double), ("minimum_regularization", ctypes.c_double)]
 
 
 class ExoticaError(RuntimeError):
@@ -595,7 +597,8 @@ class Problem(object):
         check(lib().exo_problem_hessian_batch(self.h, d_x, d_jac, int(n_evals), int(T), int(layout), d_hess, stream))
 
     def ik_solve_batch(self, Q0, max_iterations=100, tolerance=1e-5, regularization_rate=1e-9, maximum_regularization=1e9,
-                       gradient_tolerance=1e-9, step_tolerance=1e-5):
+                       gradient_tolerance=1e-9, step_tolerance=1e-5, max_step=0.0, threshold_increase=0.1, threshold_decrease=0.5,
+                       minimum_regularization=1e-12):
         """Multi-start IK: Q0[E][N] start states -> (Q[E][N], cost[E], iterations[E], termination[E]).  Needs set_cost(T=1)."""
         Q0 = np.ascontiguousarray(Q0, dtype=np.float64)
         E, N = Q0.shape
@@ -603,7 +606,8 @@ class Problem(object):
         di, dt = DeviceBuffer((E + 1) // 2 + 1), DeviceBuffer((E + 1) // 2 + 1)  # int32 arrays in double-sized storage
         dq.upload(Q0.T)
         prm = IkParams(int(max_iterations), float(tolerance), float(regularization_rate), float(maximum_regularization),
-                       float(gradient_tolerance), float(step_tolerance))
+                       float(gradient_tolerance), float(step_tolerance), float(max_step), float(threshold_increase), float(threshold_decrease),
+                       float(minimum_regularization))
         check(lib().exo_problem_ik_solve_batch(self.h, dq.ptr, E, ctypes.byref(prm), dc.ptr, di.ptr, dt.ptr, None))
         check(lib().exo_device_synchronize())
         Q = np.ascontiguousarray(dq.download((N, E)).T)

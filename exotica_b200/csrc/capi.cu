@@ -1483,7 +1483,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         p->d_ik = nullptr;
         p->d_ik_i = nullptr;
         p->ik_capacity = 0;
-        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 3) * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 4) * sizeof(double)));
         CUDA_TRY(cudaMalloc((void**)&p->d_ik_i, ((size_t)2 * E + 4) * sizeof(int32_t)));
         p->ik_capacity = E;
     }
@@ -1506,6 +1506,13 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     K.err_prev = w; w += E;
     K.stop = w; w += E;
     K.lambda = w; w += E;
+    K.steplen = w; w += E;
+    K.single_iteration = prm->max_iterations == 1 ? 1 : 0;
+    K.max_step = prm->max_step;
+    K.th_stepinc = prm->threshold_regularization_increase;
+    K.th_stepdec = prm->threshold_regularization_decrease;
+    K.regmin = prm->minimum_regularization;
+    const bool max_step_mode = K.single_iteration && K.max_step != 0.0;  // one clamped step instead of the line search
     K.cost = d_cost;
     K.active = p->d_ik_i;
     K.ls_done = p->d_ik_i + E;
@@ -1541,6 +1548,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         G.ct = C.ct;
         G.T = 1; G.t_first = 0; G.T_goal = C.T_goal; G.n_maps = C.n_maps; G.length_phi = C.length_phi; G.n_rot = C.n_rot;
         LS.q = d_q; LS.q_trial = K.q_trial; LS.qd = K.qd; LS.err_prev = K.err_prev; LS.cost = d_cost; LS.active = K.active; LS.ls_done = K.ls_done;
+        LS.steplen = K.steplen;
     }
     // Chain programs: the line search of every iteration is one fused kernel (exo_problem_set_kernel(1) takes the trial /
     // update / accept launches instead).  EXO_IK_ONE_LAUNCH=1 runs the WHOLE solve as one launch, every lane iterating on its
@@ -1560,7 +1568,11 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         rc = launch(p, d_q, E, E, 1, EXO_LAYOUT_SOA, d_phi, d_jac, stream, false);  // prob_->Update(q_)
         if (rc != EXO_OK) return rc;
         CUDA_TRY(launch_ik_step(K, C, stream));
-        if (fused_ls)
+        if (max_step_mode)
+        {
+            // exo_ik_step_kernel has clamped the step and taken it (ScaleToStepSize; q_ -= qd_)
+        }
+        else if (fused_ls)
         {
             // chain programs: the ten trial states are evaluated in registers by one kernel
             chain_bind(p->chain, K.q_trial, nullptr, nullptr, E, 1, E, 1, E, 1, (int64_t)N * E, E);
@@ -1570,7 +1582,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         else
         for (int ai = 0; ai < 10; ++ai)
         {
-            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+            const double alpha = ai == 0 ? 1.0 : 0.1 - (9 - ai) * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1), see ik_alpha()
             CUDA_TRY(launch_ik_trial(K, alpha, stream));
             rc = launch(p, K.q_trial, E, E, 1, EXO_LAYOUT_SOA, d_phi, nullptr, stream, false);  // prob_->Update(q_tmp): FK only
             if (rc != EXO_OK) return rc;

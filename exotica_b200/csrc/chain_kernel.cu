@@ -891,10 +891,11 @@ __global__ void __maxnreg__(128) exo_chain_ik_linesearch_kernel(const __grid_con
     const double err_prev = L.err_prev[e];
     for (int ai = 0; ai < 10; ++ai)
     {
-        const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+        const double alpha = ik_alpha(ai);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
         for (int c = 0; c < N; ++c) L.q_trial[(int64_t)c * E + e] = L.q[(int64_t)c * E + e] - alpha * L.qd[(int64_t)c * E + e];
         const double error = chain_cost_only<NJ, ALLREV>(P, G, xe, 0);
         L.cost[e] = error;  // error_: the cost at the last state evaluated
+        L.steplen[e] = alpha;
         if (error < err_prev)
         {
             for (int c = 0; c < N; ++c)
@@ -983,12 +984,13 @@ __global__ void __maxnreg__(168) exo_chain_ik_solve_kernel(const __grid_constant
         chain_eval_one<NJ, ALLREV>(P, xe, phi_e, jac_e);  // prob_->Update(q_)
         if (!ik_step_one<0>(K, C, e)) break;
         const double err_prev = L.err_prev[e];
-        for (int ai = 0; ai < 10; ++ai)
+        for (int ai = 0; ai < 10 && !L.ls_done[e]; ++ai)  // (the MaxStep mode has taken its step already)
         {
-            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
+            const double alpha = ik_alpha(ai);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1)
             for (int c = 0; c < N; ++c) L.q_trial[(int64_t)c * E + e] = L.q[(int64_t)c * E + e] - alpha * L.qd[(int64_t)c * E + e];
             const double error = chain_cost_only<NJ, ALLREV>(P, G, xt, 0);
             L.cost[e] = error;
+            L.steplen[e] = alpha;
             if (error < err_prev)
             {
                 for (int c = 0; c < N; ++c)

@@ -8,6 +8,15 @@ namespace exo
 {
 namespace dev
 {
+// alpha_space_ = Eigen::VectorXd::LinSpaced(10, 1.0, 0.1) (ik_solver.cpp:56).  Eigen 3.3 (external; the version Ubuntu 18.04 / 20.04
+// ship) evaluates a descending LinSpaced from the high end, (i == 0) ? low : high - (size - 1 - i) * step with step = (high - low) / 9;
+// separate multiply and subtract (no FMA) like the host code.
+static __device__ __forceinline__ double ik_alpha(int ai)
+{
+    const double step = (0.1 - 1.0) / 9.0;
+    return ai == 0 ? 1.0 : __dsub_rn(0.1, __dmul_rn((double)(9 - ai), step));
+}
+
 // error, damped weighted pseudo-inverse step qd (Cholesky; lambda x10 on failure), |cJ|_F -- from the Phi / J of the current state.
 // Returns false when the configuration stops here (FunctionTolerance or Divergence).
 // LJT > 0: the task space has exactly LJT rows (6: one EffFrame, the usual IK problem) -- every loop unrolls and the LJT x LJT
@@ -130,6 +139,20 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
         K.qd[(int64_t)c * E + e] = K.w_inv[c] * acc;
     }
     K.stop[e] = sqrt(stop2);
+    if (K.single_iteration && K.max_step != 0.0)
+    {
+        // ScaleToStepSize + q_ -= qd_ (ik_solver.cpp:139-143,235-243): no line search in the interactive one-step mode
+        double max_vel = 0.0;
+        for (int c = 0; c < N; ++c) max_vel = fmax(max_vel, fabs(K.qd[(int64_t)c * E + e]));
+        for (int c = 0; c < N; ++c)
+        {
+            double v = K.qd[(int64_t)c * E + e];
+            if (max_vel > K.max_step) v = v * K.max_step / max_vel;
+            K.qd[(int64_t)c * E + e] = v;
+            K.q[(int64_t)c * E + e] -= v;
+        }
+        K.ls_done[e] = 1;
+    }
     return true;
 }
 
@@ -154,6 +177,30 @@ static __device__ __forceinline__ bool ik_finish_one(const IkParams& K, int64_t 
         K.termination[e] = IK_TERM_GRADIENT_TOLERANCE;
         K.active[e] = 0;
         return false;
+    }
+    if (K.single_iteration && K.max_step == 0.0)
+    {
+        // adapt the regularisation to the step length the line search ended on (ik_solver.cpp:187-199; ik_solver.h:81-97)
+        const double steplength = K.steplen[e];
+        double lambda = K.lambda[e];
+        if (steplength > K.th_stepdec)
+        {
+            lambda /= 10.0;
+            if (lambda < K.regmin) lambda = K.regmin;
+        }
+        if (steplength <= K.th_stepinc)
+        {
+            lambda *= 10.0;
+            if (lambda > K.regmax) lambda = K.regmax;
+            if (lambda == K.regmax)
+            {
+                K.lambda[e] = lambda;
+                K.termination[e] = IK_TERM_DIVERGENCE;
+                K.active[e] = 0;
+                return false;
+            }
+        }
+        K.lambda[e] = lambda;
     }
     if (last_iteration)
     {

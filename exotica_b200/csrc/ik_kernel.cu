@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(128) exo_ik_accept_kernel(const __grid_constan
     if (e >= K.n_evals || !K.active[e] || K.ls_done[e]) return;
     const double error = ik_cost(C, e);
     K.cost[e] = error;  // error_: the cost at the last state evaluated
+    K.steplen[e] = alpha;
     if (error < K.err_prev[e])
     {
         for (int c = 0; c < K.n_ctrl; ++c)
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(128) exo_ik_init_kernel(const __grid_constant_
     K.lambda[e] = lambda0;
     K.cost[e] = 0.0;
     K.stop[e] = 0.0;
+    K.steplen[e] = 0.0;
 }
 }  // namespace
 

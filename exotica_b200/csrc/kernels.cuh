@@ -158,6 +158,7 @@ struct ChainLineSearchParams
     double* cost;            // [E] error at the last state evaluated
     const int32_t* active;   // [E]
     int32_t* ls_done;        // [E]
+    double* steplen;         // [E] steplength_: the last alpha tried (read by the MaxIterations == 1 regularisation adaptation)
 };
 cudaError_t chain_ik_linesearch_launch(const ChainParams& P, const ChainGradParams& G, const ChainLineSearchParams& L, cudaStream_t stream);
 struct IkParams;
@@ -233,6 +234,11 @@ struct IkParams
     int64_t n_evals;
     int32_t n_ctrl, length_jac;
     double tolerance, step_tolerance, gradient_tolerance, regmax;
+    // MaxIterations == 1 (ik_solver.cpp:139-143,187-199): MaxStep != 0 replaces the line search by one clamped step; MaxStep == 0
+    // adapts lambda from the accepted step length and stops with Divergence when it reaches MaximumRegularization
+    double max_step, th_stepinc, th_stepdec, regmin;
+    int32_t single_iteration, pad0;
+    double* steplen;      // [E] steplength_
     const double* jac;    // [LJ][N][E] of the current states
     double* q;            // [N][E] current states (in / out)
     double* q_trial;      // [N][E]

@@ -523,8 +523,10 @@ class IKSolver(object):
         self.maximum_regularization = float(props.get("MaximumRegularization", 1e9))
         self.gradient_tolerance = float(props.get("GradientToleranceConvergenceThreshold", 1e-9))
         self.step_tolerance = float(props.get("StepToleranceConvergenceThreshold", 1e-5))
-        if float(props.get("MaxStep", 0.0)) != 0.0:
-            raise ExoticaError("IKSolver: the MaxStep mode is not available on the batched path")
+        self.max_step = float(props.get("MaxStep", 0.0))  # only used if MaxIterations == 1 (ik_solver.in)
+        self.minimum_regularization = float(props.get("MinimumRegularization", 1e-12))
+        self.threshold_increase = float(props.get("ThresholdRegularizationIncrease", 0.1))
+        self.threshold_decrease = float(props.get("ThresholdRegularizationDecrease", 0.5))
         self.problem = None
 
     def specify_problem(self, problem):
@@ -539,7 +541,8 @@ class IKSolver(object):
         Q0 = np.ascontiguousarray(Q0, dtype=np.float64).reshape(-1, self.problem.N)
         E = Q0.shape[0]
         prm = _capi.IkParams(self.max_iterations, self.tolerance, self.regularization_rate, self.maximum_regularization,
-                             self.gradient_tolerance, self.step_tolerance)
+                             self.gradient_tolerance, self.step_tolerance, self.max_step, self.threshold_increase, self.threshold_decrease,
+                             self.minimum_regularization)
         Q, cost = np.empty_like(Q0), np.empty(E)
         it, term = np.zeros(E, dtype=np.int32), np.zeros(E, dtype=np.int32)
         _check(_host.lib().exo_host_problem_ik_solve_batch(self.problem._h, Q0.ctypes.data, E, ctypes.byref(prm), Q.ctypes.data, cost.ctypes.data,

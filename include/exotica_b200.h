@@ -367,7 +367,10 @@ int exo_problem_hessian_batch(exo_problem* problem, const double* d_x, const dou
  *     UnconstrainedEndPoseProblem, for n_evals independent start states at once (multi-start IK): damped weighted
  *     pseudo-inverse step (Cholesky of S J W^-1 J^T S + lambda I, lambda x10 on failure), backtracking line search over
  *     alpha = linspace(1, 0.1, 10), the reference's termination tests.  Parameters: init/ik_solver.in + MaxIterations of
- *     exotica_core/init/motion_solver.in.  The MaxStep mode (MaxIterations == 1) is not supported.
+ *     exotica_core/init/motion_solver.in.  MaxIterations == 1 (the reference's interactive mode, exotica_examples/resources/configs/
+ *     example_ik.xml:5) follows ik_solver.cpp:139-143,187-199: with MaxStep != 0 the line search is replaced by one step clamped to
+ *     MaxStep per joint; with MaxStep == 0 lambda is adapted from the accepted step length and reaching MaximumRegularization ends
+ *     the solve with Divergence.
  * Requires exo_problem_set_cost (T = 1: rho, goal, W).  d_q: SoA [N][n_evals] start states in, solutions out.  d_cost[n_evals]:
  * cost at the returned state; d_iterations[n_evals]; d_termination[n_evals]: exotica::TerminationCriterion values
  * (planning_problem.h:49-62: 0 IterationLimit, 2 StepTolerance, 3 FunctionTolerance, 4 GradientTolerance, 5 Divergence). */
@@ -379,6 +382,10 @@ typedef struct
     double maximum_regularization;   /* MaximumRegularization = 1e9 */
     double gradient_tolerance;       /* GradientToleranceConvergenceThreshold = 1e-9 */
     double step_tolerance;           /* StepToleranceConvergenceThreshold = 1e-5 */
+    double max_step;                         /* MaxStep = 0 (only read when max_iterations == 1) */
+    double threshold_regularization_increase;/* ThresholdRegularizationIncrease = 0.1 */
+    double threshold_regularization_decrease;/* ThresholdRegularizationDecrease = 0.5 */
+    double minimum_regularization;           /* MinimumRegularization = 1e-12 */
 } exo_ik_params;
 int exo_problem_ik_solve_batch(exo_problem* problem, double* d_q, int64_t n_evals, const exo_ik_params* params, double* d_cost,
                                int32_t* d_iterations, int32_t* d_termination, void* stream);

@@ -1742,6 +1742,18 @@ static double ik_cost_at(exo_oracle* o, const double* q, const double* rho, cons
 int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
                         double lambda, double regmax, double gradient_tolerance, double step_tolerance, double* cost_out, int* iterations_out)
 {
+    /* init/ik_solver.in defaults of the parameters that only matter when MaxIterations == 1 */
+    return exo_oracle_ik_solve_ex(o, q, rho, goal, W, max_iterations, tolerance, lambda, regmax, gradient_tolerance, step_tolerance, 0.0, 0.1, 0.5,
+                                  1e-12, cost_out, iterations_out, NULL);
+}
+
+/* + MaxStep, ThresholdRegularizationIncrease / Decrease, MinimumRegularization (ik_solver.cpp:139-143,187-199; ik_solver.h:81-97);
+ * lambda_out: lambda_ when Solve returns. */
+int exo_oracle_ik_solve_ex(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
+                           double lambda, double regmax, double gradient_tolerance, double step_tolerance, double max_step, double th_stepinc,
+                           double th_stepdec, double regmin, double* cost_out, int* iterations_out, double* lambda_out)
+{
+    double steplength = 0.0; /* steplength_ (a member the reference never initialises; 0 here) */
     const int N = o->n_ctrl, lp = o->length_phi, lj = o->length_jac;
     double* phi = (double*)malloc((size_t)(lp + 1) * sizeof(double));
     double* jac = (double*)malloc((size_t)(lj + 1) * N * sizeof(double));
@@ -1838,9 +1850,22 @@ int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const doubl
             for (r = 0; r < lj; ++r) acc += cj[(size_t)r * N + c] * z[r];
             qd[c] = (W ? 1.0 / W[c] : 1.0) * acc;
         }
+        if (max_iterations == 1 && max_step != 0.0)
+        {
+            /* ScaleToStepSize (ik_solver.cpp:235-243), then q_ -= qd_: no line search */
+            double max_vel = 0.0;
+            for (c = 0; c < N; ++c) max_vel = fabs(qd[c]) > max_vel ? fabs(qd[c]) : max_vel;
+            if (max_vel > max_step)
+                for (c = 0; c < N; ++c) qd[c] = qd[c] * max_step / max_vel;
+            for (c = 0; c < N; ++c) q[c] -= qd[c];
+        }
+        else
         for (ai = 0; ai < 10; ++ai)
         {
-            const double alpha = 1.0 + ai * ((0.1 - 1.0) / 9.0); /* LinSpaced(10, 1.0, 0.1) */
+            /* Eigen::VectorXd::LinSpaced(10, 1.0, 0.1) (ik_solver.cpp:56); Eigen 3.3 (external) evaluates a descending LinSpaced
+               from the high end: (i == 0) ? low : high - (size - 1 - i) * step */
+            const double alpha = ai == 0 ? 1.0 : 0.1 - (9 - ai) * ((0.1 - 1.0) / 9.0);
+            steplength = alpha;
             for (c = 0; c < N; ++c) qt[c] = q[c] - alpha * qd[c];
             error = ik_cost_at(o, qt, rho, goal, phi, jac, z /* scratch */);
             if (error < error_prev)
@@ -1866,7 +1891,25 @@ int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const doubl
             ++it;
             break;
         }
+        /* adapt the regularisation to the step length (ik_solver.cpp:187-199) */
+        if (max_iterations == 1 && max_step == 0.0 && steplength > th_stepdec)
+        {
+            lambda /= 10.0;
+            if (lambda < regmin) lambda = regmin;
+        }
+        if (max_iterations == 1 && max_step == 0.0 && steplength <= th_stepinc)
+        {
+            lambda *= 10.0;
+            if (lambda > regmax) lambda = regmax;
+            if (lambda == regmax)
+            {
+                term = 5; /* Divergence */
+                ++it;
+                break;
+            }
+        }
     }
+    if (lambda_out) *lambda_out = lambda;
     if (cost_out) *cost_out = ik_cost_at(o, q, rho, goal, phi, jac, yd);
     if (iterations_out) *iterations_out = it;
     free(phi); free(jac); free(yd); free(cj); free(A); free(L); free(z); free(qd); free(qt); free(srow);

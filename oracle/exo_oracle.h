@@ -145,6 +145,9 @@ int exo_oracle_problem_hessian(exo_oracle* o, const double* x, double* hess);
 /* ---- IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) ---- */
 int exo_oracle_ik_solve(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
                         double lambda, double regmax, double gradient_tolerance, double step_tolerance, double* cost_out, int* iterations_out);
+int exo_oracle_ik_solve_ex(exo_oracle* o, double* q, const double* rho, const double* goal, const double* W, int max_iterations, double tolerance,
+                           double lambda, double regmax, double gradient_tolerance, double step_tolerance, double max_step, double th_stepinc,
+                           double th_stepdec, double regmin, double* cost_out, int* iterations_out, double* lambda_out);
 
 #ifdef __cplusplus
 }

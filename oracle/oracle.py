@@ -80,6 +80,7 @@ def lib():
         L.exo_oracle_problem_hessian.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.exo_oracle_ik_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                           ctypes.c_double, ctypes.c_double, _dp, _ip]
+        L.exo_oracle_ik_solve_ex.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, ctypes.c_int] + [ctypes.c_double] * 9 + [_dp, _ip, _dp]
         L.exo_oracle_get_rotation.argtypes = [_dp, ctypes.c_int, _dp]
         L.exo_oracle_problem_ydiff.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.exo_oracle_trajectory_cost.restype = ctypes.c_double
@@ -296,7 +297,8 @@ class Oracle(object):
 
 
     def ik_solve(self, q0, rho, goal=None, W=None, max_iterations=100, tolerance=1e-5, regularization_rate=1e-9, maximum_regularization=1e9,
-                 gradient_tolerance=1e-9, step_tolerance=1e-5):
+                 gradient_tolerance=1e-9, step_tolerance=1e-5, max_step=0.0, threshold_increase=0.1, threshold_decrease=0.5,
+                 minimum_regularization=1e-12):
         """IKSolver::Solve from q0: returns (q, cost, iterations, termination)."""
         q = np.ascontiguousarray(q0, dtype=np.float64).copy()
         rho = np.ascontiguousarray(rho, dtype=np.float64)
@@ -304,9 +306,12 @@ class Oracle(object):
         Wp = _d(np.ascontiguousarray(W, dtype=np.float64)) if W is not None else None
         cost = ctypes.c_double(0)
         iters = ctypes.c_int(0)
-        term = lib().exo_oracle_ik_solve(self.h, _d(q), _d(rho), _d(goal), Wp, int(max_iterations), float(tolerance), float(regularization_rate),
-                                         float(maximum_regularization), float(gradient_tolerance), float(step_tolerance),
-                                         ctypes.byref(cost), ctypes.byref(iters))
+        lam = ctypes.c_double(0)
+        term = lib().exo_oracle_ik_solve_ex(self.h, _d(q), _d(rho), _d(goal), Wp, int(max_iterations), float(tolerance), float(regularization_rate),
+                                            float(maximum_regularization), float(gradient_tolerance), float(step_tolerance), float(max_step),
+                                            float(threshold_increase), float(threshold_decrease), float(minimum_regularization),
+                                            ctypes.byref(cost), ctypes.byref(iters), ctypes.byref(lam))
+        self.last_ik_lambda = lam.value
         return q, cost.value, iters.value, term
 
     def problem_hessian(self, x):

@@ -1061,3 +1061,45 @@ def test_full_size_cfg2a_rpy_1m(oracle_lib):
         assert record("cfg2a_rpy_1m_phi_%s" % prob.last_kernel(), e_phi) <= TOL and record("cfg2a_rpy_1m_jac_%s" % prob.last_kernel(), e_jac) <= TOL
         # pitch stays inside [-pi/2, pi/2], roll / yaw inside (-pi, pi]: KDL's GetRPY ranges
         assert np.abs(phi[:, 4]).max() <= np.pi / 2 and np.abs(phi[:, 3]).max() <= np.pi and np.abs(phi[:, 5]).max() <= np.pi
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_batched_ik_single_iteration_modes(oracle_lib, kernel, monkeypatch):
+    """MaxIterations == 1, the reference's interactive configuration (example_ik.xml:5): with MaxStep the step is clamped per joint
+    and taken without a line search (ik_solver.cpp:139-143), without it lambda adapts to the accepted step length and reaching
+    MaximumRegularization ends the solve with Divergence (:187-199).  example_ik.xml's own shape: link 6 + quaternion offset, W."""
+    orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+    off = [0, 0, 0, 0.7071067811865476, -4.3297802811774664e-17, 0.7071067811865475, 4.3297802811774664e-17]
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_6_link", "LinkOffset": off}]}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    prob.set_kernel(kernel)
+    rng = np.random.default_rng(401)
+    goal = np.array([0.5, 0.0, 0.5, 0.0, 0.0, 0.0])
+    W = np.array([7.0, 6, 5, 4, 3, 2, 1])
+    prob.set_cost([1.0], T=1, goal=goal, W=W)
+    E = 64
+    Q0 = random_states(orc, E, seed=402) * 0.5
+    cases = [dict(max_step=0.1), dict(max_step=1e-3), dict(), dict(regularization_rate=1e8), dict(maximum_regularization=1e-8),
+             dict(threshold_increase=1.0), dict(max_step=0.05, tolerance=1e3),
+             dict(maximum_regularization=5e-9, threshold_increase=1.0, threshold_decrease=2.0)]  # the last one ends in Divergence
+    for one_launch in (False, True):
+        if one_launch:
+            if kernel != 0:
+                continue
+            monkeypatch.setenv("EXO_IK_ONE_LAUNCH", "1")
+        for kw in cases:
+            Q, cost, iters, term = prob.ik_solve_batch(Q0, max_iterations=1, **kw)
+            for e in range(E):
+                q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], [1.0], goal=goal, W=W, max_iterations=1, **kw)
+                assert term[e] == t_ref and iters[e] == it_ref, (kw, e, term[e], t_ref, iters[e], it_ref)
+                assert record("ik_single_iteration_q", np.max(np.abs(Q[e] - q_ref))) <= TOL, kw
+                assert abs(cost[e] - c_ref) <= TOL * max(1.0, c_ref)
+            if kw.get("max_step"):
+                assert np.max(np.abs(Q - Q0)) <= kw["max_step"] * (1 + 1e-12)  # no joint moves further than MaxStep
+    # a solver that keeps calling Solve with MaxIterations = 1 (interactive IK) converges like the multi-iteration solver does
+    monkeypatch.delenv("EXO_IK_ONE_LAUNCH", raising=False)
+    Q = Q0.copy()
+    for _ in range(30):
+        Q, cost, iters, term = prob.ik_solve_batch(Q, max_iterations=1)
+    assert np.median(cost) < 1e-4
