@@ -86,6 +86,15 @@ struct exo_problem
     int kernel_choice = 0;        // 0 auto, 1 interpreter only, 2..3 chain kernel variants (CHAIN_REGS, CHAIN_TWO_PASS)
     bool chain_ok = false;        // the compiled program lowered to ChainParams
     ChainParams chain;            // problem constants of the chain kernel (buffers / strides filled per launch)
+    // TMA output path of the chain kernel: staging plan + tensor maps of the last buffers bound (re-encoded when they change)
+    ChainTmaParams chain_tma;
+    struct TmaKey
+    {
+        const void *phi = nullptr, *jac = nullptr;
+        int64_t n = 0, phi_sk = 0, j_sc = 0, j_sr = 0;
+        int tile = -1, version = -1;
+        bool ok = false;
+    } chain_tma_key;
     bool plan_valid = false;      // interpreter launch plan (depends on the program and on split_spheres only)
     bool plan_split = false;
     bool fused_spheres = false;   // exo_problem_set_kernel(6): SphereCollision inside the interpreter (no second launch)
@@ -694,10 +703,30 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         CUDA_TRY(cudaEventRecord(p->ev0, stream));
     }
     cudaError_t e;
+    bool tma = false;
     if (chain)
     {
         chain_bind(p->chain, k.x, k.phi, k.jac, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
-        e = chain_launch(p->chain, p->kernel_choice >= 2 ? p->kernel_choice - 2 : CHAIN_DEFAULT, stream);
+        // SoA buffers of chains that own every column: outputs staged in shared memory and stored by the TMA unit
+        if (p->kernel_choice == 0 || p->kernel_choice >= 7)
+        {
+            const int tile = p->kernel_choice == 7 ? 64 : (p->kernel_choice == 8 ? 128 : 0);
+            exo_problem::TmaKey& key = p->chain_tma_key;
+            if (key.phi != k.phi || key.jac != k.jac || key.n != E || key.phi_sk != k.phi_sk || key.j_sc != k.j_sc || key.j_sr != k.j_sr || key.tile != tile ||
+                key.version != p->compiled_version)
+            {
+                key.phi = k.phi; key.jac = k.jac; key.n = E; key.phi_sk = k.phi_sk; key.j_sc = k.j_sc; key.j_sr = k.j_sr; key.tile = tile;
+                key.version = p->compiled_version;
+                key.ok = chain_tma_plan(p->chain, tile, p->chain_tma);
+            }
+            tma = key.ok;
+            if (!tma && p->kernel_choice >= 7)
+                return fail(EXO_ERR_UNSUPPORTED, "the TMA output path needs SoA buffers (even row pitch, 16-byte aligned) and a chain that owns every Jacobian column");
+        }
+        if (tma)
+            e = chain_tma_launch(p->chain, p->chain_tma, stream);
+        else
+            e = chain_launch(p->chain, p->kernel_choice == 2 || p->kernel_choice == 3 ? p->kernel_choice - 2 : CHAIN_DEFAULT, stream);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         p->launches++;
     }
@@ -729,7 +758,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
             }
         }
     }
-    p->last_kernel = chain ? "exo_chain_kernel" : (split ? "exo_spheres_kernel" : "exo_eval_kernel");
+    p->last_kernel = chain ? (tma ? "exo_chain_tma_kernel" : "exo_chain_kernel") : (split ? "exo_spheres_kernel" : "exo_eval_kernel");
     if (timed)
     {
         CUDA_TRY(cudaEventRecord(p->ev1, stream));
@@ -760,15 +789,15 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 6)
-        return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants), 4..5 (interpreter, one- / two-pass program) or 6 (interpreter with SphereCollision fused in)");
+    if (choice < 0 || choice > 8)
+        return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants, per-lane stores), 4..5 (interpreter, one- / two-pass program), 6 (interpreter with SphereCollision fused in) or 7..8 (chain kernel with TMA stores, 64 / 128 evaluations per tile)");
     const int mode = choice == 4 ? COMPILE_ONE_PASS : (choice == 5 ? COMPILE_TWO_PASS : COMPILE_AUTO);
     if (mode != p->compile_mode)
     {
         p->compile_mode = mode;
         p->compiled_version = -1;  // recompile at the next launch
     }
-    p->kernel_choice = choice >= 4 ? 1 : choice;
+    p->kernel_choice = (choice >= 4 && choice <= 6) ? 1 : choice;
     p->fused_spheres = choice == 6;
     return EXO_OK;
 }

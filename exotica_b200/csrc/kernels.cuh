@@ -125,6 +125,32 @@ void chain_bind(ChainParams& P, const double* x, double* phi, double* jac, int64
                 int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
 cudaError_t chain_launch(const ChainParams& P, int variant, cudaStream_t stream);
 
+// ---- TMA tensor stores (tma.cu): SoA outputs leave the SM as 2-D tiles [rows][TILE evaluations] staged in shared memory -----------
+// Opaque 128-byte tensor map (CUtensorMap) as a kernel parameter; encoded on the host by cuTensorMapEncodeTiled, which is
+// resolved through cudaGetDriverEntryPoint (no link-time dependency on libcuda).
+struct alignas(64) TmaDesc
+{
+    unsigned long long v[16];
+};
+// 2-D FP64 tensor [rows][inner] with row pitch pitch_bytes (a multiple of 16, base 16-byte aligned), box [box_rows][box_inner]
+// (each <= 256).  False when the driver refuses the geometry (the caller takes its per-lane store path).
+bool tma_encode_2d(TmaDesc& out, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_rows);
+
+// Serial-chain kernel with TMA output (chain_tma_kernel.cu): each CTA stages the Phi / J entries of its `tile` evaluations as
+// [row][tile] in shared memory (immediate-offset st.shared, no 64-bit address arithmetic per entry) and one lane hands every
+// frame's blocks to the TMA unit (cp.async.bulk.tensor.2d.global.shared::cta, L2 evict-first).  Eligible: SoA buffers with an
+// even number of evaluations per row, every controlled joint in the chain in column order, EffFrame / EffPosition rows.
+struct ChainTmaParams
+{
+    TmaDesc phi[CH_MAXF], jac[CH_MAXF];                      // per requested frame: its Phi rows / its n_rows x N Jacobian rows
+    int32_t stage_phi_row[CH_MAXF], stage_j_row[CH_MAXF];    // first staging row of the frame's blocks
+    int32_t stage_rows, tile;
+};
+// Plans tile size, staging layout and tensor maps for the buffers bound to P; false: not eligible (use chain_launch).
+// tile: 0 = automatic, else 64 or 128.
+bool chain_tma_plan(const ChainParams& P, int tile, ChainTmaParams& M);
+cudaError_t chain_tma_launch(const ChainParams& P, const ChainTmaParams& M, cudaStream_t stream);
+
 // Fused forward kinematics + task cost + cost gradient for chain programs (exo_chain_costgrad_kernel): Phi and J are formed in
 // registers and contracted on the spot, only N doubles per evaluation (and its cost) reach HBM.
 struct ChainGradParams

@@ -232,9 +232,13 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
  * emitted on the fly; used automatically for large trees), 6 = the interpreter with SphereCollision evaluated inside it
  * (by default programs with a SphereCollision map run as two launches: the interpreter parks every evaluation's frames
  * in a scratch buffer -- at most EXO_SPH_DUMP_MIB MiB, default 1024, larger batches go in chunks -- and
- * exo_spheres_kernel runs the pair loops one warp per evaluation).  Tests compare all of them. */
+ * exo_spheres_kernel runs the pair loops one warp per evaluation), 7 / 8 = the chain kernel with TMA output (each CTA stages
+ * the Phi / J entries of its 64 / 128 evaluations in shared memory and the TMA unit stores them as 2-D tiles; needs
+ * EXO_LAYOUT_SOA device buffers with an even, 16-byte aligned row pitch and a chain that owns every Jacobian column, else
+ * EXO_ERR_UNSUPPORTED at launch; choice 0 takes this path automatically when those conditions hold, environment
+ * EXO_CHAIN_TMA=0 keeps choice 0 on the per-lane stores).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
-/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
+/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_chain_tma_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
  * second launch of a SphereCollision program) / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);
 
