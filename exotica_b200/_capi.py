@@ -91,6 +91,7 @@ SYMBOLS = [
     ("exo_problem_program_info", ctypes.c_int, [_vp, _ip]),
     ("exo_problem_chain_info", ctypes.c_int, [_vp, _ip]),
     ("exo_problem_set_kernel", ctypes.c_int, [_vp, ctypes.c_int]),
+    ("exo_problem_generated_kernel_source", ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
     ("exo_problem_set_cost", ctypes.c_int, [_vp, ctypes.POINTER(CostDesc)]),
     ("exo_problem_cost_batch", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
     ("exo_problem_cost_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
@@ -626,6 +627,14 @@ class Problem(object):
 
     def set_kernel(self, choice):
         check(lib().exo_problem_set_kernel(self.h, int(choice)))
+
+    def generated_kernel_source(self, compile=False):
+        """CUDA source of the per-robot generated tree kernel; compile=True also runs NVRTC (works without a GPU)."""
+        need = ctypes.c_int64(0)
+        check(lib().exo_problem_generated_kernel_source(self.h, None, 0, ctypes.byref(need), 0))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib().exo_problem_generated_kernel_source(self.h, buf, need.value, None, 1 if compile else 0))
+        return buf.value.decode()
 
     def last_kernel(self):
         return lib().exo_problem_last_kernel(self.h).decode()

@@ -95,6 +95,15 @@ struct exo_problem
         int tile = -1, version = -1;
         bool ok = false;
     } chain_tma_key;
+    // per-robot generated kernel for tree programs (tree_codegen.cpp / tree_jit.cu)
+    int tree_version = -2;        // compiled_version the plan below was generated for
+    bool tree_ok = false;         // source generated (the program is inside the generator's scope)
+    void* tree_kernel = nullptr;  // loaded module entry (nullptr until the first eligible launch on a device)
+    bool tree_jit_failed = false;
+    std::string tree_why;         // why the generated kernel does not apply
+    TreeGenPlan tree_plan;
+    TreeGenParams tree_params;
+    TmaKey tree_key;
     bool plan_valid = false;      // interpreter launch plan (depends on the program and on split_spheres only)
     bool plan_split = false;
     bool fused_spheres = false;   // exo_problem_set_kernel(6): SphereCollision inside the interpreter (no second launch)
@@ -608,6 +617,39 @@ static int64_t sph_dump_cap_bytes()
     return (int64_t)(mib > 0 ? mib : 1024) << 20;
 }
 
+// Source of the per-robot kernel for the current model state (generated from the two-pass form of the program)
+static bool tree_prepare(exo_problem* p)
+{
+    if (p->tree_version == p->tree->version) return p->tree_ok;
+    p->tree_version = p->tree->version;
+    p->tree_ok = false;
+    p->tree_kernel = nullptr;
+    p->tree_jit_failed = false;
+    p->tree_key = exo_problem::TmaKey();
+    std::string err;
+    Program tp;
+    std::vector<MapSpec> maps = p->maps;
+    if (!compile_program(p->tree->model, maps, tp, err, COMPILE_TWO_PASS))
+    {
+        p->tree_why = err;
+        return false;
+    }
+    p->tree_ok = tree_codegen(tp, p->tree_plan, p->tree_why);
+    return p->tree_ok;
+}
+
+static int64_t tree_min_evals()
+{
+    static int64_t n = -1;
+    if (n < 0)
+    {
+        const char* env = getenv("EXO_TREE_MIN_EVALS");
+        n = env ? atoll(env) : 4096;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
 // e_offset: index of this launch's first evaluation in the caller's batch (the host pipeline launches chunk by chunk; per-evaluation
 // side outputs such as the minimum sphere distance are indexed by the caller's evaluation number)
 static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E, int32_t T, int32_t layout, double* d_phi, double* d_jac,
@@ -638,14 +680,45 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
     const bool chain = p->chain_ok && p->kernel_choice != 1;
-    if (!chain && p->kernel_choice >= 2) return fail(EXO_ERR_UNSUPPORTED, "the compiled program is not a serial chain: the chain kernel cannot run it");
+    if (!chain && p->kernel_choice >= 2 && p->kernel_choice != 9) return fail(EXO_ERR_UNSUPPORTED, "the compiled program is not a serial chain: the chain kernel cannot run it");
     LaunchConfig cfg;
     int n_sph_ops = 0;
     for (const Op& op : p->prog.ops) n_sph_ops += op.kind == OP_EMIT_SPHERES;
     const bool split = !chain && n_sph_ops > 0 && n_sph_ops <= SPH_SPLIT_MAX_OPS && !p->fused_spheres;
     int64_t chunk = E;  // split launches go in chunks whose parked slots fit the dump buffer
     double* dump = nullptr;
-    if (!chain)
+    // tree programs: the per-robot generated kernel (TMA output) when the buffers qualify; run-time compiled on first use, so
+    // small batches stay on the interpreter unless exo_problem_set_kernel(9) asks for it
+    bool gen = false;
+    if (!chain && n_sph_ops == 0 && (p->kernel_choice == 9 || (p->kernel_choice == 0 && E >= tree_min_evals() && !p->tree_jit_failed)))
+    {
+        if (tree_prepare(p))
+        {
+            exo_problem::TmaKey& key = p->tree_key;
+            if (key.phi != k.phi || key.jac != k.jac || key.n != E || key.phi_sk != k.phi_sk || key.j_sc != k.j_sc || key.j_sr != k.j_sr || key.version != p->tree_version ||
+                p->tree_params.x != k.x || p->tree_params.x_sk != k.x_sk)
+            {
+                key.phi = k.phi; key.jac = k.jac; key.n = E; key.phi_sk = k.phi_sk; key.j_sc = k.j_sc; key.j_sr = k.j_sr; key.version = p->tree_version;
+                key.ok = tree_jit_bind(p->tree_plan, p->tree_params, k.x, k.phi, k.jac, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
+                if (!key.ok) p->tree_why = "the generated kernel needs EXO_LAYOUT_SOA device buffers with an even, 16-byte aligned row pitch";
+            }
+            if (key.ok && !p->tree_kernel && !p->tree_jit_failed)
+            {
+                std::string jerr;
+                p->tree_kernel = tree_jit_get(p->tree_plan, jerr);
+                if (!p->tree_kernel)
+                {
+                    p->tree_jit_failed = true;
+                    p->tree_why = "run-time compilation failed: " + jerr;
+                }
+            }
+            gen = key.ok && p->tree_kernel;
+        }
+        if (!gen && p->kernel_choice == 9) return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
+    }
+    else if (p->kernel_choice == 9)
+        return fail(EXO_ERR_UNSUPPORTED, chain ? "the program is a serial chain: the chain kernels run it" : "generated tree kernel not applicable: SphereCollision");
+    if (!chain && !gen)
     {
         if (!p->plan_valid || p->plan_split != split)
         {
@@ -730,6 +803,12 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         p->launches++;
     }
+    else if (gen)
+    {
+        e = tree_jit_launch(p->tree_kernel, p->tree_plan, p->tree_params, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "generated kernel launch");
+        p->launches++;
+    }
     else
     {
         const KernelParams k0 = k;
@@ -758,7 +837,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
             }
         }
     }
-    p->last_kernel = chain ? (tma ? "exo_chain_tma_kernel" : "exo_chain_kernel") : (split ? "exo_spheres_kernel" : "exo_eval_kernel");
+    p->last_kernel = gen ? "exo_tree_kernel" : chain ? (tma ? "exo_chain_tma_kernel" : "exo_chain_kernel") : (split ? "exo_spheres_kernel" : "exo_eval_kernel");
     if (timed)
     {
         CUDA_TRY(cudaEventRecord(p->ev1, stream));
@@ -789,8 +868,8 @@ int exo_problem_last_kernel_ms(exo_problem* p, float* ms)
 int exo_problem_set_kernel(exo_problem* p, int choice)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
-    if (choice < 0 || choice > 8)
-        return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants, per-lane stores), 4..5 (interpreter, one- / two-pass program), 6 (interpreter with SphereCollision fused in) or 7..8 (chain kernel with TMA stores, 64 / 128 evaluations per tile)");
+    if (choice < 0 || choice > 9)
+        return fail(EXO_ERR_INVALID, "kernel choice must be 0 (auto), 1 (interpreter), 2..3 (chain kernel variants, per-lane stores), 4..5 (interpreter, one- / two-pass program), 6 (interpreter with SphereCollision fused in), 7..8 (chain kernel with TMA stores, 64 / 128 evaluations per tile) or 9 (per-robot generated tree kernel)");
     const int mode = choice == 4 ? COMPILE_ONE_PASS : (choice == 5 ? COMPILE_TWO_PASS : COMPILE_AUTO);
     if (mode != p->compile_mode)
     {
@@ -799,6 +878,28 @@ int exo_problem_set_kernel(exo_problem* p, int choice)
     }
     p->kernel_choice = (choice >= 4 && choice <= 6) ? 1 : choice;
     p->fused_spheres = choice == 6;
+    return EXO_OK;
+}
+
+int exo_problem_generated_kernel_source(exo_problem* p, char* out, int64_t capacity, int64_t* needed, int32_t compile)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!tree_prepare(p)) return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
+    const std::string& src = p->tree_plan.source;
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (out && capacity > 0)
+    {
+        const size_t n = std::min((size_t)capacity - 1, src.size());
+        memcpy(out, src.data(), n);
+        out[n] = 0;
+    }
+    if (compile)
+    {
+        std::vector<char> cubin;
+        std::string err;
+        if (!tree_jit_compile(p->tree_plan, cubin, err)) return fail(EXO_ERR_UNSUPPORTED, "run-time compilation failed: " + err);
+    }
     return EXO_OK;
 }
 

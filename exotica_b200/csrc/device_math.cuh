@@ -467,7 +467,7 @@ __device__ __forceinline__ void write_phi(int map_kind, int rot_type, const Fr& 
 }
 
 // JointLimit::Update (joint_limit.cpp:63-99); phi starts from the SetZero value 0.  qs: staged state, stride qstride.
-__device__ __forceinline__ void emit_joint_limit(const double* c, int N, const double* qs, int qstride, double* ph, int64_t phi_sk, double* jr,
+__device__ __forceinline__ void emit_joint_limit(const double* c, int N, const double* qs, int64_t qstride, double* ph, int64_t phi_sk, double* jr,
                                                  int64_t j_sr, int64_t j_sc)
 {
     const double safe = c[0];

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+#include <vector>
+
 #include "program.h"
 
 namespace exo
@@ -135,6 +138,9 @@ struct alignas(64) TmaDesc
 // 2-D FP64 tensor [rows][inner] with row pitch pitch_bytes (a multiple of 16, base 16-byte aligned), box [box_rows][box_inner]
 // (each <= 256).  False when the driver refuses the geometry (the caller takes its per-lane store path).
 bool tma_encode_2d(TmaDesc& out, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_rows);
+// 3-D FP64 tensor [d2][d1][inner] with byte pitches pitch1 (between d1 entries) and pitch2 (between d2 entries), box [b2][b1][box_inner]
+bool tma_encode_3d(TmaDesc& out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box_inner,
+                   uint32_t b1, uint32_t b2);
 
 // Serial-chain kernel with TMA output (chain_tma_kernel.cu): each CTA stages the Phi / J entries of its `tile` evaluations as
 // [row][tile] in shared memory (immediate-offset st.shared, no 64-bit address arithmetic per entry) and one lane hands every
@@ -150,6 +156,42 @@ struct ChainTmaParams
 // tile: 0 = automatic, else 64 or 128.
 bool chain_tma_plan(const ChainParams& P, int tile, ChainTmaParams& M);
 cudaError_t chain_tma_launch(const ChainParams& P, const ChainTmaParams& M, cudaStream_t stream);
+
+// ---- per-robot generated kernel for tree programs (tree_codegen.cpp, tree_jit.cu) --------------------------------------------------
+// The two-pass tree program unrolled into straight-line CUDA C++ (constants as literals, one warp per tile of 32 evaluations,
+// Phi / J leaving through TMA boxes, structural zeros from a shared zero tile), compiled at run time with NVRTC for sm_100a.
+constexpr int TREE_MAXMAPS = 24;
+struct TreeGenPlan
+{
+    struct MapShape
+    {
+        int phi;           // 1: 2-D box of Phi[LP][E]; 0: 3-D box of J[LJ][N][E]
+        int ncols, nrows;  // box = [nrows][ncols][32]
+    };
+    std::string source;
+    std::vector<MapShape> maps;
+    int warps_per_cta = 4;
+    size_t smem_bytes = 0;
+    int n_ctrl = 0, length_phi = 0, length_jac = 0;
+};
+struct TreeGenParams  // mirrored by the generated source
+{
+    const double* x;
+    double* phi;
+    double* jac;
+    long long n_evals, x_sk, phi_sk, j_sr, j_sc;
+    TmaDesc maps[TREE_MAXMAPS];
+};
+// Generates the source; false + why when the program is outside the generated kernel's scope (the interpreter runs it).
+bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why);
+// NVRTC only (no device needed): source -> sm_100a cubin
+bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::string& err);
+// NVRTC + module cache (keyed by source text and device): an opaque kernel handle, nullptr + err on failure
+void* tree_jit_get(const TreeGenPlan& plan, std::string& err);
+// Tensor maps of one binding; false when the buffers do not qualify (layout, alignment, odd row pitch)
+bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, double* phi, double* jac, int64_t n_evals, int64_t x_se, int64_t x_sk,
+                   int64_t phi_se, int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
+cudaError_t tree_jit_launch(void* kernel, const TreeGenPlan& plan, const TreeGenParams& P, cudaStream_t stream);
 
 // Fused forward kinematics + task cost + cost gradient for chain programs (exo_chain_costgrad_kernel): Phi and J are formed in
 // registers and contracted on the spot, only N doubles per evaluation (and its cost) reach HBM.

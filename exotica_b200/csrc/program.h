@@ -127,7 +127,9 @@ enum
 // EMIT_FRAME int table: [N] contributor entries by Jacobian column, then [n_joint_ops] entries by joint-op ordinal.
 // column entry: -1 none, else (jslot << 2) | (prismatic << 1) | negative
 // ordinal entry: -1 none, else (column << 2) | (prismatic << 1) | negative
+#ifndef __CUDACC_RTC__  // host helper: hidden from the run-time compiled kernels, which include this header for the enums
 static inline int32_t contrib_pack(int jslot, bool prismatic, bool negative) { return (jslot << 2) | (prismatic ? 2 : 0) | (negative ? 1 : 0); }
+#endif
 
 // OP_EMIT_SPHERES int table layout (per sphere, 4 ints): anchor frame source, anchor accumulator index (-1 if
 // the sphere has no controlled ancestor), group, offset of its constants (3 offset doubles + radius) -- then

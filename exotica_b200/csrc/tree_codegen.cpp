@@ -1,0 +1,654 @@
+// tree_codegen.cpp -- turns a compiled tree program into the CUDA source of a kernel specialised for that robot and problem.
+//
+// The interpreter (kernels.cu) decodes the op list per evaluation: 29 k warp-instructions per 32 evaluations on the 38-DoF
+// humanoid of BASELINE.json config 4, two thirds of them decode, address arithmetic and per-lane stores of structural zeros.
+// Here the same two-pass program (compiler.cpp) is unrolled on the host into straight-line CUDA C++ and compiled at run time
+// (NVRTC, tree_jit.cu):
+//   * every transform constant is a literal and exact 0 / +-1 entries of the constant frames are folded away;
+//   * one warp = one tile of 32 evaluations; Phi and the non-zero Jacobian columns are staged [row][32] in the warp's own
+//     shared-memory buffers and leave through the TMA unit (2-D boxes for Phi, 3-D boxes [rows][columns][32] of J[LJ][N][E]);
+//     no CTA-wide barrier after start-up;
+//   * structural zeros of J (63 % of the bytes of config 4) are TMA boxes read from one shared zero tile, issued by one lane
+//     before the arithmetic starts: no per-lane instruction is spent on them.
+// Reference path replaced: KinematicTree::UpdateTree / UpdateFK / ComputeJ (exotica_core/src/kinematic_tree.cpp:695-737,
+// 829-867,919-945) + EffFrame / EffPosition / JointLimit::Update + Phi.SetZero / jacobian.setZero.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+#include "../../include/exotica_b200.h"
+#include "compiler.h"
+#include "kernels.cuh"
+
+namespace exo
+{
+namespace
+{
+struct Emitter
+{
+    std::string s;
+    void line(const char* fmt, ...) __attribute__((format(printf, 2, 3)))
+    {
+        va_list ap, aq;
+        va_start(ap, fmt);
+        va_copy(aq, ap);
+        const int n = vsnprintf(nullptr, 0, fmt, ap);
+        va_end(ap);
+        std::string buf((size_t)(n > 0 ? n : 0) + 1, '\0');
+        vsnprintf(&buf[0], buf.size(), fmt, aq);
+        va_end(aq);
+        buf.resize((size_t)(n > 0 ? n : 0));
+        s += buf;
+        s += '\n';
+    }
+};
+
+std::string lit(double v)
+{
+    if (v == 0.0) return "0.0";
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.17g", v);
+    std::string r = buf;
+    if (r.find_first_of(".eEn") == std::string::npos) r += ".0";  // keep it a double literal
+    if (v < 0) r = "(" + r + ")";
+    return r;
+}
+
+// sum_k a_k * K_k (+ tail) with exact zeros dropped, +-1 folded and the rest as an fma chain; "0.0" when nothing is left
+std::string dot_const(const std::vector<std::string>& a, const std::vector<double>& K, const std::string& tail)
+{
+    std::string acc = tail;
+    for (size_t k = 0; k < a.size(); ++k)
+    {
+        if (K[k] == 0.0) continue;
+        if (K[k] == 1.0)
+            acc = acc.empty() ? a[k] : "(" + acc + " + " + a[k] + ")";
+        else if (K[k] == -1.0)
+            acc = acc.empty() ? "(-" + a[k] + ")" : "(" + acc + " - " + a[k] + ")";
+        else
+            acc = acc.empty() ? "(" + a[k] + " * " + lit(K[k]) + ")" : "fma(" + a[k] + ", " + lit(K[k]) + ", " + acc + ")";
+    }
+    return acc.empty() ? std::string("0.0") : acc;
+}
+
+const char* kM[9] = {"m0", "m1", "m2", "m3", "m4", "m5", "m6", "m7", "m8"};
+const char* kP[3] = {"x", "y", "z"};
+
+// dst = a * C for a constant frame C (12 doubles: rotation row-major, translation); a and dst may be the same variable
+void emit_mul_const(Emitter& o, const char* dst, const char* a, const double* C)
+{
+    o.line("    {");
+    for (int r = 0; r < 3; ++r)
+    {
+        const std::vector<std::string> row = {std::string(a) + "." + kM[3 * r], std::string(a) + "." + kM[3 * r + 1], std::string(a) + "." + kM[3 * r + 2]};
+        for (int c = 0; c < 3; ++c) o.line("        const double t%d = %s;", 3 * r + c, dot_const(row, {C[c], C[3 + c], C[6 + c]}, "").c_str());
+        o.line("        const double p%d = %s;", r, dot_const(row, {C[9], C[10], C[11]}, std::string(a) + "." + kP[r]).c_str());
+    }
+    for (int k = 0; k < 9; ++k) o.line("        %s.%s = t%d;", dst, kM[k], k);
+    for (int k = 0; k < 3; ++k) o.line("        %s.%s = p%d;", dst, kP[k], k);
+    o.line("    }");
+}
+
+// dst = C * a for a constant frame C (the inverse of a constant temp_B)
+void emit_const_mul(Emitter& o, const char* dst, const double* C, const char* a)
+{
+    o.line("    {");
+    for (int r = 0; r < 3; ++r)
+    {
+        for (int c = 0; c < 3; ++c)
+        {
+            const std::vector<std::string> col = {std::string(a) + "." + kM[c], std::string(a) + "." + kM[3 + c], std::string(a) + "." + kM[6 + c]};
+            o.line("        const double t%d = %s;", 3 * r + c, dot_const(col, {C[3 * r], C[3 * r + 1], C[3 * r + 2]}, "").c_str());
+        }
+        const std::vector<std::string> p = {std::string(a) + ".x", std::string(a) + ".y", std::string(a) + ".z"};
+        o.line("        const double p%d = %s;", r, dot_const(p, {C[3 * r], C[3 * r + 1], C[3 * r + 2]}, lit(C[9 + r])).c_str());
+    }
+    for (int k = 0; k < 9; ++k) o.line("        %s.%s = t%d;", dst, kM[k], k);
+    for (int k = 0; k < 3; ++k) o.line("        %s.%s = p%d;", dst, kP[k], k);
+    o.line("    }");
+}
+
+void emit_set_const(Emitter& o, const char* dst, const double* C)
+{
+    for (int k = 0; k < 9; ++k) o.line("    %s.%s = %s;", dst, kM[k], lit(C[k]).c_str());
+    for (int k = 0; k < 3; ++k) o.line("    %s.%s = %s;", dst, kP[k], lit(C[9 + k]).c_str());
+}
+
+bool is_identity12(const double* C)
+{
+    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    for (int k = 0; k < 12; ++k)
+        if (C[k] != I[k]) return false;
+    return true;
+}
+
+struct Item  // one block of values a lane stages: the Phi entries of a frame, or one Jacobian column of one frame
+{
+    int op;               // index of the op that produces it
+    bool phi;
+    int nrows;            // Phi entries / Jacobian rows
+    int key, col;         // J: first Jacobian row of the frame, column
+    int ps, flags, cst_b; // J: position slot, TP_F_* flags, constant offset of Binv
+    int box = -1, col_in_box = 0;
+    int batch = -1;       // index of its batch within its pass
+};
+struct Box
+{
+    bool phi;
+    int nrows, ncols;
+    int off;        // first staging row
+    int c_col, c_row;
+    int map = -1;
+};
+struct Batch
+{
+    std::vector<int> items;
+    std::vector<Box> boxes;
+    int last_item = -1;  // flushed right after this item has been staged
+};
+
+int env_int(const char* name, int dflt, int lo, int hi)
+{
+    const char* v = getenv(name);
+    int r = v ? atoi(v) : dflt;
+    if (r < lo) r = lo;
+    if (r > hi) r = hi;
+    return r;
+}
+}  // namespace
+
+bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
+{
+    const ProgramHeader& H = prog.hdr;
+    if (!H.two_pass)
+    {
+        why = "the program has no two-pass form (SphereCollision, Distance or state-dependent base frames)";
+        return false;
+    }
+    if (H.n_generated > 0)
+    {
+        why = "trajectory-driven links";
+        return false;
+    }
+    const int N = H.n_ctrl;
+    const int n_ops = (int)prog.ops.size();
+    // ---- eligibility + the items every op stages ------------------------------------------------------------------------------
+    std::vector<Item> items;
+    std::vector<std::vector<int>> op_items(n_ops);
+    int n_pos = 0, max_op_values = 0;
+    for (int i = 0; i < n_ops; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_END) break;
+        if (op.kind == OP_JOINT)
+        {
+            const int32_t* tp = &prog.ints[op.tab];
+            int vals = 0;
+            for (int k = 0; k < tp[0]; ++k)
+            {
+                const int32_t* ent = tp + 1 + TP_INTS * k;
+                if (ent[3] != ROWS_VW && ent[3] != ROWS_V)
+                {
+                    why = "a map keeps Jacobian rows other than (v, w) / (v)";
+                    return false;
+                }
+                Item it;
+                it.op = i; it.phi = false; it.nrows = ent[3] == ROWS_VW ? 6 : 3;
+                it.key = ent[2]; it.col = ent[1]; it.ps = ent[0]; it.flags = ent[4]; it.cst_b = ent[5];
+                op_items[i].push_back((int)items.size());
+                items.push_back(it);
+                vals += it.nrows;
+                max_op_values = std::max(max_op_values, it.nrows);
+            }
+        }
+        else if (op.kind == OP_EMIT_FRAME)
+        {
+            const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
+            if ((row_mode != ROWS_VW && row_mode != ROWS_V) || (op.flags & F_B_MASK) == F_B_SLOT)
+            {
+                why = "a requested frame is outside the generated kernel's scope";
+                return false;
+            }
+            int rows = 0;
+            if (op.map_kind == EXO_MAP_EFF_POSITION) rows = 3;
+            else if (op.map_kind == EXO_MAP_FRAMES) rows = 12;
+            else if (op.map_kind == EXO_MAP_EFF_FRAME && rotation_length(op.rot_type) > 0) rows = 3 + rotation_length(op.rot_type);
+            else
+            {
+                why = "a task map is outside the generated kernel's scope";
+                return false;
+            }
+            Item it;
+            it.op = i; it.phi = true; it.nrows = rows; it.key = op.phi_off; it.col = 0; it.ps = op.n_items; it.flags = 0; it.cst_b = 0;
+            op_items[i].push_back((int)items.size());
+            items.push_back(it);
+            n_pos = std::max(n_pos, op.n_items + 1);
+            max_op_values = std::max(max_op_values, rows);
+        }
+        else if (op.kind != OP_EMIT_JLIMIT && op.kind != OP_EMIT_FILL)
+        {
+            why = "an op is outside the generated kernel's scope";
+            return false;
+        }
+    }
+    if (n_pos > 16)
+    {
+        why = "more than 16 requested frames";
+        return false;
+    }
+    // ---- geometry ---------------------------------------------------------------------------------------------------------------
+    const int WPC = env_int("EXO_TREE_WPC", 4, 1, 8);            // warps (= tiles in flight) per CTA
+    int CAP = env_int("EXO_TREE_CAP", 24, 3, 96);                // staging rows per buffer
+    const int ZC = env_int("EXO_TREE_ZC", 4, 1, 8);              // columns of the zero tile
+    if (CAP < max_op_values) CAP = max_op_values;
+    if (CAP > 96)
+    {
+        why = "one frame has more entries than the staging buffer holds";
+        return false;
+    }
+    // ---- batches: ops are taken in program order (pass 1: frame emits, pass 2: joints) until the buffer is full --------------------
+    std::vector<Batch> batches[2];
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        Batch cur;
+        int used = 0;
+        for (int i = 0; i < n_ops; ++i)
+        {
+            const Op& op = prog.ops[i];
+            if (op.kind == OP_END) break;
+            if ((pass == 0) != (op.kind == OP_EMIT_FRAME)) continue;
+            if (op.kind != OP_EMIT_FRAME && op.kind != OP_JOINT) continue;
+            for (int it : op_items[i])
+            {
+                if (used + items[it].nrows > CAP && !cur.items.empty())
+                {
+                    batches[pass].push_back(cur);
+                    cur = Batch();
+                    used = 0;
+                }
+                items[it].batch = (int)batches[pass].size();
+                cur.items.push_back(it);
+                cur.last_item = it;
+                used += items[it].nrows;
+            }
+        }
+        if (!cur.items.empty()) batches[pass].push_back(cur);
+    }
+    // boxes: Phi -> one 2-D box per frame; J -> per frame, runs of consecutive columns become one 3-D box [rows][columns][32]
+    plan.maps.clear();
+    auto map_id = [&](bool phi, int ncols, int nrows) {
+        for (size_t m = 0; m < plan.maps.size(); ++m)
+            if (plan.maps[m].phi == (phi ? 1 : 0) && plan.maps[m].ncols == ncols && plan.maps[m].nrows == nrows) return (int)m;
+        TreeGenPlan::MapShape sh;
+        sh.phi = phi ? 1 : 0; sh.ncols = ncols; sh.nrows = nrows;
+        plan.maps.push_back(sh);
+        return (int)plan.maps.size() - 1;
+    };
+    for (int pass = 0; pass < 2; ++pass)
+        for (Batch& b : batches[pass])
+        {
+            int off = 0;
+            if (pass == 0)
+            {
+                for (int it : b.items)
+                {
+                    Box bx;
+                    bx.phi = true; bx.nrows = items[it].nrows; bx.ncols = 1; bx.off = off; bx.c_col = 0; bx.c_row = items[it].key;
+                    bx.map = map_id(true, 1, bx.nrows);
+                    items[it].box = (int)b.boxes.size();
+                    b.boxes.push_back(bx);
+                    off += bx.nrows;
+                }
+                continue;
+            }
+            std::vector<int> order = b.items;
+            std::sort(order.begin(), order.end(), [&](int a, int c) { return items[a].key != items[c].key ? items[a].key < items[c].key : items[a].col < items[c].col; });
+            for (size_t k = 0; k < order.size();)
+            {
+                size_t k1 = k + 1;
+                while (k1 < order.size() && items[order[k1]].key == items[order[k]].key && items[order[k1]].nrows == items[order[k]].nrows &&
+                       items[order[k1]].col == items[order[k1 - 1]].col + 1)
+                    ++k1;
+                Box bx;
+                bx.phi = false; bx.nrows = items[order[k]].nrows; bx.ncols = (int)(k1 - k); bx.off = off; bx.c_col = items[order[k]].col;
+                bx.c_row = items[order[k]].key;
+                bx.map = map_id(false, bx.ncols, bx.nrows);
+                for (size_t q = k; q < k1; ++q)
+                {
+                    items[order[q]].box = (int)b.boxes.size();
+                    items[order[q]].col_in_box = (int)(q - k);
+                }
+                b.boxes.push_back(bx);
+                off += bx.nrows * bx.ncols;
+                k = k1;
+            }
+        }
+    // structural zeros: per frame emit, runs of columns no joint owns -> boxes [rows][<= ZC columns][32] from the zero tile
+    struct ZBox
+    {
+        int map, c_col, c_row;
+    };
+    std::vector<ZBox> zboxes;
+    int z_rows_max = 0;
+    for (int i = 0; i < n_ops; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_END) break;
+        if (op.kind != OP_EMIT_FRAME) continue;
+        const int nrows = op.n_rows;
+        const int32_t* zl = &prog.ints[op.pad];
+        for (int k = 1; k <= zl[0];)
+        {
+            int k1 = k + 1;
+            while (k1 <= zl[0] && zl[k1] == zl[k1 - 1] + 1) ++k1;
+            const int c0 = zl[k], len = k1 - k;
+            const int w = std::min(len, ZC);
+            const int id = map_id(false, w, nrows);
+            for (int c = 0; c < len; c += w) zboxes.push_back({id, c0 + std::min(c, len - w), op.jrow_off});
+            z_rows_max = std::max(z_rows_max, w * nrows);
+            k = k1;
+        }
+    }
+    if ((int)plan.maps.size() > TREE_MAXMAPS)
+    {
+        why = "more distinct TMA box shapes than the kernel parameter holds";
+        return false;
+    }
+    const int ZROWS = std::max(z_rows_max, 1);
+    const int n_slots = H.n_frame_slots;
+    const int per_warp = 2 * CAP + 12 * n_slots;  // staging rows (two buffers) + frame slots, in rows of 32 doubles
+    plan.warps_per_cta = WPC;
+    plan.smem_bytes = (size_t)(ZROWS + WPC * per_warp) * 32 * sizeof(double);
+    plan.n_ctrl = N;
+    plan.length_phi = H.length_phi;
+    plan.length_jac = H.length_jac;
+    if (plan.smem_bytes > 200 * 1024)
+    {
+        why = "the program needs more shared memory per warp than a CTA can hold";
+        return false;
+    }
+
+    // ---- source ---------------------------------------------------------------------------------------------------------------------
+    Emitter o;
+    o.line("// generated by exotica_b200 tree_codegen: %d ops, %d controlled joints, %d frame slots, %d staging rows x 2, %d zero rows, %d TMA shapes", n_ops, N,
+           n_slots, CAP, ZROWS, (int)plan.maps.size());
+    o.line("#define EXO_STORE_CS 1");
+    o.line("#include \"device_math.cuh\"");
+    o.line("using namespace exo;");
+    o.line("using namespace exo::dev;");
+    o.line("struct alignas(64) TmaDesc { unsigned long long v[16]; };");
+    o.line("struct TreeGenParams { const double* x; double* phi; double* jac; long long n_evals, x_sk, phi_sk, j_sr, j_sc; TmaDesc maps[%d]; };", TREE_MAXMAPS);
+    o.line("static __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }");
+    o.line("static __device__ __forceinline__ void tma2(const TmaDesc* m, const void* s, int c0, int c1, unsigned long long pol)");
+    o.line("{ asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%%0, {%%2, %%3}], [%%1], %%4;\" :: \"l\"(m), \"r\"(smem_u32(s)), \"r\"(c0), \"r\"(c1), \"l\"(pol) : \"memory\"); }");
+    o.line("static __device__ __forceinline__ void tma3(const TmaDesc* m, const void* s, int c0, int c1, int c2, unsigned long long pol)");
+    o.line("{ asm volatile(\"cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%%0, {%%2, %%3, %%4}], [%%1], %%5;\" :: \"l\"(m), \"r\"(smem_u32(s)), \"r\"(c0), \"r\"(c1), \"r\"(c2), \"l\"(pol) : \"memory\"); }");
+    o.line("static __device__ __forceinline__ void tma_commit() { asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\"); }");
+    o.line("static __device__ __forceinline__ void tma_wait_read() { asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\"); }");
+    o.line("static __device__ __forceinline__ void fence_staged() { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); }");
+    o.line("static __device__ __noinline__ double2 slow_sincos(double q) { double s, c; sincos(q, &s, &c); return make_double2(s, c); }");
+    o.line("#define SINCOS(q, s, c) do { if (fabs(q) <= 1.0e5) fast_sincos((q), (s), (c)); else { const double2 sc_ = slow_sincos(q); (s) = sc_.x; (c) = sc_.y; } } while (0)");
+    // constants of JointLimit / fill ops
+    for (int i = 0; i < n_ops; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_END) break;
+        int n = 0;
+        if (op.kind == OP_EMIT_JLIMIT) n = 1 + 2 * N;
+        if (op.kind == OP_EMIT_FILL) n = op.n_items;
+        if (n == 0) continue;
+        std::string arr;
+        for (int k = 0; k < n; ++k) arr += (k ? ", " : "") + lit(prog.dbls[op.cst + k]);
+        o.line("__constant__ double kOp%d[%d] = {%s};", i, n, arr.c_str());
+    }
+    const int min_blocks = env_int("EXO_TREE_MINB", 0, 0, 8);
+    if (min_blocks)
+        o.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32, min_blocks);
+    else
+        o.line("extern \"C\" __global__ void __launch_bounds__(%d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32);
+    o.line("{");
+    o.line("    extern __shared__ __align__(128) double smem[];");
+    o.line("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;");
+    o.line("    for (int i = threadIdx.x; i < %d; i += %d) smem[i] = 0.0;  // the zero tile", ZROWS * 32, WPC * 32);
+    o.line("    fence_staged();");
+    o.line("    __syncthreads();");
+    o.line("    const long long e0 = ((long long)blockIdx.x * %d + warp) * 32;", WPC);
+    o.line("    if (e0 >= P.n_evals) return;");
+    o.line("    const bool valid = e0 + lane < P.n_evals;");
+    o.line("    const long long e = valid ? e0 + lane : P.n_evals - 1;  // lanes past the batch redo the last evaluation; the TMA unit clips them");
+    o.line("    const int e0i = (int)e0;");
+    o.line("    double* const wsm = smem + %d + warp * %d;", ZROWS * 32, per_warp * 32);
+    o.line("    double* const stg0 = wsm + lane;                 // staging buffer 0: row r at stg0[r * 32]");
+    o.line("    double* const stg1 = wsm + %d + lane;", CAP * 32);
+    o.line("    double* const slot = wsm + %d + lane;            // frame slot s, word k at slot[(12 * s + k) * 32]", 2 * CAP * 32);
+    o.line("    const double* const xq = P.x + e;");
+    o.line("    unsigned long long pol = 0;");
+    o.line("    if (lane == 0) asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %%0, 1.0;\" : \"=l\"(pol));");
+    o.line("    Fr cur;");
+    for (int k = 0; k < n_pos; ++k) o.line("    double pa%d_x = 0.0, pa%d_y = 0.0, pa%d_z = 0.0;", k, k, k);
+
+    int flip = 0;  // staging buffer the next batch uses
+    // zero boxes ride along with the flushes of pass 2 in equal shares (one lane issues them: no per-lane work at all)
+    auto emit_flush = [&](const Batch& b, int buf, size_t z0, size_t z1) {
+        o.line("    if (lane == 0) tma_wait_read();  // the other staging buffer has been read out");
+        o.line("    fence_staged();");
+        o.line("    __syncwarp();");
+        o.line("    if (lane == 0)");
+        o.line("    {");
+        for (const Box& bx : b.boxes)
+        {
+            if (bx.phi)
+                o.line("        tma2(&P.maps[%d], wsm + %d, e0i, %d, pol);", bx.map, (buf * CAP + bx.off) * 32, bx.c_row);
+            else
+                o.line("        tma3(&P.maps[%d], wsm + %d, e0i, %d, %d, pol);", bx.map, (buf * CAP + bx.off) * 32, bx.c_col, bx.c_row);
+        }
+        for (size_t z = z0; z < z1; ++z) o.line("        tma3(&P.maps[%d], smem, e0i, %d, %d, pol);", zboxes[z].map, zboxes[z].c_col, zboxes[z].c_row);
+        o.line("        tma_commit();");
+        o.line("    }");
+    };
+    auto load_src = [&](int src, const char* dst, bool& is_identity) {
+        is_identity = false;
+        if (src == SRC_ROOT)
+            is_identity = true;
+        else if (src >= 0)
+        {
+            for (int k = 0; k < 9; ++k) o.line("    %s.%s = slot[%d];", dst, kM[k], (12 * src + k) * 32);
+            for (int k = 0; k < 3; ++k) o.line("    %s.%s = slot[%d];", dst, kP[k], (12 * src + 9 + k) * 32);
+        }
+        else if (strcmp(dst, "cur") != 0)
+            o.line("    %s = cur;", dst);
+    };
+
+    // joint values are loaded AHEAD joints before they are used (the asm statements of the TMA path pin loads in place, and a
+    // load issued where it is needed costs its full latency: ~1 us from DRAM while the memory system is saturated with stores)
+    const int AHEAD = env_int("EXO_TREE_AHEAD", 8, 0, 16);
+    std::vector<std::pair<int, int>> qseq;  // (pass, op) of every joint that reads the state, in execution order
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+            if (prog.ops[i].kind == OP_JOINT && prog.ops[i].qidx >= 0) qseq.push_back({pass, i});
+    size_t q_issued = 0;
+    auto issue_loads = [&](size_t upto, int cur_pass) {  // emit the loads of qseq[q_issued .. upto)
+        for (; q_issued < upto && q_issued < qseq.size(); ++q_issued)
+        {
+            if (qseq[q_issued].first != cur_pass) break;  // pass-2 values are loaded inside the pass-2 scope
+            o.line("    const double q_%d = xq[%d * P.x_sk];", (int)q_issued, prog.ops[qseq[q_issued].second].qidx);
+        }
+    };
+    size_t q_used = 0;
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        if (pass == 1) o.line("    if (P.jac)\n    {");
+        issue_loads(q_used + AHEAD + 1, pass);
+        o.line("    // ---- pass %d: %s", pass, pass == 0 ? "compose the tree, Phi of every requested frame, park the frame origins" : "compose it again, Jacobian columns of every joint");
+        for (int i = 0; i < n_ops; ++i)
+        {
+            const Op& op = prog.ops[i];
+            if (op.kind == OP_END) break;
+            const double* c = prog.dbls.data() + op.cst;
+            if (op.kind == OP_JOINT)
+            {
+                o.line("    // op %d: joint, state %d", i, op.qidx);
+                bool ident = false;
+                load_src(op.src, "cur", ident);
+                const int pre = op.flags & F_PRE_MASK;
+                double prec[12];
+                memcpy(prec, c, sizeof(prec));
+                if (pre == F_PRE_NONE)
+                {
+                    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+                    memcpy(prec, I, sizeof(prec));
+                }
+                else if (pre == F_PRE_TRANS)
+                {
+                    static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                    memcpy(prec, I9, sizeof(I9));
+                }
+                if (ident)
+                    emit_set_const(o, "cur", prec);
+                else if (!is_identity12(prec))
+                    emit_mul_const(o, "cur", "cur", prec);
+                o.line("    {");
+                if (op.qidx >= 0)
+                {
+                    issue_loads(q_used + 1, pass);  // AHEAD == 0, or the first joints of a pass
+                    if (c[CJ_QMULT] == 1.0 && c[CJ_QOFF] == 0.0)
+                        o.line("        const double q = q_%d;", (int)q_used);
+                    else
+                        o.line("        const double q = fma(%s, q_%d, %s);", lit(c[CJ_QMULT]).c_str(), (int)q_used, lit(c[CJ_QOFF]).c_str());
+                    ++q_used;
+                }
+                else
+                    o.line("        const double q = %s;", lit(c[CJ_QOFF]).c_str());
+                if ((op.flags & F_PRISMATIC) || (pass == 1 && !op_items[i].empty())) o.line("        const double wx = cur.m2, wy = cur.m5, wz = cur.m8;");
+                if (op.flags & F_PRISMATIC)
+                {
+                    o.line("        cur.x = fma(wx, q, cur.x); cur.y = fma(wy, q, cur.y); cur.z = fma(wz, q, cur.z);");
+                }
+                else
+                {
+                    o.line("        double sn, cs;");
+                    o.line("        SINCOS(q, sn, cs);");
+                    o.line("        const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;");
+                    o.line("        cur.m0 = fma(cs, a0, sn * cur.m1); cur.m1 = fma(cs, cur.m1, -(sn * a0));");
+                    o.line("        cur.m3 = fma(cs, a3, sn * cur.m4); cur.m4 = fma(cs, cur.m4, -(sn * a3));");
+                    o.line("        cur.m6 = fma(cs, a6, sn * cur.m7); cur.m7 = fma(cs, cur.m7, -(sn * a6));");
+                }
+                if (pass == 1)
+                {
+                    // KinematicTree::ComputeJ (kinematic_tree.cpp:919-945) for every requested frame below this joint
+                    for (int itx : op_items[i])
+                    {
+                        const Item& it = items[itx];
+                        const Batch& bt = batches[1][it.batch];
+                        const Box& bx = bt.boxes[it.box];
+                        const int ibuf = (flip + it.batch) & 1;
+                        const char* stg = ibuf ? "stg1" : "stg0";
+                        o.line("        {");
+                        if (it.flags & TP_F_PRISMATIC)
+                            o.line("            double v0 = wx, v1 = wy, v2 = wz, w0 = 0.0, w1 = 0.0, w2 = 0.0;");
+                        else
+                        {
+                            o.line("            const double dx = pa%d_x - cur.x, dy = pa%d_y - cur.y, dz = pa%d_z - cur.z;", it.ps, it.ps, it.ps);
+                            o.line("            double v0 = wy * dz - wz * dy, v1 = wz * dx - wx * dz, v2 = wx * dy - wy * dx, w0 = wx, w1 = wy, w2 = wz;");
+                        }
+                        if (it.flags & TP_F_BCONST)
+                        {
+                            const double* b = prog.dbls.data() + it.cst_b;
+                            for (int r = 0; r < 3; ++r)
+                                o.line("            const double tv%d = %s;", r, dot_const({"v0", "v1", "v2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
+                            o.line("            v0 = tv0; v1 = tv1; v2 = tv2;");
+                            if (it.nrows == 6)
+                            {
+                                for (int r = 0; r < 3; ++r)
+                                    o.line("            const double tw%d = %s;", r, dot_const({"w0", "w1", "w2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
+                                o.line("            w0 = tw0; w1 = tw1; w2 = tw2;");
+                            }
+                        }
+                        const char* vals[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
+                        for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * 32, vals[r]);
+                        if (it.nrows != 6) o.line("            (void)w0; (void)w1; (void)w2;");
+                        o.line("        }");
+                        if (bt.last_item == itx)
+                        {
+                            const size_t nb = batches[1].size();
+                            emit_flush(bt, ibuf, zboxes.size() * it.batch / nb, zboxes.size() * (it.batch + 1) / nb);
+                        }
+                    }
+                }
+                o.line("    }");
+                if (op.dst >= 0)
+                {
+                    for (int k = 0; k < 9; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + k) * 32, kM[k]);
+                    for (int k = 0; k < 3; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + 9 + k) * 32, kP[k]);
+                }
+                issue_loads(q_used + AHEAD + 1, pass);
+            }
+            else if (op.kind == OP_EMIT_FRAME && pass == 0)
+            {
+                o.line("    // op %d: requested frame -> Phi[%d..], position slot %d", i, op.phi_off, op.n_items);
+                o.line("    {");
+                o.line("    Fr A;");
+                bool ident = false;
+                load_src(op.src, "A", ident);
+                const int offa = op.flags & F_OFFA_MASK;
+                double offc[12];
+                memcpy(offc, c + CE_OFFA_M, sizeof(offc));
+                if (offa == F_OFFA_NONE)
+                {
+                    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+                    memcpy(offc, I, sizeof(offc));
+                }
+                else if (offa == F_OFFA_TRANS)
+                {
+                    static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                    memcpy(offc, I9, sizeof(I9));
+                }
+                if (ident)
+                    emit_set_const(o, "A", offc);
+                else if (!is_identity12(offc))
+                    emit_mul_const(o, "A", "A", offc);
+                o.line("    pa%d_x = A.x; pa%d_y = A.y; pa%d_z = A.z;", op.n_items, op.n_items, op.n_items);
+                if ((op.flags & F_B_MASK) == F_B_CONST) emit_const_mul(o, "A", c + CE_B_M, "A");
+                const int itx = op_items[i][0];
+                const Item& it = items[itx];
+                const Batch& bt = batches[0][it.batch];
+                const Box& bx = bt.boxes[it.box];
+                const int ibuf = (flip + it.batch) & 1;
+                o.line("    write_phi(%d, %d, A, %s + %d, 32);", op.map_kind, op.rot_type, ibuf ? "stg1" : "stg0", bx.off * 32);
+                o.line("    }");
+                if (bt.last_item == itx) emit_flush(bt, ibuf, 0, 0);
+            }
+            else if (op.kind == OP_EMIT_JLIMIT && pass == 0)
+            {
+                o.line("    if (valid) emit_joint_limit(kOp%d, %d, xq, (int)P.x_sk, P.phi + %d * P.phi_sk + e, P.phi_sk, P.jac ? P.jac + %d * P.j_sr + e : nullptr, P.j_sr, P.j_sc);",
+                       i, N, op.phi_off, op.jrow_off);
+            }
+            else if (op.kind == OP_EMIT_FILL && pass == 0)
+            {
+                o.line("    if (valid) emit_fill(kOp%d, %d, %d, %d, P.phi + %d * P.phi_sk + e, P.phi_sk, P.jac ? P.jac + %d * P.j_sr + e : nullptr, P.j_sr, P.j_sc);", i,
+                       op.n_items, op.n_rows, N, op.phi_off, op.jrow_off);
+            }
+        }
+        flip = (int)((flip + batches[pass].size()) & 1);
+        if (pass == 1) o.line("    }");
+    }
+    if (batches[1].empty() && !zboxes.empty())
+    {
+        o.line("    if (lane == 0 && P.jac)");
+        o.line("    {");
+        for (const ZBox& z : zboxes) o.line("        tma3(&P.maps[%d], smem, e0i, %d, %d, pol);", z.map, z.c_col, z.c_row);
+        o.line("        tma_commit();");
+        o.line("    }");
+    }
+    o.line("    if (lane == 0) tma_wait_read();  // shared memory must outlive the TMA reads");
+    o.line("}");
+    plan.source.swap(o.s);
+    return true;
+}
+
+}  // namespace exo

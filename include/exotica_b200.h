@@ -146,6 +146,9 @@ typedef struct
     int32_t enable_z;        /* CenterOfMass EnableZ (init/center_of_mass.in): 0 keeps x and y only */
 } exo_task_map_desc;
 
+/* The library's run-time compiled kernels include this header for the enums above; the host entry points below are hidden
+ * from NVRTC (which defines __CUDACC_RTC__ and rejects host function declarations). */
+#ifndef __CUDACC_RTC__
 /* ---- errors / device ------------------------------------------------------------------------- */
 const char* exo_last_error(void);
 int exo_device_count(int* count);
@@ -236,9 +239,18 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
  * the Phi / J entries of its 64 / 128 evaluations in shared memory and the TMA unit stores them as 2-D tiles; needs
  * EXO_LAYOUT_SOA device buffers with an even, 16-byte aligned row pitch and a chain that owns every Jacobian column, else
  * EXO_ERR_UNSUPPORTED at launch; choice 0 takes this path automatically when those conditions hold, environment
- * EXO_CHAIN_TMA=0 keeps choice 0 on the per-lane stores).  Tests compare all of them. */
+ * EXO_CHAIN_TMA=0 keeps choice 0 on the per-lane stores), 9 = the per-robot generated kernel for tree programs (the
+ * two-pass program unrolled into straight-line CUDA C++ with the robot's constants as literals, compiled at run time with
+ * NVRTC for sm_100a and cached; one warp per 32 evaluations, Phi / J staged in shared memory and stored by the TMA unit,
+ * structural zeros of J from a shared zero tile; EffFrame / EffPosition / raw frames / JointLimit maps with constant base
+ * frames, EXO_LAYOUT_SOA buffers with an even row pitch; EXO_ERR_UNSUPPORTED otherwise; choice 0 takes it for batches of at
+ * least EXO_TREE_MIN_EVALS = 4096 evaluations, smaller ones stay on the interpreter).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
-/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_chain_tma_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
+/* CUDA source of the per-robot generated kernel (choice 9 above) for the current model state: copies at most capacity - 1
+ * characters into out (may be NULL) and reports the size needed; compile != 0 also runs NVRTC (no device needed) and returns
+ * EXO_ERR_UNSUPPORTED with the compiler log if it fails.  Replaces nothing in the reference: introspection for tests. */
+int exo_problem_generated_kernel_source(exo_problem* problem, char* out, int64_t capacity, int64_t* needed, int32_t compile);
+/* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_chain_tma_kernel" / "exo_tree_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
  * second launch of a SphereCollision program) / "none"). */
 const char* exo_problem_last_kernel(const exo_problem* problem);
 
@@ -393,6 +405,7 @@ typedef struct
 } exo_ik_params;
 int exo_problem_ik_solve_batch(exo_problem* problem, double* d_q, int64_t n_evals, const exo_ik_params* params, double* d_cost,
                                int32_t* d_iterations, int32_t* d_termination, void* stream);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

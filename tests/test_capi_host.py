@@ -104,7 +104,7 @@ def test_errors_use_the_status_and_message_channel(oracle_lib):
         prob2 = _capi.Problem(tree)
         prob2.add_task_map(_capi.MAP_CENTER_OF_MASS, elem_a=[3])
     with pytest.raises(_capi.ExoticaError, match="kernel choice"):
-        prob.set_kernel(9)
+        prob.set_kernel(10)
 
 
 def test_trajectory_matches_the_independent_restatement():
@@ -143,3 +143,26 @@ def test_trajectory_matches_the_independent_restatement():
         exo.Trajectory("1\n2 4\n0 0 0 0\n0 1 0 0").get_position(0.0)
     with pytest.raises(exo.ExoticaError, match="Invalid trajectory data size"):
         exo.Trajectory("1\n2 5\n0 0 0 0 0\n1 1 0 0 0").get_position(0.0)
+
+
+def test_generated_tree_kernel_source_compiles_without_a_gpu():
+    """tree_codegen.cpp unrolls the 38-DoF humanoid's two-pass program into CUDA C++ and NVRTC compiles it for sm_100a (neither
+    needs a device); serial chains of SphereCollision maps are outside the generator's scope and say so."""
+    from oracle import oracle
+    urdf, srdf = robot_paths("valkyrie_sim")
+    orc = oracle.Oracle(oracle.load_robot(urdf, srdf, "whole_body"))
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": l} for l in ("leftFoot", "rightFoot", "leftPalm", "rightPalm")]}, {"type": "JointLimit"}]
+    orc.set_problem(maps)
+    gtree, prob = gpu_problem_from_maps(orc, maps)
+    src = prob.generated_kernel_source(compile=True)
+    # 6 + 6 + 6 + 3 + 7 + 7 joints feed the four frames, three of them the sliding joints of the floating base; two passes
+    assert src.count("SINCOS(q, sn, cs);") == 2 * 32 and src.count("emit_joint_limit(") == 1
+    assert "cp.async.bulk.tensor.3d.global.shared::cta" in src
+    urdf, srdf = robot_paths("lwr_simplified")
+    orc = oracle.Oracle(oracle.load_robot(urdf, srdf, "arm"))
+    maps = [{"type": "SphereCollision", "Precision": 0.1, "EndEffector": [{"Link": "lwr_arm_7_link", "Radius": 0.1, "Group": "a"},
+                                                                       {"Link": "", "LinkOffset": [0.5, 0, 0.5], "Radius": 0.1, "Group": "b"}]}]
+    orc.set_problem(maps)
+    gtree, prob = gpu_problem_from_maps(orc, maps)
+    with pytest.raises(_capi.ExoticaError, match="generated tree kernel not applicable"):
+        prob.generated_kernel_source()

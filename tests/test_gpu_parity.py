@@ -33,9 +33,13 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
     # (the default runs it as a second launch, exo_spheres_kernel), 7 / 8: the chain kernel with TMA stores (64 / 128 evaluations
     # per tile; SoA buffers with an even row pitch and chains that own every column only -- auto takes it when it applies)
     has_spheres = any(m["type"] == "SphereCollision" for m in maps)
-    for choice in (1, 0, 2, 3, 4, 5, 6, 7, 8):
+    # 9: the per-robot generated kernel for tree programs (run-time compiled; EffFrame / EffPosition / JointLimit maps with
+    # constant base frames, SoA buffers with an even row pitch)
+    for choice in (1, 0, 2, 3, 4, 5, 6, 7, 8, 9):
         prob.set_kernel(choice)
         if choice in (2, 3, 7, 8) and not any(k.startswith("exo_chain") for k in kernels):
+            continue
+        if choice == 9 and any(k.startswith("exo_chain") for k in kernels):
             continue
         if choice == 6 and not has_spheres:
             continue
@@ -43,6 +47,8 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
             phi, jac = run_gpu(prob, X, layout=layout, T=T)
         except _capi.ExoticaError as err:
             if choice in (7, 8) and "TMA output path" in str(err):
+                continue
+            if choice == 9 and "generated tree kernel not applicable" in str(err) and "compilation failed" not in str(err):
                 continue
             raise
         kernels.add(prob.last_kernel())
@@ -160,6 +166,45 @@ def test_valkyrie_multi_end_effector(oracle_lib):
     maps = [{"type": "EffFrame", "EndEffector": [{"Link": "leftPalm", "Base": "rightPalm"}]},
             {"type": "EffPosition", "EndEffector": [{"Link": "head"}]}]
     _check(orc, maps, X[:256])
+
+
+@pytest.mark.parametrize("E", [32, 3002, 4097, 8191 + 1])
+def test_generated_tree_kernel(oracle_lib, E):
+    """Per-robot generated kernel (tree_codegen.cpp + NVRTC, exo_problem_set_kernel(9)) on the 38-DoF humanoid: every rotation
+    encoding, EffPosition and JointLimit beside the EffFrame map, ragged tiles (the TMA unit clips them), a constant base offset,
+    an angle beyond the fast trig range, odd batch sizes falling back to the interpreter."""
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffFrame", "Type": "Quaternion" if E == 32 else ("AngleAxis" if E == 3002 else "RPY"), "EndEffector": [
+                {"Link": "leftFoot"}, {"Link": "rightFoot", "LinkOffset": [0.01, 0.02, 0.03, 0.1, 0.2, 0.3]},
+                {"Link": "leftPalm", "BaseOffset": [0.2, 0.1, 0.3, 0.0, 0.3, 0.1]}, {"Link": "rightPalm"}]},
+            {"type": "EffPosition", "EndEffector": [{"Link": "head"}, {"Link": "torso"}]},
+            {"type": "JointLimit", "SafePercentage": 0.05}]
+    X = random_states(orc, E, seed=500 + E)
+    X[:, 3:6] = np.random.default_rng(E).uniform(-1.3, 1.3, size=(E, 3))
+    X[min(E - 1, 40), 20] = 3.0e5  # beyond the fast sin / cos reduction: the cold path of that joint
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    wrap = angle_entries(maps, orc)
+    prob.set_kernel(9)
+    if E % 2:
+        with pytest.raises(_capi.ExoticaError, match="even, 16-byte aligned row pitch"):
+            run_gpu(prob, X)
+        prob.set_kernel(0)  # auto: the interpreter takes the odd batch
+        phi, jac = run_gpu(prob, X)
+        assert prob.last_kernel() == "exo_eval_kernel"
+    else:
+        phi, jac = run_gpu(prob, X)
+        assert prob.last_kernel() == "exo_tree_kernel"
+        phi_only, _ = run_gpu(prob, X, want_jacobian=False)
+        assert np.array_equal(phi_only, phi)
+    assert record("generated_tree_phi", max_abs_err(phi, phi_ref, wrap)) <= TOL
+    assert record("generated_tree_jac", max_abs_err(jac, jac_ref)) <= TOL
+    # model state change (a joint outside the group): the source is regenerated with the new constants
+    if E == 3002:
+        prob.set_kernel(9)
+        src = prob.generated_kernel_source()
+        assert "exo_tree_kernel" in src and "cp.async.bulk.tensor.3d" in src
 
 
 def test_gimbal_lock_set(oracle_lib):
