@@ -679,7 +679,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     k.n_evals = E;
     int rc = fill_strides(p, layout, stride_E, k);
     if (rc != EXO_OK) return rc;
-    const bool chain = p->chain_ok && p->kernel_choice != 1;
+    const bool chain = p->chain_ok && p->kernel_choice != 1 && p->kernel_choice != 9;
     if (!chain && p->kernel_choice >= 2 && p->kernel_choice != 9) return fail(EXO_ERR_UNSUPPORTED, "the compiled program is not a serial chain: the chain kernel cannot run it");
     LaunchConfig cfg;
     int n_sph_ops = 0;
@@ -717,7 +717,7 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
         if (!gen && p->kernel_choice == 9) return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
     }
     else if (p->kernel_choice == 9)
-        return fail(EXO_ERR_UNSUPPORTED, chain ? "the program is a serial chain: the chain kernels run it" : "generated tree kernel not applicable: SphereCollision");
+        return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: SphereCollision");
     if (!chain && !gen)
     {
         if (!p->plan_valid || p->plan_split != split)

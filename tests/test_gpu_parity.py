@@ -39,8 +39,6 @@ def _check(orc, maps, X, layout=_capi.LAYOUT_SOA, T=1, generated=None, tol=TOL):
         prob.set_kernel(choice)
         if choice in (2, 3, 7, 8) and not any(k.startswith("exo_chain") for k in kernels):
             continue
-        if choice == 9 and any(k.startswith("exo_chain") for k in kernels):
-            continue
         if choice == 6 and not has_spheres:
             continue
         try:
@@ -83,8 +81,8 @@ def test_lwr_example_ik_config(oracle_lib):
              "LinkOffset": [0, 0, 0, 0.7071067811865476, -4.3297802811774664e-17, 0.7071067811865475, 4.3297802811774664e-17]}]}]
     X = np.vstack([np.zeros((1, 7)), random_states(orc, 1023, seed=3)])
     prob, phi, jac = _check(orc, maps, X)
-    # link 6 leaves column 6 to no chain joint: the per-lane store kernel runs it, the TMA path declines
-    assert prob.kernels_used == {"exo_eval_kernel", "exo_chain_kernel"}
+    # link 6 leaves column 6 to no chain joint: the per-lane store kernel runs it, the chain kernel's TMA path declines
+    assert prob.kernels_used == {"exo_eval_kernel", "exo_chain_kernel", "exo_tree_kernel"}
     assert np.all(jac[:, :, 6] == 0.0)  # joint 6 moves link 7 only
 
 
