@@ -165,7 +165,7 @@ struct TreeGenPlan
 {
     struct MapShape
     {
-        int phi;           // 1: 2-D box of Phi[LP][E]; 0: 3-D box of J[LJ][N][E]
+        int phi;           // 1: 2-D box of Phi[LP][E]; 0: 3-D box of J[LJ][N][E]; 2: 2-D box of the flattened J[LJ * N][E]
         int ncols, nrows;  // box = [nrows][ncols][32]
     };
     std::string source;
@@ -173,6 +173,7 @@ struct TreeGenPlan
     int warps_per_cta = 4;
     size_t smem_bytes = 0;
     int n_ctrl = 0, length_phi = 0, length_jac = 0;
+    bool needs_flat_jacobian = false;  // some boxes address J as [LJ * N][E]: the row pitch must be N column pitches
 };
 struct TreeGenParams  // mirrored by the generated source
 {

@@ -136,6 +136,7 @@ struct Item  // one block of values a lane stages: the Phi entries of a frame, o
     int ps, flags, cst_b; // J: position slot, TP_F_* flags, constant offset of Binv
     int box = -1, col_in_box = 0;
     int batch = -1;       // index of its batch within its pass
+    int jop = -1;         // J: the joint op whose axis / origin the column is built from
 };
 struct Box
 {
@@ -241,6 +242,32 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         why = "more than 16 requested frames";
         return false;
     }
+    // One pass when the axes and origins of all joints fit in registers (serial arms): the columns of a frame are staged right
+    // after its Phi, from the recorded (w, p) of the joints below it.  Larger trees recompose the tree for the Jacobian pass.
+    int n_joint_ops = 0;
+    for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i) n_joint_ops += prog.ops[i].kind == OP_JOINT;
+    const bool one_pass = n_joint_ops <= env_int("EXO_TREE_ONEPASS_MAX", 8, 0, 16);
+    std::vector<char> joint_recorded(n_ops, 0);
+    if (one_pass)
+    {
+        std::vector<int> frame_op_of_ps(n_pos, -1);
+        for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+            if (prog.ops[i].kind == OP_EMIT_FRAME) frame_op_of_ps[prog.ops[i].n_items] = i;
+        for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+        {
+            if (prog.ops[i].kind != OP_JOINT) continue;
+            for (int itx : op_items[i])
+            {
+                items[itx].jop = i;
+                op_items[frame_op_of_ps[items[itx].ps]].push_back(itx);
+                joint_recorded[i] = 1;
+            }
+            op_items[i].clear();
+        }
+    }
+    else
+        for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+            for (int itx : op_items[i]) items[itx].jop = i;
     // ---- geometry ---------------------------------------------------------------------------------------------------------------
     const int WPC = env_int("EXO_TREE_WPC", 4, 1, 8);            // warps (= tiles in flight) per CTA
     int CAP = env_int("EXO_TREE_CAP", 24, 3, 96);                // staging rows per buffer
@@ -265,7 +292,8 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             if (op.kind != OP_EMIT_FRAME && op.kind != OP_JOINT) continue;
             for (int it : op_items[i])
             {
-                if (used + items[it].nrows > CAP && !cur.items.empty())
+                const bool kind_change = !cur.items.empty() && items[cur.items.back()].phi != items[it].phi;
+                if ((used + items[it].nrows > CAP || kind_change) && !cur.items.empty())
                 {
                     batches[pass].push_back(cur);
                     cur = Batch();
@@ -281,11 +309,11 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     }
     // boxes: Phi -> one 2-D box per frame; J -> per frame, runs of consecutive columns become one 3-D box [rows][columns][32]
     plan.maps.clear();
-    auto map_id = [&](bool phi, int ncols, int nrows) {
+    auto map_id = [&](int kind, int ncols, int nrows) {  // kind: 0 J [rows][columns][32], 1 Phi [rows][32], 2 J flattened [LJ * N rows][32]
         for (size_t m = 0; m < plan.maps.size(); ++m)
-            if (plan.maps[m].phi == (phi ? 1 : 0) && plan.maps[m].ncols == ncols && plan.maps[m].nrows == nrows) return (int)m;
+            if (plan.maps[m].phi == kind && plan.maps[m].ncols == ncols && plan.maps[m].nrows == nrows) return (int)m;
         TreeGenPlan::MapShape sh;
-        sh.phi = phi ? 1 : 0; sh.ncols = ncols; sh.nrows = nrows;
+        sh.phi = kind; sh.ncols = ncols; sh.nrows = nrows;
         plan.maps.push_back(sh);
         return (int)plan.maps.size() - 1;
     };
@@ -293,13 +321,13 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         for (Batch& b : batches[pass])
         {
             int off = 0;
-            if (pass == 0)
+            if (items[b.items[0]].phi)
             {
                 for (int it : b.items)
                 {
                     Box bx;
                     bx.phi = true; bx.nrows = items[it].nrows; bx.ncols = 1; bx.off = off; bx.c_col = 0; bx.c_row = items[it].key;
-                    bx.map = map_id(true, 1, bx.nrows);
+                    bx.map = map_id(1, 1, bx.nrows);
                     items[it].box = (int)b.boxes.size();
                     b.boxes.push_back(bx);
                     off += bx.nrows;
@@ -317,7 +345,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 Box bx;
                 bx.phi = false; bx.nrows = items[order[k]].nrows; bx.ncols = (int)(k1 - k); bx.off = off; bx.c_col = items[order[k]].col;
                 bx.c_row = items[order[k]].key;
-                bx.map = map_id(false, bx.ncols, bx.nrows);
+                bx.map = map_id(0, bx.ncols, bx.nrows);
                 for (size_t q = k; q < k1; ++q)
                 {
                     items[order[q]].box = (int)b.boxes.size();
@@ -331,14 +359,35 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     // structural zeros: per frame emit, runs of columns no joint owns -> boxes [rows][<= ZC columns][32] from the zero tile
     struct ZBox
     {
-        int map, c_col, c_row;
+        int map, c_col, c_row;  // c_col < 0: box of the flattened view J[LJ * N][E], c_row its first flattened row
     };
     std::vector<ZBox> zboxes;
     int z_rows_max = 0;
+    const int ZFLAT = env_int("EXO_TREE_ZFLAT", 24, 1, 64);  // rows of the flattened zero boxes
+    bool needs_flat = false;
+    auto flat_zero_run = [&](int row0, int len) {  // flattened rows [row0, row0 + len) are zero
+        if (len <= 0) return;
+        const int h = std::min(len, ZFLAT);
+        const int id = map_id(2, 1, h);
+        for (int r = 0; r < len; r += h) zboxes.push_back({id, -1, row0 + std::min(r, len - h)});
+        z_rows_max = std::max(z_rows_max, h);
+        needs_flat = true;
+    };
     for (int i = 0; i < n_ops; ++i)
     {
         const Op& op = prog.ops[i];
         if (op.kind == OP_END) break;
+        if (op.kind == OP_EMIT_JLIMIT)
+        {
+            // rows jrow_off + i, i < N: the diagonal entry is a per-lane store, the N flattened rows between two diagonals are zero
+            for (int r = 0; r + 1 < N; ++r) flat_zero_run((op.jrow_off + r) * N + r + 1, N);
+            continue;
+        }
+        if (op.kind == OP_EMIT_FILL)
+        {
+            flat_zero_run(op.jrow_off * N, op.n_rows * N);
+            continue;
+        }
         if (op.kind != OP_EMIT_FRAME) continue;
         const int nrows = op.n_rows;
         const int32_t* zl = &prog.ints[op.pad];
@@ -348,12 +397,13 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             while (k1 <= zl[0] && zl[k1] == zl[k1 - 1] + 1) ++k1;
             const int c0 = zl[k], len = k1 - k;
             const int w = std::min(len, ZC);
-            const int id = map_id(false, w, nrows);
+            const int id = map_id(0, w, nrows);
             for (int c = 0; c < len; c += w) zboxes.push_back({id, c0 + std::min(c, len - w), op.jrow_off});
             z_rows_max = std::max(z_rows_max, w * nrows);
             k = k1;
         }
     }
+    plan.needs_flat_jacobian = needs_flat;
     if ((int)plan.maps.size() > TREE_MAXMAPS)
     {
         why = "more distinct TMA box shapes than the kernel parameter holds";
@@ -393,19 +443,6 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     o.line("static __device__ __forceinline__ void fence_staged() { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); }");
     o.line("static __device__ __noinline__ double2 slow_sincos(double q) { double s, c; sincos(q, &s, &c); return make_double2(s, c); }");
     o.line("#define SINCOS(q, s, c) do { if (fabs(q) <= 1.0e5) fast_sincos((q), (s), (c)); else { const double2 sc_ = slow_sincos(q); (s) = sc_.x; (c) = sc_.y; } } while (0)");
-    // constants of JointLimit / fill ops
-    for (int i = 0; i < n_ops; ++i)
-    {
-        const Op& op = prog.ops[i];
-        if (op.kind == OP_END) break;
-        int n = 0;
-        if (op.kind == OP_EMIT_JLIMIT) n = 1 + 2 * N;
-        if (op.kind == OP_EMIT_FILL) n = op.n_items;
-        if (n == 0) continue;
-        std::string arr;
-        for (int k = 0; k < n; ++k) arr += (k ? ", " : "") + lit(prog.dbls[op.cst + k]);
-        o.line("__constant__ double kOp%d[%d] = {%s};", i, n, arr.c_str());
-    }
     const int min_blocks = env_int("EXO_TREE_MINB", 0, 0, 8);
     if (min_blocks)
         o.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32, min_blocks);
@@ -425,16 +462,30 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     o.line("    double* const wsm = smem + %d + warp * %d;", ZROWS * 32, per_warp * 32);
     o.line("    double* const stg0 = wsm + lane;                 // staging buffer 0: row r at stg0[r * 32]");
     o.line("    double* const stg1 = wsm + %d + lane;", CAP * 32);
-    o.line("    double* const slot = wsm + %d + lane;            // frame slot s, word k at slot[(12 * s + k) * 32]", 2 * CAP * 32);
+    if (n_slots > 0) o.line("    double* const slot = wsm + %d + lane;            // frame slot s, word k at slot[(12 * s + k) * 32]", 2 * CAP * 32);
     o.line("    const double* const xq = P.x + e;");
     o.line("    unsigned long long pol = 0;");
     o.line("    if (lane == 0) asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %%0, 1.0;\" : \"=l\"(pol));");
     o.line("    Fr cur;");
     for (int k = 0; k < n_pos; ++k) o.line("    double pa%d_x = 0.0, pa%d_y = 0.0, pa%d_z = 0.0;", k, k, k);
+    for (int i = 0; i < n_ops; ++i)
+        if (joint_recorded[i]) o.line("    double jw%d_x, jw%d_y, jw%d_z, jp%d_x, jp%d_y, jp%d_z;  // axis and origin of the joint of op %d", i, i, i, i, i, i, i);
 
-    int flip = 0;  // staging buffer the next batch uses
-    // zero boxes ride along with the flushes of pass 2 in equal shares (one lane issues them: no per-lane work at all)
-    auto emit_flush = [&](const Batch& b, int buf, size_t z0, size_t z1) {
+    // J batches in execution order: zero boxes ride along with their flushes in equal shares (one lane issues them: no per-lane
+    // work at all)
+    int n_jbatches = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (const Batch& b : batches[pass]) n_jbatches += items[b.items[0]].phi ? 0 : 1;
+    int jb_seen = 0;
+    auto emit_zbox = [&](const ZBox& z, const char* ind) {
+        if (z.c_col < 0)
+            o.line("%stma2(&P.maps[%d], smem, e0i, %d, pol);", ind, z.map, z.c_row);
+        else
+            o.line("%stma3(&P.maps[%d], smem, e0i, %d, %d, pol);", ind, z.map, z.c_col, z.c_row);
+    };
+    int flip = 0;  // staging buffer of the first batch of the pass being emitted
+    auto emit_flush = [&](const Batch& b, int buf) {
+        const bool jb = !items[b.items[0]].phi;
         o.line("    if (lane == 0) tma_wait_read();  // the other staging buffer has been read out");
         o.line("    fence_staged();");
         o.line("    __syncwarp();");
@@ -447,7 +498,12 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             else
                 o.line("        tma3(&P.maps[%d], wsm + %d, e0i, %d, %d, pol);", bx.map, (buf * CAP + bx.off) * 32, bx.c_col, bx.c_row);
         }
-        for (size_t z = z0; z < z1; ++z) o.line("        tma3(&P.maps[%d], smem, e0i, %d, %d, pol);", zboxes[z].map, zboxes[z].c_col, zboxes[z].c_row);
+        if (jb)
+        {
+            const size_t z0 = zboxes.size() * jb_seen / n_jbatches, z1 = zboxes.size() * (jb_seen + 1) / n_jbatches;
+            for (size_t z = z0; z < z1; ++z) emit_zbox(zboxes[z], "        ");
+            ++jb_seen;
+        }
         o.line("        tma_commit();");
         o.line("    }");
     };
@@ -463,12 +519,47 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         else if (strcmp(dst, "cur") != 0)
             o.line("    %s = cur;", dst);
     };
+    // Jacobian column of one (joint, frame) pair into its staging rows -- KinematicTree::ComputeJ (kinematic_tree.cpp:919-945);
+    // w / p name the joint's axis and origin (registers of the current joint, or the recorded ones in one-pass mode)
+    auto emit_column = [&](const Item& it, int pass, const char* wn, const char* pn) {
+        const Batch& bt = batches[pass][it.batch];
+        const Box& bx = bt.boxes[it.box];
+        const int ibuf = (flip + it.batch) & 1;
+        const char* stg = ibuf ? "stg1" : "stg0";
+        o.line("        {");
+        if (it.flags & TP_F_PRISMATIC)
+            o.line("            double v0 = %sx, v1 = %sy, v2 = %sz, w0 = 0.0, w1 = 0.0, w2 = 0.0;", wn, wn, wn);
+        else
+        {
+            o.line("            const double dx = pa%d_x - %sx, dy = pa%d_y - %sy, dz = pa%d_z - %sz;", it.ps, pn, it.ps, pn, it.ps, pn);
+            o.line("            double v0 = %sy * dz - %sz * dy, v1 = %sz * dx - %sx * dz, v2 = %sx * dy - %sy * dx, w0 = %sx, w1 = %sy, w2 = %sz;", wn, wn, wn, wn, wn, wn, wn,
+                   wn, wn);
+        }
+        if (it.flags & TP_F_BCONST)
+        {
+            const double* b = prog.dbls.data() + it.cst_b;
+            for (int r = 0; r < 3; ++r) o.line("            const double tv%d = %s;", r, dot_const({"v0", "v1", "v2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
+            o.line("            v0 = tv0; v1 = tv1; v2 = tv2;");
+            if (it.nrows == 6)
+            {
+                for (int r = 0; r < 3; ++r)
+                    o.line("            const double tw%d = %s;", r, dot_const({"w0", "w1", "w2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
+                o.line("            w0 = tw0; w1 = tw1; w2 = tw2;");
+            }
+        }
+        const char* vals[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
+        for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * 32, vals[r]);
+        if (it.nrows != 6) o.line("            (void)w0; (void)w1; (void)w2;");
+        o.line("        }");
+        if (bt.last_item == (int)(&it - items.data())) emit_flush(bt, ibuf);
+    };
 
     // joint values are loaded AHEAD joints before they are used (the asm statements of the TMA path pin loads in place, and a
     // load issued where it is needed costs its full latency: ~1 us from DRAM while the memory system is saturated with stores)
     const int AHEAD = env_int("EXO_TREE_AHEAD", 8, 0, 16);
+    const int n_passes = one_pass ? 1 : 2;
     std::vector<std::pair<int, int>> qseq;  // (pass, op) of every joint that reads the state, in execution order
-    for (int pass = 0; pass < 2; ++pass)
+    for (int pass = 0; pass < n_passes; ++pass)
         for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
             if (prog.ops[i].kind == OP_JOINT && prog.ops[i].qidx >= 0) qseq.push_back({pass, i});
     size_t q_issued = 0;
@@ -480,11 +571,13 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         }
     };
     size_t q_used = 0;
-    for (int pass = 0; pass < 2; ++pass)
+    for (int pass = 0; pass < n_passes; ++pass)
     {
         if (pass == 1) o.line("    if (P.jac)\n    {");
+        o.line("    // ---- pass %d: %s", pass,
+               one_pass ? "compose the chain, record every joint's axis and origin, Phi and Jacobian columns of every requested frame"
+                        : (pass == 0 ? "compose the tree, Phi of every requested frame, park the frame origins" : "compose it again, Jacobian columns of every joint"));
         issue_loads(q_used + AHEAD + 1, pass);
-        o.line("    // ---- pass %d: %s", pass, pass == 0 ? "compose the tree, Phi of every requested frame, park the frame origins" : "compose it again, Jacobian columns of every joint");
         for (int i = 0; i < n_ops; ++i)
         {
             const Op& op = prog.ops[i];
@@ -524,7 +617,13 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 }
                 else
                     o.line("        const double q = %s;", lit(c[CJ_QOFF]).c_str());
-                if ((op.flags & F_PRISMATIC) || (pass == 1 && !op_items[i].empty())) o.line("        const double wx = cur.m2, wy = cur.m5, wz = cur.m8;");
+                const bool columns_now = pass == 1 && !op_items[i].empty();
+                if ((op.flags & F_PRISMATIC) || columns_now) o.line("        const double wx = cur.m2, wy = cur.m5, wz = cur.m8;");
+                if (joint_recorded[i])
+                {
+                    // the z column and the origin of the frame in front of the joint: its world axis and a point on it
+                    o.line("        jw%d_x = cur.m2; jw%d_y = cur.m5; jw%d_z = cur.m8; jp%d_x = cur.x; jp%d_y = cur.y; jp%d_z = cur.z;", i, i, i, i, i, i);
+                }
                 if (op.flags & F_PRISMATIC)
                 {
                     o.line("        cur.x = fma(wx, q, cur.x); cur.y = fma(wy, q, cur.y); cur.z = fma(wz, q, cur.z);");
@@ -538,48 +637,8 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                     o.line("        cur.m3 = fma(cs, a3, sn * cur.m4); cur.m4 = fma(cs, cur.m4, -(sn * a3));");
                     o.line("        cur.m6 = fma(cs, a6, sn * cur.m7); cur.m7 = fma(cs, cur.m7, -(sn * a6));");
                 }
-                if (pass == 1)
-                {
-                    // KinematicTree::ComputeJ (kinematic_tree.cpp:919-945) for every requested frame below this joint
-                    for (int itx : op_items[i])
-                    {
-                        const Item& it = items[itx];
-                        const Batch& bt = batches[1][it.batch];
-                        const Box& bx = bt.boxes[it.box];
-                        const int ibuf = (flip + it.batch) & 1;
-                        const char* stg = ibuf ? "stg1" : "stg0";
-                        o.line("        {");
-                        if (it.flags & TP_F_PRISMATIC)
-                            o.line("            double v0 = wx, v1 = wy, v2 = wz, w0 = 0.0, w1 = 0.0, w2 = 0.0;");
-                        else
-                        {
-                            o.line("            const double dx = pa%d_x - cur.x, dy = pa%d_y - cur.y, dz = pa%d_z - cur.z;", it.ps, it.ps, it.ps);
-                            o.line("            double v0 = wy * dz - wz * dy, v1 = wz * dx - wx * dz, v2 = wx * dy - wy * dx, w0 = wx, w1 = wy, w2 = wz;");
-                        }
-                        if (it.flags & TP_F_BCONST)
-                        {
-                            const double* b = prog.dbls.data() + it.cst_b;
-                            for (int r = 0; r < 3; ++r)
-                                o.line("            const double tv%d = %s;", r, dot_const({"v0", "v1", "v2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
-                            o.line("            v0 = tv0; v1 = tv1; v2 = tv2;");
-                            if (it.nrows == 6)
-                            {
-                                for (int r = 0; r < 3; ++r)
-                                    o.line("            const double tw%d = %s;", r, dot_const({"w0", "w1", "w2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
-                                o.line("            w0 = tw0; w1 = tw1; w2 = tw2;");
-                            }
-                        }
-                        const char* vals[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
-                        for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * 32, vals[r]);
-                        if (it.nrows != 6) o.line("            (void)w0; (void)w1; (void)w2;");
-                        o.line("        }");
-                        if (bt.last_item == itx)
-                        {
-                            const size_t nb = batches[1].size();
-                            emit_flush(bt, ibuf, zboxes.size() * it.batch / nb, zboxes.size() * (it.batch + 1) / nb);
-                        }
-                    }
-                }
+                if (columns_now)
+                    for (int itx : op_items[i]) emit_column(items[itx], 1, "w", "cur.");
                 o.line("    }");
                 if (op.dst >= 0)
                 {
@@ -621,27 +680,71 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 const int ibuf = (flip + it.batch) & 1;
                 o.line("    write_phi(%d, %d, A, %s + %d, 32);", op.map_kind, op.rot_type, ibuf ? "stg1" : "stg0", bx.off * 32);
                 o.line("    }");
-                if (bt.last_item == itx) emit_flush(bt, ibuf, 0, 0);
+                if (bt.last_item == itx) emit_flush(bt, ibuf);
+                if (op_items[i].size() > 1)
+                {
+                    // one-pass mode: the frame's Jacobian columns from the recorded joint axes / origins
+                    o.line("    if (P.jac)");
+                    o.line("    {");
+                    for (size_t k = 1; k < op_items[i].size(); ++k)
+                    {
+                        const Item& ji = items[op_items[i][k]];
+                        char wn[32], pn[32];
+                        snprintf(wn, sizeof(wn), "jw%d_", ji.jop);
+                        snprintf(pn, sizeof(pn), "jp%d_", ji.jop);
+                        emit_column(ji, 0, wn, pn);
+                    }
+                    o.line("    }");
+                    o.line("    else");
+                    o.line("    {");
+                    o.line("        if (lane == 0) tma_wait_read();  // no Jacobian batches in between: the next Phi block reuses a buffer");
+                    o.line("        __syncwarp();");
+                    o.line("    }");
+                }
             }
             else if (op.kind == OP_EMIT_JLIMIT && pass == 0)
             {
-                o.line("    if (valid) emit_joint_limit(kOp%d, %d, xq, (int)P.x_sk, P.phi + %d * P.phi_sk + e, P.phi_sk, P.jac ? P.jac + %d * P.j_sr + e : nullptr, P.j_sr, P.j_sc);",
-                       i, N, op.phi_off, op.jrow_off);
+                // JointLimit::Update (joint_limit.cpp:63-99): per-lane streaming stores of phi and of the diagonal of its Jacobian block
+                // (the zeros between the diagonal entries are TMA boxes of the zero tile)
+                o.line("    // op %d: JointLimit", i);
+                o.line("    if (valid)");
+                o.line("    {");
+                const double safe = c[0];
+                for (int k = 0; k < N; ++k)
+                {
+                    const double lo = c[1 + k], hi = c[1 + N + k];
+                    const double tau = (0.5 * safe) * (hi - lo);
+                    const double lo_t = lo + tau, hi_t = hi - tau;
+                    o.line("        {");
+                    o.line("            const double q = xq[%d * P.x_sk];", k);
+                    o.line("            double v = 0.0;");
+                    o.line("            if (q < %s) v = q - %s - %s;", lit(lo_t).c_str(), lit(lo).c_str(), lit(tau).c_str());
+                    o.line("            if (q > %s) v = q - %s + %s;", lit(hi_t).c_str(), lit(hi).c_str(), lit(tau).c_str());
+                    o.line("            __stcs(P.phi + %d * P.phi_sk + e, v);", op.phi_off + k);
+                    o.line("            if (P.jac) __stcs(P.jac + %d * P.j_sr + %d * P.j_sc + e, (q >= %s && q <= %s) ? 0.0 : 1.0);", op.jrow_off + k, k, lit(lo_t).c_str(),
+                           lit(hi_t).c_str());
+                    o.line("        }");
+                }
+                o.line("    }");
             }
             else if (op.kind == OP_EMIT_FILL && pass == 0)
             {
-                o.line("    if (valid) emit_fill(kOp%d, %d, %d, %d, P.phi + %d * P.phi_sk + e, P.phi_sk, P.jac ? P.jac + %d * P.j_sr + e : nullptr, P.j_sr, P.j_sc);", i,
-                       op.n_items, op.n_rows, N, op.phi_off, op.jrow_off);
+                // unused map: Phi.SetZero() values per lane; its zero Jacobian rows are TMA boxes of the zero tile
+                o.line("    // op %d: unused map", i);
+                o.line("    if (valid)");
+                o.line("    {");
+                for (int k = 0; k < op.n_items; ++k) o.line("        __stcs(P.phi + %d * P.phi_sk + e, %s);", op.phi_off + k, lit(c[k]).c_str());
+                o.line("    }");
             }
         }
         flip = (int)((flip + batches[pass].size()) & 1);
         if (pass == 1) o.line("    }");
     }
-    if (batches[1].empty() && !zboxes.empty())
+    if (jb_seen == 0 && !zboxes.empty())
     {
         o.line("    if (lane == 0 && P.jac)");
         o.line("    {");
-        for (const ZBox& z : zboxes) o.line("        tma3(&P.maps[%d], smem, e0i, %d, %d, pol);", z.map, z.c_col, z.c_row);
+        for (const ZBox& z : zboxes) emit_zbox(z, "        ");
         o.line("        tma_commit();");
         o.line("    }");
     }

@@ -245,15 +245,21 @@ bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, d
     if (n_evals < 1 || n_evals > 0x7fffffff || x_se != 1 || phi_se != 1 || (jac && j_se != 1)) return false;
     if (phi_sk < n_evals || (phi_sk & 1)) return false;
     if (jac && (j_sc < n_evals || (j_sc & 1) || (j_sr & 1))) return false;
+    if (jac && plan.needs_flat_jacobian && j_sr != (int64_t)plan.n_ctrl * j_sc) return false;
     if ((int)plan.maps.size() > TREE_MAXMAPS) return false;
     P.x = x; P.phi = phi; P.jac = jac;
     P.n_evals = n_evals; P.x_sk = x_sk; P.phi_sk = phi_sk; P.j_sr = j_sr; P.j_sc = j_sc;
     for (size_t m = 0; m < plan.maps.size(); ++m)
     {
         const TreeGenPlan::MapShape& sh = plan.maps[m];
-        if (sh.phi)
+        if (sh.phi == 1)
         {
             if (!tma_encode_2d(P.maps[m], phi, (uint64_t)n_evals, (uint64_t)plan.length_phi, (uint64_t)phi_sk * 8, 32, (uint32_t)sh.nrows)) return false;
+        }
+        else if (sh.phi == 2)
+        {
+            if (jac && !tma_encode_2d(P.maps[m], jac, (uint64_t)n_evals, (uint64_t)plan.length_jac * plan.n_ctrl, (uint64_t)j_sc * 8, 32, (uint32_t)sh.nrows))
+                return false;
         }
         else if (jac)
         {
