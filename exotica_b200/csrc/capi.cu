@@ -127,6 +127,8 @@ struct exo_problem
     double* d_jac[NBUF] = {};
     double* d_cost[NBUF] = {};
     double* d_grad[NBUF] = {};
+    double* d_cgs[NBUF] = {};       // per-stream scratch of the cost-gradient chunks (cost_gradient_impl)
+    int64_t cgs_bytes[NBUF] = {};
     int64_t pipe_chunk = 0;
     bool pipe_has_jac = false;
 };
@@ -349,7 +351,9 @@ static void free_pipeline(exo_problem* p)
         if (p->d_jac[i]) cudaFree(p->d_jac[i]);
         if (p->d_cost[i]) cudaFree(p->d_cost[i]);
         if (p->d_grad[i]) cudaFree(p->d_grad[i]);
-        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = p->d_cost[i] = p->d_grad[i] = nullptr;
+        if (p->d_cgs[i]) cudaFree(p->d_cgs[i]);
+        p->d_x[i] = p->d_phi[i] = p->d_jac[i] = p->d_cost[i] = p->d_grad[i] = p->d_cgs[i] = nullptr;
+        p->cgs_bytes[i] = 0;
     }
     p->pipe_chunk = 0;
 }
@@ -1191,7 +1195,10 @@ static bool fused_costgrad_eligible(exo_problem* p, ChainGradParams& g)
     return true;
 }
 
-int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj, double* d_grad, void* stream)
+// scratch / scratch_bytes: the buffer holding per-evaluation costs (+ Phi, J when the program is not fused); the public entry point
+// uses the problem's own, the host pipeline one per stream so that its chunks overlap
+static int cost_gradient_impl(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj, double* d_grad, void* stream,
+                              double** scratch, int64_t* scratch_bytes)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
     if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
@@ -1216,16 +1223,16 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
     memset(&g, 0, sizeof(g));
     const bool fused = fused_costgrad_eligible(p, g);
     const int64_t need = (E + (fused ? 0 : E * (LP + LJ * N))) * (int64_t)sizeof(double);
-    if (p->cg_bytes < need)
+    if (*scratch_bytes < need)
     {
         CUDA_TRY(cudaStreamSynchronize(s));
-        if (p->d_cg) CUDA_TRY(cudaFree(p->d_cg));
-        p->d_cg = nullptr;
-        p->cg_bytes = 0;
-        CUDA_TRY(cudaMalloc((void**)&p->d_cg, (size_t)need));
-        p->cg_bytes = need;
+        if (*scratch) CUDA_TRY(cudaFree(*scratch));
+        *scratch = nullptr;
+        *scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)scratch, (size_t)need));
+        *scratch_bytes = need;
     }
-    double* d_cost_eval = p->d_cg;
+    double* d_cost_eval = *scratch;
     if (fused)
     {
         const CostParams& c = p->cost;
@@ -1249,7 +1256,7 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
         return EXO_OK;
     }
     // general programs: Phi and J into the scratch buffer, then the cost and cost-gradient kernels
-    double* d_phi = p->d_cg + E;
+    double* d_phi = *scratch + E;
     double* d_jac = d_grad ? d_phi + E * LP : nullptr;  // cost only: forward kinematics without Jacobians
     rc = launch(p, d_x, E, E, (int32_t)T, layout, d_phi, d_jac, s, false);
     if (rc != EXO_OK) return rc;
@@ -1260,6 +1267,12 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
     }
     if (!d_grad) return EXO_OK;
     return exo_problem_cost_jacobian_batch(p, d_x, d_phi, d_jac, n_traj, layout, d_grad, stream);
+}
+
+int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj, double* d_grad, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    return cost_gradient_impl(p, d_x, n_traj, layout, d_cost_traj, d_grad, stream, &p->d_cg, &p->cg_bytes);
 }
 
 int exo_problem_aico_task_messages_batch(exo_problem* p, const double* d_qhat, const double* d_phi, const double* d_jac, int64_t n_traj, int32_t layout,
@@ -1449,23 +1462,34 @@ int exo_problem_cost_jacobian_batch_host(exo_problem* p, const double* h_x, int6
     // whole trajectories per chunk, ~32 MiB of device-side Phi + J per buffer; Phi and J never leave the device: N doubles per
     // evaluation (and one cost per trajectory) come back instead of length_jacobian x N
     int64_t traj_per_chunk = std::max<int64_t>(1, (32ll << 20) / std::max<int64_t>(1, (N + LP + LJ * N) * T * (int64_t)sizeof(double)));
+    {
+        // fused programs keep nothing but the states and the gradient on the device: chunks of ~4 MiB of states (large enough for
+        // the link, small enough that the first copy back starts early), one eighth of the batch at most
+        if (p->compiled_version != p->tree->version)
+        {
+            const int rcc = compile_and_upload(p);
+            if (rcc != EXO_OK) return rcc;
+        }
+        ChainGradParams probe;
+        memset(&probe, 0, sizeof(probe));
+        if (fused_costgrad_eligible(p, probe))
+        {
+            traj_per_chunk = std::max<int64_t>(1, (4ll << 20) / std::max<int64_t>(1, N * T * (int64_t)sizeof(double)));
+            traj_per_chunk = std::min(traj_per_chunk, std::max<int64_t>(1, (n_traj + exo_problem::NBUF - 1) / exo_problem::NBUF));
+        }
+    }
     if (traj_per_chunk > n_traj) traj_per_chunk = n_traj;
     int rc = ensure_pipeline(p, traj_per_chunk * T, false);
     if (rc != EXO_OK) return rc;
-    EventGuard prev_done;
     int b = 0;
     for (int64_t t0 = 0; t0 < n_traj; t0 += traj_per_chunk, b = (b + 1) % exo_problem::NBUF)
     {
         const int64_t nt = std::min(traj_per_chunk, n_traj - t0), n = nt * T;
         cudaStream_t s = p->streams[b];
         CUDA_TRY(cudaMemcpyAsync(p->d_x[b], h_x + t0 * T * N, n * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        // one scratch buffer per problem (exo_problem_cost_gradient_batch): the chunks' kernels are serialised on it through an
-        // event, their copies still overlap
-        if (prev_done.ev) CUDA_TRY(cudaStreamWaitEvent(s, prev_done.ev, 0));
-        rc = exo_problem_cost_gradient_batch(p, p->d_x[b], nt, layout, h_cost_traj ? p->d_cost[b] : nullptr, p->d_grad[b], s);
+        // every stream has its own scratch, so the chunks' kernels and copies overlap freely
+        rc = cost_gradient_impl(p, p->d_x[b], nt, layout, h_cost_traj ? p->d_cost[b] : nullptr, p->d_grad[b], s, &p->d_cgs[b], &p->cgs_bytes[b]);
         if (rc != EXO_OK) return rc;
-        if (!prev_done.ev) CUDA_TRY(cudaEventCreateWithFlags(&prev_done.ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(prev_done.ev, s));
         if (h_cost_traj) CUDA_TRY(cudaMemcpyAsync(h_cost_traj + t0, p->d_cost[b], nt * sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(h_grad + t0 * T * N, p->d_grad[b], n * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     }

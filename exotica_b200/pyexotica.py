@@ -445,16 +445,21 @@ class PlanningProblem(object):
         _check(_host.lib().exo_host_problem_cost_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data))
         return cost
 
-    def cost_jacobian_batch(self, X):
+    def cost_jacobian_batch(self, X, out_cost=None, out_jacobian=None):
         """(cost[B], jacobian like X): the gradient of cost_batch with respect to every state.  Time-indexed problems:
         AbstractTimeIndexedProblem.get_cost_jacobian() of each trajectory reshaped to [T][N] with a zero row for t = 0; end-pose
-        problems: get_scalar_jacobian().  Phi and J stay on the device: N doubles per evaluation come back."""
+        problems: get_scalar_jacobian().  Phi and J stay on the device: N doubles per evaluation come back.  out_cost /
+        out_jacobian: caller-owned result arrays (C-contiguous float64, shapes (B,) and X.shape) -- pinned ones (PinnedArray(...).array,
+        for X too) let the chunks' copies run asynchronously at link speed instead of through the driver's pageable staging."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         want = (self.T, self.N) if self.time_indexed else (self.N,)
         if X.ndim != len(want) + 1 or tuple(X.shape[1:]) != want:
             raise ExoticaError("Wrong state vector size! Got %s expected (B, %s)" % (X.shape, ", ".join(str(v) for v in want)))
-        cost = np.empty(X.shape[0])
-        jac = np.empty_like(X)
+        for name, arr, shape in (("out_cost", out_cost, (X.shape[0],)), ("out_jacobian", out_jacobian, X.shape)):
+            if arr is not None and (not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags.c_contiguous or arr.shape != tuple(shape)):
+                raise ExoticaError("%s must be a C-contiguous float64 array of shape %s" % (name, tuple(shape)))
+        cost = np.empty(X.shape[0]) if out_cost is None else out_cost
+        jac = np.empty_like(X) if out_jacobian is None else out_jacobian
         _check(_host.lib().exo_host_problem_cost_jacobian_batch(self._h, X.ctypes.data, X.shape[0], cost.ctypes.data, jac.ctypes.data))
         return cost, jac
 

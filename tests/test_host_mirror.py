@@ -147,6 +147,15 @@ def test_time_indexed_problem_trajectories_and_cost(oracle_lib):
     for b in range(B):
         gref = orc.trajectory_cost_jacobian(X[b], [10.0, 100.0], goal=goal, ct=1.0 / tau / T, W=W)
         assert np.max(np.abs(grad[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+    # the same through pinned, caller-owned buffers and many overlapping chunks (per-stream scratch): bitwise the same numbers
+    Xbig = np.tile(X, (40, 1, 1))
+    px, pc, pg = exo.PinnedArray(Xbig.shape), exo.PinnedArray((Xbig.shape[0],)), exo.PinnedArray(Xbig.shape)
+    px.array[:] = Xbig
+    c3, g3 = prob.cost_jacobian_batch(px.array, out_cost=pc.array, out_jacobian=pg.array)
+    assert c3 is pc.array and g3 is pg.array
+    assert np.array_equal(c3, np.tile(cost2, 40)) and np.array_equal(g3, np.tile(grad, (40, 1, 1)))
+    with pytest.raises(exo.ExoticaError, match="out_jacobian must be"):
+        prob.cost_jacobian_batch(X, out_jacobian=np.empty((B, T, 6)))
     # Update(x, t) of one timestep (abstract_time_indexed_problem.cpp:220-292)
     prob.update(X[2, 7], 7)
     assert max_abs_err(prob.Phi[7], phi_ref[2 * T + 7], angle_entries(maps, orc)) <= 1e-10

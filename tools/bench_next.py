@@ -128,7 +128,18 @@ def main():
     t1 = time.perf_counter()
     prob.cost_jacobian_batch(X)
     t2 = time.perf_counter()
-    line("host path: X in, cost + gradient out (Phi, J stay in HBM)", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * (E * N + B))
+    line("host path: X in (pinned), cost + gradient out into pageable arrays (Phi, J stay in HBM)", (t2 - t1) * 1e3, E, "evals", None, d2h_bytes=8 * (E * N + B))
+    pcost, pgrad = exo.PinnedArray((B,)), exo.PinnedArray((B, T, N))
+    prob.cost_jacobian_batch(X, out_cost=pcost.array, out_jacobian=pgrad.array)
+    best = 1e9
+    for _ in range(5):
+        t1 = time.perf_counter()
+        prob.cost_jacobian_batch(X, out_cost=pcost.array, out_jacobian=pgrad.array)
+        best = min(best, time.perf_counter() - t1)
+    c_ref, g_ref = prob.cost_jacobian_batch(X)
+    assert np.array_equal(c_ref, pcost.array) and np.array_equal(g_ref, pgrad.array)
+    line("host path: X in, cost + gradient out, all buffers pinned (best of 5)", best * 1e3, E, "evals", None, d2h_bytes=8 * (E * N + B),
+         h2d_bytes=8 * E * N, link_GBps=8 * (2 * E * N + B) / best / 1e9)
     prob.cost_batch(X)
     t1 = time.perf_counter()
     prob.cost_batch(X)
