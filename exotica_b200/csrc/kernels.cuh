@@ -171,6 +171,7 @@ struct TreeGenPlan
     std::string source;
     std::vector<MapShape> maps;
     int warps_per_cta = 4;
+    int tile = 32;  // evaluations per tile (inner box dimension)
     size_t smem_bytes = 0;
     int n_ctrl = 0, length_phi = 0, length_jac = 0;
     bool needs_flat_jacobian = false;  // some boxes address J as [LJ * N][E]: the row pitch must be N column pitches

@@ -269,7 +269,10 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
             for (int itx : op_items[i]) items[itx].jop = i;
     // ---- geometry ---------------------------------------------------------------------------------------------------------------
-    const int WPC = env_int("EXO_TREE_WPC", 4, 1, 8);            // warps (= tiles in flight) per CTA
+    const int TILE = env_int("EXO_TREE_TILE", 32, 32, 64) >= 64 ? 64 : 32;  // evaluations per tile: one warp, or a pair of warps (512-byte rows)
+    int WPC = env_int("EXO_TREE_WPC", 4, 1, 8);                  // warps per CTA
+    if (TILE == 64 && (WPC & 1)) ++WPC;
+    const int TPC = WPC * 32 / TILE;                             // tiles in flight per CTA
     int CAP = env_int("EXO_TREE_CAP", 24, 3, 96);                // staging rows per buffer
     const int ZC = env_int("EXO_TREE_ZC", 4, 1, 8);              // columns of the zero tile
     if (CAP < max_op_values) CAP = max_op_values;
@@ -411,9 +414,10 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     }
     const int ZROWS = std::max(z_rows_max, 1);
     const int n_slots = H.n_frame_slots;
-    const int per_warp = 2 * CAP + 12 * n_slots;  // staging rows (two buffers) + frame slots, in rows of 32 doubles
+    const int per_warp = 2 * CAP + 12 * n_slots;  // per tile: staging rows (two buffers) + frame slots, in rows of TILE doubles
     plan.warps_per_cta = WPC;
-    plan.smem_bytes = (size_t)(ZROWS + WPC * per_warp) * 32 * sizeof(double);
+    plan.tile = TILE;
+    plan.smem_bytes = (size_t)(ZROWS + TPC * per_warp) * TILE * sizeof(double);
     plan.n_ctrl = N;
     plan.length_phi = H.length_phi;
     plan.length_jac = H.length_jac;
@@ -450,19 +454,23 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         o.line("extern \"C\" __global__ void __launch_bounds__(%d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32);
     o.line("{");
     o.line("    extern __shared__ __align__(128) double smem[];");
-    o.line("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;");
-    o.line("    for (int i = threadIdx.x; i < %d; i += %d) smem[i] = 0.0;  // the zero tile", ZROWS * 32, WPC * 32);
+    o.line("    const int lane = threadIdx.x & %d, warp = threadIdx.x / %d;  // position in the tile, tile of the CTA", TILE - 1, TILE);
+    if (TILE == 32)
+        o.line("#define TILE_SYNC() __syncwarp()");
+    else
+        o.line("#define TILE_SYNC() asm volatile(\"bar.sync %%0, 64;\" ::\"r\"(1 + warp) : \"memory\")  // the two warps of this tile");
+    o.line("    for (int i = threadIdx.x; i < %d; i += %d) smem[i] = 0.0;  // the zero tile", ZROWS * TILE, WPC * 32);
     o.line("    fence_staged();");
     o.line("    __syncthreads();");
-    o.line("    const long long e0 = ((long long)blockIdx.x * %d + warp) * 32;", WPC);
+    o.line("    const long long e0 = ((long long)blockIdx.x * %d + warp) * %d;", TPC, TILE);
     o.line("    if (e0 >= P.n_evals) return;");
     o.line("    const bool valid = e0 + lane < P.n_evals;");
     o.line("    const long long e = valid ? e0 + lane : P.n_evals - 1;  // lanes past the batch redo the last evaluation; the TMA unit clips them");
     o.line("    const int e0i = (int)e0;");
-    o.line("    double* const wsm = smem + %d + warp * %d;", ZROWS * 32, per_warp * 32);
-    o.line("    double* const stg0 = wsm + lane;                 // staging buffer 0: row r at stg0[r * 32]");
-    o.line("    double* const stg1 = wsm + %d + lane;", CAP * 32);
-    if (n_slots > 0) o.line("    double* const slot = wsm + %d + lane;            // frame slot s, word k at slot[(12 * s + k) * 32]", 2 * CAP * 32);
+    o.line("    double* const wsm = smem + %d + warp * %d;", ZROWS * TILE, per_warp * TILE);
+    o.line("    double* const stg0 = wsm + lane;                 // staging buffer 0: row r at stg0[r * %d]", TILE);
+    o.line("    double* const stg1 = wsm + %d + lane;", CAP * TILE);
+    if (n_slots > 0) o.line("    double* const slot = wsm + %d + lane;            // frame slot s, word k at slot[(12 * s + k) * %d]", 2 * CAP * TILE, TILE);
     o.line("    const double* const xq = P.x + e;");
     o.line("    unsigned long long pol = 0;");
     o.line("    if (lane == 0) asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %%0, 1.0;\" : \"=l\"(pol));");
@@ -488,15 +496,15 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         const bool jb = !items[b.items[0]].phi;
         o.line("    if (lane == 0) tma_wait_read();  // the other staging buffer has been read out");
         o.line("    fence_staged();");
-        o.line("    __syncwarp();");
+        o.line("    TILE_SYNC();");
         o.line("    if (lane == 0)");
         o.line("    {");
         for (const Box& bx : b.boxes)
         {
             if (bx.phi)
-                o.line("        tma2(&P.maps[%d], wsm + %d, e0i, %d, pol);", bx.map, (buf * CAP + bx.off) * 32, bx.c_row);
+                o.line("        tma2(&P.maps[%d], wsm + %d, e0i, %d, pol);", bx.map, (buf * CAP + bx.off) * TILE, bx.c_row);
             else
-                o.line("        tma3(&P.maps[%d], wsm + %d, e0i, %d, %d, pol);", bx.map, (buf * CAP + bx.off) * 32, bx.c_col, bx.c_row);
+                o.line("        tma3(&P.maps[%d], wsm + %d, e0i, %d, %d, pol);", bx.map, (buf * CAP + bx.off) * TILE, bx.c_col, bx.c_row);
         }
         if (jb)
         {
@@ -513,8 +521,8 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             is_identity = true;
         else if (src >= 0)
         {
-            for (int k = 0; k < 9; ++k) o.line("    %s.%s = slot[%d];", dst, kM[k], (12 * src + k) * 32);
-            for (int k = 0; k < 3; ++k) o.line("    %s.%s = slot[%d];", dst, kP[k], (12 * src + 9 + k) * 32);
+            for (int k = 0; k < 9; ++k) o.line("    %s.%s = slot[%d];", dst, kM[k], (12 * src + k) * TILE);
+            for (int k = 0; k < 3; ++k) o.line("    %s.%s = slot[%d];", dst, kP[k], (12 * src + 9 + k) * TILE);
         }
         else if (strcmp(dst, "cur") != 0)
             o.line("    %s = cur;", dst);
@@ -548,7 +556,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             }
         }
         const char* vals[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
-        for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * 32, vals[r]);
+        for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * TILE, vals[r]);
         if (it.nrows != 6) o.line("            (void)w0; (void)w1; (void)w2;");
         o.line("        }");
         if (bt.last_item == (int)(&it - items.data())) emit_flush(bt, ibuf);
@@ -642,8 +650,8 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 o.line("    }");
                 if (op.dst >= 0)
                 {
-                    for (int k = 0; k < 9; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + k) * 32, kM[k]);
-                    for (int k = 0; k < 3; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + 9 + k) * 32, kP[k]);
+                    for (int k = 0; k < 9; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + k) * TILE, kM[k]);
+                    for (int k = 0; k < 3; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + 9 + k) * TILE, kP[k]);
                 }
                 issue_loads(q_used + AHEAD + 1, pass);
             }
@@ -678,7 +686,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 const Batch& bt = batches[0][it.batch];
                 const Box& bx = bt.boxes[it.box];
                 const int ibuf = (flip + it.batch) & 1;
-                o.line("    write_phi(%d, %d, A, %s + %d, 32);", op.map_kind, op.rot_type, ibuf ? "stg1" : "stg0", bx.off * 32);
+                o.line("    write_phi(%d, %d, A, %s + %d, %d);", op.map_kind, op.rot_type, ibuf ? "stg1" : "stg0", bx.off * TILE, TILE);
                 o.line("    }");
                 if (bt.last_item == itx) emit_flush(bt, ibuf);
                 if (op_items[i].size() > 1)
@@ -698,7 +706,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                     o.line("    else");
                     o.line("    {");
                     o.line("        if (lane == 0) tma_wait_read();  // no Jacobian batches in between: the next Phi block reuses a buffer");
-                    o.line("        __syncwarp();");
+                    o.line("        TILE_SYNC();");
                     o.line("    }");
                 }
             }

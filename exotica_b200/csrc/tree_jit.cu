@@ -254,16 +254,16 @@ bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, d
         const TreeGenPlan::MapShape& sh = plan.maps[m];
         if (sh.phi == 1)
         {
-            if (!tma_encode_2d(P.maps[m], phi, (uint64_t)n_evals, (uint64_t)plan.length_phi, (uint64_t)phi_sk * 8, 32, (uint32_t)sh.nrows)) return false;
+            if (!tma_encode_2d(P.maps[m], phi, (uint64_t)n_evals, (uint64_t)plan.length_phi, (uint64_t)phi_sk * 8, (uint32_t)plan.tile, (uint32_t)sh.nrows)) return false;
         }
         else if (sh.phi == 2)
         {
-            if (jac && !tma_encode_2d(P.maps[m], jac, (uint64_t)n_evals, (uint64_t)plan.length_jac * plan.n_ctrl, (uint64_t)j_sc * 8, 32, (uint32_t)sh.nrows))
+            if (jac && !tma_encode_2d(P.maps[m], jac, (uint64_t)n_evals, (uint64_t)plan.length_jac * plan.n_ctrl, (uint64_t)j_sc * 8, (uint32_t)plan.tile, (uint32_t)sh.nrows))
                 return false;
         }
         else if (jac)
         {
-            if (!tma_encode_3d(P.maps[m], jac, (uint64_t)n_evals, (uint64_t)plan.n_ctrl, (uint64_t)plan.length_jac, (uint64_t)j_sc * 8, (uint64_t)j_sr * 8, 32,
+            if (!tma_encode_3d(P.maps[m], jac, (uint64_t)n_evals, (uint64_t)plan.n_ctrl, (uint64_t)plan.length_jac, (uint64_t)j_sc * 8, (uint64_t)j_sr * 8, (uint32_t)plan.tile,
                                (uint32_t)sh.ncols, (uint32_t)sh.nrows))
                 return false;
         }
