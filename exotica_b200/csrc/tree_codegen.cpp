@@ -127,6 +127,105 @@ bool is_identity12(const double* C)
     return true;
 }
 
+// dst = the frame `src` names: a slot of the tile's shared memory, the running frame, or the root (identity: nothing is emitted)
+void emit_frame_source(Emitter& o, int src, const char* dst, int TILE, bool& is_identity)
+{
+    is_identity = false;
+    if (src == SRC_ROOT)
+        is_identity = true;
+    else if (src >= 0)
+    {
+        for (int k = 0; k < 9; ++k) o.line("    %s.%s = slot[%d];", dst, kM[k], (12 * src + k) * TILE);
+        for (int k = 0; k < 3; ++k) o.line("    %s.%s = slot[%d];", dst, kP[k], (12 * src + 9 + k) * TILE);
+    }
+    else if (strcmp(dst, "cur") != 0)
+        o.line("    %s = cur;", dst);
+}
+
+// a constant frame of the program with its kind flag applied (none / translation only / full)
+void const_frame(const double* c, int kind, int k_none, int k_trans, double out[12])
+{
+    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    memcpy(out, c, 12 * sizeof(double));
+    if (kind == k_none)
+        memcpy(out, I, 12 * sizeof(double));
+    else if (kind == k_trans)
+        memcpy(out, I, 9 * sizeof(double));
+}
+
+// OP_JOINT, first half: cur = parent frame * constant pre-multiplication
+void emit_joint_pre(Emitter& o, const Op& op, const double* c, int TILE)
+{
+    bool ident = false;
+    emit_frame_source(o, op.src, "cur", TILE, ident);
+    double prec[12];
+    const_frame(c, op.flags & F_PRE_MASK, F_PRE_NONE, F_PRE_TRANS, prec);
+    if (ident)
+        emit_set_const(o, "cur", prec);
+    else if (!is_identity12(prec))
+        emit_mul_const(o, "cur", "cur", prec);
+}
+
+// OP_JOINT, second half (inside the block the caller opened, after `q` is defined): the joint's world axis (if wanted), its
+// recorded axis / origin (one-pass programs, record_op >= 0) and the motion about / along z
+void emit_joint_motion(Emitter& o, const Op& op, bool want_w, int record_op)
+{
+    if ((op.flags & F_PRISMATIC) || want_w) o.line("        const double wx = cur.m2, wy = cur.m5, wz = cur.m8;");
+    if (record_op >= 0)
+    {
+        // the z column and the origin of the frame in front of the joint: its world axis and a point on it
+        const int i = record_op;
+        o.line("        jw%d_x = cur.m2; jw%d_y = cur.m5; jw%d_z = cur.m8; jp%d_x = cur.x; jp%d_y = cur.y; jp%d_z = cur.z;", i, i, i, i, i, i);
+    }
+    if (op.flags & F_PRISMATIC)
+    {
+        o.line("        cur.x = fma(wx, q, cur.x); cur.y = fma(wy, q, cur.y); cur.z = fma(wz, q, cur.z);");
+    }
+    else
+    {
+        o.line("        double sn, cs;");
+        o.line("        SINCOS(q, sn, cs);");
+        o.line("        const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;");
+        o.line("        cur.m0 = fma(cs, a0, sn * cur.m1); cur.m1 = fma(cs, cur.m1, -(sn * a0));");
+        o.line("        cur.m3 = fma(cs, a3, sn * cur.m4); cur.m4 = fma(cs, cur.m4, -(sn * a3));");
+        o.line("        cur.m6 = fma(cs, a6, sn * cur.m7); cur.m7 = fma(cs, cur.m7, -(sn * a6));");
+    }
+}
+
+void emit_slot_store(Emitter& o, int dst, int TILE)
+{
+    if (dst < 0) return;
+    for (int k = 0; k < 9; ++k) o.line("    slot[%d] = cur.%s;", (12 * dst + k) * TILE, kM[k]);
+    for (int k = 0; k < 3; ++k) o.line("    slot[%d] = cur.%s;", (12 * dst + 9 + k) * TILE, kP[k]);
+}
+
+// OP_EMIT_FRAME: A = frame * offset (its origin parked in pa<slot>), then A = Binv * A for a constant base (A is then Phi)
+void emit_requested_frame(Emitter& o, const Op& op, const double* c, int TILE)
+{
+    o.line("    Fr A;");
+    bool ident = false;
+    emit_frame_source(o, op.src, "A", TILE, ident);
+    double offc[12];
+    const_frame(c + CE_OFFA_M, op.flags & F_OFFA_MASK, F_OFFA_NONE, F_OFFA_TRANS, offc);
+    if (ident)
+        emit_set_const(o, "A", offc);
+    else if (!is_identity12(offc))
+        emit_mul_const(o, "A", "A", offc);
+    o.line("    pa%d_x = A.x; pa%d_y = A.y; pa%d_z = A.z;", op.n_items, op.n_items, op.n_items);
+    if ((op.flags & F_B_MASK) == F_B_CONST) emit_const_mul(o, "A", c + CE_B_M, "A");
+}
+
+// what every generated kernel starts with
+void emit_prelude(Emitter& o)
+{
+    o.line("#define EXO_STORE_CS 1");
+    o.line("#include \"device_math.cuh\"");
+    o.line("using namespace exo;");
+    o.line("using namespace exo::dev;");
+    o.line("static __device__ __noinline__ double2 slow_sincos(double q) { double s, c; sincos(q, &s, &c); return make_double2(s, c); }");
+    o.line("#define SINCOS(q, s, c) do { if (fabs(q) <= 1.0e5) fast_sincos((q), (s), (c)); else { const double2 sc_ = slow_sincos(q); (s) = sc_.x; (c) = sc_.y; } } while (0)");
+}
+
 struct Item  // one block of values a lane stages: the Phi entries of a frame, or one Jacobian column of one frame
 {
     int op;               // index of the op that produces it
@@ -431,10 +530,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     Emitter o;
     o.line("// generated by exotica_b200 tree_codegen: %d ops, %d controlled joints, %d frame slots, %d staging rows x 2, %d zero rows, %d TMA shapes", n_ops, N,
            n_slots, CAP, ZROWS, (int)plan.maps.size());
-    o.line("#define EXO_STORE_CS 1");
-    o.line("#include \"device_math.cuh\"");
-    o.line("using namespace exo;");
-    o.line("using namespace exo::dev;");
+    emit_prelude(o);
     o.line("struct alignas(64) TmaDesc { unsigned long long v[16]; };");
     o.line("struct TreeGenParams { const double* x; double* phi; double* jac; long long n_evals, x_sk, phi_sk, j_sr, j_sc; TmaDesc maps[%d]; };", TREE_MAXMAPS);
     o.line("static __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }");
@@ -445,8 +541,6 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     o.line("static __device__ __forceinline__ void tma_commit() { asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\"); }");
     o.line("static __device__ __forceinline__ void tma_wait_read() { asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\"); }");
     o.line("static __device__ __forceinline__ void fence_staged() { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); }");
-    o.line("static __device__ __noinline__ double2 slow_sincos(double q) { double s, c; sincos(q, &s, &c); return make_double2(s, c); }");
-    o.line("#define SINCOS(q, s, c) do { if (fabs(q) <= 1.0e5) fast_sincos((q), (s), (c)); else { const double2 sc_ = slow_sincos(q); (s) = sc_.x; (c) = sc_.y; } } while (0)");
     const int min_blocks = env_int("EXO_TREE_MINB", 0, 0, 8);
     if (min_blocks)
         o.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32, min_blocks);
@@ -515,18 +609,6 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         o.line("        tma_commit();");
         o.line("    }");
     };
-    auto load_src = [&](int src, const char* dst, bool& is_identity) {
-        is_identity = false;
-        if (src == SRC_ROOT)
-            is_identity = true;
-        else if (src >= 0)
-        {
-            for (int k = 0; k < 9; ++k) o.line("    %s.%s = slot[%d];", dst, kM[k], (12 * src + k) * TILE);
-            for (int k = 0; k < 3; ++k) o.line("    %s.%s = slot[%d];", dst, kP[k], (12 * src + 9 + k) * TILE);
-        }
-        else if (strcmp(dst, "cur") != 0)
-            o.line("    %s = cur;", dst);
-    };
     // Jacobian column of one (joint, frame) pair into its staging rows -- KinematicTree::ComputeJ (kinematic_tree.cpp:919-945);
     // w / p name the joint's axis and origin (registers of the current joint, or the recorded ones in one-pass mode)
     auto emit_column = [&](const Item& it, int pass, const char* wn, const char* pn) {
@@ -594,25 +676,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             if (op.kind == OP_JOINT)
             {
                 o.line("    // op %d: joint, state %d", i, op.qidx);
-                bool ident = false;
-                load_src(op.src, "cur", ident);
-                const int pre = op.flags & F_PRE_MASK;
-                double prec[12];
-                memcpy(prec, c, sizeof(prec));
-                if (pre == F_PRE_NONE)
-                {
-                    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
-                    memcpy(prec, I, sizeof(prec));
-                }
-                else if (pre == F_PRE_TRANS)
-                {
-                    static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-                    memcpy(prec, I9, sizeof(I9));
-                }
-                if (ident)
-                    emit_set_const(o, "cur", prec);
-                else if (!is_identity12(prec))
-                    emit_mul_const(o, "cur", "cur", prec);
+                emit_joint_pre(o, op, c, TILE);
                 o.line("    {");
                 if (op.qidx >= 0)
                 {
@@ -626,61 +690,18 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 else
                     o.line("        const double q = %s;", lit(c[CJ_QOFF]).c_str());
                 const bool columns_now = pass == 1 && !op_items[i].empty();
-                if ((op.flags & F_PRISMATIC) || columns_now) o.line("        const double wx = cur.m2, wy = cur.m5, wz = cur.m8;");
-                if (joint_recorded[i])
-                {
-                    // the z column and the origin of the frame in front of the joint: its world axis and a point on it
-                    o.line("        jw%d_x = cur.m2; jw%d_y = cur.m5; jw%d_z = cur.m8; jp%d_x = cur.x; jp%d_y = cur.y; jp%d_z = cur.z;", i, i, i, i, i, i);
-                }
-                if (op.flags & F_PRISMATIC)
-                {
-                    o.line("        cur.x = fma(wx, q, cur.x); cur.y = fma(wy, q, cur.y); cur.z = fma(wz, q, cur.z);");
-                }
-                else
-                {
-                    o.line("        double sn, cs;");
-                    o.line("        SINCOS(q, sn, cs);");
-                    o.line("        const double a0 = cur.m0, a3 = cur.m3, a6 = cur.m6;");
-                    o.line("        cur.m0 = fma(cs, a0, sn * cur.m1); cur.m1 = fma(cs, cur.m1, -(sn * a0));");
-                    o.line("        cur.m3 = fma(cs, a3, sn * cur.m4); cur.m4 = fma(cs, cur.m4, -(sn * a3));");
-                    o.line("        cur.m6 = fma(cs, a6, sn * cur.m7); cur.m7 = fma(cs, cur.m7, -(sn * a6));");
-                }
+                emit_joint_motion(o, op, columns_now, joint_recorded[i] ? i : -1);
                 if (columns_now)
                     for (int itx : op_items[i]) emit_column(items[itx], 1, "w", "cur.");
                 o.line("    }");
-                if (op.dst >= 0)
-                {
-                    for (int k = 0; k < 9; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + k) * TILE, kM[k]);
-                    for (int k = 0; k < 3; ++k) o.line("    slot[%d] = cur.%s;", (12 * op.dst + 9 + k) * TILE, kP[k]);
-                }
+                emit_slot_store(o, op.dst, TILE);
                 issue_loads(q_used + AHEAD + 1, pass);
             }
             else if (op.kind == OP_EMIT_FRAME && pass == 0)
             {
                 o.line("    // op %d: requested frame -> Phi[%d..], position slot %d", i, op.phi_off, op.n_items);
                 o.line("    {");
-                o.line("    Fr A;");
-                bool ident = false;
-                load_src(op.src, "A", ident);
-                const int offa = op.flags & F_OFFA_MASK;
-                double offc[12];
-                memcpy(offc, c + CE_OFFA_M, sizeof(offc));
-                if (offa == F_OFFA_NONE)
-                {
-                    static const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
-                    memcpy(offc, I, sizeof(offc));
-                }
-                else if (offa == F_OFFA_TRANS)
-                {
-                    static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-                    memcpy(offc, I9, sizeof(I9));
-                }
-                if (ident)
-                    emit_set_const(o, "A", offc);
-                else if (!is_identity12(offc))
-                    emit_mul_const(o, "A", "A", offc);
-                o.line("    pa%d_x = A.x; pa%d_y = A.y; pa%d_z = A.z;", op.n_items, op.n_items, op.n_items);
-                if ((op.flags & F_B_MASK) == F_B_CONST) emit_const_mul(o, "A", c + CE_B_M, "A");
+                emit_requested_frame(o, op, c, TILE);
                 const int itx = op_items[i][0];
                 const Item& it = items[itx];
                 const Batch& bt = batches[0][it.batch];
