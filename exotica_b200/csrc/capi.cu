@@ -104,6 +104,15 @@ struct exo_problem
     TreeGenPlan tree_plan;
     TreeGenParams tree_params;
     TmaKey tree_key;
+    // generated fused cost + gradient kernel for tree programs (tree_costgrad_codegen)
+    int tcg_version = -2;         // tree version the source below was generated for
+    int64_t cost_epoch = 0, tcg_cost_epoch = -1;  // exo_problem_set_cost calls / the one the cost structure below was read at
+    bool tcg_ok = false;
+    void* tcg_kernel = nullptr;
+    bool tcg_jit_failed = false;
+    std::string tcg_why;
+    TreeCostSpec tcg_spec;
+    TreeCostPlan tcg_plan;
     bool plan_valid = false;      // interpreter launch plan (depends on the program and on split_spheres only)
     bool plan_split = false;
     bool fused_spheres = false;   // exo_problem_set_kernel(6): SphereCollision inside the interpreter (no second launch)
@@ -1088,6 +1097,7 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
     c.goal_rot = p->d_goal_rot;
     c.W = p->d_W;
     p->cost_set = true;
+    p->cost_epoch++;
     return EXO_OK;
 }
 
@@ -1195,6 +1205,89 @@ static bool fused_costgrad_eligible(exo_problem* p, ChainGradParams& g)
     return true;
 }
 
+// Can the generated cost kernel serve this problem and cost?  Fills the per-frame cost map / goal rotation indices (position slots
+// follow the order of the frame emits in the two-pass program, which is the order of the maps' frames).
+static bool tree_costgrad_spec(exo_problem* p, const Program& tp, TreeCostSpec& spec)
+{
+    const CostParams& c = p->cost;
+    spec = TreeCostSpec();
+    std::vector<char> covered(p->maps.size(), 0);
+    for (const Op& op : tp.ops)
+    {
+        if (op.kind == OP_END) break;
+        if (op.kind != OP_EMIT_FRAME) continue;
+        int k_of = -1, rot = 0, frame_rot = -1;
+        for (int k = 0; k < c.n_maps && k_of < 0; ++k)
+        {
+            const CostMapP& m = c.map[k];
+            const bool lie = m.kind == EXO_MAP_EFF_FRAME || m.kind == EXO_MAP_EFF_ORIENTATION;
+            if (op.phi_off >= m.start && op.phi_off < m.start + m.length)
+            {
+                if (m.kind != EXO_MAP_EFF_FRAME && m.kind != EXO_MAP_EFF_POSITION) return false;
+                k_of = k;
+                frame_rot = m.kind == EXO_MAP_EFF_FRAME ? rot + (op.phi_off - m.start) / m.stride : -1;
+            }
+            else if (lie)
+                rot += m.n_frames;
+        }
+        if (k_of < 0) return false;
+        if ((int)spec.frame_map.size() <= op.n_items)
+        {
+            spec.frame_map.resize(op.n_items + 1, -1);
+            spec.frame_rot.resize(op.n_items + 1, -1);
+        }
+        spec.frame_map[op.n_items] = k_of;
+        spec.frame_rot[op.n_items] = frame_rot;
+        covered[k_of] = 1;
+    }
+    for (int k = 0; k < c.n_maps; ++k)
+    {
+        if (covered[k]) continue;
+        if (c.map[k].kind == EXO_MAP_JOINT_LIMIT && spec.jl_map < 0)
+        {
+            spec.jl_map = k;
+            continue;
+        }
+        // anything else (unused maps filled with their SetZero values, maps without frames) must not carry a cost
+        for (int t = 0; t < c.T; ++t)
+            if (p->cost_rho[(size_t)t * c.n_maps + k] != 0.0) return false;
+    }
+    return true;
+}
+
+// Source of the generated cost kernel for the current model state and cost structure
+static bool tree_costgrad_prepare(exo_problem* p)
+{
+    if (p->chain_ok || p->kernel_choice == 1) return false;
+    if (p->tcg_version == p->tree->version && p->tcg_cost_epoch == p->cost_epoch) return p->tcg_ok;
+    p->tcg_cost_epoch = p->cost_epoch;
+    std::string err;
+    Program tp;
+    std::vector<MapSpec> maps = p->maps;
+    if (!compile_program(p->tree->model, maps, tp, err, COMPILE_TWO_PASS))
+    {
+        p->tcg_why = err;
+        p->tcg_version = p->tree->version;
+        return p->tcg_ok = false;
+    }
+    TreeCostSpec spec;
+    if (!tree_costgrad_spec(p, tp, spec))
+    {
+        p->tcg_why = "the cost is not made of EffFrame / EffPosition / JointLimit maps";
+        p->tcg_version = p->tree->version;
+        return p->tcg_ok = false;
+    }
+    const bool same = p->tcg_version == p->tree->version && spec.frame_map == p->tcg_spec.frame_map && spec.frame_rot == p->tcg_spec.frame_rot &&
+                      spec.jl_map == p->tcg_spec.jl_map;
+    if (same) return p->tcg_ok;
+    p->tcg_version = p->tree->version;
+    p->tcg_spec = spec;
+    p->tcg_kernel = nullptr;
+    p->tcg_jit_failed = false;
+    p->tcg_ok = tree_costgrad_codegen(tp, spec, p->tcg_plan, p->tcg_why);
+    return p->tcg_ok;
+}
+
 // scratch / scratch_bytes: the buffer holding per-evaluation costs (+ Phi, J when the program is not fused); the public entry point
 // uses the problem's own, the host pipeline one per stream so that its chunks overlap
 static int cost_gradient_impl(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj, double* d_grad, void* stream,
@@ -1222,7 +1315,23 @@ static int cost_gradient_impl(exo_problem* p, const double* d_x, int64_t n_traj,
     ChainGradParams g;
     memset(&g, 0, sizeof(g));
     const bool fused = fused_costgrad_eligible(p, g);
-    const int64_t need = (E + (fused ? 0 : E * (LP + LJ * N))) * (int64_t)sizeof(double);
+    // tree programs: the generated fused kernel (run-time compiled on first use)
+    bool tree_fused = false;
+    if (!fused && !p->tcg_jit_failed && tree_costgrad_prepare(p))
+    {
+        if (!p->tcg_kernel)
+        {
+            std::string jerr;
+            p->tcg_kernel = tree_costgrad_jit_get(p->tcg_plan, jerr);
+            if (!p->tcg_kernel)
+            {
+                p->tcg_jit_failed = true;
+                p->tcg_why = "run-time compilation failed: " + jerr;
+            }
+        }
+        tree_fused = p->tcg_kernel != nullptr;
+    }
+    const int64_t need = (E + ((fused || tree_fused) ? 0 : E * (LP + LJ * N))) * (int64_t)sizeof(double);
     if (*scratch_bytes < need)
     {
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -1253,6 +1362,28 @@ static int cost_gradient_impl(exo_problem* p, const double* d_x, int64_t n_traj,
             p->launches++;
         }
         p->last_kernel = d_grad ? "exo_chain_costgrad_kernel" : "exo_chain_cost_kernel";
+        return EXO_OK;
+    }
+    if (tree_fused)
+    {
+        const CostParams& c = p->cost;
+        TreeCostParams tc;
+        memset(&tc, 0, sizeof(tc));
+        tc.x = d_x; tc.grad = d_grad; tc.cost_eval = d_cost_traj ? d_cost_eval : nullptr;
+        tc.rho = c.rho; tc.goal = c.goal; tc.goal_rot = c.goal_rot; tc.W = c.W;
+        tc.n_evals = E; tc.x_se = k.x_se; tc.x_sk = k.x_sk; tc.g_se = k.x_se; tc.g_sk = k.x_sk;
+        tc.ct = c.ct;
+        tc.T = c.T; tc.t_first = c.t_first; tc.T_goal = c.T_goal; tc.n_maps = c.n_maps; tc.length_phi = c.length_phi; tc.n_rot = c.n_rot;
+        cudaError_t e = tree_costgrad_jit_launch(p->tcg_kernel, p->tcg_plan, tc, s);
+        if (e != cudaSuccess) return cuda_fail(e, "generated cost-gradient kernel launch");
+        p->launches++;
+        if (d_cost_traj)
+        {
+            e = launch_reduce(d_cost_eval, n_traj, (int)T, 0, 1, d_cost_traj, s);
+            if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+            p->launches++;
+        }
+        p->last_kernel = "exo_tree_costgrad_kernel";
         return EXO_OK;
     }
     // general programs: Phi and J into the scratch buffer, then the cost and cost-gradient kernels

@@ -195,6 +195,36 @@ bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, d
                    int64_t phi_se, int64_t phi_sk, int64_t j_se, int64_t j_sr, int64_t j_sc);
 cudaError_t tree_jit_launch(void* kernel, const TreeGenPlan& plan, const TreeGenParams& P, cudaStream_t stream);
 
+// Generated fused forward kinematics + task cost + cost gradient for tree programs (exo_tree_costgrad_kernel): what
+// exo_chain_costgrad_kernel is for serial chains.  The cost STRUCTURE is compiled in (which cost map and goal rotation every
+// requested frame belongs to, the JointLimit map); rho, goals and W stay run-time arrays.
+struct TreeCostSpec
+{
+    std::vector<int> frame_map;  // per requested frame (position slot): index of its cost map (its rho)
+    std::vector<int> frame_rot;  // per requested frame: index into goal_rot, or -1 for position-only frames (EffPosition)
+    int jl_map = -1;             // cost map index of the JointLimit map or -1
+};
+struct TreeCostPlan
+{
+    std::string source;
+    int warps_per_cta = 4;
+    size_t smem_bytes = 0;
+};
+struct TreeCostParams  // mirrored by the generated source
+{
+    const double* x;
+    double* grad;       // may be NULL: cost only
+    double* cost_eval;  // [n_evals] or NULL
+    const double *rho, *goal, *goal_rot, *W;
+    long long n_evals, x_se, x_sk, g_se, g_sk;
+    double ct;
+    int T, t_first, T_goal, n_maps, length_phi, n_rot;
+};
+bool tree_costgrad_codegen(const Program& prog, const TreeCostSpec& cs, TreeCostPlan& plan, std::string& why);
+void* tree_costgrad_jit_get(const TreeCostPlan& plan, std::string& err);
+bool tree_costgrad_jit_compile(const TreeCostPlan& plan, std::vector<char>& cubin, std::string& err);
+cudaError_t tree_costgrad_jit_launch(void* kernel, const TreeCostPlan& plan, const TreeCostParams& P, cudaStream_t stream);
+
 // Fused forward kinematics + task cost + cost gradient for chain programs (exo_chain_costgrad_kernel): Phi and J are formed in
 // registers and contracted on the spot, only N doubles per evaluation (and its cost) reach HBM.
 struct ChainGradParams

@@ -783,4 +783,268 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     return true;
 }
 
+// ---- fused forward kinematics + task cost + cost gradient for tree programs ---------------------------------------------------------
+// The generated counterpart of exo_chain_costgrad_kernel (chain_kernel.cu): grad[e][n] = 2 ct (J^T S ydiff)[n] + the JointLimit and
+// transition terms (AbstractTimeIndexedProblem::GetCostJacobian, abstract_time_indexed_problem.cpp:309-342; T = 1:
+// UnconstrainedEndPoseProblem::GetScalarJacobian) without ever materialising J.  Pass 1 composes the tree, forms ydiff of every
+// requested frame (SO(3) log for EffFrame: TaskSpaceVector::operator-, task_space_vector.cpp:64-91), adds its cost and keeps
+// S ydiff (turned by Binv^T for a constant base) in registers; pass 2 composes the tree again and dots every joint's column with
+// S ydiff of the frames below it -- the joint owns exactly one gradient entry, which is complete and stored on the spot.  HBM
+// traffic per evaluation: N doubles in, N + 1 out.
+bool tree_costgrad_codegen(const Program& prog, const TreeCostSpec& cs, TreeCostPlan& plan, std::string& why)
+{
+    const ProgramHeader& H = prog.hdr;
+    if (!H.two_pass || H.n_generated > 0)
+    {
+        why = "the program has no two-pass form";
+        return false;
+    }
+    const int N = H.n_ctrl;
+    const int n_ops = (int)prog.ops.size();
+    int n_pos = 0, jl_op = -1;
+    for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_EMIT_FRAME)
+        {
+            const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
+            if ((row_mode != ROWS_VW && row_mode != ROWS_V) || (op.flags & F_B_MASK) == F_B_SLOT ||
+                (op.map_kind != EXO_MAP_EFF_FRAME && op.map_kind != EXO_MAP_EFF_POSITION))
+            {
+                why = "a requested frame is outside the generated cost kernel's scope";
+                return false;
+            }
+            n_pos = std::max(n_pos, op.n_items + 1);
+        }
+        else if (op.kind == OP_EMIT_JLIMIT)
+            jl_op = i;
+        else if (op.kind != OP_JOINT && op.kind != OP_EMIT_FILL)
+        {
+            why = "an op is outside the generated cost kernel's scope";
+            return false;
+        }
+    }
+    if (n_pos > 16 || (int)cs.frame_map.size() < n_pos || (int)cs.frame_rot.size() < n_pos)
+    {
+        why = "more requested frames than the generated cost kernel keeps in registers";
+        return false;
+    }
+    if (cs.jl_map >= 0 && jl_op < 0)
+    {
+        why = "the cost names a JointLimit map the program does not evaluate";
+        return false;
+    }
+    const int WPC = env_int("EXO_TREE_WPC", 4, 1, 8);
+    const int AHEAD = env_int("EXO_TREE_AHEAD", 8, 0, 16);
+    const int TILE = 32;
+    const int n_slots = H.n_frame_slots;
+    plan.warps_per_cta = WPC;
+    plan.smem_bytes = (size_t)WPC * 12 * n_slots * TILE * sizeof(double);
+
+    Emitter o;
+    o.line("// generated by exotica_b200 tree_costgrad_codegen: %d ops, %d controlled joints, %d frame slots", n_ops, N, n_slots);
+    emit_prelude(o);
+    o.line("struct TreeCostParams { const double* x; double* grad; double* cost_eval; const double* rho; const double* goal; const double* goal_rot; const double* W;");
+    o.line("    long long n_evals, x_se, x_sk, g_se, g_sk; double ct; int T, t_first, T_goal, n_maps, length_phi, n_rot; };");
+    o.line("extern \"C\" __global__ void __launch_bounds__(%d) exo_tree_costgrad_kernel(const __grid_constant__ TreeCostParams P)", WPC * 32);
+    o.line("{");
+    if (n_slots > 0) o.line("    extern __shared__ __align__(16) double smem[];");
+    o.line("    const long long e = (long long)blockIdx.x * %d + threadIdx.x;", WPC * 32);
+    o.line("    if (e >= P.n_evals) return;");
+    if (n_slots > 0) o.line("    double* const slot = smem + (threadIdx.x >> 5) * %d + (threadIdx.x & 31);  // frame slot s, word k at slot[(12 * s + k) * 32]", 12 * n_slots * TILE);
+    o.line("    const double* const xq = P.x + e * P.x_se;");
+    o.line("    const int t = (int)(e %% P.T);");
+    o.line("    const bool skip = t < P.t_first;  // GetCost sums t = 1 .. T - 1: the first timestep carries neither cost nor gradient");
+    o.line("    const double* const rho = P.rho + (long long)t * P.n_maps;");
+    o.line("    const int tg = P.T_goal > 1 ? t : 0;");
+    o.line("    const double* const goal = P.goal + (long long)tg * P.length_phi;");
+    o.line("    const double* const grot = P.goal_rot + (long long)tg * P.n_rot * 9;");
+    o.line("    double* const ge = P.grad ? P.grad + e * P.g_se : nullptr;");
+    o.line("    double c = 0.0;");
+    o.line("    Fr cur;");
+    for (int k = 0; k < n_pos; ++k)
+    {
+        o.line("    double pa%d_x = 0.0, pa%d_y = 0.0, pa%d_z = 0.0;", k, k, k);
+        o.line("    double s%d_0 = 0.0, s%d_1 = 0.0, s%d_2 = 0.0, s%d_3 = 0.0, s%d_4 = 0.0, s%d_5 = 0.0;  // S ydiff of the frame (turned by Binv^T)", k, k, k, k, k, k);
+    }
+    if (cs.jl_map >= 0) o.line("    const double rho_jl = rho[%d];", cs.jl_map);
+
+    // JointLimit and transition terms of column n (both diagonal in the joint index): their share of the cost goes into c, their
+    // share of the gradient (before the factor 2 ct) into `s`
+    const double* jlc = jl_op >= 0 ? prog.dbls.data() + prog.ops[jl_op].cst : nullptr;
+    const int jl_phi_off = jl_op >= 0 ? prog.ops[jl_op].phi_off : 0;
+    auto emit_extra = [&](int n, const char* ind) {
+        o.line("%sconst double xn = xq[%d * P.x_sk];", ind, n);
+        o.line("%sdouble s = 0.0;", ind);
+        if (cs.jl_map >= 0)
+        {
+            const double safe = jlc[0], lo = jlc[1 + n], hi = jlc[1 + N + n];
+            const double tau = (0.5 * safe) * (hi - lo);
+            const double lo_t = lo + tau, hi_t = hi - tau;
+            o.line("%s{", ind);
+            o.line("%s    double v = 0.0;", ind);
+            o.line("%s    if (xn < %s) v = xn - %s - %s;", ind, lit(lo_t).c_str(), lit(lo).c_str(), lit(tau).c_str());
+            o.line("%s    if (xn > %s) v = xn - %s + %s;", ind, lit(hi_t).c_str(), lit(hi).c_str(), lit(tau).c_str());
+            o.line("%s    const double yd = v - goal[%d];", ind, jl_phi_off + n);
+            o.line("%s    c += rho_jl * yd * yd;", ind);
+            o.line("%s    if (!(xn >= %s && xn <= %s)) s += rho_jl * yd;", ind, lit(lo_t).c_str(), lit(hi_t).c_str());
+            o.line("%s}", ind);
+        }
+        o.line("%sif (P.W && t > 0)", ind);
+        o.line("%s{", ind);
+        o.line("%s    const double w = P.W[%d];", ind, n);
+        o.line("%s    const double d0 = xn - xq[%d * P.x_sk - P.x_se];", ind, n);
+        o.line("%s    c += w * d0 * d0;", ind);
+        o.line("%s    s += w * d0;", ind);
+        o.line("%s    if (t + 1 < P.T) s -= w * (xq[%d * P.x_sk + P.x_se] - xn);", ind, n);
+        o.line("%s}", ind);
+    };
+
+    std::vector<std::pair<int, int>> qseq;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+            if (prog.ops[i].kind == OP_JOINT && prog.ops[i].qidx >= 0) qseq.push_back({pass, i});
+    size_t q_issued = 0, q_used = 0;
+    auto issue_loads = [&](size_t upto, int cur_pass) {
+        for (; q_issued < upto && q_issued < qseq.size(); ++q_issued)
+        {
+            if (qseq[q_issued].first != cur_pass) break;
+            o.line("    const double q_%d = xq[%d * P.x_sk];", (int)q_issued, prog.ops[qseq[q_issued].second].qidx);
+        }
+    };
+    std::vector<char> owned(N, 0);  // columns some joint of the program owns
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        if (pass == 1) o.line("    if (ge)\n    {");
+        o.line("    // ---- pass %d: %s", pass, pass == 0 ? "compose the tree; ydiff, cost and S ydiff of every requested frame" : "compose it again; every joint's gradient entry");
+        issue_loads(q_used + AHEAD + 1, pass);
+        for (int i = 0; i < n_ops; ++i)
+        {
+            const Op& op = prog.ops[i];
+            if (op.kind == OP_END) break;
+            const double* c = prog.dbls.data() + op.cst;
+            if (op.kind == OP_JOINT)
+            {
+                const int32_t* tp = &prog.ints[op.tab];
+                o.line("    // op %d: joint, state %d", i, op.qidx);
+                emit_joint_pre(o, op, c, TILE);
+                o.line("    {");
+                if (op.qidx >= 0)
+                {
+                    issue_loads(q_used + 1, pass);
+                    if (c[CJ_QMULT] == 1.0 && c[CJ_QOFF] == 0.0)
+                        o.line("        const double q = q_%d;", (int)q_used);
+                    else
+                        o.line("        const double q = fma(%s, q_%d, %s);", lit(c[CJ_QMULT]).c_str(), (int)q_used, lit(c[CJ_QOFF]).c_str());
+                    ++q_used;
+                }
+                else
+                    o.line("        const double q = %s;", lit(c[CJ_QOFF]).c_str());
+                const bool dots = pass == 1 && tp[0] > 0;
+                emit_joint_motion(o, op, dots, -1);
+                if (dots)
+                {
+                    // column . S ydiff for every frame below the joint: (w x d) . yv + w . yw (revolute), w . yv (prismatic)
+                    const int col = tp[2];
+                    owned[col] = 1;
+                    o.line("        double g = 0.0;");
+                    for (int k = 0; k < tp[0]; ++k)
+                    {
+                        const int32_t* ent = tp + 1 + TP_INTS * k;
+                        const int ps = ent[0];
+                        if (ent[1] != col)
+                        {
+                            why = "a joint feeds more than one Jacobian column";
+                            return false;
+                        }
+                        if (ent[4] & TP_F_PRISMATIC)
+                            o.line("        g += wx * s%d_0 + wy * s%d_1 + wz * s%d_2;", ps, ps, ps);
+                        else
+                        {
+                            o.line("        {");
+                            o.line("            const double dx = pa%d_x - cur.x, dy = pa%d_y - cur.y, dz = pa%d_z - cur.z;", ps, ps, ps);
+                            o.line("            g += (wy * dz - wz * dy) * s%d_0 + (wz * dx - wx * dz) * s%d_1 + (wx * dy - wy * dx) * s%d_2;", ps, ps, ps);
+                            if (ent[3] == ROWS_VW) o.line("            g += wx * s%d_3 + wy * s%d_4 + wz * s%d_5;", ps, ps, ps);
+                            o.line("        }");
+                        }
+                    }
+                    o.line("        {");
+                    emit_extra(col, "            ");
+                    o.line("            ge[%d * P.g_sk] = skip ? 0.0 : 2.0 * P.ct * (g + s);", col);
+                    o.line("        }");
+                }
+                o.line("    }");
+                emit_slot_store(o, op.dst, TILE);
+                issue_loads(q_used + AHEAD + 1, pass);
+            }
+            else if (op.kind == OP_EMIT_FRAME && pass == 0)
+            {
+                const int ps = op.n_items;
+                const bool six = cs.frame_rot[ps] >= 0;
+                o.line("    // op %d: requested frame %d, cost map %d", i, ps, cs.frame_map[ps]);
+                o.line("    {");
+                emit_requested_frame(o, op, c, TILE);  // A = Phi
+                o.line("    double y0 = A.x - goal[%d], y1 = A.y - goal[%d], y2 = A.z - goal[%d], y3 = 0.0, y4 = 0.0, y5 = 0.0;", op.phi_off, op.phi_off + 1, op.phi_off + 2);
+                if (six)
+                {
+                    // rotvec = M1 * (M2^-1 M1).GetRot()  (TaskSpaceVector::operator-, task_space_vector.cpp:64-91)
+                    o.line("    {");
+                    o.line("        const double* M2 = grot + %d;", 9 * cs.frame_rot[ps]);
+                    o.line("        Fr M;");
+                    for (int r = 0; r < 3; ++r)
+                        for (int k = 0; k < 3; ++k) o.line("        M.m%d = M2[%d] * A.m%d + M2[%d] * A.m%d + M2[%d] * A.m%d;", 3 * r + k, r, k, 3 + r, 3 + k, 6 + r, 6 + k);
+                    o.line("        M.x = M.y = M.z = 0.0;");
+                    o.line("        double vx, vy, vz;");
+                    o.line("        get_angle_axis(M, vx, vy, vz);");
+                    o.line("        y3 = A.m0 * vx + A.m1 * vy + A.m2 * vz;");
+                    o.line("        y4 = A.m3 * vx + A.m4 * vy + A.m5 * vz;");
+                    o.line("        y5 = A.m6 * vx + A.m7 * vy + A.m8 * vz;");
+                    o.line("    }");
+                }
+                o.line("    const double r = rho[%d];", cs.frame_map[ps]);
+                o.line("    c += r * (y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3 + y4 * y4 + y5 * y5);");
+                o.line("    y0 *= r; y1 *= r; y2 *= r; y3 *= r; y4 *= r; y5 *= r;  // S ydiff");
+                if ((op.flags & F_B_MASK) == F_B_CONST)
+                {
+                    // column = Binv [v; w]  ->  dot against Binv^T (S ydiff)
+                    const double* b = c + CE_B_M;
+                    for (int k = 0; k < 3; ++k) o.line("    s%d_%d = %s;", ps, k, dot_const({"y0", "y1", "y2"}, {b[k], b[3 + k], b[6 + k]}, "").c_str());
+                    for (int k = 0; k < 3; ++k) o.line("    s%d_%d = %s;", ps, 3 + k, dot_const({"y3", "y4", "y5"}, {b[k], b[3 + k], b[6 + k]}, "").c_str());
+                }
+                else
+                    o.line("    s%d_0 = y0; s%d_1 = y1; s%d_2 = y2; s%d_3 = y3; s%d_4 = y4; s%d_5 = y5;", ps, ps, ps, ps, ps, ps);
+                o.line("    }");
+            }
+        }
+        if (pass == 1)
+        {
+            // columns no joint of the program owns: JointLimit and transition terms only
+            for (int n = 0; n < N; ++n)
+            {
+                if (owned[n]) continue;
+                o.line("    {");
+                emit_extra(n, "        ");
+                o.line("        ge[%d * P.g_sk] = skip ? 0.0 : 2.0 * P.ct * s;", n);
+                o.line("    }");
+            }
+            o.line("    }");
+            o.line("    else");
+            o.line("    {");
+            o.line("    // cost only: the JointLimit and transition shares of every column");
+            for (int n = 0; n < N; ++n)
+            {
+                o.line("    {");
+                emit_extra(n, "        ");
+                o.line("        (void)s;");
+                o.line("    }");
+            }
+            o.line("    }");
+        }
+    }
+    o.line("    if (P.cost_eval) P.cost_eval[e] = skip ? 0.0 : P.ct * c;");
+    o.line("}");
+    plan.source.swap(o.s);
+    return true;
+}
+
 }  // namespace exo

@@ -135,7 +135,9 @@ std::mutex g_mu;
 std::map<std::pair<int, std::string>, Compiled*> g_cache;
 }  // namespace
 
-bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::string& err)
+namespace
+{
+bool compile_source(const std::string& source, std::vector<char>& cubin, std::string& err)
 {
     Nvrtc& n = nvrtc();
     if (!n.lib)
@@ -146,7 +148,7 @@ bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::st
     const char* headers[] = {kSrcDeviceMath, kSrcProgram, kSrcApi, kSrcStdint, kSrcStddef, kSrcMathConstants};
     const char* names[] = {"device_math.cuh", "program.h", "../../include/exotica_b200.h", "stdint.h", "stddef.h", "math_constants.h"};
     nvrtcProgram prog = nullptr;
-    nvrtcResult r = n.CreateProgram(&prog, plan.source.c_str(), "exo_tree_kernel.cu", 6, headers, names);
+    nvrtcResult r = n.CreateProgram(&prog, source.c_str(), "exo_tree_kernel.cu", 6, headers, names);
     if (r != 0)
     {
         err = std::string("nvrtcCreateProgram: ") + n.GetErrorString(r);
@@ -180,7 +182,7 @@ bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::st
         const std::string base = dump;
         if (FILE* f = fopen((base + ".cu").c_str(), "w"))
         {
-            fwrite(plan.source.data(), 1, plan.source.size(), f);
+            fwrite(source.data(), 1, source.size(), f);
             fclose(f);
         }
         if (FILE* f = fopen((base + ".cubin").c_str(), "wb"))
@@ -192,7 +194,8 @@ bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::st
     return true;
 }
 
-void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
+// module cache: compiled kernels by (device, source text)
+Compiled* get_kernel(const std::string& source, const char* entry, std::string& err)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess)
@@ -208,7 +211,7 @@ void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
         return nullptr;
     }
     std::lock_guard<std::mutex> lock(g_mu);
-    const auto key = std::make_pair(dev, plan.source);
+    const auto key = std::make_pair(dev, source);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return it->second;
     Driver& d = driver();
@@ -218,7 +221,7 @@ void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
         return nullptr;
     }
     std::vector<char> cubin;
-    if (!tree_jit_compile(plan, cubin, err)) return nullptr;
+    if (!compile_source(source, cubin, err)) return nullptr;
     CUmodule mod = nullptr;
     CUresult cr = d.ModuleLoadData(&mod, cubin.data());
     if (cr != CUDA_SUCCESS)
@@ -227,7 +230,7 @@ void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
         return nullptr;
     }
     Compiled* c = new Compiled();
-    cr = d.ModuleGetFunction(&c->fn, mod, "exo_tree_kernel");
+    cr = d.ModuleGetFunction(&c->fn, mod, entry);
     if (cr != CUDA_SUCCESS)
     {
         err = "cuModuleGetFunction failed (" + std::to_string((int)cr) + ")";
@@ -236,6 +239,49 @@ void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
     }
     g_cache[key] = c;
     return c;
+}
+
+cudaError_t launch_kernel(Compiled* c, size_t smem_bytes, int threads, int64_t n_evals, void* params, cudaStream_t stream)
+{
+    Driver& d = driver();
+    if (!c || !d.ok) return cudaErrorInvalidDeviceFunction;
+    if (smem_bytes > c->smem_set)
+    {
+        if (d.FuncSetAttribute(c->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_bytes) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+        c->smem_set = smem_bytes;
+    }
+    const int64_t blocks = (n_evals + threads - 1) / threads;
+    if (blocks > 0x7fffffff) return cudaErrorInvalidConfiguration;
+    void* args[] = {params};
+    const CUresult r = d.LaunchKernel(c->fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem_bytes, (CUstream)stream, args, nullptr);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
+}
+}  // namespace
+
+bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::string& err)
+{
+    return compile_source(plan.source, cubin, err);
+}
+
+void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
+{
+    return get_kernel(plan.source, "exo_tree_kernel", err);
+}
+
+bool tree_costgrad_jit_compile(const TreeCostPlan& plan, std::vector<char>& cubin, std::string& err)
+{
+    return compile_source(plan.source, cubin, err);
+}
+
+void* tree_costgrad_jit_get(const TreeCostPlan& plan, std::string& err)
+{
+    return get_kernel(plan.source, "exo_tree_costgrad_kernel", err);
+}
+
+cudaError_t tree_costgrad_jit_launch(void* kernel, const TreeCostPlan& plan, const TreeCostParams& P, cudaStream_t stream)
+{
+    TreeCostParams params = P;
+    return launch_kernel(static_cast<Compiled*>(kernel), plan.smem_bytes, plan.warps_per_cta * 32, P.n_evals, &params, stream);
 }
 
 bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, double* phi, double* jac, int64_t n_evals, int64_t x_se, int64_t x_sk,
@@ -273,22 +319,8 @@ bool tree_jit_bind(const TreeGenPlan& plan, TreeGenParams& P, const double* x, d
 
 cudaError_t tree_jit_launch(void* kernel, const TreeGenPlan& plan, const TreeGenParams& P, cudaStream_t stream)
 {
-    Compiled* c = static_cast<Compiled*>(kernel);
-    Driver& d = driver();
-    if (!c || !d.ok) return cudaErrorInvalidDeviceFunction;
-    if (plan.smem_bytes > c->smem_set)
-    {
-        if (d.FuncSetAttribute(c->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)plan.smem_bytes) != CUDA_SUCCESS) return cudaErrorInvalidValue;
-        c->smem_set = plan.smem_bytes;
-    }
-    const int threads = plan.warps_per_cta * 32;
-    const int64_t blocks = (P.n_evals + threads - 1) / threads;
-    if (blocks > 0x7fffffff) return cudaErrorInvalidConfiguration;
     TreeGenParams params = P;
-    void* args[] = {&params};
-    const CUresult r = d.LaunchKernel(c->fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, (unsigned)plan.smem_bytes, (CUstream)stream, args, nullptr);
-    if (r != CUDA_SUCCESS) return cudaErrorLaunchFailure;
-    return cudaSuccess;
+    return launch_kernel(static_cast<Compiled*>(kernel), plan.smem_bytes, plan.warps_per_cta * 32, P.n_evals, &params, stream);
 }
 
 }  // namespace exo

@@ -715,8 +715,9 @@ def test_aico_task_messages(oracle_lib, layout):
 
 
 def test_cost_gradient_and_aico_messages_on_a_tree_robot(oracle_lib):
-    # 38 controlled joints: the general (any N) instantiations of the cost-gradient and AICO kernels, and the three-kernel path of
-    # exo_problem_cost_gradient_batch (tree programs have no fused kernel)
+    # 38 controlled joints: the general (any N) instantiations of the cost-gradient and AICO kernels; exo_problem_cost_gradient_batch
+    # through the generated fused kernel of tree programs (exo_tree_costgrad_kernel: J never reaches HBM) and through the three-kernel
+    # path (exo_problem_set_kernel(1)), both against the oracle and in both layouts
     orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
     maps = [{"type": "EffFrame", "EndEffector": [{"Link": "leftPalm"}, {"Link": "rightFoot", "LinkOffset": [0.0, 0.0, -0.05]}]},
             {"type": "JointLimit", "SafePercentage": 0.1},
@@ -735,8 +736,24 @@ def test_cost_gradient_and_aico_messages_on_a_tree_robot(oracle_lib):
     ct = 1.0 / 0.1 / T
     prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
     E = B * T
+    prob.set_kernel(1)
     cost, grad = _gpu_cost_gradient_fused(prob, X.reshape(E, N), B, T)
     assert prob.last_kernel() == "exo_cost_gradient_kernel"
+    prob.set_kernel(0)
+    for layout in (_capi.LAYOUT_SOA, _capi.LAYOUT_AOS_ROWMAJOR):
+        cost_f, grad_f = _gpu_cost_gradient_fused(prob, X.reshape(E, N), B, T, layout=layout)
+        assert prob.last_kernel() == "exo_tree_costgrad_kernel"
+        assert record("tree_costgrad_vs_unfused", np.max(np.abs(grad_f - grad)) / max(1.0, np.abs(grad).max())) <= 1e-12
+        assert np.max(np.abs(cost_f - cost)) <= 1e-12 * max(1.0, np.abs(cost).max())
+        for b in range(B):
+            gref = orc.trajectory_cost_jacobian(X[b], rho, goal=goal, ct=ct, W=W)
+            assert np.max(np.abs(grad_f.reshape(B, T, N)[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+    # cost only (NULL gradient) through the same generated kernel
+    dxc, dcc = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(B)
+    dxc.upload(X.reshape(E, N).T)
+    prob.cost_gradient_batch_device(dxc.ptr, B, None, dcc.ptr)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    assert prob.last_kernel() == "exo_tree_costgrad_kernel" and np.max(np.abs(dcc.download((B,)) - cost)) <= 1e-12 * max(1.0, np.abs(cost).max())
     grad = grad.reshape(B, T, N)
     LP, LJ = prob.length_phi, prob.length_jacobian
     dx, dphi, djac, dR, dr, drh, dc = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, E * N * N, E * N, E, E))

@@ -18,6 +18,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import exotica_b200 as exo  # noqa: E402
@@ -148,6 +149,35 @@ def main():
 
     backend.h = None  # borrowed handle: the host problem owns (and destroys) it
     for b in (dx, dphi, djac, dg, dc):
+        b.free()
+
+    # whole-body problem (38-DoF humanoid, four end-effector frames + joint limits): cost and gradient of 2^18 configurations through
+    # the generated fused kernel of tree programs and through the Phi / J round trip (update + cost + cost-gradient kernels)
+    from bench_configs import frame, scene
+    maps = [("exotica/EffFrame", {"Name": "Eff", "EndEffector": [frame("leftFoot"), frame("rightFoot"), frame("leftPalm"), frame("rightPalm")]}),
+            ("exotica/JointLimit", {"Name": "JL"})]
+    init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "wb", "PlanningScene": scene("valkyrie_sim", "whole_body"), "Maps": maps,
+                                                    "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "10"}), ("exotica/Task", {"Task": "JL", "Rho": "100"})]})
+    wb = exo.Setup.create_problem(init)
+    E2, N2 = 1 << 18, wb.N
+    lim = wb.get_scene().get_kinematic_tree().get_joint_limits()
+    lo = np.where(lim[:, 0] < -1e19, -1.0, lim[:, 0])
+    hi = np.where(lim[:, 1] > 1e19, 1.0, lim[:, 1])
+    X2 = np.random.default_rng(9).uniform(lo, hi, size=(E2, N2))
+    wb.cost_batch(X2[:2])
+    b2 = _capi.Problem.__new__(_capi.Problem)
+    b2.h = _host.lib().exo_host_problem_backend(wb._h)
+    dx2, dg2, dc2 = _capi.DeviceBuffer(E2 * N2), _capi.DeviceBuffer(E2 * N2), _capi.DeviceBuffer(E2)
+    dx2.upload(X2.T)
+    ms = timed(lambda: b2.cost_gradient_batch_device(dx2.ptr, E2, dg2.ptr, dc2.ptr), args.reps)
+    g_fused = dg2.download((N2, E2))
+    line("whole-body cost + gradient, %s (J never materialised), device" % b2.last_kernel(), ms, E2, "evals", 8 * (2 * N2 + 1))
+    b2.set_kernel(1)
+    ms = timed(lambda: b2.cost_gradient_batch_device(dx2.ptr, E2, dg2.ptr, dc2.ptr), args.reps)
+    line("whole-body cost + gradient, Phi / J round trip (update + cost + %s), device" % b2.last_kernel(), ms, E2, "evals", None,
+         max_abs_diff_vs_fused=float(np.max(np.abs(dg2.download((N2, E2)) - g_fused))))
+    b2.h = None
+    for b in (dx2, dg2, dc2):
         b.free()
 
     # multi-start IK on example_ik.xml's problem shape
