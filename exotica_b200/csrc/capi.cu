@@ -104,6 +104,11 @@ struct exo_problem
     TreeGenPlan tree_plan;
     TreeGenParams tree_params;
     TmaKey tree_key;
+    // generated front half of split SphereCollision programs (tree_park_codegen)
+    int park_version = -2;
+    bool park_ok = false, park_jit_failed = false;
+    void* park_kernel = nullptr;
+    TreeParkPlan park_plan;
     // generated fused cost + gradient kernel for tree programs (tree_costgrad_codegen)
     int tcg_version = -2;         // tree version the source below was generated for
     int64_t cost_epoch = 0, tcg_cost_epoch = -1;  // exo_problem_set_cost calls / the one the cost structure below was read at
@@ -755,9 +760,9 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
             if (k.T > 1 && max_chunk > k.T) max_chunk = max_chunk / k.T * k.T;  // whole trajectories per chunk where they fit
             if (chunk > max_chunk) chunk = max_chunk;
             k.sph_row = (int32_t)row;
-            k.sph_block = chunk * row;
+            k.sph_block = (chunk + 31) / 32 * 32 * row;  // whole tiles of 32 evaluations (the generated park kernel writes tiled rows)
             k.sph_n_ops = n_sph_ops;
-            const int64_t need = per_eval * chunk;
+            const int64_t need = (int64_t)n_sph_ops * k.sph_block * (int64_t)sizeof(double);
             exo_problem::SphDump* slot = nullptr;
             for (auto& sd : p->sph_dumps)
                 if (sd.stream == stream) slot = &sd;
@@ -787,6 +792,25 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
             CUDA_TRY(cudaEventCreate(&p->ev1));
         }
         CUDA_TRY(cudaEventRecord(p->ev0, stream));
+    }
+    // front half of split SphereCollision programs: generated when the program holds nothing else (run-time compiled on first use)
+    bool park = false;
+    if (split && p->kernel_choice == 0 && E >= tree_min_evals() && !p->park_jit_failed)
+    {
+        if (p->park_version != p->compiled_version)
+        {
+            std::string why;
+            p->park_version = p->compiled_version;
+            p->park_kernel = nullptr;
+            p->park_ok = tree_park_codegen(p->prog, p->park_plan, why);
+        }
+        if (p->park_ok && !p->park_kernel)
+        {
+            std::string jerr;
+            p->park_kernel = tree_park_jit_get(p->park_plan, jerr);
+            if (!p->park_kernel) p->park_jit_failed = true;
+        }
+        park = p->park_ok && p->park_kernel;
     }
     cudaError_t e;
     bool tma = false;
@@ -835,11 +859,23 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
             k.jac = k0.jac ? k0.jac + c0 * k0.j_se : nullptr;
             k.min_dist = k0.min_dist ? k0.min_dist + c0 : nullptr;
             k.sph_dump = dump;
+            k.sph_tiled = park ? 1 : 0;
             LaunchConfig c = cfg;
             const int64_t per_cta = (int64_t)(c.threads / 32) * c.tile;
             const int64_t want = (n + per_cta - 1) / per_cta;
             if (want < c.blocks) c.blocks = (int)want;
-            e = launch_eval(c, k, stream);
+            if (park)
+            {
+                // split SphereCollision programs: the generated straight-line kernel parks the rows instead of the interpreter
+                TreeParkParams pk;
+                memset(&pk, 0, sizeof(pk));
+                pk.x = k.x; pk.generated = k.generated; pk.dump = k.sph_dump;
+                pk.n_evals = n; pk.x_se = k.x_se; pk.x_sk = k.x_sk; pk.e_base = k.e_base; pk.sph_block = k.sph_block;
+                pk.T = k.T; pk.n_generated = p->prog.hdr.n_generated; pk.sph_row = k.sph_row;
+                e = tree_park_jit_launch(p->park_kernel, p->park_plan, pk, stream);
+            }
+            else
+                e = launch_eval(c, k, stream);
             if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
             p->launches++;
             if (split)

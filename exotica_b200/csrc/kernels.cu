@@ -675,10 +675,20 @@ __global__ void __maxnreg__(EXO_SPHERES_MAXNREG) exo_spheres_kernel(const Kernel
     const int64_t stride = (int64_t)gridDim.x * WPC;
 
     auto fetch = [&](int64_t e, int ord, int buf) {
-        const char* src = reinterpret_cast<const char*>(P.sph_dump + (int64_t)ord * P.sph_block + e * row);
         const uint32_t dst = stage_s + (uint32_t)(buf * row) * 8u;
-        for (int i = lane; i < (row >> 1); i += 32)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i) : "memory");
+        if (P.sph_tiled)
+        {
+            // rows written by the generated park kernel: word k of evaluation e at [e / 32][k][e % 32]
+            const char* src = reinterpret_cast<const char*>(P.sph_dump + (int64_t)ord * P.sph_block + (e & ~(int64_t)31) * row + (e & 31));
+            for (int i = lane; i < row; i += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(src + 256 * i) : "memory");
+        }
+        else
+        {
+            const char* src = reinterpret_cast<const char*>(P.sph_dump + (int64_t)ord * P.sph_block + e * row);
+            for (int i = lane; i < (row >> 1); i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i) : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 

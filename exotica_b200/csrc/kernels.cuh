@@ -34,6 +34,8 @@ struct KernelParams
     int32_t sph_row;               // doubles per row: the program's scratch words rounded up to an even count (16-byte rows)
     int32_t sph_n_ops;             // SphereCollision ops in the program (<= SPH_SPLIT_MAX_OPS)
     int64_t e_base;                // index of evaluation 0 of this launch in the caller's batch (timestep = (e_base + e) % T)
+    int32_t sph_tiled;             // 1: the parked rows are tiled [e / 32][word][e % 32] (written by the generated park kernel)
+    int32_t pad_tiled;
 };
 
 constexpr int SPH_SPLIT_MAX_OPS = 16;  // programs with more SphereCollision maps evaluate them inside the interpreter
@@ -221,6 +223,25 @@ struct TreeCostParams  // mirrored by the generated source
     int T, t_first, T_goal, n_maps, length_phi, n_rot;
 };
 bool tree_costgrad_codegen(const Program& prog, const TreeCostSpec& cs, TreeCostPlan& plan, std::string& why);
+
+// Generated front half of split SphereCollision programs (exo_tree_park_kernel): composes the tree and parks every evaluation's
+// frame / joint slots as the row exo_spheres_kernel reads, in place of the interpreter.
+struct TreeParkPlan
+{
+    std::string source;
+    int threads = 128;
+};
+struct TreeParkParams  // mirrored by the generated source
+{
+    const double* x;
+    const double* generated;
+    double* dump;
+    long long n_evals, x_se, x_sk, e_base, sph_block;
+    int T, n_generated, sph_row;
+};
+bool tree_park_codegen(const Program& prog, TreeParkPlan& plan, std::string& why);
+void* tree_park_jit_get(const TreeParkPlan& plan, std::string& err);
+cudaError_t tree_park_jit_launch(void* kernel, const TreeParkPlan& plan, const TreeParkParams& P, cudaStream_t stream);
 void* tree_costgrad_jit_get(const TreeCostPlan& plan, std::string& err);
 bool tree_costgrad_jit_compile(const TreeCostPlan& plan, std::vector<char>& cubin, std::string& err);
 cudaError_t tree_costgrad_jit_launch(void* kernel, const TreeCostPlan& plan, const TreeCostParams& P, cudaStream_t stream);

@@ -1047,4 +1047,148 @@ bool tree_costgrad_codegen(const Program& prog, const TreeCostSpec& cs, TreeCost
     return true;
 }
 
+// ---- front half of split SphereCollision programs ----------------------------------------------------------------------------------
+// exo_spheres_kernel (kernels.cu) runs the sphere-pair loops one warp per evaluation from a row of parked frame / joint slots.  The
+// interpreter used to produce those rows (0.20 ms of cfg5's 2.07 ms at 6 warps per SM: its 1 KB of per-lane scratch limits
+// residency).  For programs made of joints, trajectory-driven links and SphereCollision maps only, this generator unrolls the same
+// one-pass program into straight-line code that keeps nothing but the running frame in registers and writes every slot the moment
+// it exists, into TILED rows ([sphere op][e / 32][word][e % 32]: every store of a warp is one full 256-byte segment;
+// exo_spheres_kernel gathers its evaluation's words 8 bytes at a time, KernelParams::sph_tiled).  Evaluation-major rows written in
+// pieces were measured no faster than the interpreter's transposed dump (180 vs 203 us of cfg5's 2.07 ms): partial lines.
+bool tree_park_codegen(const Program& prog, TreeParkPlan& plan, std::string& why)
+{
+    const ProgramHeader& H = prog.hdr;
+    if (H.two_pass)
+    {
+        why = "two-pass program";
+        return false;
+    }
+    const int n_ops = (int)prog.ops.size();
+    const int joint_base = 12 * H.n_frame_slots;
+    // which producer is live in each slot at every SphereCollision op, and which slots later producers read back
+    std::vector<int> owner_f(H.n_frame_slots, -1), owner_j(H.n_joint_slots, -1);
+    std::vector<std::vector<int>> rows_f(n_ops), rows_j(n_ops);  // per producer op: the sphere-op ordinals whose row takes its frame / joint slot
+    std::vector<char> read_back(H.n_frame_slots, 0);
+    int n_sph = 0;
+    for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_JOINT || op.kind == OP_TABLE)
+        {
+            if (op.src >= 0) read_back[op.src] = 1;
+            if (op.dst >= 0) owner_f[op.dst] = i;
+            if (op.kind == OP_JOINT && op.jslot >= 0) owner_j[op.jslot] = i;
+        }
+        else if (op.kind == OP_EMIT_SPHERES)
+        {
+            for (int s = 0; s < H.n_frame_slots; ++s)
+                if (owner_f[s] >= 0) rows_f[owner_f[s]].push_back(n_sph);
+            for (int s = 0; s < H.n_joint_slots; ++s)
+                if (owner_j[s] >= 0) rows_j[owner_j[s]].push_back(n_sph);
+            ++n_sph;
+        }
+        else
+        {
+            why = "maps other than SphereCollision share the program";
+            return false;
+        }
+    }
+    if (n_sph == 0)
+    {
+        why = "no SphereCollision map";
+        return false;
+    }
+    const int AHEAD = env_int("EXO_TREE_AHEAD", 8, 0, 16);
+    plan.threads = 128;
+    Emitter o;
+    o.line("// generated by exotica_b200 tree_park_codegen: %d ops, %d frame slots, %d joint slots, %d SphereCollision maps", n_ops, H.n_frame_slots, H.n_joint_slots, n_sph);
+    emit_prelude(o);
+    o.line("struct TreeParkParams { const double* x; const double* generated; double* dump; long long n_evals, x_se, x_sk, e_base, sph_block; int T, n_generated, sph_row; };");
+    o.line("extern \"C\" __global__ void __launch_bounds__(%d) exo_tree_park_kernel(const __grid_constant__ TreeParkParams P)", plan.threads);
+    o.line("{");
+    o.line("    const long long e = (long long)blockIdx.x * %d + threadIdx.x;", plan.threads);
+    o.line("    if (e >= P.n_evals) return;");
+    o.line("    const double* const xq = P.x + e * P.x_se;");
+    o.line("    // tiled rows: word k of evaluation e at [e / 32][k][e %% 32] -- every store of a warp is one full 256-byte segment");
+    o.line("    double* const row = P.dump + (e & ~31ll) * P.sph_row + (e & 31);  // sphere op k: + k * P.sph_block; word w: + 32 * w");
+    o.line("    Fr cur;");
+    for (int s = 0; s < H.n_frame_slots; ++s)
+        if (read_back[s]) o.line("    Fr fs%d;  // frame slot %d: a later joint starts from it", s, s);
+    std::vector<int> qseq;
+    for (int i = 0; i < n_ops && prog.ops[i].kind != OP_END; ++i)
+        if (prog.ops[i].kind == OP_JOINT && prog.ops[i].qidx >= 0) qseq.push_back(i);
+    size_t q_issued = 0, q_used = 0;
+    auto issue_loads = [&](size_t upto) {
+        for (; q_issued < upto && q_issued < qseq.size(); ++q_issued) o.line("    const double q_%d = xq[%d * P.x_sk];", (int)q_issued, prog.ops[qseq[q_issued]].qidx);
+    };
+    issue_loads(AHEAD + 1);
+    for (int i = 0; i < n_ops; ++i)
+    {
+        const Op& op = prog.ops[i];
+        if (op.kind == OP_END) break;
+        if (op.kind != OP_JOINT && op.kind != OP_TABLE) continue;
+        const double* c = prog.dbls.data() + op.cst;
+        o.line("    // op %d: %s", i, op.kind == OP_JOINT ? "joint" : "trajectory-driven link");
+        // cur = parent * pre  (the parent is the running frame, the root, or a slot kept in registers)
+        {
+            double prec[12];
+            const_frame(c, op.flags & F_PRE_MASK, F_PRE_NONE, F_PRE_TRANS, prec);
+            if (op.src == SRC_ROOT)
+                emit_set_const(o, "cur", prec);
+            else
+            {
+                if (op.src >= 0) o.line("    cur = fs%d;", op.src);
+                if (!is_identity12(prec)) emit_mul_const(o, "cur", "cur", prec);
+            }
+        }
+        o.line("    {");
+        if (op.kind == OP_TABLE)
+        {
+            o.line("        const double* g = P.generated + ((long long)((P.e_base + e) %% P.T) * P.n_generated + %d) * 12;", op.qidx);
+            o.line("        Fr gf;");
+            for (int k = 0; k < 9; ++k) o.line("        gf.%s = g[%d];", kM[k], k);
+            for (int k = 0; k < 3; ++k) o.line("        gf.%s = g[%d];", kP[k], 9 + k);
+            o.line("        cur = fr_mul(cur, gf);");
+        }
+        else
+        {
+            if (op.qidx >= 0)
+            {
+                issue_loads(q_used + 1);
+                if (c[CJ_QMULT] == 1.0 && c[CJ_QOFF] == 0.0)
+                    o.line("        const double q = q_%d;", (int)q_used);
+                else
+                    o.line("        const double q = fma(%s, q_%d, %s);", lit(c[CJ_QMULT]).c_str(), (int)q_used, lit(c[CJ_QOFF]).c_str());
+                ++q_used;
+            }
+            else
+                o.line("        const double q = %s;", lit(c[CJ_QOFF]).c_str());
+            const bool park_joint = !rows_j[i].empty();
+            emit_joint_motion(o, op, park_joint, -1);
+            // joint slot: world axis (the z column in front of the motion) and origin (after a sliding joint's translation)
+            for (int k : rows_j[i])
+            {
+                o.line("        {");
+                o.line("            double* js = row + %d * P.sph_block + %d;", k, 32 * (joint_base + 6 * op.jslot));
+                o.line("            js[0] = wx; js[32] = wy; js[64] = wz; js[96] = cur.x; js[128] = cur.y; js[160] = cur.z;");
+                o.line("        }");
+            }
+        }
+        o.line("    }");
+        for (int k : rows_f[i])
+        {
+            o.line("    {");
+            o.line("        double* fsl = row + %d * P.sph_block + %d;", k, 32 * 12 * op.dst);
+            for (int w = 0; w < 9; ++w) o.line("        fsl[%d] = cur.%s;", 32 * w, kM[w]);
+            for (int w = 0; w < 3; ++w) o.line("        fsl[%d] = cur.%s;", 32 * (9 + w), kP[w]);
+            o.line("    }");
+        }
+        if (op.dst >= 0 && read_back[op.dst]) o.line("    fs%d = cur;", op.dst);
+        issue_loads(q_used + AHEAD + 1);
+    }
+    o.line("}");
+    plan.source.swap(o.s);
+    return true;
+}
+
 }  // namespace exo

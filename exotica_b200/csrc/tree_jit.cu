@@ -278,6 +278,17 @@ void* tree_costgrad_jit_get(const TreeCostPlan& plan, std::string& err)
     return get_kernel(plan.source, "exo_tree_costgrad_kernel", err);
 }
 
+void* tree_park_jit_get(const TreeParkPlan& plan, std::string& err)
+{
+    return get_kernel(plan.source, "exo_tree_park_kernel", err);
+}
+
+cudaError_t tree_park_jit_launch(void* kernel, const TreeParkPlan& plan, const TreeParkParams& P, cudaStream_t stream)
+{
+    TreeParkParams params = P;
+    return launch_kernel(static_cast<Compiled*>(kernel), 0, plan.threads, P.n_evals, &params, stream);
+}
+
 cudaError_t tree_costgrad_jit_launch(void* kernel, const TreeCostPlan& plan, const TreeCostParams& P, cudaStream_t stream)
 {
     TreeCostParams params = P;

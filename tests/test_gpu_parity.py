@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): |Phi_gpu - Phi_oracle| and |J_gpu - J_oracle| <=
 Euler-angle encodings are compared modulo 2 pi (the LWR base yaw sits on the atan2
 cut); the rotation-matrix encoding, which has no cuts, is checked without wrapping.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -295,6 +297,53 @@ def test_sphere_collision_split_launch_in_chunks(oracle_lib, monkeypatch):
     run_gpu(prob, X, T=T)
     assert np.array_equal(d_split, dmin.download((E,)))
     prob.set_min_distance_output(0)
+
+
+@pytest.mark.parametrize("robot", ["lwr", "valkyrie"])
+def test_sphere_collision_generated_front_half(oracle_lib, robot, monkeypatch):
+    """Batches of >= EXO_TREE_MIN_EVALS evaluations of a SphereCollision-only problem: the rows exo_spheres_kernel reads are parked by
+    the generated straight-line kernel (tree_park_codegen) instead of the interpreter -- a serial arm with a trajectory-driven
+    obstacle, and a branched robot whose limbs collide with each other (frame slots read back by later joints).  The same
+    Phi / J as with the interpreter's front half to 1e-12, and the oracle's to 1e-10."""
+    if robot == "lwr":
+        tree = oracle_lib.load_robot(*robot_paths("lwr_simplified"), joint_group="arm")
+        tree.add_environment_element("Obstacle", generated_slot=0)
+        orc = oracle_lib.Oracle(tree)
+        B, T = 200, 25
+        gen = np.zeros((T, 1, 12))
+        for t in range(T):
+            gen[t, 0] = oracle_lib.get_frame([0.5 - 0.02 * t, 0.1, 0.6 + 0.01 * t, 0, 0, 0.1 * t])
+        maps = _lwr_sphere_maps()
+        X = random_states(orc, B * T - 3, seed=179)
+    else:
+        orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+        frames = [{"Link": link, "Radius": 0.08, "Group": grp, "LinkOffset": [0.01, 0.02, 0.03]}
+                  for link, grp in (("leftPalm", "a"), ("leftForearmLink", "a"), ("rightPalm", "b"), ("rightForearmLink", "b"), ("torso", "c"), ("pelvis", "c"),
+                                    ("leftFoot", "b"))]
+        maps = [{"type": "SphereCollision", "Precision": 0.05, "EndEffector": frames}]
+        T, gen = 1, None
+        X = random_states(orc, 4200, seed=180)
+    orc.set_problem(maps)
+    tree_gpu, prob = gpu_problem_from_maps(orc, maps)
+    if gen is not None:
+        prob.set_generated(gen)
+    if os.path.exists("/tmp/exo_park_test.cu"):
+        os.remove("/tmp/exo_park_test.cu")
+    monkeypatch.setenv("EXO_TREE_DUMP", "/tmp/exo_park_test")  # the park kernel really was compiled for this problem
+    phi, jac = run_gpu(prob, X, T=T)
+    assert prob.last_kernel() == "exo_spheres_kernel" and prob.launch_count() == 2
+    assert "exo_tree_park_kernel" in open("/tmp/exo_park_test.cu").read()
+    monkeypatch.delenv("EXO_TREE_DUMP")
+    sel = np.random.default_rng(3).choice(X.shape[0], 600, replace=False)
+    sel -= sel % T  # whole timesteps of the generated table: evaluation e is timestep e % T
+    sel = np.unique(np.concatenate([sel + t for t in range(T)]))[:1500]
+    phi_ref, jac_ref = zip(*[orc.problem_update_batch(X[e:e + 1], T=1, generated=None if gen is None else gen[e % T:e % T + 1]) for e in sel[:300]])
+    assert record("park_phi", max_abs_err(phi[sel[:300]], np.concatenate(phi_ref))) <= TOL
+    assert record("park_jac", max_abs_err(jac[sel[:300]], np.concatenate(jac_ref))) <= TOL
+    # the interpreter's front half (small batches take it): the same numbers up to the rounding of the folded constant products
+    n = 1024 - (1024 % T)
+    phi_i, jac_i = run_gpu(prob, X[:n], T=T)
+    assert max_abs_err(phi_i, phi[:n]) <= 1e-12 and max_abs_err(jac_i, jac[:n]) <= 1e-12
 
 
 def test_sphere_collision_three_groups_robot_vs_robot(oracle_lib):
