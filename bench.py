@@ -238,8 +238,11 @@ class DeviceScalar(object):
 
     def reduce(self, comm, value, op):
         import numpy as np
+        # collectives of one communicator are issued in one order on every rank: drain the streams around this one
+        self.capi.check(self.capi.lib().exo_device_synchronize())
         self.buf.upload(np.array([value], dtype=np.float64))
         comm.allreduce(self.buf.ptr, self.buf.ptr, 1, op, None)
+        self.capi.check(self.capi.lib().exo_device_synchronize())
         return float(self.buf.download((1,))[0])
 
 
@@ -406,8 +409,9 @@ def measure_multi_gpu(exo, capi, exd, comm, rank, world, reps=50, B=4096):
         gmin = float(keep[5].download((1,))[0])
         res = {"trajectories": B, "T": T, "evals": B * T, "scaling": "strong", "ms_per_step": ms_full, "evals_per_s": B * T / (ms_full * 1e-3),
                "ms_without_collective": ms_nocoll, "collective_us": 1e3 * (ms_full - ms_nocoll),
-               "step": ("update (Phi, J) + cost kernel + ncclAllGather(%d costs), one CUDA graph" % B) if name == "cfg3" else
-                       ("update (interpreter + pair kernel) + per-trajectory min + ncclAllGather(%d distances) + global min, one CUDA graph" % B)}
+               "step": ("update (Phi, J) + cost kernel + all-gather(%d costs), one CUDA graph" % B) if name == "cfg3" else
+                       ("update (park + pair kernel) + per-trajectory min + all-gather(%d distances) + global min, one CUDA graph" % B),
+               "collective_path": "peer windows (one kernel over NVLink peer memory)" if comm.peer_collective_count() >= 0 and world > 1 else "NCCL"}
         comm.barrier(stream)
         if rank == 0:
             # the same step on ONE GPU (this one) for all B trajectories: the strong-scaling reference, measured in the same process
@@ -456,6 +460,8 @@ def run_ours(args):
     if capi.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
     comm, rank, world, local_rank = exd.init_from_env()
+    # several ranks on one node: keep every rank's pinned pools and copy-issuing threads on its GPU's NUMA node (EXO_BENCH_NUMA=0: off)
+    numa = exd.bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("EXO_BENCH_NUMA", "1") != "0" else None
     if rank == 0:
         from oracle import oracle
         oracle.use_native_build()  # CPU-baseline build flags; bit-identical results to the generic build
@@ -578,7 +584,7 @@ def run_ours(args):
                        "parallelism": "configurations sharded across %d GPU(s), no collective in the timed region" % world},
             "clocks": sampler.summary(clock_note), "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N * 8, "d2h_bytes_per_step": E * (LP + LJ * N) * 8,
-                    "steps": e2e_steps, "api": "exotica_b200.PlanningProblem.update_batch (pinned host X[E][N] -> Phi[E][6], J[E][6][7])",
+                    "steps": e2e_steps, "api": "exotica_b200.PlanningProblem.update_batch (pinned host X[E][N] -> Phi[E][6], J[E][6][7])", "numa_binding": numa,
                     "max_abs_err_vs_oracle": e2e_err},
             "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample,

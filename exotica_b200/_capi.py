@@ -120,6 +120,8 @@ SYMBOLS = [
     ("exo_comm_rank", ctypes.c_int, [_vp]),
     ("exo_comm_world_size", ctypes.c_int, [_vp]),
     ("exo_comm_collective_count", ctypes.c_int64, [_vp]),
+
+    ("exo_comm_peer_collective_count", ctypes.c_int64, [_vp]),
     ("exo_comm_allgather", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp]),
     ("exo_comm_allreduce", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp]),
     ("exo_comm_barrier", ctypes.c_int, [_vp, _vp]),
@@ -338,6 +340,10 @@ class Comm(object):
 
     def collective_count(self):
         return int(lib().exo_comm_collective_count(self.h))
+
+    def peer_collective_count(self):
+        """Collectives that went through the peer-memory windows instead of NCCL; -1: the windows are not available."""
+        return int(lib().exo_comm_peer_collective_count(self.h))
 
     def cost_allgather(self, problem, d_x, n_traj_local, n_traj_per_rank, d_cost_all, layout=LAYOUT_SOA, stream=None):
         """problem: a _capi.Problem or raw exo_problem handle."""

@@ -97,6 +97,38 @@ def release_unique_id(rank, token=None, directory=None):
         pass
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs, through the GPU's PCI bus id from NVML), so that
+    the pinned host pools allocated afterwards -- and the threads that fill them -- sit on the memory controller next to that GPU's
+    PCIe root port.  With eight ranks on one node every host<->device copy otherwise crosses the socket interconnect for half of the
+    GPUs.  Returns {"numa_node", "cpus"} or None when the topology cannot be read (single-node hosts, containers without sysfs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def init_from_env():
     """One process per GPU, launched torchrun-style (RANK, WORLD_SIZE, LOCAL_RANK in the environment; a plain `python` run is
     rank 0 of 1): selects the rank's device, builds the communicator, returns (comm, rank, world, local_rank)."""
