@@ -251,8 +251,30 @@ __device__ __forceinline__ double norm3_scaled(double a, double b, double c)
     return t1 * sqrt(1 + (a / c) * (a / c) + (b / c) * (b / c));
 }
 
-static __device__ __noinline__ void get_angle_axis(const Fr& f, double& ox, double& oy, double& oz)
+// The two encoders below are cold (one of six rotation types each) and stay out of line; their arguments and results travel in
+// registers (nine doubles by value in, a small struct by value out) -- a `const Fr&` / pointer interface made every caller spill a
+// 96-byte argument block to local memory in front of the rotation-type switch, whatever type it then took.
+#ifdef EXO_INLINE_ENCODERS  // the run-time generated kernels call them from straight-line code with many live registers: a call
+#define EXO_ENCODER_LINKAGE __forceinline__  // would save and restore most of them, so there they are expanded in place
+#else
+#define EXO_ENCODER_LINKAGE __noinline__
+#endif
+struct Rot3
 {
+    double x, y, z;
+};
+struct Rot4
+{
+    double x, y, z, w;
+};
+struct Mat9
+{
+    double m0, m1, m2, m3, m4, m5, m6, m7, m8;
+};
+static __device__ EXO_ENCODER_LINKAGE Rot3 angle_axis_of(double m0, double m1, double m2, double m3, double m4, double m5, double m6, double m7, double m8)
+{
+    const Mat9 f = {m0, m1, m2, m3, m4, m5, m6, m7, m8};
+    double ox, oy, oz;
     // KDL::Rotation::GetRot = axis * angle with GetRotAngle's symmetric-matrix handling
     const double eps = 1e-6, eps2 = 1e-5;
     double x, y, z, angle;
@@ -260,8 +282,8 @@ static __device__ __noinline__ void get_angle_axis(const Fr& f, double& ox, doub
     {
         if ((fabs(f.m1 + f.m3) < eps2) && (fabs(f.m2 + f.m6) < eps2) && (fabs(f.m5 + f.m7) < eps2) && (fabs(f.m0 + f.m4 + f.m8 - 3) < eps2))
         {
-            ox = oy = oz = 0.0;
-            return;
+            const Rot3 zero = {0.0, 0.0, 0.0};
+            return zero;
         }
         angle = CUDART_PI;
         const double xx = (f.m0 + 1) / 2, yy = (f.m4 + 1) / 2, zz = (f.m8 + 1) / 2;
@@ -301,12 +323,20 @@ static __device__ __noinline__ void get_angle_axis(const Fr& f, double& ox, doub
     ox = x * angle;
     oy = y * angle;
     oz = z * angle;
+    const Rot3 out = {ox, oy, oz};
+    return out;
+}
+__device__ __forceinline__ void get_angle_axis(const Fr& f, double& ox, double& oy, double& oz)
+{
+    const Rot3 r = angle_axis_of(f.m0, f.m1, f.m2, f.m3, f.m4, f.m5, f.m6, f.m7, f.m8);
+    ox = r.x; oy = r.y; oz = r.z;
 }
 
-static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y z w */)
+static __device__ EXO_ENCODER_LINKAGE Rot4 quaternion_of(double m0, double m1, double m2, double m3, double m4, double m5, double m6, double m7, double m8)
 {
     // Eigen::Quaterniond(Matrix3d).coeffs()
-    const double m[9] = {f.m0, f.m1, f.m2, f.m3, f.m4, f.m5, f.m6, f.m7, f.m8};
+    const double m[9] = {m0, m1, m2, m3, m4, m5, m6, m7, m8};
+    double q[4];
     double t = m[0] + m[4] + m[8];
     if (t > 0.0)
     {
@@ -335,6 +365,13 @@ static __device__ __noinline__ void get_quaternion(const Fr& f, double* q /* x y
         q[2] = (i == 2) ? qi : ((j == 2) ? qj : qk);
         q[3] = qw;
     }
+    const Rot4 out = {q[0], q[1], q[2], q[3]};
+    return out;
+}
+__device__ __forceinline__ void get_quaternion(const Fr& f, double* q /* x y z w */)
+{
+    const Rot4 r = quaternion_of(f.m0, f.m1, f.m2, f.m3, f.m4, f.m5, f.m6, f.m7, f.m8);
+    q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
 }
 
 

@@ -219,6 +219,7 @@ void emit_requested_frame(Emitter& o, const Op& op, const double* c, int TILE)
 void emit_prelude(Emitter& o)
 {
     o.line("#define EXO_STORE_CS 1");
+    o.line("#define EXO_INLINE_ENCODERS 1");
     o.line("#include \"device_math.cuh\"");
     o.line("using namespace exo;");
     o.line("using namespace exo::dev;");

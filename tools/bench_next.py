@@ -160,9 +160,9 @@ def main():
                                                     "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "10"}), ("exotica/Task", {"Task": "JL", "Rho": "100"})]})
     wb = exo.Setup.create_problem(init)
     E2, N2 = 1 << 18, wb.N
-    lim = wb.get_scene().get_kinematic_tree().get_joint_limits()
-    lo = np.where(lim[:, 0] < -1e19, -1.0, lim[:, 0])
-    hi = np.where(lim[:, 1] > 1e19, 1.0, lim[:, 1])
+    lim2 = wb.get_scene().get_kinematic_tree().get_joint_limits()
+    lo = np.where(lim2[:, 0] < -1e19, -1.0, lim2[:, 0])
+    hi = np.where(lim2[:, 1] > 1e19, 1.0, lim2[:, 1])
     X2 = np.random.default_rng(9).uniform(lo, hi, size=(E2, N2))
     wb.cost_batch(X2[:2])
     b2 = _capi.Problem.__new__(_capi.Problem)
