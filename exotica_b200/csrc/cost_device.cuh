@@ -22,6 +22,16 @@ __device__ __forceinline__ double warp_min_d(double v)
     return v;
 }
 
+// sin / cos of an Euler angle read back from Phi: the kernels' own reduction (device_math.cuh) inside its range -- Phi holds atan2
+// results, so always --, CUDA's beyond it
+__device__ __forceinline__ void euler_sincos(double a, double& s, double& c)
+{
+    if (fabs(a) <= 1.0e5)
+        fast_sincos(a, s, c);
+    else
+        sincos(a, &s, &c);
+}
+
 // exotica::GetRotation (tools/conversions.cpp:114-148) over KDL::Rotation::{Quaternion, RPY, EulerZYX, EulerZYZ, Rot}
 static __device__ Fr dev_get_rotation(const double* d, int64_t sk, int type)
 {
@@ -43,9 +53,9 @@ static __device__ Fr dev_get_rotation(const double* d, int64_t sk, int type)
             const bool zyx = type == EXO_ROT_ZYX;  // EulerZYX(a, b, c) = RPY(c, b, a)
             const double roll = zyx ? d[2 * sk] : d[0], pitch = d[sk], yaw = zyx ? d[0] : d[2 * sk];
             double sa, ca, sb, cb, sc, cc;
-            sincos(yaw, &sa, &ca);
-            sincos(pitch, &sb, &cb);
-            sincos(roll, &sc, &cc);
+            euler_sincos(yaw, sa, ca);
+            euler_sincos(pitch, sb, cb);
+            euler_sincos(roll, sc, cc);
             r.m0 = ca * cb; r.m1 = ca * sb * sc - sa * cc; r.m2 = ca * sb * cc + sa * sc;
             r.m3 = sa * cb; r.m4 = sa * sb * sc + ca * cc; r.m5 = sa * sb * cc - ca * sc;
             r.m6 = -sb; r.m7 = cb * sc; r.m8 = cb * cc;
@@ -54,9 +64,9 @@ static __device__ Fr dev_get_rotation(const double* d, int64_t sk, int type)
         case EXO_ROT_ZYZ:
         {
             double sa, ca, sb, cb, sg, cg;
-            sincos(d[0], &sa, &ca);
-            sincos(d[sk], &sb, &cb);
-            sincos(d[2 * sk], &sg, &cg);
+            euler_sincos(d[0], sa, ca);
+            euler_sincos(d[sk], sb, cb);
+            euler_sincos(d[2 * sk], sg, cg);
             r.m0 = ca * cb * cg - sa * sg; r.m1 = -ca * cb * sg - sa * cg; r.m2 = ca * sb;
             r.m3 = sa * cb * cg + ca * sg; r.m4 = -sa * cb * sg + ca * cg; r.m5 = sa * sb;
             r.m6 = -sb * cg; r.m7 = sb * sg; r.m8 = cb;

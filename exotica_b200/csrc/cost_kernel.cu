@@ -40,6 +40,30 @@ __global__ void __launch_bounds__(128) exo_cost_kernel(const __grid_constant__ C
     }
 }
 
+// Longer trajectories (T > 32): one CTA per trajectory, one lane per timestep -- four times the loads in flight of the warp-per-
+// trajectory form, which was latency-bound (59 us for 4096 x 100 timesteps, long-scoreboard stalls 7 per issue); fixed summation
+// order (lanes, then the four warps), so the result does not depend on scheduling
+__global__ void __launch_bounds__(128) exo_cost_block_kernel(const __grid_constant__ CostParams P)
+{
+    __shared__ double part[4];
+    for (int64_t b = blockIdx.x; b < P.n_traj; b += gridDim.x)
+    {
+        double acc = 0.0;
+        for (int t = threadIdx.x; t < P.T; t += 128)
+        {
+            const int64_t e = b * P.T + t;
+            const double c = t >= P.t_first ? eval_cost(P, e, t) : 0.0;
+            if (P.cost_eval) P.cost_eval[e] = c;
+            acc += c;
+        }
+        acc = warp_sum_d(acc);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0 && P.cost_traj) P.cost_traj[b] = (part[0] + part[1]) + (part[2] + part[3]);
+        __syncthreads();
+    }
+}
+
 // End-pose problems (T = 1): one lane per configuration instead of one warp per single-timestep "trajectory"
 __global__ void __launch_bounds__(128) exo_cost_endpose_kernel(const __grid_constant__ CostParams P)
 {
@@ -278,6 +302,11 @@ cudaError_t launch_cost(const CostParams& P, cudaStream_t stream)
     {
         const int64_t b1 = (P.n_traj + 127) / 128;
         exo_cost_endpose_kernel<<<(int)(b1 < 148 * 16 ? b1 : 148 * 16), 128, 0, stream>>>(P);
+        return cudaGetLastError();
+    }
+    if (P.T > 32)
+    {
+        exo_cost_block_kernel<<<(int)(P.n_traj < 148 * 32 ? P.n_traj : 148 * 32), 128, 0, stream>>>(P);
         return cudaGetLastError();
     }
     const int64_t blocks = (P.n_traj + 3) / 4;  // 4 warps (trajectories) per CTA
