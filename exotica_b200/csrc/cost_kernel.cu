@@ -200,6 +200,11 @@ __global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_con
             }
 #pragma unroll
             for (int k = 0; k < NT * (NT + 1) / 2; ++k) Racc[k] = 0.0;
+#ifndef EXO_AICO_UNROLL
+#define EXO_AICO_UNROLL 1  // 2 or 3 rows cost 20 registers (178: two CTAs per SM instead of three) for no more loads in flight per SM
+#endif
+            constexpr int kRowsInFlight = EXO_AICO_UNROLL;  // rows of J whose loads are issued before the first is consumed
+#pragma unroll kRowsInFlight
             for (int r = 0; r < LJ; ++r)
             {
                 const double yd = v[r * 128], prec = a[r * 128];
