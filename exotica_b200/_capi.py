@@ -634,12 +634,14 @@ class Problem(object):
     def set_kernel(self, choice):
         check(lib().exo_problem_set_kernel(self.h, int(choice)))
 
-    def generated_kernel_source(self, compile=False):
-        """CUDA source of the per-robot generated tree kernel; compile=True also runs NVRTC (works without a GPU)."""
+    def generated_kernel_source(self, compile=False, cost=False):
+        """CUDA source of the per-robot generated tree kernel (cost=True: of the fused cost + gradient kernel, after set_cost);
+        compile=True also runs NVRTC (works without a GPU)."""
         need = ctypes.c_int64(0)
-        check(lib().exo_problem_generated_kernel_source(self.h, None, 0, ctypes.byref(need), 0))
+        kind = 2 if cost else 0
+        check(lib().exo_problem_generated_kernel_source(self.h, None, 0, ctypes.byref(need), kind))
         buf = ctypes.create_string_buffer(need.value)
-        check(lib().exo_problem_generated_kernel_source(self.h, buf, need.value, None, 1 if compile else 0))
+        check(lib().exo_problem_generated_kernel_source(self.h, buf, need.value, None, kind | (1 if compile else 0)))
         return buf.value.decode()
 
     def last_kernel(self):

@@ -930,12 +930,21 @@ int exo_problem_set_kernel(exo_problem* p, int choice)
     return EXO_OK;
 }
 
+static bool tree_costgrad_prepare(exo_problem* p);
+
 int exo_problem_generated_kernel_source(exo_problem* p, char* out, int64_t capacity, int64_t* needed, int32_t compile)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
     if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
-    if (!tree_prepare(p)) return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
-    const std::string& src = p->tree_plan.source;
+    const bool cost_kernel = (compile & 2) != 0;  // bit 1: the fused cost + gradient kernel (needs exo_problem_set_cost) instead of the update kernel
+    if (cost_kernel)
+    {
+        if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+        if (!tree_costgrad_prepare(p)) return fail(EXO_ERR_UNSUPPORTED, "generated cost kernel not applicable: " + p->tcg_why);
+    }
+    else if (!tree_prepare(p))
+        return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
+    const std::string& src = cost_kernel ? p->tcg_plan.source : p->tree_plan.source;
     if (needed) *needed = (int64_t)src.size() + 1;
     if (out && capacity > 0)
     {
@@ -943,11 +952,12 @@ int exo_problem_generated_kernel_source(exo_problem* p, char* out, int64_t capac
         memcpy(out, src.data(), n);
         out[n] = 0;
     }
-    if (compile)
+    if (compile & 1)
     {
         std::vector<char> cubin;
         std::string err;
-        if (!tree_jit_compile(p->tree_plan, cubin, err)) return fail(EXO_ERR_UNSUPPORTED, "run-time compilation failed: " + err);
+        const bool ok = cost_kernel ? tree_costgrad_jit_compile(p->tcg_plan, cubin, err) : tree_jit_compile(p->tree_plan, cubin, err);
+        if (!ok) return fail(EXO_ERR_UNSUPPORTED, "run-time compilation failed: " + err);
     }
     return EXO_OK;
 }

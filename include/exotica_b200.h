@@ -247,8 +247,10 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
  * least EXO_TREE_MIN_EVALS = 4096 evaluations, smaller ones stay on the interpreter).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);
 /* CUDA source of the per-robot generated kernel (choice 9 above) for the current model state: copies at most capacity - 1
- * characters into out (may be NULL) and reports the size needed; compile != 0 also runs NVRTC (no device needed) and returns
- * EXO_ERR_UNSUPPORTED with the compiler log if it fails.  Replaces nothing in the reference: introspection for tests. */
+ * characters into out (may be NULL) and reports the size needed; bit 0 of `compile` also runs NVRTC (no device needed) and returns
+ * EXO_ERR_UNSUPPORTED with the compiler log if it fails; bit 1 selects the generated fused cost + gradient kernel of tree programs
+ * (exo_tree_costgrad_kernel, after exo_problem_set_cost) instead of the update kernel.  Replaces nothing in the reference:
+ * introspection for tests. */
 int exo_problem_generated_kernel_source(exo_problem* problem, char* out, int64_t capacity, int64_t* needed, int32_t compile);
 /* Name of the kernel the most recent launch used ("exo_chain_kernel" / "exo_chain_tma_kernel" / "exo_tree_kernel" / "exo_eval_kernel" / "exo_spheres_kernel" (the
  * second launch of a SphereCollision program) / "none"). */
