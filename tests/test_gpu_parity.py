@@ -797,6 +797,8 @@ def test_cost_gradient_and_aico_messages_on_a_tree_robot(oracle_lib):
         for b in range(B):
             gref = orc.trajectory_cost_jacobian(X[b], rho, goal=goal, ct=ct, W=W)
             assert np.max(np.abs(grad_f.reshape(B, T, N)[b] - gref)) <= 1e-10 * max(1.0, np.abs(gref).max())
+    src = prob.generated_kernel_source(cost=True)
+    assert "exo_tree_costgrad_kernel" in src and "get_angle_axis(M, vx, vy, vz);" in src
     # cost only (NULL gradient) through the same generated kernel
     dxc, dcc = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(B)
     dxc.upload(X.reshape(E, N).T)
