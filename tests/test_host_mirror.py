@@ -405,6 +405,7 @@ def test_cfg4_through_the_product_loader_at_full_size(oracle_lib):
     X[:, 3:6] = rng.uniform(-np.pi, np.pi, size=(E, 3))
     X[:, 4] = np.clip(X[:, 4], -np.pi / 2 + 0.05, np.pi / 2 - 0.05)
     sel, phi, jac = _device_update_sampled(prob, X, 1, blocks=4, block=256)
+    assert prob.last_kernel() == "exo_tree_kernel"  # URDF loader -> compiler -> generated source -> NVRTC -> TMA kernel
     phi_ref, jac_ref = orc.problem_update_batch(X[sel])
     assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
 
