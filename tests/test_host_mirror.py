@@ -350,19 +350,25 @@ def test_ik_solver_and_hessian_through_the_python_surface(oracle_lib):
 
 
 # ---- the product loader -> compiler -> kernel chain at BASELINE.json's sizes (no oracle tree handed to the C-ABI) -----------------
-def _device_update_sampled(prob, X, T, blocks=8, block=512):
-    """Full-size update on device buffers (evaluation-major), then `blocks` contiguous slices of `block` evaluations come back."""
+def _device_update_sampled(prob, X, T, blocks=8, block=512, layout=None):
+    """Full-size update on device buffers (evaluation-major, or the kernel-native SoA layout), then `blocks` contiguous slices of
+    `block` evaluations come back."""
     from exotica_b200 import _capi
+    layout = exo.LAYOUT_AOS_ROWMAJOR if layout is None else layout
     E, N = X.shape
     LP, LJ = prob.length_Phi, prob.length_jacobian
     dx, dphi, djac = _capi.DeviceBuffer(E * N), _capi.DeviceBuffer(E * LP), _capi.DeviceBuffer(E * LJ * N)
-    dx.upload(X)
-    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=exo.LAYOUT_AOS_ROWMAJOR)
+    dx.upload(X.T if layout == exo.LAYOUT_SOA else X)
+    prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, layout=layout)
     _capi.check(_capi.lib().exo_device_synchronize())
     starts = np.linspace(0, E - block, blocks).astype(np.int64) // T * T
     sel = np.concatenate([np.arange(s, s + block) for s in starts])
-    phi = np.concatenate([dphi.download((block, LP), offset=s * LP) for s in starts])
-    jac = np.concatenate([djac.download((block, LJ, N), offset=s * LJ * N) for s in starts])
+    if layout == exo.LAYOUT_SOA:  # Phi[LP][E], J[LJ][N][E]: one slice per row
+        phi = np.concatenate([np.stack([dphi.download((block,), offset=k * E + s) for k in range(LP)], axis=1) for s in starts])
+        jac = np.concatenate([np.stack([djac.download((block,), offset=k * E + s) for k in range(LJ * N)], axis=1).reshape(block, LJ, N) for s in starts])
+    else:
+        phi = np.concatenate([dphi.download((block, LP), offset=s * LP) for s in starts])
+        jac = np.concatenate([djac.download((block, LJ, N), offset=s * LJ * N) for s in starts])
     for b in (dx, dphi, djac):
         b.free()
     return sel, phi, jac
@@ -381,10 +387,11 @@ def test_cfg3_through_the_product_loader_at_full_size(oracle_lib):
     rng = np.random.default_rng(21)
     q0 = rng.uniform(orc.lower, orc.upper, size=(B, 1, 7))
     X = np.clip(q0 + np.cumsum(rng.normal(0, 0.05, size=(B, T, 7)), axis=1), orc.lower - 0.1, orc.upper + 0.1).reshape(B * T, 7)
-    sel, phi, jac = _device_update_sampled(prob, X, T)
-    assert prob.last_kernel() in ("exo_chain_kernel", "exo_chain_tma_kernel")
-    phi_ref, jac_ref = orc.problem_update_batch(X[sel], T=T)
-    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    for layout in (exo.LAYOUT_AOS_ROWMAJOR, exo.LAYOUT_SOA):
+        sel, phi, jac = _device_update_sampled(prob, X, T, layout=layout)
+        assert prob.last_kernel() == "exo_chain_kernel"  # the JointLimit block keeps cfg3 on the per-lane store kernel
+        phi_ref, jac_ref = orc.problem_update_batch(X[sel], T=T)
+        assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
 
 
 @pytest.mark.gpu
@@ -405,7 +412,11 @@ def test_cfg4_through_the_product_loader_at_full_size(oracle_lib):
     X[:, 3:6] = rng.uniform(-np.pi, np.pi, size=(E, 3))
     X[:, 4] = np.clip(X[:, 4], -np.pi / 2 + 0.05, np.pi / 2 - 0.05)
     sel, phi, jac = _device_update_sampled(prob, X, 1, blocks=4, block=256)
-    assert prob.last_kernel() == "exo_tree_kernel"  # URDF loader -> compiler -> generated source -> NVRTC -> TMA kernel
+    phi_ref, jac_ref = orc.problem_update_batch(X[sel])
+    assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    # the kernel-native layout: URDF loader -> compiler -> generated source -> NVRTC -> TMA kernel
+    sel, phi, jac = _device_update_sampled(prob, X, 1, blocks=2, block=128, layout=exo.LAYOUT_SOA)
+    assert prob.last_kernel() == "exo_tree_kernel"
     phi_ref, jac_ref = orc.problem_update_batch(X[sel])
     assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
 
