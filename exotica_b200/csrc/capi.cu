@@ -96,6 +96,7 @@ struct exo_problem
         bool ok = false;
     } chain_tma_key;
     // per-robot generated kernel for tree programs (tree_codegen.cpp / tree_jit.cu)
+    int tree_small_calls = 0;     // launches with 256 <= E < EXO_TREE_MIN_EVALS so far: from the 16th on they take the generated kernel too
     int tree_version = -2;        // compiled_version the plan below was generated for
     bool tree_ok = false;         // source generated (the program is inside the generator's scope)
     void* tree_kernel = nullptr;  // loaded module entry (nullptr until the first eligible launch on a device)
@@ -708,7 +709,10 @@ static int launch(exo_problem* p, const double* d_x, int64_t E, int64_t stride_E
     // tree programs: the per-robot generated kernel (TMA output) when the buffers qualify; run-time compiled on first use, so
     // small batches stay on the interpreter unless exo_problem_set_kernel(9) asks for it
     bool gen = false;
-    if (!chain && n_sph_ops == 0 && (p->kernel_choice == 9 || (p->kernel_choice == 0 && E >= tree_min_evals() && !p->tree_jit_failed)))
+    // a solver that keeps calling with a smaller batch earns the compiler after a few calls (the interpreter serves the first ones)
+    if (!chain && n_sph_ops == 0 && p->kernel_choice == 0 && E < tree_min_evals() && E >= 256 && p->tree_small_calls < 1000000) p->tree_small_calls++;
+    const bool worth_compiling = E >= tree_min_evals() || (E >= 256 && p->tree_small_calls >= 16);
+    if (!chain && n_sph_ops == 0 && (p->kernel_choice == 9 || (p->kernel_choice == 0 && worth_compiling && !p->tree_jit_failed)))
     {
         if (tree_prepare(p))
         {
@@ -1523,6 +1527,9 @@ int exo_problem_cost_allgather(exo_problem* p, exo_comm* comm, const double* d_x
     return exo_comm_allgather(comm, mine, d_cost_all, n_traj_per_rank, stream);
 }
 
+extern "C" int exo_internal_min_gather(exo_comm* c, const double* d_min_traj_local, int64_t n_traj_local, int64_t n_traj_per_rank, double* d_min_traj_all,
+                                       double* d_min_global, void* stream);
+
 int exo_min_distance_allgather(exo_comm* comm, const double* d_min_eval, int64_t n_traj_local, int32_t T, int64_t n_traj_per_rank, double* d_min_traj_all,
                                double* d_min_global, void* stream)
 {
@@ -1537,6 +1544,9 @@ int exo_min_distance_allgather(exo_comm* comm, const double* d_min_eval, int64_t
         double* mine = d_min_traj_all + (int64_t)exo_comm_rank(comm) * n_traj_per_rank;
         e = launch_reduce(d_min_eval, n_traj_local, T, 0, EXO_REDUCE_MIN, mine, s);
         if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+        // several ranks with peer windows: padding, exchange and global minimum in one kernel over NVLink peer memory
+        if (exo_comm_world_size(comm) > 1 && exo_internal_min_gather(comm, mine, n_traj_local, n_traj_per_rank, d_min_traj_all, d_min_global, stream) == EXO_OK)
+            return EXO_OK;
         e = launch_fill(mine + n_traj_local, n_traj_per_rank - n_traj_local, (double)INFINITY, s);
         if (e != cudaSuccess) return cuda_fail(e, "fill kernel launch");
         int rc = exo_comm_allgather(comm, mine, d_min_traj_all, n_traj_per_rank, stream);

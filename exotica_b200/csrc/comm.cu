@@ -13,6 +13,7 @@
 // Messages of at most 64 KB per rank -- every message of this path -- bypass NCCL: one kernel over peer-mapped windows (NVLink P2P
 // stores + flags, below); NCCL remains the rendezvous, the carrier of large messages and the fallback (EXO_COMM_PEER=0).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>
@@ -205,6 +206,61 @@ __global__ void __launch_bounds__(512) exo_peer_collective_kernel(Window w, Peer
                 a = op == EXO_REDUCE_MIN ? fmin(a, b) : (op == EXO_REDUCE_MAX ? fmax(a, b) : a + b);
             }
             recv[i] = a;
+        }
+    }
+}
+
+// Exchange and global result of exo_min_distance_allgather in one kernel: this rank's per-trajectory minima (padded with +inf for
+// the trajectories it does not hold) into every peer's window, flags, wait, then the gathered minima copied out and reduced to the
+// global minimum -- every rank holds every trajectory's value, so no second collective is needed.  Replaces fill + gather + reduce.
+// (The reduction over the timesteps stays a kernel of its own: done by this one CTA it took 215 us for 2048 x 100 evaluations.)
+__global__ void __launch_bounds__(512) exo_peer_min_gather_kernel(Window w, PeerTable peers, const double* traj_in, int n_local, int count, double* recv_all,
+                                                                  double* global_out, int rank, int world)  // traj_in may be a slot of recv_all
+{
+    __shared__ unsigned long long s_seq;
+    __shared__ double s_part[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_seq = ++(*w.seq);
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const size_t slot = ((size_t)(seq & 1) * world + rank) * WIN_SLOT;
+    for (int k = tid; k < world * count; k += blockDim.x)
+    {
+        const int p = k % world, i = k / world;
+        peers.buf[p][slot + i] = i < n_local ? traj_in[i] : INFINITY;
+    }
+    __syncthreads();
+    if (tid < world)
+    {
+        __threadfence_system();
+        st_release_sys(peers.flag[tid] + rank, seq);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(w.flag + tid) < seq)
+            if (clock64() - t0 > 600000000000ll)
+            {
+                *w.error = 1;
+                break;
+            }
+    }
+    __syncthreads();
+    const double* mine = w.buf + (size_t)(seq & 1) * world * WIN_SLOT;
+    double g = INFINITY;
+    for (int idx = tid; idx < world * count; idx += blockDim.x)
+    {
+        const int r = idx / count, i = idx - r * count;
+        const double v = __ldcg(mine + (size_t)r * WIN_SLOT + i);
+        if (recv_all) recv_all[(int64_t)r * count + i] = v;
+        g = fmin(g, v);
+    }
+    if (global_out)
+    {
+        for (int o = 16; o > 0; o >>= 1) g = fmin(g, __shfl_xor_sync(0xffffffffu, g, o));
+        if (lane == 0) s_part[warp] = g;
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int k = 1; k < 16; ++k) g = fmin(g, s_part[k]);
+            global_out[0] = g;
         }
     }
 }
@@ -414,6 +470,20 @@ int exo_comm_world_size(const exo_comm* c)
 int64_t exo_comm_collective_count(const exo_comm* c)
 {
     return c ? c->collectives : -1;
+}
+
+// used by exo_min_distance_allgather (capi.cu) on this rank's per-trajectory minima: EXO_OK when the fused peer kernel took the call,
+// EXO_ERR_UNSUPPORTED (no error text) when the communicator has no peer windows or the message does not fit them -- the caller then
+// runs the unfused sequence
+int exo_internal_min_gather(exo_comm* c, const double* d_min_traj_local, int64_t n_traj_local, int64_t n_traj_per_rank, double* d_min_traj_all,
+                            double* d_min_global, void* stream)
+{
+    if (!c || !c->peer_ok || n_traj_per_rank < 1 || n_traj_per_rank > WIN_SLOT || n_traj_local > n_traj_per_rank) return EXO_ERR_UNSUPPORTED;
+    exo_peer_min_gather_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(c->win, c->peers, d_min_traj_local, (int)n_traj_local, (int)n_traj_per_rank, d_min_traj_all,
+                                                                     d_min_global, c->rank, c->world);
+    CUDA_TRY(cudaGetLastError());
+    c->peer_collectives++;
+    return EXO_OK;
 }
 
 int64_t exo_comm_peer_collective_count(const exo_comm* c)

@@ -200,7 +200,15 @@ def test_generated_tree_kernel(oracle_lib, E):
         assert np.array_equal(phi_only, phi)
     assert record("generated_tree_phi", max_abs_err(phi, phi_ref, wrap)) <= TOL
     assert record("generated_tree_jac", max_abs_err(jac, jac_ref)) <= TOL
-    # model state change (a joint outside the group): the source is regenerated with the new constants
+    # a solver loop with a small batch: the interpreter serves the first calls, the generated kernel the later ones
+    if E == 3002:
+        prob.set_kernel(0)
+        seen = []
+        for _ in range(18):
+            phi_s, jac_s = run_gpu(prob, X[:512])
+            seen.append(prob.last_kernel())
+        assert seen[0] == "exo_eval_kernel" and seen[-1] == "exo_tree_kernel"
+        assert max_abs_err(phi_s, phi_ref[:512], wrap) <= TOL and max_abs_err(jac_s, jac_ref[:512]) <= TOL
     if E == 3002:
         prob.set_kernel(9)
         src = prob.generated_kernel_source()

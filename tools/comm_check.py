@@ -74,6 +74,7 @@ def main():
         print(json.dumps({"check": "collectives", "world": world, "max_abs_err": worst, "allgather_512_doubles_us": us,
                           "peer_collectives": comm.peer_collective_count(), "nccl_collectives": comm.collective_count(),
                           "path": "peer windows" if comm.peer_collective_count() > 0 else "NCCL"}), flush=True)
+    graph.__del__()  # graphs that captured NCCL kernels go before their communicator
     comm.barrier(stream)
     comm.destroy()
     if worst > 1e-12:
