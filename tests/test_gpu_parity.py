@@ -179,6 +179,8 @@ def test_generated_tree_kernel(oracle_lib, E):
                 {"Link": "leftPalm", "BaseOffset": [0.2, 0.1, 0.3, 0.0, 0.3, 0.1]}, {"Link": "rightPalm"}]},
             {"type": "EffPosition", "EndEffector": [{"Link": "head"}, {"Link": "torso"}]},
             {"type": "JointLimit", "SafePercentage": 0.05}]
+    if E == 8192:  # an unused map between the used ones: its SetZero values per lane, its Jacobian rows from the zero tile
+        maps.insert(1, {"type": "EffFrame", "Type": "Quaternion", "used": False, "EndEffector": [{"Link": "leftForearmLink"}, {"Link": "pelvis"}]})
     X = random_states(orc, E, seed=500 + E)
     X[:, 3:6] = np.random.default_rng(E).uniform(-1.3, 1.3, size=(E, 3))
     X[min(E - 1, 40), 20] = 3.0e5  # beyond the fast sin / cos reduction: the cold path of that joint
