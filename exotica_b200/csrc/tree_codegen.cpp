@@ -237,6 +237,7 @@ struct Item  // one block of values a lane stages: the Phi entries of a frame, o
     int box = -1, col_in_box = 0;
     int batch = -1;       // index of its batch within its pass
     int jop = -1;         // J: the joint op whose axis / origin the column is built from
+    int row_mode = ROWS_VW;  // J: which rows of the column the map keeps (program.h RowMode)
 };
 struct Box
 {
@@ -293,13 +294,14 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             for (int k = 0; k < tp[0]; ++k)
             {
                 const int32_t* ent = tp + 1 + TP_INTS * k;
-                if (ent[3] != ROWS_VW && ent[3] != ROWS_V)
+                if (ent[3] != ROWS_VW && ent[3] != ROWS_V && ent[3] != ROWS_W && ent[3] != ROWS_VXY)
                 {
-                    why = "a map keeps Jacobian rows other than (v, w) / (v)";
+                    why = "a map keeps Jacobian rows other than (v, w) / (v) / (w) / (vx, vy)";
                     return false;
                 }
                 Item it;
-                it.op = i; it.phi = false; it.nrows = ent[3] == ROWS_VW ? 6 : 3;
+                it.op = i; it.phi = false; it.nrows = ent[3] == ROWS_VW ? 6 : (ent[3] == ROWS_VXY ? 2 : 3);
+                it.row_mode = ent[3];
                 it.key = ent[2]; it.col = ent[1]; it.ps = ent[0]; it.flags = ent[4]; it.cst_b = ent[5];
                 op_items[i].push_back((int)items.size());
                 items.push_back(it);
@@ -310,13 +312,15 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         else if (op.kind == OP_EMIT_FRAME)
         {
             const int row_mode = (op.flags & F_ROWS_MASK) >> F_ROWS_SHIFT;
-            if ((row_mode != ROWS_VW && row_mode != ROWS_V) || (op.flags & F_B_MASK) == F_B_SLOT)
+            if ((row_mode != ROWS_VW && row_mode != ROWS_V && row_mode != ROWS_W && row_mode != ROWS_VXY) || (op.flags & F_B_MASK) == F_B_SLOT)
             {
                 why = "a requested frame is outside the generated kernel's scope";
                 return false;
             }
             int rows = 0;
             if (op.map_kind == EXO_MAP_EFF_POSITION) rows = 3;
+            else if (op.map_kind == EXO_MAP_EFF_POSITION_XY) rows = 2;
+            else if (op.map_kind == EXO_MAP_EFF_ORIENTATION && rotation_length(op.rot_type) > 0) rows = rotation_length(op.rot_type);
             else if (op.map_kind == EXO_MAP_FRAMES) rows = 12;
             else if (op.map_kind == EXO_MAP_EFF_FRAME && rotation_length(op.rot_type) > 0) rows = 3 + rotation_length(op.rot_type);
             else
@@ -331,7 +335,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             n_pos = std::max(n_pos, op.n_items + 1);
             max_op_values = std::max(max_op_values, rows);
         }
-        else if (op.kind != OP_EMIT_JLIMIT && op.kind != OP_EMIT_FILL)
+        else if (op.kind != OP_EMIT_JLIMIT && op.kind != OP_EMIT_FILL && op.kind != OP_EMIT_JPOSE)
         {
             why = "an op is outside the generated kernel's scope";
             return false;
@@ -491,6 +495,17 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             flat_zero_run(op.jrow_off * N, op.n_rows * N);
             continue;
         }
+        if (op.kind == OP_EMIT_JPOSE)
+        {
+            // row i holds a single one in column map[i] (a per-lane store): zeros in front of it and behind it
+            for (int r = 0; r < op.n_items; ++r)
+            {
+                const int c1 = prog.ints[op.tab + r];
+                flat_zero_run((op.jrow_off + r) * N, c1);
+                flat_zero_run((op.jrow_off + r) * N + c1 + 1, N - c1 - 1);
+            }
+            continue;
+        }
         if (op.kind != OP_EMIT_FRAME) continue;
         const int nrows = op.n_rows;
         const int32_t* zl = &prog.ints[op.pad];
@@ -631,16 +646,19 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             const double* b = prog.dbls.data() + it.cst_b;
             for (int r = 0; r < 3; ++r) o.line("            const double tv%d = %s;", r, dot_const({"v0", "v1", "v2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
             o.line("            v0 = tv0; v1 = tv1; v2 = tv2;");
-            if (it.nrows == 6)
+            if (it.row_mode == ROWS_VW || it.row_mode == ROWS_W)
             {
                 for (int r = 0; r < 3; ++r)
                     o.line("            const double tw%d = %s;", r, dot_const({"w0", "w1", "w2"}, {b[3 * r], b[3 * r + 1], b[3 * r + 2]}, "").c_str());
                 o.line("            w0 = tw0; w1 = tw1; w2 = tw2;");
             }
         }
-        const char* vals[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
+        // EffFrame / raw frames: (v, w); EffPosition: v; EffOrientation: w; EffPositionXY: (vx, vy)
+        const char* vals_vw[6] = {"v0", "v1", "v2", "w0", "w1", "w2"};
+        const char* vals_w[3] = {"w0", "w1", "w2"};
+        const char* const* vals = it.row_mode == ROWS_W ? vals_w : vals_vw;
         for (int r = 0; r < it.nrows; ++r) o.line("            %s[%d] = %s;", stg, (bx.off + r * bx.ncols + it.col_in_box) * TILE, vals[r]);
-        if (it.nrows != 6) o.line("            (void)w0; (void)w1; (void)w2;");
+        o.line("            (void)v0; (void)v1; (void)v2; (void)w0; (void)w1; (void)w2;");
         o.line("        }");
         if (bt.last_item == (int)(&it - items.data())) emit_flush(bt, ibuf);
     };
@@ -754,6 +772,21 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                     o.line("            if (P.jac) __stcs(P.jac + %d * P.j_sr + %d * P.j_sc + e, (q >= %s && q <= %s) ? 0.0 : 1.0);", op.jrow_off + k, k, lit(lo_t).c_str(),
                            lit(hi_t).c_str());
                     o.line("        }");
+                }
+                o.line("    }");
+            }
+            else if (op.kind == OP_EMIT_JPOSE && pass == 0)
+            {
+                // JointPose::Update (joint_pose.cpp:36-57): phi_i = q[map_i] - ref_i, J(i, map_i) = 1 -- per-lane streaming stores; the zeros
+                // around the ones are TMA boxes of the zero tile
+                o.line("    // op %d: JointPose", i);
+                o.line("    if (valid)");
+                o.line("    {");
+                for (int k = 0; k < op.n_items; ++k)
+                {
+                    const int c1 = prog.ints[op.tab + k];
+                    o.line("        __stcs(P.phi + %d * P.phi_sk + e, xq[%d * P.x_sk] - %s);", op.phi_off + k, c1, lit(c[k]).c_str());
+                    o.line("        if (P.jac) __stcs(P.jac + %d * P.j_sr + %d * P.j_sc + e, 1.0);", op.jrow_off + k, c1);
                 }
                 o.line("    }");
             }

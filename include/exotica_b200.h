@@ -242,8 +242,8 @@ int exo_problem_last_kernel_ms(exo_problem* problem, float* ms);
  * EXO_CHAIN_TMA=0 keeps choice 0 on the per-lane stores), 9 = the per-robot generated kernel for tree programs (the
  * two-pass program unrolled into straight-line CUDA C++ with the robot's constants as literals, compiled at run time with
  * NVRTC for sm_100a and cached; one warp per 32 evaluations, Phi / J staged in shared memory and stored by the TMA unit,
- * structural zeros of J from a shared zero tile; EffFrame / EffPosition / raw frames / JointLimit maps with constant base
- * frames, EXO_LAYOUT_SOA buffers with an even row pitch; EXO_ERR_UNSUPPORTED otherwise; choice 0 takes it for batches of at
+ * structural zeros of J from a shared zero tile; EffFrame / EffPosition / EffOrientation / EffPositionXY / raw frames /
+ * JointLimit / JointPose maps with constant base frames, EXO_LAYOUT_SOA buffers with an even row pitch; EXO_ERR_UNSUPPORTED otherwise; choice 0 takes it for batches of at
  * least EXO_TREE_MIN_EVALS = 4096 evaluations, and from the 16th call on for batches of at least 256 -- a solver loop earns the
  * 0.3-2 s of compilation, a one-off small call stays on the interpreter).  Tests compare all of them. */
 int exo_problem_set_kernel(exo_problem* problem, int choice);

@@ -217,6 +217,36 @@ def test_generated_tree_kernel(oracle_lib, E):
         assert "exo_tree_kernel" in src and "cp.async.bulk.tensor.3d" in src
 
 
+def test_generated_tree_kernel_sibling_maps(oracle_lib):
+    """EffOrientation (angular rows), EffPositionXY (two linear rows) and JointPose beside an EffFrame map on the humanoid: all inside
+    the generated kernel's scope; a Distance map is not (its program has no two-pass form) and says so."""
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffOrientation", "Type": "ZYZ", "EndEffector": [{"Link": "leftPalm", "LinkOffset": [0, 0, 0.05, 0.2, 0.1, -0.3]}, {"Link": "head"}]},
+            {"type": "EffPositionXY", "EndEffector": [{"Link": "rightFoot"}, {"Link": "torso", "BaseOffset": [0.1, 0.2, 0.0]}]},
+            {"type": "JointPose", "JointMap": [7, 20, 3, 37], "JointRef": [0.1, -0.2, 0.3, 0.05]},
+            {"type": "EffFrame", "Type": "Matrix", "EndEffector": [{"Link": "rightPalm"}]}]
+    E = 4096
+    X = random_states(orc, E, seed=611)
+    X[:, 3:6] = np.random.default_rng(612).uniform(-1.2, 1.2, size=(E, 3))
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    phi_ref, jac_ref = orc.problem_update_batch(X)
+    prob.set_kernel(9)
+    phi, jac = run_gpu(prob, X)
+    assert prob.last_kernel() == "exo_tree_kernel"
+    assert record("generated_siblings_phi", max_abs_err(phi, phi_ref, angle_entries(maps, orc))) <= TOL
+    assert record("generated_siblings_jac", max_abs_err(jac, jac_ref)) <= TOL
+    prob.set_kernel(1)
+    phi_i, jac_i = run_gpu(prob, X[:512])
+    assert max_abs_err(phi_i, phi[:512], angle_entries(maps, orc)) <= 1e-12 and max_abs_err(jac_i, jac[:512]) <= 1e-12
+    maps = [{"type": "Distance", "EndEffector": [{"Link": "leftPalm", "Base": "rightPalm"}]}]
+    orc.set_problem(maps)
+    tree2, prob2 = gpu_problem_from_maps(orc, maps)
+    prob2.set_kernel(9)
+    with pytest.raises(_capi.ExoticaError, match="generated tree kernel not applicable"):
+        run_gpu(prob2, X[:64])
+
+
 def test_gimbal_lock_set(oracle_lib):
     # pitch within 1e-13 of +-pi/2 on the floating base: the |pitch| > pi/2 - 1e-12 branch of GetRPY must agree
     orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
