@@ -1814,7 +1814,8 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     if (!d_q || !d_cost || !d_iterations || !d_termination) return fail(EXO_ERR_INVALID, "NULL buffer");
     if (prm->max_iterations < 1) return fail(EXO_ERR_INVALID, "max_iterations must be >= 1");
     const int N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
-    if (LJ > IK_MAXLJ || N > CH_MAXN) return fail(EXO_ERR_UNSUPPORTED, "batched IK supports up to 16 task-space rows and 16 joints");
+    if (LJ > IK_BIG_MAXLJ || N > IK_MAXN) return fail(EXO_ERR_UNSUPPORTED, "batched IK supports up to 64 task-space rows and 64 joints");
+    const bool big = LJ > IK_MAXLJ || N > CH_MAXN;  // whole-body problems: the step kernel with its system in a global workspace
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t E = n_evals;
     if (p->ik_capacity < E)
@@ -1824,7 +1825,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         p->d_ik = nullptr;
         p->d_ik_i = nullptr;
         p->ik_capacity = 0;
-        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 4) * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 4 + (big ? (size_t)LJ * LJ : 0)) * sizeof(double)));
         CUDA_TRY(cudaMalloc((void**)&p->d_ik_i, ((size_t)2 * E + 4) * sizeof(int32_t)));
         p->ik_capacity = E;
     }
@@ -1848,6 +1849,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     K.stop = w; w += E;
     K.lambda = w; w += E;
     K.steplen = w; w += E;
+    K.big_A = big ? w : nullptr;
     K.single_iteration = prm->max_iterations == 1 ? 1 : 0;
     K.max_step = prm->max_step;
     K.th_stepinc = prm->threshold_regularization_increase;

@@ -33,6 +33,132 @@ __global__ void __launch_bounds__(128) exo_ik_step_kernel(const __grid_constant_
         ik_step_one<0>(K, C, e);
 }
 
+// The same step for task spaces of up to IK_BIG_MAXLJ rows and IK_MAXN joints (whole-body problems: four end-effector frames of a
+// humanoid are 24 rows, 38 joints): one lane per configuration as above, but A = cJ W^-1 cJ^T lives in a global workspace laid out
+// [entry][E] (every access of a warp is one coalesced segment) -- its lower triangle holds A, the strict upper triangle the Cholesky
+// factor transposed, so a failed factorisation restarts with a larger lambda without rebuilding A.  A is accumulated column by
+// column of cJ (one column in local memory, rank-one update), so J is read once.
+__global__ void __launch_bounds__(128) exo_ik_step_big_kernel(const __grid_constant__ IkParams K, const __grid_constant__ CostParams C)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K.n_evals || !K.active[e]) return;
+    const int LJ = K.length_jac, N = K.n_ctrl;
+    const int64_t E = K.n_evals;
+    double yd[IK_BIG_MAXLJ], col[IK_BIG_MAXLJ], diag[IK_BIG_MAXLJ];
+    eval_ydiff(C, e, 0, yd, 1);
+    double error = 0.0;
+    for (int r = 0; r < LJ; ++r)
+    {
+        const double s = K.row_rho[r];
+        error += yd[r] * s * yd[r];
+        yd[r] *= s;
+    }
+    K.cost[e] = error;
+    K.err_prev[e] = error;
+    K.ls_done[e] = 0;
+    if (error < K.tolerance)
+    {
+        K.termination[e] = IK_TERM_FUNCTION_TOLERANCE;
+        K.active[e] = 0;
+        return;
+    }
+    const double* J = K.jac + e;
+    double* A = K.big_A + e;  // entry (r, s) at A[(r * LJ + s) * E]
+    for (int r = 0; r < LJ; ++r)
+        for (int s2 = 0; s2 <= r; ++s2) A[(int64_t)(r * LJ + s2) * E] = 0.0;
+    double stop2 = 0.0;
+    for (int c = 0; c < N; ++c)
+    {
+        for (int r = 0; r < LJ; ++r)
+        {
+            col[r] = K.row_rho[r] * J[(int64_t)(r * N + c) * E];
+            stop2 += col[r] * col[r];
+        }
+        const double wi = K.w_inv[c];
+        for (int r = 0; r < LJ; ++r)
+        {
+            const double a = col[r] * wi;
+            for (int s2 = 0; s2 <= r; ++s2) A[(int64_t)(r * LJ + s2) * E] += a * col[s2];
+        }
+    }
+    double lambda = K.lambda[e];
+    bool ok = false;
+    while (!ok)
+    {
+        // Eigen::LLT of A + lambda I; L(i, j), i > j, is kept at the transposed position (j, i)
+        ok = true;
+        for (int j = 0; j < LJ && ok; ++j)
+        {
+            double d = A[(int64_t)(j * LJ + j) * E] + lambda;
+            for (int k = 0; k < j; ++k)
+            {
+                const double l = A[(int64_t)(k * LJ + j) * E];
+                d -= l * l;
+            }
+            if (!(d > 0.0))
+            {
+                ok = false;
+                break;
+            }
+            const double ljj = sqrt(d);
+            diag[j] = ljj;
+            for (int i = j + 1; i < LJ; ++i)
+            {
+                double v = A[(int64_t)(i * LJ + j) * E];
+                for (int k = 0; k < j; ++k) v -= A[(int64_t)(k * LJ + i) * E] * A[(int64_t)(k * LJ + j) * E];
+                A[(int64_t)(j * LJ + i) * E] = v / ljj;
+            }
+        }
+        if (!ok)
+        {
+            lambda *= 10.0;  // IncreaseRegularization (ik_solver.h: regfactor_ = 10)
+            if (lambda > K.regmax)
+            {
+                K.lambda[e] = K.regmax;
+                K.termination[e] = IK_TERM_DIVERGENCE;
+                K.active[e] = 0;
+                return;
+            }
+        }
+    }
+    K.lambda[e] = lambda;
+    // z = (A + lambda I)^-1 yd: forward / backward substitution with L (z overwrites yd)
+    for (int i = 0; i < LJ; ++i)
+    {
+        double v = yd[i];
+        for (int k = 0; k < i; ++k) v -= A[(int64_t)(k * LJ + i) * E] * yd[k];
+        yd[i] = v / diag[i];
+    }
+    for (int i = LJ - 1; i >= 0; --i)
+    {
+        double v = yd[i];
+        for (int k = i + 1; k < LJ; ++k) v -= A[(int64_t)(i * LJ + k) * E] * yd[k];
+        yd[i] = v / diag[i];
+    }
+    // qd = W^-1 cJ^T z
+    for (int c = 0; c < N; ++c)
+    {
+        double acc = 0.0;
+        for (int r = 0; r < LJ; ++r) acc += K.row_rho[r] * J[(int64_t)(r * N + c) * E] * yd[r];
+        K.qd[(int64_t)c * E + e] = K.w_inv[c] * acc;
+    }
+    K.stop[e] = sqrt(stop2);
+    if (K.single_iteration && K.max_step != 0.0)
+    {
+        // ScaleToStepSize + q_ -= qd_ (ik_solver.cpp:139-143,235-243)
+        double max_vel = 0.0;
+        for (int c = 0; c < N; ++c) max_vel = fmax(max_vel, fabs(K.qd[(int64_t)c * E + e]));
+        for (int c = 0; c < N; ++c)
+        {
+            double v = K.qd[(int64_t)c * E + e];
+            if (max_vel > K.max_step) v = v * K.max_step / max_vel;
+            K.qd[(int64_t)c * E + e] = v;
+            K.q[(int64_t)c * E + e] -= v;
+        }
+        K.ls_done[e] = 1;
+    }
+}
+
 // q_trial = q - alpha qd for the configurations still searching; the others keep q (their evaluation is ignored)
 __global__ void __launch_bounds__(128) exo_ik_trial_kernel(const __grid_constant__ IkParams K, double alpha)
 {
@@ -101,7 +227,10 @@ cudaError_t launch_ik_init(const IkParams& K, double lambda0, cudaStream_t s)
 }
 cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s)
 {
-    exo_ik_step_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, C);
+    if (K.big_A)
+        exo_ik_step_big_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, C);
+    else
+        exo_ik_step_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, C);
     return cudaGetLastError();
 }
 cudaError_t launch_ik_trial(const IkParams& K, double alpha, cudaStream_t s)

@@ -340,7 +340,9 @@ cudaError_t launch_fill(double* out, int64_t n, double value, cudaStream_t strea
 void host_get_rotation(const double* data, int type, double* out9);
 
 // ---- batched IK step (ik_kernel.cu) ----
-constexpr int IK_MAXLJ = 16;  // rows of the task-space Jacobian
+constexpr int IK_MAXLJ = 16;  // rows of the task-space Jacobian the register / local-memory step kernel handles
+constexpr int IK_BIG_MAXLJ = 64;  // ... and the workspace step kernel (whole-body problems: several end-effector frames)
+constexpr int IK_MAXN = 64;       // controlled joints
 enum
 {
     // exotica::TerminationCriterion (exotica_core/include/exotica_core/planning_problem.h:49-62)
@@ -373,11 +375,12 @@ struct IkParams
     int32_t* iterations;  // [E]
     int32_t* termination; // [E]
     int32_t* n_active;    // [1]
-    double row_rho[IK_MAXLJ];  // rho of the map that owns each Jacobian row (S = diag)
-    double w_inv[CH_MAXN];     // 1 / W[c]
+    double* big_A;        // [LJ][LJ][E] workspace of exo_ik_step_big_kernel (A in the lower triangle, its Cholesky factor above it) or NULL
+    double row_rho[IK_BIG_MAXLJ];  // rho of the map that owns each Jacobian row (S = diag)
+    double w_inv[IK_MAXN];         // 1 / W[c]
 };
 cudaError_t launch_ik_init(const IkParams& K, double lambda0, cudaStream_t s);
-cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);
+cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);  // K.big_A != NULL: the workspace kernel
 cudaError_t launch_ik_trial(const IkParams& K, double alpha, cudaStream_t s);
 cudaError_t launch_ik_accept(const IkParams& K, const CostParams& C, double alpha, cudaStream_t s);
 cudaError_t launch_ik_finish(const IkParams& K, int last_iteration, cudaStream_t s);

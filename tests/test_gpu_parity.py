@@ -1186,6 +1186,37 @@ def test_batched_ik_matches_the_reference_solver(oracle_lib, monkeypatch):
     assert n_same >= E // 2 and (cost[term == 3] < 1e-5).all()
 
 
+def test_batched_ik_whole_body(oracle_lib):
+    """IKSolver::Solve on the 38-DoF humanoid with four end-effector frames (24 task rows: the step kernel with its 24 x 24 system in
+    a global workspace) and a JointLimit map without weight, from perturbed start states: the reference's path per start state where
+    it converges -- iteration counts, termination criteria, solutions."""
+    orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+    maps = [{"type": "EffFrame", "EndEffector": [{"Link": l} for l in ("leftFoot", "rightFoot", "leftPalm", "rightPalm")]}, {"type": "JointLimit"}]
+    orc.set_problem(maps)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    rng = np.random.default_rng(311)
+    lo, hi = np.maximum(orc.lower, -0.5), np.minimum(orc.upper, 0.5)
+    q_goal = rng.uniform(lo, hi) * 0.5
+    goal = orc.zero_goal()
+    goal[:24] = orc.problem_update(q_goal)[0][:24]
+    rho = [1.0, 0.0]
+    prob.set_cost(rho, T=1, goal=goal)
+    E = 64
+    Q0 = q_goal + rng.normal(0, 0.05, size=(E, orc.n))
+    Q, cost, iters, term = prob.ik_solve_batch(Q0, max_iterations=40)
+    n_same = 0
+    for e in range(0, E, 4):
+        q_ref, c_ref, it_ref, t_ref = orc.ik_solve(Q0[e], rho, goal=goal, max_iterations=40)
+        assert record("ik_wb_cost_rel", abs(cost[e] - orc.trajectory_cost(Q[e:e + 1], rho, goal=goal)[0]) / max(1.0, cost[e])) <= TOL
+        if t_ref == 3:
+            assert term[e] == 3 and iters[e] == it_ref
+            assert np.max(np.abs(Q[e] - q_ref)) <= 1e-6 and abs(cost[e] - c_ref) <= 1e-9
+            n_same += 1
+        else:
+            assert term[e] == t_ref or abs(cost[e] - c_ref) <= 1e-3 * max(1.0, c_ref)
+    assert n_same >= 8
+
+
 def test_batched_ik_position_only_on_the_three_dof_robot(oracle_lib):
     orc = _oracle(oracle_lib, "test_robot", "arm")
     maps = [{"type": "EffPosition", "EndEffector": [{"Link": "endeff"}]}]

@@ -44,6 +44,12 @@ def timed(fn, reps):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
+def wb_goal(problem, q):
+    """Phi of the whole-body problem's EffFrame map at state q (the IK goal)."""
+    problem.update(q)
+    return np.array(problem.Phi)[:24]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
@@ -176,6 +182,20 @@ def main():
     ms = timed(lambda: b2.cost_gradient_batch_device(dx2.ptr, E2, dg2.ptr, dc2.ptr), args.reps)
     line("whole-body cost + gradient, Phi / J round trip (update + cost + %s), device" % b2.last_kernel(), ms, E2, "evals", None,
          max_abs_diff_vs_fused=float(np.max(np.abs(dg2.download((N2, E2)) - g_fused))))
+    # whole-body multi-start IK (BASELINE config 4's shape: 38 DoF, four end-effector frames = 24 task rows): 65 536 start states
+    q_goal = np.random.default_rng(10).uniform(np.maximum(lo, -0.5), np.minimum(hi, 0.5)) * 0.5
+    goal = " ".join("%.17g" % v for v in wb_goal(wb, q_goal))
+    ik_init = ("exotica/UnconstrainedEndPoseProblem", {"Name": "wbik", "PlanningScene": scene("valkyrie_sim", "whole_body"), "Maps": maps[:1],
+                                                       "Cost": [("exotica/Task", {"Task": "Eff", "Rho": "1", "Goal": goal})]})
+    solver = exo.IKSolver({"MaxIterations": 20})
+    solver.specify_problem(exo.Setup.create_problem(ik_init))
+    Q0 = q_goal + np.random.default_rng(11).normal(0, 0.05, size=(1 << 16, N2))
+    solver.solve_batch(Q0[:4096])
+    t1 = time.perf_counter()
+    Q, cost, iters, term = solver.solve_batch(Q0)
+    t2 = time.perf_counter()
+    line("whole-body batched IK (host call, 65536 starts, <= 20 iterations, 24 task rows x 38 joints)", (t2 - t1) * 1e3, Q0.shape[0], "solves",
+         None, mean_iterations=float(iters.mean()), cost_below_1e_4=float((cost < 1e-4).mean()))
     b2.h = None
     for b in (dx2, dg2, dc2):
         b.free()
