@@ -42,8 +42,13 @@ __global__ void __launch_bounds__(128) exo_cost_kernel(const __grid_constant__ C
 
 // Longer trajectories (T > 32): one CTA per trajectory, one lane per timestep -- four times the loads in flight of the warp-per-
 // trajectory form, which was latency-bound (59 us for 4096 x 100 timesteps, long-scoreboard stalls 7 per issue); fixed summation
-// order (lanes, then the four warps), so the result does not depend on scheduling
-__global__ void __launch_bounds__(128) exo_cost_block_kernel(const __grid_constant__ CostParams P)
+// order (lanes, then the four warps), so the result does not depend on scheduling.  What bounds it (ncu, 4096 x 100 timesteps): the
+// ~1000 warp-instructions of one evaluation are a serial stream (dependent FP64 chains of the rotation log, ~10 exposed memory waits)
+// at 14 cycles per issue, so the time follows the resident warps: 4 / 5 / 7 / 8 CTAs per SM (118 / 96 / 72 / 64 registers) take
+// 39.3 / 35.7 / 30.2 / 29.8 us -- hence the 64-register build.  Measured and dropped: staging the trajectory's Phi rows, states and
+// the goal / rho tables in shared memory first (every load independent, none left in the evaluation; 44 us -- the load and
+// evaluation phases of a CTA no longer overlap) and L1 / L2 prefetches of the evaluation's entries (38 us).
+__global__ void __launch_bounds__(128, 8) exo_cost_block_kernel(const __grid_constant__ CostParams P)
 {
     __shared__ double part[4];
     for (int64_t b = blockIdx.x; b < P.n_traj; b += gridDim.x)
@@ -80,8 +85,10 @@ __global__ void __launch_bounds__(128) exo_cost_endpose_kernel(const __grid_cons
 //   grad[t] = 2 ct J[t]^T S[t] ydiff[t] + 2 ct W xdiff[t] - 2 ct W xdiff[t + 1]      (t >= t_first; zero before)
 // and UnconstrainedEndPoseProblem::GetScalarJacobian (unconstrained_end_pose_problem.cpp:84-87) when T = 1.  One lane per
 // evaluation: ydiff (SO(3) log included) goes to shared memory [row][lane], then one pass over the Jacobian (coalesced in SoA).
+// Occupancy: the ydiff phase is a latency-bound serial stream like exo_cost_block_kernel's, so resident warps count -- 4 / 6 / 7 / 8
+// CTAs per SM (108 / 80 / 72 / 64 registers) take 115 / 95 / 95 / 85 us on 4096 x 100 timesteps (LWR, EffFrame + JointLimit).
 template <int NT>  // NT = 8: at most 8 controlled joints (register accumulators); NT = 0: any N
-__global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_constant__ CostGradParams P)
+__global__ void __launch_bounds__(128, NT > 0 ? 8 : 4) exo_cost_gradient_kernel(const __grid_constant__ CostGradParams P)
 {
     extern __shared__ double yd_s[];  // [length_jac][128]
     double* yd = yd_s + threadIdx.x;
@@ -162,8 +169,9 @@ __global__ void __launch_bounds__(128) exo_cost_gradient_kernel(const __grid_con
 // tasks with precision rho > 0 add  C += rho |ydiff|^2,  R += rho J^T J,  v = -ydiff + J qhat,  r += rho J^T v,  rhat += rho |v|^2.
 // One lane per evaluation; per row the precision and v sit in shared memory [row][lane]; J is re-read from L1 / L2 for the
 // N (N + 1) / 2 distinct entries of the symmetric R.
+// (NT = 8 holds N (N + 3) / 2 accumulators: 4 CTAs per SM at 128 registers 160 us, 3 at 162 registers 171 us, 5 / 6 with spills 235 / 267 us)
 template <int NT>  // NT = 8: at most 8 controlled joints, R and r accumulate in registers; NT = 0: any N
-__global__ void __launch_bounds__(128) exo_aico_messages_kernel(const __grid_constant__ AicoParams P)
+__global__ void __launch_bounds__(128, NT > 0 ? 4 : 1) exo_aico_messages_kernel(const __grid_constant__ AicoParams P)
 {
     extern __shared__ double sh[];  // [2][length_jac][128]
     const CostParams& C = P.c;

@@ -28,7 +28,7 @@ static __device__ __forceinline__ bool ik_step_one(const IkParams& K, const Cost
     const int LJ = LJT > 0 ? LJT : K.length_jac, N = K.n_ctrl;
     double yd[CAP], A[CAP * CAP], Ainv[CAP * CAP], z[CAP];
     {
-        double yd_any[IK_BIG_MAXLJ];  // eval_ydiff indexes by map: runtime subscripts
+        double yd_any[IK_MAXLJ];  // eval_ydiff indexes by map: runtime subscripts
         eval_ydiff(C, e, 0, yd_any, 1);
 #pragma unroll
         for (int r = 0; r < CAP; ++r) yd[r] = r < LJ ? yd_any[r] : 0.0;
