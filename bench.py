@@ -376,12 +376,13 @@ def measure_multi_gpu(exo, capi, exd, comm, rank, world, reps=50, B=4096):
             def step(with_collective):
                 if name == "cfg5":
                     capi.check(capi.lib().exo_problem_set_min_distance_output(backend, d_min_eval.ptr))
-                if nb > 0:
+                if nb > 0 and name == "cfg5":
                     prob.update_batch_device(d_x.ptr, nb * T, d_phi.ptr, d_jac.ptr, layout=exo.LAYOUT_SOA, stream=stream.ptr)
                 if name == "cfg3":
-                    # Phi and J of every (trajectory, timestep) stay in HBM for the caller; the costs are gathered
+                    # Phi and J of every (trajectory, timestep) stay in HBM for the caller; the costs are gathered.  Update + GetCost in
+                    # one call: the generated kernel forms every evaluation's cost while its Phi is in registers
                     if nb > 0:
-                        prob.cost_batch_device(d_x.ptr, d_phi.ptr, nb, mine, layout=exo.LAYOUT_SOA, stream=stream.ptr)
+                        prob.update_cost_batch_device(d_x.ptr, nb, d_phi.ptr, d_jac.ptr, mine, layout=exo.LAYOUT_SOA, stream=stream.ptr)
                     if with_collective:
                         c.allgather(mine, d_all.ptr, per_rank, stream)
                 elif with_collective:
@@ -409,7 +410,7 @@ def measure_multi_gpu(exo, capi, exd, comm, rank, world, reps=50, B=4096):
         gmin = float(keep[5].download((1,))[0])
         res = {"trajectories": B, "T": T, "evals": B * T, "scaling": "strong", "ms_per_step": ms_full, "evals_per_s": B * T / (ms_full * 1e-3),
                "ms_without_collective": ms_nocoll, "collective_us": 1e3 * (ms_full - ms_nocoll),
-               "step": ("update (Phi, J) + cost kernel + all-gather(%d costs), one CUDA graph" % B) if name == "cfg3" else
+               "step": ("update (Phi, J) with the cost epilogue + per-trajectory sum + all-gather(%d costs), one CUDA graph" % B) if name == "cfg3" else
                        ("update (park + pair kernel) + per-trajectory min + all-gather(%d distances) + global min, one CUDA graph" % B),
                "collective_path": "peer windows (one kernel over NVLink peer memory)" if comm.peer_collective_count() >= 0 and world > 1 else "NCCL"}
         comm.barrier(stream)

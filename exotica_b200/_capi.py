@@ -98,6 +98,7 @@ SYMBOLS = [
     ("exo_problem_cost_jacobian_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_aico_task_messages_batch", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
     ("exo_problem_cost_gradient_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp]),
+    ("exo_problem_update_cost_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
     ("exo_problem_cost_jacobian_batch_host", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp]),
     ("exo_problem_set_min_distance_output", ctypes.c_int, [_vp, _vp]),
     ("exo_problem_ik_solve_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(IkParams), _vp, _vp, _vp, _vp]),
@@ -588,6 +589,10 @@ class Problem(object):
     def cost_gradient_batch_device(self, d_x, n_traj, d_grad, d_cost_traj=None, layout=LAYOUT_SOA, stream=None):
         check(lib().exo_problem_cost_gradient_batch(self.h, d_x, int(n_traj), int(layout), d_cost_traj, d_grad, stream))
 
+    def update_cost_batch_device(self, d_x, n_traj, d_phi, d_jac, d_cost_traj, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
+        """update_batch_device + cost_batch_device in one call (one generated kernel + the per-trajectory sum where it applies)."""
+        check(lib().exo_problem_update_cost_batch(self.h, d_x, int(n_traj), int(layout), d_phi, d_jac, d_cost_traj, d_cost_eval, stream))
+
     def cost_jacobian_batch_host(self, X, with_cost=True):
         """X[B][T][N] (or [B][N] for end-pose problems) -> (cost[B] or None, grad like X) through the host pipeline; Phi and J
         stay on the device."""
@@ -634,11 +639,11 @@ class Problem(object):
     def set_kernel(self, choice):
         check(lib().exo_problem_set_kernel(self.h, int(choice)))
 
-    def generated_kernel_source(self, compile=False, cost=False):
-        """CUDA source of the per-robot generated tree kernel (cost=True: of the fused cost + gradient kernel, after set_cost);
-        compile=True also runs NVRTC (works without a GPU)."""
+    def generated_kernel_source(self, compile=False, cost=False, update_cost=False):
+        """CUDA source of the per-robot generated tree kernel (cost=True: of the fused cost + gradient kernel, update_cost=True: of the
+        update kernel with the cost epilogue -- both after set_cost); compile=True also runs NVRTC (works without a GPU)."""
         need = ctypes.c_int64(0)
-        kind = 2 if cost else 0
+        kind = 2 if cost else (4 if update_cost else 0)
         check(lib().exo_problem_generated_kernel_source(self.h, None, 0, ctypes.byref(need), kind))
         buf = ctypes.create_string_buffer(need.value)
         check(lib().exo_problem_generated_kernel_source(self.h, buf, need.value, None, kind | (1 if compile else 0)))

@@ -57,6 +57,7 @@ HOST_SYMBOLS = [
     ("exo_host_problem_cost_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     ("exo_host_problem_cost_jacobian_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
     ("exo_host_problem_cost_batch_device", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
+    ("exo_host_problem_update_cost_batch_device", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     ("exo_host_problem_ik_solve_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(_capi.IkParams), _vp, _vp, _vp, _vp]),
     ("exo_host_problem_hessian_batch", ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     ("exo_host_problem_last_kernel_ms", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),

@@ -119,6 +119,18 @@ struct exo_problem
     std::string tcg_why;
     TreeCostSpec tcg_spec;
     TreeCostPlan tcg_plan;
+    // generated update + cost kernel (tree_codegen with a cost epilogue) behind exo_problem_update_cost_batch
+    int uc_version = -2;
+    int64_t uc_cost_epoch = -1;
+    bool uc_ok = false, uc_jit_failed = false;
+    void* uc_kernel = nullptr;
+    std::string uc_why;
+    TreeCostSpec uc_spec;
+    TreeGenPlan uc_plan;
+    TreeGenParams uc_params;
+    TmaKey uc_key;
+    double* d_uc_cost = nullptr;  // per-evaluation costs when the caller does not ask for them
+    int64_t uc_cost_bytes = 0;
     bool plan_valid = false;      // interpreter launch plan (depends on the program and on split_spheres only)
     bool plan_split = false;
     bool fused_spheres = false;   // exo_problem_set_kernel(6): SphereCollision inside the interpreter (no second launch)
@@ -386,6 +398,7 @@ int exo_problem_destroy(exo_problem* p)
     for (auto& sd : p->sph_dumps)
         if (sd.d) cudaFree(sd.d);
     if (p->d_cg) cudaFree(p->d_cg);
+    if (p->d_uc_cost) cudaFree(p->d_uc_cost);
     if (p->shadow) exo_problem_destroy(p->shadow);
     if (p->d_shadow_phi) cudaFree(p->d_shadow_phi);
     if (p->d_shadow_jac) cudaFree(p->d_shadow_jac);
@@ -935,20 +948,27 @@ int exo_problem_set_kernel(exo_problem* p, int choice)
 }
 
 static bool tree_costgrad_prepare(exo_problem* p);
+static bool update_cost_prepare(exo_problem* p);
 
 int exo_problem_generated_kernel_source(exo_problem* p, char* out, int64_t capacity, int64_t* needed, int32_t compile)
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
     if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
     const bool cost_kernel = (compile & 2) != 0;  // bit 1: the fused cost + gradient kernel (needs exo_problem_set_cost) instead of the update kernel
+    const bool uc_kernel = !cost_kernel && (compile & 4) != 0;  // bit 2: the update kernel with the cost epilogue (exo_problem_update_cost_batch)
     if (cost_kernel)
     {
         if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
         if (!tree_costgrad_prepare(p)) return fail(EXO_ERR_UNSUPPORTED, "generated cost kernel not applicable: " + p->tcg_why);
     }
+    else if (uc_kernel)
+    {
+        if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+        if (!update_cost_prepare(p)) return fail(EXO_ERR_UNSUPPORTED, "generated update + cost kernel not applicable: " + p->uc_why);
+    }
     else if (!tree_prepare(p))
         return fail(EXO_ERR_UNSUPPORTED, "generated tree kernel not applicable: " + p->tree_why);
-    const std::string& src = cost_kernel ? p->tcg_plan.source : p->tree_plan.source;
+    const std::string& src = cost_kernel ? p->tcg_plan.source : (uc_kernel ? p->uc_plan.source : p->tree_plan.source);
     if (needed) *needed = (int64_t)src.size() + 1;
     if (out && capacity > 0)
     {
@@ -960,7 +980,7 @@ int exo_problem_generated_kernel_source(exo_problem* p, char* out, int64_t capac
     {
         std::vector<char> cubin;
         std::string err;
-        const bool ok = cost_kernel ? tree_costgrad_jit_compile(p->tcg_plan, cubin, err) : tree_jit_compile(p->tree_plan, cubin, err);
+        const bool ok = cost_kernel ? tree_costgrad_jit_compile(p->tcg_plan, cubin, err) : tree_jit_compile(uc_kernel ? p->uc_plan : p->tree_plan, cubin, err);
         if (!ok) return fail(EXO_ERR_UNSUPPORTED, "run-time compilation failed: " + err);
     }
     return EXO_OK;
@@ -1454,6 +1474,125 @@ int exo_problem_cost_gradient_batch(exo_problem* p, const double* d_x, int64_t n
 {
     if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
     return cost_gradient_impl(p, d_x, n_traj, layout, d_cost_traj, d_grad, stream, &p->d_cg, &p->cg_bytes);
+}
+
+// Source of the generated update + cost kernel for the current model state and cost structure
+static bool update_cost_prepare(exo_problem* p)
+{
+    if (p->uc_version == p->tree->version && p->uc_cost_epoch == p->cost_epoch) return p->uc_ok;
+    p->uc_cost_epoch = p->cost_epoch;
+    std::string err;
+    Program tp;
+    std::vector<MapSpec> maps = p->maps;
+    if (!compile_program(p->tree->model, maps, tp, err, COMPILE_TWO_PASS))
+    {
+        p->uc_why = err;
+        p->uc_version = p->tree->version;
+        return p->uc_ok = false;
+    }
+    TreeCostSpec spec;
+    if (!tree_costgrad_spec(p, tp, spec))
+    {
+        p->uc_why = "the cost is not made of EffFrame / EffPosition / JointLimit maps";
+        p->uc_version = p->tree->version;
+        return p->uc_ok = false;
+    }
+    const bool same = p->uc_version == p->tree->version && spec.frame_map == p->uc_spec.frame_map && spec.frame_rot == p->uc_spec.frame_rot &&
+                      spec.jl_map == p->uc_spec.jl_map;
+    if (same) return p->uc_ok;
+    p->uc_version = p->tree->version;
+    p->uc_spec = spec;
+    p->uc_kernel = nullptr;
+    p->uc_jit_failed = false;
+    p->uc_key = exo_problem::TmaKey();
+    p->uc_ok = tree_codegen(tp, p->uc_plan, p->uc_why, &p->uc_spec);
+    return p->uc_ok;
+}
+
+int exo_problem_update_cost_batch(exo_problem* p, const double* d_x, int64_t n_traj, int32_t layout, double* d_phi, double* d_jac, double* d_cost_traj,
+                                  double* d_cost_eval, void* stream)
+{
+    if (!p) return fail(EXO_ERR_INVALID, "NULL argument");
+    if (!p->finalized) return fail(EXO_ERR_STATE, "problem not finalized");
+    if (!p->cost_set) return fail(EXO_ERR_STATE, "exo_problem_set_cost has not been called");
+    if (n_traj < 0) return fail(EXO_ERR_INVALID, "negative batch size");
+    if (n_traj == 0) return EXO_OK;
+    if (!d_x || !d_phi || (!d_cost_traj && !d_cost_eval)) return fail(EXO_ERR_INVALID, "NULL buffer");
+    if (p->compiled_version != p->tree->version)
+    {
+        int rc = compile_and_upload(p);
+        if (rc != EXO_OK) return rc;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t T = p->cost.T, E = n_traj * T;
+    if (p->prog.hdr.n_generated > 0 && T != p->T) return fail(EXO_ERR_INVALID, "T of the cost does not match exo_problem_set_generated");
+    // one generated kernel (forward kinematics, Jacobians and the cost of every evaluation while its Phi is in registers) + the
+    // per-trajectory sum, for SoA buffers and costs made of EffFrame / EffPosition / JointLimit maps; run-time compiled, so small
+    // batches and everything else take the two calls below
+    const bool want = p->kernel_choice == 0 || p->kernel_choice == 9;
+    if (want && layout == EXO_LAYOUT_SOA && !p->uc_jit_failed && (E >= tree_min_evals() || p->kernel_choice == 9) && update_cost_prepare(p))
+    {
+        KernelParams k;
+        memset(&k, 0, sizeof(k));
+        k.x = d_x; k.phi = d_phi; k.jac = d_jac; k.n_evals = E;
+        int rc = fill_strides(p, layout, E, k);
+        if (rc != EXO_OK) return rc;
+        exo_problem::TmaKey& key = p->uc_key;
+        if (key.phi != k.phi || key.jac != k.jac || key.n != E || key.phi_sk != k.phi_sk || key.j_sc != k.j_sc || key.j_sr != k.j_sr || key.version != p->uc_version ||
+            p->uc_params.x != k.x || p->uc_params.x_sk != k.x_sk)
+        {
+            key.phi = k.phi; key.jac = k.jac; key.n = E; key.phi_sk = k.phi_sk; key.j_sc = k.j_sc; key.j_sr = k.j_sr; key.version = p->uc_version;
+            key.ok = tree_jit_bind(p->uc_plan, p->uc_params, k.x, k.phi, k.jac, E, k.x_se, k.x_sk, k.phi_se, k.phi_sk, k.j_se, k.j_sr, k.j_sc);
+        }
+        if (key.ok && !p->uc_kernel)
+        {
+            std::string jerr;
+            p->uc_kernel = tree_jit_get(p->uc_plan, jerr);
+            if (!p->uc_kernel)
+            {
+                p->uc_jit_failed = true;
+                p->uc_why = "run-time compilation failed: " + jerr;
+            }
+        }
+        if (key.ok && p->uc_kernel)
+        {
+            double* ce = d_cost_eval;
+            if (!ce)
+            {
+                const int64_t need = E * (int64_t)sizeof(double);
+                if (p->uc_cost_bytes < need)
+                {
+                    CUDA_TRY(cudaStreamSynchronize(s));
+                    if (p->d_uc_cost) CUDA_TRY(cudaFree(p->d_uc_cost));
+                    p->d_uc_cost = nullptr;
+                    p->uc_cost_bytes = 0;
+                    CUDA_TRY(cudaMalloc((void**)&p->d_uc_cost, (size_t)need));
+                    p->uc_cost_bytes = need;
+                }
+                ce = p->d_uc_cost;
+            }
+            const CostParams& c = p->cost;
+            TreeGenParams& tp = p->uc_params;
+            tp.cost_eval = ce;
+            tp.rho = c.rho; tp.goal = c.goal; tp.goal_rot = c.goal_rot; tp.W = c.W;
+            tp.ct = c.ct;
+            tp.T = c.T; tp.t_first = c.t_first; tp.T_goal = c.T_goal; tp.n_maps = c.n_maps; tp.length_phi = c.length_phi; tp.n_rot = c.n_rot;
+            cudaError_t e = tree_jit_launch(p->uc_kernel, p->uc_plan, tp, s);
+            if (e != cudaSuccess) return cuda_fail(e, "generated update + cost kernel launch");
+            p->launches++;
+            if (d_cost_traj)
+            {
+                e = launch_reduce(ce, n_traj, (int)T, 0, 1, d_cost_traj, s);
+                if (e != cudaSuccess) return cuda_fail(e, "reduce kernel launch");
+                p->launches++;
+            }
+            p->last_kernel = "exo_tree_update_cost_kernel";
+            return EXO_OK;
+        }
+    }
+    int rc = launch(p, d_x, E, E, (int32_t)T, layout, d_phi, d_jac, s, false);
+    if (rc != EXO_OK) return rc;
+    return exo_problem_cost_batch(p, d_x, d_phi, n_traj, layout, d_cost_traj, d_cost_eval, stream);
 }
 
 int exo_problem_aico_task_messages_batch(exo_problem* p, const double* d_qhat, const double* d_phi, const double* d_jac, int64_t n_traj, int32_t layout,

@@ -708,6 +708,9 @@ public:
     void CostJacobianBatch(const double* x, int64_t n_trajectories, double* cost, double* jacobian);
     // device variant on the buffers of UpdateBatchDevice; cost_eval (per timestep) may be NULL
     void CostBatchDevice(const double* d_x, const double* d_phi, int64_t n_trajectories, int layout, double* d_cost, double* d_cost_eval, void* stream);
+    // UpdateBatchDevice + CostBatchDevice in one call: Update(x, t) of every timestep and GetCost() of every trajectory
+    void UpdateCostBatchDevice(const double* d_x, int64_t n_trajectories, int layout, double* d_phi, double* d_jacobian, double* d_cost, double* d_cost_eval,
+                               void* stream);
     // NEW: multi-start IK (IKSolver::Solve, exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) from n start states
     // q0[n][N]; solutions[n][N], cost[n], iterations[n], termination[n] (exotica::TerminationCriterion values)
     void IkSolveBatch(const double* q0, int64_t n, const exo_ik_params& params, double* solutions, double* cost, int32_t* iterations,

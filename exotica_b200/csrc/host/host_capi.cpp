@@ -526,6 +526,12 @@ int exo_host_problem_cost_batch_device(exo_host_problem* p, const double* d_x, c
     HOST_TRY(p->problem->CostBatchDevice(d_x, d_phi, n_traj, layout, d_cost, d_cost_eval, stream))
 }
 
+int exo_host_problem_update_cost_batch_device(exo_host_problem* p, const double* d_x, int64_t n_traj, int layout, double* d_phi, double* d_jac, double* d_cost,
+                                              double* d_cost_eval, void* stream)
+{
+    HOST_TRY(p->problem->UpdateCostBatchDevice(d_x, n_traj, layout, d_phi, d_jac, d_cost, d_cost_eval, stream))
+}
+
 int exo_host_problem_ik_solve_batch(exo_host_problem* p, const double* q0, int64_t n, const exo_ik_params* params, double* solutions, double* cost,
                                     int32_t* iterations, int32_t* termination)
 {

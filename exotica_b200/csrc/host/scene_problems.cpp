@@ -1041,6 +1041,15 @@ void PlanningProblem::CostBatchDevice(const double* d_x, const double* d_phi, in
     CheckRc(exo_problem_cost_batch(GetBackend(), d_x, d_phi, n_trajectories, layout, d_cost, d_cost_eval, stream));
 }
 
+void PlanningProblem::UpdateCostBatchDevice(const double* d_x, int64_t n_trajectories, int layout, double* d_phi, double* d_jacobian, double* d_cost,
+                                            double* d_cost_eval, void* stream)
+{
+    PushCost();
+    PrepareBackend();
+    CheckRc(exo_problem_update_cost_batch(GetBackend(), d_x, n_trajectories, layout, d_phi, (flags_ & KIN_J) ? d_jacobian : nullptr, d_cost, d_cost_eval, stream));
+    number_of_problem_updates_ += (unsigned int)(n_trajectories * GetT());
+}
+
 exo_problem* PlanningProblem::GetBackend()
 {
     KinematicTree& kt = scene_->GetKinematicTree();

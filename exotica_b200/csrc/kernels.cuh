@@ -177,6 +177,7 @@ struct TreeGenPlan
     size_t smem_bytes = 0;
     int n_ctrl = 0, length_phi = 0, length_jac = 0;
     bool needs_flat_jacobian = false;  // some boxes address J as [LJ * N][E]: the row pitch must be N column pitches
+    const char* kernel_name = "exo_tree_kernel";  // "exo_tree_update_cost_kernel" when generated with a cost epilogue
 };
 struct TreeGenParams  // mirrored by the generated source
 {
@@ -185,9 +186,18 @@ struct TreeGenParams  // mirrored by the generated source
     double* jac;
     long long n_evals, x_sk, phi_sk, j_sr, j_sc;
     TmaDesc maps[TREE_MAXMAPS];
+    // cost epilogue (exo_tree_update_cost_kernel only): the task + transition cost of every evaluation, formed from the Phi entries
+    // while they are in registers
+    double* cost_eval;  // [n_evals]
+    const double *rho, *goal, *goal_rot, *W;
+    double ct;
+    int T, t_first, T_goal, n_maps, length_phi, n_rot;
 };
-// Generates the source; false + why when the program is outside the generated kernel's scope (the interpreter runs it).
-bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why);
+struct TreeCostSpec;
+// Generates the source; false + why when the program is outside the generated kernel's scope (the interpreter runs it).  With a
+// cost structure the kernel also writes every evaluation's scalar cost (PlanningProblem::Update + GetScalarTaskCost /
+// GetScalarTransitionCost in one pass over the state).
+bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why, const TreeCostSpec* cost = nullptr);
 // NVRTC only (no device needed): source -> sm_100a cubin
 bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::string& err);
 // NVRTC + module cache (keyed by source text and device): an opaque kernel handle, nullptr + err on failure

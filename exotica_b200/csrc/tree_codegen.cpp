@@ -264,7 +264,7 @@ int env_int(const char* name, int dflt, int lo, int hi)
 }
 }  // namespace
 
-bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
+bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why, const TreeCostSpec* cost)
 {
     const ProgramHeader& H = prog.hdr;
     if (!H.two_pass)
@@ -282,7 +282,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     // ---- eligibility + the items every op stages ------------------------------------------------------------------------------
     std::vector<Item> items;
     std::vector<std::vector<int>> op_items(n_ops);
-    int n_pos = 0, max_op_values = 0;
+    int n_pos = 0, max_op_values = 0, jl_ops = 0;
     for (int i = 0; i < n_ops; ++i)
     {
         const Op& op = prog.ops[i];
@@ -328,6 +328,12 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 why = "a task map is outside the generated kernel's scope";
                 return false;
             }
+            if (cost && ((op.map_kind != EXO_MAP_EFF_FRAME && op.map_kind != EXO_MAP_EFF_POSITION) || (row_mode != ROWS_VW && row_mode != ROWS_V) ||
+                         op.n_items >= (int)cost->frame_map.size() || cost->frame_map[op.n_items] < 0))
+            {
+                why = "a requested frame is outside the cost epilogue's scope";
+                return false;
+            }
             Item it;
             it.op = i; it.phi = true; it.nrows = rows; it.key = op.phi_off; it.col = 0; it.ps = op.n_items; it.flags = 0; it.cst_b = 0;
             op_items[i].push_back((int)items.size());
@@ -340,6 +346,13 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
             why = "an op is outside the generated kernel's scope";
             return false;
         }
+        else if (cost && op.kind == OP_EMIT_JLIMIT)
+            jl_ops++;
+    }
+    if (cost && cost->jl_map >= 0 && jl_ops != 1)
+    {
+        why = "the cost names a JointLimit map the program does not evaluate exactly once";
+        return false;
     }
     if (n_pos > 16)
     {
@@ -548,7 +561,9 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
            n_slots, CAP, ZROWS, (int)plan.maps.size());
     emit_prelude(o);
     o.line("struct alignas(64) TmaDesc { unsigned long long v[16]; };");
-    o.line("struct TreeGenParams { const double* x; double* phi; double* jac; long long n_evals, x_sk, phi_sk, j_sr, j_sc; TmaDesc maps[%d]; };", TREE_MAXMAPS);
+    o.line("struct TreeGenParams { const double* x; double* phi; double* jac; long long n_evals, x_sk, phi_sk, j_sr, j_sc; TmaDesc maps[%d];", TREE_MAXMAPS);
+    o.line("    double* cost_eval; const double* rho; const double* goal; const double* goal_rot; const double* W; double ct; int T, t_first, T_goal, n_maps, length_phi, n_rot; };");
+    plan.kernel_name = cost ? "exo_tree_update_cost_kernel" : "exo_tree_kernel";
     o.line("static __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }");
     o.line("static __device__ __forceinline__ void tma2(const TmaDesc* m, const void* s, int c0, int c1, unsigned long long pol)");
     o.line("{ asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%%0, {%%2, %%3}], [%%1], %%4;\" :: \"l\"(m), \"r\"(smem_u32(s)), \"r\"(c0), \"r\"(c1), \"l\"(pol) : \"memory\"); }");
@@ -559,9 +574,9 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     o.line("static __device__ __forceinline__ void fence_staged() { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); }");
     const int min_blocks = env_int("EXO_TREE_MINB", 0, 0, 8);
     if (min_blocks)
-        o.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32, min_blocks);
+        o.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) %s(const __grid_constant__ TreeGenParams P)", WPC * 32, min_blocks, plan.kernel_name);
     else
-        o.line("extern \"C\" __global__ void __launch_bounds__(%d) exo_tree_kernel(const __grid_constant__ TreeGenParams P)", WPC * 32);
+        o.line("extern \"C\" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ TreeGenParams P)", WPC * 32, plan.kernel_name);
     o.line("{");
     o.line("    extern __shared__ __align__(128) double smem[];");
     o.line("    const int lane = threadIdx.x & %d, warp = threadIdx.x / %d;  // position in the tile, tile of the CTA", TILE - 1, TILE);
@@ -585,6 +600,18 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
     o.line("    unsigned long long pol = 0;");
     o.line("    if (lane == 0) asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %%0, 1.0;\" : \"=l\"(pol));");
     o.line("    Fr cur;");
+    if (cost)
+    {
+        // cost epilogue: ct (ydiff^T S ydiff + xdiff^T W xdiff) of this evaluation, as exo_cost_kernel forms it from Phi in HBM
+        // (TimeIndexedTask::Update, TaskSpaceVector::operator-, GetScalarTaskCost / GetScalarTransitionCost)
+        o.line("    const int t = (int)(e %% P.T);");
+        o.line("    const double* const rho = P.rho + (long long)t * P.n_maps;");
+        o.line("    const int tg = P.T_goal > 1 ? t : 0;");
+        o.line("    const double* const goal = P.goal + (long long)tg * P.length_phi;");
+        o.line("    const double* const grot = P.goal_rot + (long long)tg * P.n_rot * 9;");
+        o.line("    double c = 0.0;");
+        if (cost->jl_map >= 0) o.line("    const double rho_jl = rho[%d];", cost->jl_map);
+    }
     for (int k = 0; k < n_pos; ++k) o.line("    double pa%d_x = 0.0, pa%d_y = 0.0, pa%d_z = 0.0;", k, k, k);
     for (int i = 0; i < n_ops; ++i)
         if (joint_recorded[i]) o.line("    double jw%d_x, jw%d_y, jw%d_z, jp%d_x, jp%d_y, jp%d_z;  // axis and origin of the joint of op %d", i, i, i, i, i, i, i);
@@ -727,6 +754,28 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                 const Box& bx = bt.boxes[it.box];
                 const int ibuf = (flip + it.batch) & 1;
                 o.line("    write_phi(%d, %d, A, %s + %d, %d);", op.map_kind, op.rot_type, ibuf ? "stg1" : "stg0", bx.off * TILE, TILE);
+                if (cost)
+                {
+                    const int ps = op.n_items;
+                    o.line("    {");
+                    o.line("        const double y0 = A.x - goal[%d], y1 = A.y - goal[%d], y2 = A.z - goal[%d];", op.phi_off, op.phi_off + 1, op.phi_off + 2);
+                    o.line("        double s = y0 * y0 + y1 * y1 + y2 * y2;");
+                    if (cost->frame_rot[ps] >= 0)
+                    {
+                        // rotvec = M1 * (M2^-1 M1).GetRot()  (TaskSpaceVector::operator-, task_space_vector.cpp:64-91)
+                        o.line("        const double* M2 = grot + %d;", 9 * cost->frame_rot[ps]);
+                        o.line("        Fr M;");
+                        for (int r = 0; r < 3; ++r)
+                            for (int k = 0; k < 3; ++k) o.line("        M.m%d = M2[%d] * A.m%d + M2[%d] * A.m%d + M2[%d] * A.m%d;", 3 * r + k, r, k, 3 + r, 3 + k, 6 + r, 6 + k);
+                        o.line("        M.x = M.y = M.z = 0.0;");
+                        o.line("        double vx, vy, vz;");
+                        o.line("        get_angle_axis(M, vx, vy, vz);");
+                        o.line("        const double y3 = A.m0 * vx + A.m1 * vy + A.m2 * vz, y4 = A.m3 * vx + A.m4 * vy + A.m5 * vz, y5 = A.m6 * vx + A.m7 * vy + A.m8 * vz;");
+                        o.line("        s += y3 * y3 + y4 * y4 + y5 * y5;");
+                    }
+                    o.line("        c += rho[%d] * s;", cost->frame_map[ps]);
+                    o.line("    }");
+                }
                 o.line("    }");
                 if (bt.last_item == itx) emit_flush(bt, ibuf);
                 if (op_items[i].size() > 1)
@@ -768,6 +817,7 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
                     o.line("            double v = 0.0;");
                     o.line("            if (q < %s) v = q - %s - %s;", lit(lo_t).c_str(), lit(lo).c_str(), lit(tau).c_str());
                     o.line("            if (q > %s) v = q - %s + %s;", lit(hi_t).c_str(), lit(hi).c_str(), lit(tau).c_str());
+                    if (cost && cost->jl_map >= 0) o.line("            { const double yd = v - goal[%d]; c += rho_jl * yd * yd; }", op.phi_off + k);
                     o.line("            __stcs(P.phi + %d * P.phi_sk + e, v);", op.phi_off + k);
                     o.line("            if (P.jac) __stcs(P.jac + %d * P.j_sr + %d * P.j_sc + e, (q >= %s && q <= %s) ? 0.0 : 1.0);", op.jrow_off + k, k, lit(lo_t).c_str(),
                            lit(hi_t).c_str());
@@ -802,6 +852,18 @@ bool tree_codegen(const Program& prog, TreeGenPlan& plan, std::string& why)
         }
         flip = (int)((flip + batches[pass].size()) & 1);
         if (pass == 1) o.line("    }");
+    }
+    if (cost)
+    {
+        o.line("    // transition cost and the evaluation's total (the first timesteps, t < t_first, carry no cost: GetCost sums t = 1 .. T - 1)");
+        o.line("    if (valid)");
+        o.line("    {");
+        o.line("        if (P.W && t > 0)");
+        o.line("        {");
+        for (int n = 0; n < N; ++n) o.line("            { const double d = xq[%d * P.x_sk] - xq[%d * P.x_sk - 1]; c += P.W[%d] * d * d; }", n, n, n);
+        o.line("        }");
+        o.line("        P.cost_eval[e] = t < P.t_first ? 0.0 : P.ct * c;");
+        o.line("    }");
     }
     if (jb_seen == 0 && !zboxes.empty())
     {

@@ -265,7 +265,7 @@ bool tree_jit_compile(const TreeGenPlan& plan, std::vector<char>& cubin, std::st
 
 void* tree_jit_get(const TreeGenPlan& plan, std::string& err)
 {
-    return get_kernel(plan.source, "exo_tree_kernel", err);
+    return get_kernel(plan.source, plan.kernel_name, err);
 }
 
 bool tree_costgrad_jit_compile(const TreeCostPlan& plan, std::vector<char>& cubin, std::string& err)

@@ -475,6 +475,13 @@ class PlanningProblem(object):
         """Same on the device buffers of update_batch_device (asynchronous on `stream`)."""
         _check(_host.lib().exo_host_problem_cost_batch_device(self._h, d_x, d_phi, int(n_trajectories), int(layout), d_cost, d_cost_eval, stream))
 
+    def update_cost_batch_device(self, d_x, n_trajectories, d_phi, d_jacobian, d_cost, d_cost_eval=None, layout=LAYOUT_SOA, stream=None):
+        """update_batch_device and cost_batch_device in one call: Update(x, t) of every timestep and get_cost() of every trajectory.
+        SoA buffers of problems whose cost is made of EffFrame / EffPosition / JointLimit maps run one generated kernel (the cost of
+        an evaluation is formed while its Phi is still in registers) plus the per-trajectory sum."""
+        _check(_host.lib().exo_host_problem_update_cost_batch_device(self._h, d_x, int(n_trajectories), int(layout), d_phi, d_jacobian, d_cost, d_cost_eval,
+                                                                     stream))
+
     def last_kernel_ms(self):
         ms = ctypes.c_float(0)
         _check(_host.lib().exo_host_problem_last_kernel_ms(self._h, ctypes.byref(ms)))

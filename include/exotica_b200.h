@@ -317,6 +317,16 @@ int exo_problem_aico_task_messages_batch(exo_problem* problem, const double* d_q
  * must be serialised. */
 int exo_problem_cost_gradient_batch(exo_problem* problem, const double* d_x, int64_t n_traj, int32_t layout, double* d_cost_traj,
                                     double* d_grad, void* stream);
+/* exo_problem_update_batch and exo_problem_cost_batch in one call -- what a time-indexed solver does per roll-out: Update(x, t)
+ * for every timestep (tasks.cpp:306-314 fills Phi, J and ydiff), then GetCost() (abstract_time_indexed_problem.cpp:299-307).
+ * d_phi / d_jac (d_jac may be NULL) receive exactly what exo_problem_update_batch writes for the n_traj * T evaluations,
+ * d_cost_traj[n_traj] and / or d_cost_eval[n_traj * T] what exo_problem_cost_batch writes.  EXO_LAYOUT_SOA buffers of problems
+ * whose cost is made of EffFrame / EffPosition / JointLimit maps run ONE generated kernel (exo_tree_update_cost_kernel, compiled at
+ * run time like exo_tree_kernel: every evaluation's cost is formed while its Phi entries are still in registers, so Phi is not
+ * read back from HBM and the cost kernel's launch disappears) plus the per-trajectory sum; everything else is the two calls
+ * back to back.  Asynchronous on `stream`; calls on one problem must be serialised. */
+int exo_problem_update_cost_batch(exo_problem* problem, const double* d_x, int64_t n_traj, int32_t layout, double* d_phi, double* d_jac,
+                                  double* d_cost_traj, double* d_cost_eval, void* stream);
 /* Host buffers, states X[B][T][N] evaluation-major: H2D of the states -> forward kinematics + Jacobians (they stay on the
  * device) -> cost and cost-gradient kernels -> D2H of h_grad[B][T][N] and, if h_cost_traj is not NULL, one cost per
  * trajectory.  What a gradient-based solver on the host needs per iteration, at N + 1/T doubles per evaluation over PCIe. */

@@ -101,6 +101,11 @@ int exo_host_problem_cost_batch(exo_host_problem* problem, const double* x, int6
 int exo_host_problem_cost_jacobian_batch(exo_host_problem* problem, const double* x, int64_t n_traj, double* cost, double* jacobian);
 int exo_host_problem_cost_batch_device(exo_host_problem* problem, const double* d_x, const double* d_phi, int64_t n_traj, int layout,
                                        double* d_cost, double* d_cost_eval, void* stream);
+/* NEW Update(x, t) of every timestep + GetCost() of every trajectory on device buffers (exo_problem_update_cost_batch): d_phi /
+ * d_jac as exo_host_problem_update_batch_device fills them, d_cost[n_traj] / d_cost_eval[n_traj * T] (either may be NULL) as
+ * exo_host_problem_cost_batch_device does. */
+int exo_host_problem_update_cost_batch_device(exo_host_problem* problem, const double* d_x, int64_t n_traj, int layout, double* d_phi, double* d_jac,
+                                              double* d_cost, double* d_cost_eval, void* stream);
 /* NEW multi-start IK: IKSolver::Solve (exotations/solvers/exotica_ik_solver/src/ik_solver.cpp:73-240) from n start states
  * q0[n][N] -> solutions[n][N], cost[n], iterations[n], termination[n] (exotica::TerminationCriterion values). */
 int exo_host_problem_ik_solve_batch(exo_host_problem* problem, const double* q0, int64_t n, const exo_ik_params* params, double* solutions,

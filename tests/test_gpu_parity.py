@@ -578,7 +578,47 @@ def _gpu_costs(prob, X, B, T, rho, goal=None, ct=1.0, W=None, layout=_capi.LAYOU
     prob.set_cost(rho, T=T, goal=goal, ct=ct, W=W)
     prob.cost_batch_device(dx.ptr, dphi.ptr, B, dct.ptr, dce.ptr, layout=layout)
     _capi.check(_capi.lib().exo_device_synchronize())
+    _check_update_cost(prob, dx, B, T, layout, dphi, djac, dct, dce)
     return dct.download((B,)), dce.download((E,))
+
+
+def _check_update_cost(prob, dx, B, T, layout, dphi, djac, dct, dce):
+    """exo_problem_update_cost_batch (Update + GetCost in one call) against the two separate calls whose results sit in dphi / djac /
+    dct / dce: through the generated kernel with the cost epilogue where the problem and the layout qualify, through the two-call
+    path otherwise."""
+    E = B * T
+    LP, LJ, N = prob.length_phi, prob.length_jacobian, prob.n
+    fused = False
+    if layout == _capi.LAYOUT_SOA and E % 2 == 0:
+        try:
+            fused = "exo_tree_update_cost_kernel" in prob.generated_kernel_source(update_cost=True)
+        except _capi.ExoticaError:
+            fused = False
+    dphi2, djac2, dct2, dce2 = (_capi.DeviceBuffer(n) for n in (E * LP, E * LJ * N, B, E))
+    for b in (dphi2, djac2, dct2, dce2):
+        b.fill_bytes(0xFF)
+    if fused:
+        prob.set_kernel(9)  # small batches: ask for the generated kernel (choice 0 keeps them on the two-call path)
+    try:
+        prob.update_cost_batch_device(dx.ptr, B, dphi2.ptr, djac2.ptr, dct2.ptr, dce2.ptr, layout=layout)
+        _capi.check(_capi.lib().exo_device_synchronize())
+        assert prob.last_kernel() == ("exo_tree_update_cost_kernel" if fused else "exo_cost_kernel")
+        # without the per-evaluation costs: the library's own scratch
+        dct3 = _capi.DeviceBuffer(B)
+        dct3.fill_bytes(0xFF)
+        prob.update_cost_batch_device(dx.ptr, B, dphi2.ptr, djac2.ptr, dct3.ptr, None, layout=layout)
+        _capi.check(_capi.lib().exo_device_synchronize())
+    finally:
+        if fused:
+            prob.set_kernel(0)
+    phi_a, phi_b = dphi.download((E * LP,)), dphi2.download((E * LP,))
+    jac_a, jac_b = djac.download((E * LJ * N,)), djac2.download((E * LJ * N,))
+    assert record("update_cost_phi", np.max(np.abs(phi_a - phi_b))) <= 1e-12 and record("update_cost_jac", np.max(np.abs(jac_a - jac_b))) <= 1e-12
+    ce_a, ce_b = dce.download((E,)), dce2.download((E,))
+    ct_a, ct_b = dct.download((B,)), dct2.download((B,))
+    assert record("update_cost_eval_rel", np.max(np.abs(ce_a - ce_b)) / max(1.0, np.max(np.abs(ce_a)))) <= 1e-12
+    assert record("update_cost_traj_rel", np.max(np.abs(ct_a - ct_b)) / max(1.0, np.max(np.abs(ct_a)))) <= 1e-12
+    assert np.array_equal(dct3.download((B,)), ct_b)
 
 
 @pytest.mark.parametrize("rot", ["RPY", "Quaternion", "ZYZ", "AngleAxis", "Matrix", "ZYX"])
@@ -852,6 +892,12 @@ def test_cost_gradient_and_aico_messages_on_a_tree_robot(oracle_lib):
     prob.update_batch_device(dx.ptr, E, dphi.ptr, djac.ptr, T=T)
     prob.aico_task_messages_device(dx.ptr, dphi.ptr, djac.ptr, B, dR.ptr, dr.ptr, drh.ptr, dc.ptr)
     _capi.check(_capi.lib().exo_device_synchronize())
+    # Update + GetCost in one call on the tree robot (two-pass generated kernel with the cost epilogue) against the separate calls
+    dct, dce = _capi.DeviceBuffer(B), _capi.DeviceBuffer(E)
+    prob.cost_batch_device(dx.ptr, dphi.ptr, B, dct.ptr, dce.ptr)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    assert np.max(np.abs(dct.download((B,)) - cost)) <= 1e-12 * max(1.0, np.abs(cost).max())
+    _check_update_cost(prob, dx, B, T, _capi.LAYOUT_SOA, dphi, djac, dct, dce)
     R = dR.download((N, N, E)).transpose(2, 0, 1).reshape(B, T, N, N)
     r = dr.download((N, E)).T.reshape(B, T, N)
     rhat = drh.download((E,)).reshape(B, T)
@@ -1040,6 +1086,22 @@ def test_full_size_cfg3_time_indexed(oracle_lib):
     sel = np.random.default_rng(3).integers(0, B * T, 4096)
     phi_ref, jac_ref = orc.problem_update_batch(X[sel])
     assert max_abs_err(phi[sel], phi_ref, angle_entries(maps, orc)) <= TOL and max_abs_err(jac[sel], jac_ref) <= TOL
+    # Update + GetCost of all 4096 trajectories in one call (automatic choice at this size: the generated kernel with the cost
+    # epilogue) -- Phi / J against the run above, costs against the oracle
+    E, N, LP, LJ = B * T, 7, prob.length_phi, prob.length_jacobian
+    dx, dphi, djac, dct = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, B))
+    dx.upload(X.T)
+    goal = orc.zero_goal()
+    goal[:6] = [0.4, 0.1, 0.6, 0.2, -0.1, 0.3]
+    prob.set_cost(np.ones((T, 2)) * [10.0, 1.0], T=T, goal=goal, ct=1.0 / 0.05 / T, W=np.ones(7))
+    prob.update_cost_batch_device(dx.ptr, B, dphi.ptr, djac.ptr, dct.ptr)
+    _capi.check(_capi.lib().exo_device_synchronize())
+    assert prob.last_kernel() == "exo_tree_update_cost_kernel"
+    assert np.max(np.abs(dphi.download((LP, E)).T - phi)) <= 1e-12 and np.max(np.abs(djac.download((LJ, N, E)).transpose(2, 0, 1) - jac)) <= 1e-12
+    cost = dct.download((B,))
+    for b in range(0, B, 128):
+        ref = orc.trajectory_cost(X[b * T:(b + 1) * T], np.ones((T, 2)) * [10.0, 1.0], goal=goal, ct=1.0 / 0.05 / T, W=np.ones(7))[0]
+        assert record("cfg3_update_cost_rel", abs(cost[b] - ref) / max(1.0, ref)) <= TOL
 
 
 def test_full_size_cfg4_humanoid(oracle_lib):

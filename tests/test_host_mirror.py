@@ -392,6 +392,32 @@ def test_cfg3_through_the_product_loader_at_full_size(oracle_lib):
         assert prob.last_kernel() == "exo_chain_kernel"  # the JointLimit block keeps cfg3 on the per-lane store kernel
         phi_ref, jac_ref = orc.problem_update_batch(X[sel], T=T)
         assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+    # Update + GetCost of every trajectory in one call (what bench.py's multi-GPU cfg3 step runs): the generated kernel with the cost
+    # epilogue for the kernel-native layout, update + cost kernels otherwise; costs against problem.cost_batch and the oracle
+    from exotica_b200 import _capi
+    E, N, LP, LJ = B * T, 7, prob.length_Phi, prob.length_jacobian
+    ref_cost = prob.cost_batch(X.reshape(B, T, N))
+    for layout, kernel in ((exo.LAYOUT_SOA, "exo_tree_update_cost_kernel"), (exo.LAYOUT_AOS_ROWMAJOR, "exo_cost_kernel")):
+        dx, dphi, djac, dct = (_capi.DeviceBuffer(n) for n in (E * N, E * LP, E * LJ * N, B))
+        dx.upload(X.T if layout == exo.LAYOUT_SOA else X)
+        prob.update_cost_batch_device(dx.ptr, B, dphi.ptr, djac.ptr, dct.ptr, layout=layout)
+        _capi.check(_capi.lib().exo_device_synchronize())
+        assert prob.last_kernel() == kernel
+        cost = dct.download((B,))
+        assert np.max(np.abs(cost - ref_cost)) <= 1e-12 * max(1.0, ref_cost.max())
+        s0 = 1234 * T
+        if layout == exo.LAYOUT_SOA:
+            phi = np.stack([dphi.download((T,), offset=k * E + s0) for k in range(LP)], axis=1)
+            jac = np.stack([djac.download((T,), offset=k * E + s0) for k in range(LJ * N)], axis=1).reshape(T, LJ, N)
+        else:
+            phi, jac = dphi.download((T, LP), offset=s0 * LP), djac.download((T, LJ, N), offset=s0 * LJ * N)
+        phi_ref, jac_ref = orc.problem_update_batch(X[s0:s0 + T], T=T)
+        assert max_abs_err(phi, phi_ref, angle_entries(maps, orc)) <= 1e-10 and max_abs_err(jac, jac_ref) <= 1e-10
+        for b in (dx, dphi, djac, dct):
+            b.free()
+    for b in (0, 1234, B - 1):
+        ref = orc.trajectory_cost(X[b * T:(b + 1) * T], [1.0, 1.0], ct=1.0 / 0.05 / T, W=np.ones(N))[0]
+        assert abs(ref_cost[b] - ref) <= 1e-10 * max(1.0, ref)
 
 
 @pytest.mark.gpu

@@ -20,6 +20,7 @@ solver = exo.IKSolver({"MaxIterations": int(sys.argv[1]) if len(sys.argv) > 1 el
 solver.specify_problem(prob)
 Q0 = np.random.default_rng(7).uniform(lim[:, 0], lim[:, 1], size=(1 << 16, prob.N))
 solver.solve_batch(Q0)
-t0 = time.perf_counter()
-Q, cost, it, term = solver.solve_batch(Q0)
-print("IK %.2f ms, mean iterations %.1f" % ((time.perf_counter() - t0) * 1e3, it.mean()))
+for rep in range(int(os.environ.get("IK_PROBE_REPS", "1"))):
+    t0 = time.perf_counter()
+    Q, cost, it, term = solver.solve_batch(Q0)
+    print("IK %.2f ms, mean iterations %.1f, kernel %s" % ((time.perf_counter() - t0) * 1e3, it.mean(), prob.last_kernel()))
