@@ -122,8 +122,9 @@ int cuda_fail(cudaError_t e, const char* what)
 // all-gather, measured inside the step's CUDA graph) is then most of a 60 us step.  Every rank owns a WINDOW in its own HBM --
 // two message buffers [parity][rank][WIN_SLOT] and one flag per rank -- exported with cudaIpcGetMemHandle and mapped by every
 // peer (NVLink / NVSwitch peer access).  One kernel per collective: the rank stores its message into every peer's window over
-// NVLink, fences, raises its flag in every peer's window with the collective's sequence number, waits for all flags in its own
-// window, and copies / reduces the gathered slots into the caller's buffer.  No NCCL call, no proxy thread, capturable in a CUDA
+// NVLink -- by default as 16-byte cells that carry their own flags (ll_store below: 512-double all-gather 3.7 us at two GPUs, 8.7 us
+// at eight); with EXO_COMM_LL=0 as plain doubles followed by a fence and a flag store per peer (7.4 / 11.7 us) --, waits until every
+// peer's message is complete in its own window, and copies / reduces the gathered slots into the caller's buffer.  No NCCL call, no proxy thread, capturable in a CUDA
 // graph (the sequence number lives in device memory).  Two parities: a rank can run at most one collective ahead of the slowest
 // peer, which may still be reading the previous one.
 constexpr int WIN_SLOT = 8192;   // doubles per rank and message (64 KB): larger messages go through NCCL
@@ -135,12 +136,45 @@ struct Window
     unsigned long long* flag;    // [WIN_MAXW] sequence number of the last message of every rank that has fully arrived here
     unsigned long long* seq;     // [1] collectives issued by this rank (device-side so that graph replays advance it)
     int* error;                  // [1] set when a peer did not show up within the spin limit
+    uint4* ll;                   // [2][world][WIN_SLOT] flag-in-payload cells {value lo, tag, value hi, tag} (see ll_store)
 };
 struct PeerTable
 {
     double* buf[WIN_MAXW];
     unsigned long long* flag[WIN_MAXW];
+    uint4* ll[WIN_MAXW];
 };
+
+// Flag-in-payload exchange (the default; EXO_COMM_LL=0 restores store + fence + flag): every double travels as one 16-byte store
+// {low word, tag, high word, tag} whose tag is derived from the collective's sequence number.  NVLink delivers at least 8 bytes
+// atomically, so a cell whose two tags match the expected one holds both halves of the value: the receiver polls the cells of its own
+// window and needs neither the sender's system-scope fence (a round trip over NVLink) nor a separate flag store behind it -- the
+// message is complete one one-way latency after it was written.  Tags never repeat within 2^32 - 1 collectives and are never 0 (the
+// window starts zeroed); the two parities keep a cell from being overwritten while its previous value may still be read.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const uint4* p, unsigned tag, int* error)
+{
+    const long long t0 = clock64();
+    for (;;)
+    {
+        unsigned a, b, c, d;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+        if (b == tag && d == tag) return __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+        if (clock64() - t0 > 600000000000ll)  // minutes: a dead peer (ranks may legitimately be seconds apart on the host)
+        {
+            *error = 1;
+            return 0.0;
+        }
+    }
+}
+__device__ __forceinline__ unsigned ll_tag(unsigned long long seq)
+{
+    return (unsigned)(seq % 0xFFFFFFFFull) + 1u;
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
@@ -154,8 +188,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 // op < 0: all-gather into recv[world][recv_stride]; op = EXO_REDUCE_*: all-reduce into recv[count]
-__global__ void __launch_bounds__(512) exo_peer_collective_kernel(Window w, PeerTable peers, const double* __restrict__ send, double* __restrict__ recv, int count,
-                                                                   int64_t recv_stride, int rank, int world, int op)
+__global__ void __launch_bounds__(512) exo_peer_collective_kernel(Window w, PeerTable peers, const double* send, double* recv, int count, int64_t recv_stride,
+                                                                   int rank, int world, int op, int ll)
 {
     __shared__ unsigned long long s_seq;
     const int tid = threadIdx.x;
@@ -163,6 +197,39 @@ __global__ void __launch_bounds__(512) exo_peer_collective_kernel(Window w, Peer
     __syncthreads();
     const unsigned long long seq = s_seq;
     const size_t slot = ((size_t)(seq & 1) * world + rank) * WIN_SLOT;
+    if (ll)
+    {
+        const unsigned tag = ll_tag(seq);
+        for (int k = tid; k < world * count; k += blockDim.x)
+        {
+            const int p = k % world, i = k / world;
+            ll_store(peers.ll[p] + slot + i, send[i], tag);
+        }
+        __syncthreads();  // send may alias recv: all reads of the message precede the first write of the result
+        const uint4* mine = w.ll + (size_t)(seq & 1) * world * WIN_SLOT;
+        if (op < 0)
+        {
+            for (int idx = tid; idx < world * count; idx += blockDim.x)
+            {
+                const int r = idx / count, i = idx - r * count;
+                recv[(int64_t)r * recv_stride + i] = ll_wait(mine + (size_t)r * WIN_SLOT + i, tag, w.error);
+            }
+        }
+        else
+        {
+            for (int i = tid; i < count; i += blockDim.x)
+            {
+                double a = ll_wait(mine + i, tag, w.error);
+                for (int r = 1; r < world; ++r)
+                {
+                    const double b = ll_wait(mine + (size_t)r * WIN_SLOT + i, tag, w.error);
+                    a = op == EXO_REDUCE_MIN ? fmin(a, b) : (op == EXO_REDUCE_MAX ? fmax(a, b) : a + b);
+                }
+                recv[i] = a;
+            }
+        }
+        return;
+    }
     // my message into every window (my own included): thread t serves peer t % world, so all NVLink destinations are in flight at once
     for (int k = tid; k < world * count; k += blockDim.x)
     {
@@ -215,7 +282,7 @@ __global__ void __launch_bounds__(512) exo_peer_collective_kernel(Window w, Peer
 // global minimum -- every rank holds every trajectory's value, so no second collective is needed.  Replaces fill + gather + reduce.
 // (The reduction over the timesteps stays a kernel of its own: done by this one CTA it took 215 us for 2048 x 100 evaluations.)
 __global__ void __launch_bounds__(512) exo_peer_min_gather_kernel(Window w, PeerTable peers, const double* traj_in, int n_local, int count, double* recv_all,
-                                                                  double* global_out, int rank, int world)  // traj_in may be a slot of recv_all
+                                                                  double* global_out, int rank, int world, int ll)  // traj_in may be a slot of recv_all
 {
     __shared__ unsigned long long s_seq;
     __shared__ double s_part[16];
@@ -224,33 +291,54 @@ __global__ void __launch_bounds__(512) exo_peer_min_gather_kernel(Window w, Peer
     __syncthreads();
     const unsigned long long seq = s_seq;
     const size_t slot = ((size_t)(seq & 1) * world + rank) * WIN_SLOT;
-    for (int k = tid; k < world * count; k += blockDim.x)
-    {
-        const int p = k % world, i = k / world;
-        peers.buf[p][slot + i] = i < n_local ? traj_in[i] : INFINITY;
-    }
-    __syncthreads();
-    if (tid < world)
-    {
-        __threadfence_system();
-        st_release_sys(peers.flag[tid] + rank, seq);
-        const long long t0 = clock64();
-        while (ld_acquire_sys(w.flag + tid) < seq)
-            if (clock64() - t0 > 600000000000ll)
-            {
-                *w.error = 1;
-                break;
-            }
-    }
-    __syncthreads();
-    const double* mine = w.buf + (size_t)(seq & 1) * world * WIN_SLOT;
     double g = INFINITY;
-    for (int idx = tid; idx < world * count; idx += blockDim.x)
+    if (ll)
     {
-        const int r = idx / count, i = idx - r * count;
-        const double v = __ldcg(mine + (size_t)r * WIN_SLOT + i);
-        if (recv_all) recv_all[(int64_t)r * count + i] = v;
-        g = fmin(g, v);
+        const unsigned tag = ll_tag(seq);
+        for (int k = tid; k < world * count; k += blockDim.x)
+        {
+            const int p = k % world, i = k / world;
+            ll_store(peers.ll[p] + slot + i, i < n_local ? traj_in[i] : INFINITY, tag);
+        }
+        __syncthreads();  // traj_in may be a slot of recv_all
+        const uint4* mine = w.ll + (size_t)(seq & 1) * world * WIN_SLOT;
+        for (int idx = tid; idx < world * count; idx += blockDim.x)
+        {
+            const int r = idx / count, i = idx - r * count;
+            const double v = ll_wait(mine + (size_t)r * WIN_SLOT + i, tag, w.error);
+            if (recv_all) recv_all[(int64_t)r * count + i] = v;
+            g = fmin(g, v);
+        }
+    }
+    else
+    {
+        for (int k = tid; k < world * count; k += blockDim.x)
+        {
+            const int p = k % world, i = k / world;
+            peers.buf[p][slot + i] = i < n_local ? traj_in[i] : INFINITY;
+        }
+        __syncthreads();
+        if (tid < world)
+        {
+            __threadfence_system();
+            st_release_sys(peers.flag[tid] + rank, seq);
+            const long long t0 = clock64();
+            while (ld_acquire_sys(w.flag + tid) < seq)
+                if (clock64() - t0 > 600000000000ll)
+                {
+                    *w.error = 1;
+                    break;
+                }
+        }
+        __syncthreads();
+        const double* mine = w.buf + (size_t)(seq & 1) * world * WIN_SLOT;
+        for (int idx = tid; idx < world * count; idx += blockDim.x)
+        {
+            const int r = idx / count, i = idx - r * count;
+            const double v = __ldcg(mine + (size_t)r * WIN_SLOT + i);
+            if (recv_all) recv_all[(int64_t)r * count + i] = v;
+            g = fmin(g, v);
+        }
     }
     if (global_out)
     {
@@ -274,6 +362,7 @@ struct exo_comm
     int64_t peer_collectives = 0;
     // peer-memory window (world > 1, every rank could map every other rank's window)
     bool peer_ok = false;
+    bool ll = true;             // flag-in-payload exchange (ll_store) instead of store + fence + flag
     void* d_window = nullptr;
     Window win = {};
     PeerTable peers = {};
@@ -300,7 +389,8 @@ static void peer_window_setup(exo_comm* c)
     const char* env = getenv("EXO_COMM_PEER");
     if (c->world < 2 || c->world > WIN_MAXW || (env && atoi(env) == 0)) return;
     const size_t buf_bytes = (size_t)2 * c->world * WIN_SLOT * sizeof(double);
-    const size_t bytes = buf_bytes + (WIN_MAXW + 2) * sizeof(unsigned long long);
+    const size_t ll_off = buf_bytes + (WIN_MAXW + 2) * sizeof(unsigned long long);  // a multiple of 16
+    const size_t bytes = ll_off + (size_t)2 * c->world * WIN_SLOT * sizeof(uint4);
     struct Wire
     {
         cudaIpcMemHandle_t handle;
@@ -340,6 +430,7 @@ static void peer_window_setup(exo_comm* c)
             }
             c->peers.buf[r] = static_cast<double*>(base);
             c->peers.flag[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + buf_bytes);
+            c->peers.ll[r] = reinterpret_cast<uint4*>(static_cast<char*>(base) + ll_off);
         }
     }
     // every rank mapped every window?  (collective even when this rank failed early: the others are waiting in it)
@@ -359,6 +450,9 @@ static void peer_window_setup(exo_comm* c)
     c->win.flag = reinterpret_cast<unsigned long long*>(base + buf_bytes);
     c->win.seq = c->win.flag + WIN_MAXW;
     c->win.error = reinterpret_cast<int*>(c->win.flag + WIN_MAXW + 1);
+    c->win.ll = reinterpret_cast<uint4*>(base + ll_off);
+    const char* ll_env = getenv("EXO_COMM_LL");
+    c->ll = !(ll_env && atoi(ll_env) == 0);
     c->peer_ok = true;
 }
 
@@ -366,7 +460,7 @@ static void peer_window_setup(exo_comm* c)
 static bool peer_collective(exo_comm* c, const double* d_send, double* d_recv, int64_t count, int64_t recv_stride, int op, cudaStream_t s, cudaError_t& err)
 {
     if (!c->peer_ok || count < 1 || count > WIN_SLOT) return false;
-    exo_peer_collective_kernel<<<1, 512, 0, s>>>(c->win, c->peers, d_send, d_recv, (int)count, recv_stride, c->rank, c->world, op);
+    exo_peer_collective_kernel<<<1, 512, 0, s>>>(c->win, c->peers, d_send, d_recv, (int)count, recv_stride, c->rank, c->world, op, c->ll ? 1 : 0);
     err = cudaGetLastError();
     c->peer_collectives++;
     return true;
@@ -480,7 +574,7 @@ int exo_internal_min_gather(exo_comm* c, const double* d_min_traj_local, int64_t
 {
     if (!c || !c->peer_ok || n_traj_per_rank < 1 || n_traj_per_rank > WIN_SLOT || n_traj_local > n_traj_per_rank) return EXO_ERR_UNSUPPORTED;
     exo_peer_min_gather_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(c->win, c->peers, d_min_traj_local, (int)n_traj_local, (int)n_traj_per_rank, d_min_traj_all,
-                                                                     d_min_global, c->rank, c->world);
+                                                                     d_min_global, c->rank, c->world, c->ll ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     c->peer_collectives++;
     return EXO_OK;
