@@ -98,6 +98,7 @@ def test_errors_use_the_status_and_message_channel(oracle_lib):
     for rc in (L.exo_problem_cost_batch(prob.h, p, p, 1, 0, p, None, None),
                L.exo_problem_cost_jacobian_batch(prob.h, p, p, p, 1, 0, p, None),
                L.exo_problem_cost_gradient_batch(prob.h, p, 1, 0, None, p, None),
+               L.exo_problem_update_cost_batch(prob.h, p, 1, 0, p, p, p, None, None),
                L.exo_problem_aico_task_messages_batch(prob.h, p, p, p, 1, 0, p, p, p, p, None)):
         assert rc != 0 and b"exo_problem_set_cost has not been called" in L.exo_last_error()
     with pytest.raises(_capi.ExoticaError, match="CenterOfMass needs mass"):

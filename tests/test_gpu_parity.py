@@ -663,6 +663,10 @@ def test_end_pose_cost_and_layouts(oracle_lib):
         ref = np.array([orc.trajectory_cost(X[e:e + 1], [2.0, 0.5])[0] for e in range(257)])
         assert np.max(np.abs(cost - ref)) <= 1e-10 * max(1.0, ref.max())
         assert np.array_equal(cost, cost_eval)
+    # an even batch: Update + GetScalarCost in one call takes the generated kernel with the cost epilogue (T = 1, one goal, no W)
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    cost, cost_eval = _gpu_costs(prob, X[:256], 256, 1, [2.0, 0.5])
+    assert np.max(np.abs(cost - ref[:256])) <= 1e-10 * max(1.0, ref.max())
 
 
 def _gpu_cost_gradient(prob, X, B, T, rho, goal=None, ct=1.0, W=None, layout=_capi.LAYOUT_SOA):
