@@ -167,3 +167,32 @@ def test_generated_tree_kernel_source_compiles_without_a_gpu():
     gtree, prob = gpu_problem_from_maps(orc, maps)
     with pytest.raises(_capi.ExoticaError, match="generated tree kernel not applicable"):
         prob.generated_kernel_source()
+
+
+def build_c_consumer(tmp_path):
+    """gcc -std=c99 on tests/c_consumer/consumer.c against include/*.h and the in-tree shared library; returns the binary's path."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "exotica_b200", "lib")
+    exe = str(tmp_path / "consumer")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O2", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_consumer", "consumer.c"), "-o", exe, "-L" + lib_dir, "-lexotica_b200", "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def test_plain_c_consumer_of_the_boundary(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 program with nothing but the two headers and the .so loads the reference's example_ik.xml
+    (Setup::LoadProblem), reads dimensions, task indexing and joint limits -- the host logic, no CUDA call (n_evals = 0)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    examples = os.path.join(root, "tests", "fixtures", "exotica_examples")
+    exe = build_c_consumer(tmp_path)
+    out = subprocess.check_output([exe, "exotica_examples", examples, os.path.join(examples, "resources", "configs", "example_ik.xml"), "0"], text=True).splitlines()
+    assert out[0] == "type exotica/UnconstrainedEndPoseProblem N 7 length_Phi 6 length_jacobian 6 T 1"
+    assert out[1] == "task Position id 0 start 0 length 6 startJ 0 lengthJ 6 used 1"
+    limits = np.array(out[2].split()[1:], dtype=float).reshape(7, 2)
+    assert np.all(limits[:, 0] < 0) and np.allclose(limits[:, 0], -limits[:, 1])
+    # errors reach the C caller through the return code and exo_last_error
+    r = subprocess.run([exe, "exotica_examples", examples, os.path.join(examples, "resources", "configs", "example_ik.xml").replace("example_ik", "nope"), "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "cannot open" in r.stderr

@@ -656,3 +656,29 @@ def test_planar_base_and_mimic_joints_on_the_gpu(oracle_lib, group):
         # the finger's mimic partner moves opposite to grip: d(finger_right)/d(grip) exists only through ... nothing (no column for
         # the mimic element), while d(palm wrt upper)/d(base) vanishes identically
         assert not jac[:, 6:12, 0:3].any()
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_evaluates_a_batch(tmp_path):
+    """tests/c_consumer/consumer.c (C99, the two headers, the .so) loads example_ik.xml and evaluates 4096 configurations from host
+    buffers; the same batch through the Python mirror gives the same numbers."""
+    import subprocess
+    from test_capi_host import build_c_consumer
+    exe = build_c_consumer(tmp_path)
+    xml = os.path.join(EXAMPLES, "resources", "configs", "example_ik.xml")
+    n = 4096
+    out = subprocess.check_output([exe, "exotica_examples", EXAMPLES, xml, str(n)], text=True).splitlines()
+    facts = {l.split()[0]: l.split()[1:] for l in out}
+    assert facts["kernel"][0].startswith("exo_chain") and int(facts["kernel"][4]) == n
+    exo.Setup.set_package_path("exotica_examples", EXAMPLES)
+    prob = exo.Setup.load_problem(xml)
+    lim = prob.get_scene().get_kinematic_tree().get_joint_limits()
+    s, X = 12345, np.empty((n, 7))
+    for e in range(n):
+        for i in range(7):
+            s = (s * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+            X[e, i] = lim[i, 0] + (lim[i, 1] - lim[i, 0]) * ((s >> 11) / 9007199254740992.0)
+    phi, jac = prob.update_batch(X)
+    assert np.array_equal(np.array(facts["last"], dtype=float), phi[-1])
+    sum_phi, sum_j = float(facts["sum_Phi"][0]), float(facts["sum_Phi"][2])  # "sum_Phi <v> sum_J <v>"
+    assert abs(sum_phi - phi.sum()) <= 1e-9 * np.abs(phi).sum() and abs(sum_j - jac.sum()) <= 1e-9 * np.abs(jac).sum()
