@@ -44,7 +44,8 @@ using namespace dev;
 // ALLREV is a bit set: 1 = every joint revolute, 2 = signed-swap link step (dh_link), 4 = 128-register build of the signed-swap
 // kernel (16 instead of 14 warps per SM).  Measured: the extra warps pay where arithmetic bounds the kernel (cfg2b, EffPosition
 // only: 60.5 -> 55.2 us) and cost 1.5-2 us where the store pattern does (cfg2a 86.1 -> 87.6 us, cfg3 76 -> 78.5 us), so the launcher
-// picks bit 4 only for position-only frames.
+// picks bit 4 only for position-only frames.  Denser still does not pay: 112 / 96 registers (18 / 20 warps per SM, 20 / 100 bytes of
+// spills) take cfg2b from 51.7 to 53.5 / 55.8 us.
 #ifndef EXO_CHAIN_DENSE_MAXNREG
 #define EXO_CHAIN_DENSE_MAXNREG 128
 #endif
