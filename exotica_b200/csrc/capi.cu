@@ -1139,9 +1139,24 @@ int exo_problem_set_cost(exo_problem* p, const exo_cost_desc* d)
         }
     }
     if (d->goal) goal.assign(d->goal, d->goal + (size_t)d->T_goal * LP);
+    // a binding that forwards TimeIndexedTask::y hands over one goal per timestep; when they are all the same row (the usual case: one
+    // target for the whole trajectory) the kernels get ONE row, which every lane of a warp reads as a broadcast instead of 32 rows
+    // 8 * length_Phi bytes apart (update + cost 83.8 -> 76.4 us on cfg3)
+    int T_goal = d->T_goal;
+    if (T_goal > 1)
+    {
+        bool same = true;
+        for (int t = 1; t < T_goal && same; ++t) same = memcmp(&goal[(size_t)t * LP], &goal[0], sizeof(double) * (size_t)LP) == 0;
+        if (same)
+        {
+            T_goal = 1;
+            goal.resize((size_t)LP);
+            c.T_goal = 1;
+        }
+    }
     c.n_rot = n_rot;
-    goal_rot.assign((size_t)d->T_goal * n_rot * 9 + 9, 0.0);
-    for (int t = 0; t < d->T_goal; ++t)
+    goal_rot.assign((size_t)T_goal * n_rot * 9 + 9, 0.0);
+    for (int t = 0; t < T_goal; ++t)
     {
         int ri = 0;
         for (int k = 0; k < n_maps; ++k)

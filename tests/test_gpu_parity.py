@@ -652,6 +652,58 @@ def test_trajectory_cost_matches_oracle(oracle_lib, rot):
         assert cost_eval[b * T] == 0.0  # GetCost starts at t = 1
 
 
+@pytest.mark.parametrize("robot", ["lwr", "valkyrie"])
+def test_goal_per_timestep(oracle_lib, robot):
+    """TimeIndexedTask keeps one goal y[t] per timestep (tasks.cpp:166-244); a binding that forwards them pushes goal[T][length_Phi]
+    (exo_cost_desc.T_goal = T).  A target that moves along the trajectory: cost, its gradient (three-kernel path, fused chain kernel /
+    generated tree kernel) and Update + GetCost in one call, all against the oracle; identical rows collapse to one without changing
+    a bit."""
+    if robot == "lwr":
+        orc = _oracle(oracle_lib, "lwr_simplified", "arm")
+        maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "JointLimit", "SafePercentage": 0.1}]
+        stride, lead = 7, 3
+    else:
+        orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
+        maps = [{"type": "EffFrame", "Type": "Quaternion", "EndEffector": [{"Link": "leftPalm"}, {"Link": "rightFoot"}]}, {"type": "JointLimit"}]
+        stride, lead = 7, 3
+    orc.set_problem(maps)
+    N = orc.n
+    B, T = 8, 16
+    E = B * T
+    rng = np.random.default_rng(17)
+    lo, hi = np.maximum(orc.lower, -1.0), np.minimum(orc.upper, 1.0)
+    X = np.clip(rng.uniform(lo, hi, size=(B, 1, N)) + np.cumsum(rng.normal(0, 0.03, size=(B, T, N)), axis=1), lo - 0.05, hi + 0.05)
+    n_frames = len(maps[0]["EndEffector"])
+    goals = np.tile(orc.zero_goal(), (T, 1))
+    for t in range(T):
+        for f in range(n_frames):
+            target = oracle_lib.get_frame([0.4 + 0.01 * t, 0.1 - 0.02 * f, 0.6 - 0.005 * t, 0.3 + 0.02 * t, -0.2, 0.5 - 0.03 * t])
+            goals[t, f * stride:f * stride + lead] = target[9:]
+            goals[t, f * stride + lead:(f + 1) * stride] = oracle_lib.set_rotation(target[:9], "Quaternion")
+    rho = np.ones((T, 2)) * [4.0, 20.0]
+    W = np.linspace(1.0, 2.0, N)
+    ct = 1.0 / 0.05 / T
+    tree, prob = gpu_problem_from_maps(orc, maps)
+    cost, cost_eval = _gpu_costs(prob, X.reshape(E, N), B, T, rho, goal=goals, ct=ct, W=W)  # also runs exo_problem_update_cost_batch
+    grad = _gpu_cost_gradient(prob, X.reshape(E, N), B, T, rho, goal=goals, ct=ct, W=W).reshape(B, T, N)
+    cost_f, grad_f = _gpu_cost_gradient_fused(prob, X.reshape(E, N), B, T)
+    assert prob.last_kernel() == ("exo_chain_costgrad_kernel" if robot == "lwr" else "exo_tree_costgrad_kernel")
+    grad_f = grad_f.reshape(B, T, N)
+    for b in range(B):
+        ref, ref_t = orc.trajectory_cost(X[b], rho, goal=goals, ct=ct, W=W)
+        gref = orc.trajectory_cost_jacobian(X[b], rho, goal=goals, ct=ct, W=W)
+        assert np.max(np.abs(cost_eval[b * T:(b + 1) * T] - ref_t)) <= TOL * max(1.0, np.max(ref_t))
+        assert abs(cost[b] - ref) <= TOL * max(1.0, ref) and abs(cost_f[b] - ref) <= TOL * max(1.0, ref)
+        assert np.max(np.abs(grad[b] - gref)) <= TOL * max(1.0, np.abs(gref).max())
+        assert np.max(np.abs(grad_f[b] - gref)) <= TOL * max(1.0, np.abs(gref).max())
+    # the same goal in every row is stored once: bit-identical results to pushing the single row
+    tree, p1 = gpu_problem_from_maps(orc, maps)
+    tree, pT = gpu_problem_from_maps(orc, maps)
+    c1, e1 = _gpu_costs(p1, X.reshape(E, N), B, T, rho, goal=goals[3], ct=ct, W=W)
+    cT, eT = _gpu_costs(pT, X.reshape(E, N), B, T, rho, goal=np.tile(goals[3], (T, 1)), ct=ct, W=W)
+    assert np.array_equal(c1, cT) and np.array_equal(e1, eT)
+
+
 def test_end_pose_cost_and_layouts(oracle_lib):
     orc = _oracle(oracle_lib, "lwr_simplified", "arm")
     maps = [{"type": "EffPosition", "EndEffector": [{"Link": "lwr_arm_7_link"}]}, {"type": "EffFrame", "EndEffector": [{"Link": "lwr_arm_6_link"}]}]
