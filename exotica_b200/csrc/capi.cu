@@ -2080,13 +2080,15 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         for (int ai = 0; ai < 10; ++ai)
         {
             const double alpha = ai == 0 ? 1.0 : 0.1 - (9 - ai) * ((0.1 - 1.0) / 9.0);  // Eigen::VectorXd::LinSpaced(10, 1.0, 0.1), see ik_alpha()
-            CUDA_TRY(launch_ik_trial(K, alpha, stream));
+            CUDA_TRY(launch_ik_trial(K, alpha, ai == 0, stream));
             rc = launch(p, K.q_trial, E, E, 1, EXO_LAYOUT_SOA, d_phi, nullptr, stream, false);  // prob_->Update(q_tmp): FK only
             if (rc != EXO_OK) return rc;
             CUDA_TRY(launch_ik_accept(K, C, alpha, stream));
         }
         const bool last = it + 1 == prm->max_iterations;
-        const bool poll = last || (it % 4 == 3);
+        // the staged line search is thirty launches per iteration: ask every iteration whether anyone is still active; the fused chain
+        // kernels make an iteration so cheap that every fourth is enough
+        const bool poll = last || !fused_ls || (it % 4 == 3);
         if (poll) CUDA_TRY(cudaMemsetAsync(K.n_active, 0, sizeof(int32_t), stream));
         CUDA_TRY(launch_ik_finish(K, last ? 1 : 0, stream));
         if (poll && !last)

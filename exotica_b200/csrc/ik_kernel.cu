@@ -182,11 +182,14 @@ __global__ void __launch_bounds__(128) exo_ik_step_big_kernel(const __grid_const
 }
 
 // q_trial = q - alpha qd for the configurations still searching; the others keep q (their evaluation is ignored)
-__global__ void __launch_bounds__(128) exo_ik_trial_kernel(const __grid_constant__ IkParams K, double alpha)
+__global__ void __launch_bounds__(128) exo_ik_trial_kernel(const __grid_constant__ IkParams K, double alpha, int first)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= K.n_evals) return;
     const bool search = K.active[e] && !K.ls_done[e];
+    // configurations that are not searching keep q: written with the first step length of a line search, unchanged afterwards (a
+    // configuration that accepts a step copies q_trial into q), so the later step lengths touch the searching ones only
+    if (!search && !first) return;
     for (int c = 0; c < K.n_ctrl; ++c)
     {
         const int64_t i = (int64_t)c * K.n_evals + e;
@@ -255,9 +258,9 @@ cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t 
         exo_ik_step_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, C);
     return cudaGetLastError();
 }
-cudaError_t launch_ik_trial(const IkParams& K, double alpha, cudaStream_t s)
+cudaError_t launch_ik_trial(const IkParams& K, double alpha, bool first, cudaStream_t s)
 {
-    exo_ik_trial_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, alpha);
+    exo_ik_trial_kernel<<<ik_blocks(K.n_evals), 128, 0, s>>>(K, alpha, first ? 1 : 0);
     return cudaGetLastError();
 }
 cudaError_t launch_ik_accept(const IkParams& K, const CostParams& C, double alpha, cudaStream_t s)

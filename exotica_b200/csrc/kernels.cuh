@@ -391,7 +391,7 @@ struct IkParams
 };
 cudaError_t launch_ik_init(const IkParams& K, double lambda0, cudaStream_t s);
 cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);  // K.big_A != NULL: the workspace kernel
-cudaError_t launch_ik_trial(const IkParams& K, double alpha, cudaStream_t s);
+cudaError_t launch_ik_trial(const IkParams& K, double alpha, bool first, cudaStream_t s);  // first: the first step length of a line search
 cudaError_t launch_ik_accept(const IkParams& K, const CostParams& C, double alpha, cudaStream_t s);
 cudaError_t launch_ik_finish(const IkParams& K, int last_iteration, cudaStream_t s);
 
