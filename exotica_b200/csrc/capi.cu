@@ -68,7 +68,7 @@ struct exo_problem
     int64_t shadow_capacity = 0;
     // batched IK workspace (exo_problem_ik_solve_batch)
     double* d_ik = nullptr;     // doubles: phi, jac, q_trial, qd, err_prev, stop, lambda
-    int32_t* d_ik_i = nullptr;  // ints: active, ls_done, n_active
+    int32_t* d_ik_i = nullptr;  // ints: active, ls_done, n_active, n_list, list
     int64_t ik_capacity = 0;
     std::vector<double> cost_rho_t0;  // rho of every map at t = 0 (IK uses end-pose problems)
     std::vector<double> cost_rho;     // host copy of rho[T][n_maps] (eligibility of the fused cost-gradient kernel)
@@ -1979,8 +1979,8 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
         p->d_ik = nullptr;
         p->d_ik_i = nullptr;
         p->ik_capacity = 0;
-        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 4 + (big ? (size_t)LJ * LJ : 0)) * sizeof(double)));
-        CUDA_TRY(cudaMalloc((void**)&p->d_ik_i, ((size_t)2 * E + 4) * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik, (size_t)E * (LP + (size_t)LJ * N + 2 * N + 4) * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->d_ik_i, ((size_t)3 * E + 8) * sizeof(int32_t)));
         p->ik_capacity = E;
     }
     double* w = p->d_ik;
@@ -2003,7 +2003,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     K.stop = w; w += E;
     K.lambda = w; w += E;
     K.steplen = w; w += E;
-    K.big_A = big ? w : nullptr;
+    K.warp_step = big ? 1 : 0;
     K.single_iteration = prm->max_iterations == 1 ? 1 : 0;
     K.max_step = prm->max_step;
     K.th_stepinc = prm->threshold_regularization_increase;
@@ -2014,6 +2014,8 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     K.active = p->d_ik_i;
     K.ls_done = p->d_ik_i + E;
     K.n_active = p->d_ik_i + 2 * E;
+    K.n_list = p->d_ik_i + 2 * E + 4;
+    K.list = p->d_ik_i + 2 * E + 8;
     K.iterations = d_iterations;
     K.termination = d_termination;
     for (size_t i = 0; i < p->maps.size(); ++i)

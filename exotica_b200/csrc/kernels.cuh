@@ -385,12 +385,15 @@ struct IkParams
     int32_t* iterations;  // [E]
     int32_t* termination; // [E]
     int32_t* n_active;    // [1]
-    double* big_A;        // [LJ][LJ][E] workspace of exo_ik_step_big_kernel (A in the lower triangle, its Cholesky factor above it) or NULL
+    int32_t warp_step;    // 1: task spaces beyond the register kernel's (IK_MAXLJ rows, CH_MAXN joints): exo_ik_step_warp_kernel, one warp per configuration
+    int32_t pad_ws;
+    int32_t* list;        // [E] the active configurations, compacted before every step of the warp-per-configuration kernel (order irrelevant)
+    int32_t* n_list;      // [1]
     double row_rho[IK_BIG_MAXLJ];  // rho of the map that owns each Jacobian row (S = diag)
     double w_inv[IK_MAXN];         // 1 / W[c]
 };
 cudaError_t launch_ik_init(const IkParams& K, double lambda0, cudaStream_t s);
-cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);  // K.big_A != NULL: the workspace kernel
+cudaError_t launch_ik_step(const IkParams& K, const CostParams& C, cudaStream_t s);  // K.warp_step: the warp-per-configuration kernel
 cudaError_t launch_ik_trial(const IkParams& K, double alpha, bool first, cudaStream_t s);  // first: the first step length of a line search
 cudaError_t launch_ik_accept(const IkParams& K, const CostParams& C, double alpha, cudaStream_t s);
 cudaError_t launch_ik_finish(const IkParams& K, int last_iteration, cudaStream_t s);
