@@ -1969,7 +1969,7 @@ int exo_problem_ik_solve_batch(exo_problem* p, double* d_q, int64_t n_evals, con
     if (prm->max_iterations < 1) return fail(EXO_ERR_INVALID, "max_iterations must be >= 1");
     const int N = p->prog.hdr.n_ctrl, LP = p->prog.hdr.length_phi, LJ = p->prog.hdr.length_jac;
     if (LJ > IK_BIG_MAXLJ || N > IK_MAXN) return fail(EXO_ERR_UNSUPPORTED, "batched IK supports up to 64 task-space rows and 64 joints");
-    const bool big = LJ > IK_MAXLJ || N > CH_MAXN;  // whole-body problems: the step kernel with its system in a global workspace
+    const bool big = LJ > IK_MAXLJ || N > CH_MAXN;  // whole-body problems: one warp per configuration, the system in shared memory (exo_ik_step_warp_kernel)
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t E = n_evals;
     if (p->ik_capacity < E)

@@ -351,7 +351,7 @@ void host_get_rotation(const double* data, int type, double* out9);
 
 // ---- batched IK step (ik_kernel.cu) ----
 constexpr int IK_MAXLJ = 16;  // rows of the task-space Jacobian the register / local-memory step kernel handles
-constexpr int IK_BIG_MAXLJ = 64;  // ... and the workspace step kernel (whole-body problems: several end-effector frames)
+constexpr int IK_BIG_MAXLJ = 64;  // ... and the warp-per-configuration step kernel (whole-body problems: several end-effector frames)
 constexpr int IK_MAXN = 64;       // controlled joints
 enum
 {
