@@ -1307,7 +1307,8 @@ def test_batched_ik_matches_the_reference_solver(oracle_lib, monkeypatch):
 def test_batched_ik_whole_body(oracle_lib):
     """IKSolver::Solve on the 38-DoF humanoid with four end-effector frames (24 task rows: the step kernel that gives every active
     configuration a warp and keeps its 24 x 24 system in shared memory) and a JointLimit map without weight, from perturbed start states: the reference's path per start state where
-    it converges -- iteration counts, termination criteria, solutions."""
+    it converges -- iteration counts, termination criteria, solutions.  With the JointLimit rows the system is 62 x 62: more rows than a
+    warp has lanes (the factorisation's row loop wraps), close to the 64-row limit."""
     orc = _oracle(oracle_lib, "valkyrie_sim", "whole_body")
     maps = [{"type": "EffFrame", "EndEffector": [{"Link": l} for l in ("leftFoot", "rightFoot", "leftPalm", "rightPalm")]}, {"type": "JointLimit"}]
     orc.set_problem(maps)
