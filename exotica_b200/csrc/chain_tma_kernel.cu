@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(TILE) __maxnreg__(TILE == 64 ? EXO_CHAIN_TMA_M
     const char* xe = reinterpret_cast<const char*>(P.x) + e * P.x_se_b;
     double q[NJ];
 #pragma unroll
-    // joint values are read once: streaming loads (evict-first in L2, which is full of the outputs' dirty lines): 82.3 -> 81.8 us on cfg2a
+    // joint values are read once: streaming loads (evict-first in L2, which is full of the outputs' dirty lines): 82.3 -> 81.8 us on cfg2a.
+    // Not in exo_chain_kernel: its JointLimit prefix reads the state a second time (cfg3 67.7 -> 72.1 us with streaming loads there).
     for (int j = 0; j < NJ; ++j) q[j] = __ldcs(reinterpret_cast<const double*>(xe + P.joint[j].x_byte_off));
     // as in exo_chain_kernel: pull the joint values of a CTA most of a resident generation behind this one into L2
     if (e + P.prefetch_ahead < P.n_evals)
